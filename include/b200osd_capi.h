@@ -1,0 +1,161 @@
+/*
+ * b200osd_capi.h -- the C ABI of the B200-native Osd evaluator (libb200osd.so).
+ *
+ * This is the ONLY boundary between host code (C++ wrapper classes in include/b200osd/, the Python
+ * mirror in opensubdiv_b200/, or a third-party binding) and the hand-written sm_100a kernels.  It
+ * plays the role the three `extern "C"` launchers play in the reference CUDA backend:
+ *
+ *   reference (OpenSubdiv 3.6.0, paths relative to opensubdiv/)            replaced by
+ *   ---------------------------------------------------------------------  -----------------------------------
+ *   CudaEvalStencils               osd/cudaEvaluator.cpp:33-44,            b200osd_eval_stencils
+ *                                  osd/cudaKernel.cu:351-383               b200osd_stencil_table_eval (fast path)
+ *   CudaEvalPatches                osd/cudaEvaluator.cpp:46-53,            b200osd_eval_patches  (nOut = 1)
+ *                                  osd/cudaKernel.cu:387-400
+ *   CudaEvalPatchesWithDerivatives osd/cudaEvaluator.cpp:55-67,            b200osd_eval_patches  (nOut = 3 or 6)
+ *                                  osd/cudaKernel.cu:402-424
+ *   CudaStencilTable ctor/dtor     osd/cudaEvaluator.cpp:100-145           b200osd_stencil_table_create/_destroy
+ *   CudaPatchTable::allocate       osd/cudaPatchTable.cpp:69-162           b200osd_patch_table_create/_set/_destroy
+ *   CudaVertexBuffer               osd/cudaVertexBuffer.cpp:35-93          b200osd_vertex_buffer_*
+ *   CudaEvaluator::Synchronize     osd/cudaEvaluator.cpp:377-380           b200osd_synchronize
+ *
+ * Conventions
+ *  - Plain C: pointers, ints, no C++ or torch types.  All `float*`/`int*` data arguments of the
+ *    eval functions are DEVICE pointers (anything cudaMalloc-compatible, e.g. a torch tensor's
+ *    data_ptr()); `*_create`, `*_update` and `*_read` take HOST pointers and copy.
+ *  - Descriptors are int[3] = {offset, length, stride} in floats (Osd::BufferDescriptor,
+ *    osd/bufferDescriptor.h:61-104).  Unlike the reference C launchers the descriptor offset is
+ *    applied INSIDE this library (pass the un-offset base pointer).
+ *  - nOut is 1 (value), 3 (value, du, dv) or 6 (value, du, dv, duu, duv, dvv).  A NULL entry of
+ *    dsts[] skips that output (osd/cudaKernel.cu:300-327); dsts[0] == NULL with nOut == 1 is an error.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, as the reference uses).
+ *    Launches are asynchronous; call b200osd_synchronize before reading results on the host.
+ *  - Return value: B200OSD_OK, or an error code; B200OSD_ERR_INVALID corresponds to the reference
+ *    evaluators returning `false` (length mismatch / NULL src or dst, osd/cpuEvaluator.cpp:46-47,
+ *    :165-176).  b200osd_last_error() gives a thread-local message.
+ *  - Stencil row addressing is absolute: row i of [start,end) is written to element i of each dst
+ *    (the CUDA backend's convention, osd/cudaKernel.cu:85-98); end <= start is a successful no-op.
+ *  - There is NO CPU fallback: every entry point that computes fails with B200OSD_ERR_CUDA when no
+ *    usable sm_100 device is present.
+ */
+#ifndef B200OSD_CAPI_H
+#define B200OSD_CAPI_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B200OSD_API
+#else
+#define B200OSD_API __attribute__((visibility("default")))
+#endif
+
+enum {
+    B200OSD_OK = 0,
+    B200OSD_ERR_INVALID = 1,   /* the reference evaluator would return false */
+    B200OSD_ERR_CUDA = 2,      /* CUDA runtime / launch failure, or no device */
+    B200OSD_ERR_ALLOC = 3,     /* host or device allocation failed (reference: Create() returns NULL) */
+    B200OSD_ERR_UNSUPPORTED = 4
+};
+
+/* POD mirrors of the Osd value types (layouts verified by static_assert in the C++ wrappers). */
+typedef struct b200osd_patch_coord { int arrayIndex, patchIndex, vertIndex; float s, t; } b200osd_patch_coord;      /* osd/types.h:42-64   */
+typedef struct b200osd_patch_array { int regDesc, desc, numPatches, indexBase, stride, primitiveIdBase; } b200osd_patch_array; /* osd/types.h:66-122 */
+typedef struct b200osd_patch_param { unsigned int field0, field1; float sharpness; } b200osd_patch_param;           /* osd/types.h:127-130 */
+
+typedef struct b200osd_stencil_table b200osd_stencil_table;
+typedef struct b200osd_patch_table   b200osd_patch_table;
+typedef struct b200osd_vertex_buffer b200osd_vertex_buffer;
+
+/* ---- library -------------------------------------------------------------------------------- */
+B200OSD_API const char *b200osd_version(void);
+B200OSD_API const char *b200osd_last_error(void);
+/* Number of kernels this library has launched since load (or the last reset) -- bench.py's gpu_launches. */
+B200OSD_API long long   b200osd_launch_count(void);
+B200OSD_API void        b200osd_reset_launch_count(void);
+B200OSD_API int         b200osd_synchronize(void *stream);   /* NULL: cudaDeviceSynchronize (CudaEvaluator::Synchronize) */
+
+/* ---- vertex buffer (CudaVertexBuffer, osd/cudaVertexBuffer.h:42-80) -------------------------- */
+B200OSD_API b200osd_vertex_buffer *b200osd_vertex_buffer_create(int numElements, int numVertices);
+B200OSD_API void   b200osd_vertex_buffer_destroy(b200osd_vertex_buffer *vb);
+B200OSD_API int    b200osd_vertex_buffer_num_elements(const b200osd_vertex_buffer *vb);
+B200OSD_API int    b200osd_vertex_buffer_num_vertices(const b200osd_vertex_buffer *vb);
+B200OSD_API float *b200osd_vertex_buffer_bind(b200osd_vertex_buffer *vb);     /* BindCudaBuffer(): device pointer */
+/* UpdateData(src,startVertex,numVertices): host -> device.  stream == NULL: blocking cudaMemcpy like the
+ * reference (cudaVertexBuffer.cpp:56-64); otherwise cudaMemcpyAsync on that stream (pin hostSrc for overlap). */
+B200OSD_API int    b200osd_vertex_buffer_update(b200osd_vertex_buffer *vb, const float *hostSrc,
+                                                int startVertex, int numVertices, void *stream);
+/* device -> host read-back of a vertex range (what clients do after Synchronize()). */
+B200OSD_API int    b200osd_vertex_buffer_read(b200osd_vertex_buffer *vb, float *hostDst,
+                                              int startVertex, int numVertices, void *stream);
+
+/* ---- stencil table (CudaStencilTable, osd/cudaEvaluator.h:52-92) ------------------------------
+ * Host arrays in Far::StencilTable / Far::LimitStencilTable layout (far/stencilTable.h:156-186,434-456):
+ * sizes[n], offsets[n], indices[ne], weights[ne] and optional derivative weights (NULL = absent).
+ * The table keeps (a) verbatim device copies (the Get*Buffer() pointers of the reference class) and
+ * (b) a B200-specific bucketed copy (rows sorted by size inside windows, 32-row slices stored
+ * element-major for coalesced 128-bit loads) used by b200osd_stencil_table_eval.
+ * flags: bit 0 = skip the bucketed copy (verbatim only).                                         */
+B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
+        int numStencils, const int *sizes, const int *offsets, const int *indices, const float *weights,
+        const float *duWeights, const float *dvWeights,
+        const float *duuWeights, const float *duvWeights, const float *dvvWeights, int flags);
+B200OSD_API void b200osd_stencil_table_destroy(b200osd_stencil_table *t);
+B200OSD_API int  b200osd_stencil_table_num_stencils(const b200osd_stencil_table *t);
+B200OSD_API int  b200osd_stencil_table_num_control_vertices(const b200osd_stencil_table *t); /* 1 + max index */
+B200OSD_API long long b200osd_stencil_table_num_elements(const b200osd_stencil_table *t);
+/* which: 0 sizes, 1 offsets, 2 indices, 3 weights, 4 du, 5 dv, 6 duu, 7 duv, 8 dvv -> device pointer or NULL */
+B200OSD_API const void *b200osd_stencil_table_buffer(const b200osd_stencil_table *t, int which);
+/* bytes of the bucketed device copy actually streamed per full evaluation with nOut weight streams */
+B200OSD_API long long b200osd_stencil_table_stream_bytes(const b200osd_stencil_table *t, int nOut);
+
+/* EvalStencils through the table's bucketed layout (fast path). */
+B200OSD_API int b200osd_stencil_table_eval(const b200osd_stencil_table *t,
+        const float *src, const int srcDesc[3],
+        int nOut, float *const dsts[], const int dstDescs[][3],
+        int start, int end, void *stream);
+
+/* EvalStencils on plain reference-layout DEVICE arrays (raw CudaEvaluator::EvalStencils overloads,
+ * osd/cudaEvaluator.h:171-178,284-295,449-466).  weights[k] for k < nOut. */
+B200OSD_API int b200osd_eval_stencils(
+        const float *src, const int srcDesc[3],
+        int nOut, float *const dsts[], const int dstDescs[][3],
+        const int *sizes, const int *offsets, const int *indices, const float *const weights[],
+        int start, int end, void *stream);
+
+/* ---- patch table (CudaPatchTable, osd/cudaPatchTable.h:51-112) --------------------------------
+ * A patch table is a set of (PatchArray[], index buffer, PatchParam[]) triples as flattened by
+ * Osd::CpuPatchTable (osd/cpuPatchTable.cpp:35-156): which = 0 vertex, 1 varying (params shared with
+ * vertex: pass NULL/0), 2+c face-varying channel c.                                               */
+B200OSD_API b200osd_patch_table *b200osd_patch_table_create(int numFVarChannels);
+B200OSD_API void b200osd_patch_table_destroy(b200osd_patch_table *t);
+B200OSD_API int  b200osd_patch_table_set(b200osd_patch_table *t, int which,
+        int numArrays, const b200osd_patch_array *arrays,
+        int numIndices, const int *indices,
+        int numParams, const b200osd_patch_param *params);
+B200OSD_API int  b200osd_patch_table_num_fvar_channels(const b200osd_patch_table *t);
+/* kind: 0 PatchArray buffer, 1 index buffer, 2 PatchParam buffer -> device pointer or NULL */
+B200OSD_API const void *b200osd_patch_table_buffer(const b200osd_patch_table *t, int which, int kind);
+B200OSD_API int  b200osd_patch_table_count(const b200osd_patch_table *t, int which, int kind);
+
+/* EvalPatches / EvalPatchesVarying / EvalPatchesFaceVarying on DEVICE arrays (raw overloads,
+ * osd/cudaEvaluator.h:706-713,752-761,815-827): the caller picks the triple, exactly like the
+ * reference templates do (cudaEvaluator.h:502-523, 857-878, 1068-1090). */
+B200OSD_API int b200osd_eval_patches(
+        const float *src, const int srcDesc[3],
+        int nOut, float *const dsts[], const int dstDescs[][3],
+        int numPatchCoords, const b200osd_patch_coord *patchCoords,
+        const b200osd_patch_array *patchArrays, const int *patchIndices,
+        const b200osd_patch_param *patchParams, void *stream);
+
+/* ---- tuning / introspection (used by bench.py and the tests; not needed by clients) ---------- */
+/* Selects the stencil kernel variant used by b200osd_stencil_table_eval: 0 = auto. */
+B200OSD_API void b200osd_set_stencil_variant(int variant);
+B200OSD_API int  b200osd_get_stencil_variant(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200OSD_CAPI_H */

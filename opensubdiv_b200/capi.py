@@ -1,0 +1,101 @@
+"""ctypes binding of libb200osd.so -- the C ABI declared in include/b200osd_capi.h.
+
+There is no CPU fallback: if the library has not been built this module raises at load time, and
+every compute entry point returns an error code when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200osd.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+
+# every symbol include/b200osd_capi.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "b200osd_version", "b200osd_last_error", "b200osd_launch_count", "b200osd_reset_launch_count",
+    "b200osd_synchronize",
+    "b200osd_vertex_buffer_create", "b200osd_vertex_buffer_destroy", "b200osd_vertex_buffer_num_elements",
+    "b200osd_vertex_buffer_num_vertices", "b200osd_vertex_buffer_bind", "b200osd_vertex_buffer_update",
+    "b200osd_vertex_buffer_read",
+    "b200osd_stencil_table_create", "b200osd_stencil_table_destroy", "b200osd_stencil_table_num_stencils",
+    "b200osd_stencil_table_num_control_vertices", "b200osd_stencil_table_num_elements",
+    "b200osd_stencil_table_buffer", "b200osd_stencil_table_stream_bytes", "b200osd_stencil_table_eval",
+    "b200osd_eval_stencils",
+    "b200osd_patch_table_create", "b200osd_patch_table_destroy", "b200osd_patch_table_set",
+    "b200osd_patch_table_num_fvar_channels", "b200osd_patch_table_buffer", "b200osd_patch_table_count",
+    "b200osd_eval_patches",
+    "b200osd_set_stencil_variant", "b200osd_get_stencil_variant",
+]
+
+
+class B200OsdError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200OsdError(
+            f"{LIB_PATH} is missing: build it with `python -m opensubdiv_b200._build` "
+            "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i, ll = C.c_void_p, C.c_int, C.c_longlong
+    L.b200osd_version.restype = C.c_char_p
+    L.b200osd_last_error.restype = C.c_char_p
+    L.b200osd_launch_count.restype = ll
+    L.b200osd_synchronize.argtypes = [vp]
+    L.b200osd_vertex_buffer_create.restype = vp
+    L.b200osd_vertex_buffer_create.argtypes = [i, i]
+    L.b200osd_vertex_buffer_destroy.argtypes = [vp]
+    L.b200osd_vertex_buffer_num_elements.argtypes = [vp]
+    L.b200osd_vertex_buffer_num_vertices.argtypes = [vp]
+    L.b200osd_vertex_buffer_bind.restype = vp
+    L.b200osd_vertex_buffer_bind.argtypes = [vp]
+    L.b200osd_vertex_buffer_update.argtypes = [vp, vp, i, i, vp]
+    L.b200osd_vertex_buffer_read.argtypes = [vp, vp, i, i, vp]
+    L.b200osd_stencil_table_create.restype = vp
+    L.b200osd_stencil_table_create.argtypes = [i] + [vp] * 9 + [i]
+    L.b200osd_stencil_table_destroy.argtypes = [vp]
+    L.b200osd_stencil_table_num_stencils.argtypes = [vp]
+    L.b200osd_stencil_table_num_control_vertices.argtypes = [vp]
+    L.b200osd_stencil_table_num_elements.argtypes = [vp]
+    L.b200osd_stencil_table_num_elements.restype = ll
+    L.b200osd_stencil_table_buffer.restype = vp
+    L.b200osd_stencil_table_buffer.argtypes = [vp, i]
+    L.b200osd_stencil_table_stream_bytes.restype = ll
+    L.b200osd_stencil_table_stream_bytes.argtypes = [vp, i]
+    L.b200osd_stencil_table_eval.argtypes = [vp, vp, vp, i, vp, vp, i, i, vp]
+    L.b200osd_eval_stencils.argtypes = [vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, vp]
+    L.b200osd_patch_table_create.restype = vp
+    L.b200osd_patch_table_create.argtypes = [i]
+    L.b200osd_patch_table_destroy.argtypes = [vp]
+    L.b200osd_patch_table_set.argtypes = [vp, i, i, vp, i, vp, i, vp]
+    L.b200osd_patch_table_num_fvar_channels.argtypes = [vp]
+    L.b200osd_patch_table_buffer.restype = vp
+    L.b200osd_patch_table_buffer.argtypes = [vp, i, i]
+    L.b200osd_patch_table_count.argtypes = [vp, i, i]
+    L.b200osd_eval_patches.argtypes = [vp, vp, i, vp, vp, i, vp, vp, vp, vp, vp]
+    L.b200osd_set_stencil_variant.argtypes = [i]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().b200osd_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str) -> bool:
+    """OK -> True; ERR_INVALID -> False (the reference evaluators' `return false`); anything else raises."""
+    if rc == OK:
+        return True
+    if rc == ERR_INVALID:
+        return False
+    raise B200OsdError(f"{what} failed (code {rc}): {last_error()}")

@@ -1,0 +1,213 @@
+// patch.cu -- host side of the limit-evaluation path: argument validation mirroring the reference
+// evaluator, component tiling, kernel dispatch, and the device patch-table container.
+//
+// Reference behaviour mirrored (paths relative to /root/reference/opensubdiv):
+//   osd/cpuEvaluator.cpp:165-176,224-241,300-331  src NULL -> false; value-only form with dst NULL -> false;
+//                                                 a non-NULL output whose length != srcDesc.length -> false
+//   osd/cudaKernel.cu:300-327                     NULL derivative outputs are skipped
+//   osd/cudaPatchTable.cpp:69-162                 device copies of PatchArray[], indices, PatchParam[] (+varying, fvar)
+#include "patch_kernels.cuh"
+
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+using namespace b200osd;
+
+namespace {
+
+// Quartic box-spline basis of the regular Loop patch: 12 bivariate quartics, coefficients x12 on the monomials
+//   1 s t s^2 st t^2 s^3 s^2t st^2 t^3 s^4 s^3t s^2t^2 st^3 t^4     (osd/patchBasis.h:557-572 in expanded form)
+const signed char kBox12[12][15] = {
+    { 1, -2, -4, 0, 6, 6, 2, 0, -6, -4, -1, -2, 0, 2, 1 },
+    { 1, 2, -2, 0, -6, 0, -4, 0, 6, 2, 2, 4, 0, -2, -1 },
+    { 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, -1, -2, 0, 0, 0 },
+    { 1, -4, -2, 6, 6, 0, -4, -6, 0, 2, 1, 2, 0, -2, -1 },
+    { 6, 0, 0, -12, -12, -12, 8, 12, 12, 8, -1, -2, 0, -2, -1 },
+    { 1, 4, 2, 6, 6, 0, -4, -6, -12, -4, -1, -2, 0, 4, 2 },
+    { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 0, 0, 0 },
+    { 1, -2, 2, 0, -6, 0, 2, 6, 0, -4, -1, -2, 0, 4, 2 },
+    { 1, 2, 4, 0, 6, 6, -4, -12, -6, -4, 2, 4, 0, -2, -1 },
+    { 0, 0, 0, 0, 0, 0, 2, 6, 6, 2, -1, -2, 0, -2, -1 },
+    { 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, -2, -1 },
+    { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 1 },
+};
+const signed char kMonoA[15] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 4, 3, 2, 1, 0 };
+const signed char kMonoB[15] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4 };
+
+std::once_flag g_box_once;
+int g_box_rc = B200OSD_OK;
+int g_box_device = -1;
+
+// The derivative tables are obtained by differentiating kBox12 monomial by monomial.
+int upload_box_tables() {
+    static const int das[6] = { 0, 1, 0, 2, 1, 0 }, dbs[6] = { 0, 0, 1, 0, 1, 2 };
+    static const int divisor[6] = { 1, 2, 2, 12, 6, 12 };
+    signed char tab[6][12][15];
+    std::memset(tab, 0, sizeof(tab));
+    for (int k = 0; k < 6; ++k)
+        for (int i = 0; i < 12; ++i)
+            for (int m = 0; m < 15; ++m) {
+                int a = kMonoA[m], b = kMonoB[m], c = kBox12[i][m];
+                if (c == 0 || a < das[k] || b < dbs[k]) continue;
+                for (int q = 0; q < das[k]; ++q) c *= (a - q);
+                for (int q = 0; q < dbs[k]; ++q) c *= (b - q);
+                int n = -1;
+                for (int mm = 0; mm < 15; ++mm)
+                    if (kMonoA[mm] == a - das[k] && kMonoB[mm] == b - dbs[k]) n = mm;
+                tab[k][i][n] += (signed char)(c / divisor[k]);
+            }
+    const float scale[6] = { 1.0f / 12.0f, 1.0f / 6.0f, 1.0f / 6.0f, 1.0f, 0.5f, 1.0f };
+    B200_CUDA_TRY(cudaMemcpyToSymbol(g_box_tab, tab, sizeof(tab)));
+    B200_CUDA_TRY(cudaMemcpyToSymbol(g_box_scale, scale, sizeof(scale)));
+    return B200OSD_OK;
+}
+
+int ensure_box_tables() {
+    // __constant__ symbols are per device: (re)upload when the current device changes.
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev != g_box_device) {
+        int rc = upload_box_tables();
+        if (rc) return rc;
+        g_box_device = dev;
+    }
+    return B200OSD_OK;
+}
+
+template <int ORDER>
+int launch_patches(const PatchIO &io, int LT, cudaStream_t st) {
+    const int block = 128;
+    const int grid = (io.n + block - 1) / block;
+    switch (LT) {
+        case 1: patch_kernel<1, ORDER><<<grid, block, 0, st>>>(io); break;
+        case 2: patch_kernel<2, ORDER><<<grid, block, 0, st>>>(io); break;
+        case 3: patch_kernel<3, ORDER><<<grid, block, 0, st>>>(io); break;
+        default: patch_kernel<4, ORDER><<<grid, block, 0, st>>>(io); break;
+    }
+    return check_launch("patch_kernel");
+}
+
+}  // namespace
+
+struct b200osd_patch_table {
+    struct Triple {
+        b200osd_patch_array *arrays = nullptr;
+        int *indices = nullptr;
+        b200osd_patch_param *params = nullptr;
+        int nArrays = 0, nIndices = 0, nParams = 0;
+    };
+    std::vector<Triple> triples;   // 0 vertex, 1 varying, 2+c fvar channel c
+    int numFVar = 0;
+};
+
+static void free_triple(b200osd_patch_table::Triple &tr) {
+    cudaFree(tr.arrays); cudaFree(tr.indices); cudaFree(tr.params);
+    tr = b200osd_patch_table::Triple();
+}
+
+template <typename T>
+static int upload_array(T **d, const T *h, int n) {
+    *d = nullptr;
+    if (n <= 0 || !h) return B200OSD_OK;
+    cudaError_t e = cudaMalloc((void **)d, (size_t)n * sizeof(T));
+    if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); *d = nullptr; return B200OSD_ERR_ALLOC; }
+    e = cudaMemcpy(*d, h, (size_t)n * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(e)); cudaFree(*d); *d = nullptr; return B200OSD_ERR_CUDA; }
+    return B200OSD_OK;
+}
+
+extern "C" {
+
+int b200osd_eval_patches(const float *src, const int srcDesc[3], int nOut, float *const dsts[],
+                         const int dstDescs[][3], int numPatchCoords, const b200osd_patch_coord *patchCoords,
+                         const b200osd_patch_array *patchArrays, const int *patchIndices,
+                         const b200osd_patch_param *patchParams, void *stream) {
+    if (nOut != 1 && nOut != 3 && nOut != 6) { set_error("nOut must be 1, 3 or 6 (got %d)", nOut); return B200OSD_ERR_INVALID; }
+    if (!src) { set_error("src is NULL"); return B200OSD_ERR_INVALID; }                          // cpuEvaluator.cpp:165-169
+    if (nOut == 1 && !dsts[0]) { set_error("dst is NULL"); return B200OSD_ERR_INVALID; }         // cpuEvaluator.cpp:170-176
+    const int L = srcDesc[1];
+    if (L <= 0) { set_error("srcDesc.length must be positive"); return B200OSD_ERR_INVALID; }
+    for (int k = 0; k < nOut; ++k)
+        if (dsts[k] && dstDescs[k][1] != L) {
+            set_error("output %d length %d != srcDesc.length %d", k, dstDescs[k][1], L);
+            return B200OSD_ERR_INVALID;
+        }
+    if (numPatchCoords <= 0) return B200OSD_OK;
+    if (!patchCoords || !patchArrays || !patchIndices || !patchParams) { set_error("patch table / coords are NULL"); return B200OSD_ERR_INVALID; }
+    int rc = ensure_box_tables();
+    if (rc) return rc;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    // components are evaluated in tiles of at most 4 (xyz, uv, rgba fit in one launch)
+    for (int c0 = 0; c0 < L; c0 += 4) {
+        const int LT = (L - c0) < 4 ? (L - c0) : 4;
+        PatchIO io;
+        io.src = src + srcDesc[0] + c0;
+        io.srcStride = srcDesc[2];
+        for (int k = 0; k < kPatchMaxOut; ++k) { io.dst[k] = nullptr; io.dstStride[k] = 0; }
+        for (int k = 0; k < nOut; ++k)
+            if (dsts[k]) { io.dst[k] = dsts[k] + dstDescs[k][0] + c0; io.dstStride[k] = dstDescs[k][2]; }
+        io.n = numPatchCoords;
+        io.coords = patchCoords;
+        io.arrays = patchArrays;
+        io.indices = patchIndices;
+        io.params = patchParams;
+        rc = nOut == 1 ? launch_patches<0>(io, LT, st) : (nOut == 3 ? launch_patches<1>(io, LT, st) : launch_patches<2>(io, LT, st));
+        if (rc) return rc;
+    }
+    return B200OSD_OK;
+}
+
+// -------------------------------------------------------------------------------- patch table --
+b200osd_patch_table *b200osd_patch_table_create(int numFVarChannels) {
+    if (numFVarChannels < 0) return nullptr;
+    b200osd_patch_table *t = new (std::nothrow) b200osd_patch_table;
+    if (!t) return nullptr;
+    t->numFVar = numFVarChannels;
+    t->triples.resize(2 + numFVarChannels);
+    return t;
+}
+
+
+void b200osd_patch_table_destroy(b200osd_patch_table *t) {
+    if (!t) return;
+    for (auto &tr : t->triples) free_triple(tr);
+    delete t;
+}
+
+int b200osd_patch_table_set(b200osd_patch_table *t, int which, int numArrays, const b200osd_patch_array *arrays,
+                            int numIndices, const int *indices, int numParams, const b200osd_patch_param *params) {
+    if (!t || which < 0 || which >= (int)t->triples.size()) { set_error("patch_table_set: bad table / slot"); return B200OSD_ERR_INVALID; }
+    b200osd_patch_table::Triple &tr = t->triples[which];
+    free_triple(tr);
+    int rc = upload_array(&tr.arrays, arrays, numArrays);
+    if (!rc) rc = upload_array(&tr.indices, indices, numIndices);
+    if (!rc) rc = upload_array(&tr.params, params, numParams);
+    if (rc) { free_triple(tr); return rc; }
+    tr.nArrays = tr.arrays ? numArrays : 0;
+    tr.nIndices = tr.indices ? numIndices : 0;
+    tr.nParams = tr.params ? numParams : 0;
+    return B200OSD_OK;
+}
+
+int b200osd_patch_table_num_fvar_channels(const b200osd_patch_table *t) { return t ? t->numFVar : 0; }
+
+const void *b200osd_patch_table_buffer(const b200osd_patch_table *t, int which, int kind) {
+    if (!t || which < 0 || which >= (int)t->triples.size()) return nullptr;
+    const b200osd_patch_table::Triple &tr = t->triples[which];
+    // the varying triple shares the vertex PatchParams (osd/cudaEvaluator.h:857-878)
+    if (kind == 2 && which == 1 && !tr.params) return t->triples[0].params;
+    return kind == 0 ? (const void *)tr.arrays : (kind == 1 ? (const void *)tr.indices : (const void *)tr.params);
+}
+
+int b200osd_patch_table_count(const b200osd_patch_table *t, int which, int kind) {
+    if (!t || which < 0 || which >= (int)t->triples.size()) return 0;
+    const b200osd_patch_table::Triple &tr = t->triples[which];
+    if (kind == 2 && which == 1 && !tr.params) return t->triples[0].nParams;
+    return kind == 0 ? tr.nArrays : (kind == 1 ? tr.nIndices : tr.nParams);
+}
+
+}  // extern "C"

@@ -1,0 +1,450 @@
+// patch_kernels.cuh -- device code of the limit-evaluation path (EvalPatches*), sm_100a.
+//
+// Semantics restated from the reference (paths relative to /root/reference/opensubdiv):
+//   osd/cpuEvaluator.cpp:157-381   per PatchCoord: array/param lookup, basis weights, gather-sum of control points
+//   osd/patchBasisTypes.h:241-426  patch type ids, PatchParam bit fields, (s,t) normalisation into the sub-patch
+//   osd/patchBasis.h:53-1610       linear / B-spline / Gregory / box-spline / Gregory-triangle bases, boundary
+//                                  folding, derivative scaling (d1 = +-2^depth, d2 = sign*d1*d1)
+//
+// Design (one thread per PatchCoord, everything in registers):
+//   REGULAR (bicubic B-spline, the overwhelmingly common type) is evaluated in SEPARABLE form: the 1-D weight
+//   vectors in s and t (value / 1st / 2nd derivative, boundary-folded and pre-scaled) are kept, each of the 4 rows
+//   of control points is first contracted with the three s-vectors, and the row results are then combined with
+//   the t-vectors.  That is 16*3 + 4*6 = 72 multiply-adds per component instead of the 16*6 = 96 (plus 96
+//   products to form the tensor weights) of the reference formulation; boundary folding is linear in the 1-D
+//   weights so it commutes with the tensor product.  Summation order differs from the reference, see DESIGN.md.
+//   GREGORY_BASIS and QUADS are unrolled per control point with compile-time point tables.
+//   LOOP / GREGORY_TRIANGLE / TRIANGLES use a weight-array formulation (local memory), correct but not tuned.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200osd {
+
+constexpr int kPatchMaxOut = 6;
+
+struct PatchIO {
+    const float *src;                 // already offset by srcDesc.offset (+ component tile offset)
+    int srcStride;
+    float *dst[kPatchMaxOut];         // already offset (+ component tile offset); NULL = skip
+    int dstStride[kPatchMaxOut];
+    int n;
+    const b200osd_patch_coord *coords;
+    const b200osd_patch_array *arrays;
+    const int *indices;
+    const b200osd_patch_param *params;
+};
+
+enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_BASIS = 9, PT_GREGORY_TRIANGLE = 10 };
+
+// Derived box-spline tables (filled once on the host, see patch.cu): g_box_tab[k][i][m], k = value,ds,dt,dss,dst,dtt
+__constant__ signed char g_box_tab[6][12][15];
+__constant__ float g_box_scale[6];
+
+// ---------------------------------------------------------------------------------- 1-D bases --
+template <int ORDER>
+__device__ __forceinline__ void bspline_1d(float t, float (&b)[4], float (&d)[4], float (&dd)[4]) {
+    const float c = 1.0f - t;
+    const float t2 = t * t, c2 = c * c;
+    const float sixth = 1.0f / 6.0f;
+    b[0] = sixth * c2 * c;
+    b[3] = sixth * t2 * t;
+    b[1] = sixth * fmaf(t2, fmaf(3.0f, t, -6.0f), 4.0f);          // (3t^3 - 6t^2 + 4)/6
+    b[2] = sixth * fmaf(c2, fmaf(3.0f, c, -6.0f), 4.0f);          // symmetric: b2(t) = b1(1-t)
+    if (ORDER >= 1) {
+        d[0] = -0.5f * c2;
+        d[3] = 0.5f * t2;
+        d[1] = t * fmaf(1.5f, t, -2.0f);
+        d[2] = -c * fmaf(1.5f, c, -2.0f);
+    }
+    if (ORDER >= 2) {
+        dd[0] = c;
+        dd[1] = fmaf(3.0f, t, -2.0f);
+        dd[2] = fmaf(3.0f, c, -2.0f);
+        dd[3] = t;
+    }
+}
+
+template <int ORDER>
+__device__ __forceinline__ void bezier_1d(float t, float (&b)[4], float (&d)[4], float (&dd)[4]) {
+    const float c = 1.0f - t;
+    const float t2 = t * t, c2 = c * c;
+    b[0] = c2 * c;
+    b[1] = 3.0f * c2 * t;
+    b[2] = 3.0f * t2 * c;
+    b[3] = t2 * t;
+    if (ORDER >= 1) {
+        d[0] = -3.0f * c2;
+        d[1] = 3.0f * c * fmaf(-3.0f, t, 1.0f);                   // 3(1-t)(1-3t)
+        d[2] = 3.0f * t * fmaf(-3.0f, t, 2.0f);                   // 3t(2-3t)
+        d[3] = 3.0f * t2;
+    }
+    if (ORDER >= 2) {
+        dd[0] = 6.0f * c;
+        dd[1] = fmaf(18.0f, t, -12.0f);
+        dd[2] = fmaf(-18.0f, t, 6.0f);
+        dd[3] = 6.0f * t;
+    }
+}
+
+// phantom end point folding of a 1-D weight vector: lo = fold index 0 into 1,2 ; hi = fold index 3 into 2,1
+__device__ __forceinline__ void fold_lo(float (&w)[4]) { w[2] -= w[0]; w[1] = fmaf(2.0f, w[0], w[1]); w[0] = 0.0f; }
+__device__ __forceinline__ void fold_hi(float (&w)[4]) { w[1] -= w[3]; w[2] = fmaf(2.0f, w[3], w[2]); w[3] = 0.0f; }
+
+template <int LT>
+__device__ __forceinline__ void load_cv(const float *src, int stride, int idx, float (&v)[LT]) {
+    const float *p = src + (size_t)idx * (size_t)stride;
+#pragma unroll
+    for (int c = 0; c < LT; ++c) v[c] = __ldg(p + c);
+}
+
+template <int LT, int NSETS>
+__device__ __forceinline__ void store_outputs(const PatchIO &io, int i, const float (&out)[NSETS][LT]) {
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k) {
+        float *d = io.dst[k];
+        if (!d) continue;
+        d += (size_t)i * (size_t)io.dstStride[k];
+#pragma unroll
+        for (int c = 0; c < LT; ++c) st_stream_f1(d + c, out[k][c]);
+    }
+}
+
+// -------------------------------------------------------------------------------- REGULAR path --
+template <int LT, int ORDER>
+__device__ __forceinline__ void eval_regular(const PatchIO &io, const int *cvs, float s, float t, int boundary,
+                                             float d1, float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
+    float bs[4], ds[4], dss[4], bt[4], dt[4], dtt[4];
+    bspline_1d<ORDER>(s, bs, ds, dss);
+    bspline_1d<ORDER>(t, bt, dt, dtt);
+    if (boundary) {
+        if (boundary & 1) { fold_lo(bt); if (ORDER >= 1) fold_lo(dt); if (ORDER >= 2) fold_lo(dtt); }
+        if (boundary & 2) { fold_hi(bs); if (ORDER >= 1) fold_hi(ds); if (ORDER >= 2) fold_hi(dss); }
+        if (boundary & 4) { fold_hi(bt); if (ORDER >= 1) fold_hi(dt); if (ORDER >= 2) fold_hi(dtt); }
+        if (boundary & 8) { fold_lo(bs); if (ORDER >= 1) fold_lo(ds); if (ORDER >= 2) fold_lo(dss); }
+    }
+    if (ORDER >= 1) {
+        const float d2 = d1 * d1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ds[j] *= d1; dt[j] *= d1;
+            if (ORDER >= 2) { dss[j] *= d2; dtt[j] *= d2; }
+        }
+    }
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+        for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int id[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) id[j] = __ldg(cvs + 4 * i + j);
+        float r0[LT], r1[LT], r2[LT];
+#pragma unroll
+        for (int c = 0; c < LT; ++c) { r0[c] = 0.0f; r1[c] = 0.0f; r2[c] = 0.0f; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[LT];
+            load_cv<LT>(io.src, io.srcStride, id[j], v);
+#pragma unroll
+            for (int c = 0; c < LT; ++c) {
+                r0[c] = fmaf(bs[j], v[c], r0[c]);
+                if (ORDER >= 1) r1[c] = fmaf(ds[j], v[c], r1[c]);
+                if (ORDER >= 2) r2[c] = fmaf(dss[j], v[c], r2[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < LT; ++c) {
+            out[0][c] = fmaf(bt[i], r0[c], out[0][c]);
+            if (ORDER >= 1) {
+                out[1][c] = fmaf(bt[i], r1[c], out[1][c]);
+                out[2][c] = fmaf(dt[i], r0[c], out[2][c]);
+            }
+            if (ORDER >= 2) {
+                out[3][c] = fmaf(bt[i], r2[c], out[3][c]);
+                out[4][c] = fmaf(dt[i], r1[c], out[4][c]);
+                out[5][c] = fmaf(dtt[i], r0[c], out[5][c]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- GREGORY_BASIS path --
+// 20 points, 5 per corner c: P, E+, E-, F+, F-; Bezier net position (col,row) per point; the face points carry
+// the rational blend G+ = a/(a+b), G- = 1-G+ with (a,b) the distances from corner c along E+ / E-
+// (osd/patchBasis.h:345-378); the reciprocal is replaced by 1 when a+b <= 0.  Derivatives use the reference's
+// default approximation: Bezier derivative weights times the same G (osd/patchBasis.h:421-440).
+template <int LT, int ORDER>
+__device__ __forceinline__ void eval_gregory(const PatchIO &io, const int *cvs, float s, float t, float d1,
+                                             float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
+    constexpr int COL[20] = { 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2, 0, 0, 1, 1, 1 };
+    constexpr int ROW[20] = { 0, 0, 1, 1, 1, 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2 };
+    float bs[4], ds[4], dss[4], bt[4], dt[4], dtt[4];
+    bezier_1d<ORDER>(s, bs, ds, dss);
+    bezier_1d<ORDER>(t, bt, dt, dtt);
+    const float sc = 1.0f - s, tc = 1.0f - t;
+    float G[8];
+    {
+        const float a[4] = { s, t, sc, tc };
+        const float den[4] = { s + t, sc + t, sc + tc, s + tc };
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float r = (den[c] <= 0.0f) ? 1.0f : __frcp_rn(den[c]);
+            G[2 * c] = a[c] * r;
+            G[2 * c + 1] = 1.0f - G[2 * c];
+        }
+    }
+    if (ORDER >= 1) {
+        const float d2 = d1 * d1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ds[j] *= d1; dt[j] *= d1;
+            if (ORDER >= 2) { dss[j] *= d2; dtt[j] *= d2; }
+        }
+    }
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+        for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 20; ++i) {
+        const int col = COL[i], row = ROW[i], p = i % 5;
+        const float g = (p >= 3) ? G[2 * (i / 5) + (p - 3)] : 1.0f;
+        float v[LT];
+        load_cv<LT>(io.src, io.srcStride, __ldg(cvs + i), v);
+        const float gs = bs[col] * g, gt = bt[row];
+        float w[NSETS];
+        w[0] = gs * gt;
+        if (ORDER >= 1) { w[1] = ds[col] * g * gt; w[2] = gs * dt[row]; }
+        if (ORDER >= 2) { w[3] = dss[col] * g * gt; w[4] = ds[col] * g * dt[row]; w[5] = gs * dtt[row]; }
+#pragma unroll
+        for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+            for (int c = 0; c < LT; ++c) out[k][c] = fmaf(w[k], v[c], out[k][c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------- QUADS path --
+template <int LT, int ORDER>
+__device__ __forceinline__ void eval_quads(const PatchIO &io, const int *cvs, float s, float t, float d1,
+                                           float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
+    const float sc = 1.0f - s, tc = 1.0f - t;
+    const float wP[4] = { sc * tc, s * tc, s * t, sc * t };
+    const float wS[4] = { -tc * d1, tc * d1, t * d1, -t * d1 };
+    const float wT[4] = { -sc * d1, -s * d1, s * d1, sc * d1 };
+    const float d2 = d1 * d1;
+    const float wST[4] = { d2, -d2, d2, -d2 };
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+        for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float v[LT];
+        load_cv<LT>(io.src, io.srcStride, __ldg(cvs + i), v);
+#pragma unroll
+        for (int c = 0; c < LT; ++c) {
+            out[0][c] = fmaf(wP[i], v[c], out[0][c]);
+            if (ORDER >= 1) { out[1][c] = fmaf(wS[i], v[c], out[1][c]); out[2][c] = fmaf(wT[i], v[c], out[2][c]); }
+            if (ORDER >= 2) out[4][c] = fmaf(wST[i], v[c], out[4][c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------- triangle bases (weight-array form) --
+__device__ __forceinline__ void refl(float *w, int phantom, int plus0, int plus1, int minus) {
+    const float v = w[phantom];
+    w[plus0] += v;
+    w[plus1] += v;
+    w[minus] -= v;
+}
+
+// Box-spline boundary folding (osd/patchBasis.h:663-886): every phantom point is a reflection B + (B' - I).
+__device__ void box_fold_boundary(int mask, float *w) {
+    const signed char PH[3][3] = { { 0, 1, 2 }, { 6, 9, 11 }, { 10, 7, 3 } };
+    const signed char B1[3] = { 4, 5, 8 }, B2[3] = { 5, 8, 4 }, I1[3] = { 8, 4, 5 };
+    const signed char B0[3] = { 3, 2, 11 }, I0[3] = { 7, 1, 9 };
+    const signed char B3[3] = { 6, 10, 0 }, I2[3] = { 9, 7, 1 };
+    const signed char VP[3][2] = { { 3, 0 }, { 2, 6 }, { 11, 10 } };
+    const signed char VB0[3] = { 7, 1, 9 }, VI0[3] = { 8, 4, 5 };
+    const signed char VB2[3] = { 1, 9, 7 }, VI1[3] = { 5, 8, 4 };
+    const int upper = (mask >> 3) & 3;
+    int ebits = mask & 7, vbits = 0;
+    if (upper == 1) { vbits = ebits; ebits = 0; }
+    else if (upper == 2) { vbits = ((ebits & 1) << 2) | (ebits >> 1); }
+    for (int e = 0; e < 3; ++e) {
+        if (!(ebits & (1 << e))) continue;
+        const int prev = (e + 2) % 3, next = (e + 1) % 3;
+        if (ebits & (1 << prev)) refl(w, PH[e][0], B1[e], B1[e], I1[e]);
+        else                     refl(w, PH[e][0], B1[e], B0[e], I0[e]);
+        refl(w, PH[e][1], B1[e], B2[e], I1[e]);
+        if (ebits & (1 << next)) refl(w, PH[e][2], B2[e], B2[e], I1[e]);
+        else                     refl(w, PH[e][2], B2[e], B3[e], I2[e]);
+        w[PH[e][0]] = 0.0f; w[PH[e][1]] = 0.0f; w[PH[e][2]] = 0.0f;
+    }
+    for (int v = 0; v < 3; ++v) {
+        if (!(vbits & (1 << v))) continue;
+        refl(w, VP[v][0], B1[v], VB0[v], VI0[v]);
+        refl(w, VP[v][1], B1[v], VB2[v], VI1[v]);
+        w[VP[v][0]] = 0.0f; w[VP[v][1]] = 0.0f;
+    }
+}
+
+__device__ __forceinline__ float bern(int n, int i, int j, int k, float u, float v, float w) {
+    if (i < 0 || j < 0 || k < 0) return 0.0f;
+    const float fact[5] = { 1.0f, 1.0f, 2.0f, 6.0f, 24.0f };
+    float r = fact[n] / (fact[i] * fact[j] * fact[k]);
+    for (int q = 0; q < i; ++q) r *= u;
+    for (int q = 0; q < j; ++q) r *= v;
+    for (int q = 0; q < k; ++q) r *= w;
+    return r;
+}
+
+// Weight arrays for LOOP (12), GREGORY_TRIANGLE (18) and TRIANGLES (3); returns the number of points.
+template <int ORDER>
+__device__ int tri_weights(int type, float s, float t, int boundary, float (*w)[20]) {
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+    if (type == PT_TRIANGLES) {
+        w[0][0] = 1.0f - s - t; w[0][1] = s; w[0][2] = t;
+        if (ORDER >= 1) {
+            w[1][0] = -1.0f; w[1][1] = 1.0f; w[1][2] = 0.0f;
+            w[2][0] = -1.0f; w[2][1] = 0.0f; w[2][2] = 1.0f;
+        }
+        if (ORDER >= 2)
+            for (int k = 3; k < 6; ++k) { w[k][0] = 0.0f; w[k][1] = 0.0f; w[k][2] = 0.0f; }
+        return 3;
+    }
+    if (type == PT_LOOP) {
+        float M[15];
+        M[0] = 1.0f; M[1] = s; M[2] = t;
+        M[3] = s * s; M[4] = s * t; M[5] = t * t;
+        M[6] = M[3] * s; M[7] = M[4] * s; M[8] = M[4] * t; M[9] = M[5] * t;
+        M[10] = M[6] * s; M[11] = M[7] * s; M[12] = M[3] * M[5]; M[13] = M[8] * t; M[14] = M[9] * t;
+        for (int k = 0; k < NSETS; ++k) {
+            for (int i = 0; i < 12; ++i) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int m = 0; m < 15; ++m) acc = fmaf((float)g_box_tab[k][i][m], M[m], acc);
+                w[k][i] = g_box_scale[k] * acc;
+            }
+            if (boundary) box_fold_boundary(boundary, w[k]);
+        }
+        return 12;
+    }
+    // GREGORY_TRIANGLE: quartic Bernstein over the triangle + rational blends on the 3 interior points
+    {
+        const signed char PI[15] = { 0, 1, 2, 3, 4, 0, 1, 2, 3, 0, 1, 2, 0, 1, 0 };
+        const signed char PJ[15] = { 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4 };
+        const signed char SRC[18] = { 0, 1, 5, 6, 6, 4, 8, 3, 7, 7, 14, 12, 13, 10, 10, 2, 11, 9 };
+        const signed char GI[18] = { -1, -1, -1, 0, 1, -1, -1, -1, 2, 3, -1, -1, -1, 4, 5, -1, -1, -1 };
+        const int DS[6] = { 0, 1, 0, 2, 1, 0 }, DT[6] = { 0, 0, 1, 0, 1, 2 };
+        const float u = s, v = t, ww = 1.0f - u - v;
+        float G[6] = { 1.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.0f };
+        if ((u + v) > 0.0f)  { G[0] = u / (u + v);   G[1] = v / (u + v); }
+        if ((v + ww) > 0.0f) { G[2] = v / (v + ww);  G[3] = ww / (v + ww); }
+        if ((ww + u) > 0.0f) { G[4] = ww / (ww + u); G[5] = u / (ww + u); }
+        for (int k = 0; k < NSETS; ++k) {
+            float B[15];
+            const int ds = DS[k], dt = DT[k];
+            for (int n = 0; n < 15; ++n) {
+                const int i = PI[n], j = PJ[n], kk = 4 - i - j;
+                float r;
+                if (ds + dt == 0) r = bern(4, i, j, kk, u, v, ww);
+                else if (ds + dt == 1)
+                    r = 4.0f * ((ds ? bern(3, i - 1, j, kk, u, v, ww) : bern(3, i, j - 1, kk, u, v, ww)) - bern(3, i, j, kk - 1, u, v, ww));
+                else if (ds == 2)
+                    r = 12.0f * (bern(2, i - 2, j, kk, u, v, ww) - 2.0f * bern(2, i - 1, j, kk - 1, u, v, ww) + bern(2, i, j, kk - 2, u, v, ww));
+                else if (dt == 2)
+                    r = 12.0f * (bern(2, i, j - 2, kk, u, v, ww) - 2.0f * bern(2, i, j - 1, kk - 1, u, v, ww) + bern(2, i, j, kk - 2, u, v, ww));
+                else
+                    r = 12.0f * (bern(2, i - 1, j - 1, kk, u, v, ww) - bern(2, i - 1, j, kk - 1, u, v, ww)
+                                 - bern(2, i, j - 1, kk - 1, u, v, ww) + bern(2, i, j, kk - 2, u, v, ww));
+                B[n] = r;
+            }
+            for (int i = 0; i < 18; ++i) w[k][i] = (GI[i] < 0) ? B[SRC[i]] : B[SRC[i]] * G[GI[i]];
+        }
+        return 18;
+    }
+}
+
+// --------------------------------------------------------------------------------------- kernel --
+template <int LT, int ORDER>
+__global__ void __launch_bounds__(128) patch_kernel(PatchIO io) {
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= io.n) return;
+
+    const int *cw = reinterpret_cast<const int *>(io.coords + i);
+    const int arrayIndex = ld_stream_i1(cw + 0);
+    const int patchIndex = ld_stream_i1(cw + 1);
+    float s = __int_as_float(ld_stream_i1(cw + 3));
+    float t = __int_as_float(ld_stream_i1(cw + 4));
+
+    const int *aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
+    const int regDesc = __ldg(aw + 0), irrDesc = __ldg(aw + 1);
+    const int indexBase = __ldg(aw + 3), stride = __ldg(aw + 4), primBase = __ldg(aw + 5);
+    const unsigned field1 = __ldg(&io.params[patchIndex].field1);
+
+    const int depth = (int)(field1 & 0xfu);
+    const int nonquad = (int)((field1 >> 4) & 1u);
+    const bool regular = ((field1 >> 5) & 1u) != 0;
+    const int boundary = (int)((field1 >> 7) & 0x1fu);
+    const int pv = (int)((field1 >> 12) & 0x3ffu), pu = (int)((field1 >> 22) & 0x3ffu);
+    const int type = regular ? regDesc : irrDesc;
+    const int *cvs = io.indices + indexBase + stride * (patchIndex - primBase);
+
+    const float fracInv = (float)(1 << (depth - nonquad));
+    const bool isTri = (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES);
+    float sign = 1.0f;
+    if (isTri && (pu + pv) >= (1 << depth)) {
+        const int df = 1 << depth;
+        s = (float)(df - pu) - s * fracInv;
+        t = (float)(df - pv) - t * fracInv;
+        sign = -1.0f;
+    } else {
+        s = fmaf(s, fracInv, -(float)pu);
+        t = fmaf(t, fracInv, -(float)pv);
+    }
+    const float d1 = sign * (float)(1 << depth);
+
+    float out[NSETS][LT];
+    if (type == PT_REGULAR) {
+        eval_regular<LT, ORDER>(io, cvs, s, t, boundary, d1, out);
+    } else if (type == PT_GREGORY_BASIS) {
+        eval_gregory<LT, ORDER>(io, cvs, s, t, d1, out);
+    } else if (type == PT_QUADS) {
+        eval_quads<LT, ORDER>(io, cvs, s, t, d1, out);
+    } else if (isTri) {
+        float w[NSETS][20];
+        const int np = tri_weights<ORDER>(type, s, t, boundary, w);
+        const float d2 = sign * d1 * d1;     // osd/patchBasis.h:1598: d2Scale = derivSign * d1Scale * d1Scale
+#pragma unroll
+        for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+            for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+        for (int j = 0; j < np; ++j) {
+            float v[LT];
+            load_cv<LT>(io.src, io.srcStride, __ldg(cvs + j), v);
+#pragma unroll
+            for (int k = 0; k < NSETS; ++k) {
+                const float wk = w[k][j] * (k == 0 ? 1.0f : (k < 3 ? d1 : d2));
+#pragma unroll
+                for (int c = 0; c < LT; ++c) out[k][c] = fmaf(wk, v[c], out[k][c]);
+            }
+        }
+    } else {
+        // unknown descriptor: the reference evaluates zero points, i.e. writes zeros
+#pragma unroll
+        for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+            for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+    }
+    store_outputs<LT, NSETS>(io, i, out);
+}
+
+}  // namespace b200osd

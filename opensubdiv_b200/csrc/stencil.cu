@@ -1,0 +1,380 @@
+// stencil.cu -- host side of the stencil path: B200 stencil-table construction (bucketing / slicing),
+// argument validation mirroring the reference evaluator, and kernel dispatch.
+//
+// Reference behaviour mirrored (paths relative to /root/reference/opensubdiv):
+//   osd/cpuEvaluator.cpp:46-47,70-72,105-110  end<=start -> true (no-op); any length mismatch -> false
+//   osd/cudaEvaluator.cpp:159                 dst == NULL -> false (value-only form)
+//   osd/cudaEvaluator.cpp:100-145             CudaStencilTable: verbatim device copies of the Far vectors
+#include "stencil_kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+using namespace b200osd;
+
+namespace b200osd {
+int g_stencil_variant = 0;
+}
+
+struct b200osd_stencil_table {
+    int n = 0;
+    long long ne = 0;
+    int nCV = 0;
+    int numW = 1;
+    // verbatim copies (reference layout)
+    int *d_sizes = nullptr, *d_offsets = nullptr, *d_indices = nullptr;
+    float *d_w[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    // bucketed copy
+    bool hasSell = false;
+    int window = 0;
+    int numSlices = 0;
+    size_t totalVec = 0;
+    int4 *d_idx4 = nullptr;
+    float4 *d_w4[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    int2 *d_meta = nullptr;
+    int *d_rows = nullptr;
+    std::vector<int> windowSliceStart;   // host: first slice of each window (+ sentinel)
+    // per-call scratch: 16-byte packed copy of the control vertices
+    float4 *d_pack = nullptr;
+    size_t packCap = 0;
+};
+
+namespace {
+
+constexpr int kWindowRows = 2048;   // rows sorted together; keeps a window's outputs close in time and space
+
+template <typename T>
+int upload(T **dptr, const T *host, size_t count) {
+    *dptr = nullptr;
+    if (count == 0) return B200OSD_OK;
+    cudaError_t e = cudaMalloc((void **)dptr, count * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        *dptr = nullptr;
+        return B200OSD_ERR_ALLOC;
+    }
+    e = cudaMemcpy(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("cudaMemcpy H2D failed: %s", cudaGetErrorString(e));
+        cudaFree(*dptr);
+        *dptr = nullptr;
+        return B200OSD_ERR_CUDA;
+    }
+    return B200OSD_OK;
+}
+
+int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, const int *indices,
+               const float *const w[kMaxOut]) {
+    const int n = t->n;
+    t->window = kWindowRows;
+    const int numWindows = (n + kWindowRows - 1) / kWindowRows;
+    std::vector<int> order(n);
+    std::vector<int2> meta;
+    std::vector<int> rows;
+    t->windowSliceStart.assign(numWindows + 1, 0);
+    meta.reserve(n / kSliceRows + numWindows);
+    rows.reserve((size_t)n + (size_t)numWindows * kSliceRows);
+
+    size_t totalVec = 0;   // in units of 4 elements (one int4 per lane slot)
+    for (int wdw = 0; wdw < numWindows; ++wdw) {
+        const int r0 = wdw * kWindowRows, r1 = std::min(n, r0 + kWindowRows);
+        int *ord = order.data() + r0;
+        std::iota(ord, ord + (r1 - r0), r0);
+        std::stable_sort(ord, ord + (r1 - r0), [&](int a, int b) { return sizes[a] < sizes[b]; });
+        t->windowSliceStart[wdw] = (int)meta.size();
+        for (int s0 = r0; s0 < r1; s0 += kSliceRows) {
+            const int s1 = std::min(r1, s0 + kSliceRows);
+            int maxSize = 0;
+            for (int q = s0; q < s1; ++q) maxSize = std::max(maxSize, sizes[order[q]]);
+            const int lenVec = (maxSize + kVec - 1) / kVec;
+            if (totalVec > 0xffffffffull - (size_t)lenVec * kSliceRows) {
+                set_error("stencil table too large for 32-bit slice bases");
+                return B200OSD_ERR_UNSUPPORTED;
+            }
+            meta.push_back(make_int2((int)(unsigned)totalVec, lenVec));
+            for (int q = 0; q < kSliceRows; ++q) rows.push_back(s0 + q < s1 ? order[s0 + q] : -1);
+            totalVec += (size_t)lenVec * kSliceRows;
+        }
+    }
+    t->windowSliceStart[numWindows] = (int)meta.size();
+    t->numSlices = (int)meta.size();
+    t->totalVec = totalVec;
+
+    // element-major fill: slot (slice, g, lane) holds elements 4g..4g+3 of the lane's row (zero weight padding)
+    std::vector<int4> idx4(totalVec);
+    std::memset(idx4.data(), 0, totalVec * sizeof(int4));
+    for (int s = 0; s < t->numSlices; ++s) {
+        const size_t base = (unsigned)meta[s].x;
+        for (int lane = 0; lane < kSliceRows; ++lane) {
+            const int row = rows[(size_t)s * kSliceRows + lane];
+            if (row < 0) continue;
+            const int sz = sizes[row], off = offsets[row];
+            for (int j = 0; j < sz; ++j) {
+                int *slot = reinterpret_cast<int *>(&idx4[base + (size_t)(j / kVec) * kSliceRows + lane]);
+                slot[j % kVec] = indices[off + j];
+            }
+        }
+    }
+    int rc = upload(&t->d_idx4, idx4.data(), totalVec);
+    if (rc) return rc;
+    {
+        std::vector<int4>().swap(idx4);
+    }
+    std::vector<float4> w4(totalVec);
+    for (int k = 0; k < t->numW; ++k) {
+        std::memset(w4.data(), 0, totalVec * sizeof(float4));
+        for (int s = 0; s < t->numSlices; ++s) {
+            const size_t base = (unsigned)meta[s].x;
+            for (int lane = 0; lane < kSliceRows; ++lane) {
+                const int row = rows[(size_t)s * kSliceRows + lane];
+                if (row < 0) continue;
+                const int sz = sizes[row], off = offsets[row];
+                for (int j = 0; j < sz; ++j) {
+                    float *slot = reinterpret_cast<float *>(&w4[base + (size_t)(j / kVec) * kSliceRows + lane]);
+                    slot[j % kVec] = w[k][off + j];
+                }
+            }
+        }
+        rc = upload(&t->d_w4[k], w4.data(), totalVec);
+        if (rc) return rc;
+    }
+    rc = upload(&t->d_meta, meta.data(), meta.size());
+    if (rc) return rc;
+    rc = upload(&t->d_rows, rows.data(), rows.size());
+    if (rc) return rc;
+    t->hasSell = true;
+    return B200OSD_OK;
+}
+
+// Validation shared by both entry points.  Returns B200OSD_OK with *noop = true for end <= start.
+int prepare_io(StencilIO &io, const float *src, const int srcDesc[3], int nOut, float *const dsts[],
+               const int dstDescs[][3], int start, int end, bool *noop) {
+    *noop = false;
+    if (nOut != 1 && nOut != 3 && nOut != 6) {
+        set_error("nOut must be 1, 3 or 6 (got %d)", nOut);
+        return B200OSD_ERR_INVALID;
+    }
+    if (end <= start) { *noop = true; return B200OSD_OK; }           // cpuEvaluator.cpp:46
+    if (!src) { set_error("src is NULL"); return B200OSD_ERR_INVALID; }
+    if (nOut == 1 && !dsts[0]) { set_error("dst is NULL"); return B200OSD_ERR_INVALID; }   // cudaEvaluator.cpp:159
+    const int L = srcDesc[1];
+    if (L <= 0) { set_error("srcDesc.length must be positive"); return B200OSD_ERR_INVALID; }
+    for (int k = 0; k < nOut; ++k) {
+        if (dstDescs[k][1] != L) {                                    // cpuEvaluator.cpp:47,70-72,105-110
+            set_error("output %d length %d != srcDesc.length %d", k, dstDescs[k][1], L);
+            return B200OSD_ERR_INVALID;
+        }
+    }
+    io.src = src + srcDesc[0];
+    io.srcStride = srcDesc[2];
+    io.L = L;
+    io.start = start;
+    io.end = end;
+    for (int k = 0; k < kMaxOut; ++k) { io.dst[k] = nullptr; io.dstStride[k] = 0; io.dstVec[k] = 1; }
+    for (int k = 0; k < nOut; ++k) {
+        if (!dsts[k]) continue;
+        float *d = dsts[k] + dstDescs[k][0];
+        io.dst[k] = d;
+        io.dstStride[k] = dstDescs[k][2];
+        const uintptr_t a = reinterpret_cast<uintptr_t>(d);
+        const int st = dstDescs[k][2];
+        io.dstVec[k] = (a % 16 == 0 && st % 4 == 0) ? 4 : ((a % 8 == 0 && st % 2 == 0) ? 2 : 1);
+    }
+    return B200OSD_OK;
+}
+
+bool src_is_vec4(const StencilIO &io) {
+    return reinterpret_cast<uintptr_t>(io.src) % 16 == 0 && io.srcStride % 4 == 0;
+}
+
+template <int K>
+int launch_csr(const StencilIO &io, const CsrTable &t, cudaStream_t st) {
+    const int rows = io.end - io.start;
+    const int block = 128;
+    const int grid = (rows + block - 1) / block;
+    const bool v4 = src_is_vec4(io);
+#define CSR_CASE(LL)                                                                   \
+    case LL:                                                                           \
+        if (v4 && (LL % 4 == 0)) csr_kernel<LL, K, true><<<grid, block, 0, st>>>(io, t); \
+        else csr_kernel<LL, K, false><<<grid, block, 0, st>>>(io, t);                  \
+        break;
+    switch (io.L) {
+        CSR_CASE(1) CSR_CASE(2) CSR_CASE(3) CSR_CASE(4) CSR_CASE(6) CSR_CASE(8)
+        default: csr_kernel_anyL<K><<<grid, block, 0, st>>>(io, t); break;
+    }
+#undef CSR_CASE
+    return check_launch("csr_kernel");
+}
+
+template <int K>
+int launch_sell(const StencilIO &io, const SellTable &t, bool vec4, cudaStream_t st) {
+    const int slices = t.sliceEnd - t.sliceBegin;
+    const int block = 256;
+    const int grid = (slices + (block / 32) - 1) / (block / 32);
+    constexpr int U = (K == 1) ? 2 : 1;
+#define SELL_CASE(LL)                                                                          \
+    case LL:                                                                                   \
+        if (vec4) sell_kernel<LL, K, true, U><<<grid, block, 0, st>>>(io, t);                  \
+        else sell_kernel<LL, K, false, U><<<grid, block, 0, st>>>(io, t);                      \
+        break;
+    switch (io.L) {
+        SELL_CASE(1) SELL_CASE(2) SELL_CASE(3) SELL_CASE(4) SELL_CASE(6) SELL_CASE(8)
+        default: sell_kernel_anyL<K><<<grid, block, 0, st>>>(io, t); break;
+    }
+#undef SELL_CASE
+    return check_launch("sell_kernel");
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ C ABI ----
+extern "C" {
+
+b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, const int *sizes, const int *offsets,
+                                                    const int *indices, const float *weights,
+                                                    const float *du, const float *dv, const float *duu,
+                                                    const float *duv, const float *dvv, int flags) {
+    if (numStencils < 0 || (numStencils > 0 && (!sizes || !offsets || !indices || !weights))) {
+        set_error("stencil_table_create: missing arrays");
+        return nullptr;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    b200osd_stencil_table *t = new (std::nothrow) b200osd_stencil_table;
+    if (!t) return nullptr;
+    t->n = numStencils;
+    long long ne = 0;
+    int maxIdx = -1;
+    for (int i = 0; i < numStencils; ++i) ne = std::max<long long>(ne, (long long)offsets[i] + sizes[i]);
+    for (long long e = 0; e < ne; ++e) maxIdx = std::max(maxIdx, indices[e]);
+    t->ne = ne;
+    t->nCV = maxIdx + 1;
+    const float *w[kMaxOut] = { weights, du, dv, duu, duv, dvv };
+    t->numW = (du && dv) ? ((duu && duv && dvv) ? 6 : 3) : 1;
+
+    int rc = upload(&t->d_sizes, sizes, (size_t)numStencils);
+    if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
+    if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
+    for (int k = 0; k < t->numW && !rc; ++k) rc = upload(&t->d_w[k], w[k], (size_t)ne);
+    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w);
+    if (rc) {
+        b200osd_stencil_table_destroy(t);
+        return nullptr;
+    }
+    return t;
+}
+
+void b200osd_stencil_table_destroy(b200osd_stencil_table *t) {
+    if (!t) return;
+    cudaFree(t->d_sizes); cudaFree(t->d_offsets); cudaFree(t->d_indices);
+    for (int k = 0; k < kMaxOut; ++k) { cudaFree(t->d_w[k]); cudaFree(t->d_w4[k]); }
+    cudaFree(t->d_idx4); cudaFree(t->d_meta); cudaFree(t->d_rows); cudaFree(t->d_pack);
+    delete t;
+}
+
+int b200osd_stencil_table_num_stencils(const b200osd_stencil_table *t) { return t ? t->n : 0; }
+int b200osd_stencil_table_num_control_vertices(const b200osd_stencil_table *t) { return t ? t->nCV : 0; }
+long long b200osd_stencil_table_num_elements(const b200osd_stencil_table *t) { return t ? t->ne : 0; }
+
+const void *b200osd_stencil_table_buffer(const b200osd_stencil_table *t, int which) {
+    if (!t) return nullptr;
+    switch (which) {
+        case 0: return t->d_sizes;
+        case 1: return t->d_offsets;
+        case 2: return t->d_indices;
+        default: return (which >= 3 && which < 3 + kMaxOut) ? t->d_w[which - 3] : nullptr;
+    }
+}
+
+long long b200osd_stencil_table_stream_bytes(const b200osd_stencil_table *t, int nOut) {
+    if (!t || !t->hasSell) return 0;
+    return (long long)t->totalVec * 16 * (1 + nOut) + (long long)t->numSlices * (8 + 4 * kSliceRows);
+}
+
+int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src, const int srcDesc[3], int nOut,
+                               float *const dsts[], const int dstDescs[][3], int start, int end, void *stream) {
+    b200osd_stencil_table *t = const_cast<b200osd_stencil_table *>(tc);
+    if (!t) { set_error("stencil table is NULL"); return B200OSD_ERR_INVALID; }
+    StencilIO io;
+    bool noop = false;
+    int rc = prepare_io(io, src, srcDesc, nOut, dsts, dstDescs, start, end, &noop);
+    if (rc || noop) return rc;
+    if (start < 0 || end > t->n) { set_error("row range [%d,%d) outside table of %d rows", start, end, t->n); return B200OSD_ERR_INVALID; }
+    if (nOut > t->numW) { set_error("table has %d weight streams, %d outputs requested", t->numW, nOut); return B200OSD_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+
+    if (!t->hasSell || g_stencil_variant == 1) {
+        CsrTable c;
+        c.sizes = t->d_sizes; c.offsets = t->d_offsets; c.indices = t->d_indices;
+        for (int k = 0; k < kMaxOut; ++k) c.w[k] = t->d_w[k];
+        return nOut == 1 ? launch_csr<1>(io, c, st) : (nOut == 3 ? launch_csr<3>(io, c, st) : launch_csr<6>(io, c, st));
+    }
+
+    SellTable s;
+    s.idx4 = t->d_idx4;
+    for (int k = 0; k < kMaxOut; ++k) s.w4[k] = t->d_w4[k];
+    s.meta = t->d_meta;
+    s.rows = t->d_rows;
+    s.sliceBegin = t->windowSliceStart[start / t->window];
+    s.sliceEnd = t->windowSliceStart[(end + t->window - 1) / t->window];
+
+    // Source access: 128-bit gathers.  Lengths that are not a multiple of 4 (xyz, xyz+normal) or unaligned /
+    // interleaved sources are first repacked (control vertices only: the small hot set) into 16-byte rows.
+    bool vec4 = false;
+    const int L = io.L;
+    const bool specialised = (L == 3 || L == 4 || L == 6 || L == 8);
+    if (specialised && g_stencil_variant != 2) {
+        const bool natural = (L % 4 == 0) && src_is_vec4(io);
+        const long long work = (long long)(end - start);
+        if (natural) {
+            vec4 = true;
+        } else if (work >= 4096 || g_stencil_variant == 3) {
+            const int nv4 = (L + 3) / 4;
+            const size_t need = (size_t)t->nCV * nv4;
+            if (need > t->packCap) {
+                cudaFree(t->d_pack);
+                t->d_pack = nullptr;
+                t->packCap = 0;
+                B200_CUDA_TRY(cudaMalloc((void **)&t->d_pack, need * sizeof(float4)));
+                t->packCap = need;
+            }
+            const int total = t->nCV * nv4;
+            pack_src_kernel<<<(total + 255) / 256, 256, 0, st>>>(io.src, io.srcStride, L, t->nCV, t->d_pack);
+            rc = check_launch("pack_src_kernel");
+            if (rc) return rc;
+            io.src = reinterpret_cast<const float *>(t->d_pack);
+            io.srcStride = 4 * nv4;
+            vec4 = true;
+        }
+    }
+    return nOut == 1 ? launch_sell<1>(io, s, vec4, st) : (nOut == 3 ? launch_sell<3>(io, s, vec4, st) : launch_sell<6>(io, s, vec4, st));
+}
+
+int b200osd_eval_stencils(const float *src, const int srcDesc[3], int nOut, float *const dsts[],
+                          const int dstDescs[][3], const int *sizes, const int *offsets, const int *indices,
+                          const float *const weights[], int start, int end, void *stream) {
+    StencilIO io;
+    bool noop = false;
+    int rc = prepare_io(io, src, srcDesc, nOut, dsts, dstDescs, start, end, &noop);
+    if (rc || noop) return rc;
+    if (!sizes || !offsets || !indices) { set_error("stencil arrays are NULL"); return B200OSD_ERR_INVALID; }
+    CsrTable c;
+    c.sizes = sizes; c.offsets = offsets; c.indices = indices;
+    for (int k = 0; k < kMaxOut; ++k) c.w[k] = nullptr;
+    for (int k = 0; k < nOut; ++k) {
+        if (!weights[k]) { set_error("weights[%d] is NULL", k); return B200OSD_ERR_INVALID; }
+        c.w[k] = weights[k];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    return nOut == 1 ? launch_csr<1>(io, c, st) : (nOut == 3 ? launch_csr<3>(io, c, st) : launch_csr<6>(io, c, st));
+}
+
+void b200osd_set_stencil_variant(int v) { g_stencil_variant = v; }
+int b200osd_get_stencil_variant(void) { return g_stencil_variant; }
+
+}  // extern "C"

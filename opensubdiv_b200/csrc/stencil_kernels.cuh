@@ -1,0 +1,309 @@
+// stencil_kernels.cuh -- device code of the stencil path (EvalStencils), sm_100a.
+//
+// Semantics restated from the reference (paths relative to /root/reference/opensubdiv):
+//   osd/cpuKernel.cpp:71-240  for row i: out_k[i] = sum_j w_k[off_i + j] * src[idx[off_i + j]]   (k = value,du,dv,duu,duv,dvv)
+//   osd/cudaKernel.cu:85-98   row i of [start,end) is written to element i of dst (absolute index)
+//
+// Two kernel families:
+//   csr_*   : plain reference layout (sizes/offsets/indices/weights), one thread per row.  Serves the raw
+//             pointer API (any table a client hands us) -- correct for everything, not the fast path.
+//   sell_*  : the B200StencilTable layout.  Rows are sorted by size inside windows and cut into slices of
+//             32 rows; a slice stores its elements element-major in groups of 4 (lane l owns row l of the
+//             slice and finds its elements j=4g..4g+3 in one int4 / float4 at [base + g*32 + l]), so every
+//             warp-wide load of the index / weight streams is one fully coalesced 512-byte request and no
+//             shuffle or shared-memory reduction is needed: each lane accumulates its own row in registers.
+//             Primvar gathers go through L1/L2 (the control-vertex set is small and hot).
+#pragma once
+
+#include "common.cuh"
+
+namespace b200osd {
+
+constexpr int kMaxOut = 6;
+constexpr int kSliceRows = 32;     // rows per slice == warp size
+constexpr int kVec = 4;            // elements per 128-bit load
+
+struct StencilIO {
+    const float *src;              // already offset by srcDesc.offset
+    int srcStride;                 // floats between vertices (== 4*ceil(L/4) when the packed copy is used)
+    int L;                         // primvar length
+    float *dst[kMaxOut];           // already offset; NULL = skip
+    int dstStride[kMaxOut];
+    int dstVec[kMaxOut];           // widest aligned store usable for this output: 1, 2 or 4 floats
+    int start, end;                // absolute row range
+};
+
+struct CsrTable {
+    const int *sizes, *offsets, *indices;
+    const float *w[kMaxOut];
+};
+
+struct SellTable {
+    const int4 *idx4;              // [totalVec] element-major index groups
+    const float4 *w4[kMaxOut];     // same layout, one per weight stream
+    const int2 *meta;              // per slice: {baseVec, lenVec}
+    const int *rows;               // [numSlices*32] original row of each lane slot, -1 = padding
+    int sliceBegin, sliceEnd;
+};
+
+// ------------------------------------------------------------------------------- vertex access --
+template <int L>
+__device__ __forceinline__ void load_vertex_scalar(const float *src, int stride, int idx, float (&v)[L]) {
+    const float *p = src + (size_t)idx * (size_t)stride;
+#pragma unroll
+    for (int k = 0; k < L; ++k) v[k] = p[k];
+}
+
+// stride is a multiple of 4 floats and src is 16-byte aligned (packed copy, or a naturally aligned buffer)
+template <int L>
+__device__ __forceinline__ void load_vertex_vec4(const float *src, int stride, int idx, float (&v)[L]) {
+    const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)idx * (size_t)stride);
+#pragma unroll
+    for (int c = 0; c < (L + 3) / 4; ++c) {
+        float4 t = p[c];
+        if (4 * c + 0 < L) v[4 * c + 0] = t.x;
+        if (4 * c + 1 < L) v[4 * c + 1] = t.y;
+        if (4 * c + 2 < L) v[4 * c + 2] = t.z;
+        if (4 * c + 3 < L) v[4 * c + 3] = t.w;
+    }
+}
+
+template <int L, bool VEC4>
+__device__ __forceinline__ void load_vertex(const float *src, int stride, int idx, float (&v)[L]) {
+    if (VEC4) load_vertex_vec4<L>(src, stride, idx, v);
+    else      load_vertex_scalar<L>(src, stride, idx, v);
+}
+
+template <int L>
+__device__ __forceinline__ void store_vertex(float *p, const float (&v)[L], int vec) {
+    if ((L % 4 == 0) && vec == 4) {
+#pragma unroll
+        for (int k = 0; k < L / 4; ++k) st_stream_f4(p + 4 * k, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    } else if ((L % 2 == 0) && vec >= 2) {
+#pragma unroll
+        for (int k = 0; k < L / 2; ++k) st_stream_f2(p + 2 * k, v[2 * k], v[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < L; ++k) st_stream_f1(p + k, v[k]);
+    }
+}
+
+template <int L, int K>
+__device__ __forceinline__ void store_row(const StencilIO &io, int row, const float (&acc)[K][L]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float *d = io.dst[k];
+        if (d) store_vertex<L>(d + (size_t)row * (size_t)io.dstStride[k], acc[k], io.dstVec[k]);
+    }
+}
+
+template <int L, int K>
+__device__ __forceinline__ void accumulate(float (&acc)[K][L], const float (&v)[L], const float (&w)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int c = 0; c < L; ++c) acc[k][c] = fmaf(w[k], v[c], acc[k][c]);
+}
+
+// ------------------------------------------------------------------------------------ CSR path --
+template <int L, int K, bool VEC4>
+__global__ void __launch_bounds__(128) csr_kernel(StencilIO io, CsrTable t) {
+    int row = io.start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= io.end) return;
+    int off = t.offsets[row];
+    int n = t.sizes[row];
+    float acc[K][L];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int c = 0; c < L; ++c) acc[k][c] = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+        int idx = t.indices[off + j];
+        float w[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k] = t.w[k][off + j];
+        float v[L];
+        load_vertex<L, VEC4>(io.src, io.srcStride, idx, v);
+        accumulate<L, K>(acc, v, w);
+    }
+    store_row<L, K>(io, row, acc);
+}
+
+// Any primvar length: components are processed in tiles of 4, re-walking the row per tile.
+template <int K>
+__global__ void __launch_bounds__(128) csr_kernel_anyL(StencilIO io, CsrTable t) {
+    int row = io.start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= io.end) return;
+    int off = t.offsets[row];
+    int n = t.sizes[row];
+    for (int c0 = 0; c0 < io.L; c0 += 4) {
+        int nc = min(4, io.L - c0);
+        float acc[K][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[k][c] = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            int idx = t.indices[off + j];
+            const float *p = io.src + (size_t)idx * (size_t)io.srcStride + c0;
+            float v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = (c < nc) ? p[c] : 0.0f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float w = t.w[k][off + j];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[k][c] = fmaf(w, v[c], acc[k][c]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float *d = io.dst[k];
+            if (!d) continue;
+            d += (size_t)row * (size_t)io.dstStride[k] + c0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < nc) d[c] = acc[k][c];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------- SELL path --
+// One warp per slice, one lane per row.  UNROLL index groups are issued back to back so that each lane has
+// 2*UNROLL 128-bit stream loads in flight before the first gather is consumed.
+template <int L, int K, bool VEC4, int UNROLL>
+__global__ void __launch_bounds__(256) sell_kernel(StencilIO io, SellTable t) {
+    const int lane = threadIdx.x & 31;
+    const int slice = t.sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (slice >= t.sliceEnd) return;
+    const int2 m = t.meta[slice];
+    const int row = t.rows[(size_t)slice * kSliceRows + lane];
+    const size_t base = (size_t)(unsigned)m.x + lane;
+    const int4 *ip = t.idx4 + base;
+    const float4 *wp[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) wp[k] = t.w4[k] + base;
+
+    float acc[K][L];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int c = 0; c < L; ++c) acc[k][c] = 0.0f;
+
+    int g = 0;
+    const int ng = m.y;
+    for (; g + UNROLL <= ng; g += UNROLL) {
+        int4 id[UNROLL];
+        float4 w[UNROLL][K];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            id[u] = ld_stream_i4(ip + (size_t)(g + u) * kSliceRows);
+#pragma unroll
+            for (int k = 0; k < K; ++k) w[u][k] = ld_stream_f4(wp[k] + (size_t)(g + u) * kSliceRows);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            float v0[L], v1[L], v2[L], v3[L];
+            load_vertex<L, VEC4>(io.src, io.srcStride, id[u].x, v0);
+            load_vertex<L, VEC4>(io.src, io.srcStride, id[u].y, v1);
+            load_vertex<L, VEC4>(io.src, io.srcStride, id[u].z, v2);
+            load_vertex<L, VEC4>(io.src, io.srcStride, id[u].w, v3);
+            float wx[K], wy[K], wz[K], ww[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { wx[k] = w[u][k].x; wy[k] = w[u][k].y; wz[k] = w[u][k].z; ww[k] = w[u][k].w; }
+            accumulate<L, K>(acc, v0, wx);
+            accumulate<L, K>(acc, v1, wy);
+            accumulate<L, K>(acc, v2, wz);
+            accumulate<L, K>(acc, v3, ww);
+        }
+    }
+    for (; g < ng; ++g) {
+        int4 id = ld_stream_i4(ip + (size_t)g * kSliceRows);
+        float4 w[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k] = ld_stream_f4(wp[k] + (size_t)g * kSliceRows);
+        float v0[L], v1[L], v2[L], v3[L];
+        load_vertex<L, VEC4>(io.src, io.srcStride, id.x, v0);
+        load_vertex<L, VEC4>(io.src, io.srcStride, id.y, v1);
+        load_vertex<L, VEC4>(io.src, io.srcStride, id.z, v2);
+        load_vertex<L, VEC4>(io.src, io.srcStride, id.w, v3);
+        float wx[K], wy[K], wz[K], ww[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { wx[k] = w[k].x; wy[k] = w[k].y; wz[k] = w[k].z; ww[k] = w[k].w; }
+        accumulate<L, K>(acc, v0, wx);
+        accumulate<L, K>(acc, v1, wy);
+        accumulate<L, K>(acc, v2, wz);
+        accumulate<L, K>(acc, v3, ww);
+    }
+    if (row >= io.start && row < io.end) store_row<L, K>(io, row, acc);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) sell_kernel_anyL(StencilIO io, SellTable t) {
+    const int lane = threadIdx.x & 31;
+    const int slice = t.sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (slice >= t.sliceEnd) return;
+    const int2 m = t.meta[slice];
+    const int row = t.rows[(size_t)slice * kSliceRows + lane];
+    const size_t base = (size_t)(unsigned)m.x + lane;
+    const bool live = (row >= io.start && row < io.end);
+    for (int c0 = 0; c0 < io.L; c0 += 4) {
+        int nc = min(4, io.L - c0);
+        float acc[K][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[k][c] = 0.0f;
+        for (int g = 0; g < m.y; ++g) {
+            int4 id = t.idx4[base + (size_t)g * kSliceRows];
+            int ids[4] = { id.x, id.y, id.z, id.w };
+            float4 w[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) w[k] = t.w4[k][base + (size_t)g * kSliceRows];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float *p = io.src + (size_t)ids[q] * (size_t)io.srcStride + c0;
+                float v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = (c < nc) ? p[c] : 0.0f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float wk = q == 0 ? w[k].x : (q == 1 ? w[k].y : (q == 2 ? w[k].z : w[k].w));
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[k][c] = fmaf(wk, v[c], acc[k][c]);
+                }
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float *d = io.dst[k];
+                if (!d) continue;
+                d += (size_t)row * (size_t)io.dstStride[k] + c0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nc) d[c] = acc[k][c];
+            }
+        }
+    }
+}
+
+// Repack `n` source vertices (length L, arbitrary stride) into 16-byte aligned rows of 4*ceil(L/4) floats so
+// that every gather is ceil(L/4) 128-bit loads.  n is the control-vertex count (small: it is the hot set).
+__global__ void __launch_bounds__(256) pack_src_kernel(const float *src, int srcStride, int L, int n, float4 *out) {
+    int nv4 = (L + 3) >> 2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * nv4) return;
+    int v = i / nv4, c = i - v * nv4;
+    const float *p = src + (size_t)v * (size_t)srcStride + 4 * c;
+    int rem = L - 4 * c;
+    float4 r;
+    r.x = p[0];
+    r.y = rem > 1 ? p[1] : 0.0f;
+    r.z = rem > 2 ? p[2] : 0.0f;
+    r.w = rem > 3 ? p[3] : 0.0f;
+    out[i] = r;
+}
+
+}  // namespace b200osd

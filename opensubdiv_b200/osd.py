@@ -1,0 +1,367 @@
+"""Host-side mirror of the Osd evaluator interface for the B200 backend.
+
+Same class / method names, argument meaning and error behaviour as the reference CUDA backend
+(paths relative to /root/reference/opensubdiv):
+
+    BufferDescriptor   osd/bufferDescriptor.h:61-104
+    B200VertexBuffer   <-> CudaVertexBuffer   osd/cudaVertexBuffer.h:42-80
+    B200StencilTable   <-> CudaStencilTable   osd/cudaEvaluator.h:52-92
+    B200PatchTable     <-> CudaPatchTable     osd/cudaPatchTable.h:51-112
+    B200Evaluator      <-> CudaEvaluator      osd/cudaEvaluator.h:94-1262
+
+Everything here is a thin veneer over the C ABI (include/b200osd_capi.h); the C++ header-only twin that
+drops into Osd::Mesh<> lives in include/b200osd/.  PyTorch is used for plumbing only (current stream,
+zero-copy tensor views for torch.distributed).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+
+# numpy mirrors of the Osd POD types
+PATCH_COORD_DTYPE = np.dtype([("arrayIndex", "<i4"), ("patchIndex", "<i4"), ("vertIndex", "<i4"),
+                              ("s", "<f4"), ("t", "<f4")])                               # osd/types.h:42-64
+PATCH_ARRAY_DTYPE = np.dtype([("regDesc", "<i4"), ("desc", "<i4"), ("numPatches", "<i4"),
+                              ("indexBase", "<i4"), ("stride", "<i4"), ("primitiveIdBase", "<i4")])  # :66-122
+PATCH_PARAM_DTYPE = np.dtype([("field0", "<u4"), ("field1", "<u4"), ("sharpness", "<f4")])           # :127-130
+
+
+@dataclass(frozen=True)
+class BufferDescriptor:
+    """offset / length / stride in floats (osd/bufferDescriptor.h:61-104)."""
+    offset: int = 0
+    length: int = 0
+    stride: int = 0
+
+    def GetLocalOffset(self) -> int:
+        return self.offset % self.stride if self.stride > 0 else 0
+
+    def IsValid(self) -> bool:
+        return self.length > 0 and self.length <= self.stride - self.GetLocalOffset()
+
+    def as_c(self):
+        return (C.c_int * 3)(self.offset, self.length, self.stride)
+
+
+def _desc(d) -> BufferDescriptor:
+    return d if isinstance(d, BufferDescriptor) else BufferDescriptor(*d)
+
+
+def _stream_ptr(deviceContext=None) -> Optional[int]:
+    """deviceContext may be None (torch's current stream), an int cudaStream_t, or a torch.cuda.Stream."""
+    if deviceContext is None:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.cuda.current_stream().cuda_stream or None
+        except Exception:
+            pass
+        return None
+    if isinstance(deviceContext, int):
+        return deviceContext or None
+    return getattr(deviceContext, "cuda_stream", None) or None
+
+
+def _dev_ptr(buf) -> Optional[int]:
+    if buf is None:
+        return None
+    if hasattr(buf, "BindCudaBuffer"):
+        return buf.BindCudaBuffer()
+    if hasattr(buf, "data_ptr"):
+        if not buf.is_cuda:
+            raise capi.B200OsdError("evaluator buffers must live on the GPU (got a CPU tensor)")
+        return buf.data_ptr()
+    if isinstance(buf, int):
+        return buf
+    raise TypeError(f"cannot take a device pointer from {type(buf)}")
+
+
+class _CudaArrayView:
+    def __init__(self, ptr: int, n: int, owner):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+class B200VertexBuffer:
+    """Device vertex buffer; mirrors CudaVertexBuffer (Create / UpdateData / GetNum* / BindCudaBuffer)."""
+
+    def __init__(self, handle, numElements: int, numVertices: int):
+        self._h = handle
+        self._numElements = numElements
+        self._numVertices = numVertices
+        self._tensor = None
+
+    @classmethod
+    def Create(cls, numElements: int, numVertices: int, deviceContext=None) -> Optional["B200VertexBuffer"]:
+        h = capi.lib().b200osd_vertex_buffer_create(numElements, numVertices)
+        return cls(h, numElements, numVertices) if h else None       # NULL on failure, like the reference
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b200osd_vertex_buffer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def UpdateData(self, src, startVertex: int, numVertices: int, deviceContext=None) -> None:
+        """Host -> device copy of numVertices vertices (src: numpy array or CPU tensor, ideally pinned)."""
+        ptr = src.ctypes.data if isinstance(src, np.ndarray) else src.data_ptr()
+        rc = capi.lib().b200osd_vertex_buffer_update(self._h, ptr, startVertex, numVertices, _stream_ptr(deviceContext))
+        if not capi.check(rc, "B200VertexBuffer::UpdateData"):
+            raise capi.B200OsdError(capi.last_error())
+
+    def ReadData(self, dst, startVertex: int, numVertices: int, deviceContext=None) -> None:
+        """Device -> host read-back into dst (numpy array or CPU tensor); asynchronous on the stream."""
+        ptr = dst.ctypes.data if isinstance(dst, np.ndarray) else dst.data_ptr()
+        rc = capi.lib().b200osd_vertex_buffer_read(self._h, ptr, startVertex, numVertices, _stream_ptr(deviceContext))
+        if not capi.check(rc, "B200VertexBuffer::ReadData"):
+            raise capi.B200OsdError(capi.last_error())
+
+    def GetNumElements(self) -> int:
+        return self._numElements
+
+    def GetNumVertices(self) -> int:
+        return self._numVertices
+
+    def BindCudaBuffer(self) -> int:
+        return capi.lib().b200osd_vertex_buffer_bind(self._h)
+
+    def BindVBO(self, deviceContext=None) -> int:      # Osd::Mesh calls this name (osd/mesh.h:562-568)
+        return self.BindCudaBuffer()
+
+    def as_tensor(self):
+        """Zero-copy torch view [numVertices, numElements] (for torch.distributed collectives)."""
+        if self._tensor is None:
+            import torch
+            view = _CudaArrayView(self.BindCudaBuffer(), self._numElements * self._numVertices, self)
+            self._tensor = torch.as_tensor(view, device="cuda").view(self._numVertices, self._numElements)
+        return self._tensor
+
+
+class B200StencilTable:
+    """Device stencil table; mirrors CudaStencilTable plus the B200 bucketed layout."""
+
+    def __init__(self, handle, keep=None):
+        self._h = handle
+        self._keep = keep
+
+    @classmethod
+    def Create(cls, table, deviceContext=None, bucketed: bool = True) -> Optional["B200StencilTable"]:
+        """`table` is anything with the Far::StencilTable / LimitStencilTable accessors as numpy arrays:
+        sizes, offsets, indices, weights and optionally du, dv, duu, duv, dvv (far/stencilTable.h:156-186,434-456)."""
+        def arr(name, dt):
+            a = getattr(table, name, None)
+            return None if a is None else np.ascontiguousarray(a, dtype=dt)
+        sizes, offsets, indices = arr("sizes", np.int32), arr("offsets", np.int32), arr("indices", np.int32)
+        w = [arr(n, np.float32) for n in ("weights", "du", "dv", "duu", "duv", "dvv")]
+        p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        h = capi.lib().b200osd_stencil_table_create(len(sizes), p(sizes), p(offsets), p(indices), *[p(x) for x in w],
+                                                    0 if bucketed else 1)
+        return cls(h) if h else None
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b200osd_stencil_table_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _buf(self, which):
+        return capi.lib().b200osd_stencil_table_buffer(self._h, which)
+
+    def GetSizesBuffer(self): return self._buf(0)
+    def GetOffsetsBuffer(self): return self._buf(1)
+    def GetIndicesBuffer(self): return self._buf(2)
+    def GetWeightsBuffer(self): return self._buf(3)
+    def GetDuWeightsBuffer(self): return self._buf(4)
+    def GetDvWeightsBuffer(self): return self._buf(5)
+    def GetDuuWeightsBuffer(self): return self._buf(6)
+    def GetDuvWeightsBuffer(self): return self._buf(7)
+    def GetDvvWeightsBuffer(self): return self._buf(8)
+
+    def GetNumStencils(self) -> int:
+        return capi.lib().b200osd_stencil_table_num_stencils(self._h)
+
+    def GetNumControlVertices(self) -> int:
+        return capi.lib().b200osd_stencil_table_num_control_vertices(self._h)
+
+    def GetNumElements(self) -> int:
+        return capi.lib().b200osd_stencil_table_num_elements(self._h)
+
+    def GetStreamBytes(self, nOut: int = 1) -> int:
+        return capi.lib().b200osd_stencil_table_stream_bytes(self._h, nOut)
+
+
+class B200PatchTable:
+    """Device patch table; mirrors CudaPatchTable (built from the flattened Osd::CpuPatchTable arrays)."""
+
+    VertexBufferBinding = int     # Osd::Mesh needs PT::VertexBufferBinding (osd/mesh.h:71,426)
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def Create(cls, table, deviceContext=None) -> Optional["B200PatchTable"]:
+        """`table` has .vertex, .varying (or None) and .fvar (list) triples, each with numpy .arrays
+        (PATCH_ARRAY_DTYPE), .indices (int32) and .params (PATCH_PARAM_DTYPE) -- the layout Osd::CpuPatchTable
+        produces from a Far::PatchTable (osd/cpuPatchTable.cpp:35-156)."""
+        L = capi.lib()
+        fvar = list(getattr(table, "fvar", []) or [])
+        h = L.b200osd_patch_table_create(len(fvar))
+        if not h:
+            return None
+        self = cls(h)
+
+        def put(which, tr, with_params=True):
+            if tr is None:
+                return True
+            a = np.ascontiguousarray(tr.arrays, dtype=PATCH_ARRAY_DTYPE)
+            ix = np.ascontiguousarray(tr.indices, dtype=np.int32)
+            pr = np.ascontiguousarray(tr.params, dtype=PATCH_PARAM_DTYPE) if with_params else None
+            rc = L.b200osd_patch_table_set(h, which, len(a), a.ctypes.data, len(ix), ix.ctypes.data if len(ix) else None,
+                                           0 if pr is None else len(pr), None if pr is None else pr.ctypes.data)
+            return capi.check(rc, "B200PatchTable::Create")
+        ok = put(0, table.vertex) and put(1, getattr(table, "varying", None), with_params=False)
+        for c, tr in enumerate(fvar):
+            ok = ok and put(2 + c, tr)
+        return self if ok else None
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b200osd_patch_table_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _buf(self, which, kind):
+        return capi.lib().b200osd_patch_table_buffer(self._h, which, kind)
+
+    def GetPatchArrayBuffer(self): return self._buf(0, 0)
+    def GetPatchIndexBuffer(self): return self._buf(0, 1)
+    def GetPatchParamBuffer(self): return self._buf(0, 2)
+    def GetVaryingPatchArrayBuffer(self): return self._buf(1, 0)
+    def GetVaryingPatchIndexBuffer(self): return self._buf(1, 1)
+    def GetNumFVarChannels(self) -> int: return capi.lib().b200osd_patch_table_num_fvar_channels(self._h)
+    def GetFVarPatchArrayBuffer(self, fvarChannel: int = 0): return self._buf(2 + fvarChannel, 0)
+    def GetFVarPatchIndexBuffer(self, fvarChannel: int = 0): return self._buf(2 + fvarChannel, 1)
+    def GetFVarPatchParamBuffer(self, fvarChannel: int = 0): return self._buf(2 + fvarChannel, 2)
+
+
+def _is_desc(d) -> bool:
+    return isinstance(d, BufferDescriptor) or (isinstance(d, (tuple, list)) and len(d) == 3
+                                               and all(isinstance(v, (int, np.integer)) for v in d))
+
+
+def _split_outputs(args):
+    """(buf, desc, buf, desc, ..., rest...) -> ([(buf, desc)...], rest)."""
+    outs, i = [], 0
+    while i + 1 < len(args) and _is_desc(args[i + 1]):
+        outs.append((args[i], _desc(args[i + 1])))
+        i += 2
+    return outs, args[i:]
+
+
+class B200Evaluator:
+    """Static evaluator; mirrors CudaEvaluator.  Every method returns the reference's bool."""
+
+    # ---------------------------------------------------------------------------- stencils --
+    @staticmethod
+    def EvalStencils(srcBuffer, srcDesc, *args, instance=None, deviceContext=None, start: int = 0,
+                     end: Optional[int] = None) -> bool:
+        """EvalStencils(src, srcDesc, dst, dstDesc [, du, duDesc, dv, dvDesc [, duu, duuDesc, duv, duvDesc, dvv, dvvDesc]],
+                        stencilTable [, instance [, deviceContext]])          (osd/cudaEvaluator.h:125-143,217-242,352-386)"""
+        outs, rest = _split_outputs(args)
+        if len(outs) not in (1, 3, 6) or not rest:
+            raise TypeError("EvalStencils expects 1, 3 or 6 (buffer, descriptor) outputs followed by a stencil table")
+        table = rest[0]
+        if len(rest) > 2 and deviceContext is None:
+            deviceContext = rest[2]
+        n = len(outs)
+        sd = _desc(srcDesc).as_c()
+        dsts = (C.c_void_p * n)(*[_dev_ptr(b) for b, _ in outs])
+        dds = (C.c_int * (3 * n))(*[v for _, d in outs for v in (d.offset, d.length, d.stride)])
+        end = table.GetNumStencils() if end is None else end
+        rc = capi.lib().b200osd_stencil_table_eval(table._h, _dev_ptr(srcBuffer), sd, n, dsts, dds, start, end,
+                                                   _stream_ptr(deviceContext))
+        return capi.check(rc, "B200Evaluator::EvalStencils")
+
+    @staticmethod
+    def EvalStencilsRaw(src, srcDesc, outs: Sequence, sizes, offsets, indices, weights: Sequence, start: int, end: int,
+                        deviceContext=None) -> bool:
+        """Raw-pointer overloads on reference-layout device arrays (osd/cudaEvaluator.h:171-178,284-295,449-466).
+        outs = [(dst, dstDesc), ...] (1, 3 or 6); weights = matching device weight arrays."""
+        n = len(outs)
+        sd = _desc(srcDesc).as_c()
+        dsts = (C.c_void_p * n)(*[_dev_ptr(b) for b, _ in outs])
+        dds = (C.c_int * (3 * n))(*[v for _, d in outs for v in (_desc(d).offset, _desc(d).length, _desc(d).stride)])
+        ws = (C.c_void_p * n)(*[_dev_ptr(w) for w in weights[:n]])
+        rc = capi.lib().b200osd_eval_stencils(_dev_ptr(src), sd, n, dsts, dds, _dev_ptr(sizes), _dev_ptr(offsets),
+                                              _dev_ptr(indices), ws, start, end, _stream_ptr(deviceContext))
+        return capi.check(rc, "B200Evaluator::EvalStencils(raw)")
+
+    # ----------------------------------------------------------------------------- patches --
+    @staticmethod
+    def _eval_patches(srcBuffer, srcDesc, outs, numPatchCoords, patchCoords, arrays, indices, params, deviceContext) -> bool:
+        n = len(outs)
+        if n not in (1, 3, 6):
+            raise TypeError("EvalPatches expects 1, 3 or 6 (buffer, descriptor) outputs")
+        sd = _desc(srcDesc).as_c()
+        dsts = (C.c_void_p * n)(*[_dev_ptr(b) for b, _ in outs])
+        dds = (C.c_int * (3 * n))(*[v for _, d in outs for v in (d.offset, d.length, d.stride)])
+        rc = capi.lib().b200osd_eval_patches(_dev_ptr(srcBuffer), sd, n, dsts, dds, numPatchCoords, _dev_ptr(patchCoords),
+                                             arrays, indices, params, _stream_ptr(deviceContext))
+        return capi.check(rc, "B200Evaluator::EvalPatches")
+
+    @staticmethod
+    def _parse_patch_args(args):
+        outs, rest = _split_outputs(args)
+        if len(rest) < 3:
+            raise TypeError("expected (numPatchCoords, patchCoords, patchTable [, fvarChannel] [, instance [, deviceContext]])")
+        return outs, rest
+
+    @staticmethod
+    def EvalPatches(srcBuffer, srcDesc, *args, deviceContext=None) -> bool:
+        """EvalPatches(src, srcDesc, dst, dstDesc [, du, duDesc, dv, dvDesc [, duu.., duv.., dvv..]],
+                       numPatchCoords, patchCoords, patchTable [, instance [, deviceContext]])   (osd/cudaEvaluator.h:502-677)"""
+        outs, rest = B200Evaluator._parse_patch_args(args)
+        n, coords, pt = rest[0], rest[1], rest[2]
+        return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetPatchArrayBuffer(),
+                                           pt.GetPatchIndexBuffer(), pt.GetPatchParamBuffer(), deviceContext)
+
+    @staticmethod
+    def EvalPatchesVarying(srcBuffer, srcDesc, *args, deviceContext=None) -> bool:
+        """Same kernel on the varying triple + vertex PatchParams (osd/cudaEvaluator.h:857-1036)."""
+        outs, rest = B200Evaluator._parse_patch_args(args)
+        n, coords, pt = rest[0], rest[1], rest[2]
+        return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetVaryingPatchArrayBuffer(),
+                                           pt.GetVaryingPatchIndexBuffer(), pt.GetPatchParamBuffer(), deviceContext)
+
+    @staticmethod
+    def EvalPatchesFaceVarying(srcBuffer, srcDesc, *args, deviceContext=None) -> bool:
+        """Same kernel on the face-varying triple of `fvarChannel` (osd/cudaEvaluator.h:1068-1254)."""
+        outs, rest = B200Evaluator._parse_patch_args(args)
+        n, coords, pt = rest[0], rest[1], rest[2]
+        ch = rest[3] if len(rest) > 3 and isinstance(rest[3], (int, np.integer)) else 0
+        return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetFVarPatchArrayBuffer(ch),
+                                           pt.GetFVarPatchIndexBuffer(ch), pt.GetFVarPatchParamBuffer(ch), deviceContext)
+
+    @staticmethod
+    def EvalPatchesRaw(src, srcDesc, outs: Sequence, numPatchCoords, patchCoords, patchArrays, patchIndices, patchParams,
+                       deviceContext=None) -> bool:
+        """Raw-pointer overloads (osd/cudaEvaluator.h:706-713,752-761,815-827)."""
+        outs = [(b, _desc(d)) for b, d in outs]
+        return B200Evaluator._eval_patches(src, srcDesc, outs, numPatchCoords, patchCoords, _dev_ptr(patchArrays),
+                                           _dev_ptr(patchIndices), _dev_ptr(patchParams), deviceContext)
+
+    @staticmethod
+    def Synchronize(deviceContext=None) -> None:
+        capi.check(capi.lib().b200osd_synchronize(_stream_ptr(deviceContext) if deviceContext is not None else None),
+                   "B200Evaluator::Synchronize")

@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE -- ctypes view of oracle/liboracle.so (oracle/osd_oracle.c).
+
+The C oracle is a single-threaded restatement of the reference CPU algorithm (see the header of
+osd_oracle.c for the file:line map).  It travels to the GPU box, where /root/reference is absent, and is
+the checker for every `-m gpu` parity test.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module; opensubdiv_b200/ never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC_PATH = os.path.join(_HERE, "osd_oracle.c")
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+DESC_DTYPE = np.dtype([("offset", "<i4"), ("length", "<i4"), ("stride", "<i4")])
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """gcc -O2 -ffp-contract=off: separate multiply/add like the reference's x86-64 build."""
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(SRC_PATH):
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([cc, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c99", "-Wall",
+                               "-o", LIB_PATH, SRC_PATH])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.oracle_eval_stencils.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.oracle_eval_patches.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+        L.oracle_patch_basis.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_float] + [vp] * 6
+        L.oracle_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _descs(descs) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(descs, dtype=np.int32).reshape(-1, 3))
+
+
+def eval_stencils(src: np.ndarray, src_desc, dsts: Sequence[Optional[np.ndarray]], dst_descs,
+                  sizes, offsets, indices, weights: Sequence[np.ndarray], start: int = 0,
+                  end: Optional[int] = None) -> bool:
+    """Restates Osd::CpuEvaluator::EvalStencils (osd/cpuEvaluator.cpp:37-125 -> osd/cpuKernel.cpp:71-240)."""
+    nw = len(dsts)
+    end = len(sizes) if end is None else end
+    sd, dd = _descs([src_desc]), _descs(dst_descs)
+    dptr = (C.c_void_p * nw)(*[None if d is None else d.ctypes.data for d in dsts])
+    wptr = (C.c_void_p * nw)(*[w.ctypes.data for w in weights[:nw]])
+    return bool(lib().oracle_eval_stencils(nw, _p(src), _p(sd), dptr, _p(dd), _p(sizes), _p(offsets), _p(indices),
+                                           wptr, start, end))
+
+
+def eval_patches(src: np.ndarray, src_desc, dsts: Sequence[Optional[np.ndarray]], dst_descs,
+                 coords: np.ndarray, arrays: np.ndarray, indices: np.ndarray, params: np.ndarray) -> bool:
+    """Restates Osd::CpuEvaluator::EvalPatches (osd/cpuEvaluator.cpp:157-381)."""
+    nw = len(dsts)
+    sd, dd = _descs([src_desc]), _descs(dst_descs)
+    dptr = (C.c_void_p * nw)(*[None if d is None else d.ctypes.data for d in dsts])
+    return bool(lib().oracle_eval_patches(nw, _p(src), _p(sd), dptr, _p(dd), len(coords), _p(coords), _p(arrays),
+                                          _p(indices), _p(params)))
+
+
+def patch_basis(patch_type: int, field0: int, field1: int, s: float, t: float, nw: int = 6):
+    """Restates OsdEvaluatePatchBasis (osd/patchBasis.h:1555-1610)."""
+    w = [np.zeros(20, dtype=np.float32) for _ in range(6)]
+    ptrs = [_p(x) for x in w[:nw]] + [None] * (6 - nw)
+    n = lib().oracle_patch_basis(patch_type, int(field0) & 0xFFFFFFFF, int(field1) & 0xFFFFFFFF, s, t, *ptrs)
+    return n, w[:nw]
