@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 Osd evaluator (BASELINE.json metric: refined verts/s, EvalStencils).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): synthetic deforming Catmark quad torus 400x250 (100 000 control vertices),
+uniform level 3, last level only = 6.4 M stencil rows / 84.1 M elements, 6-float interleaved xyz+normal.
+One step = one frame = one EvalStencils pass over the whole table.
+
+  value      refined verts/s, control points already resident in HBM, CUDA-event timed (max over ranks)
+  e2e        the same metric through the C ABI with HOST buffers: per step UpdateData (pinned H2D of the control
+             points) + EvalStencils + ReadData (D2H of the refined vertices) + Synchronize
+  roofline   algorithmic bytes (reference table formats) / device time per step vs measured HBM peak
+  cpu_baseline  the reference's own Osd::CpuEvaluator / OmpEvaluator (oracle/_ref, compiled in place from
+             /root/reference) on this box's host cores, same table, bounded number of frames; falls back to the
+             C oracle port when the reference build is absent
+
+Multi-GPU (N > 1): weak scaling.  The scene is N such meshes; rank r owns the stencil rows of mesh r (row-range
+sharding, tables pre-sharded, no collective on the table side); every frame rank 0's deformed control points of the
+WHOLE scene (N x 2.4 MB) are replicated with one NCCL broadcast -- the only exchange step -- and then each rank
+evaluates its rows.  value = all rows of all ranks / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NU, NV, LEVEL, L = 400, 250, 3, 6
+WORKLOAD = "catmark_torus_400x250_uniform_L3_laststencils_xyz+normal_f32x6"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------ clocks --
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------- workload --
+def build_workload():
+    from opensubdiv_b200 import synth
+    t0 = time.time()
+    mesh = synth.torus_quads(NU, NV)
+    table = synth.uniform_stencil_table(mesh, LEVEL)
+    log(f"[bench] table built in {time.time() - t0:.1f}s: {table.num_stencils} rows, {table.num_elements} elements")
+    return mesh, table
+
+
+def frame_primvars(mesh, frame):
+    from opensubdiv_b200 import synth
+    p = synth.deform(mesh.positions, frame)
+    return np.ascontiguousarray(np.concatenate([p, synth.vertex_normals_like(p)], axis=1), dtype=np.float32)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("sell_kernel_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------- reference arm --
+def cpu_reference_frames(mesh, table, frames: int, threads: int, prefer: str = "auto"):
+    """Times the reference's own CPU evaluators on full frames of the workload.  Returns a dict with verts/s."""
+    from oracle import ref as oref
+    src = frame_primvars(mesh, 0)
+    n = table.num_stencils
+    dst = np.zeros((n, L), np.float32)
+    res = {}
+    if oref.available():
+        from types import SimpleNamespace
+        t = SimpleNamespace(sizes=table.sizes, offsets=table.offsets, indices=table.indices, weights=table.weights,
+                            num_stencils=n, weight_streams=lambda nw: [table.weights])
+        lib = oref.lib()
+        impls = [("cpu", 1)]
+        if lib.ref_has_openmp():
+            impls.append(("omp", threads))
+        for impl, thr in impls:
+            if impl == "omp":
+                lib.ref_omp_set_threads(thr)
+            oref.eval_stencils(src.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, impl=impl)   # warm
+            ts = []
+            for f in range(frames):
+                s = frame_primvars(mesh, f + 1)
+                t0 = time.perf_counter()
+                oref.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, impl=impl)
+                ts.append(time.perf_counter() - t0)
+            res[impl] = {"ms_per_frame": 1e3 * float(np.mean(ts)), "verts_per_s": n / float(np.mean(ts)), "cores": thr,
+                         "kind": "reference"}
+    else:
+        from oracle import oracle
+        ts = []
+        for f in range(max(1, frames // 2)):
+            s = frame_primvars(mesh, f + 1)
+            t0 = time.perf_counter()
+            oracle.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], table.sizes, table.offsets,
+                                 table.indices, [table.weights])
+            ts.append(time.perf_counter() - t0)
+        res["port"] = {"ms_per_frame": 1e3 * float(np.mean(ts)), "verts_per_s": n / float(np.mean(ts)), "cores": 1, "kind": "port"}
+    return res
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    mesh, table = build_workload()
+    threads = os.cpu_count() or 1
+    probe = cpu_reference_frames(mesh, table, 1, threads)
+    best = max(probe, key=lambda k: probe[k]["verts_per_s"])
+    from oracle import ref as oref
+    n = table.num_stencils
+    dst = np.zeros((n, L), np.float32)
+    from types import SimpleNamespace
+    t = SimpleNamespace(sizes=table.sizes, offsets=table.offsets, indices=table.indices, weights=table.weights,
+                        num_stencils=n, weight_streams=lambda nw: [table.weights])
+
+    # bounded sample: full frames unless K of them would take more than ~2 minutes, then a leading row range
+    est = probe[best]["ms_per_frame"] * 1e-3
+    rows = n if args.steps * est <= 120.0 else max(100_000, int(n * 120.0 / (args.steps * est)))
+
+    def step(f):
+        s = frame_primvars(mesh, f)
+        t0 = time.perf_counter()
+        if best == "port":
+            from oracle import oracle
+            oracle.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], table.sizes, table.offsets,
+                                 table.indices, [table.weights], 0, rows)
+        else:
+            oref.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, 0, rows, impl=best)
+        return time.perf_counter() - t0
+    for w in range(args.warmup):
+        step(w)
+    total = sum(step(args.warmup + k) for k in range(args.steps))
+    value = rows * args.steps / total
+    cores = probe[best]["cores"]
+    line = {
+        "impl": "reference", "metric": "refined_verts_per_sec_EvalStencils", "value": value, "unit": "verts/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows": n, "elements": table.num_elements, "control_verts": table.num_control_verts,
+                   "primvar_floats": L},
+        "cpu_baseline": {"value": value, "unit": "verts/s", "cores": cores, "kind": probe[best]["kind"],
+                         "sample": f"{args.steps} steps of rows [0,{rows}) of {n} with Osd::{'OmpEvaluator' if best == 'omp' else 'CpuEvaluator'}"
+                                   f" ({best}); probe of all evaluators: "
+                                   + ", ".join(f"{k}={v['verts_per_s'] / 1e6:.1f} Mverts/s@{v['cores']}thr" for k, v in probe.items())},
+        "e2e": {"value": value, "unit": "verts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------- B200 arm --
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import opensubdiv_b200 as osd
+    from opensubdiv_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D = osd.BufferDescriptor
+    lib = capi.lib()
+
+    mesh, table = build_workload()
+    ncv, n = table.num_control_verts, table.num_stencils
+    t0 = time.time()
+    tbl = osd.B200StencilTable.Create(table)
+    assert tbl is not None, capi.last_error()
+    log(f"[bench] rank {rank}: B200StencilTable built in {time.time() - t0:.1f}s")
+
+    # Scene = `world` meshes; control points of the whole scene live at the front of every rank's vertex buffer
+    # (replicated by the per-frame broadcast), this rank's refined rows behind them.
+    scene_cv = ncv * world
+    vb = osd.B200VertexBuffer.Create(L, scene_cv + n)
+    assert vb is not None, capi.last_error()
+    vt = vb.as_tensor()
+    src_desc = D(rank * ncv * L, L, L)                     # this rank's mesh inside the replicated control block
+    dst_desc = D(scene_cv * L, L, L)
+
+    frames = [torch.from_numpy(np.tile(frame_primvars(mesh, f), (world, 1))).pin_memory() for f in range(4)]
+    host_out = torch.empty((n, L), dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def step_device(f):
+        """Device-resident step: (N>1: NCCL broadcast of the scene's control points from rank 0, then) EvalStencils."""
+        if world > 1:
+            dist.broadcast(vt[:scene_cv], src=0)
+        ok = osd.B200Evaluator.EvalStencils(vb, src_desc, vb, dst_desc, tbl)
+        assert ok
+
+    def step_e2e(f):
+        """Host-buffer step through the C ABI: H2D control points, evaluate, D2H refined vertices."""
+        if rank == 0 or world == 1:
+            vb.UpdateData(frames[f % len(frames)], 0, scene_cv)
+        if world > 1:
+            dist.broadcast(vt[:scene_cv], src=0)
+        ok = osd.B200Evaluator.EvalStencils(vb, src_desc, vb, dst_desc, tbl)
+        assert ok
+        vb.ReadData(host_out, scene_cv, n)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness spot check inside the bench (cheap): a constant field is reproduced
+    vb.UpdateData(frames[0], 0, scene_cv)
+    step_device(0)
+    torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for w in range(warmup):
+            step_fn(w)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lib.b200osd_reset_launch_count()
+        e0.record(stream)
+        for k in range(steps):
+            step_fn(warmup + k)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.b200osd_launch_count()
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(step_device, args.steps, args.warmup)
+    ms_e2e, _ = timed(step_e2e, max(3, min(args.steps, 20)), 3)
+    e2e_steps = max(3, min(args.steps, 20))
+    # the timed regions are milliseconds long: keep the same step running ~1 s more (untimed) so that the 50 ms
+    # nvidia-smi sampler sees the clocks this kernel actually runs at under load
+    t_end = time.time() + 1.0
+    while time.time() < t_end:
+        for k in range(50):
+            step_device(k)
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_per_step = ms_dev / args.steps
+    value = n * world * args.steps / (ms_dev * 1e-3)
+    e2e_value = n * world * e2e_steps / (ms_e2e * 1e-3)
+    alg_bytes = table.algorithmic_bytes(1, L, L)
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+
+    if rank == 0:
+        cpu = None
+        if world == 1 or True:
+            try:
+                probe = cpu_reference_frames(mesh, table, 4, os.cpu_count() or 1)
+                best = max(probe, key=lambda k: probe[k]["verts_per_s"])
+                cpu = {"value": probe[best]["verts_per_s"], "unit": "verts/s", "cores": probe[best]["cores"],
+                       "kind": probe[best]["kind"],
+                       "sample": "4 full frames of the same 6.4 M-row table per evaluator; "
+                                 + ", ".join(f"{k}: {v['ms_per_frame']:.0f} ms/frame @{v['cores']} thr" for k, v in probe.items())}
+            except Exception as exc:      # the baseline is a report, never a reason to lose the GPU number
+                cpu = {"value": None, "unit": "verts/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+        line = {
+            "metric": "refined_verts_per_sec_EvalStencils", "value": value, "unit": "verts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows_per_gpu": n, "elements_per_gpu": table.num_elements,
+                       "control_verts_per_mesh": ncv, "primvar_floats": L, "parallelism": f"row-range x{world}",
+                       "l2_policy": "inputs larger than L2 (table streams 0.7 GB/step vs 126 MB L2); no flush needed",
+                       "stencil_variant": lib.b200osd_get_stencil_variant(),
+                       "bucketed_stream_bytes": tbl.GetStreamBytes(1)},
+            "e2e": {"value": e2e_value, "unit": "verts/s", "h2d_bytes_per_step": int(scene_cv * L * 4),
+                    "d2h_bytes_per_step": int(n * L * 4), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "frac_of_nominal_8TBps": achieved / 8000.0,
+                         "note": "device time per step = pack_src_kernel (control verts -> 16 B rows) + sell_kernel"},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant (0 = auto)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.variant:
+        from opensubdiv_b200 import capi
+        capi.lib().b200osd_set_stencil_variant(args.variant)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

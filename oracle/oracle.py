@@ -28,7 +28,7 @@ def build(force: bool = False) -> str:
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(SRC_PATH):
         cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
         subprocess.check_call([cc, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c99", "-Wall",
-                               "-o", LIB_PATH, SRC_PATH])
+                               "-o", LIB_PATH, SRC_PATH, "-lm"])
     return LIB_PATH
 
 
@@ -42,6 +42,7 @@ def lib():
         L.oracle_eval_patches.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
         L.oracle_patch_basis.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_float] + [vp] * 6
         L.oracle_version.restype = C.c_char_p
+        L.oracle_set_abs_mode.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -83,3 +84,13 @@ def patch_basis(patch_type: int, field0: int, field1: int, s: float, t: float, n
     ptrs = [_p(x) for x in w[:nw]] + [None] * (6 - nw)
     n = lib().oracle_patch_basis(patch_type, int(field0) & 0xFFFFFFFF, int(field1) & 0xFFFFFFFF, s, t, *ptrs)
     return n, w[:nw]
+
+
+class abs_mode:
+    """Context manager: inside it eval_stencils / eval_patches return S = sum_j |w_j| |x_j| (the tolerance scale)."""
+
+    def __enter__(self):
+        lib().oracle_set_abs_mode(1)
+
+    def __exit__(self, *exc):
+        lib().oracle_set_abs_mode(0)

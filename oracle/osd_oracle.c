@@ -23,8 +23,15 @@
  *   osd/patchBasisTypes.h:241-426 patch descriptor ids, PatchParam bit fields, (s,t) normalisation
  *   osd/patchBasis.h:53-1610      the six bases, boundary folding, derivative scaling
  */
+#include <math.h>
 #include <stddef.h>
 #include <string.h>
+
+/* Tolerance scale mode (tests only): when set, every accumulation uses |value| * |weight|, so the evaluators
+ * return S = sum_j |w_j| |x_j| -- the magnitude against which a 1e-6 relative bound is meaningful when signed
+ * derivative weights cancel ("Parity at 1e-6 relative"). */
+static int g_abs_mode = 0;
+void oracle_set_abs_mode(int on) { g_abs_mode = on; }
 
 #define ORACLE_MAX_LEN 64          /* max primvar length handled by the stack temporaries */
 
@@ -72,7 +79,8 @@ int oracle_eval_stencils(int nw,
             const float *v = src + (ptrdiff_t)indices[off + j] * srcDesc->stride;
             for (w = 0; w < nw; ++w) {
                 float wt = weights[w][off + j];
-                for (k = 0; k < L; ++k) acc[w][k] += v[k] * wt;        /* addWithWeight, cpuKernel.cpp:52-61 */
+                if (g_abs_mode) { for (k = 0; k < L; ++k) acc[w][k] += fabsf(v[k]) * fabsf(wt); }
+                else            { for (k = 0; k < L; ++k) acc[w][k] += v[k] * wt; }   /* addWithWeight, cpuKernel.cpp:52-61 */
             }
         }
         for (w = 0; w < nw; ++w) {
@@ -591,7 +599,8 @@ int oracle_eval_patches(int nw,
             for (k = 0; k < L; ++k) acc[k] = 0.0f;
             for (j = 0; j < n; ++j) {
                 const float *v = src + (ptrdiff_t)cvs[j] * srcDesc->stride;
-                for (k = 0; k < L; ++k) acc[k] += v[k] * wbuf[q][j];
+                if (g_abs_mode) { for (k = 0; k < L; ++k) acc[k] += fabsf(v[k]) * fabsf(wbuf[q][j]); }
+                else            { for (k = 0; k < L; ++k) acc[k] += v[k] * wbuf[q][j]; }
             }
             memcpy(dsts[q] + dstDescs[q].offset + (ptrdiff_t)i * dstDescs[q].stride, acc, (size_t)L * sizeof(float));
         }

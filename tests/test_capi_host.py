@@ -1,0 +1,77 @@
+"""CPU-side checks of the product's host layer: the C-ABI library loads and exports every declared symbol, argument
+validation mirrors the reference, and nothing silently falls back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import opensubdiv_b200 as osd
+from opensubdiv_b200 import capi
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "b200osd_capi.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200osd_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    lib = capi.lib()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(capi.SYMBOLS) == declared
+
+
+def test_pod_layouts_match_reference_sizes():
+    assert osd.PATCH_COORD_DTYPE.itemsize == 20      # osd/types.h:42-64
+    assert osd.PATCH_ARRAY_DTYPE.itemsize == 24      # osd/types.h:66-122
+    assert osd.PATCH_PARAM_DTYPE.itemsize == 12      # osd/types.h:127-130
+
+
+def test_buffer_descriptor_semantics():
+    d = osd.BufferDescriptor(16, 3, 13)              # osd/bufferDescriptor.h:71-78
+    assert d.GetLocalOffset() == 3 and d.IsValid()
+    assert not osd.BufferDescriptor(11, 3, 13).IsValid()
+    assert not osd.BufferDescriptor().IsValid()
+
+
+def test_validation_happens_before_any_device_work():
+    """These return the reference's `false` (ERR_INVALID) without touching CUDA, so they are checkable on CPU."""
+    lib = capi.lib()
+    sd = (C.c_int * 3)(0, 3, 3)
+    dd = (C.c_int * 3)(0, 4, 4)
+    dsts = (C.c_void_p * 1)(1 << 20)
+    w = (C.c_void_p * 1)(1 << 20)
+    # length mismatch -> false (osd/cpuEvaluator.cpp:47)
+    assert lib.b200osd_eval_stencils(1 << 20, sd, 1, dsts, dd, 1 << 20, 1 << 20, 1 << 20, w, 0, 10, None) == capi.ERR_INVALID
+    # end <= start -> true, no-op (osd/cpuEvaluator.cpp:46)
+    assert lib.b200osd_eval_stencils(1 << 20, sd, 1, dsts, dd, 1 << 20, 1 << 20, 1 << 20, w, 7, 7, None) == capi.OK
+    # NULL dst in the value-only form -> false (osd/cudaEvaluator.cpp:159)
+    nul = (C.c_void_p * 1)(None)
+    dd3 = (C.c_int * 3)(0, 3, 3)
+    assert lib.b200osd_eval_stencils(1 << 20, sd, 1, nul, dd3, 1 << 20, 1 << 20, 1 << 20, w, 0, 10, None) == capi.ERR_INVALID
+    # EvalPatches: NULL src -> false (osd/cpuEvaluator.cpp:165-169)
+    assert lib.b200osd_eval_patches(None, sd, 1, dsts, dd3, 5, 1 << 20, 1 << 20, 1 << 20, 1 << 20, None) == capi.ERR_INVALID
+    assert lib.b200osd_eval_patches(1 << 20, sd, 2, dsts, dd3, 5, 1 << 20, 1 << 20, 1 << 20, 1 << 20, None) == capi.ERR_INVALID
+    assert b"nOut" in lib.b200osd_last_error()
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert osd.B200VertexBuffer.Create(3, 16) is None          # Create() -> NULL like the reference, never a host buffer
+    assert "cuda" in capi.last_error().lower()
+    t = type("T", (), dict(sizes=np.array([1], np.int32), offsets=np.array([0], np.int32),
+                           indices=np.array([0], np.int32), weights=np.array([1.0], np.float32)))()
+    assert osd.B200StencilTable.Create(t) is None
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "opensubdiv_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower().replace("no reference code involved", ""), f

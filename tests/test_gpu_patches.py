@@ -1,0 +1,196 @@
+"""EvalPatches / EvalPatchesVarying / EvalPatchesFaceVarying parity on a real B200 (through the C ABI) vs the oracle
+and the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+import opensubdiv_b200 as osd
+from opensubdiv_b200 import synth
+from tests.gpu_util import D, dev, coords_dev, oracle_patches, oracle_stencils
+from tests.util import golden, golden_names, table_from, triple_from, assert_close, REL_TOL
+
+pytestmark = pytest.mark.gpu
+OUT6 = ("p", "du", "dv", "duu", "duv", "dvv")
+
+
+class _PT:
+    def __init__(self, vertex, varying=None, fvar=None):
+        self.vertex, self.varying, self.fvar = vertex, varying, fvar or []
+
+
+@pytest.mark.parametrize("name", golden_names("patches_"))
+def test_golden_patch_tables_all_arities(name):
+    d = golden(name)
+    vtx = triple_from(d, "vtx_")
+    var = triple_from(d, "var_") if "var_arrays" in d.files else None
+    fv = triple_from(d, "fvar_") if "fvar_arrays" in d.files else None
+    pt = osd.B200PatchTable.Create(_PT(vtx, var, [fv] if fv is not None else []))
+    assert pt is not None
+    coords = d["coords"]
+    n = len(coords)
+    pc = coords_dev(coords)
+    src = dev(d["vb"])
+    scales = oracle_patches(d["vb"], (0, 3, 3), 3, coords, vtx, 6, abs_scale=True)
+    for nw in (1, 3, 6):
+        # outputs interleaved in one buffer, glEvalLimit style (examples/glEvalLimit/glEvalLimit.cpp:277-287)
+        out = torch.full((n, 3 * nw), float("nan"), device="cuda")
+        args = []
+        for k in range(nw):
+            args += [out, D(3 * k, 3, 3 * nw)]
+        assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+        res = out.cpu().numpy()
+        for k in range(nw):
+            assert_close(res[:, 3 * k:3 * k + 3], d["out_" + OUT6[k]], scales[k], f"{name} nw={nw} {OUT6[k]}")
+    if var is not None:
+        vsrc = dev(d["var_vb"])
+        vs = oracle_patches(d["var_vb"], (0, 3, 3), 3, coords, var, 3, abs_scale=True)
+        outs = [torch.zeros((n, 3), device="cuda") for _ in range(3)]
+        args = []
+        for o in outs:
+            args += [o, D(0, 3, 3)]
+        assert osd.B200Evaluator.EvalPatchesVarying(vsrc, D(0, 3, 3), *args, n, pc, pt, None)
+        for k in range(3):
+            assert_close(outs[k].cpu().numpy(), d["var_out_" + OUT6[k]], vs[k], f"{name} varying {OUT6[k]}")
+    if fv is not None:
+        fsrc = dev(d["fvar_vb"])
+        fs = oracle_patches(d["fvar_vb"], (0, 2, 2), 2, coords, fv, 6, abs_scale=True)
+        outs = [torch.zeros((n, 2), device="cuda") for _ in range(6)]
+        args = []
+        for o in outs:
+            args += [o, D(0, 2, 2)]
+        assert osd.B200Evaluator.EvalPatchesFaceVarying(fsrc, D(0, 2, 2), *args, n, pc, pt, 0, None)
+        for k in range(6):
+            assert_close(outs[k].cpu().numpy(), d["fvar_out_" + OUT6[k]], fs[k], f"{name} fvar {OUT6[k]}")
+
+
+def test_refine_then_evaluate_pipeline():
+    """The glEvalLimit frame: UpdateData(cv) -> EvalStencils incl. end-cap local points -> EvalPatches (glEvalLimit.cpp:371-449)."""
+    d = golden("patches_catmark_car")
+    st = table_from(d, "st_")
+    vtx = triple_from(d, "vtx_")
+    ncv, n = st.num_control_verts, st.num_stencils
+    vb = osd.B200VertexBuffer.Create(3, ncv + n)
+    vb.UpdateData(np.ascontiguousarray(d["src0"]), 0, ncv)
+    stbl = osd.B200StencilTable.Create(st)
+    assert osd.B200Evaluator.EvalStencils(vb, D(0, 3, 3), vb, D(ncv * 3, 3, 3), stbl)
+    pt = osd.B200PatchTable.Create(_PT(vtx))
+    coords = d["coords"]
+    out = osd.B200VertexBuffer.Create(18, len(coords))
+    args = []
+    for k in range(6):
+        args += [out, D(3 * k, 3, 18)]
+    assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, len(coords), coords_dev(coords), pt, None)
+    osd.B200Evaluator.Synchronize()
+    res = np.zeros((len(coords), 18), np.float32)
+    out.ReadData(res, 0, len(coords))
+    osd.B200Evaluator.Synchronize()
+    scales = oracle_patches(d["vb"], (0, 3, 3), 3, coords, vtx, 6, abs_scale=True)
+    for k in range(6):
+        assert_close(res[:, 3 * k:3 * k + 3], d["out_" + OUT6[k]], scales[k] * 1.5 + 1e-6, f"pipeline {OUT6[k]}")
+
+
+@pytest.mark.parametrize("L,stride,offset", [(1, 1, 0), (2, 2, 0), (4, 4, 0), (6, 6, 0), (3, 5, 2), (9, 12, 1)])
+def test_primvar_lengths_and_null_outputs(L, stride, offset):
+    d = golden("patches_catmark_gregory_test2")
+    vtx = triple_from(d, "vtx_")
+    coords = d["coords"]
+    n = len(coords)
+    nv = len(d["vb"])
+    rng = np.random.default_rng(L)
+    src = rng.standard_normal(offset + nv * stride + 3).astype(np.float32)
+    exp = oracle_patches(src, (offset, L, stride), L, coords, vtx, 6)
+    scl = oracle_patches(src, (offset, L, stride), L, coords, vtx, 6, abs_scale=True)
+    pt = osd.B200PatchTable.Create(_PT(vtx))
+    outs = [torch.full((n, L), float("nan"), device="cuda") for _ in range(6)]
+    # NULL du and dvv are skipped (osd/cudaKernel.cu:300-327)
+    bufs = [outs[0], None, outs[2], outs[3], outs[4], None]
+    args = []
+    for b in bufs:
+        args += [b, D(0, L, L)]
+    assert osd.B200Evaluator.EvalPatches(dev(src), D(offset, L, stride), *args, n, coords_dev(coords), pt, None)
+    for k in (0, 2, 3, 4):
+        assert_close(outs[k].cpu().numpy(), exp[k], scl[k], f"L={L} {OUT6[k]}")
+    assert torch.isnan(outs[1]).all() and torch.isnan(outs[5]).all()
+    # errors: NULL src, value-only NULL dst, length mismatch -> false (osd/cpuEvaluator.cpp:165-176)
+    assert not osd.B200Evaluator.EvalPatches(None, D(0, L, L), outs[0], D(0, L, L), n, coords_dev(coords), pt, None)
+    assert not osd.B200Evaluator.EvalPatches(dev(src), D(0, L, stride), None, D(0, L, L), n, coords_dev(coords), pt, None)
+    assert not osd.B200Evaluator.EvalPatches(dev(src), D(0, L, stride), outs[0], D(0, L + 1, L + 1), n, coords_dev(coords), pt, None)
+    assert osd.B200Evaluator.EvalPatches(dev(src), D(0, L, stride), outs[0], D(0, L, L), 0, coords_dev(coords), pt, None)   # empty
+
+
+@pytest.fixture(scope="module")
+def torus_patches():
+    mesh = synth.torus_quads(400, 250)
+    ptab = synth.torus_patch_table(mesh)
+    pt = osd.B200PatchTable.Create(ptab)
+    return mesh, ptab, pt
+
+
+@pytest.mark.slow
+def test_ten_million_random_coords_vs_oracle_and_order_independence(torus_patches):
+    """Config-4-sized run: 10 M random PatchCoords, P + 1st + 2nd derivatives."""
+    mesh, ptab, pt = torus_patches
+    n = 10_000_000
+    coords = synth.random_patch_coords(len(mesh.faces), n, seed=2024)
+    src_np = synth.deform(mesh.positions, 3)
+    src = dev(src_np)
+    pc = coords_dev(coords)
+    out = torch.empty((n, 18), device="cuda")
+    args = []
+    for k in range(6):
+        args += [out, D(3 * k, 3, 18)]
+    assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+    # oracle on a bounded sample of the same coords
+    rng = np.random.default_rng(5)
+    pick = np.sort(rng.choice(n, 200_000, replace=False))
+    exp = oracle_patches(src_np, (0, 3, 3), 3, coords[pick], ptab.vertex, 6)
+    scl = oracle_patches(src_np, (0, 3, 3), 3, coords[pick], ptab.vertex, 6, abs_scale=True)
+    got = out[torch.from_numpy(pick).cuda()].cpu().numpy()
+    for k in range(6):
+        assert_close(got[:, 3 * k:3 * k + 3], exp[k], scl[k], f"10M {OUT6[k]}")
+    # the same coords sorted by patch must give identical bits per coordinate
+    order = np.argsort(coords["patchIndex"], kind="stable")
+    out2 = torch.empty((n, 18), device="cuda")
+    args2 = []
+    for k in range(6):
+        args2 += [out2, D(3 * k, 3, 18)]
+    assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args2, n, coords_dev(coords[order]), pt, None)
+    assert torch.equal(out2, out[torch.from_numpy(order).cuda()])
+    # partition of unity: constant field -> P = const, all derivatives ~ 0
+    const = torch.full((mesh.num_verts, 3), 1.25, device="cuda")
+    assert osd.B200Evaluator.EvalPatches(const, D(0, 3, 3), *args, n, pc, pt, None)
+    assert (out[:, 0:3] - 1.25).abs().max().item() <= 1.25 * 2 * REL_TOL
+    assert out[:, 3:].abs().max().item() <= 1e-5
+
+
+@pytest.mark.slow
+def test_limit_stencils_agree_with_patch_evaluation_on_gpu(torus_patches):
+    """Two independent GPU paths that must agree: LimitStencilTable rows (EvalStencils, 6 weight streams) and
+    EvalPatches at the same (face, s, t)."""
+    mesh, ptab, pt = torus_patches
+    n = 1_000_000
+    rng = np.random.default_rng(12345)
+    face = np.sort(rng.integers(0, len(mesh.faces), n)).astype(np.int32)
+    s, t = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+    ls = synth.torus_limit_stencil_table(mesh, face, s, t)
+    stbl = osd.B200StencilTable.Create(ls)
+    src = dev(mesh.positions)
+    a = torch.empty((n, 18), device="cuda")
+    b = torch.empty((n, 18), device="cuda")
+    args_a, args_b = [], []
+    for k in range(6):
+        args_a += [a, D(3 * k, 3, 18)]
+        args_b += [b, D(3 * k, 3, 18)]
+    assert osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), *args_a, stbl)
+    coords = np.zeros(n, osd.PATCH_COORD_DTYPE)
+    coords["patchIndex"] = face
+    coords["vertIndex"] = face * 16
+    coords["s"], coords["t"] = s, t
+    assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args_b, n, coords_dev(coords), pt, None)
+    assert (a - b).abs().max().item() <= 2e-5
+    # and the stencil side against the oracle on a window
+    exp = oracle_stencils(mesh.positions, (0, 3, 3), n, 3, ls, 6, 0, 20000)
+    scl = oracle_stencils(mesh.positions, (0, 3, 3), n, 3, ls, 6, 0, 20000, abs_scale=True)
+    got = a[:20000].cpu().numpy()
+    for k in range(6):
+        assert_close(got[:, 3 * k:3 * k + 3], exp[k][:20000], scl[k][:20000], f"limit {OUT6[k]}")

@@ -1,0 +1,246 @@
+"""EvalStencils parity on a real B200: CUDA path (through the C ABI) vs the oracle and the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+import opensubdiv_b200 as osd
+from opensubdiv_b200 import synth
+from tests.gpu_util import D, dev, set_variant, oracle_stencils
+from tests.util import golden, golden_names, table_from, assert_close, REL_TOL
+
+pytestmark = pytest.mark.gpu
+OUT6 = ("p", "du", "dv", "duu", "duv", "dvv")
+VARIANTS = (0, 1, 2, 3)        # auto, CSR kernel on the table, bucketed w/ scalar gathers, bucketed w/ packed gathers
+
+
+def refine_same_buffer(t, src, L, variant=0):
+    """Osd::Mesh::Refine layout: one buffer [control | refined], src and dst descriptors into it (osd/mesh.h:505-519)."""
+    ncv, n = t.num_control_verts, t.num_stencils
+    vb = osd.B200VertexBuffer.Create(L, ncv + n)
+    vb.UpdateData(np.ascontiguousarray(src, np.float32), 0, ncv)
+    tbl = osd.B200StencilTable.Create(t)
+    assert tbl is not None and tbl.GetNumStencils() == n
+    set_variant(variant)
+    try:
+        assert osd.B200Evaluator.EvalStencils(vb, D(0, L, L), vb, D(ncv * L, L, L), tbl)
+    finally:
+        set_variant(0)
+    osd.B200Evaluator.Synchronize()
+    return vb.as_tensor()[ncv:].cpu().numpy()
+
+
+def test_config1_catmark_cube_level4():
+    """BASELINE config 1: catmark_cube, uniform level 4, float3 xyz -- vs CpuEvaluator output and the Hbr golden file."""
+    d = golden("catmark_cube_L4")
+    for which in ("last_", "all_"):
+        t = table_from(d, which)
+        scale = oracle_stencils(d["src"], (0, 3, 3), t.num_stencils, 3, t, 1, abs_scale=True)[0]
+        for v in VARIANTS:
+            out = refine_same_buffer(t, d["src"], 3, v)
+            assert_close(out, d[which + "out"], scale, f"cube {which} variant {v}")
+    out = refine_same_buffer(table_from(d, "last_"), d["src"], 3).astype(np.float64)
+    hbr = d["hbr_level3"].astype(np.float64)
+    dist = np.sqrt(((out[:, None, :] - hbr[None, :, :]) ** 2).sum(-1)).min(axis=1)
+    assert dist.max() <= 1e-6          # the reference's own tolerance (regression/osd_regression/main.cpp:53)
+
+
+@pytest.mark.parametrize("name", golden_names("stencils_"))
+def test_regression_shapes_vertex_and_varying(name):
+    d = golden(name)
+    L = d["src"].shape[1]
+    for prefix, key in (("t_", "out"), ("v_", "v_out")):
+        t = table_from(d, prefix)
+        scale = oracle_stencils(d["src"], (0, L, L), t.num_stencils, L, t, 1, abs_scale=True)[0]
+        for v in VARIANTS:
+            assert_close(refine_same_buffer(t, d["src"], L, v), d[key], scale, f"{name} {prefix} variant {v}")
+
+
+@pytest.mark.parametrize("name", golden_names("limit_"))
+@pytest.mark.parametrize("nw", [1, 3, 6])
+def test_limit_stencils_with_derivatives(name, nw):
+    """LimitStencilTable with du/dv/duu/duv/dvv, outputs interleaved in ONE buffer addressed by different descriptors
+    (examples/glStencilViewer/glStencilViewer.cpp:188-191)."""
+    d = golden(name)
+    t = table_from(d, "t_")
+    n = t.num_stencils
+    src = dev(d["src"])
+    tbl = osd.B200StencilTable.Create(t)
+    scales = oracle_stencils(d["src"], (0, 3, 3), n, 3, t, nw, abs_scale=True)
+    for v in VARIANTS:
+        out = torch.full((n, 3 * nw), float("nan"), device="cuda")
+        args = []
+        for k in range(nw):
+            args += [out, D(3 * k, 3, 3 * nw)]
+        set_variant(v)
+        assert osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), *args, tbl)
+        set_variant(0)
+        res = out.cpu().numpy()
+        for k in range(nw):
+            assert_close(res[:, 3 * k:3 * k + 3], d["out_" + OUT6[k]], scales[k], f"{name} {OUT6[k]} variant {v}")
+    # raw-pointer overload on the reference-layout device arrays (osd/cudaEvaluator.h:449-466)
+    outs = [torch.zeros((n, 3), device="cuda") for _ in range(nw)]
+    ws = [tbl.GetWeightsBuffer(), tbl.GetDuWeightsBuffer(), tbl.GetDvWeightsBuffer(), tbl.GetDuuWeightsBuffer(),
+          tbl.GetDuvWeightsBuffer(), tbl.GetDvvWeightsBuffer()][:nw]
+    assert osd.B200Evaluator.EvalStencilsRaw(src, D(0, 3, 3), [(o, D(0, 3, 3)) for o in outs], tbl.GetSizesBuffer(),
+                                             tbl.GetOffsetsBuffer(), tbl.GetIndicesBuffer(), ws, 0, n)
+    for k in range(nw):
+        assert_close(outs[k].cpu().numpy(), d["out_" + OUT6[k]], scales[k], f"{name} raw {OUT6[k]}")
+
+
+@pytest.mark.parametrize("L,stride,offset", [(1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (5, 5, 0), (6, 6, 0), (8, 8, 0),
+                                             (12, 12, 0), (3, 4, 1), (6, 9, 2), (4, 8, 4), (3, 7, 2), (1, 5, 4), (17, 20, 1)])
+def test_descriptors_lengths_strides_offsets(L, stride, offset):
+    d = golden("stencils_catmark_car")
+    t = table_from(d, "t_")
+    ncv, n = t.num_control_verts, t.num_stencils
+    rng = np.random.default_rng(L * 100 + stride)
+    src = rng.standard_normal(offset + ncv * stride + 4).astype(np.float32)
+    expect = np.full(offset + n * stride + 4, np.nan, np.float32)
+    from oracle import oracle
+    assert oracle.eval_stencils(src, (offset, L, stride), [expect], [(offset, L, stride)], t.sizes, t.offsets, t.indices,
+                                [t.weights])
+    scale = np.full_like(expect, np.nan)
+    with oracle.abs_mode():
+        oracle.eval_stencils(src, (offset, L, stride), [scale], [(offset, L, stride)], t.sizes, t.offsets, t.indices, [t.weights])
+    tbl = osd.B200StencilTable.Create(t)
+    for v in VARIANTS:
+        out = torch.full((len(expect),), float("nan"), device="cuda")
+        set_variant(v)
+        assert osd.B200Evaluator.EvalStencils(dev(src), D(offset, L, stride), out, D(offset, L, stride), tbl)
+        set_variant(0)
+        got = out.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(expect)), "wrote outside the described elements"
+        m = ~np.isnan(expect)
+        assert_close(got[m], expect[m], scale[m], f"L={L} stride={stride} off={offset} variant {v}")
+
+
+def test_row_ranges_noop_and_errors():
+    d = golden("stencils_catmark_car")
+    t = table_from(d, "t_")
+    n = t.num_stencils
+    src = dev(d["src"])
+    tbl = osd.B200StencilTable.Create(t)
+    full = oracle_stencils(d["src"], (0, 3, 3), n, 3, t, 1)[0]
+    scale = oracle_stencils(d["src"], (0, 3, 3), n, 3, t, 1, abs_scale=True)[0]
+    for (a, b) in [(0, n), (0, 1), (n - 1, n), (17, 4099), (2048, 4096), (2047, 2049), (5000, 5001)]:
+        for v in VARIANTS:
+            out = torch.full((n, 3), float("nan"), device="cuda")
+            set_variant(v)
+            assert osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), out, D(0, 3, 3), tbl, start=a, end=b)
+            set_variant(0)
+            got = out.cpu().numpy()
+            assert np.isnan(got[:a]).all() and np.isnan(got[b:]).all(), "rows outside [start,end) were written"
+            assert_close(got[a:b], full[a:b], scale[a:b], f"range {a}:{b} variant {v}")     # absolute row addressing
+    out = torch.full((n, 3), float("nan"), device="cuda")
+    assert osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), out, D(0, 3, 3), tbl, start=9, end=9)      # no-op -> true
+    assert torch.isnan(out).all()
+    assert not osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), out, D(0, 4, 4), tbl)                  # length mismatch -> false
+    assert not osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), None, D(0, 3, 3), tbl)                 # NULL dst -> false
+    assert torch.isnan(out).all()
+
+
+def test_empty_and_degenerate_tables():
+    empty = type("T", (), dict(sizes=np.zeros(0, np.int32), offsets=np.zeros(0, np.int32), indices=np.zeros(0, np.int32),
+                               weights=np.zeros(0, np.float32)))()
+    tbl = osd.B200StencilTable.Create(empty)
+    assert tbl is not None and tbl.GetNumStencils() == 0
+    out = torch.zeros(8, device="cuda")
+    assert osd.B200Evaluator.EvalStencils(out, D(0, 3, 3), out, D(0, 3, 3), tbl)
+    # rows of size 0 (weights sum to nothing -> zeros) mixed with a row of 300 terms
+    rng = np.random.default_rng(0)
+    sizes = np.array([0, 300, 0, 1, 33, 0], np.int32)
+    offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32)
+    ne = int(sizes.sum())
+    t = type("T", (), dict(num_control_verts=50, num_stencils=6, sizes=sizes, offsets=offsets,
+                           indices=rng.integers(0, 50, ne).astype(np.int32),
+                           weights=rng.standard_normal(ne).astype(np.float32), du=None, dv=None, duu=None, duv=None, dvv=None))()
+    src = rng.standard_normal((50, 3)).astype(np.float32)
+    exp = oracle_stencils(src, (0, 3, 3), 6, 3, t, 1)[0]
+    scale = oracle_stencils(src, (0, 3, 3), 6, 3, t, 1, abs_scale=True)[0]
+    tbl = osd.B200StencilTable.Create(t)
+    for v in VARIANTS:
+        out = torch.full((6, 3), float("nan"), device="cuda")
+        set_variant(v)
+        assert osd.B200Evaluator.EvalStencils(dev(src), D(0, 3, 3), out, D(0, 3, 3), tbl)
+        set_variant(0)
+        assert_close(out.cpu().numpy(), exp, np.maximum(scale, 1e-6), f"degenerate variant {v}")
+
+
+@pytest.fixture(scope="module")
+def config2():
+    """BASELINE config 2 at full size: Catmark torus 400x250 (100k control verts), uniform level 3, last level:
+    6.4 M rows / 84.1 M elements, 6-float interleaved xyz+normal."""
+    mesh = synth.torus_quads(400, 250)
+    table = synth.uniform_stencil_table(mesh, 3)
+    assert table.num_stencils == 6_400_000 and table.num_elements == 84_100_000
+    tbl = osd.B200StencilTable.Create(table)
+    assert tbl is not None
+    return mesh, table, tbl
+
+
+def _prim6(mesh, frame):
+    p = synth.deform(mesh.positions, frame)
+    return np.ascontiguousarray(np.concatenate([p, synth.vertex_normals_like(p)], axis=1), np.float32)
+
+
+@pytest.mark.slow
+def test_config2_full_size_frames_vs_oracle(config2):
+    mesh, table, tbl = config2
+    ncv, n = table.num_control_verts, table.num_stencils
+    vb = osd.B200VertexBuffer.Create(6, ncv + n)
+    rng = np.random.default_rng(0)
+    for frame in (0, 1, 17):
+        src = _prim6(mesh, frame)
+        vb.UpdateData(src, 0, ncv)
+        assert osd.B200Evaluator.EvalStencils(vb, D(0, 6, 6), vb, D(ncv * 6, 6, 6), tbl)
+        osd.B200Evaluator.Synchronize()
+        got = vb.as_tensor()[ncv:]
+        # oracle on three row windows (the whole table would take the scalar oracle ~1 s/frame -- also fine, but bounded here)
+        for a in (0, int(rng.integers(1, n - 70000)), n - 50000):
+            b = a + 50000
+            exp = np.zeros((n, 6), np.float32)
+            scl = np.zeros((n, 6), np.float32)
+            from oracle import oracle
+            assert oracle.eval_stencils(src.reshape(-1), (0, 6, 6), [exp.reshape(-1)], [(0, 6, 6)], table.sizes, table.offsets,
+                                        table.indices, [table.weights], a, b)
+            with oracle.abs_mode():
+                oracle.eval_stencils(src.reshape(-1), (0, 6, 6), [scl.reshape(-1)], [(0, 6, 6)], table.sizes, table.offsets,
+                                     table.indices, [table.weights], a, b)
+            assert_close(got[a:b].cpu().numpy(), exp[a:b], scl[a:b], f"frame {frame} rows {a}:{b}")
+
+
+@pytest.mark.slow
+def test_config2_size_independent_properties(config2):
+    mesh, table, tbl = config2
+    ncv, n = table.num_control_verts, table.num_stencils
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((ncv, 6), device="cuda", generator=g)
+    y = torch.randn((ncv, 6), device="cuda", generator=g)
+
+    def ev(src, variant=0):
+        out = torch.empty((n, 6), device="cuda")
+        set_variant(variant)
+        assert osd.B200Evaluator.EvalStencils(src, D(0, 6, 6), out, D(0, 6, 6), tbl)
+        set_variant(0)
+        return out
+    ex, ey = ev(x), ev(y)
+    # partition of unity: refinement weights are convex, a constant field is reproduced
+    const = torch.full((ncv, 6), 2.5, device="cuda")
+    assert (ev(const) - 2.5).abs().max().item() <= 2.5 * REL_TOL
+    # convexity: every refined value lies inside the control-value range
+    assert ex.max() <= x.max() + 1e-5 and ex.min() >= x.min() - 1e-5
+    # linearity
+    lin = ev(0.75 * x - 1.5 * y)
+    assert (lin - (0.75 * ex - 1.5 * ey)).abs().max().item() <= 2e-6 * max(1.0, lin.abs().max().item())
+    # every kernel variant and the raw reference-layout path agree
+    for v in (1, 2, 3):
+        assert (ev(x, v) - ex).abs().max().item() <= 2e-6
+    raw = torch.empty((n, 6), device="cuda")
+    assert osd.B200Evaluator.EvalStencilsRaw(x, D(0, 6, 6), [(raw, D(0, 6, 6))], tbl.GetSizesBuffer(), tbl.GetOffsetsBuffer(),
+                                             tbl.GetIndicesBuffer(), [tbl.GetWeightsBuffer()], 0, n)
+    assert (raw - ex).abs().max().item() <= 2e-6
+    # independent cross-check of the whole 6.4 M-row result: torch sparse CSR matmul of the same table
+    crow = torch.from_numpy(np.concatenate([table.offsets.astype(np.int64), [table.num_elements]])).cuda()
+    A = torch.sparse_csr_tensor(crow, torch.from_numpy(table.indices.astype(np.int64)).cuda(),
+                                torch.from_numpy(table.weights).cuda(), size=(n, ncv))
+    assert (A @ x - ex).abs().max().item() <= 5e-6

@@ -1,0 +1,109 @@
+"""The C oracle (oracle/osd_oracle.c) against the committed golden vectors, which were produced by the unmodified
+reference (tests/golden/make_golden.py) -- this is what pins the oracle on machines without /root/reference."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.util import golden, golden_names, table_from, triple_from, weight_streams, assert_close
+
+OUT6 = ("p", "du", "dv", "duu", "duv", "dvv")
+
+
+def run_refine(src, t, L):
+    ncv, n = t.num_control_verts, t.num_stencils
+    buf = np.zeros((ncv + n, L), np.float32)
+    buf[:ncv] = src
+    flat = buf.reshape(-1)
+    assert oracle.eval_stencils(flat, (0, L, L), [flat], [(ncv * L, L, L)], t.sizes, t.offsets, t.indices, [t.weights])
+    return buf[ncv:]
+
+
+def test_catmark_cube_level4_matches_cpu_evaluator_bit_exact():
+    d = golden("catmark_cube_L4")
+    for which in ("last_", "all_"):
+        t = table_from(d, which)
+        out = run_refine(d["src"], t, 3)
+        # same sequential order, separate multiply and add: identical bits to Osd::CpuEvaluator
+        assert np.array_equal(out, d[which + "out"])
+
+
+def test_catmark_cube_level4_matches_hbr_baseline():
+    """Config 1 against the reference's own golden file regression/hbr_regression/baseline/catmark_cube_level3.obj
+    (Hbr vertex order differs from Far's, so compare as point sets; reference tolerance 1e-6, osd_regression/main.cpp:53)."""
+    d = golden("catmark_cube_L4")
+    out = run_refine(d["src"], table_from(d, "last_"), 3).astype(np.float64)
+    hbr = d["hbr_level3"].astype(np.float64)
+    assert out.shape == hbr.shape == (1538, 3)
+    d2 = ((out[:, None, :] - hbr[None, :, :]) ** 2).sum(-1)
+    nearest = np.sqrt(d2.min(axis=1))
+    assert nearest.max() <= 1e-6
+    assert len(np.unique(d2.argmin(axis=1))) == len(hbr)          # a bijection, not just proximity
+
+
+@pytest.mark.parametrize("name", golden_names("stencils_"))
+def test_stencil_shapes_bit_exact(name):
+    d = golden(name)
+    L = d["src"].shape[1]
+    assert np.array_equal(run_refine(d["src"], table_from(d, "t_"), L), d["out"])
+    assert np.array_equal(run_refine(d["src"], table_from(d, "v_"), L), d["v_out"])
+
+
+@pytest.mark.parametrize("name", golden_names("limit_"))
+def test_limit_stencils_with_derivatives_bit_exact(name):
+    d = golden(name)
+    t = table_from(d, "t_")
+    outs = [np.zeros((t.num_stencils, 3), np.float32) for _ in range(6)]
+    assert oracle.eval_stencils(d["src"].reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 6,
+                                t.sizes, t.offsets, t.indices, weight_streams(t, 6))
+    for k, o in zip(OUT6, outs):
+        assert np.array_equal(o, d["out_" + k]), k
+
+
+@pytest.mark.parametrize("name", golden_names("patches_"))
+def test_patches_match_cpu_evaluator(name):
+    d = golden(name)
+    tr = triple_from(d, "vtx_")
+    coords = d["coords"]
+    vb = d["vb"]
+    outs = [np.zeros((len(coords), 3), np.float32) for _ in range(6)]
+    assert oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 6, coords,
+                               tr.arrays, tr.indices, tr.params)
+    scale = [np.zeros((len(coords), 3), np.float32) for _ in range(6)]
+    with oracle.abs_mode():
+        oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in scale], [(0, 3, 3)] * 6, coords,
+                            tr.arrays, tr.indices, tr.params)
+    types = set()
+    for c in coords[:50]:
+        a = tr.arrays[c["arrayIndex"]]
+        types.add(int(a["regDesc"]) if (tr.params[c["patchIndex"]]["field1"] >> 5) & 1 else int(a["desc"]))
+    has_gregory_tri = 10 in set(int(x) for x in tr.arrays["desc"])
+    for k, o, s in zip(OUT6, outs, scale):
+        if has_gregory_tri:
+            assert_close(o, d["out_" + k], s, f"{name}:{k}")     # Bezier-triangle restated in Bernstein form: ~1 ulp
+        else:
+            assert np.array_equal(o, d["out_" + k]), (name, k)
+    if "var_out_p" in d.files:
+        vtr = triple_from(d, "var_")
+        vo = [np.zeros((len(coords), 3), np.float32) for _ in range(3)]
+        assert oracle.eval_patches(d["var_vb"].reshape(-1), (0, 3, 3), [o.reshape(-1) for o in vo], [(0, 3, 3)] * 3,
+                                   coords, vtr.arrays, vtr.indices, vtr.params)
+        for k, o in zip(OUT6, vo):
+            assert np.array_equal(o, d["var_out_" + k]), (name, "varying", k)
+    if "fvar_out_p" in d.files:
+        ftr = triple_from(d, "fvar_")
+        fo = [np.zeros((len(coords), 2), np.float32) for _ in range(6)]
+        assert oracle.eval_patches(d["fvar_vb"].reshape(-1), (0, 2, 2), [o.reshape(-1) for o in fo], [(0, 2, 2)] * 6,
+                                   coords, ftr.arrays, ftr.indices, ftr.params)
+        for k, o in zip(OUT6, fo):
+            assert np.array_equal(o, d["fvar_out_" + k]), (name, "fvar", k)
+
+
+def test_argument_checks_follow_the_reference():
+    d = golden("catmark_cube_L4")
+    t = table_from(d, "last_")
+    src = d["src"].reshape(-1).copy()
+    dst = np.zeros(t.num_stencils * 4, np.float32)
+    # length mismatch -> false (osd/cpuEvaluator.cpp:47); end <= start -> true no-op (:46)
+    assert not oracle.eval_stencils(src, (0, 3, 3), [dst], [(0, 4, 4)], t.sizes, t.offsets, t.indices, [t.weights])
+    assert oracle.eval_stencils(src, (0, 3, 3), [dst], [(0, 4, 4)], t.sizes, t.offsets, t.indices, [t.weights], 5, 5)
+    assert not dst.any()
