@@ -14,6 +14,11 @@
 
 using namespace b200osd;
 
+namespace b200osd {
+signed char g_box_tab_host[6][12][15];
+float g_box_scale_host[6];
+}
+
 namespace {
 
 // Quartic box-spline basis of the regular Loop patch: 12 bivariate quartics, coefficients x12 on the monomials
@@ -35,8 +40,6 @@ const signed char kBox12[12][15] = {
 const signed char kMonoA[15] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 4, 3, 2, 1, 0 };
 const signed char kMonoB[15] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4 };
 
-std::once_flag g_box_once;
-int g_box_rc = B200OSD_OK;
 int g_box_device = -1;
 
 // The derivative tables are obtained by differentiating kBox12 monomial by monomial.
@@ -58,6 +61,8 @@ int upload_box_tables() {
                 tab[k][i][n] += (signed char)(c / divisor[k]);
             }
     const float scale[6] = { 1.0f / 12.0f, 1.0f / 6.0f, 1.0f / 6.0f, 1.0f, 0.5f, 1.0f };
+    std::memcpy(g_box_tab_host, tab, sizeof(tab));
+    std::memcpy(g_box_scale_host, scale, sizeof(scale));
     B200_CUDA_TRY(cudaMemcpyToSymbol(g_box_tab, tab, sizeof(tab)));
     B200_CUDA_TRY(cudaMemcpyToSymbol(g_box_scale, scale, sizeof(scale)));
     return B200OSD_OK;

@@ -19,6 +19,11 @@
 
 #include "common.cuh"
 
+// Every function below is __host__ __device__ so that tests/emu can run the *identical* arithmetic on the CPU
+// (a test-only numerical harness, never a product path: libb200osd.so only ever launches the __global__ kernel).
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_HD_NOINLINE __host__ __device__
+
 namespace b200osd {
 
 constexpr int kPatchMaxOut = 6;
@@ -40,10 +45,78 @@ enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_B
 // Derived box-spline tables (filled once on the host, see patch.cu): g_box_tab[k][i][m], k = value,ds,dt,dss,dst,dtt
 __constant__ signed char g_box_tab[6][12][15];
 __constant__ float g_box_scale[6];
+#ifndef __CUDA_ARCH__
+extern signed char g_box_tab_host[6][12][15];     // host mirror (filled by the same derivation) for tests/emu
+extern float g_box_scale_host[6];
+#endif
+
+B200_HD float box_coeff(int k, int i, int m) {
+#ifdef __CUDA_ARCH__
+    return (float)g_box_tab[k][i][m];
+#else
+    return (float)g_box_tab_host[k][i][m];
+#endif
+}
+B200_HD float box_scale(int k) {
+#ifdef __CUDA_ARCH__
+    return g_box_scale[k];
+#else
+    return g_box_scale_host[k];
+#endif
+}
+B200_HD float rcp_rn(float x) {
+#ifdef __CUDA_ARCH__
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+B200_HD int ldg_i(const int *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+B200_HD unsigned ldg_u(const unsigned *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+B200_HD float ldg_f(const float *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+B200_HD int ld_coord_word(const int *p) {
+#ifdef __CUDA_ARCH__
+    return ld_stream_i1(p);
+#else
+    return *p;
+#endif
+}
+B200_HD void st_out(float *p, float v) {
+#ifdef __CUDA_ARCH__
+    st_stream_f1(p, v);
+#else
+    *p = v;
+#endif
+}
+B200_HD float int_as_float(int v) {
+#ifdef __CUDA_ARCH__
+    return __int_as_float(v);
+#else
+    union { int i; float f; } u; u.i = v; return u.f;
+#endif
+}
 
 // ---------------------------------------------------------------------------------- 1-D bases --
 template <int ORDER>
-__device__ __forceinline__ void bspline_1d(float t, float (&b)[4], float (&d)[4], float (&dd)[4]) {
+B200_HD void bspline_1d(float t, float (&b)[4], float (&d)[4], float (&dd)[4]) {
     const float c = 1.0f - t;
     const float t2 = t * t, c2 = c * c;
     const float sixth = 1.0f / 6.0f;
@@ -66,7 +139,7 @@ __device__ __forceinline__ void bspline_1d(float t, float (&b)[4], float (&d)[4]
 }
 
 template <int ORDER>
-__device__ __forceinline__ void bezier_1d(float t, float (&b)[4], float (&d)[4], float (&dd)[4]) {
+B200_HD void bezier_1d(float t, float (&b)[4], float (&d)[4], float (&dd)[4]) {
     const float c = 1.0f - t;
     const float t2 = t * t, c2 = c * c;
     b[0] = c2 * c;
@@ -88,31 +161,31 @@ __device__ __forceinline__ void bezier_1d(float t, float (&b)[4], float (&d)[4],
 }
 
 // phantom end point folding of a 1-D weight vector: lo = fold index 0 into 1,2 ; hi = fold index 3 into 2,1
-__device__ __forceinline__ void fold_lo(float (&w)[4]) { w[2] -= w[0]; w[1] = fmaf(2.0f, w[0], w[1]); w[0] = 0.0f; }
-__device__ __forceinline__ void fold_hi(float (&w)[4]) { w[1] -= w[3]; w[2] = fmaf(2.0f, w[3], w[2]); w[3] = 0.0f; }
+B200_HD void fold_lo(float (&w)[4]) { w[2] -= w[0]; w[1] = fmaf(2.0f, w[0], w[1]); w[0] = 0.0f; }
+B200_HD void fold_hi(float (&w)[4]) { w[1] -= w[3]; w[2] = fmaf(2.0f, w[3], w[2]); w[3] = 0.0f; }
 
 template <int LT>
-__device__ __forceinline__ void load_cv(const float *src, int stride, int idx, float (&v)[LT]) {
+B200_HD void load_cv(const float *src, int stride, int idx, float (&v)[LT]) {
     const float *p = src + (size_t)idx * (size_t)stride;
 #pragma unroll
-    for (int c = 0; c < LT; ++c) v[c] = __ldg(p + c);
+    for (int c = 0; c < LT; ++c) v[c] = ldg_f(p + c);
 }
 
 template <int LT, int NSETS>
-__device__ __forceinline__ void store_outputs(const PatchIO &io, int i, const float (&out)[NSETS][LT]) {
+B200_HD void store_outputs(const PatchIO &io, int i, const float (&out)[NSETS][LT]) {
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) {
         float *d = io.dst[k];
         if (!d) continue;
         d += (size_t)i * (size_t)io.dstStride[k];
 #pragma unroll
-        for (int c = 0; c < LT; ++c) st_stream_f1(d + c, out[k][c]);
+        for (int c = 0; c < LT; ++c) st_out(d + c, out[k][c]);
     }
 }
 
 // -------------------------------------------------------------------------------- REGULAR path --
 template <int LT, int ORDER>
-__device__ __forceinline__ void eval_regular(const PatchIO &io, const int *cvs, float s, float t, int boundary,
+B200_HD void eval_regular(const PatchIO &io, const int *cvs, float s, float t, int boundary,
                                              float d1, float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     float bs[4], ds[4], dss[4], bt[4], dt[4], dtt[4];
     bspline_1d<ORDER>(s, bs, ds, dss);
@@ -141,7 +214,7 @@ __device__ __forceinline__ void eval_regular(const PatchIO &io, const int *cvs, 
     for (int i = 0; i < 4; ++i) {
         int id[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) id[j] = __ldg(cvs + 4 * i + j);
+        for (int j = 0; j < 4; ++j) id[j] = ldg_i(cvs + 4 * i + j);
         float r0[LT], r1[LT], r2[LT];
 #pragma unroll
         for (int c = 0; c < LT; ++c) { r0[c] = 0.0f; r1[c] = 0.0f; r2[c] = 0.0f; }
@@ -178,7 +251,7 @@ __device__ __forceinline__ void eval_regular(const PatchIO &io, const int *cvs, 
 // (osd/patchBasis.h:345-378); the reciprocal is replaced by 1 when a+b <= 0.  Derivatives use the reference's
 // default approximation: Bezier derivative weights times the same G (osd/patchBasis.h:421-440).
 template <int LT, int ORDER>
-__device__ __forceinline__ void eval_gregory(const PatchIO &io, const int *cvs, float s, float t, float d1,
+B200_HD void eval_gregory(const PatchIO &io, const int *cvs, float s, float t, float d1,
                                              float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     constexpr int COL[20] = { 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2, 0, 0, 1, 1, 1 };
     constexpr int ROW[20] = { 0, 0, 1, 1, 1, 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2 };
@@ -192,7 +265,7 @@ __device__ __forceinline__ void eval_gregory(const PatchIO &io, const int *cvs, 
         const float den[4] = { s + t, sc + t, sc + tc, s + tc };
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float r = (den[c] <= 0.0f) ? 1.0f : __frcp_rn(den[c]);
+            const float r = (den[c] <= 0.0f) ? 1.0f : rcp_rn(den[c]);
             G[2 * c] = a[c] * r;
             G[2 * c + 1] = 1.0f - G[2 * c];
         }
@@ -215,7 +288,7 @@ __device__ __forceinline__ void eval_gregory(const PatchIO &io, const int *cvs, 
         const int col = COL[i], row = ROW[i], p = i % 5;
         const float g = (p >= 3) ? G[2 * (i / 5) + (p - 3)] : 1.0f;
         float v[LT];
-        load_cv<LT>(io.src, io.srcStride, __ldg(cvs + i), v);
+        load_cv<LT>(io.src, io.srcStride, ldg_i(cvs + i), v);
         const float gs = bs[col] * g, gt = bt[row];
         float w[NSETS];
         w[0] = gs * gt;
@@ -230,7 +303,7 @@ __device__ __forceinline__ void eval_gregory(const PatchIO &io, const int *cvs, 
 
 // ---------------------------------------------------------------------------------- QUADS path --
 template <int LT, int ORDER>
-__device__ __forceinline__ void eval_quads(const PatchIO &io, const int *cvs, float s, float t, float d1,
+B200_HD void eval_quads(const PatchIO &io, const int *cvs, float s, float t, float d1,
                                            float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     const float sc = 1.0f - s, tc = 1.0f - t;
     const float wP[4] = { sc * tc, s * tc, s * t, sc * t };
@@ -246,7 +319,7 @@ __device__ __forceinline__ void eval_quads(const PatchIO &io, const int *cvs, fl
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float v[LT];
-        load_cv<LT>(io.src, io.srcStride, __ldg(cvs + i), v);
+        load_cv<LT>(io.src, io.srcStride, ldg_i(cvs + i), v);
 #pragma unroll
         for (int c = 0; c < LT; ++c) {
             out[0][c] = fmaf(wP[i], v[c], out[0][c]);
@@ -257,7 +330,7 @@ __device__ __forceinline__ void eval_quads(const PatchIO &io, const int *cvs, fl
 }
 
 // ------------------------------------------------------------- triangle bases (weight-array form) --
-__device__ __forceinline__ void refl(float *w, int phantom, int plus0, int plus1, int minus) {
+B200_HD void refl(float *w, int phantom, int plus0, int plus1, int minus) {
     const float v = w[phantom];
     w[plus0] += v;
     w[plus1] += v;
@@ -265,7 +338,7 @@ __device__ __forceinline__ void refl(float *w, int phantom, int plus0, int plus1
 }
 
 // Box-spline boundary folding (osd/patchBasis.h:663-886): every phantom point is a reflection B + (B' - I).
-__device__ void box_fold_boundary(int mask, float *w) {
+B200_HD_NOINLINE void box_fold_boundary(int mask, float *w) {
     const signed char PH[3][3] = { { 0, 1, 2 }, { 6, 9, 11 }, { 10, 7, 3 } };
     const signed char B1[3] = { 4, 5, 8 }, B2[3] = { 5, 8, 4 }, I1[3] = { 8, 4, 5 };
     const signed char B0[3] = { 3, 2, 11 }, I0[3] = { 7, 1, 9 };
@@ -295,7 +368,7 @@ __device__ void box_fold_boundary(int mask, float *w) {
     }
 }
 
-__device__ __forceinline__ float bern(int n, int i, int j, int k, float u, float v, float w) {
+B200_HD float bern(int n, int i, int j, int k, float u, float v, float w) {
     if (i < 0 || j < 0 || k < 0) return 0.0f;
     const float fact[5] = { 1.0f, 1.0f, 2.0f, 6.0f, 24.0f };
     float r = fact[n] / (fact[i] * fact[j] * fact[k]);
@@ -307,7 +380,7 @@ __device__ __forceinline__ float bern(int n, int i, int j, int k, float u, float
 
 // Weight arrays for LOOP (12), GREGORY_TRIANGLE (18) and TRIANGLES (3); returns the number of points.
 template <int ORDER>
-__device__ int tri_weights(int type, float s, float t, int boundary, float (*w)[20]) {
+B200_HD_NOINLINE int tri_weights(int type, float s, float t, int boundary, float (*w)[20]) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
     if (type == PT_TRIANGLES) {
         w[0][0] = 1.0f - s - t; w[0][1] = s; w[0][2] = t;
@@ -329,8 +402,8 @@ __device__ int tri_weights(int type, float s, float t, int boundary, float (*w)[
             for (int i = 0; i < 12; ++i) {
                 float acc = 0.0f;
 #pragma unroll
-                for (int m = 0; m < 15; ++m) acc = fmaf((float)g_box_tab[k][i][m], M[m], acc);
-                w[k][i] = g_box_scale[k] * acc;
+                for (int m = 0; m < 15; ++m) acc = fmaf(box_coeff(k, i, m), M[m], acc);
+                w[k][i] = box_scale(k) * acc;
             }
             if (boundary) box_fold_boundary(boundary, w[k]);
         }
@@ -374,21 +447,19 @@ __device__ int tri_weights(int type, float s, float t, int boundary, float (*w)[
 
 // --------------------------------------------------------------------------------------- kernel --
 template <int LT, int ORDER>
-__global__ void __launch_bounds__(128) patch_kernel(PatchIO io) {
+B200_HD void patch_eval_coord(const PatchIO &io, int i) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= io.n) return;
 
     const int *cw = reinterpret_cast<const int *>(io.coords + i);
-    const int arrayIndex = ld_stream_i1(cw + 0);
-    const int patchIndex = ld_stream_i1(cw + 1);
-    float s = __int_as_float(ld_stream_i1(cw + 3));
-    float t = __int_as_float(ld_stream_i1(cw + 4));
+    const int arrayIndex = ld_coord_word(cw + 0);
+    const int patchIndex = ld_coord_word(cw + 1);
+    float s = int_as_float(ld_coord_word(cw + 3));
+    float t = int_as_float(ld_coord_word(cw + 4));
 
     const int *aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
-    const int regDesc = __ldg(aw + 0), irrDesc = __ldg(aw + 1);
-    const int indexBase = __ldg(aw + 3), stride = __ldg(aw + 4), primBase = __ldg(aw + 5);
-    const unsigned field1 = __ldg(&io.params[patchIndex].field1);
+    const int regDesc = ldg_i(aw + 0), irrDesc = ldg_i(aw + 1);
+    const int indexBase = ldg_i(aw + 3), stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
+    const unsigned field1 = ldg_u(&io.params[patchIndex].field1);
 
     const int depth = (int)(field1 & 0xfu);
     const int nonquad = (int)((field1 >> 4) & 1u);
@@ -429,7 +500,7 @@ __global__ void __launch_bounds__(128) patch_kernel(PatchIO io) {
             for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
         for (int j = 0; j < np; ++j) {
             float v[LT];
-            load_cv<LT>(io.src, io.srcStride, __ldg(cvs + j), v);
+            load_cv<LT>(io.src, io.srcStride, ldg_i(cvs + j), v);
 #pragma unroll
             for (int k = 0; k < NSETS; ++k) {
                 const float wk = w[k][j] * (k == 0 ? 1.0f : (k < 3 ? d1 : d2));
@@ -446,5 +517,14 @@ __global__ void __launch_bounds__(128) patch_kernel(PatchIO io) {
     }
     store_outputs<LT, NSETS>(io, i, out);
 }
+
+#ifdef __CUDACC__
+template <int LT, int ORDER>
+__global__ void __launch_bounds__(128) patch_kernel(PatchIO io) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= io.n) return;
+    patch_eval_coord<LT, ORDER>(io, i);
+}
+#endif
 
 }  // namespace b200osd

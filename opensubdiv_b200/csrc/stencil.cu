@@ -66,8 +66,17 @@ int upload(T **dptr, const T *host, size_t count) {
 }
 
 int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, const int *indices,
-               const float *const w[kMaxOut]) {
+               const float *const w[kMaxOut], bool localitySort) {
     const int n = t->n;
+    std::vector<int> rowKey;
+    if (localitySort) {
+        rowKey.resize(n);
+        for (int i = 0; i < n; ++i) {
+            int m = 0x7fffffff;
+            for (int j = 0; j < sizes[i]; ++j) m = std::min(m, indices[offsets[i] + j]);
+            rowKey[i] = m;
+        }
+    }
     t->window = kWindowRows;
     const int numWindows = (n + kWindowRows - 1) / kWindowRows;
     std::vector<int> order(n);
@@ -82,7 +91,17 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
         const int r0 = wdw * kWindowRows, r1 = std::min(n, r0 + kWindowRows);
         int *ord = order.data() + r0;
         std::iota(ord, ord + (r1 - r0), r0);
-        std::stable_sort(ord, ord + (r1 - r0), [&](int a, int b) { return sizes[a] < sizes[b]; });
+        if (localitySort) {
+            // rows of equal padded length are further ordered by their smallest control index, so the 32 rows of a
+            // slice reference neighbouring control vertices and each warp-wide gather touches few cache lines
+            std::stable_sort(ord, ord + (r1 - r0), [&](int a, int b) {
+                const int la = (sizes[a] + kVec - 1) / kVec, lb = (sizes[b] + kVec - 1) / kVec;
+                if (la != lb) return la < lb;
+                return rowKey[a] < rowKey[b];
+            });
+        } else {
+            std::stable_sort(ord, ord + (r1 - r0), [&](int a, int b) { return sizes[a] < sizes[b]; });
+        }
         t->windowSliceStart[wdw] = (int)meta.size();
         for (int s0 = r0; s0 < r1; s0 += kSliceRows) {
             const int s1 = std::min(r1, s0 + kSliceRows);
@@ -185,8 +204,12 @@ int prepare_io(StencilIO &io, const float *src, const int srcDesc[3], int nOut, 
     return B200OSD_OK;
 }
 
-bool src_is_vec4(const StencilIO &io) {
-    return reinterpret_cast<uintptr_t>(io.src) % 16 == 0 && io.srcStride % 4 == 0;
+// widest gather the source layout allows: 16-byte (stride % 4 == 0), 8-byte (stride % 2 == 0) or scalar
+int src_mode(const StencilIO &io) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(io.src);
+    if (a % 16 == 0 && io.srcStride % 4 == 0 && io.L % 4 == 0) return SRC_VEC4;
+    if (a % 8 == 0 && io.srcStride % 2 == 0 && io.L % 2 == 0) return SRC_VEC2;
+    return SRC_SCALAR;
 }
 
 template <int K>
@@ -194,11 +217,12 @@ int launch_csr(const StencilIO &io, const CsrTable &t, cudaStream_t st) {
     const int rows = io.end - io.start;
     const int block = 128;
     const int grid = (rows + block - 1) / block;
-    const bool v4 = src_is_vec4(io);
-#define CSR_CASE(LL)                                                                   \
-    case LL:                                                                           \
-        if (v4 && (LL % 4 == 0)) csr_kernel<LL, K, true><<<grid, block, 0, st>>>(io, t); \
-        else csr_kernel<LL, K, false><<<grid, block, 0, st>>>(io, t);                  \
+    const int mode = src_mode(io);
+#define CSR_CASE(LL)                                                                                          \
+    case LL:                                                                                                  \
+        if (mode == SRC_VEC4 && (LL % 4 == 0)) csr_kernel<LL, K, SRC_VEC4><<<grid, block, 0, st>>>(io, t);    \
+        else if (mode >= SRC_VEC2 && (LL % 2 == 0)) csr_kernel<LL, K, SRC_VEC2><<<grid, block, 0, st>>>(io, t); \
+        else csr_kernel<LL, K, SRC_SCALAR><<<grid, block, 0, st>>>(io, t);                                    \
         break;
     switch (io.L) {
         CSR_CASE(1) CSR_CASE(2) CSR_CASE(3) CSR_CASE(4) CSR_CASE(6) CSR_CASE(8)
@@ -208,16 +232,24 @@ int launch_csr(const StencilIO &io, const CsrTable &t, cudaStream_t st) {
     return check_launch("csr_kernel");
 }
 
+template <int LL, int K, int U>
+void launch_sell_mode(const StencilIO &io, const SellTable &t, int mode, int grid, int block, cudaStream_t st) {
+    if (mode == SRC_VEC4) sell_kernel<LL, K, SRC_VEC4, U><<<grid, block, 0, st>>>(io, t);
+    else if (mode == SRC_VEC2) sell_kernel<LL, K, SRC_VEC2, U><<<grid, block, 0, st>>>(io, t);
+    else sell_kernel<LL, K, SRC_SCALAR, U><<<grid, block, 0, st>>>(io, t);
+}
+
+// mode: SRC_* gather width valid for io.src; unroll: 1, 2 or 4 index groups in flight (K == 1 only; else 1)
 template <int K>
-int launch_sell(const StencilIO &io, const SellTable &t, bool vec4, cudaStream_t st) {
+int launch_sell(const StencilIO &io, const SellTable &t, int mode, int unroll, cudaStream_t st) {
     const int slices = t.sliceEnd - t.sliceBegin;
     const int block = 256;
     const int grid = (slices + (block / 32) - 1) / (block / 32);
-    constexpr int U = (K == 1) ? 2 : 1;
-#define SELL_CASE(LL)                                                                          \
-    case LL:                                                                                   \
-        if (vec4) sell_kernel<LL, K, true, U><<<grid, block, 0, st>>>(io, t);                  \
-        else sell_kernel<LL, K, false, U><<<grid, block, 0, st>>>(io, t);                      \
+#define SELL_CASE(LL)                                                                              \
+    case LL:                                                                                       \
+        if (K == 1 && unroll == 4) launch_sell_mode<LL, K, (K == 1 ? 4 : 1)>(io, t, mode, grid, block, st);      \
+        else if (K == 1 && unroll == 2) launch_sell_mode<LL, K, (K == 1 ? 2 : 1)>(io, t, mode, grid, block, st); \
+        else launch_sell_mode<LL, K, 1>(io, t, mode, grid, block, st);                             \
         break;
     switch (io.L) {
         SELL_CASE(1) SELL_CASE(2) SELL_CASE(3) SELL_CASE(4) SELL_CASE(6) SELL_CASE(8)
@@ -261,7 +293,7 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, const int *
     if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
     for (int k = 0; k < t->numW && !rc; ++k) rc = upload(&t->d_w[k], w[k], (size_t)ne);
-    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w);
+    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w, !(flags & 2));
     if (rc) {
         b200osd_stencil_table_destroy(t);
         return nullptr;
@@ -323,36 +355,36 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
     s.sliceBegin = t->windowSliceStart[start / t->window];
     s.sliceEnd = t->windowSliceStart[(end + t->window - 1) / t->window];
 
-    // Source access: 128-bit gathers.  Lengths that are not a multiple of 4 (xyz, xyz+normal) or unaligned /
-    // interleaved sources are first repacked (control vertices only: the small hot set) into 16-byte rows.
-    bool vec4 = false;
+    // Source access.  Default: gather straight from the caller's buffer with the widest load its layout allows
+    // (measured on B200: the compact layout beats a 16-byte repacked copy -- fewer cache lines per warp-wide gather).
+    // Variants (bench / tests): 2 scalar gathers, 3 repacked 16-byte rows, 4 natural width, 5/6/7 unroll sweeps.
+    int mode = src_mode(io);
+    int unroll = 2;
     const int L = io.L;
-    const bool specialised = (L == 3 || L == 4 || L == 6 || L == 8);
-    if (specialised && g_stencil_variant != 2) {
-        const bool natural = (L % 4 == 0) && src_is_vec4(io);
-        const long long work = (long long)(end - start);
-        if (natural) {
-            vec4 = true;
-        } else if (work >= 4096 || g_stencil_variant == 3) {
-            const int nv4 = (L + 3) / 4;
-            const size_t need = (size_t)t->nCV * nv4;
-            if (need > t->packCap) {
-                cudaFree(t->d_pack);
-                t->d_pack = nullptr;
-                t->packCap = 0;
-                B200_CUDA_TRY(cudaMalloc((void **)&t->d_pack, need * sizeof(float4)));
-                t->packCap = need;
-            }
-            const int total = t->nCV * nv4;
-            pack_src_kernel<<<(total + 255) / 256, 256, 0, st>>>(io.src, io.srcStride, L, t->nCV, t->d_pack);
-            rc = check_launch("pack_src_kernel");
-            if (rc) return rc;
-            io.src = reinterpret_cast<const float *>(t->d_pack);
-            io.srcStride = 4 * nv4;
-            vec4 = true;
+    const int v = g_stencil_variant;
+    if (v == 2 || v == 5) mode = SRC_SCALAR;
+    if (v == 5 || v == 6) unroll = 4;
+    if (v == 7) unroll = 1;
+    if (v == 3 && (L == 3 || L == 4 || L == 6 || L == 8)) {
+        const int nv4 = (L + 3) / 4;
+        const size_t need = (size_t)t->nCV * nv4;
+        if (need > t->packCap) {
+            cudaFree(t->d_pack);
+            t->d_pack = nullptr;
+            t->packCap = 0;
+            B200_CUDA_TRY(cudaMalloc((void **)&t->d_pack, need * sizeof(float4)));
+            t->packCap = need;
         }
+        const int total = t->nCV * nv4;
+        pack_src_kernel<<<(total + 255) / 256, 256, 0, st>>>(io.src, io.srcStride, L, t->nCV, t->d_pack);
+        rc = check_launch("pack_src_kernel");
+        if (rc) return rc;
+        io.src = reinterpret_cast<const float *>(t->d_pack);
+        io.srcStride = 4 * nv4;
+        mode = SRC_VEC4;
     }
-    return nOut == 1 ? launch_sell<1>(io, s, vec4, st) : (nOut == 3 ? launch_sell<3>(io, s, vec4, st) : launch_sell<6>(io, s, vec4, st));
+    return nOut == 1 ? launch_sell<1>(io, s, mode, unroll, st)
+                     : (nOut == 3 ? launch_sell<3>(io, s, mode, unroll, st) : launch_sell<6>(io, s, mode, unroll, st));
 }
 
 int b200osd_eval_stencils(const float *src, const int srcDesc[3], int nOut, float *const dsts[],

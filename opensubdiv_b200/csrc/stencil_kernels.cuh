@@ -68,10 +68,25 @@ __device__ __forceinline__ void load_vertex_vec4(const float *src, int stride, i
     }
 }
 
-template <int L, bool VEC4>
+// stride is even and src is 8-byte aligned (e.g. 6-float xyz+normal vertices): L/2 64-bit loads
+template <int L>
+__device__ __forceinline__ void load_vertex_vec2(const float *src, int stride, int idx, float (&v)[L]) {
+    const float2 *p = reinterpret_cast<const float2 *>(src + (size_t)idx * (size_t)stride);
+#pragma unroll
+    for (int c = 0; c < (L + 1) / 2; ++c) {
+        float2 t = p[c];
+        if (2 * c + 0 < L) v[2 * c + 0] = t.x;
+        if (2 * c + 1 < L) v[2 * c + 1] = t.y;
+    }
+}
+
+enum { SRC_SCALAR = 0, SRC_VEC2 = 1, SRC_VEC4 = 2 };
+
+template <int L, int SRCMODE>
 __device__ __forceinline__ void load_vertex(const float *src, int stride, int idx, float (&v)[L]) {
-    if (VEC4) load_vertex_vec4<L>(src, stride, idx, v);
-    else      load_vertex_scalar<L>(src, stride, idx, v);
+    if (SRCMODE == SRC_VEC4)      load_vertex_vec4<L>(src, stride, idx, v);
+    else if (SRCMODE == SRC_VEC2) load_vertex_vec2<L>(src, stride, idx, v);
+    else                          load_vertex_scalar<L>(src, stride, idx, v);
 }
 
 template <int L>
@@ -106,7 +121,7 @@ __device__ __forceinline__ void accumulate(float (&acc)[K][L], const float (&v)[
 }
 
 // ------------------------------------------------------------------------------------ CSR path --
-template <int L, int K, bool VEC4>
+template <int L, int K, int SRCMODE>
 __global__ void __launch_bounds__(128) csr_kernel(StencilIO io, CsrTable t) {
     int row = io.start + blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= io.end) return;
@@ -124,7 +139,7 @@ __global__ void __launch_bounds__(128) csr_kernel(StencilIO io, CsrTable t) {
 #pragma unroll
         for (int k = 0; k < K; ++k) w[k] = t.w[k][off + j];
         float v[L];
-        load_vertex<L, VEC4>(io.src, io.srcStride, idx, v);
+        load_vertex<L, SRCMODE>(io.src, io.srcStride, idx, v);
         accumulate<L, K>(acc, v, w);
     }
     store_row<L, K>(io, row, acc);
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(128) csr_kernel_anyL(StencilIO io, CsrTable t)
 // ----------------------------------------------------------------------------------- SELL path --
 // One warp per slice, one lane per row.  UNROLL index groups are issued back to back so that each lane has
 // 2*UNROLL 128-bit stream loads in flight before the first gather is consumed.
-template <int L, int K, bool VEC4, int UNROLL>
+template <int L, int K, int SRCMODE, int UNROLL>
 __global__ void __launch_bounds__(256) sell_kernel(StencilIO io, SellTable t) {
     const int lane = threadIdx.x & 31;
     const int slice = t.sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -205,10 +220,10 @@ __global__ void __launch_bounds__(256) sell_kernel(StencilIO io, SellTable t) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             float v0[L], v1[L], v2[L], v3[L];
-            load_vertex<L, VEC4>(io.src, io.srcStride, id[u].x, v0);
-            load_vertex<L, VEC4>(io.src, io.srcStride, id[u].y, v1);
-            load_vertex<L, VEC4>(io.src, io.srcStride, id[u].z, v2);
-            load_vertex<L, VEC4>(io.src, io.srcStride, id[u].w, v3);
+            load_vertex<L, SRCMODE>(io.src, io.srcStride, id[u].x, v0);
+            load_vertex<L, SRCMODE>(io.src, io.srcStride, id[u].y, v1);
+            load_vertex<L, SRCMODE>(io.src, io.srcStride, id[u].z, v2);
+            load_vertex<L, SRCMODE>(io.src, io.srcStride, id[u].w, v3);
             float wx[K], wy[K], wz[K], ww[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) { wx[k] = w[u][k].x; wy[k] = w[u][k].y; wz[k] = w[u][k].z; ww[k] = w[u][k].w; }
@@ -224,10 +239,10 @@ __global__ void __launch_bounds__(256) sell_kernel(StencilIO io, SellTable t) {
 #pragma unroll
         for (int k = 0; k < K; ++k) w[k] = ld_stream_f4(wp[k] + (size_t)g * kSliceRows);
         float v0[L], v1[L], v2[L], v3[L];
-        load_vertex<L, VEC4>(io.src, io.srcStride, id.x, v0);
-        load_vertex<L, VEC4>(io.src, io.srcStride, id.y, v1);
-        load_vertex<L, VEC4>(io.src, io.srcStride, id.z, v2);
-        load_vertex<L, VEC4>(io.src, io.srcStride, id.w, v3);
+        load_vertex<L, SRCMODE>(io.src, io.srcStride, id.x, v0);
+        load_vertex<L, SRCMODE>(io.src, io.srcStride, id.y, v1);
+        load_vertex<L, SRCMODE>(io.src, io.srcStride, id.z, v2);
+        load_vertex<L, SRCMODE>(io.src, io.srcStride, id.w, v3);
         float wx[K], wy[K], wz[K], ww[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) { wx[k] = w[k].x; wy[k] = w[k].y; wz[k] = w[k].z; ww[k] = w[k].w; }

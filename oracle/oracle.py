@@ -87,10 +87,16 @@ def patch_basis(patch_type: int, field0: int, field1: int, s: float, t: float, n
 
 
 class abs_mode:
-    """Context manager: inside it eval_stencils / eval_patches return S = sum_j |w_j| |x_j| (the tolerance scale)."""
+    """Context manager: inside it eval_stencils / eval_patches return the tolerance scale instead of the value.
+    kind=1: S = sum_j |w_j||x_j|.  kind=2 (patches): S = sum_j (|w_j| + W)|x_j| with W = max |unfolded weight| of the
+    set -- the weights themselves are formed with cancellation (boundary folding, B-spline polynomials near knots) so
+    every correct fp32 evaluation, the reference's included, carries an error ~eps*W per weight."""
+
+    def __init__(self, kind: int = 1):
+        self.kind = kind
 
     def __enter__(self):
-        lib().oracle_set_abs_mode(1)
+        lib().oracle_set_abs_mode(self.kind)
 
     def __exit__(self, *exc):
         lib().oracle_set_abs_mode(0)

@@ -30,8 +30,23 @@
 /* Tolerance scale mode (tests only): when set, every accumulation uses |value| * |weight|, so the evaluators
  * return S = sum_j |w_j| |x_j| -- the magnitude against which a 1e-6 relative bound is meaningful when signed
  * derivative weights cancel ("Parity at 1e-6 relative"). */
-static int g_abs_mode = 0;
+static int g_abs_mode = 0;      /* 0 off, 1 plain S = sum |w||x|, 2 conditioned (patches): S = sum (|w|+W)|x| */
 void oracle_set_abs_mode(int on) { g_abs_mode = on; }
+/* For patches the weights themselves are computed with cancellation (boundary folding subtracts phantom weights,
+ * the B-spline polynomials cancel near the knots), so each weight carries an absolute error ~eps*W with
+ * W = max_j |unfolded w_j| of its set.  In abs mode EvalPatches therefore returns
+ *     S = sum_j (|w_j| + W) |x_j|
+ * which bounds the rounding error of ANY correct fp32 evaluation order (reference's included) by ~n*eps*S. */
+static float g_wmax[6];
+static void note_wmax(float *const w[6], int nsets, int npts)
+{
+    int k, j;
+    for (k = 0; k < nsets; ++k) {
+        float m = 0.0f;
+        for (j = 0; j < npts; ++j) if (fabsf(w[k][j]) > m) m = fabsf(w[k][j]);
+        g_wmax[k] = m;
+    }
+}
 
 #define ORACLE_MAX_LEN 64          /* max primvar length handled by the stack temporaries */
 
@@ -221,6 +236,7 @@ static int basis_regular(float s, float t, int boundary, float *w[6], int order)
     tensor4(bs, bt, w[0]);
     if (order >= 1) { tensor4(ds, bt, w[1]); tensor4(bs, dt, w[2]); }
     if (order >= 2) { tensor4(dss, bt, w[3]); tensor4(ds, dt, w[4]); tensor4(bs, dtt, w[5]); }
+    note_wmax(w, order == 0 ? 1 : (order == 1 ? 3 : 6), 16);
     if (boundary) {
         int nsets = order == 0 ? 1 : (order == 1 ? 3 : 6);
         for (k = 0; k < nsets; ++k) bspline_fold_boundary(boundary, w[k]);
@@ -431,8 +447,10 @@ static int basis_loop(float s, float t, int boundary, float *w[6], int order)
             }
             w[k][i] = g_box_scale[k] * acc;
         }
-        if (boundary) box_fold_boundary(boundary, w[k]);
     }
+    note_wmax(w, nsets, 12);
+    for (k = 0; k < nsets; ++k)
+        if (boundary) box_fold_boundary(boundary, w[k]);
     return 12;
 }
 
@@ -545,6 +563,11 @@ int oracle_patch_basis(int patchType, unsigned field0, unsigned field1, float s,
         case PT_TRIANGLES:        n = basis_tris(s, t, w, order); break;
         default: return 0;
     }
+    if (patchType != PT_REGULAR && patchType != PT_LOOP) note_wmax(w, order == 0 ? 1 : (order == 1 ? 3 : 6), n);
+    {
+        float a1 = (float)(1 << depth), a2 = a1 * a1;
+        g_wmax[1] *= a1; g_wmax[2] *= a1; g_wmax[3] *= a2; g_wmax[4] *= a2; g_wmax[5] *= a2;
+    }
     if (order >= 1) {
         float d1 = sign * (float)(1 << depth);
         for (i = 0; i < n; ++i) { wDs[i] *= d1; wDt[i] *= d1; }
@@ -599,7 +622,7 @@ int oracle_eval_patches(int nw,
             for (k = 0; k < L; ++k) acc[k] = 0.0f;
             for (j = 0; j < n; ++j) {
                 const float *v = src + (ptrdiff_t)cvs[j] * srcDesc->stride;
-                if (g_abs_mode) { for (k = 0; k < L; ++k) acc[k] += fabsf(v[k]) * fabsf(wbuf[q][j]); }
+                if (g_abs_mode) { for (k = 0; k < L; ++k) acc[k] += fabsf(v[k]) * (fabsf(wbuf[q][j]) + (g_abs_mode == 2 ? g_wmax[q] : 0.0f)); }
                 else            { for (k = 0; k < L; ++k) acc[k] += v[k] * wbuf[q][j]; }
             }
             memcpy(dsts[q] + dstDescs[q].offset + (ptrdiff_t)i * dstDescs[q].stride, acc, (size_t)L * sizeof(float));

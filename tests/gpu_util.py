@@ -29,20 +29,20 @@ def oracle_stencils(src, src_desc, n_rows, L, t, nw, start=0, end=None, abs_scal
                                     [(0, L, L)] * nw, t.sizes, t.offsets, t.indices, ws, start,
                                     len(t.sizes) if end is None else end)
     if abs_scale:
-        with oracle.abs_mode():
+        with oracle.abs_mode(1):
             run()
     else:
         run()
     return outs
 
 
-def oracle_patches(src, src_desc, L, coords, tr, nw, abs_scale=False):
+def oracle_patches(src, src_desc, L, coords, tr, nw, abs_scale=False, plain=False):
     outs = [np.zeros((len(coords), L), np.float32) for _ in range(nw)]
     def run():
         assert oracle.eval_patches(np.ascontiguousarray(src).reshape(-1), src_desc, [o.reshape(-1) for o in outs],
                                    [(0, L, L)] * nw, coords, tr.arrays, tr.indices, tr.params)
     if abs_scale:
-        with oracle.abs_mode():
+        with oracle.abs_mode(1 if plain else 2):
             run()
     else:
         run()

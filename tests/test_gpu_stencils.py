@@ -10,7 +10,8 @@ from tests.util import golden, golden_names, table_from, assert_close, REL_TOL
 
 pytestmark = pytest.mark.gpu
 OUT6 = ("p", "du", "dv", "duu", "duv", "dvv")
-VARIANTS = (0, 1, 2, 3)        # auto, CSR kernel on the table, bucketed w/ scalar gathers, bucketed w/ packed gathers
+# 0 auto, 1 CSR kernel on the table, 2 scalar gathers, 3 repacked 16-byte gathers, 5 scalar + 4 groups in flight, 7 one group
+VARIANTS = (0, 1, 2, 3, 5, 7)
 
 
 def refine_same_buffer(t, src, L, variant=0):
@@ -233,7 +234,7 @@ def test_config2_size_independent_properties(config2):
     lin = ev(0.75 * x - 1.5 * y)
     assert (lin - (0.75 * ex - 1.5 * ey)).abs().max().item() <= 2e-6 * max(1.0, lin.abs().max().item())
     # every kernel variant and the raw reference-layout path agree
-    for v in (1, 2, 3):
+    for v in (1, 2, 3, 4, 5, 6, 7):
         assert (ev(x, v) - ex).abs().max().item() <= 2e-6
     raw = torch.empty((n, 6), device="cuda")
     assert osd.B200Evaluator.EvalStencilsRaw(x, D(0, 6, 6), [(raw, D(0, 6, 6))], tbl.GetSizesBuffer(), tbl.GetOffsetsBuffer(),

@@ -69,7 +69,7 @@ def test_patches_match_cpu_evaluator(name):
     assert oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 6, coords,
                                tr.arrays, tr.indices, tr.params)
     scale = [np.zeros((len(coords), 3), np.float32) for _ in range(6)]
-    with oracle.abs_mode():
+    with oracle.abs_mode(2):
         oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in scale], [(0, 3, 3)] * 6, coords,
                             tr.arrays, tr.indices, tr.params)
     types = set()

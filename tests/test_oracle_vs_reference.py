@@ -109,7 +109,7 @@ def test_eval_patches_live(shape, level, endcap):
         assert ref.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in a], [(0, 3, 3)] * nw, pc, pt.vertex)
         args = (pc, pt.vertex.arrays, pt.vertex.indices, pt.vertex.params)
         assert oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in b], [(0, 3, 3)] * nw, *args)
-        with oracle.abs_mode():
+        with oracle.abs_mode(2):
             oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in sc], [(0, 3, 3)] * nw, *args)
         for x, y, z in zip(a, b, sc):
             assert_close(y, x, z, shape)
