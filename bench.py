@@ -241,50 +241,72 @@ def run_b200_arm(args):
     D = osd.BufferDescriptor
     lib = capi.lib()
 
+    from opensubdiv_b200 import shard
     mesh, table = build_workload()
-    ncv, n = table.num_control_verts, table.num_stencils
+    ncv = table.num_control_verts
+    strong = (args.scaling == "strong") and world > 1
+    if strong:
+        # one mesh, rows cut into `world` contiguous ranges balanced on stencil elements; every rank needs all control points
+        plan = shard.ShardPlan.for_table(table.sizes, world, rank, align=2048)
+        alg_bytes_total = table.algorithmic_bytes(1, L, L)
+        table = shard.local_table(table, plan)
+        meshes_in_scene, my_mesh = 1, 0
+        total_rows = sum(b - a for a, b in plan.ranges)
+    else:
+        # `world` meshes; rank r owns all rows of mesh r; the scene's control points are replicated every frame
+        alg_bytes_total = table.algorithmic_bytes(1, L, L) * world
+        meshes_in_scene, my_mesh = world, rank
+        total_rows = table.num_stencils * world
+    n = table.num_stencils
     t0 = time.time()
     tbl = osd.B200StencilTable.Create(table)
     assert tbl is not None, capi.last_error()
-    log(f"[bench] rank {rank}: B200StencilTable built in {time.time() - t0:.1f}s")
+    log(f"[bench] rank {rank}: B200StencilTable of {n} rows built in {time.time() - t0:.1f}s")
 
-    # Scene = `world` meshes; control points of the whole scene live at the front of every rank's vertex buffer
-    # (replicated by the per-frame broadcast), this rank's refined rows behind them.
-    scene_cv = ncv * world
-    vb = osd.B200VertexBuffer.Create(L, scene_cv + n)
+    # vertex buffer = [ control block A | control block B | this rank's refined rows ]; A/B are the two halves of the
+    # double-buffered per-frame broadcast (frame f lives in block f % 2)
+    scene_cv = ncv * meshes_in_scene
+    vb = osd.B200VertexBuffer.Create(L, 2 * scene_cv + n)
     assert vb is not None, capi.last_error()
     vt = vb.as_tensor()
-    src_desc = D(rank * ncv * L, L, L)                     # this rank's mesh inside the replicated control block
-    dst_desc = D(scene_cv * L, L, L)
+    blocks = [vt[:scene_cv], vt[scene_cv:2 * scene_cv]]
+    src_descs = [D((b * scene_cv + my_mesh * ncv) * L, L, L) for b in (0, 1)]
+    dst_desc = D(2 * scene_cv * L, L, L)
+    bc = shard.FrameBroadcaster(blocks, root=0)
 
-    frames = [torch.from_numpy(np.tile(frame_primvars(mesh, f), (world, 1))).pin_memory() for f in range(4)]
+    frames = [torch.from_numpy(np.tile(frame_primvars(mesh, f), (meshes_in_scene, 1))).pin_memory() for f in range(4)]
     host_out = torch.empty((n, L), dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream()
+    for b in (0, 1):                                       # device-resident control points for the `value` measurement
+        vb.UpdateData(frames[b], b * scene_cv, scene_cv)
+    torch.cuda.synchronize()
 
     def step_device(f):
-        """Device-resident step: (N>1: NCCL broadcast of the scene's control points from rank 0, then) EvalStencils."""
-        if world > 1:
-            dist.broadcast(vt[:scene_cv], src=0)
-        ok = osd.B200Evaluator.EvalStencils(vb, src_desc, vb, dst_desc, tbl)
+        """Device-resident step: (N>1: broadcast of the scene's control points from rank 0 on the side stream,
+        overlapped with the previous frame's kernel) then EvalStencils of this rank's rows."""
+        bc.post(f)
+        bc.wait(f)
+        ok = osd.B200Evaluator.EvalStencils(vb, src_descs[f % 2], vb, dst_desc, tbl)
         assert ok
+        bc.release(f)
 
     def step_e2e(f):
-        """Host-buffer step through the C ABI: H2D control points, evaluate, D2H refined vertices."""
-        if rank == 0 or world == 1:
-            vb.UpdateData(frames[f % len(frames)], 0, scene_cv)
-        if world > 1:
-            dist.broadcast(vt[:scene_cv], src=0)
-        ok = osd.B200Evaluator.EvalStencils(vb, src_desc, vb, dst_desc, tbl)
+        """Host-buffer step through the C ABI: H2D control points (root), replicate, evaluate, D2H refined vertices."""
+        b = f % 2
+        if rank == 0:
+            vb.UpdateData(frames[f % len(frames)], b * scene_cv, scene_cv)
+        bc.post(f)
+        bc.wait(f)
+        ok = osd.B200Evaluator.EvalStencils(vb, src_descs[b], vb, dst_desc, tbl)
         assert ok
-        vb.ReadData(host_out, scene_cv, n)
+        bc.release(f)
+        vb.ReadData(host_out, 2 * scene_cv, n)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness spot check inside the bench (cheap): a constant field is reproduced
-    vb.UpdateData(frames[0], 0, scene_cv)
     step_device(0)
     torch.cuda.synchronize()
 
@@ -323,9 +345,9 @@ def run_b200_arm(args):
     clocks = sampler.stop() if rank == 0 else None
 
     ms_per_step = ms_dev / args.steps
-    value = n * world * args.steps / (ms_dev * 1e-3)
-    e2e_value = n * world * e2e_steps / (ms_e2e * 1e-3)
-    alg_bytes = table.algorithmic_bytes(1, L, L)
+    value = total_rows * args.steps / (ms_dev * 1e-3)
+    e2e_value = total_rows * e2e_steps / (ms_e2e * 1e-3)
+    alg_bytes = alg_bytes_total // world                      # per GPU, per launch
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
 
@@ -344,9 +366,11 @@ def run_b200_arm(args):
         line = {
             "metric": "refined_verts_per_sec_EvalStencils", "value": value, "unit": "verts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rows_per_gpu": n, "elements_per_gpu": table.num_elements,
                        "control_verts_per_mesh": ncv, "primvar_floats": L, "parallelism": f"row-range x{world}",
+                       "exchange": "none (1 GPU)" if world == 1 else
+                       f"per-frame NCCL broadcast of {scene_cv * L * 4} B of control points from rank 0, double-buffered on a side stream",
                        "l2_policy": "inputs larger than L2 (table streams 0.7 GB/step vs 126 MB L2); no flush needed",
                        "stencil_variant": lib.b200osd_get_stencil_variant(),
                        "bucketed_stream_bytes": tbl.GetStreamBytes(1)},
@@ -356,7 +380,7 @@ def run_b200_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "frac_of_nominal_8TBps": achieved / 8000.0,
-                         "note": "device time per step = pack_src_kernel (control verts -> 16 B rows) + sell_kernel"},
+                         "note": "per GPU; device time per step = one sell_kernel launch (+ the overlapped broadcast when N > 1)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
@@ -373,6 +397,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant (0 = auto)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N meshes (default), strong = one mesh cut into N row ranges")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

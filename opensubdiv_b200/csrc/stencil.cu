@@ -232,30 +232,69 @@ int launch_csr(const StencilIO &io, const CsrTable &t, cudaStream_t st) {
     return check_launch("csr_kernel");
 }
 
-template <int LL, int K, int U>
-void launch_sell_mode(const StencilIO &io, const SellTable &t, int mode, int grid, int block, cudaStream_t st) {
-    if (mode == SRC_VEC4) sell_kernel<LL, K, SRC_VEC4, U><<<grid, block, 0, st>>>(io, t);
-    else if (mode == SRC_VEC2) sell_kernel<LL, K, SRC_VEC2, U><<<grid, block, 0, st>>>(io, t);
-    else sell_kernel<LL, K, SRC_SCALAR, U><<<grid, block, 0, st>>>(io, t);
+// Launch shape of the bucketed kernels.
+struct SellPlan {
+    int mode = SRC_SCALAR;   // gather width (SRC_*)
+    int unroll = 2;          // index groups in flight per lane: 1, 2 or 4 (K == 1; otherwise 1)
+    int minBlocks = 0;       // __launch_bounds__ min blocks per SM: 0 (unspecified), 1, 6 or 8 (K == 1, unroll == 2)
+    bool persistent = false; // grid-stride persistent kernel with next-slice descriptor prefetch
+};
+
+template <int LL, int K, int SRCMODE, int U, int MINB>
+void launch_sell_final(const StencilIO &io, const SellTable &t, bool persistent, int slices, cudaStream_t st) {
+    const int block = 256;
+    const int need = (slices + (block / 32) - 1) / (block / 32);
+    if (persistent) {
+        static int perSM = 0;     // per template instantiation
+        if (!perSM) {
+            int b = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sell_kernel_persist<LL, K, SRCMODE, U, MINB>, block, 0) != cudaSuccess || b < 1) b = 4;
+            perSM = b;
+        }
+        const int grid = std::min(need, perSM * sm_count());
+        sell_kernel_persist<LL, K, SRCMODE, U, MINB><<<grid, block, 0, st>>>(io, t);
+    } else {
+        sell_kernel<LL, K, SRCMODE, U, MINB><<<need, block, 0, st>>>(io, t);
+    }
 }
 
-// mode: SRC_* gather width valid for io.src; unroll: 1, 2 or 4 index groups in flight (K == 1 only; else 1)
-template <int K>
-int launch_sell(const StencilIO &io, const SellTable &t, int mode, int unroll, cudaStream_t st) {
-    const int slices = t.sliceEnd - t.sliceBegin;
-    const int block = 256;
-    const int grid = (slices + (block / 32) - 1) / (block / 32);
-#define SELL_CASE(LL)                                                                              \
-    case LL:                                                                                       \
-        if (K == 1 && unroll == 4) launch_sell_mode<LL, K, (K == 1 ? 4 : 1)>(io, t, mode, grid, block, st);      \
-        else if (K == 1 && unroll == 2) launch_sell_mode<LL, K, (K == 1 ? 2 : 1)>(io, t, mode, grid, block, st); \
-        else launch_sell_mode<LL, K, 1>(io, t, mode, grid, block, st);                             \
-        break;
-    switch (io.L) {
-        SELL_CASE(1) SELL_CASE(2) SELL_CASE(3) SELL_CASE(4) SELL_CASE(6) SELL_CASE(8)
-        default: sell_kernel_anyL<K><<<grid, block, 0, st>>>(io, t); break;
+template <int LL, int K, int SRCMODE>
+void launch_sell_shape(const StencilIO &io, const SellTable &t, const SellPlan &p, int slices, cudaStream_t st) {
+    if (K == 1) {
+        if (p.unroll == 4) { launch_sell_final<LL, K, SRCMODE, (K == 1 ? 4 : 1), 0>(io, t, false, slices, st); return; }
+        if (p.unroll == 1) { launch_sell_final<LL, K, SRCMODE, 1, 0>(io, t, false, slices, st); return; }
+        if (p.minBlocks == 1) { launch_sell_final<LL, K, SRCMODE, (K == 1 ? 2 : 1), (K == 1 ? 1 : 0)>(io, t, p.persistent, slices, st); return; }
+        if (p.minBlocks == 8) { launch_sell_final<LL, K, SRCMODE, (K == 1 ? 2 : 1), (K == 1 ? 8 : 1)>(io, t, p.persistent, slices, st); return; }
+        if (p.minBlocks == 6) { launch_sell_final<LL, K, SRCMODE, (K == 1 ? 2 : 1), (K == 1 ? 6 : 1)>(io, t, p.persistent, slices, st); return; }
+        launch_sell_final<LL, K, SRCMODE, (K == 1 ? 2 : 1), 0>(io, t, p.persistent, slices, st);
+        return;
     }
-#undef SELL_CASE
+    launch_sell_final<LL, K, SRCMODE, 1, 0>(io, t, p.persistent, slices, st);
+}
+
+template <int LL, int K>
+void launch_sell_mode(const StencilIO &io, const SellTable &t, const SellPlan &p, int slices, cudaStream_t st) {
+    if (p.mode == SRC_VEC4) launch_sell_shape<LL, K, SRC_VEC4>(io, t, p, slices, st);
+    else if (p.mode == SRC_VEC2) launch_sell_shape<LL, K, SRC_VEC2>(io, t, p, slices, st);
+    else launch_sell_shape<LL, K, SRC_SCALAR>(io, t, p, slices, st);
+}
+
+template <int K>
+int launch_sell(const StencilIO &io, const SellTable &t, const SellPlan &p, cudaStream_t st) {
+    const int slices = t.sliceEnd - t.sliceBegin;
+    switch (io.L) {
+        case 1: launch_sell_mode<1, K>(io, t, p, slices, st); break;
+        case 2: launch_sell_mode<2, K>(io, t, p, slices, st); break;
+        case 3: launch_sell_mode<3, K>(io, t, p, slices, st); break;
+        case 4: launch_sell_mode<4, K>(io, t, p, slices, st); break;
+        case 6: launch_sell_mode<6, K>(io, t, p, slices, st); break;
+        case 8: launch_sell_mode<8, K>(io, t, p, slices, st); break;
+        default: {
+            const int grid = (slices + 7) / 8;
+            sell_kernel_anyL<K><<<grid, 256, 0, st>>>(io, t);
+            break;
+        }
+    }
     return check_launch("sell_kernel");
 }
 
@@ -357,14 +396,25 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
 
     // Source access.  Default: gather straight from the caller's buffer with the widest load its layout allows
     // (measured on B200: the compact layout beats a 16-byte repacked copy -- fewer cache lines per warp-wide gather).
-    // Variants (bench / tests): 2 scalar gathers, 3 repacked 16-byte rows, 4 natural width, 5/6/7 unroll sweeps.
-    int mode = src_mode(io);
-    int unroll = 2;
+    // Variants (bench / tests): 2 scalar gathers, 3 repacked 16-byte rows, 4 natural width, 5/6/7 unroll sweeps,
+    // 8/9/12/14 persistent grid (min blocks unspecified/6/8/1), 10/11/13 one-shot grid with min blocks 6/8/1.
+    SellPlan plan;
+    plan.mode = src_mode(io);
     const int L = io.L;
     const int v = g_stencil_variant;
-    if (v == 2 || v == 5) mode = SRC_SCALAR;
-    if (v == 5 || v == 6) unroll = 4;
-    if (v == 7) unroll = 1;
+    // measured defaults (profiles/r01_sweep.md): with derivative streams the kernel is register-heavy and latency bound,
+    // the persistent grid's descriptor prefetch wins (+27 % at K=6); 4-float primvars like 64 resident warps
+    if (v == 0) {
+        if (nOut > 1) plan.persistent = true;
+        else if (L == 4 && plan.mode == SRC_VEC4) plan.minBlocks = 8;
+    }
+    if (v == 2 || v == 5) plan.mode = SRC_SCALAR;
+    if (v == 5 || v == 6) plan.unroll = 4;
+    if (v == 7) plan.unroll = 1;
+    if (v == 8 || v == 9 || v == 12 || v == 14) plan.persistent = true;
+    if (v == 13 || v == 14) plan.minBlocks = 1;
+    if (v == 9 || v == 10) plan.minBlocks = 6;
+    if (v == 11 || v == 12) plan.minBlocks = 8;
     if (v == 3 && (L == 3 || L == 4 || L == 6 || L == 8)) {
         const int nv4 = (L + 3) / 4;
         const size_t need = (size_t)t->nCV * nv4;
@@ -381,10 +431,9 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
         if (rc) return rc;
         io.src = reinterpret_cast<const float *>(t->d_pack);
         io.srcStride = 4 * nv4;
-        mode = SRC_VEC4;
+        plan.mode = SRC_VEC4;
     }
-    return nOut == 1 ? launch_sell<1>(io, s, mode, unroll, st)
-                     : (nOut == 3 ? launch_sell<3>(io, s, mode, unroll, st) : launch_sell<6>(io, s, mode, unroll, st));
+    return nOut == 1 ? launch_sell<1>(io, s, plan, st) : (nOut == 3 ? launch_sell<3>(io, s, plan, st) : launch_sell<6>(io, s, plan, st));
 }
 
 int b200osd_eval_stencils(const float *src, const int srcDesc[3], int nOut, float *const dsts[],

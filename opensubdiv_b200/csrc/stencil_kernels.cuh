@@ -185,22 +185,16 @@ __global__ void __launch_bounds__(128) csr_kernel_anyL(StencilIO io, CsrTable t)
 }
 
 // ----------------------------------------------------------------------------------- SELL path --
-// One warp per slice, one lane per row.  UNROLL index groups are issued back to back so that each lane has
-// 2*UNROLL 128-bit stream loads in flight before the first gather is consumed.
+// One lane per row.  UNROLL index groups are issued back to back so that each lane has 2*UNROLL 128-bit stream
+// loads in flight before the first gather is consumed.
 template <int L, int K, int SRCMODE, int UNROLL>
-__global__ void __launch_bounds__(256) sell_kernel(StencilIO io, SellTable t) {
-    const int lane = threadIdx.x & 31;
-    const int slice = t.sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (slice >= t.sliceEnd) return;
-    const int2 m = t.meta[slice];
-    const int row = t.rows[(size_t)slice * kSliceRows + lane];
+__device__ __forceinline__ void sell_slice(const StencilIO &io, const SellTable &t, const int2 m, const int lane,
+                                           float (&acc)[K][L]) {
     const size_t base = (size_t)(unsigned)m.x + lane;
     const int4 *ip = t.idx4 + base;
     const float4 *wp[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) wp[k] = t.w4[k] + base;
-
-    float acc[K][L];
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -251,7 +245,49 @@ __global__ void __launch_bounds__(256) sell_kernel(StencilIO io, SellTable t) {
         accumulate<L, K>(acc, v2, wz);
         accumulate<L, K>(acc, v3, ww);
     }
+}
+
+// One warp per slice (one-shot grid).  MINB = minimum resident blocks per SM asked of the register allocator.
+template <int L, int K, int SRCMODE, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) sell_kernel(StencilIO io, SellTable t) {
+    const int lane = threadIdx.x & 31;
+    const int slice = t.sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (slice >= t.sliceEnd) return;
+    const int2 m = t.meta[slice];
+    const int row = t.rows[(size_t)slice * kSliceRows + lane];
+    float acc[K][L];
+    sell_slice<L, K, SRCMODE, UNROLL>(io, t, m, lane, acc);
     if (row >= io.start && row < io.end) store_row<L, K>(io, row, acc);
+}
+
+// Persistent form: the grid is sized to the machine and every warp walks slices with a grid stride, fetching the
+// NEXT slice's descriptor and row ids before working on the current one, so the descriptor -> stream dependent
+// DRAM round trip is paid once per warp instead of once per slice.
+template <int L, int K, int SRCMODE, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) sell_kernel_persist(StencilIO io, SellTable t) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    int slice = t.sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (slice >= t.sliceEnd) return;
+    int2 m = t.meta[slice];
+    int row = t.rows[(size_t)slice * kSliceRows + lane];
+    for (;;) {
+        const int next = slice + nwarps;
+        const bool more = next < t.sliceEnd;
+        int2 mn = make_int2(0, 0);
+        int rown = -1;
+        if (more) {
+            mn = t.meta[next];
+            rown = t.rows[(size_t)next * kSliceRows + lane];
+        }
+        float acc[K][L];
+        sell_slice<L, K, SRCMODE, UNROLL>(io, t, m, lane, acc);
+        if (row >= io.start && row < io.end) store_row<L, K>(io, row, acc);
+        if (!more) break;
+        slice = next;
+        m = mn;
+        row = rown;
+    }
 }
 
 template <int K>

@@ -1,0 +1,144 @@
+"""Row-range sharding of the stencil path across the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference has no multi-GPU code (no NCCL/MPI anywhere); this layer is new.  The path shards
+naturally: every stencil row is independent, the tables are static, and the only per-frame shared input is the small
+control-point buffer.  So
+
+  * rows are cut into `world` contiguous ranges balanced on the number of stencil ELEMENTS (the cost of a row is its
+    size, not 1) -- `balanced_row_ranges`;
+  * each rank builds a B200StencilTable of its own rows only (offsets re-based, `table.row_range(a, b)`) and owns the
+    matching slice of the refined buffer -- no collective ever touches tables or outputs, no reduction is needed
+    because no row spans ranks;
+  * once per frame the deformed control points are replicated with ONE broadcast from the rank that produced them
+    (`FrameBroadcaster`, double-buffered on a side stream so frame f+1 travels while frame f is evaluated);
+  * a consumer that wants the whole refined buffer on every rank calls `all_gather_rows` (optional, usually skipped).
+
+Everything here is plumbing over torch.distributed: NCCL over NVLink on the GPU box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def balanced_row_ranges(sizes: np.ndarray, world: int, align: int = 1) -> List[Tuple[int, int]]:
+    """`world` contiguous row ranges [a,b) covering [0,n) with near-equal sum(sizes) (+1 per row for the fixed per-row
+    cost: descriptor + output).  `align` rounds interior cut points to a multiple (e.g. the bucketing window)."""
+    n = int(len(sizes))
+    if world <= 1 or n == 0:
+        return [(0, n)] + [(n, n)] * (max(world, 1) - 1)
+    cost = np.cumsum(sizes.astype(np.int64) + 1)
+    total = int(cost[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r // world
+        c = int(np.searchsorted(cost, target, side="left")) + 1
+        if align > 1:
+            c = int(round(c / align)) * align
+        c = min(max(c, cuts[-1]), n)
+        cuts.append(c)
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    rank: int
+    ranges: List[Tuple[int, int]]
+
+    @property
+    def start(self) -> int:
+        return self.ranges[self.rank][0]
+
+    @property
+    def end(self) -> int:
+        return self.ranges[self.rank][1]
+
+    @property
+    def num_rows(self) -> int:
+        return self.end - self.start
+
+    @property
+    def max_rows(self) -> int:
+        return max(b - a for a, b in self.ranges)
+
+    @classmethod
+    def for_table(cls, sizes: np.ndarray, world: int, rank: int, align: int = 1) -> "ShardPlan":
+        return cls(world, rank, balanced_row_ranges(sizes, world, align))
+
+    def imbalance(self, sizes: np.ndarray) -> float:
+        """max shard cost / mean shard cost (1.0 = perfect)."""
+        costs = [float(sizes[a:b].astype(np.int64).sum() + (b - a)) for a, b in self.ranges]
+        return max(costs) / (sum(costs) / len(costs)) if sum(costs) else 1.0
+
+
+def local_table(table, plan: ShardPlan):
+    """This rank's rows as a self-contained reference-layout table (offsets re-based)."""
+    return table.row_range(plan.start, plan.end)
+
+
+class FrameBroadcaster:
+    """Double-buffered per-frame replication of the control points.
+
+    `buffers` are two equally-shaped tensors (CUDA for NCCL, CPU for gloo).  `post(frame)` starts broadcasting the
+    root's data for `frame` into buffers[frame % 2] on a side stream; `wait(frame)` makes the compute stream wait for
+    it and returns the buffer; `release(frame)` records that the compute stream is done reading it.  With CPU
+    tensors (gloo) everything degenerates to synchronous calls."""
+
+    def __init__(self, buffers: Sequence, root: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.buffers = list(buffers)
+        assert len(self.buffers) == 2
+        self.root, self.group = root, group
+        self.cuda = self.buffers[0].is_cuda
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if self.cuda:
+            self.comm_stream = torch.cuda.Stream()
+            self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self.free = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self.free:
+                e.record(torch.cuda.current_stream())
+
+    def post(self, frame: int) -> None:
+        b = frame % 2
+        if not self.active:
+            if self.cuda:
+                self.ready[b].record(self.torch.cuda.current_stream())
+            return
+        if self.cuda:
+            self.comm_stream.wait_event(self.free[b])                 # last reader of this buffer has finished
+            self.comm_stream.wait_stream(self.torch.cuda.current_stream())   # root's producer of this frame
+            with self.torch.cuda.stream(self.comm_stream):
+                self.dist.broadcast(self.buffers[b], src=self.root, group=self.group)
+                self.ready[b].record(self.comm_stream)
+        else:
+            self.dist.broadcast(self.buffers[b], src=self.root, group=self.group)
+
+    def wait(self, frame: int):
+        b = frame % 2
+        if self.cuda:
+            self.torch.cuda.current_stream().wait_event(self.ready[b])
+        return self.buffers[b]
+
+    def release(self, frame: int) -> None:
+        if self.cuda:
+            self.free[frame % 2].record(self.torch.cuda.current_stream())
+
+
+def all_gather_rows(local_rows, plan: ShardPlan, group=None):
+    """Concatenation of every rank's refined rows (row order preserved) -- optional; shards pad to max_rows."""
+    import torch
+    import torch.distributed as dist
+    width = local_rows.shape[1]
+    pad = torch.zeros((plan.max_rows, width), dtype=local_rows.dtype, device=local_rows.device)
+    pad[: plan.num_rows] = local_rows
+    if not (dist.is_available() and dist.is_initialized()) or plan.world == 1:
+        return pad[: plan.num_rows].clone()
+    parts = [torch.empty_like(pad) for _ in range(plan.world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[: b - a] for p, (a, b) in zip(parts, plan.ranges)], dim=0)

@@ -1,0 +1,31 @@
+"""The C++ drop-in classes (include/b200osd/*.h) against the unmodified reference headers: Osd::Mesh<B200VertexBuffer,
+B200StencilTable, B200Evaluator, B200PatchTable> must instantiate, and on a GPU give CpuEvaluator's results."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+BIN = os.path.join(ROOT, "oracle", "_ref", "dropin_test")
+
+
+def test_dropin_program_compiles_against_reference_headers():
+    if not os.path.isdir("/root/reference/opensubdiv"):
+        pytest.skip("reference sources not present")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "ref"), "-j8", "--quiet", "all"])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "ref"), "--quiet", "dropin"])
+    assert os.path.exists(BIN)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([BIN], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 2 and "no CUDA device" in r.stdout      # fails loudly, no CPU fallback
+
+
+@pytest.mark.gpu
+def test_dropin_program_matches_cpu_backend_on_gpu():
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/dropin_test was not built (needs /root/reference at build time)")
+    r = subprocess.run([BIN], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout
+    assert "DROP-IN TEST PASSED" in r.stdout

@@ -1,0 +1,103 @@
+"""Row-range sharding logic on CPU: world_size-2 (and 3) gloo process groups.  The per-rank compute is done by the
+oracle here (test infrastructure standing in for the GPU kernel); what is under test is the partition, the re-based
+per-rank tables, the per-frame broadcast and the gather: concatenated shards == single-table result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+
+from opensubdiv_b200 import shard, synth  # noqa: E402
+
+
+def test_balanced_ranges_cover_and_balance():
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(1, 40, 100_000).astype(np.int32)
+    sizes[5000:5100] = 900                                  # a high-valence cluster
+    for world in (1, 2, 3, 4, 8):
+        ranges = shard.balanced_row_ranges(sizes, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(sizes)
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        plan = shard.ShardPlan(world, 0, ranges)
+        assert plan.imbalance(sizes) < 1.02
+    assert shard.balanced_row_ranges(np.zeros(0, np.int32), 4) == [(0, 0)] * 4
+    ranges = shard.balanced_row_ranges(sizes, 4, align=2048)
+    assert all(a % 2048 == 0 for a, _ in ranges[1:])
+
+
+def test_row_range_tables_are_self_contained():
+    mesh = synth.torus_quads(12, 9)
+    t = synth.uniform_stencil_table(mesh, 2)
+    a, b = 137, 901
+    sub = t.row_range(a, b)
+    assert sub.num_stencils == b - a and sub.offsets[0] == 0
+    assert np.array_equal(np.cumsum(sub.sizes)[:-1], sub.offsets[1:])
+    for r in (0, 17, b - a - 1):
+        o, n = sub.offsets[r], sub.sizes[r]
+        O = t.offsets[a + r]
+        assert np.array_equal(sub.indices[o:o + n], t.indices[O:O + n])
+        assert np.array_equal(sub.weights[o:o + n], t.weights[O:O + n])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, scheme, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+    mesh = synth.torus_quads(16, 10) if scheme == "catmark" else synth.torus_tris(14, 9)
+    table = synth.uniform_stencil_table(mesh, 2)
+    plan = shard.ShardPlan.for_table(table.sizes, world, rank)
+    local = shard.local_table(table, plan)
+    ncv, L = table.num_control_verts, 3
+    bufs = [torch.zeros((ncv, L)), torch.zeros((ncv, L))]
+    bc = shard.FrameBroadcaster(bufs, root=0)
+    results = []
+    for frame in range(3):
+        if rank == 0:                                       # only the root knows the deformed control points
+            bufs[frame % 2].copy_(torch.from_numpy(synth.deform(mesh.positions, frame)))
+        bc.post(frame)
+        cv = bc.wait(frame).numpy()
+        out = np.zeros((local.num_stencils, L), np.float32)
+        assert oracle.eval_stencils(cv.reshape(-1), (0, L, L), [out.reshape(-1)], [(0, L, L)], local.sizes, local.offsets,
+                                    local.indices, [local.weights])
+        bc.release(frame)
+        full = shard.all_gather_rows(torch.from_numpy(out), plan).numpy()
+        ref = np.zeros((table.num_stencils, L), np.float32)
+        oracle.eval_stencils(synth.deform(mesh.positions, frame).reshape(-1), (0, L, L), [ref.reshape(-1)], [(0, L, L)],
+                             table.sizes, table.offsets, table.indices, [table.weights])
+        results.append(bool(np.array_equal(full, ref)))
+    out_q.put((rank, results, plan.ranges))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,scheme", [(2, "catmark"), (3, "loop")])
+def test_sharded_frames_equal_single_table(world, scheme):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, scheme, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, results, ranges in got:
+        assert results == [True, True, True], (rank, results)
+        assert ranges[0][0] == 0
