@@ -266,43 +266,65 @@ def run_b200_arm(args):
     # vertex buffer = [ control block A | control block B | this rank's refined rows ]; A/B are the two halves of the
     # double-buffered per-frame broadcast (frame f lives in block f % 2)
     scene_cv = ncv * meshes_in_scene
-    vb = osd.B200VertexBuffer.Create(L, 2 * scene_cv + n)
+    # ... and two refined regions so that (host-buffer path) the D2H read-back of frame f overlaps frame f+1's kernel
+    vb = osd.B200VertexBuffer.Create(L, 2 * scene_cv + 2 * n)
     assert vb is not None, capi.last_error()
     vt = vb.as_tensor()
     blocks = [vt[:scene_cv], vt[scene_cv:2 * scene_cv]]
     src_descs = [D((b * scene_cv + my_mesh * ncv) * L, L, L) for b in (0, 1)]
-    dst_desc = D(2 * scene_cv * L, L, L)
+    dst_vertex = [2 * scene_cv, 2 * scene_cv + n]
+    dst_descs = [D(v * L, L, L) for v in dst_vertex]
     bc = shard.FrameBroadcaster(blocks, root=0)
 
     frames = [torch.from_numpy(np.tile(frame_primvars(mesh, f), (meshes_in_scene, 1))).pin_memory() for f in range(4)]
-    host_out = torch.empty((n, L), dtype=torch.float32).pin_memory()
+    host_out = [torch.empty((n, L), dtype=torch.float32).pin_memory() for _ in range(2)]
     stream = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
+    kernel_done = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in d2h_done:
+        e.record(stream)
     for b in (0, 1):                                       # device-resident control points for the `value` measurement
         vb.UpdateData(frames[b], b * scene_cv, scene_cv)
     torch.cuda.synchronize()
 
-    def step_device(f):
-        """Device-resident step: (N>1: broadcast of the scene's control points from rank 0 on the side stream,
-        overlapped with the previous frame's kernel) then EvalStencils of this rank's rows."""
-        bc.post(f)
-        bc.wait(f)
-        ok = osd.B200Evaluator.EvalStencils(vb, src_descs[f % 2], vb, dst_desc, tbl)
-        assert ok
-        bc.release(f)
+    # Frames are pipelined: the broadcast of frame f+1 is posted BEFORE frame f's kernel is enqueued, so on the side
+    # stream it only waits for the kernel that last read its buffer (frame f-1) and travels while frame f is evaluated.
+    state = {"f": 0, "posted": -1}
 
-    def step_e2e(f):
-        """Host-buffer step through the C ABI: H2D control points (root), replicate, evaluate, D2H refined vertices."""
-        b = f % 2
-        if rank == 0:
-            vb.UpdateData(frames[f % len(frames)], b * scene_cv, scene_cv)
-        bc.post(f)
+    def advance(e2e):
+        f = state["f"]
+        for g in (f, f + 1):                                   # prologue posts f, steady state posts only f+1
+            if g > state["posted"]:
+                if e2e and rank == 0:                          # host-buffer path: this frame's control points H2D (root)
+                    vb.UpdateData(frames[g % len(frames)], (g % 2) * scene_cv, scene_cv)
+                bc.post(g)
+                state["posted"] = g
         bc.wait(f)
-        ok = osd.B200Evaluator.EvalStencils(vb, src_descs[b], vb, dst_desc, tbl)
+        r = f % 2 if e2e else 0
+        if e2e:
+            stream.wait_event(d2h_done[r])                     # refined region r: read-back of frame f-2 has finished
+        ok = osd.B200Evaluator.EvalStencils(vb, src_descs[f % 2], vb, dst_descs[r], tbl)
         assert ok
         bc.release(f)
-        vb.ReadData(host_out, 2 * scene_cv, n)
+        if e2e:                                                # D2H of this rank's refined vertices on the copy stream
+            kernel_done[r].record(stream)
+            copy_stream.wait_event(kernel_done[r])
+            vb.ReadData(host_out[r], dst_vertex[r], n, deviceContext=copy_stream)
+            d2h_done[r].record(copy_stream)
+        state["f"] = f + 1
+
+    def step_device(_):
+        """Device-resident step: control points already in HBM on the root; (N>1: per-frame broadcast, overlapped
+        with the previous frame's kernel) + EvalStencils of this rank's rows."""
+        advance(False)
+
+    def step_e2e(_):
+        """Host-buffer step through the C ABI: H2D control points (root), replicate, evaluate, D2H refined vertices."""
+        advance(True)
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -319,6 +341,8 @@ def run_b200_arm(args):
         e0.record(stream)
         for k in range(steps):
             step_fn(warmup + k)
+        for e in d2h_done:                                     # read-backs still in flight belong to the timed region
+            stream.wait_event(e)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
