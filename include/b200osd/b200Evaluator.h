@@ -24,6 +24,7 @@
 #include <opensubdiv/osd/types.h>
 
 #include "../b200osd_capi.h"
+#include "b200PatchTable.h"
 #include "b200StencilTable.h"
 #include "b200VertexBuffer.h"
 
@@ -117,9 +118,10 @@ public:
     }
 
     // ------------------------------------------------------------------------------------------- patches ----
-#define B200OSD_PATCH_TRIPLE_VERTEX(pt)  (pt)->GetPatchArrayBuffer(), (pt)->GetPatchIndexBuffer(), (pt)->GetPatchParamBuffer()
-#define B200OSD_PATCH_TRIPLE_VARYING(pt) (pt)->GetVaryingPatchArrayBuffer(), (pt)->GetVaryingPatchIndexBuffer(), (pt)->GetPatchParamBuffer()
-#define B200OSD_PATCH_TRIPLE_FVAR(pt, c) (pt)->GetFVarPatchArrayBuffer(c), (pt)->GetFVarPatchIndexBuffer(c), (pt)->GetFVarPatchParamBuffer(c)
+    // which: 0 vertex, 1 varying, 2+c face-varying channel c (resolved by evalPatchTable below)
+#define B200OSD_PATCH_TRIPLE_VERTEX(pt)  (pt), 0
+#define B200OSD_PATCH_TRIPLE_VARYING(pt) (pt), 1
+#define B200OSD_PATCH_TRIPLE_FVAR(pt, c) (pt), 2 + (c)
 
     template <typename SRC_BUFFER, typename DST_BUFFER, typename PATCHCOORD_BUFFER, typename PATCH_TABLE>
     static bool EvalPatches(SRC_BUFFER *srcBuffer, BufferDescriptor const &srcDesc,
@@ -129,7 +131,7 @@ public:
         (void)instance;
         float *dsts[1] = { dstBuffer->BindCudaBuffer() };
         BufferDescriptor descs[1] = { dstDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), deviceContext);
     }
 
@@ -143,7 +145,7 @@ public:
         (void)instance;
         float *dsts[3] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[3] = { dstDesc, duDesc, dvDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), deviceContext);
     }
 
@@ -161,7 +163,7 @@ public:
         float *dsts[6] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer(),
                            duuBuffer->BindCudaBuffer(), duvBuffer->BindCudaBuffer(), dvvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[6] = { dstDesc, duDesc, dvDesc, duuDesc, duvDesc, dvvDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), deviceContext);
     }
 
@@ -212,7 +214,7 @@ public:
         (void)instance;
         float *dsts[1] = { dstBuffer->BindCudaBuffer() };
         BufferDescriptor descs[1] = { dstDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), deviceContext);
     }
 
@@ -226,7 +228,7 @@ public:
         (void)instance;
         float *dsts[3] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[3] = { dstDesc, duDesc, dvDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), deviceContext);
     }
 
@@ -244,7 +246,7 @@ public:
         float *dsts[6] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer(),
                            duuBuffer->BindCudaBuffer(), duvBuffer->BindCudaBuffer(), dvvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[6] = { dstDesc, duDesc, dvDesc, duuDesc, duvDesc, dvvDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), deviceContext);
     }
 
@@ -257,7 +259,7 @@ public:
         (void)instance;
         float *dsts[1] = { dstBuffer->BindCudaBuffer() };
         BufferDescriptor descs[1] = { dstDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), deviceContext);
     }
 
@@ -271,7 +273,7 @@ public:
         (void)instance;
         float *dsts[3] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[3] = { dstDesc, duDesc, dvDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), deviceContext);
     }
 
@@ -289,7 +291,7 @@ public:
         float *dsts[6] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer(),
                            duuBuffer->BindCudaBuffer(), duvBuffer->BindCudaBuffer(), dvvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[6] = { dstDesc, duDesc, dvDesc, duuDesc, duvDesc, dvvDesc };
-        return evalPatches(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
+        return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
                            patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), deviceContext);
     }
 
@@ -338,6 +340,38 @@ private:
         flatten(n, descs, dd);
         return b200osd_eval_stencils(src, sd, n, dsts, dd, sizes, offsets, indices, weights, start, end,
                                      B200StreamOf(deviceContext)) == B200OSD_OK;
+    }
+
+    // fast path: B200PatchTable owns the handle (and the hull cache)
+    static bool evalPatchTable(const float *src, BufferDescriptor const &srcDesc, int n, float *const *dsts,
+                               BufferDescriptor const *descs, int numPatchCoords, const void *patchCoords,
+                               B200PatchTable const *table, int which, void *deviceContext) {
+        int sd[3] = { srcDesc.offset, srcDesc.length, srcDesc.stride };
+        int dd[6][3];
+        flatten(n, descs, dd);
+        return b200osd_patch_table_eval(table->GetHandle(), which, src, sd, n, dsts, dd, numPatchCoords,
+                                        (const b200osd_patch_coord *)patchCoords, B200StreamOf(deviceContext)) == B200OSD_OK;
+    }
+    static bool evalPatchTable(const float *src, BufferDescriptor const &srcDesc, int n, float *const *dsts,
+                               BufferDescriptor const *descs, int numPatchCoords, const void *patchCoords,
+                               B200PatchTable *table, int which, void *deviceContext) {
+        return evalPatchTable(src, srcDesc, n, dsts, descs, numPatchCoords, patchCoords,
+                              static_cast<B200PatchTable const *>(table), which, deviceContext);
+    }
+
+    // any other patch-table type with the reference's device-pointer accessors (e.g. Osd::CudaPatchTable)
+    template <typename PATCH_TABLE>
+    static bool evalPatchTable(const float *src, BufferDescriptor const &srcDesc, int n, float *const *dsts,
+                               BufferDescriptor const *descs, int numPatchCoords, const void *patchCoords,
+                               PATCH_TABLE *table, int which, void *deviceContext) {
+        if (which == 0)
+            return evalPatches(src, srcDesc, n, dsts, descs, numPatchCoords, patchCoords, table->GetPatchArrayBuffer(),
+                               table->GetPatchIndexBuffer(), table->GetPatchParamBuffer(), deviceContext);
+        if (which == 1)
+            return evalPatches(src, srcDesc, n, dsts, descs, numPatchCoords, patchCoords, table->GetVaryingPatchArrayBuffer(),
+                               table->GetVaryingPatchIndexBuffer(), table->GetPatchParamBuffer(), deviceContext);
+        return evalPatches(src, srcDesc, n, dsts, descs, numPatchCoords, patchCoords, table->GetFVarPatchArrayBuffer(which - 2),
+                           table->GetFVarPatchIndexBuffer(which - 2), table->GetFVarPatchParamBuffer(which - 2), deviceContext);
     }
 
     static bool evalPatches(const float *src, BufferDescriptor const &srcDesc, int n, float *const *dsts,

@@ -52,6 +52,9 @@ public:
     void *GetFVarPatchIndexBuffer(int fvarChannel = 0) const { return buf(2 + fvarChannel, 1); }
     void *GetFVarPatchParamBuffer(int fvarChannel = 0) const { return buf(2 + fvarChannel, 2); }
 
+    /// The C-ABI handle for B200Evaluator's fast path (the table may stage per-patch control hulls).
+    b200osd_patch_table const *GetHandle() const { return _h; }
+
 private:
     static_assert(sizeof(PatchArray) == sizeof(b200osd_patch_array), "Osd::PatchArray layout");
     static_assert(sizeof(PatchParam) == sizeof(b200osd_patch_param), "Osd::PatchParam layout");

@@ -150,10 +150,21 @@ B200OSD_API int b200osd_eval_patches(
         const b200osd_patch_array *patchArrays, const int *patchIndices,
         const b200osd_patch_param *patchParams, void *stream);
 
+/* EvalPatches through the table handle (fast path): which = 0 vertex, 1 varying, 2+c face-varying channel c.
+ * Same contract as b200osd_eval_patches; additionally, when numPatchCoords >= 4 x the number of patches, every
+ * patch's control points are first gathered once into a compact per-patch hull cache owned by the table. */
+B200OSD_API int b200osd_patch_table_eval(const b200osd_patch_table *t, int which,
+        const float *src, const int srcDesc[3],
+        int nOut, float *const dsts[], const int dstDescs[][3],
+        int numPatchCoords, const b200osd_patch_coord *patchCoords, void *stream);
+
 /* ---- tuning / introspection (used by bench.py and the tests; not needed by clients) ---------- */
 /* Selects the stencil kernel variant used by b200osd_stencil_table_eval: 0 = auto. */
 B200OSD_API void b200osd_set_stencil_variant(int variant);
 B200OSD_API int  b200osd_get_stencil_variant(void);
+/* Patch evaluation through the table handle: 0 = auto, 1 = always through the index buffer, 2 = always hull cache. */
+B200OSD_API void b200osd_set_patch_variant(int variant);
+B200OSD_API int  b200osd_get_patch_variant(void);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ SYMBOLS = [
     "b200osd_eval_stencils",
     "b200osd_patch_table_create", "b200osd_patch_table_destroy", "b200osd_patch_table_set",
     "b200osd_patch_table_num_fvar_channels", "b200osd_patch_table_buffer", "b200osd_patch_table_count",
-    "b200osd_eval_patches",
+    "b200osd_eval_patches", "b200osd_patch_table_eval", "b200osd_set_patch_variant", "b200osd_get_patch_variant",
     "b200osd_set_stencil_variant", "b200osd_get_stencil_variant",
 ]
 
@@ -83,6 +83,8 @@ def lib():
     L.b200osd_patch_table_buffer.argtypes = [vp, i, i]
     L.b200osd_patch_table_count.argtypes = [vp, i, i]
     L.b200osd_eval_patches.argtypes = [vp, vp, i, vp, vp, i, vp, vp, vp, vp, vp]
+    L.b200osd_patch_table_eval.argtypes = [vp, i, vp, vp, i, vp, vp, i, vp, vp]
+    L.b200osd_set_patch_variant.argtypes = [i]
     L.b200osd_set_stencil_variant.argtypes = [i]
     _lib = L
     return L

@@ -8,6 +8,7 @@
 //   osd/cudaPatchTable.cpp:69-162                 device copies of PatchArray[], indices, PatchParam[] (+varying, fvar)
 #include "patch_kernels.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -82,17 +83,86 @@ int ensure_box_tables() {
     return B200OSD_OK;
 }
 
-template <int ORDER>
-int launch_patches(const PatchIO &io, int LT, cudaStream_t st) {
-    const int block = 128;
+template <int ORDER, bool HULL>
+int launch_patches_h(const PatchIO &io, int LT, cudaStream_t st) {
+    const int block = kPatchBlock;
     const int grid = (io.n + block - 1) / block;
     switch (LT) {
-        case 1: patch_kernel<1, ORDER><<<grid, block, 0, st>>>(io); break;
-        case 2: patch_kernel<2, ORDER><<<grid, block, 0, st>>>(io); break;
-        case 3: patch_kernel<3, ORDER><<<grid, block, 0, st>>>(io); break;
-        default: patch_kernel<4, ORDER><<<grid, block, 0, st>>>(io); break;
+        case 1: patch_kernel<1, ORDER, HULL><<<grid, block, 0, st>>>(io); break;
+        case 2: patch_kernel<2, ORDER, HULL><<<grid, block, 0, st>>>(io); break;
+        case 3: patch_kernel<3, ORDER, HULL><<<grid, block, 0, st>>>(io); break;
+        default: patch_kernel<4, ORDER, HULL><<<grid, block, 0, st>>>(io); break;
     }
     return check_launch("patch_kernel");
+}
+
+template <int ORDER>
+int launch_patches(const PatchIO &io, int LT, cudaStream_t st) {
+    return io.hull4 ? launch_patches_h<ORDER, true>(io, LT, st) : launch_patches_h<ORDER, false>(io, LT, st);
+}
+
+int g_patch_variant = 0;   // 0 auto, 1 always through the index buffer, 2 always through the hull cache
+
+struct HullRequest {       // filled by b200osd_patch_table_eval when the hull cache should be used
+    float4 *hull4 = nullptr;
+    int hullStride = 0, hullTiles = 0, numArrays = 0, numPatches = 0;
+};
+
+int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float *const dsts[],
+                        const int dstDescs[][3], int numPatchCoords, const b200osd_patch_coord *patchCoords,
+                        const b200osd_patch_array *patchArrays, const int *patchIndices,
+                        const b200osd_patch_param *patchParams, const HullRequest *hull, cudaStream_t st) {
+    const int L = srcDesc[1];
+    int rc = ensure_box_tables();
+    if (rc) return rc;
+    if (hull) {
+        const long long total = (long long)hull->numPatches * hull->hullStride * hull->hullTiles;
+        hull_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src + srcDesc[0], srcDesc[2], L, patchArrays,
+                                                                           hull->numArrays, patchIndices, hull->numPatches,
+                                                                           hull->hullStride, hull->hullTiles, hull->hull4);
+        rc = check_launch("hull_gather_kernel");
+        if (rc) return rc;
+    }
+    // components are evaluated in tiles of at most 4 (xyz, uv, rgba fit in one launch)
+    for (int c0 = 0; c0 < L; c0 += 4) {
+        const int LT = (L - c0) < 4 ? (L - c0) : 4;
+        PatchIO io;
+        io.src = src + srcDesc[0] + c0;
+        io.srcStride = srcDesc[2];
+        for (int k = 0; k < kPatchMaxOut; ++k) { io.dst[k] = nullptr; io.dstStride[k] = 0; }
+        for (int k = 0; k < nOut; ++k)
+            if (dsts[k]) { io.dst[k] = dsts[k] + dstDescs[k][0] + c0; io.dstStride[k] = dstDescs[k][2]; }
+        io.n = numPatchCoords;
+        io.coords = patchCoords;
+        io.arrays = patchArrays;
+        io.indices = patchIndices;
+        io.params = patchParams;
+        io.hull4 = hull ? hull->hull4 : nullptr;
+        io.hullStride = hull ? hull->hullStride : 0;
+        io.hullTiles = hull ? hull->hullTiles : 0;
+        io.tile = c0 / 4;
+        rc = nOut == 1 ? launch_patches<0>(io, LT, st) : (nOut == 3 ? launch_patches<1>(io, LT, st) : launch_patches<2>(io, LT, st));
+        if (rc) return rc;
+    }
+    return B200OSD_OK;
+}
+
+// reference-mirroring argument checks (osd/cpuEvaluator.cpp:165-176,224-241,300-331); *empty = nothing to do
+int validate_patch_args(const float *src, const int srcDesc[3], int nOut, float *const dsts[], const int dstDescs[][3],
+                        int numPatchCoords, bool *empty) {
+    *empty = false;
+    if (nOut != 1 && nOut != 3 && nOut != 6) { set_error("nOut must be 1, 3 or 6 (got %d)", nOut); return B200OSD_ERR_INVALID; }
+    if (!src) { set_error("src is NULL"); return B200OSD_ERR_INVALID; }
+    if (nOut == 1 && !dsts[0]) { set_error("dst is NULL"); return B200OSD_ERR_INVALID; }
+    const int L = srcDesc[1];
+    if (L <= 0) { set_error("srcDesc.length must be positive"); return B200OSD_ERR_INVALID; }
+    for (int k = 0; k < nOut; ++k)
+        if (dsts[k] && dstDescs[k][1] != L) {
+            set_error("output %d length %d != srcDesc.length %d", k, dstDescs[k][1], L);
+            return B200OSD_ERR_INVALID;
+        }
+    if (numPatchCoords <= 0) *empty = true;
+    return B200OSD_OK;
 }
 
 }  // namespace
@@ -106,6 +176,10 @@ struct b200osd_patch_table {
     };
     std::vector<Triple> triples;   // 0 vertex, 1 varying, 2+c fvar channel c
     int numFVar = 0;
+    // hull cache scratch (per-call contents; grown on demand)
+    float4 *d_hull = nullptr;
+    size_t hullCap = 0;
+    std::vector<std::vector<b200osd_patch_array>> hostArrays;   // host copies of the PatchArray descriptors
 };
 
 static void free_triple(b200osd_patch_table::Triple &tr) {
@@ -130,41 +204,62 @@ int b200osd_eval_patches(const float *src, const int srcDesc[3], int nOut, float
                          const int dstDescs[][3], int numPatchCoords, const b200osd_patch_coord *patchCoords,
                          const b200osd_patch_array *patchArrays, const int *patchIndices,
                          const b200osd_patch_param *patchParams, void *stream) {
-    if (nOut != 1 && nOut != 3 && nOut != 6) { set_error("nOut must be 1, 3 or 6 (got %d)", nOut); return B200OSD_ERR_INVALID; }
-    if (!src) { set_error("src is NULL"); return B200OSD_ERR_INVALID; }                          // cpuEvaluator.cpp:165-169
-    if (nOut == 1 && !dsts[0]) { set_error("dst is NULL"); return B200OSD_ERR_INVALID; }         // cpuEvaluator.cpp:170-176
-    const int L = srcDesc[1];
-    if (L <= 0) { set_error("srcDesc.length must be positive"); return B200OSD_ERR_INVALID; }
-    for (int k = 0; k < nOut; ++k)
-        if (dsts[k] && dstDescs[k][1] != L) {
-            set_error("output %d length %d != srcDesc.length %d", k, dstDescs[k][1], L);
-            return B200OSD_ERR_INVALID;
-        }
-    if (numPatchCoords <= 0) return B200OSD_OK;
+    bool empty = false;
+    int rc = validate_patch_args(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, &empty);
+    if (rc || empty) return rc;
     if (!patchCoords || !patchArrays || !patchIndices || !patchParams) { set_error("patch table / coords are NULL"); return B200OSD_ERR_INVALID; }
-    int rc = ensure_box_tables();
-    if (rc) return rc;
-
-    cudaStream_t st = (cudaStream_t)stream;
-    // components are evaluated in tiles of at most 4 (xyz, uv, rgba fit in one launch)
-    for (int c0 = 0; c0 < L; c0 += 4) {
-        const int LT = (L - c0) < 4 ? (L - c0) : 4;
-        PatchIO io;
-        io.src = src + srcDesc[0] + c0;
-        io.srcStride = srcDesc[2];
-        for (int k = 0; k < kPatchMaxOut; ++k) { io.dst[k] = nullptr; io.dstStride[k] = 0; }
-        for (int k = 0; k < nOut; ++k)
-            if (dsts[k]) { io.dst[k] = dsts[k] + dstDescs[k][0] + c0; io.dstStride[k] = dstDescs[k][2]; }
-        io.n = numPatchCoords;
-        io.coords = patchCoords;
-        io.arrays = patchArrays;
-        io.indices = patchIndices;
-        io.params = patchParams;
-        rc = nOut == 1 ? launch_patches<0>(io, LT, st) : (nOut == 3 ? launch_patches<1>(io, LT, st) : launch_patches<2>(io, LT, st));
-        if (rc) return rc;
-    }
-    return B200OSD_OK;
+    return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, patchArrays, patchIndices,
+                               patchParams, nullptr, (cudaStream_t)stream);
 }
+
+int b200osd_patch_table_eval(const b200osd_patch_table *tc, int which, const float *src, const int srcDesc[3], int nOut,
+                             float *const dsts[], const int dstDescs[][3], int numPatchCoords,
+                             const b200osd_patch_coord *patchCoords, void *stream) {
+    b200osd_patch_table *t = const_cast<b200osd_patch_table *>(tc);
+    if (!t || which < 0 || which >= (int)t->triples.size()) { set_error("patch_table_eval: bad table / slot"); return B200OSD_ERR_INVALID; }
+    bool empty = false;
+    int rc = validate_patch_args(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, &empty);
+    if (rc || empty) return rc;
+    const b200osd_patch_table::Triple &tr = t->triples[which];
+    const b200osd_patch_param *params = tr.params;
+    int numPatches = tr.nParams;
+    if (which == 1 && !params) { params = t->triples[0].params; numPatches = t->triples[0].nParams; }   // varying shares vertex params
+    if (!patchCoords || !tr.arrays || !tr.indices || !params) { set_error("patch table slot %d is empty", which); return B200OSD_ERR_INVALID; }
+
+    // Hull cache: when many coordinates share few patches, gather every patch's control points once per call into
+    // 16-byte rows so that a coordinate reads one compact, aligned block instead of 16-20 scattered vertices.
+    HullRequest hull;
+    bool useHull = (g_patch_variant == 2) || (g_patch_variant == 0 && (long long)numPatchCoords >= 4LL * numPatches);
+    if (useHull && numPatches > 0) {
+        int hs = 0;
+        for (int a = 0; a < tr.nArrays; ++a) hs = std::max(hs, t->hostArrays[which][a].stride);
+        const int tiles = (srcDesc[1] + 3) / 4;
+        const size_t need = (size_t)numPatches * hs * tiles;
+        if (need > t->hullCap) {
+            cudaFree(t->d_hull);
+            t->d_hull = nullptr;
+            t->hullCap = 0;
+            if (cudaMalloc((void **)&t->d_hull, need * sizeof(float4)) != cudaSuccess) {
+                cudaGetLastError();
+                useHull = false;                      // not enough memory for the cache: evaluate through the indices
+            } else {
+                t->hullCap = need;
+            }
+        }
+        if (useHull) {
+            hull.hull4 = t->d_hull;
+            hull.hullStride = hs;
+            hull.hullTiles = tiles;
+            hull.numArrays = tr.nArrays;
+            hull.numPatches = numPatches;
+        }
+    }
+    return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, tr.arrays, tr.indices,
+                               params, useHull ? &hull : nullptr, (cudaStream_t)stream);
+}
+
+void b200osd_set_patch_variant(int v) { g_patch_variant = v; }
+int b200osd_get_patch_variant(void) { return g_patch_variant; }
 
 // -------------------------------------------------------------------------------- patch table --
 b200osd_patch_table *b200osd_patch_table_create(int numFVarChannels) {
@@ -173,6 +268,7 @@ b200osd_patch_table *b200osd_patch_table_create(int numFVarChannels) {
     if (!t) return nullptr;
     t->numFVar = numFVarChannels;
     t->triples.resize(2 + numFVarChannels);
+    t->hostArrays.resize(2 + numFVarChannels);
     return t;
 }
 
@@ -180,6 +276,7 @@ b200osd_patch_table *b200osd_patch_table_create(int numFVarChannels) {
 void b200osd_patch_table_destroy(b200osd_patch_table *t) {
     if (!t) return;
     for (auto &tr : t->triples) free_triple(tr);
+    cudaFree(t->d_hull);
     delete t;
 }
 
@@ -192,6 +289,7 @@ int b200osd_patch_table_set(b200osd_patch_table *t, int which, int numArrays, co
     if (!rc) rc = upload_array(&tr.indices, indices, numIndices);
     if (!rc) rc = upload_array(&tr.params, params, numParams);
     if (rc) { free_triple(tr); return rc; }
+    t->hostArrays[which].assign(arrays, arrays + (arrays ? numArrays : 0));
     tr.nArrays = tr.arrays ? numArrays : 0;
     tr.nIndices = tr.indices ? numIndices : 0;
     tr.nParams = tr.params ? numParams : 0;

@@ -38,6 +38,12 @@ struct PatchIO {
     const b200osd_patch_array *arrays;
     const int *indices;
     const b200osd_patch_param *params;
+    // optional per-frame hull cache (see hull_gather_kernel): control points of every patch gathered into
+    // 16-byte rows, [patch][tile][point]; used when many coordinates share few patches
+    const float4 *hull4;
+    int hullStride;                   // points per patch slot (max array stride)
+    int hullTiles;                    // ceil(L / 4)
+    int tile;                         // component tile evaluated by this launch
 };
 
 enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_BASIS = 9, PT_GREGORY_TRIANGLE = 10 };
@@ -164,15 +170,68 @@ B200_HD void bezier_1d(float t, float (&b)[4], float (&d)[4], float (&dd)[4]) {
 B200_HD void fold_lo(float (&w)[4]) { w[2] -= w[0]; w[1] = fmaf(2.0f, w[0], w[1]); w[0] = 0.0f; }
 B200_HD void fold_hi(float (&w)[4]) { w[1] -= w[3]; w[2] = fmaf(2.0f, w[3], w[2]); w[3] = 0.0f; }
 
-template <int LT>
-B200_HD void load_cv(const float *src, int stride, int idx, float (&v)[LT]) {
-    const float *p = src + (size_t)idx * (size_t)stride;
+// Control-point access of one patch: either through the patch's index list into the caller's primvar buffer ...
+struct CvIndirect {
+    const float *src;
+    int stride;
+    const int *cvs;
+    template <int LT>
+    B200_HD void load(int j, float (&v)[LT]) const {
+        const float *p = src + (size_t)ldg_i(cvs + j) * (size_t)stride;
 #pragma unroll
-    for (int c = 0; c < LT; ++c) v[c] = ldg_f(p + c);
-}
+        for (int c = 0; c < LT; ++c) v[c] = ldg_f(p + c);
+    }
+};
+// ... or from the hull cache: point j of this patch's component tile is one aligned 16-byte row
+struct CvHull {
+    const float4 *base;
+    template <int LT>
+    B200_HD void load(int j, float (&v)[LT]) const {
+#ifdef __CUDA_ARCH__
+        const float4 t = __ldg(base + j);
+#else
+        const float4 t = base[j];
+#endif
+        if (LT > 0) v[0] = t.x;
+        if (LT > 1) v[1] = t.y;
+        if (LT > 2) v[2] = t.z;
+        if (LT > 3) v[3] = t.w;
+    }
+};
 
+constexpr int kPatchBlock = 128;
+
+// Results leave through shared memory: a warp's 32 x LT values of one output are transposed so that consecutive lanes
+// write consecutive floats (one 128-byte request per 32 floats when the output is packed, runs of LT otherwise)
+// instead of 32 scattered LT-float records.  `live` = this lane holds a real coordinate; i0 = the warp's first one.
 template <int LT, int NSETS>
-B200_HD void store_outputs(const PatchIO &io, int i, const float (&out)[NSETS][LT]) {
+B200_HD void store_outputs(const PatchIO &io, int i, bool live, const float (&out)[NSETS][LT]) {
+#ifdef __CUDA_ARCH__
+    __shared__ float stage[kPatchBlock / 32][32 * LT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = i - lane;
+    const int nlive = min(32, io.n - i0);
+    float *st = stage[warp];
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k) {
+        float *d = io.dst[k];
+        if (!d) continue;                                   // uniform across the block
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < LT; ++c) st[lane * LT + c] = out[k][c];
+        __syncwarp();
+        const size_t stride = (size_t)io.dstStride[k];
+        float *base = d + (size_t)i0 * stride;
+#pragma unroll
+        for (int q = 0; q < LT; ++q) {
+            const int e = q * 32 + lane;
+            const int ci = e / LT, c = e - ci * LT;
+            if (ci < nlive) st_stream_f1(base + (size_t)ci * stride + c, st[e]);
+        }
+    }
+    (void)live;
+#else
+    if (!live) return;
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) {
         float *d = io.dst[k];
@@ -181,12 +240,13 @@ B200_HD void store_outputs(const PatchIO &io, int i, const float (&out)[NSETS][L
 #pragma unroll
         for (int c = 0; c < LT; ++c) st_out(d + c, out[k][c]);
     }
+#endif
 }
 
 // -------------------------------------------------------------------------------- REGULAR path --
-template <int LT, int ORDER>
-B200_HD void eval_regular(const PatchIO &io, const int *cvs, float s, float t, int boundary,
-                                             float d1, float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
+template <int LT, int ORDER, typename CV>
+B200_HD void eval_regular(const CV &cv, float s, float t, int boundary,
+                          float d1, float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     float bs[4], ds[4], dss[4], bt[4], dt[4], dtt[4];
     bspline_1d<ORDER>(s, bs, ds, dss);
     bspline_1d<ORDER>(t, bt, dt, dtt);
@@ -212,16 +272,13 @@ B200_HD void eval_regular(const PatchIO &io, const int *cvs, float s, float t, i
 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int id[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) id[j] = ldg_i(cvs + 4 * i + j);
         float r0[LT], r1[LT], r2[LT];
 #pragma unroll
         for (int c = 0; c < LT; ++c) { r0[c] = 0.0f; r1[c] = 0.0f; r2[c] = 0.0f; }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float v[LT];
-            load_cv<LT>(io.src, io.srcStride, id[j], v);
+            cv.template load<LT>(4 * i + j, v);
 #pragma unroll
             for (int c = 0; c < LT; ++c) {
                 r0[c] = fmaf(bs[j], v[c], r0[c]);
@@ -250,9 +307,9 @@ B200_HD void eval_regular(const PatchIO &io, const int *cvs, float s, float t, i
 // the rational blend G+ = a/(a+b), G- = 1-G+ with (a,b) the distances from corner c along E+ / E-
 // (osd/patchBasis.h:345-378); the reciprocal is replaced by 1 when a+b <= 0.  Derivatives use the reference's
 // default approximation: Bezier derivative weights times the same G (osd/patchBasis.h:421-440).
-template <int LT, int ORDER>
-B200_HD void eval_gregory(const PatchIO &io, const int *cvs, float s, float t, float d1,
-                                             float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
+template <int LT, int ORDER, typename CV>
+B200_HD void eval_gregory(const CV &cv, float s, float t, float d1,
+                          float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     constexpr int COL[20] = { 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2, 0, 0, 1, 1, 1 };
     constexpr int ROW[20] = { 0, 0, 1, 1, 1, 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2 };
     float bs[4], ds[4], dss[4], bt[4], dt[4], dtt[4];
@@ -288,7 +345,7 @@ B200_HD void eval_gregory(const PatchIO &io, const int *cvs, float s, float t, f
         const int col = COL[i], row = ROW[i], p = i % 5;
         const float g = (p >= 3) ? G[2 * (i / 5) + (p - 3)] : 1.0f;
         float v[LT];
-        load_cv<LT>(io.src, io.srcStride, ldg_i(cvs + i), v);
+        cv.template load<LT>(i, v);
         const float gs = bs[col] * g, gt = bt[row];
         float w[NSETS];
         w[0] = gs * gt;
@@ -302,9 +359,9 @@ B200_HD void eval_gregory(const PatchIO &io, const int *cvs, float s, float t, f
 }
 
 // ---------------------------------------------------------------------------------- QUADS path --
-template <int LT, int ORDER>
-B200_HD void eval_quads(const PatchIO &io, const int *cvs, float s, float t, float d1,
-                                           float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
+template <int LT, int ORDER, typename CV>
+B200_HD void eval_quads(const CV &cv, float s, float t, float d1,
+                        float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     const float sc = 1.0f - s, tc = 1.0f - t;
     const float wP[4] = { sc * tc, s * tc, s * t, sc * t };
     const float wS[4] = { -tc * d1, tc * d1, t * d1, -t * d1 };
@@ -319,7 +376,7 @@ B200_HD void eval_quads(const PatchIO &io, const int *cvs, float s, float t, flo
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float v[LT];
-        load_cv<LT>(io.src, io.srcStride, ldg_i(cvs + i), v);
+        cv.template load<LT>(i, v);
 #pragma unroll
         for (int c = 0; c < LT; ++c) {
             out[0][c] = fmaf(wP[i], v[c], out[0][c]);
@@ -446,61 +503,23 @@ B200_HD_NOINLINE int tri_weights(int type, float s, float t, int boundary, float
 }
 
 // --------------------------------------------------------------------------------------- kernel --
-template <int LT, int ORDER>
-B200_HD void patch_eval_coord(const PatchIO &io, int i) {
+template <int LT, int ORDER, typename CV>
+B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int boundary, float d1, float sign,
+                             float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
-
-    const int *cw = reinterpret_cast<const int *>(io.coords + i);
-    const int arrayIndex = ld_coord_word(cw + 0);
-    const int patchIndex = ld_coord_word(cw + 1);
-    float s = int_as_float(ld_coord_word(cw + 3));
-    float t = int_as_float(ld_coord_word(cw + 4));
-
-    const int *aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
-    const int regDesc = ldg_i(aw + 0), irrDesc = ldg_i(aw + 1);
-    const int indexBase = ldg_i(aw + 3), stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
-    const unsigned field1 = ldg_u(&io.params[patchIndex].field1);
-
-    const int depth = (int)(field1 & 0xfu);
-    const int nonquad = (int)((field1 >> 4) & 1u);
-    const bool regular = ((field1 >> 5) & 1u) != 0;
-    const int boundary = (int)((field1 >> 7) & 0x1fu);
-    const int pv = (int)((field1 >> 12) & 0x3ffu), pu = (int)((field1 >> 22) & 0x3ffu);
-    const int type = regular ? regDesc : irrDesc;
-    const int *cvs = io.indices + indexBase + stride * (patchIndex - primBase);
-
-    const float fracInv = (float)(1 << (depth - nonquad));
-    const bool isTri = (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES);
-    float sign = 1.0f;
-    if (isTri && (pu + pv) >= (1 << depth)) {
-        const int df = 1 << depth;
-        s = (float)(df - pu) - s * fracInv;
-        t = (float)(df - pv) - t * fracInv;
-        sign = -1.0f;
-    } else {
-        s = fmaf(s, fracInv, -(float)pu);
-        t = fmaf(t, fracInv, -(float)pv);
-    }
-    const float d1 = sign * (float)(1 << depth);
-
-    float out[NSETS][LT];
     if (type == PT_REGULAR) {
-        eval_regular<LT, ORDER>(io, cvs, s, t, boundary, d1, out);
+        eval_regular<LT, ORDER>(cv, s, t, boundary, d1, out);
     } else if (type == PT_GREGORY_BASIS) {
-        eval_gregory<LT, ORDER>(io, cvs, s, t, d1, out);
+        eval_gregory<LT, ORDER>(cv, s, t, d1, out);
     } else if (type == PT_QUADS) {
-        eval_quads<LT, ORDER>(io, cvs, s, t, d1, out);
-    } else if (isTri) {
+        eval_quads<LT, ORDER>(cv, s, t, d1, out);
+    } else if (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES) {
         float w[NSETS][20];
         const int np = tri_weights<ORDER>(type, s, t, boundary, w);
         const float d2 = sign * d1 * d1;     // osd/patchBasis.h:1598: d2Scale = derivSign * d1Scale * d1Scale
-#pragma unroll
-        for (int k = 0; k < NSETS; ++k)
-#pragma unroll
-            for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
         for (int j = 0; j < np; ++j) {
             float v[LT];
-            load_cv<LT>(io.src, io.srcStride, ldg_i(cvs + j), v);
+            cv.template load<LT>(j, v);
 #pragma unroll
             for (int k = 0; k < NSETS; ++k) {
                 const float wk = w[k][j] * (k == 0 ? 1.0f : (k < 3 ? d1 : d2));
@@ -508,22 +527,102 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i) {
                 for (int c = 0; c < LT; ++c) out[k][c] = fmaf(wk, v[c], out[k][c]);
             }
         }
-    } else {
-        // unknown descriptor: the reference evaluates zero points, i.e. writes zeros
-#pragma unroll
-        for (int k = 0; k < NSETS; ++k)
-#pragma unroll
-            for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
     }
-    store_outputs<LT, NSETS>(io, i, out);
+    // unknown descriptor: the reference evaluates zero points, i.e. writes zeros
+}
+
+template <int LT, int ORDER, bool HULL>
+B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+    float out[NSETS][LT];
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+        for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+
+    if (live) {
+        const int *cw = reinterpret_cast<const int *>(io.coords + i);
+        const int arrayIndex = ld_coord_word(cw + 0);
+        const int patchIndex = ld_coord_word(cw + 1);
+        float s = int_as_float(ld_coord_word(cw + 3));
+        float t = int_as_float(ld_coord_word(cw + 4));
+
+        const int *aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
+        const int regDesc = ldg_i(aw + 0), irrDesc = ldg_i(aw + 1);
+        const unsigned field1 = ldg_u(&io.params[patchIndex].field1);
+
+        const int depth = (int)(field1 & 0xfu);
+        const int nonquad = (int)((field1 >> 4) & 1u);
+        const bool regular = ((field1 >> 5) & 1u) != 0;
+        const int boundary = (int)((field1 >> 7) & 0x1fu);
+        const int pv = (int)((field1 >> 12) & 0x3ffu), pu = (int)((field1 >> 22) & 0x3ffu);
+        const int type = regular ? regDesc : irrDesc;
+
+        const float fracInv = (float)(1 << (depth - nonquad));
+        const bool isTri = (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES);
+        float sign = 1.0f;
+        if (isTri && (pu + pv) >= (1 << depth)) {
+            const int df = 1 << depth;
+            s = (float)(df - pu) - s * fracInv;
+            t = (float)(df - pv) - t * fracInv;
+            sign = -1.0f;
+        } else {
+            s = fmaf(s, fracInv, -(float)pu);
+            t = fmaf(t, fracInv, -(float)pv);
+        }
+        const float d1 = sign * (float)(1 << depth);
+
+        if (HULL) {
+            CvHull cv;
+            cv.base = io.hull4 + ((size_t)patchIndex * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)io.hullStride;
+            eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
+        } else {
+            const int indexBase = ldg_i(aw + 3), stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
+            CvIndirect cv;
+            cv.src = io.src;
+            cv.stride = io.srcStride;
+            cv.cvs = io.indices + indexBase + stride * (patchIndex - primBase);
+            eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
+        }
+    }
+    store_outputs<LT, NSETS>(io, i, live, out);
 }
 
 #ifdef __CUDACC__
-template <int LT, int ORDER>
-__global__ void __launch_bounds__(128) patch_kernel(PatchIO io) {
+template <int LT, int ORDER, bool HULL>
+__global__ void __launch_bounds__(kPatchBlock) patch_kernel(PatchIO io) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= io.n) return;
-    patch_eval_coord<LT, ORDER>(io, i);
+    if (i - (int)(threadIdx.x & 31) >= io.n) return;          // whole warp past the end
+    patch_eval_coord<LT, ORDER, HULL>(io, i, i < io.n);
+}
+
+// Hull cache fill: one thread per (patch, point, component tile).  The patch's control point j (through the index
+// buffer) is copied into the 16-byte row [patch][tile][j]; rows past the patch's own point count are left untouched.
+__global__ void __launch_bounds__(256) hull_gather_kernel(const float *src, int srcStride, int L,
+                                                          const b200osd_patch_array *arrays, int numArrays,
+                                                          const int *indices, int numPatches, int hullStride,
+                                                          int hullTiles, float4 *hull4) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)numPatches * hullStride * hullTiles;
+    if (gid >= total) return;
+    const int j = (int)(gid % hullStride);
+    const int tile = (int)((gid / hullStride) % hullTiles);
+    const int p = (int)(gid / ((long long)hullStride * hullTiles));
+    int a = 0;
+    for (; a < numArrays; ++a) {
+        const int base = arrays[a].primitiveIdBase;
+        if (p >= base && p < base + arrays[a].numPatches) break;
+    }
+    if (a == numArrays || j >= arrays[a].stride) return;
+    const int cv = indices[arrays[a].indexBase + arrays[a].stride * (p - arrays[a].primitiveIdBase) + j];
+    const float *q = src + (size_t)cv * (size_t)srcStride + 4 * tile;
+    const int rem = L - 4 * tile;
+    float4 r;
+    r.x = q[0];
+    r.y = rem > 1 ? q[1] : 0.0f;
+    r.z = rem > 2 ? q[2] : 0.0f;
+    r.w = rem > 3 ? q[3] : 0.0f;
+    hull4[((size_t)p * hullTiles + tile) * hullStride + j] = r;
 }
 #endif
 

@@ -328,11 +328,26 @@ class B200Evaluator:
         return outs, rest
 
     @staticmethod
+    def _eval_patch_table(srcBuffer, srcDesc, outs, numPatchCoords, patchCoords, patchTable, which, deviceContext) -> bool:
+        """Through the table handle (fast path: the table may stage per-patch control hulls)."""
+        n = len(outs)
+        if n not in (1, 3, 6):
+            raise TypeError("EvalPatches expects 1, 3 or 6 (buffer, descriptor) outputs")
+        sd = _desc(srcDesc).as_c()
+        dsts = (C.c_void_p * n)(*[_dev_ptr(b) for b, _ in outs])
+        dds = (C.c_int * (3 * n))(*[v for _, d in outs for v in (d.offset, d.length, d.stride)])
+        rc = capi.lib().b200osd_patch_table_eval(patchTable._h, which, _dev_ptr(srcBuffer), sd, n, dsts, dds, numPatchCoords,
+                                                 _dev_ptr(patchCoords), _stream_ptr(deviceContext))
+        return capi.check(rc, "B200Evaluator::EvalPatches")
+
+    @staticmethod
     def EvalPatches(srcBuffer, srcDesc, *args, deviceContext=None) -> bool:
         """EvalPatches(src, srcDesc, dst, dstDesc [, du, duDesc, dv, dvDesc [, duu.., duv.., dvv..]],
                        numPatchCoords, patchCoords, patchTable [, instance [, deviceContext]])   (osd/cudaEvaluator.h:502-677)"""
         outs, rest = B200Evaluator._parse_patch_args(args)
         n, coords, pt = rest[0], rest[1], rest[2]
+        if isinstance(pt, B200PatchTable):
+            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 0, deviceContext)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetPatchArrayBuffer(),
                                            pt.GetPatchIndexBuffer(), pt.GetPatchParamBuffer(), deviceContext)
 
@@ -341,6 +356,8 @@ class B200Evaluator:
         """Same kernel on the varying triple + vertex PatchParams (osd/cudaEvaluator.h:857-1036)."""
         outs, rest = B200Evaluator._parse_patch_args(args)
         n, coords, pt = rest[0], rest[1], rest[2]
+        if isinstance(pt, B200PatchTable):
+            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 1, deviceContext)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetVaryingPatchArrayBuffer(),
                                            pt.GetVaryingPatchIndexBuffer(), pt.GetPatchParamBuffer(), deviceContext)
 
@@ -350,6 +367,8 @@ class B200Evaluator:
         outs, rest = B200Evaluator._parse_patch_args(args)
         n, coords, pt = rest[0], rest[1], rest[2]
         ch = rest[3] if len(rest) > 3 and isinstance(rest[3], (int, np.integer)) else 0
+        if isinstance(pt, B200PatchTable):
+            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 2 + ch, deviceContext)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetFVarPatchArrayBuffer(ch),
                                            pt.GetFVarPatchIndexBuffer(ch), pt.GetFVarPatchParamBuffer(ch), deviceContext)
 

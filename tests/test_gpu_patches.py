@@ -6,7 +6,7 @@ import torch
 
 import opensubdiv_b200 as osd
 from opensubdiv_b200 import synth
-from tests.gpu_util import D, dev, coords_dev, oracle_patches, oracle_stencils
+from tests.gpu_util import D, dev, coords_dev, oracle_patches, oracle_stencils, set_patch_variant
 from tests.util import golden, golden_names, table_from, triple_from, assert_close, REL_TOL
 
 pytestmark = pytest.mark.gpu
@@ -31,16 +31,27 @@ def test_golden_patch_tables_all_arities(name):
     pc = coords_dev(coords)
     src = dev(d["vb"])
     scales = oracle_patches(d["vb"], (0, 3, 3), 3, coords, vtx, 6, abs_scale=True)
-    for nw in (1, 3, 6):
+    for variant in (0, 1, 2):          # auto, through the index buffer, through the per-patch hull cache
+      for nw in (1, 3, 6):
         # outputs interleaved in one buffer, glEvalLimit style (examples/glEvalLimit/glEvalLimit.cpp:277-287)
         out = torch.full((n, 3 * nw), float("nan"), device="cuda")
         args = []
         for k in range(nw):
             args += [out, D(3 * k, 3, 3 * nw)]
-        assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+        set_patch_variant(variant)
+        try:
+            assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+        finally:
+            set_patch_variant(0)
         res = out.cpu().numpy()
         for k in range(nw):
-            assert_close(res[:, 3 * k:3 * k + 3], d["out_" + OUT6[k]], scales[k], f"{name} nw={nw} {OUT6[k]}")
+            assert_close(res[:, 3 * k:3 * k + 3], d["out_" + OUT6[k]], scales[k], f"{name} variant={variant} nw={nw} {OUT6[k]}")
+    # raw-pointer overload (reference-layout device arrays, osd/cudaEvaluator.h:815-827)
+    outs = [torch.zeros((n, 3), device="cuda") for _ in range(6)]
+    assert osd.B200Evaluator.EvalPatchesRaw(src, D(0, 3, 3), [(o, D(0, 3, 3)) for o in outs], n, pc, pt.GetPatchArrayBuffer(),
+                                            pt.GetPatchIndexBuffer(), pt.GetPatchParamBuffer())
+    for k in range(6):
+        assert_close(outs[k].cpu().numpy(), d["out_" + OUT6[k]], scales[k], f"{name} raw {OUT6[k]}")
     if var is not None:
         vsrc = dev(d["var_vb"])
         vs = oracle_patches(d["var_vb"], (0, 3, 3), 3, coords, var, 3, abs_scale=True)
@@ -58,9 +69,14 @@ def test_golden_patch_tables_all_arities(name):
         args = []
         for o in outs:
             args += [o, D(0, 2, 2)]
-        assert osd.B200Evaluator.EvalPatchesFaceVarying(fsrc, D(0, 2, 2), *args, n, pc, pt, 0, None)
-        for k in range(6):
-            assert_close(outs[k].cpu().numpy(), d["fvar_out_" + OUT6[k]], fs[k], f"{name} fvar {OUT6[k]}")
+        for variant in (1, 2):
+            set_patch_variant(variant)
+            try:
+                assert osd.B200Evaluator.EvalPatchesFaceVarying(fsrc, D(0, 2, 2), *args, n, pc, pt, 0, None)
+            finally:
+                set_patch_variant(0)
+            for k in range(6):
+                assert_close(outs[k].cpu().numpy(), d["fvar_out_" + OUT6[k]], fs[k], f"{name} fvar v{variant} {OUT6[k]}")
 
 
 def test_refine_then_evaluate_pipeline():
@@ -101,16 +117,21 @@ def test_primvar_lengths_and_null_outputs(L, stride, offset):
     exp = oracle_patches(src, (offset, L, stride), L, coords, vtx, 6)
     scl = oracle_patches(src, (offset, L, stride), L, coords, vtx, 6, abs_scale=True)
     pt = osd.B200PatchTable.Create(_PT(vtx))
-    outs = [torch.full((n, L), float("nan"), device="cuda") for _ in range(6)]
-    # NULL du and dvv are skipped (osd/cudaKernel.cu:300-327)
-    bufs = [outs[0], None, outs[2], outs[3], outs[4], None]
-    args = []
-    for b in bufs:
-        args += [b, D(0, L, L)]
-    assert osd.B200Evaluator.EvalPatches(dev(src), D(offset, L, stride), *args, n, coords_dev(coords), pt, None)
-    for k in (0, 2, 3, 4):
-        assert_close(outs[k].cpu().numpy(), exp[k], scl[k], f"L={L} {OUT6[k]}")
-    assert torch.isnan(outs[1]).all() and torch.isnan(outs[5]).all()
+    for variant in (1, 2):
+        outs = [torch.full((n, L), float("nan"), device="cuda") for _ in range(6)]
+        # NULL du and dvv are skipped (osd/cudaKernel.cu:300-327)
+        bufs = [outs[0], None, outs[2], outs[3], outs[4], None]
+        args = []
+        for b in bufs:
+            args += [b, D(0, L, L)]
+        set_patch_variant(variant)
+        try:
+            assert osd.B200Evaluator.EvalPatches(dev(src), D(offset, L, stride), *args, n, coords_dev(coords), pt, None)
+        finally:
+            set_patch_variant(0)
+        for k in (0, 2, 3, 4):
+            assert_close(outs[k].cpu().numpy(), exp[k], scl[k], f"L={L} v{variant} {OUT6[k]}")
+        assert torch.isnan(outs[1]).all() and torch.isnan(outs[5]).all()
     # errors: NULL src, value-only NULL dst, length mismatch -> false (osd/cpuEvaluator.cpp:165-176)
     assert not osd.B200Evaluator.EvalPatches(None, D(0, L, L), outs[0], D(0, L, L), n, coords_dev(coords), pt, None)
     assert not osd.B200Evaluator.EvalPatches(dev(src), D(0, L, stride), None, D(0, L, L), n, coords_dev(coords), pt, None)
