@@ -237,7 +237,18 @@ def run_b200_arm(args):
         raise SystemExit("bench.py needs a GPU: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL kernels on a high-priority stream: their few CTAs are dispatched as soon as an SM slot frees up instead
+        # of queueing behind the 25 000-block evaluation grid (which would serialise broadcast and kernel)
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+        except Exception:
+            opts = None
+        if opts is not None:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     D = osd.BufferDescriptor
     lib = capi.lib()
 
@@ -332,7 +343,7 @@ def run_b200_arm(args):
             for b in (0, 1):                                   # both blocks valid everywhere before the first replay
                 dist.broadcast(blocks[b], src=0)
             torch.cuda.synchronize()
-            comm = torch.cuda.Stream()
+            comm = torch.cuda.Stream(priority=-1)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 cur = torch.cuda.current_stream()
@@ -451,7 +462,12 @@ def run_b200_arm(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: destroying a process group that a captured graph still references can hang
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

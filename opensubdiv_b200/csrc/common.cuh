@@ -54,6 +54,11 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2 *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ int ld_stream_i1(const int *p) {
     int r;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));

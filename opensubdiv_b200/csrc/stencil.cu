@@ -31,9 +31,11 @@ struct b200osd_stencil_table {
     int window = 0;
     int numSlices = 0;
     size_t totalVec = 0;
+    bool idx16 = false;                  // indices stored as 16-bit offsets from a per-slice base
     int4 *d_idx4 = nullptr;
+    uint2 *d_idx16 = nullptr;
     float4 *d_w4[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    int2 *d_meta = nullptr;
+    int4 *d_meta = nullptr;
     int *d_rows = nullptr;
     std::vector<int> windowSliceStart;   // host: first slice of each window (+ sentinel)
     // per-call scratch: 16-byte packed copy of the control vertices
@@ -66,7 +68,7 @@ int upload(T **dptr, const T *host, size_t count) {
 }
 
 int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, const int *indices,
-               const float *const w[kMaxOut], bool localitySort) {
+               const float *const w[kMaxOut], bool localitySort, bool allowIdx16) {
     const int n = t->n;
     std::vector<int> rowKey;
     if (localitySort) {
@@ -80,8 +82,9 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
     t->window = kWindowRows;
     const int numWindows = (n + kWindowRows - 1) / kWindowRows;
     std::vector<int> order(n);
-    std::vector<int2> meta;
+    std::vector<int4> meta;
     std::vector<int> rows;
+    bool fits16 = allowIdx16;
     t->windowSliceStart.assign(numWindows + 1, 0);
     meta.reserve(n / kSliceRows + numWindows);
     rows.reserve((size_t)n + (size_t)numWindows * kSliceRows);
@@ -105,14 +108,24 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
         t->windowSliceStart[wdw] = (int)meta.size();
         for (int s0 = r0; s0 < r1; s0 += kSliceRows) {
             const int s1 = std::min(r1, s0 + kSliceRows);
-            int maxSize = 0;
-            for (int q = s0; q < s1; ++q) maxSize = std::max(maxSize, sizes[order[q]]);
+            int maxSize = 0, lo = 0x7fffffff, hi = -1;
+            for (int q = s0; q < s1; ++q) {
+                const int r = order[q];
+                maxSize = std::max(maxSize, sizes[r]);
+                for (int j = 0; j < sizes[r]; ++j) {
+                    const int ix = indices[offsets[r] + j];
+                    lo = std::min(lo, ix);
+                    hi = std::max(hi, ix);
+                }
+            }
+            if (hi < 0) { lo = 0; hi = 0; }
+            if (hi - lo > 0xffff) fits16 = false;
             const int lenVec = (maxSize + kVec - 1) / kVec;
             if (totalVec > 0xffffffffull - (size_t)lenVec * kSliceRows) {
                 set_error("stencil table too large for 32-bit slice bases");
                 return B200OSD_ERR_UNSUPPORTED;
             }
-            meta.push_back(make_int2((int)(unsigned)totalVec, lenVec));
+            meta.push_back(make_int4((int)(unsigned)totalVec, lenVec, lo, 0));
             for (int q = 0; q < kSliceRows; ++q) rows.push_back(s0 + q < s1 ? order[s0 + q] : -1);
             totalVec += (size_t)lenVec * kSliceRows;
         }
@@ -121,26 +134,48 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
     t->numSlices = (int)meta.size();
     t->totalVec = totalVec;
 
-    // element-major fill: slot (slice, g, lane) holds elements 4g..4g+3 of the lane's row (zero weight padding)
-    std::vector<int4> idx4(totalVec);
-    std::memset(idx4.data(), 0, totalVec * sizeof(int4));
-    for (int s = 0; s < t->numSlices; ++s) {
-        const size_t base = (unsigned)meta[s].x;
-        for (int lane = 0; lane < kSliceRows; ++lane) {
-            const int row = rows[(size_t)s * kSliceRows + lane];
-            if (row < 0) continue;
-            const int sz = sizes[row], off = offsets[row];
-            for (int j = 0; j < sz; ++j) {
-                int *slot = reinterpret_cast<int *>(&idx4[base + (size_t)(j / kVec) * kSliceRows + lane]);
-                slot[j % kVec] = indices[off + j];
+    // element-major fill: slot (slice, g, lane) holds elements 4g..4g+3 of the lane's row (zero weight padding).
+    // Indices are stored as 16-bit offsets from the slice's smallest index when every slice spans < 65536 control
+    // vertices (refined meshes: a slice's rows touch one neighbourhood) -- 2 instead of 4 bytes per element, no
+    // indirection; otherwise as plain 32-bit indices.
+    t->idx16 = fits16;
+    int rc = B200OSD_OK;
+    if (fits16) {
+        std::vector<uint2> idx16(totalVec);
+        std::memset(idx16.data(), 0, totalVec * sizeof(uint2));
+        for (int s = 0; s < t->numSlices; ++s) {
+            const size_t base = (unsigned)meta[s].x;
+            const int lo = meta[s].z;
+            for (int lane = 0; lane < kSliceRows; ++lane) {
+                const int row = rows[(size_t)s * kSliceRows + lane];
+                if (row < 0) continue;
+                const int sz = sizes[row], off = offsets[row];
+                for (int j = 0; j < sz; ++j) {
+                    unsigned short *slot = reinterpret_cast<unsigned short *>(&idx16[base + (size_t)(j / kVec) * kSliceRows + lane]);
+                    slot[j % kVec] = (unsigned short)(indices[off + j] - lo);
+                }
             }
         }
+        rc = upload(&t->d_idx16, idx16.data(), totalVec);
+    } else {
+        for (auto &m : meta) m.z = 0;
+        std::vector<int4> idx4(totalVec);
+        std::memset(idx4.data(), 0, totalVec * sizeof(int4));
+        for (int s = 0; s < t->numSlices; ++s) {
+            const size_t base = (unsigned)meta[s].x;
+            for (int lane = 0; lane < kSliceRows; ++lane) {
+                const int row = rows[(size_t)s * kSliceRows + lane];
+                if (row < 0) continue;
+                const int sz = sizes[row], off = offsets[row];
+                for (int j = 0; j < sz; ++j) {
+                    int *slot = reinterpret_cast<int *>(&idx4[base + (size_t)(j / kVec) * kSliceRows + lane]);
+                    slot[j % kVec] = indices[off + j];
+                }
+            }
+        }
+        rc = upload(&t->d_idx4, idx4.data(), totalVec);
     }
-    int rc = upload(&t->d_idx4, idx4.data(), totalVec);
     if (rc) return rc;
-    {
-        std::vector<int4>().swap(idx4);
-    }
     std::vector<float4> w4(totalVec);
     for (int k = 0; k < t->numW; ++k) {
         std::memset(w4.data(), 0, totalVec * sizeof(float4));
@@ -235,41 +270,39 @@ int launch_csr(const StencilIO &io, const CsrTable &t, cudaStream_t st) {
 // Launch shape of the bucketed kernels.
 struct SellPlan {
     int mode = SRC_SCALAR;   // gather width (SRC_*)
-    int unroll = 2;          // index groups in flight per lane: 1, 2 or 4 (K == 1; otherwise 1)
-    int minBlocks = 0;       // __launch_bounds__ min blocks per SM: 0 (unspecified), 1, 6 or 8 (K == 1, unroll == 2)
+    int minBlocks = 0;       // __launch_bounds__ min blocks per SM: 0 (unspecified) or 8 (K == 1)
     bool persistent = false; // grid-stride persistent kernel with next-slice descriptor prefetch
 };
 
-template <int LL, int K, int SRCMODE, int U, int MINB>
+template <int LL, int K, int SRCMODE, int MINB, bool IDX16>
 void launch_sell_final(const StencilIO &io, const SellTable &t, bool persistent, int slices, cudaStream_t st) {
+    constexpr int U = (K == 1) ? 2 : 1;      // index groups in flight per lane (measured best: profiles/r01_*)
     const int block = 256;
     const int need = (slices + (block / 32) - 1) / (block / 32);
     if (persistent) {
         static int perSM = 0;     // per template instantiation
         if (!perSM) {
             int b = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sell_kernel_persist<LL, K, SRCMODE, U, MINB>, block, 0) != cudaSuccess || b < 1) b = 4;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sell_kernel_persist<LL, K, SRCMODE, U, MINB, IDX16>, block, 0) != cudaSuccess || b < 1) b = 4;
             perSM = b;
         }
         const int grid = std::min(need, perSM * sm_count());
-        sell_kernel_persist<LL, K, SRCMODE, U, MINB><<<grid, block, 0, st>>>(io, t);
+        sell_kernel_persist<LL, K, SRCMODE, U, MINB, IDX16><<<grid, block, 0, st>>>(io, t);
     } else {
-        sell_kernel<LL, K, SRCMODE, U, MINB><<<need, block, 0, st>>>(io, t);
+        sell_kernel<LL, K, SRCMODE, U, MINB, IDX16><<<need, block, 0, st>>>(io, t);
     }
 }
 
 template <int LL, int K, int SRCMODE>
 void launch_sell_shape(const StencilIO &io, const SellTable &t, const SellPlan &p, int slices, cudaStream_t st) {
-    if (K == 1) {
-        if (p.unroll == 4) { launch_sell_final<LL, K, SRCMODE, (K == 1 ? 4 : 1), 0>(io, t, false, slices, st); return; }
-        if (p.unroll == 1) { launch_sell_final<LL, K, SRCMODE, 1, 0>(io, t, false, slices, st); return; }
-        if (p.minBlocks == 1) { launch_sell_final<LL, K, SRCMODE, (K == 1 ? 2 : 1), (K == 1 ? 1 : 0)>(io, t, p.persistent, slices, st); return; }
-        if (p.minBlocks == 8) { launch_sell_final<LL, K, SRCMODE, (K == 1 ? 2 : 1), (K == 1 ? 8 : 1)>(io, t, p.persistent, slices, st); return; }
-        if (p.minBlocks == 6) { launch_sell_final<LL, K, SRCMODE, (K == 1 ? 2 : 1), (K == 1 ? 6 : 1)>(io, t, p.persistent, slices, st); return; }
-        launch_sell_final<LL, K, SRCMODE, (K == 1 ? 2 : 1), 0>(io, t, p.persistent, slices, st);
+    const bool i16 = t.idx16 != nullptr;
+    if (K == 1 && p.minBlocks == 8) {
+        if (i16) launch_sell_final<LL, K, SRCMODE, (K == 1 ? 8 : 0), true>(io, t, p.persistent, slices, st);
+        else launch_sell_final<LL, K, SRCMODE, (K == 1 ? 8 : 0), false>(io, t, p.persistent, slices, st);
         return;
     }
-    launch_sell_final<LL, K, SRCMODE, 1, 0>(io, t, p.persistent, slices, st);
+    if (i16) launch_sell_final<LL, K, SRCMODE, 0, true>(io, t, p.persistent, slices, st);
+    else launch_sell_final<LL, K, SRCMODE, 0, false>(io, t, p.persistent, slices, st);
 }
 
 template <int LL, int K>
@@ -332,7 +365,7 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, const int *
     if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
     for (int k = 0; k < t->numW && !rc; ++k) rc = upload(&t->d_w[k], w[k], (size_t)ne);
-    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w, !(flags & 2));
+    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w, (flags & 2) != 0, !(flags & 4));
     if (rc) {
         b200osd_stencil_table_destroy(t);
         return nullptr;
@@ -344,7 +377,7 @@ void b200osd_stencil_table_destroy(b200osd_stencil_table *t) {
     if (!t) return;
     cudaFree(t->d_sizes); cudaFree(t->d_offsets); cudaFree(t->d_indices);
     for (int k = 0; k < kMaxOut; ++k) { cudaFree(t->d_w[k]); cudaFree(t->d_w4[k]); }
-    cudaFree(t->d_idx4); cudaFree(t->d_meta); cudaFree(t->d_rows); cudaFree(t->d_pack);
+    cudaFree(t->d_idx4); cudaFree(t->d_idx16); cudaFree(t->d_meta); cudaFree(t->d_rows); cudaFree(t->d_pack);
     delete t;
 }
 
@@ -364,7 +397,7 @@ const void *b200osd_stencil_table_buffer(const b200osd_stencil_table *t, int whi
 
 long long b200osd_stencil_table_stream_bytes(const b200osd_stencil_table *t, int nOut) {
     if (!t || !t->hasSell) return 0;
-    return (long long)t->totalVec * 16 * (1 + nOut) + (long long)t->numSlices * (8 + 4 * kSliceRows);
+    return (long long)t->totalVec * ((t->idx16 ? 8 : 16) + 16 * nOut) + (long long)t->numSlices * (16 + 4 * kSliceRows);
 }
 
 int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src, const int srcDesc[3], int nOut,
@@ -388,6 +421,7 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
 
     SellTable s;
     s.idx4 = t->d_idx4;
+    s.idx16 = t->d_idx16;
     for (int k = 0; k < kMaxOut; ++k) s.w4[k] = t->d_w4[k];
     s.meta = t->d_meta;
     s.rows = t->d_rows;
@@ -396,24 +430,20 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
 
     // Source access.  Default: gather straight from the caller's buffer with the widest load its layout allows
     // (measured on B200: the compact layout beats a 16-byte repacked copy -- fewer cache lines per warp-wide gather).
-    // Variants (bench / tests): 2 scalar gathers, 3 repacked 16-byte rows, 4 natural width, 5/6/7 unroll sweeps,
-    // 8/9/12/14 persistent grid (min blocks unspecified/6/8/1), 10/11/13 one-shot grid with min blocks 6/8/1.
+    // Variants (bench / tests): 1 CSR kernel, 2 scalar gathers, 3 repacked 16-byte rows, 4 natural width,
+    // 8 persistent grid, 11 one-shot grid with 8 resident blocks/SM asked of the register allocator, 12 both.
     SellPlan plan;
     plan.mode = src_mode(io);
     const int L = io.L;
     const int v = g_stencil_variant;
-    // measured defaults (profiles/r01_sweep.md): with derivative streams the kernel is register-heavy and latency bound,
-    // the persistent grid's descriptor prefetch wins (+27 % at K=6); 4-float primvars like 64 resident warps
+    // measured defaults (profiles/r01_*): with derivative streams the kernel is register-heavy and latency bound and the
+    // persistent grid's descriptor prefetch wins (+27 % at K=6); 4-float primvars like 64 resident warps
     if (v == 0) {
         if (nOut > 1) plan.persistent = true;
         else if (L == 4 && plan.mode == SRC_VEC4) plan.minBlocks = 8;
     }
-    if (v == 2 || v == 5) plan.mode = SRC_SCALAR;
-    if (v == 5 || v == 6) plan.unroll = 4;
-    if (v == 7) plan.unroll = 1;
-    if (v == 8 || v == 9 || v == 12 || v == 14) plan.persistent = true;
-    if (v == 13 || v == 14) plan.minBlocks = 1;
-    if (v == 9 || v == 10) plan.minBlocks = 6;
+    if (v == 2) plan.mode = SRC_SCALAR;
+    if (v == 8 || v == 12) plan.persistent = true;
     if (v == 11 || v == 12) plan.minBlocks = 8;
     if (v == 3 && (L == 3 || L == 4 || L == 6 || L == 8)) {
         const int nv4 = (L + 3) / 4;

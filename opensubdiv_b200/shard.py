@@ -98,7 +98,7 @@ class FrameBroadcaster:
         self.cuda = self.buffers[0].is_cuda
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         if self.cuda:
-            self.comm_stream = torch.cuda.Stream()
+            self.comm_stream = torch.cuda.Stream(priority=-1)
             self.ready = [torch.cuda.Event(), torch.cuda.Event()]
             self.free = [torch.cuda.Event(), torch.cuda.Event()]
             for e in self.free:

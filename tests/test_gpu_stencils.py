@@ -10,16 +10,16 @@ from tests.util import golden, golden_names, table_from, assert_close, REL_TOL
 
 pytestmark = pytest.mark.gpu
 OUT6 = ("p", "du", "dv", "duu", "duv", "dvv")
-# 0 auto, 1 CSR kernel on the table, 2 scalar gathers, 3 repacked 16-byte gathers, 5 scalar + 4 groups in flight, 7 one group
-VARIANTS = (0, 1, 2, 3, 5, 7)
+# 0 auto, 1 CSR kernel on the table, 2 scalar gathers, 3 repacked 16-byte gathers, 8 persistent grid, 11 64 warps/SM, 12 both
+VARIANTS = (0, 1, 2, 3, 8, 11, 12)
 
 
-def refine_same_buffer(t, src, L, variant=0):
+def refine_same_buffer(t, src, L, variant=0, idx16=True):
     """Osd::Mesh::Refine layout: one buffer [control | refined], src and dst descriptors into it (osd/mesh.h:505-519)."""
     ncv, n = t.num_control_verts, t.num_stencils
     vb = osd.B200VertexBuffer.Create(L, ncv + n)
     vb.UpdateData(np.ascontiguousarray(src, np.float32), 0, ncv)
-    tbl = osd.B200StencilTable.Create(t)
+    tbl = osd.B200StencilTable.Create(t, idx16=idx16)
     assert tbl is not None and tbl.GetNumStencils() == n
     set_variant(variant)
     try:
@@ -54,6 +54,8 @@ def test_regression_shapes_vertex_and_varying(name):
         scale = oracle_stencils(d["src"], (0, L, L), t.num_stencils, L, t, 1, abs_scale=True)[0]
         for v in VARIANTS:
             assert_close(refine_same_buffer(t, d["src"], L, v), d[key], scale, f"{name} {prefix} variant {v}")
+        for v in (0, 8):      # the same table kept with 32-bit indices
+            assert_close(refine_same_buffer(t, d["src"], L, v, idx16=False), d[key], scale, f"{name} {prefix} idx32 variant {v}")
 
 
 @pytest.mark.parametrize("name", golden_names("limit_"))
@@ -167,6 +169,30 @@ def test_empty_and_degenerate_tables():
         assert_close(out.cpu().numpy(), exp, np.maximum(scale, 1e-6), f"degenerate variant {v}")
 
 
+def test_wide_index_span_falls_back_to_32bit_indices():
+    """Slices whose rows reference control vertices > 65535 apart cannot use 16-bit offsets: the table must silently keep
+    32-bit indices (and give the same results)."""
+    rng = np.random.default_rng(3)
+    ncv, n = 300_000, 5000
+    sizes = rng.integers(1, 24, n).astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32)
+    ne = int(sizes.sum())
+    t = type("T", (), dict(num_control_verts=ncv, num_stencils=n, sizes=sizes, offsets=offsets,
+                           indices=rng.integers(0, ncv, ne).astype(np.int32), weights=rng.random(ne).astype(np.float32),
+                           du=None, dv=None, duu=None, duv=None, dvv=None))()
+    src = rng.standard_normal((ncv, 3)).astype(np.float32)
+    exp = oracle_stencils(src, (0, 3, 3), n, 3, t, 1)[0]
+    scale = oracle_stencils(src, (0, 3, 3), n, 3, t, 1, abs_scale=True)[0]
+    tbl = osd.B200StencilTable.Create(t)
+    assert tbl.GetStreamBytes(1) > int(sizes.sum()) * 8          # 4-byte indices + 4-byte weights (+ padding)
+    for v in VARIANTS:
+        out = torch.full((n, 3), float("nan"), device="cuda")
+        set_variant(v)
+        assert osd.B200Evaluator.EvalStencils(dev(src), D(0, 3, 3), out, D(0, 3, 3), tbl)
+        set_variant(0)
+        assert_close(out.cpu().numpy(), exp, scale, f"wide span variant {v}")
+
+
 @pytest.fixture(scope="module")
 def config2():
     """BASELINE config 2 at full size: Catmark torus 400x250 (100k control verts), uniform level 3, last level:
@@ -234,7 +260,7 @@ def test_config2_size_independent_properties(config2):
     lin = ev(0.75 * x - 1.5 * y)
     assert (lin - (0.75 * ex - 1.5 * ey)).abs().max().item() <= 2e-6 * max(1.0, lin.abs().max().item())
     # every kernel variant and the raw reference-layout path agree
-    for v in (1, 2, 3, 4, 5, 6, 7):
+    for v in (1, 2, 3, 4, 8, 11, 12):
         assert (ev(x, v) - ex).abs().max().item() <= 2e-6
     raw = torch.empty((n, 6), device="cuda")
     assert osd.B200Evaluator.EvalStencilsRaw(x, D(0, 6, 6), [(raw, D(0, 6, 6))], tbl.GetSizesBuffer(), tbl.GetOffsetsBuffer(),
