@@ -31,9 +31,9 @@ struct b200osd_stencil_table {
     int window = 0;
     int numSlices = 0;
     size_t totalVec = 0;
-    bool idx16 = false;                  // indices stored as 16-bit offsets from a per-slice base
-    int4 *d_idx4 = nullptr;
-    uint2 *d_idx16 = nullptr;
+    uint2 *d_ipool = nullptr;            // index pool (8-byte units), 16- or 32-bit per slice
+    size_t ipoolUnits = 0;
+    int slices16 = 0;                    // slices stored with 16-bit offsets
     float4 *d_w4[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     int4 *d_meta = nullptr;
     int *d_rows = nullptr;
@@ -84,7 +84,7 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
     std::vector<int> order(n);
     std::vector<int4> meta;
     std::vector<int> rows;
-    bool fits16 = allowIdx16;
+    size_t poolUnits = 0;   // 8-byte units of index storage
     t->windowSliceStart.assign(numWindows + 1, 0);
     meta.reserve(n / kSliceRows + numWindows);
     rows.reserve((size_t)n + (size_t)numWindows * kSliceRows);
@@ -119,13 +119,20 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
                 }
             }
             if (hi < 0) { lo = 0; hi = 0; }
-            if (hi - lo > 0xffff) fits16 = false;
+            const bool is16 = allowIdx16 && (hi - lo <= 0xffff);
             const int lenVec = (maxSize + kVec - 1) / kVec;
+            if (!is16 && (poolUnits & 1)) ++poolUnits;      // 32-bit groups are int4: keep them 16-byte aligned
             if (totalVec > 0xffffffffull - (size_t)lenVec * kSliceRows) {
                 set_error("stencil table too large for 32-bit slice bases");
                 return B200OSD_ERR_UNSUPPORTED;
             }
-            meta.push_back(make_int4((int)(unsigned)totalVec, lenVec, lo, 0));
+            if (poolUnits > 0xffffffffull - 2ull * lenVec * kSliceRows) {
+                set_error("stencil table too large for 32-bit index-pool offsets");
+                return B200OSD_ERR_UNSUPPORTED;
+            }
+            meta.push_back(make_int4((int)(unsigned)totalVec, lenVec, is16 ? lo : -1, (int)(unsigned)poolUnits));
+            poolUnits += (size_t)lenVec * kSliceRows * (is16 ? 1 : 2);
+            t->slices16 += is16 ? 1 : 0;
             for (int q = 0; q < kSliceRows; ++q) rows.push_back(s0 + q < s1 ? order[s0 + q] : -1);
             totalVec += (size_t)lenVec * kSliceRows;
         }
@@ -135,45 +142,29 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
     t->totalVec = totalVec;
 
     // element-major fill: slot (slice, g, lane) holds elements 4g..4g+3 of the lane's row (zero weight padding).
-    // Indices are stored as 16-bit offsets from the slice's smallest index when every slice spans < 65536 control
-    // vertices (refined meshes: a slice's rows touch one neighbourhood) -- 2 instead of 4 bytes per element, no
-    // indirection; otherwise as plain 32-bit indices.
-    t->idx16 = fits16;
+    // Per slice the indices are 16-bit offsets from the slice's smallest index when the slice spans < 65536 control
+    // vertices (refined meshes: a slice's rows touch one neighbourhood; 2 instead of 4 bytes per element and no
+    // indirection) and plain 32-bit indices otherwise.
     int rc = B200OSD_OK;
-    if (fits16) {
-        std::vector<uint2> idx16(totalVec);
-        std::memset(idx16.data(), 0, totalVec * sizeof(uint2));
+    {
+        std::vector<uint2> pool(poolUnits);
+        std::memset(pool.data(), 0, poolUnits * sizeof(uint2));
         for (int s = 0; s < t->numSlices; ++s) {
-            const size_t base = (unsigned)meta[s].x;
             const int lo = meta[s].z;
+            uint2 *sp = pool.data() + (size_t)(unsigned)meta[s].w;
             for (int lane = 0; lane < kSliceRows; ++lane) {
                 const int row = rows[(size_t)s * kSliceRows + lane];
                 if (row < 0) continue;
                 const int sz = sizes[row], off = offsets[row];
                 for (int j = 0; j < sz; ++j) {
-                    unsigned short *slot = reinterpret_cast<unsigned short *>(&idx16[base + (size_t)(j / kVec) * kSliceRows + lane]);
-                    slot[j % kVec] = (unsigned short)(indices[off + j] - lo);
+                    const size_t slot = (size_t)(j / kVec) * kSliceRows + lane;
+                    if (lo >= 0) reinterpret_cast<unsigned short *>(sp + slot)[j % kVec] = (unsigned short)(indices[off + j] - lo);
+                    else reinterpret_cast<int *>(reinterpret_cast<int4 *>(sp) + slot)[j % kVec] = indices[off + j];
                 }
             }
         }
-        rc = upload(&t->d_idx16, idx16.data(), totalVec);
-    } else {
-        for (auto &m : meta) m.z = 0;
-        std::vector<int4> idx4(totalVec);
-        std::memset(idx4.data(), 0, totalVec * sizeof(int4));
-        for (int s = 0; s < t->numSlices; ++s) {
-            const size_t base = (unsigned)meta[s].x;
-            for (int lane = 0; lane < kSliceRows; ++lane) {
-                const int row = rows[(size_t)s * kSliceRows + lane];
-                if (row < 0) continue;
-                const int sz = sizes[row], off = offsets[row];
-                for (int j = 0; j < sz; ++j) {
-                    int *slot = reinterpret_cast<int *>(&idx4[base + (size_t)(j / kVec) * kSliceRows + lane]);
-                    slot[j % kVec] = indices[off + j];
-                }
-            }
-        }
-        rc = upload(&t->d_idx4, idx4.data(), totalVec);
+        t->ipoolUnits = poolUnits;
+        rc = upload(&t->d_ipool, pool.data(), poolUnits);
     }
     if (rc) return rc;
     std::vector<float4> w4(totalVec);
@@ -274,7 +265,7 @@ struct SellPlan {
     bool persistent = false; // grid-stride persistent kernel with next-slice descriptor prefetch
 };
 
-template <int LL, int K, int SRCMODE, int MINB, bool IDX16>
+template <int LL, int K, int SRCMODE, int MINB>
 void launch_sell_final(const StencilIO &io, const SellTable &t, bool persistent, int slices, cudaStream_t st) {
     constexpr int U = (K == 1) ? 2 : 1;      // index groups in flight per lane (measured best: profiles/r01_*)
     const int block = 256;
@@ -283,26 +274,23 @@ void launch_sell_final(const StencilIO &io, const SellTable &t, bool persistent,
         static int perSM = 0;     // per template instantiation
         if (!perSM) {
             int b = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sell_kernel_persist<LL, K, SRCMODE, U, MINB, IDX16>, block, 0) != cudaSuccess || b < 1) b = 4;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sell_kernel_persist<LL, K, SRCMODE, U, MINB>, block, 0) != cudaSuccess || b < 1) b = 4;
             perSM = b;
         }
         const int grid = std::min(need, perSM * sm_count());
-        sell_kernel_persist<LL, K, SRCMODE, U, MINB, IDX16><<<grid, block, 0, st>>>(io, t);
+        sell_kernel_persist<LL, K, SRCMODE, U, MINB><<<grid, block, 0, st>>>(io, t);
     } else {
-        sell_kernel<LL, K, SRCMODE, U, MINB, IDX16><<<need, block, 0, st>>>(io, t);
+        sell_kernel<LL, K, SRCMODE, U, MINB><<<need, block, 0, st>>>(io, t);
     }
 }
 
 template <int LL, int K, int SRCMODE>
 void launch_sell_shape(const StencilIO &io, const SellTable &t, const SellPlan &p, int slices, cudaStream_t st) {
-    const bool i16 = t.idx16 != nullptr;
     if (K == 1 && p.minBlocks == 8) {
-        if (i16) launch_sell_final<LL, K, SRCMODE, (K == 1 ? 8 : 0), true>(io, t, p.persistent, slices, st);
-        else launch_sell_final<LL, K, SRCMODE, (K == 1 ? 8 : 0), false>(io, t, p.persistent, slices, st);
+        launch_sell_final<LL, K, SRCMODE, (K == 1 ? 8 : 0)>(io, t, p.persistent, slices, st);
         return;
     }
-    if (i16) launch_sell_final<LL, K, SRCMODE, 0, true>(io, t, p.persistent, slices, st);
-    else launch_sell_final<LL, K, SRCMODE, 0, false>(io, t, p.persistent, slices, st);
+    launch_sell_final<LL, K, SRCMODE, 0>(io, t, p.persistent, slices, st);
 }
 
 template <int LL, int K>
@@ -377,7 +365,7 @@ void b200osd_stencil_table_destroy(b200osd_stencil_table *t) {
     if (!t) return;
     cudaFree(t->d_sizes); cudaFree(t->d_offsets); cudaFree(t->d_indices);
     for (int k = 0; k < kMaxOut; ++k) { cudaFree(t->d_w[k]); cudaFree(t->d_w4[k]); }
-    cudaFree(t->d_idx4); cudaFree(t->d_idx16); cudaFree(t->d_meta); cudaFree(t->d_rows); cudaFree(t->d_pack);
+    cudaFree(t->d_ipool); cudaFree(t->d_meta); cudaFree(t->d_rows); cudaFree(t->d_pack);
     delete t;
 }
 
@@ -397,7 +385,7 @@ const void *b200osd_stencil_table_buffer(const b200osd_stencil_table *t, int whi
 
 long long b200osd_stencil_table_stream_bytes(const b200osd_stencil_table *t, int nOut) {
     if (!t || !t->hasSell) return 0;
-    return (long long)t->totalVec * ((t->idx16 ? 8 : 16) + 16 * nOut) + (long long)t->numSlices * (16 + 4 * kSliceRows);
+    return (long long)t->ipoolUnits * 8 + (long long)t->totalVec * 16 * nOut + (long long)t->numSlices * (16 + 4 * kSliceRows);
 }
 
 int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src, const int srcDesc[3], int nOut,
@@ -420,8 +408,7 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
     }
 
     SellTable s;
-    s.idx4 = t->d_idx4;
-    s.idx16 = t->d_idx16;
+    s.ipool = t->d_ipool;
     for (int k = 0; k < kMaxOut; ++k) s.w4[k] = t->d_w4[k];
     s.meta = t->d_meta;
     s.rows = t->d_rows;
@@ -440,7 +427,7 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
     // persistent grid's descriptor prefetch wins (+27 % at K=6); 4-float primvars like 64 resident warps
     if (v == 0) {
         if (nOut > 1) plan.persistent = true;
-        else if (L == 4 && plan.mode == SRC_VEC4) plan.minBlocks = 8;
+        else if (L <= 6) plan.minBlocks = 8;
     }
     if (v == 2) plan.mode = SRC_SCALAR;
     if (v == 8 || v == 12) plan.persistent = true;

@@ -39,10 +39,11 @@ struct CsrTable {
 };
 
 struct SellTable {
-    const int4 *idx4;              // [totalVec] element-major index groups (32-bit indices), or NULL
-    const uint2 *idx16;            // [totalVec] the same groups as 4 x 16-bit offsets from the slice's index base, or NULL
-    const float4 *w4[kMaxOut];     // same layout, one per weight stream
-    const int4 *meta;              // per slice: {baseVec, lenVec, indexBase, 0}
+    const uint2 *ipool;            // index pool in 8-byte units: per slice either 4 x 16-bit offsets (one uint2) or 4 x 32-bit
+                                   // indices (one int4 = two units) per lane slot, element-major like the weights
+    const float4 *w4[kMaxOut];     // [totalVec] weight groups, one array per weight stream
+    const int4 *meta;              // per slice: {baseVec (weight slots), lenVec, indexBase (>= 0: 16-bit offsets from it,
+                                   //             -1: 32-bit indices), first unit of the slice in ipool}
     const int *rows;               // [numSlices*32] original row of each lane slot, -1 = padding
     int sliceBegin, sliceEnd;
 };
@@ -188,21 +189,23 @@ __global__ void __launch_bounds__(128) csr_kernel_anyL(StencilIO io, CsrTable t)
 // ----------------------------------------------------------------------------------- SELL path --
 // One lane per row.  UNROLL index groups are issued back to back so that each lane has 2*UNROLL 128-bit stream
 // loads in flight before the first gather is consumed.
-// One index group of a lane: 4 control-vertex indices, from either index encoding.
-template <bool IDX16>
-__device__ __forceinline__ int4 load_index_group(const SellTable &t, size_t slot, int indexBase) {
-    if (IDX16) {
-        const uint2 q = ld_stream_u2(t.idx16 + slot);
+// One index group of a lane: 4 control-vertex indices.  `slot` = g*32 + lane inside the slice.  The encoding is a
+// per-slice property (warp-uniform branch): 16-bit offsets from the slice's smallest index when the slice spans fewer
+// than 65536 control vertices (practically always on refined meshes), plain 32-bit indices otherwise.
+__device__ __forceinline__ int4 load_index_group(const uint2 *slicePool, int slot, int indexBase) {
+    if (indexBase >= 0) {
+        const uint2 q = ld_stream_u2(slicePool + slot);
         return make_int4(indexBase + (int)(q.x & 0xffffu), indexBase + (int)(q.x >> 16),
                          indexBase + (int)(q.y & 0xffffu), indexBase + (int)(q.y >> 16));
     }
-    return ld_stream_i4(t.idx4 + slot);
+    return ld_stream_i4(reinterpret_cast<const int4 *>(slicePool) + slot);
 }
 
-template <int L, int K, int SRCMODE, int UNROLL, bool IDX16>
+template <int L, int K, int SRCMODE, int UNROLL>
 __device__ __forceinline__ void sell_slice(const StencilIO &io, const SellTable &t, const int4 m, const int lane,
                                            float (&acc)[K][L]) {
     const size_t base = (size_t)(unsigned)m.x + lane;
+    const uint2 *slicePool = t.ipool + (size_t)(unsigned)m.w;
     const float4 *wp[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) wp[k] = t.w4[k] + base;
@@ -218,7 +221,7 @@ __device__ __forceinline__ void sell_slice(const StencilIO &io, const SellTable 
         float4 w[UNROLL][K];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            id[u] = load_index_group<IDX16>(t, base + (size_t)(g + u) * kSliceRows, m.z);
+            id[u] = load_index_group(slicePool, (g + u) * kSliceRows + lane, m.z);
 #pragma unroll
             for (int k = 0; k < K; ++k) w[u][k] = ld_stream_f4(wp[k] + (size_t)(g + u) * kSliceRows);
         }
@@ -239,7 +242,7 @@ __device__ __forceinline__ void sell_slice(const StencilIO &io, const SellTable 
         }
     }
     for (; g < ng; ++g) {
-        int4 id = load_index_group<IDX16>(t, base + (size_t)g * kSliceRows, m.z);
+        int4 id = load_index_group(slicePool, g * kSliceRows + lane, m.z);
         float4 w[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) w[k] = ld_stream_f4(wp[k] + (size_t)g * kSliceRows);
@@ -259,7 +262,7 @@ __device__ __forceinline__ void sell_slice(const StencilIO &io, const SellTable 
 }
 
 // One warp per slice (one-shot grid).  MINB = minimum resident blocks per SM asked of the register allocator.
-template <int L, int K, int SRCMODE, int UNROLL, int MINB, bool IDX16>
+template <int L, int K, int SRCMODE, int UNROLL, int MINB>
 __global__ void __launch_bounds__(256, MINB) sell_kernel(StencilIO io, SellTable t) {
     const int lane = threadIdx.x & 31;
     const int slice = t.sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -267,14 +270,14 @@ __global__ void __launch_bounds__(256, MINB) sell_kernel(StencilIO io, SellTable
     const int4 m = t.meta[slice];
     const int row = t.rows[(size_t)slice * kSliceRows + lane];
     float acc[K][L];
-    sell_slice<L, K, SRCMODE, UNROLL, IDX16>(io, t, m, lane, acc);
+    sell_slice<L, K, SRCMODE, UNROLL>(io, t, m, lane, acc);
     if (row >= io.start && row < io.end) store_row<L, K>(io, row, acc);
 }
 
 // Persistent form: the grid is sized to the machine and every warp walks slices with a grid stride, fetching the
 // NEXT slice's descriptor and row ids before working on the current one, so the descriptor -> stream dependent
 // DRAM round trip is paid once per warp instead of once per slice.
-template <int L, int K, int SRCMODE, int UNROLL, int MINB, bool IDX16>
+template <int L, int K, int SRCMODE, int UNROLL, int MINB>
 __global__ void __launch_bounds__(256, MINB) sell_kernel_persist(StencilIO io, SellTable t) {
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(256, MINB) sell_kernel_persist(StencilIO io, S
             rown = t.rows[(size_t)next * kSliceRows + lane];
         }
         float acc[K][L];
-        sell_slice<L, K, SRCMODE, UNROLL, IDX16>(io, t, m, lane, acc);
+        sell_slice<L, K, SRCMODE, UNROLL>(io, t, m, lane, acc);
         if (row >= io.start && row < io.end) store_row<L, K>(io, row, acc);
         if (!more) break;
         slice = next;
@@ -318,8 +321,7 @@ __global__ void __launch_bounds__(256) sell_kernel_anyL(StencilIO io, SellTable 
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[k][c] = 0.0f;
         for (int g = 0; g < m.y; ++g) {
-            const int4 id = t.idx16 ? load_index_group<true>(t, base + (size_t)g * kSliceRows, m.z)
-                                    : load_index_group<false>(t, base + (size_t)g * kSliceRows, m.z);
+            const int4 id = load_index_group(t.ipool + (size_t)(unsigned)m.w, g * kSliceRows + lane, m.z);
             int ids[4] = { id.x, id.y, id.z, id.w };
             float4 w[K];
 #pragma unroll
