@@ -98,7 +98,8 @@ B200OSD_API int    b200osd_vertex_buffer_read(b200osd_vertex_buffer *vb, float *
  * (b) a B200-specific bucketed copy (rows sorted by size inside windows, 32-row slices stored
  * element-major for coalesced 128-bit loads) used by b200osd_stencil_table_eval.
  * flags: bit 0 = skip the bucketed copy (verbatim only); bit 1 = also order rows by locality inside a window;
- * bit 2 = keep 32-bit indices even when every slice fits 16-bit offsets.                                       */
+ * bit 2 = keep 32-bit indices even when a slice fits 16-bit offsets; bit 3 = sort each row's elements by control index
+ * (same terms, different summation order than the reference: opt-in).                                       */
 B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
         int numStencils, const int *sizes, const int *offsets, const int *indices, const float *weights,
         const float *duWeights, const float *dvWeights,

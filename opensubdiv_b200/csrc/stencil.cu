@@ -68,8 +68,23 @@ int upload(T **dptr, const T *host, size_t count) {
 }
 
 int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, const int *indices,
-               const float *const w[kMaxOut], bool localitySort, bool allowIdx16) {
+               const float *const w[kMaxOut], bool localitySort, bool allowIdx16, bool sortElements) {
     const int n = t->n;
+    // Element order inside a row.  Default: the table's own order, i.e. the reference's summation order (parity first:
+    // rows of 100+ terms differ by > 1e-6 relative once the order changes).  Opt-in (flag bit 3): each row's elements
+    // sorted by control index -- the rows of a slice are neighbours on the surface and share most control vertices, so
+    // position j of all 32 lanes then refers to (nearly) the same vertex and a warp-wide gather touches fewer lines.
+    std::vector<int> perm;          // perm[off + j] = original position (relative to off) of the row's j-th element
+    if (sortElements) {
+        perm.resize((size_t)t->ne);
+        for (int i = 0; i < n; ++i) {
+            int *p = perm.data() + offsets[i];
+            const int *ix = indices + offsets[i];
+            std::iota(p, p + sizes[i], 0);
+            std::stable_sort(p, p + sizes[i], [&](int a, int b) { return ix[a] < ix[b]; });
+        }
+    }
+    auto elem = [&](int off, int j) { return sortElements ? off + perm[(size_t)off + j] : off + j; };
     std::vector<int> rowKey;
     if (localitySort) {
         rowKey.resize(n);
@@ -158,8 +173,9 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
                 const int sz = sizes[row], off = offsets[row];
                 for (int j = 0; j < sz; ++j) {
                     const size_t slot = (size_t)(j / kVec) * kSliceRows + lane;
-                    if (lo >= 0) reinterpret_cast<unsigned short *>(sp + slot)[j % kVec] = (unsigned short)(indices[off + j] - lo);
-                    else reinterpret_cast<int *>(reinterpret_cast<int4 *>(sp) + slot)[j % kVec] = indices[off + j];
+                    const int ix = indices[elem(off, j)];
+                    if (lo >= 0) reinterpret_cast<unsigned short *>(sp + slot)[j % kVec] = (unsigned short)(ix - lo);
+                    else reinterpret_cast<int *>(reinterpret_cast<int4 *>(sp) + slot)[j % kVec] = ix;
                 }
             }
         }
@@ -178,7 +194,7 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
                 const int sz = sizes[row], off = offsets[row];
                 for (int j = 0; j < sz; ++j) {
                     float *slot = reinterpret_cast<float *>(&w4[base + (size_t)(j / kVec) * kSliceRows + lane]);
-                    slot[j % kVec] = w[k][off + j];
+                    slot[j % kVec] = w[k][elem(off, j)];
                 }
             }
         }
@@ -295,7 +311,8 @@ void launch_sell_shape(const StencilIO &io, const SellTable &t, const SellPlan &
 
 template <int LL, int K>
 void launch_sell_mode(const StencilIO &io, const SellTable &t, const SellPlan &p, int slices, cudaStream_t st) {
-    if (p.mode == SRC_VEC4) launch_sell_shape<LL, K, SRC_VEC4>(io, t, p, slices, st);
+    if (p.mode == SRC_V24 && LL == 6) launch_sell_shape<LL, K, (LL == 6 ? SRC_V24 : SRC_VEC2)>(io, t, p, slices, st);
+    else if (p.mode == SRC_VEC4) launch_sell_shape<LL, K, SRC_VEC4>(io, t, p, slices, st);
     else if (p.mode == SRC_VEC2) launch_sell_shape<LL, K, SRC_VEC2>(io, t, p, slices, st);
     else launch_sell_shape<LL, K, SRC_SCALAR>(io, t, p, slices, st);
 }
@@ -353,7 +370,7 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, const int *
     if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
     for (int k = 0; k < t->numW && !rc; ++k) rc = upload(&t->d_w[k], w[k], (size_t)ne);
-    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w, (flags & 2) != 0, !(flags & 4));
+    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w, (flags & 2) != 0, !(flags & 4), (flags & 8) != 0);
     if (rc) {
         b200osd_stencil_table_destroy(t);
         return nullptr;
@@ -418,6 +435,7 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
     // Source access.  Default: gather straight from the caller's buffer with the widest load its layout allows
     // (measured on B200: the compact layout beats a 16-byte repacked copy -- fewer cache lines per warp-wide gather).
     // Variants (bench / tests): 1 CSR kernel, 2 scalar gathers, 3 repacked 16-byte rows, 4 natural width,
+    // 5/6 xyz+normal vertices through one 128-bit + one 64-bit load (8 / unspecified blocks per SM),
     // 8 persistent grid, 11 one-shot grid with 8 resident blocks/SM asked of the register allocator, 12 both.
     SellPlan plan;
     plan.mode = src_mode(io);
@@ -430,6 +448,8 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
         else if (L <= 6) plan.minBlocks = 8;
     }
     if (v == 2) plan.mode = SRC_SCALAR;
+    if ((v == 5 || v == 6) && L == 6 && plan.mode == SRC_VEC2 && io.srcStride == 6) plan.mode = SRC_V24;   // 128+64-bit gathers
+    if (v == 6) plan.minBlocks = 0;
     if (v == 8 || v == 12) plan.persistent = true;
     if (v == 11 || v == 12) plan.minBlocks = 8;
     if (v == 3 && (L == 3 || L == 4 || L == 6 || L == 8)) {

@@ -82,11 +82,38 @@ __device__ __forceinline__ void load_vertex_vec2(const float *src, int stride, i
     }
 }
 
-enum { SRC_SCALAR = 0, SRC_VEC2 = 1, SRC_VEC4 = 2 };
+// 6-float vertices (xyz+normal) at an 8-byte aligned, 24-byte stride: every vertex is either 16-byte aligned or 8 off.
+// One 128-bit and one 64-bit load per vertex, their order chosen per lane by the address parity (no divergence: both
+// loads are executed by every lane, only the addresses and the final component selection differ) -- two gather
+// instructions instead of three.
+__device__ __forceinline__ void load_vertex_6x24(const float *src, int stride, int idx, float (&v)[6]) {
+    const char *a = reinterpret_cast<const char *>(src + (size_t)idx * (size_t)stride);
+    const bool hi = (reinterpret_cast<uintptr_t>(a) & 8u) != 0;
+    const float4 A = *reinterpret_cast<const float4 *>(a + (hi ? 8 : 0));
+    const float2 B = *reinterpret_cast<const float2 *>(a + (hi ? 0 : 16));
+    v[0] = hi ? B.x : A.x;
+    v[1] = hi ? B.y : A.y;
+    v[2] = hi ? A.x : A.z;
+    v[3] = hi ? A.y : A.w;
+    v[4] = hi ? A.z : B.x;
+    v[5] = hi ? A.w : B.y;
+}
+
+enum { SRC_SCALAR = 0, SRC_VEC2 = 1, SRC_VEC4 = 2, SRC_V24 = 3 };
+
+template <int L>
+__device__ __forceinline__ void load_vertex_v24(const float *src, int stride, int idx, float (&v)[L]) {
+    load_vertex_vec2<L>(src, stride, idx, v);
+}
+template <>
+__device__ __forceinline__ void load_vertex_v24<6>(const float *src, int stride, int idx, float (&v)[6]) {
+    load_vertex_6x24(src, stride, idx, v);
+}
 
 template <int L, int SRCMODE>
 __device__ __forceinline__ void load_vertex(const float *src, int stride, int idx, float (&v)[L]) {
-    if (SRCMODE == SRC_VEC4)      load_vertex_vec4<L>(src, stride, idx, v);
+    if (SRCMODE == SRC_V24)       load_vertex_v24<L>(src, stride, idx, v);
+    else if (SRCMODE == SRC_VEC4) load_vertex_vec4<L>(src, stride, idx, v);
     else if (SRCMODE == SRC_VEC2) load_vertex_vec2<L>(src, stride, idx, v);
     else                          load_vertex_scalar<L>(src, stride, idx, v);
 }

@@ -153,7 +153,7 @@ class B200StencilTable:
 
     @classmethod
     def Create(cls, table, deviceContext=None, bucketed: bool = True, locality: bool = False,
-               idx16: bool = True) -> Optional["B200StencilTable"]:
+               idx16: bool = True, sort_elements: bool = False) -> Optional["B200StencilTable"]:
         """`table` is anything with the Far::StencilTable / LimitStencilTable accessors as numpy arrays:
         sizes, offsets, indices, weights and optionally du, dv, duu, duv, dvv (far/stencilTable.h:156-186,434-456)."""
         def arr(name, dt):
@@ -163,7 +163,7 @@ class B200StencilTable:
         w = [arr(n, np.float32) for n in ("weights", "du", "dv", "duu", "duv", "dvv")]
         p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
         h = capi.lib().b200osd_stencil_table_create(len(sizes), p(sizes), p(offsets), p(indices), *[p(x) for x in w],
-                                                    (0 if bucketed else 1) | (2 if locality else 0) | (0 if idx16 else 4))
+                                                    (0 if bucketed else 1) | (2 if locality else 0) | (0 if idx16 else 4) | (8 if sort_elements else 0))
         return cls(h) if h else None
 
     def __del__(self):

@@ -10,16 +10,16 @@ from tests.util import golden, golden_names, table_from, assert_close, REL_TOL
 
 pytestmark = pytest.mark.gpu
 OUT6 = ("p", "du", "dv", "duu", "duv", "dvv")
-# 0 auto, 1 CSR kernel on the table, 2 scalar gathers, 3 repacked 16-byte gathers, 8 persistent grid, 11 64 warps/SM, 12 both
-VARIANTS = (0, 1, 2, 3, 8, 11, 12)
+# 0 auto, 1 CSR kernel on the table, 2 scalar gathers, 3 repacked 16-byte gathers, 5/6 128+64-bit gathers for 6-float vertices, 8 persistent grid, 11 64 warps/SM, 12 both
+VARIANTS = (0, 1, 2, 3, 5, 6, 8, 11, 12)
 
 
-def refine_same_buffer(t, src, L, variant=0, idx16=True):
+def refine_same_buffer(t, src, L, variant=0, idx16=True, sort_elements=False):
     """Osd::Mesh::Refine layout: one buffer [control | refined], src and dst descriptors into it (osd/mesh.h:505-519)."""
     ncv, n = t.num_control_verts, t.num_stencils
     vb = osd.B200VertexBuffer.Create(L, ncv + n)
     vb.UpdateData(np.ascontiguousarray(src, np.float32), 0, ncv)
-    tbl = osd.B200StencilTable.Create(t, idx16=idx16)
+    tbl = osd.B200StencilTable.Create(t, idx16=idx16, sort_elements=sort_elements)
     assert tbl is not None and tbl.GetNumStencils() == n
     set_variant(variant)
     try:
@@ -54,8 +54,11 @@ def test_regression_shapes_vertex_and_varying(name):
         scale = oracle_stencils(d["src"], (0, L, L), t.num_stencils, L, t, 1, abs_scale=True)[0]
         for v in VARIANTS:
             assert_close(refine_same_buffer(t, d["src"], L, v), d[key], scale, f"{name} {prefix} variant {v}")
-        for v in (0, 8):      # the same table kept with 32-bit indices
+        for v in (0, 8):      # the same table kept with 32-bit indices / with the reference's element order
             assert_close(refine_same_buffer(t, d["src"], L, v, idx16=False), d[key], scale, f"{name} {prefix} idx32 variant {v}")
+            # opt-in element sorting changes the summation order: same terms, looser agreement on rows of 100+ terms
+            assert_close(refine_same_buffer(t, d["src"], L, v, sort_elements=True), d[key], scale, f"{name} {prefix} sorted variant {v}",
+                         tol=5e-6)
 
 
 @pytest.mark.parametrize("name", golden_names("limit_"))
@@ -234,6 +237,47 @@ def test_config2_full_size_frames_vs_oracle(config2):
                 oracle.eval_stencils(src.reshape(-1), (0, 6, 6), [scl.reshape(-1)], [(0, 6, 6)], table.sizes, table.offsets,
                                      table.indices, [table.weights], a, b)
             assert_close(got[a:b].cpu().numpy(), exp[a:b], scl[a:b], f"frame {frame} rows {a}:{b}")
+
+
+@pytest.mark.slow
+def test_config2_table_built_by_far_reference_order_vs_sorted():
+    """Config 2 with the table built by the REAL Far::StencilTableFactory (insertion order inside rows, unlike the
+    index-sorted synthetic table): parity against the oracle in the reference's order, and the effect of the opt-in
+    element sorting on speed (printed; recorded in profiles/)."""
+    from oracle import oracle, ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libosdref.so not present")
+    mesh = synth.torus_quads(400, 250)
+    m = ref.Mesh.from_topology("catmark", mesh.num_verts, np.full(len(mesh.faces), 4, np.int32), mesh.faces.reshape(-1))
+    far = m.refine_uniform(3).stencil_table()
+    assert far.num_stencils == 6_400_000
+    ncv, n = far.num_control_verts, far.num_stencils
+    src = _prim6(mesh, 2)
+    x = dev(src)
+    out = torch.empty((n, 6), device="cuda")
+    import time
+    for sort in (False, True):
+        tbl = osd.B200StencilTable.Create(far, sort_elements=sort)
+        for _ in range(5):
+            assert osd.B200Evaluator.EvalStencils(x, D(0, 6, 6), out, D(0, 6, 6), tbl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            osd.B200Evaluator.EvalStencils(x, D(0, 6, 6), out, D(0, 6, 6), tbl)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"FAR-ORDER-TABLE cfg2 L=6 sort_elements={sort}: {e0.elapsed_time(e1) / 50:.4f} ms/frame, stream {tbl.GetStreamBytes(1) / 1e6:.0f} MB")
+        a, b = 3_000_000, 3_040_000
+        exp = np.zeros((n, 6), np.float32)
+        scl = np.zeros((n, 6), np.float32)
+        assert oracle.eval_stencils(src.reshape(-1), (0, 6, 6), [exp.reshape(-1)], [(0, 6, 6)], far.sizes, far.offsets, far.indices,
+                                    [far.weights], a, b)
+        with oracle.abs_mode():
+            oracle.eval_stencils(src.reshape(-1), (0, 6, 6), [scl.reshape(-1)], [(0, 6, 6)], far.sizes, far.offsets, far.indices,
+                                 [far.weights], a, b)
+        assert_close(out[a:b].cpu().numpy(), exp[a:b], scl[a:b], f"far table sort={sort}")
+        del tbl
 
 
 @pytest.mark.slow

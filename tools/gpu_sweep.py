@@ -50,10 +50,10 @@ def time_calls(fn, iters, warm=10):
     return e0.elapsed_time(e1) / iters
 
 
-def stencil_case(name, table, Ls, nouts, iters, variants=(0, 1, 2, 3, 8, 11, 12), locality=False, idx16=True):
+def stencil_case(name, table, Ls, nouts, iters, variants=(0, 1, 2, 3, 8, 11, 12), locality=False, idx16=True, sort_elements=False):
     lib = capi.lib()
     t0 = time.time()
-    tbl = osd.B200StencilTable.Create(table, locality=locality, idx16=idx16)
+    tbl = osd.B200StencilTable.Create(table, locality=locality, idx16=idx16, sort_elements=sort_elements)
     assert tbl is not None, capi.last_error()
     build_s = time.time() - t0
     ncv, n = table.num_control_verts, table.num_stencils
@@ -69,7 +69,7 @@ def stencil_case(name, table, Ls, nouts, iters, variants=(0, 1, 2, 3, 8, 11, 12)
                 lib.b200osd_set_stencil_variant(v)
                 ms = time_calls(lambda: osd.B200Evaluator.EvalStencils(src, D(0, L, L), *args, tbl), iters)
                 lib.b200osd_set_stencil_variant(0)
-                emit(case=name, kind="stencil", locality=locality, idx16=idx16, L=L, nout=nout, variant=v, ms=ms, rows=n, elements=table.num_elements,
+                emit(case=name, kind="stencil", locality=locality, idx16=idx16, sorted_elems=sort_elements, L=L, nout=nout, variant=v, ms=ms, rows=n, elements=table.num_elements,
                      gverts_per_s=n / ms / 1e6, alg_MB=alg / 1e6, alg_GBps=alg / ms / 1e6, frac_of_measured_peak=alg / ms / 1e6 / PEAK,
                      stream_MB=tbl.GetStreamBytes(nout) / 1e6, table_build_s=build_s)
     del tbl
@@ -118,22 +118,21 @@ def main():
         mesh = synth.torus_quads(400, 250)
         table = synth.uniform_stencil_table(mesh, 3)
         if a.quick:
-            stencil_case("cfg2_catmark_400x250_L3", table, (6, 3), (1,), 5, variants=(0,))
+            stencil_case("cfg2_catmark_400x250_L3", table, (6, 3), (1,), 5, variants=(0, 5, 6))
         else:
-            stencil_case("cfg2_catmark_400x250_L3", table, (6, 3, 4, 8), (1,), a.iters, variants=(0, 8, 11, 12))
-            stencil_case("cfg2_catmark_400x250_L3", table, (6, 3), (1,), a.iters, variants=(0, 11), idx16=False)
+            stencil_case("cfg2_catmark_400x250_L3", table, (6, 3, 4, 8), (1,), a.iters, variants=(0, 11))
+
             del table
             rng = np.random.default_rng(12345)
             face = np.sort(rng.integers(0, len(mesh.faces), 1_000_000)).astype(np.int32)
             ls = synth.torus_limit_stencil_table(mesh, face, rng.random(1_000_000, dtype=np.float32),
                                                  rng.random(1_000_000, dtype=np.float32))
-            stencil_case("cfg3_limit_1M_x16", ls, (3,), (1, 3, 6), a.iters, variants=(0, 8))
-            stencil_case("cfg3_limit_1M_x16", ls, (3,), (6,), a.iters, variants=(0,), idx16=False)
+            stencil_case("cfg3_limit_1M_x16", ls, (3,), (1, 3, 6), a.iters, variants=(0,))
             del ls
             mesh5 = synth.torus_tris(1000, 500)
             t5 = synth.uniform_stencil_table(mesh5, 2)
-            stencil_case("cfg5_loop_1000x500_L2", t5, (3,), (1,), a.iters, variants=(0, 11))
-            stencil_case("cfg5_loop_1000x500_L2", t5, (3,), (1,), a.iters, variants=(0,), idx16=False)
+            stencil_case("cfg5_loop_1000x500_L2", t5, (3,), (1,), a.iters, variants=(0,))
+
             del t5
     if a.only in ("", "patch") and not a.quick:
         patch_case("cfg4_torus_regular_10M", synth.torus_quads(400, 250), 10_000_000, max(10, a.iters // 5))
