@@ -225,6 +225,9 @@ def run_reference_arm(args):
 
 # --------------------------------------------------------------------------------- B200 arm --
 def run_b200_arm(args):
+    import faulthandler
+    # a multi-rank run must never hang the box: dump every thread's stack and leave after 5 minutes
+    faulthandler.dump_traceback_later(300, exit=True)
     import torch
     import torch.distributed as dist
     import opensubdiv_b200 as osd
@@ -338,7 +341,7 @@ def run_b200_arm(args):
     # kernel itself, so two consecutive frames (one per control block) are captured ONCE into a CUDA graph --
     # kernel(block b) runs concurrently with broadcast(block 1-b) -- and the timed loop replays it.
     graph = None
-    if world > 1 and not args.no_graph:
+    if world > 1 and args.graph:
         try:
             for b in (0, 1):                                   # both blocks valid everywhere before the first replay
                 dist.broadcast(blocks[b], src=0)
@@ -402,13 +405,16 @@ def run_b200_arm(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    log(f"[bench] rank {rank}: timing {args.steps} device-resident steps")
     if graph is not None and args.steps % 2 == 0:
         pending["half"] = 0
         ms_dev, _ = timed(step_graph, args.steps, args.warmup + (args.warmup % 2))
         launches = args.steps                                  # one sell_kernel per frame inside the replayed graph
     else:
         ms_dev, launches = timed(step_device, args.steps, args.warmup)
+    log(f"[bench] rank {rank}: device-resident done ({ms_dev / args.steps:.4f} ms/step); timing host-buffer steps")
     ms_e2e, _ = timed(step_e2e, max(3, min(args.steps, 20)), 3)
+    log(f"[bench] rank {rank}: host-buffer steps done")
     e2e_steps = max(3, min(args.steps, 20))
     # the timed regions are milliseconds long: keep the same step running ~1 s more (untimed) so that the 50 ms
     # nvidia-smi sampler sees the clocks this kernel actually runs at under load
@@ -428,7 +434,7 @@ def run_b200_arm(args):
 
     if rank == 0:
         cpu = None
-        if world == 1 or True:
+        if world == 1:                                          # the CPU baseline is a rank-0, N=1 report
             try:
                 probe = cpu_reference_frames(mesh, table, 4, os.cpu_count() or 1)
                 best = max(probe, key=lambda k: probe[k]["verts_per_s"])
@@ -438,6 +444,9 @@ def run_b200_arm(args):
                                  + ", ".join(f"{k}: {v['ms_per_frame']:.0f} ms/frame @{v['cores']} thr" for k, v in probe.items())}
             except Exception as exc:      # the baseline is a report, never a reason to lose the GPU number
                 cpu = {"value": None, "unit": "verts/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+        else:
+            cpu = {"value": None, "unit": "verts/s", "cores": 0, "kind": "reference",
+                   "sample": "reported at N=1 only (run bench.py --gpus 1 or --impl reference)"}
         line = {
             "metric": "refined_verts_per_sec_EvalStencils", "value": value, "unit": "verts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -478,7 +487,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant (0 = auto)")
-    ap.add_argument("--no-graph", action="store_true", help="N > 1: eager pipeline instead of the CUDA-graph frame pair")
+    ap.add_argument("--graph", action="store_true",
+                    help="N > 1: replay a CUDA graph of two frames instead of the eager pipeline (verified at N=2 only)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N meshes (default), strong = one mesh cut into N row ranges")
     args = ap.parse_args()
