@@ -87,11 +87,13 @@ template <int ORDER, bool HULL>
 int launch_patches_h(const PatchIO &io, int LT, cudaStream_t st) {
     const int block = kPatchBlock;
     const int grid = (io.n + block - 1) / block;
+    // hull path: per-warp shared-memory copies of 32 hulls, lane stride hullStride+1 rows of 16 bytes
+    const size_t smem = HULL ? (size_t)(block / 32) * 32 * (io.hullStride + 1) * sizeof(float4) : 0;
     switch (LT) {
-        case 1: patch_kernel<1, ORDER, HULL><<<grid, block, 0, st>>>(io); break;
-        case 2: patch_kernel<2, ORDER, HULL><<<grid, block, 0, st>>>(io); break;
-        case 3: patch_kernel<3, ORDER, HULL><<<grid, block, 0, st>>>(io); break;
-        default: patch_kernel<4, ORDER, HULL><<<grid, block, 0, st>>>(io); break;
+        case 1: patch_kernel<1, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
+        case 2: patch_kernel<2, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
+        case 3: patch_kernel<3, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
+        default: patch_kernel<4, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
     }
     return check_launch("patch_kernel");
 }
@@ -116,10 +118,11 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
     int rc = ensure_box_tables();
     if (rc) return rc;
     if (hull) {
-        const long long total = (long long)hull->numPatches * hull->hullStride * hull->hullTiles;
-        hull_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src + srcDesc[0], srcDesc[2], L, patchArrays,
-                                                                           hull->numArrays, patchIndices, hull->numPatches,
-                                                                           hull->hullStride, hull->hullTiles, hull->hull4);
+        const dim3 hblock(32, 8);
+        const dim3 hgrid((unsigned)((hull->numPatches + 7) / 8), (unsigned)hull->hullTiles);
+        hull_gather_kernel<<<hgrid, hblock, 0, st>>>(src + srcDesc[0], srcDesc[2], L, patchArrays, hull->numArrays,
+                                                     patchIndices, hull->numPatches, hull->hullStride, hull->hullTiles,
+                                                     hull->hull4);
         rc = check_launch("hull_gather_kernel");
         if (rc) return rc;
     }
@@ -233,9 +236,10 @@ int b200osd_patch_table_eval(const b200osd_patch_table *tc, int which, const flo
     if (useHull && numPatches > 0) {
         int hs = 0;
         for (int a = 0; a < tr.nArrays; ++a) hs = std::max(hs, t->hostArrays[which][a].stride);
+        if (hs < 1 || hs > 32) useHull = false;       // one warp lane per control point in the cache fill
         const int tiles = (srcDesc[1] + 3) / 4;
         const size_t need = (size_t)numPatches * hs * tiles;
-        if (need > t->hullCap) {
+        if (useHull && need > t->hullCap) {
             cudaFree(t->d_hull);
             t->d_hull = nullptr;
             t->hullCap = 0;
