@@ -87,8 +87,7 @@ template <int ORDER, bool HULL>
 int launch_patches_h(const PatchIO &io, int LT, cudaStream_t st) {
     const int block = kPatchBlock;
     const int grid = (io.n + block - 1) / block;
-    // hull path: per-warp shared-memory copies of 32 hulls, lane stride hullStride+1 rows of 16 bytes
-    const size_t smem = HULL ? (size_t)(block / 32) * 32 * (io.hullStride + 1) * sizeof(float4) : 0;
+    const size_t smem = 0;
     switch (LT) {
         case 1: patch_kernel<1, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
         case 2: patch_kernel<2, ORDER, HULL><<<grid, block, smem, st>>>(io); break;

@@ -182,18 +182,6 @@ struct CvIndirect {
         for (int c = 0; c < LT; ++c) v[c] = ldg_f(p + c);
     }
 };
-// ... or from this warp's shared-memory copy of the lane's hull (rows of 16 bytes, lane stride hullStride+1 rows) ...
-struct CvShared {
-    const float4 *base;
-    template <int LT>
-    B200_HD void load(int j, float (&v)[LT]) const {
-        const float4 t = base[j];
-        if (LT > 0) v[0] = t.x;
-        if (LT > 1) v[1] = t.y;
-        if (LT > 2) v[2] = t.z;
-        if (LT > 3) v[3] = t.w;
-    }
-};
 // ... or from the hull cache: point j of this patch's component tile is one aligned 16-byte row
 struct CvHull {
     const float4 *base;
@@ -543,36 +531,6 @@ B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int bound
     // unknown descriptor: the reference evaluates zero points, i.e. writes zeros
 }
 
-#ifdef __CUDACC__
-// Hull staging for incoherent coordinates (HULL path).  When the 32 coordinates of a warp sit on many different
-// patches, a per-lane read of "my patch's point j" touches 32 different cache lines per instruction (32 L1 wavefronts).
-// Instead the warp copies its 32 hulls into shared memory cooperatively -- consecutive lanes read consecutive 16-byte
-// rows of the same hull, so one instruction covers 2 hulls in 4 wavefronts -- and every lane then evaluates from its
-// own shared-memory copy (lane stride hullStride+1 rows: conflict-free 128-bit reads).  Coherent warps (few distinct
-// patches, e.g. coordinates generated patch by patch) skip the staging: their direct reads are broadcasts.
-__device__ __forceinline__ bool stage_hulls(const PatchIO &io, int patchIndex, bool live, float4 *warpShared) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int key = live ? patchIndex : -1 - lane;
-    const unsigned peers = __match_any_sync(full, key);
-    const int distinct = __popc(__ballot_sync(full, (__ffs(peers) - 1) == lane));
-    if (distinct <= 6) return false;
-    const int hs = io.hullStride;
-    const int rowStride = hs + 1;
-    const int total = 32 * hs;
-    for (int e = lane; e < total; e += 32) {
-        const int c = e / hs, j = e - c * hs;
-        const int p = __shfl_sync(full, live ? patchIndex : -1, c);
-        if (p >= 0) {
-            const float4 v = __ldg(io.hull4 + ((size_t)p * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)hs + j);
-            warpShared[c * rowStride + j] = v;
-        }
-    }
-    __syncwarp();
-    return true;
-}
-#endif
-
 template <int LT, int ORDER, bool HULL>
 B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
@@ -591,16 +549,6 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
         s = int_as_float(ld_coord_word(cw + 3));
         t = int_as_float(ld_coord_word(cw + 4));
     }
-#ifdef __CUDA_ARCH__
-    bool useShared = false;
-    const float4 *sharedHull = nullptr;
-    if (HULL) {
-        extern __shared__ float4 hullShared[];
-        float4 *warpShared = hullShared + (size_t)(threadIdx.x >> 5) * 32 * (io.hullStride + 1);
-        useShared = stage_hulls(io, patchIndex, live, warpShared);
-        sharedHull = warpShared + (threadIdx.x & 31) * (io.hullStride + 1);
-    }
-#endif
     if (live) {
 
         const int *aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
@@ -629,18 +577,13 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
         const float d1 = sign * (float)(1 << depth);
 
         if (HULL) {
-#ifdef __CUDA_ARCH__
-            if (useShared) {
-                CvShared cv;
-                cv.base = sharedHull;
-                eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
-            } else
-#endif
-            {
-                CvHull cv;
-                cv.base = io.hull4 + ((size_t)patchIndex * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)io.hullStride;
-                eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
-            }
+            // hull cache: the patch's control points as compact 16-byte rows (8 sectors per coordinate instead of 18
+            // scattered ones for incoherent coordinates; broadcast reads for coherent ones).  Measured alternatives that
+            // did not pay (profiles/r01c_patch_sweeps.md): per-warp shared-memory staging of the hulls, and dispatching
+            // coherent warps through the index buffer.
+            CvHull cv;
+            cv.base = io.hull4 + ((size_t)patchIndex * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)io.hullStride;
+            eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
         } else {
             const int indexBase = ldg_i(aw + 3), stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
             CvIndirect cv;
