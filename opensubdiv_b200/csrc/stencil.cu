@@ -38,9 +38,6 @@ struct b200osd_stencil_table {
     int4 *d_meta = nullptr;
     int *d_rows = nullptr;
     std::vector<int> windowSliceStart;   // host: first slice of each window (+ sentinel)
-    // per-call scratch: 16-byte packed copy of the control vertices
-    float4 *d_pack = nullptr;
-    size_t packCap = 0;
 };
 
 namespace {
@@ -311,8 +308,7 @@ void launch_sell_shape(const StencilIO &io, const SellTable &t, const SellPlan &
 
 template <int LL, int K>
 void launch_sell_mode(const StencilIO &io, const SellTable &t, const SellPlan &p, int slices, cudaStream_t st) {
-    if (p.mode == SRC_V24 && LL == 6) launch_sell_shape<LL, K, (LL == 6 ? SRC_V24 : SRC_VEC2)>(io, t, p, slices, st);
-    else if (p.mode == SRC_VEC4) launch_sell_shape<LL, K, SRC_VEC4>(io, t, p, slices, st);
+    if (p.mode == SRC_VEC4) launch_sell_shape<LL, K, SRC_VEC4>(io, t, p, slices, st);
     else if (p.mode == SRC_VEC2) launch_sell_shape<LL, K, SRC_VEC2>(io, t, p, slices, st);
     else launch_sell_shape<LL, K, SRC_SCALAR>(io, t, p, slices, st);
 }
@@ -382,7 +378,7 @@ void b200osd_stencil_table_destroy(b200osd_stencil_table *t) {
     if (!t) return;
     cudaFree(t->d_sizes); cudaFree(t->d_offsets); cudaFree(t->d_indices);
     for (int k = 0; k < kMaxOut; ++k) { cudaFree(t->d_w[k]); cudaFree(t->d_w4[k]); }
-    cudaFree(t->d_ipool); cudaFree(t->d_meta); cudaFree(t->d_rows); cudaFree(t->d_pack);
+    cudaFree(t->d_ipool); cudaFree(t->d_meta); cudaFree(t->d_rows);
     delete t;
 }
 
@@ -432,44 +428,23 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
     s.sliceBegin = t->windowSliceStart[start / t->window];
     s.sliceEnd = t->windowSliceStart[(end + t->window - 1) / t->window];
 
-    // Source access.  Default: gather straight from the caller's buffer with the widest load its layout allows
-    // (measured on B200: the compact layout beats a 16-byte repacked copy -- fewer cache lines per warp-wide gather).
-    // Variants (bench / tests): 1 CSR kernel, 2 scalar gathers, 3 repacked 16-byte rows, 4 natural width,
-    // 5/6 xyz+normal vertices through one 128-bit + one 64-bit load (8 / unspecified blocks per SM),
-    // 8 persistent grid, 11 one-shot grid with 8 resident blocks/SM asked of the register allocator, 12 both.
+    // Source access: gather straight from the caller's buffer with the widest load its layout allows.  Measured and
+    // rejected: a 16-byte repacked copy of the control vertices, 128+64-bit loads for 24-byte vertices.
+    // Variants (bench / tests): 1 CSR kernel, 2 scalar gathers, 8 persistent grid, 11 one-shot grid with 8 resident
+    // blocks/SM asked of the register allocator, 12 both.
     SellPlan plan;
     plan.mode = src_mode(io);
     const int L = io.L;
     const int v = g_stencil_variant;
-    // measured defaults (profiles/r01_*): with derivative streams the kernel is register-heavy and latency bound and the
-    // persistent grid's descriptor prefetch wins (+27 % at K=6); 4-float primvars like 64 resident warps
+    // measured defaults (profiles/r01*): with derivative streams the kernel is register-heavy and latency bound and the
+    // persistent grid's descriptor prefetch wins (+27 % at K=6); up to 6 floats 64 resident warps win (+10 % at L=6)
     if (v == 0) {
         if (nOut > 1) plan.persistent = true;
         else if (L <= 6) plan.minBlocks = 8;
     }
     if (v == 2) plan.mode = SRC_SCALAR;
-    if ((v == 5 || v == 6) && L == 6 && plan.mode == SRC_VEC2 && io.srcStride == 6) plan.mode = SRC_V24;   // 128+64-bit gathers
-    if (v == 6) plan.minBlocks = 0;
     if (v == 8 || v == 12) plan.persistent = true;
     if (v == 11 || v == 12) plan.minBlocks = 8;
-    if (v == 3 && (L == 3 || L == 4 || L == 6 || L == 8)) {
-        const int nv4 = (L + 3) / 4;
-        const size_t need = (size_t)t->nCV * nv4;
-        if (need > t->packCap) {
-            cudaFree(t->d_pack);
-            t->d_pack = nullptr;
-            t->packCap = 0;
-            B200_CUDA_TRY(cudaMalloc((void **)&t->d_pack, need * sizeof(float4)));
-            t->packCap = need;
-        }
-        const int total = t->nCV * nv4;
-        pack_src_kernel<<<(total + 255) / 256, 256, 0, st>>>(io.src, io.srcStride, L, t->nCV, t->d_pack);
-        rc = check_launch("pack_src_kernel");
-        if (rc) return rc;
-        io.src = reinterpret_cast<const float *>(t->d_pack);
-        io.srcStride = 4 * nv4;
-        plan.mode = SRC_VEC4;
-    }
     return nOut == 1 ? launch_sell<1>(io, s, plan, st) : (nOut == 3 ? launch_sell<3>(io, s, plan, st) : launch_sell<6>(io, s, plan, st));
 }
 

@@ -25,7 +25,7 @@ constexpr int kVec = 4;            // elements per 128-bit load
 
 struct StencilIO {
     const float *src;              // already offset by srcDesc.offset
-    int srcStride;                 // floats between vertices (== 4*ceil(L/4) when the packed copy is used)
+    int srcStride;                 // floats between vertices
     int L;                         // primvar length
     float *dst[kMaxOut];           // already offset; NULL = skip
     int dstStride[kMaxOut];
@@ -56,7 +56,7 @@ __device__ __forceinline__ void load_vertex_scalar(const float *src, int stride,
     for (int k = 0; k < L; ++k) v[k] = p[k];
 }
 
-// stride is a multiple of 4 floats and src is 16-byte aligned (packed copy, or a naturally aligned buffer)
+// stride is a multiple of 4 floats and src is 16-byte aligned
 template <int L>
 __device__ __forceinline__ void load_vertex_vec4(const float *src, int stride, int idx, float (&v)[L]) {
     const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)idx * (size_t)stride);
@@ -82,38 +82,11 @@ __device__ __forceinline__ void load_vertex_vec2(const float *src, int stride, i
     }
 }
 
-// 6-float vertices (xyz+normal) at an 8-byte aligned, 24-byte stride: every vertex is either 16-byte aligned or 8 off.
-// One 128-bit and one 64-bit load per vertex, their order chosen per lane by the address parity (no divergence: both
-// loads are executed by every lane, only the addresses and the final component selection differ) -- two gather
-// instructions instead of three.
-__device__ __forceinline__ void load_vertex_6x24(const float *src, int stride, int idx, float (&v)[6]) {
-    const char *a = reinterpret_cast<const char *>(src + (size_t)idx * (size_t)stride);
-    const bool hi = (reinterpret_cast<uintptr_t>(a) & 8u) != 0;
-    const float4 A = *reinterpret_cast<const float4 *>(a + (hi ? 8 : 0));
-    const float2 B = *reinterpret_cast<const float2 *>(a + (hi ? 0 : 16));
-    v[0] = hi ? B.x : A.x;
-    v[1] = hi ? B.y : A.y;
-    v[2] = hi ? A.x : A.z;
-    v[3] = hi ? A.y : A.w;
-    v[4] = hi ? A.z : B.x;
-    v[5] = hi ? A.w : B.y;
-}
-
-enum { SRC_SCALAR = 0, SRC_VEC2 = 1, SRC_VEC4 = 2, SRC_V24 = 3 };
-
-template <int L>
-__device__ __forceinline__ void load_vertex_v24(const float *src, int stride, int idx, float (&v)[L]) {
-    load_vertex_vec2<L>(src, stride, idx, v);
-}
-template <>
-__device__ __forceinline__ void load_vertex_v24<6>(const float *src, int stride, int idx, float (&v)[6]) {
-    load_vertex_6x24(src, stride, idx, v);
-}
+enum { SRC_SCALAR = 0, SRC_VEC2 = 1, SRC_VEC4 = 2 };
 
 template <int L, int SRCMODE>
 __device__ __forceinline__ void load_vertex(const float *src, int stride, int idx, float (&v)[L]) {
-    if (SRCMODE == SRC_V24)       load_vertex_v24<L>(src, stride, idx, v);
-    else if (SRCMODE == SRC_VEC4) load_vertex_vec4<L>(src, stride, idx, v);
+    if (SRCMODE == SRC_VEC4)      load_vertex_vec4<L>(src, stride, idx, v);
     else if (SRCMODE == SRC_VEC2) load_vertex_vec2<L>(src, stride, idx, v);
     else                          load_vertex_scalar<L>(src, stride, idx, v);
 }
@@ -379,23 +352,6 @@ __global__ void __launch_bounds__(256) sell_kernel_anyL(StencilIO io, SellTable 
             }
         }
     }
-}
-
-// Repack `n` source vertices (length L, arbitrary stride) into 16-byte aligned rows of 4*ceil(L/4) floats so
-// that every gather is ceil(L/4) 128-bit loads.  n is the control-vertex count (small: it is the hot set).
-__global__ void __launch_bounds__(256) pack_src_kernel(const float *src, int srcStride, int L, int n, float4 *out) {
-    int nv4 = (L + 3) >> 2;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * nv4) return;
-    int v = i / nv4, c = i - v * nv4;
-    const float *p = src + (size_t)v * (size_t)srcStride + 4 * c;
-    int rem = L - 4 * c;
-    float4 r;
-    r.x = p[0];
-    r.y = rem > 1 ? p[1] : 0.0f;
-    r.z = rem > 2 ? p[2] : 0.0f;
-    r.w = rem > 3 ? p[3] : 0.0f;
-    out[i] = r;
 }
 
 }  // namespace b200osd
