@@ -17,6 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC_PATH = os.path.join(_HERE, "osd_oracle.c")
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
+LIB64_PATH = os.path.join(_HERE, "liboracle_f64.so")
 
 DESC_DTYPE = np.dtype([("offset", "<i4"), ("length", "<i4"), ("stride", "<i4")])
 
@@ -30,6 +31,50 @@ def build(force: bool = False) -> str:
         subprocess.check_call([cc, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c99", "-Wall",
                                "-o", LIB_PATH, SRC_PATH, "-lm"])
     return LIB_PATH
+
+
+_lib64 = None
+
+
+def lib64():
+    """The same restatement compiled with -DORACLE_F64 (all arithmetic in double on the same fp32 inputs): the
+    "truth" used to measure the rounding error of the reference and of the B200 kernels.  Not the parity oracle."""
+    global _lib64
+    if _lib64 is None:
+        if not os.path.exists(LIB64_PATH) or os.path.getmtime(LIB64_PATH) < os.path.getmtime(SRC_PATH):
+            cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+            subprocess.check_call([cc, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c99", "-Wall", "-DORACLE_F64",
+                                   "-o", LIB64_PATH, SRC_PATH, "-lm"])
+        L = C.CDLL(LIB64_PATH)
+        vp = C.c_void_p
+        L.oracle_eval_stencils.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.oracle_eval_patches.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+        L.oracle_set_abs_mode.argtypes = [C.c_int]
+        _lib64 = L
+    return _lib64
+
+
+def eval_stencils_f64(src, src_desc, n_rows, L, sizes, offsets, indices, weights, start=0, end=None):
+    """Double-precision evaluation of the same table on the same fp32 inputs -> list of [n_rows, L] float64 arrays."""
+    nw = len(weights)
+    end = len(sizes) if end is None else end
+    src64 = np.ascontiguousarray(src, dtype=np.float64).reshape(-1)
+    w64 = [np.ascontiguousarray(w, dtype=np.float64) for w in weights]
+    outs = [np.zeros((n_rows, L), np.float64) for _ in range(nw)]
+    sd, dd = _descs([src_desc]), _descs([(0, L, L)] * nw)
+    dptr = (C.c_void_p * nw)(*[o.ctypes.data for o in outs])
+    wptr = (C.c_void_p * nw)(*[w.ctypes.data for w in w64])
+    assert lib64().oracle_eval_stencils(nw, _p(src64), _p(sd), dptr, _p(dd), _p(sizes), _p(offsets), _p(indices), wptr, start, end)
+    return outs
+
+
+def eval_patches_f64(src, src_desc, L, coords, arrays, indices, params, nw=6):
+    src64 = np.ascontiguousarray(src, dtype=np.float64).reshape(-1)
+    outs = [np.zeros((len(coords), L), np.float64) for _ in range(nw)]
+    sd, dd = _descs([src_desc]), _descs([(0, L, L)] * nw)
+    dptr = (C.c_void_p * nw)(*[o.ctypes.data for o in outs])
+    assert lib64().oracle_eval_patches(nw, _p(src64), _p(sd), dptr, _p(dd), len(coords), _p(coords), _p(arrays), _p(indices), _p(params))
+    return outs
 
 
 def lib():

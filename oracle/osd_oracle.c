@@ -27,6 +27,18 @@
 #include <stddef.h>
 #include <string.h>
 
+/* Arithmetic type.  Default float = the reference's arithmetic (this is THE oracle).  Compiled a second time with
+ * -DORACLE_F64 every value (primvars, weights, results) is a double: the same algorithm evaluated in double precision on
+ * the same fp32 inputs, i.e. the "truth" against which the rounding error of the reference and of the B200 kernels
+ * can both be measured (tests/test_accuracy_vs_f64.py).  PatchCoord (s,t) stay fp32 inputs in both builds. */
+#ifdef ORACLE_F64
+typedef double real;
+#define RABS fabs
+#else
+typedef float real;
+#define RABS fabsf
+#endif
+
 /* Tolerance scale mode (tests only): when set, every accumulation uses |value| * |weight|, so the evaluators
  * return S = sum_j |w_j| |x_j| -- the magnitude against which a 1e-6 relative bound is meaningful when signed
  * derivative weights cancel ("Parity at 1e-6 relative"). */
@@ -37,13 +49,13 @@ void oracle_set_abs_mode(int on) { g_abs_mode = on; }
  * W = max_j |unfolded w_j| of its set.  In abs mode EvalPatches therefore returns
  *     S = sum_j (|w_j| + W) |x_j|
  * which bounds the rounding error of ANY correct fp32 evaluation order (reference's included) by ~n*eps*S. */
-static float g_wmax[6];
-static void note_wmax(float *const w[6], int nsets, int npts)
+static real g_wmax[6];
+static void note_wmax(real *const w[6], int nsets, int npts)
 {
     int k, j;
     for (k = 0; k < nsets; ++k) {
-        float m = 0.0f;
-        for (j = 0; j < npts; ++j) if (fabsf(w[k][j]) > m) m = fabsf(w[k][j]);
+        real m = 0.0f;
+        for (j = 0; j < npts; ++j) if (RABS(w[k][j]) > m) m = RABS(w[k][j]);
         g_wmax[k] = m;
     }
 }
@@ -72,10 +84,10 @@ enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_B
  * cpuEvaluator.cpp:47,70-72,105-110).  end<=start is a successful no-op (cpuEvaluator.cpp:46).
  * -----------------------------------------------------------------------------------------------*/
 int oracle_eval_stencils(int nw,
-                         const float *src, const oracle_desc *srcDesc,
-                         float *const *dsts, const oracle_desc *dstDescs,
+                         const real *src, const oracle_desc *srcDesc,
+                         real *const *dsts, const oracle_desc *dstDescs,
                          const int *sizes, const int *offsets, const int *indices,
-                         const float *const *weights, int start, int end)
+                         const real *const *weights, int start, int end)
 {
     int L, i, j, k, w;
     if (end <= start) return 1;
@@ -86,21 +98,21 @@ int oracle_eval_stencils(int nw,
 
     src += srcDesc->offset;
     for (i = start; i < end; ++i) {
-        float acc[6][ORACLE_MAX_LEN];
+        real acc[6][ORACLE_MAX_LEN];
         int off = offsets[i];
         int n = sizes[i];
         memset(acc, 0, sizeof(acc));
         for (j = 0; j < n; ++j) {
-            const float *v = src + (ptrdiff_t)indices[off + j] * srcDesc->stride;
+            const real *v = src + (ptrdiff_t)indices[off + j] * srcDesc->stride;
             for (w = 0; w < nw; ++w) {
-                float wt = weights[w][off + j];
-                if (g_abs_mode) { for (k = 0; k < L; ++k) acc[w][k] += fabsf(v[k]) * fabsf(wt); }
+                real wt = weights[w][off + j];
+                if (g_abs_mode) { for (k = 0; k < L; ++k) acc[w][k] += RABS(v[k]) * RABS(wt); }
                 else            { for (k = 0; k < L; ++k) acc[w][k] += v[k] * wt; }   /* addWithWeight, cpuKernel.cpp:52-61 */
             }
         }
         for (w = 0; w < nw; ++w) {
             if (!dsts[w]) continue;
-            memcpy(dsts[w] + dstDescs[w].offset + (ptrdiff_t)i * dstDescs[w].stride, acc[w], (size_t)L * sizeof(float));
+            memcpy(dsts[w] + dstDescs[w].offset + (ptrdiff_t)i * dstDescs[w].stride, acc[w], (size_t)L * sizeof(real));
         }
     }
     return 1;
@@ -121,10 +133,14 @@ static int pp_u(unsigned f1)        { return (int)((f1 >> 22) & 0x3ffu); }
 /* ---------------------------------------------------------------------------- 1-D cubic curves --
  * Uniform cubic B-spline (osd/patchBasis.h:99-135) and cubic Bernstein (:247-283) bases with first
  * and second derivatives.  d1/d2 may be NULL.  */
-static void bspline3(float t, float *b, float *d1, float *d2)
+static void bspline3(real t, real *b, real *d1, real *d2)
 {
-    const float sixth = (float)(1.0f / 6.0f);
-    float t2 = t * t, t3 = t * t2;
+    #ifdef ORACLE_F64
+    const real sixth = 1.0 / 6.0;
+#else
+    const real sixth = (real)(1.0f / 6.0f);
+#endif
+    real t2 = t * t, t3 = t * t2;
     b[0] = sixth * (1.0f - 3.0f * (t - t2) - t3);
     b[1] = sixth * (4.0f - 6.0f * t2 + 3.0f * t3);
     b[2] = sixth * (1.0f + 3.0f * (t + t2 - t3));
@@ -143,9 +159,9 @@ static void bspline3(float t, float *b, float *d1, float *d2)
     }
 }
 
-static void bezier3(float t, float *b, float *d1, float *d2)
+static void bezier3(real t, real *b, real *d1, real *d2)
 {
-    float t2 = t * t, c = 1.0f - t, c2 = c * c;
+    real t2 = t * t, c = 1.0f - t, c2 = c * c;
     b[0] = c2 * c;
     b[1] = c2 * t * 3.0f;
     b[2] = t2 * c * 3.0f;
@@ -165,7 +181,7 @@ static void bezier3(float t, float *b, float *d1, float *d2)
 }
 
 /* w[4*row + col] = cs[col] * ct[row]  (osd/patchBasis.h:218-243) */
-static void tensor4(const float *cs, const float *ct, float *w)
+static void tensor4(const real *cs, const real *ct, real *w)
 {
     int r, c;
     for (r = 0; r < 4; ++r)
@@ -174,9 +190,9 @@ static void tensor4(const float *cs, const float *ct, float *w)
 
 /* ------------------------------------------------------------------------------------ linear --
  * osd/patchBasis.h:53-97 (bilinear quad) and :493-525 (linear triangle). */
-static int basis_quads(float s, float t, float *w[6], int order)
+static int basis_quads(real s, real t, real *w[6], int order)
 {
-    float sc = 1.0f - s, tc = 1.0f - t;
+    real sc = 1.0f - s, tc = 1.0f - t;
     w[0][0] = sc * tc; w[0][1] = s * tc; w[0][2] = s * t; w[0][3] = sc * t;
     if (order >= 1) {
         w[1][0] = -tc; w[1][1] = tc; w[1][2] = t; w[1][3] = -t;
@@ -190,7 +206,7 @@ static int basis_quads(float s, float t, float *w[6], int order)
     return 4;
 }
 
-static int basis_tris(float s, float t, float *w[6], int order)
+static int basis_tris(real s, real t, real *w[6], int order)
 {
     w[0][0] = 1.0f - s - t; w[0][1] = s; w[0][2] = t;
     if (order >= 1) {
@@ -209,7 +225,7 @@ static int basis_tris(float s, float t, float *w[6], int order)
  * Tensor product (osd/patchBasis.h:204-245) followed by boundary folding (:138-200): for each boundary
  * edge the phantom row/column of weights w0 is folded into its two neighbours, w1 += 2*w0, w2 -= w0,
  * w0 = 0, edges taken in bit order 1 (row 0), 2 (col 3), 4 (row 3), 8 (col 0).  */
-static void fold_line(float *w, int i0, int i1, int i2, int step, int count)
+static void fold_line(real *w, int i0, int i1, int i2, int step, int count)
 {
     int k;
     for (k = 0; k < count; ++k, i0 += step, i1 += step, i2 += step) {
@@ -219,7 +235,7 @@ static void fold_line(float *w, int i0, int i1, int i2, int step, int count)
     }
 }
 
-static void bspline_fold_boundary(int mask, float *w)
+static void bspline_fold_boundary(int mask, real *w)
 {
     if (mask & 1) fold_line(w, 0, 4, 8, 1, 4);        /* t = 0 edge: row 0 -> rows 1,2 */
     if (mask & 2) fold_line(w, 3, 2, 1, 4, 4);        /* s = 1 edge: col 3 -> cols 2,1 */
@@ -227,9 +243,9 @@ static void bspline_fold_boundary(int mask, float *w)
     if (mask & 8) fold_line(w, 0, 1, 2, 4, 4);        /* s = 0 edge: col 0 -> cols 1,2 */
 }
 
-static int basis_regular(float s, float t, int boundary, float *w[6], int order)
+static int basis_regular(real s, real t, int boundary, real *w[6], int order)
 {
-    float bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4];
+    real bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4];
     int k;
     bspline3(s, bs, order >= 1 ? ds : NULL, order >= 2 ? dss : NULL);
     bspline3(t, bt, order >= 1 ? dt : NULL, order >= 2 ? dtt : NULL);
@@ -254,11 +270,11 @@ static int basis_regular(float s, float t, int boundary, float *w[6], int order)
 static const signed char GREG_COL[20] = { 0, 1, 0, 1, 1,   3, 3, 2, 2, 2,   3, 2, 3, 2, 2,   0, 0, 1, 1, 1 };
 static const signed char GREG_ROW[20] = { 0, 0, 1, 1, 1,   0, 1, 0, 1, 1,   3, 3, 2, 2, 2,   3, 2, 3, 2, 2 };
 
-static int basis_gregory(float s, float t, float *w[6], int order)
+static int basis_gregory(real s, real t, real *w[6], int order)
 {
-    float bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4], G[8];
-    float sc = 1.0f - s, tc = 1.0f - t;
-    float a[4], b[4];
+    real bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4], G[8];
+    real sc = 1.0f - s, tc = 1.0f - t;
+    real a[4], b[4];
     int c, i;
     bezier3(s, bs, order >= 1 ? ds : NULL, order >= 2 ? dss : NULL);
     bezier3(t, bt, order >= 1 ? dt : NULL, order >= 2 ? dtt : NULL);
@@ -268,8 +284,8 @@ static int basis_gregory(float s, float t, float *w[6], int order)
     a[2] = sc; b[2] = tc;
     a[3] = tc; b[3] = s;
     for (c = 0; c < 4; ++c) {
-        float d = (c == 0) ? (s + t) : (c == 1) ? (sc + t) : (c == 2) ? (sc + tc) : (s + tc);
-        float r = (d <= 0.0f) ? 1.0f : (1.0f / d);
+        real d = (c == 0) ? (s + t) : (c == 1) ? (sc + t) : (c == 2) ? (sc + tc) : (s + tc);
+        real r = (d <= 0.0f) ? 1.0f : (1.0f / d);
         G[2 * c] = a[c] * r;
         G[2 * c + 1] = 1.0f - a[c] * r;
         (void)b;
@@ -277,7 +293,7 @@ static int basis_gregory(float s, float t, float *w[6], int order)
     for (i = 0; i < 20; ++i) {
         int col = GREG_COL[i], row = GREG_ROW[i], p = i % 5;
         int rational = (p >= 3);
-        float g = rational ? G[2 * (i / 5) + (p - 3)] : 1.0f;
+        real g = rational ? G[2 * (i / 5) + (p - 3)] : 1.0f;
         if (rational) {
             w[0][i] = bs[col] * bt[row] * g;
             if (order >= 1) {
@@ -311,7 +327,7 @@ static int basis_gregory(float s, float t, float *w[6], int order)
  *   m: 0:1  1:s  2:t  3:s^2  4:st  5:t^2  6:s^3  7:s^2t  8:st^2  9:t^3  10:s^4  11:s^3t  12:s^2t^2  13:st^3  14:t^4
  * All derivative tables are DERIVED here by differentiating that one table (d/ds s^a t^b = a s^(a-1) t^b),
  * then normalised to the integer scale the reference uses (1/12, 1/6, 1, 1/2, 1) so that evaluation
- * in increasing-monomial order reproduces the same float sequence.  */
+ * in increasing-monomial order reproduces the same real sequence.  */
 static const signed char BOX12[12][15] = {
     /*        1   s   t  ss  st  tt sss sst stt ttt  s4 s3t s2t2 st3  t4 */
     /* 0*/ {  1, -2, -4,  0,  6,  6,  2,  0, -6, -4, -1, -2,  0,  2,  1 },
@@ -341,7 +357,7 @@ static int mono_index(int a, int b)
 /* tables[k][i][m], k: 0 value, 1 d/ds, 2 d/dt, 3 dss, 4 dst, 5 dtt; scales[k] the common factor */
 static int   g_box_ready = 0;
 static int   g_box_tab[6][12][15];
-static float g_box_scale[6];
+static real g_box_scale[6];
 
 static void box_init(void)
 {
@@ -362,10 +378,15 @@ static void box_init(void)
             }
         }
     }
-    g_box_scale[0] = (float)(1.0f / 12.0f);
-    g_box_scale[1] = g_box_scale[2] = (float)(1.0f / 6.0f);
+#ifdef ORACLE_F64
+    g_box_scale[0] = 1.0 / 12.0;
+    g_box_scale[1] = g_box_scale[2] = 1.0 / 6.0;
+#else
+    g_box_scale[0] = (real)(1.0f / 12.0f);
+    g_box_scale[1] = g_box_scale[2] = (real)(1.0f / 6.0f);
+#endif
     g_box_scale[3] = g_box_scale[5] = 1.0f;
-    g_box_scale[4] = (float)(1.0f / 2.0f);
+    g_box_scale[4] = (real)(1.0f / 2.0f);
     g_box_ready = 1;
 }
 
@@ -381,15 +402,15 @@ static void box_init(void)
  *            7   8   9
  *             10  11
  */
-static void refl(float *w, int phantom, int plus0, int plus1, int minus)
+static void refl(real *w, int phantom, int plus0, int plus1, int minus)
 {
-    float v = w[phantom];
+    real v = w[phantom];
     w[plus0] += v;
     w[plus1] += v;
     w[minus] -= v;
 }
 
-static void box_fold_boundary(int mask, float *w)
+static void box_fold_boundary(int mask, real *w)
 {
     /* per edge e: phantom triple, the three patch corners' ring points used by the reflections.
      * Roles for edge 0:  phantoms (0,1,2); B1=4, B2=5; I1=8; B0=3,I0=7 (left neighbour), B3=6,I2=9 (right).  */
@@ -428,9 +449,9 @@ static void box_fold_boundary(int mask, float *w)
     }
 }
 
-static int basis_loop(float s, float t, int boundary, float *w[6], int order)
+static int basis_loop(real s, real t, int boundary, real *w[6], int order)
 {
-    float M[15];
+    real M[15];
     int nsets = order == 0 ? 1 : (order == 1 ? 3 : 6), k, i, m;
     if (!g_box_ready) box_init();
     /* monomials built by repeated multiplication exactly as :533-556 */
@@ -440,10 +461,10 @@ static int basis_loop(float s, float t, int boundary, float *w[6], int order)
     M[10] = M[6] * s; M[11] = M[7] * s; M[12] = M[3] * M[5]; M[13] = M[8] * t; M[14] = M[9] * t;
     for (k = 0; k < nsets; ++k) {
         for (i = 0; i < 12; ++i) {
-            float acc = 0.0f;
+            real acc = 0.0f;
             for (m = 0; m < 15; ++m) {
                 int c = g_box_tab[k][i][m];
-                if (c) acc += (float)c * M[m];
+                if (c) acc += (real)c * M[m];
             }
             w[k][i] = g_box_scale[k] * acc;
         }
@@ -461,10 +482,10 @@ static int basis_loop(float s, float t, int boundary, float *w[6], int order)
  *   dB4_ijk/ds = 4 (B3_{i-1,j,k} - B3_{i,j,k-1}),   d2/ds2 = 12 (B2_{i-2,j,k} - 2 B2_{i-1,j,k-1} + B2_{i,j,k-2}), ...
  * The 18 Gregory-triangle points reuse 12 boundary Bernstein weights and split the 3 interior ones
  * with rational blends G (:1044-1110), default 1/0 when a denominator vanishes (:1132-1145).  */
-static float bern(int n, int i, int j, int k, float u, float v, float w)
+static real bern(int n, int i, int j, int k, real u, real v, real w)
 {
-    static const float fact[5] = { 1.0f, 1.0f, 2.0f, 6.0f, 24.0f };
-    float r;
+    static const real fact[5] = { 1.0f, 1.0f, 2.0f, 6.0f, 24.0f };
+    real r;
     int q;
     if (i < 0 || j < 0 || k < 0) return 0.0f;
     r = fact[n] / (fact[i] * fact[j] * fact[k]);
@@ -474,20 +495,20 @@ static float bern(int n, int i, int j, int k, float u, float v, float w)
     return r;
 }
 
-static void bezier_tri4(float s, float t, int ds, int dt, float *B)
+static void bezier_tri4(real s, real t, int ds, int dt, real *B)
 {
     /* point order: index -> (i = power of u, j = power of v), k = 4-i-j */
     static const signed char PI[15] = { 0, 1, 2, 3, 4, 0, 1, 2, 3, 0, 1, 2, 0, 1, 0 };
     static const signed char PJ[15] = { 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4 };
-    float u = s, v = t, w = 1.0f - u - v;
+    real u = s, v = t, w = 1.0f - u - v;
     int n;
     for (n = 0; n < 15; ++n) {
         int i = PI[n], j = PJ[n], k = 4 - i - j;
-        float r;
+        real r;
         if (ds + dt == 0) {
             r = bern(4, i, j, k, u, v, w);
         } else if (ds + dt == 1) {
-            float lower = ds ? bern(3, i - 1, j, k, u, v, w) : bern(3, i, j - 1, k, u, v, w);
+            real lower = ds ? bern(3, i - 1, j, k, u, v, w) : bern(3, i, j - 1, k, u, v, w);
             r = 4.0f * (lower - bern(3, i, j, k - 1, u, v, w));
         } else if (ds == 2) {
             r = 12.0f * (bern(2, i - 2, j, k, u, v, w) - 2.0f * bern(2, i - 1, j, k - 1, u, v, w) + bern(2, i, j, k - 2, u, v, w));
@@ -501,7 +522,7 @@ static void bezier_tri4(float s, float t, int ds, int dt, float *B)
     }
 }
 
-static void gregory_tri_from_bezier(const float *B, const float *G, float *w)
+static void gregory_tri_from_bezier(const real *B, const real *G, real *w)
 {
     /* 18 points = 3 corners x {P, E+, E-, F+, F-} + 3 edge mid points (osd/patchBasis.h:1044-1110) */
     static const signed char SRC[18] = { 0, 1, 5, 6, 6,   4, 8, 3, 7, 7,   14, 12, 13, 10, 10,   2, 11, 9 };
@@ -510,11 +531,11 @@ static void gregory_tri_from_bezier(const float *B, const float *G, float *w)
     for (i = 0; i < 18; ++i) w[i] = (GI[i] < 0) ? B[SRC[i]] : B[SRC[i]] * G[GI[i]];
 }
 
-static int basis_gregory_tri(float s, float t, float *w[6], int order)
+static int basis_gregory_tri(real s, real t, real *w[6], int order)
 {
     static const int DS[6] = { 0, 1, 0, 2, 1, 0 }, DT[6] = { 0, 0, 1, 0, 1, 2 };
-    float G[6] = { 1.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.0f };
-    float u = s, v = t, ww = 1.0f - u - v, B[15];
+    real G[6] = { 1.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.0f };
+    real u = s, v = t, ww = 1.0f - u - v, B[15];
     int nsets = order == 0 ? 1 : (order == 1 ? 3 : 6), k;
     if ((u + v) > 0.0f)  { G[0] = u / (u + v);   G[1] = v / (u + v); }
     if ((v + ww) > 0.0f) { G[2] = v / (v + ww);  G[3] = ww / (v + ww); }
@@ -532,26 +553,26 @@ static int basis_gregory_tri(float s, float t, float *w[6], int order)
  * d1 = sign * 2^depth and d2 = sign * d1 * d1 (sign = -1 for a rotated triangle).
  * order: 0 -> wP only, 1 -> +wDs,wDt, 2 -> +wDss,wDst,wDtt.  Returns the number of points.
  * -----------------------------------------------------------------------------------------------*/
-int oracle_patch_basis(int patchType, unsigned field0, unsigned field1, float s, float t,
-                       float *wP, float *wDs, float *wDt, float *wDss, float *wDst, float *wDtt)
+int oracle_patch_basis(int patchType, unsigned field0, unsigned field1, real s, real t,
+                       real *wP, real *wDs, real *wDt, real *wDss, real *wDst, real *wDtt)
 {
-    float *w[6];
+    real *w[6];
     int order = (wDs && wDt) ? ((wDss && wDst && wDtt) ? 2 : 1) : 0;
     int depth = pp_depth(field1), n = 0, i;
     int isTri = (patchType == PT_LOOP || patchType == PT_GREGORY_TRIANGLE || patchType == PT_TRIANGLES);
-    float sign = 1.0f;
-    float fracInv = (float)(1 << (depth - pp_nonquad(field1)));
+    real sign = 1.0f;
+    real fracInv = (real)(1 << (depth - pp_nonquad(field1)));
     (void)field0;
     w[0] = wP; w[1] = wDs; w[2] = wDt; w[3] = wDss; w[4] = wDst; w[5] = wDtt;
 
     if (isTri && (pp_u(field1) + pp_v(field1)) >= (1 << depth)) {
         int df = 1 << depth;
-        s = (float)(df - pp_u(field1)) - (s * fracInv);
-        t = (float)(df - pp_v(field1)) - (t * fracInv);
+        s = (real)(df - pp_u(field1)) - (s * fracInv);
+        t = (real)(df - pp_v(field1)) - (t * fracInv);
         sign = -1.0f;
     } else {
-        s = s * fracInv - (float)pp_u(field1);
-        t = t * fracInv - (float)pp_v(field1);
+        s = s * fracInv - (real)pp_u(field1);
+        t = t * fracInv - (real)pp_v(field1);
     }
 
     switch (patchType) {
@@ -565,14 +586,14 @@ int oracle_patch_basis(int patchType, unsigned field0, unsigned field1, float s,
     }
     if (patchType != PT_REGULAR && patchType != PT_LOOP) note_wmax(w, order == 0 ? 1 : (order == 1 ? 3 : 6), n);
     {
-        float a1 = (float)(1 << depth), a2 = a1 * a1;
+        real a1 = (real)(1 << depth), a2 = a1 * a1;
         g_wmax[1] *= a1; g_wmax[2] *= a1; g_wmax[3] *= a2; g_wmax[4] *= a2; g_wmax[5] *= a2;
     }
     if (order >= 1) {
-        float d1 = sign * (float)(1 << depth);
+        real d1 = sign * (real)(1 << depth);
         for (i = 0; i < n; ++i) { wDs[i] *= d1; wDt[i] *= d1; }
         if (order >= 2) {
-            float d2 = sign * d1 * d1;
+            real d2 = sign * d1 * d1;
             for (i = 0; i < n; ++i) { wDss[i] *= d2; wDst[i] *= d2; wDtt[i] *= d2; }
         }
     }
@@ -592,12 +613,12 @@ int oracle_patch_basis(int patchType, unsigned field0, unsigned field1, float s,
  * (the CUDA backend's behaviour, osd/cudaKernel.cu:300-327; the CPU reference would dereference them).
  * -----------------------------------------------------------------------------------------------*/
 int oracle_eval_patches(int nw,
-                        const float *src, const oracle_desc *srcDesc,
-                        float *const *dsts, const oracle_desc *dstDescs,
+                        const real *src, const oracle_desc *srcDesc,
+                        real *const *dsts, const oracle_desc *dstDescs,
                         int numPatchCoords, const oracle_coord *coords,
                         const oracle_array *arrays, const int *indices, const oracle_param *params)
 {
-    float wbuf[6][20];
+    real wbuf[6][20];
     int L, i, j, k, q;
     if (!src) return 0;
     if (nw == 1 && !dsts[0]) return 0;
@@ -617,15 +638,15 @@ int oracle_eval_patches(int nw,
                                    wbuf[0], nw >= 3 ? wbuf[1] : NULL, nw >= 3 ? wbuf[2] : NULL,
                                    nw >= 6 ? wbuf[3] : NULL, nw >= 6 ? wbuf[4] : NULL, nw >= 6 ? wbuf[5] : NULL);
         for (q = 0; q < nw; ++q) {
-            float acc[ORACLE_MAX_LEN];
+            real acc[ORACLE_MAX_LEN];
             if (!dsts[q]) continue;
             for (k = 0; k < L; ++k) acc[k] = 0.0f;
             for (j = 0; j < n; ++j) {
-                const float *v = src + (ptrdiff_t)cvs[j] * srcDesc->stride;
-                if (g_abs_mode) { for (k = 0; k < L; ++k) acc[k] += fabsf(v[k]) * (fabsf(wbuf[q][j]) + (g_abs_mode == 2 ? g_wmax[q] : 0.0f)); }
+                const real *v = src + (ptrdiff_t)cvs[j] * srcDesc->stride;
+                if (g_abs_mode) { for (k = 0; k < L; ++k) acc[k] += RABS(v[k]) * (RABS(wbuf[q][j]) + (g_abs_mode == 2 ? g_wmax[q] : 0.0f)); }
                 else            { for (k = 0; k < L; ++k) acc[k] += v[k] * wbuf[q][j]; }
             }
-            memcpy(dsts[q] + dstDescs[q].offset + (ptrdiff_t)i * dstDescs[q].stride, acc, (size_t)L * sizeof(float));
+            memcpy(dsts[q] + dstDescs[q].offset + (ptrdiff_t)i * dstDescs[q].stride, acc, (size_t)L * sizeof(real));
         }
     }
     return 1;
