@@ -44,6 +44,8 @@ def lib():
     L.ref_shape_name.restype = C.c_char_p
     L.ref_mesh_from_shape.restype = vp
     L.ref_mesh_from_shape.argtypes = [C.c_char_p]
+    L.ref_mesh_from_shape_tiled.restype = vp
+    L.ref_mesh_from_shape_tiled.argtypes = [C.c_char_p, C.c_int]
     L.ref_mesh_from_topology.restype = vp
     L.ref_mesh_from_topology.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp,
                                          C.c_int, vp, vp, C.c_int, vp, vp]
@@ -165,6 +167,11 @@ class Mesh:
     @classmethod
     def from_shape(cls, name: str) -> "Mesh":
         return cls(lib().ref_mesh_from_shape(name.encode()))
+
+    @classmethod
+    def from_shape_tiled(cls, name: str, copies: int) -> "Mesh":
+        """`copies` replicas of a regression shape side by side (creases, corners and UVs replicated)."""
+        return cls(lib().ref_mesh_from_shape_tiled(name.encode(), copies))
 
     @classmethod
     def from_topology(cls, scheme: str, num_verts: int, verts_per_face: np.ndarray, face_verts: np.ndarray,

@@ -42,6 +42,7 @@
 #include <far_utils.h>    // -I$(REF)/regression/common : TopologyRefinerFactory<Shape>, GetSdcOptions
 #include <shapes/all.h>   // -I$(REF)/regression        : the embedded regression OBJ strings
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -171,6 +172,52 @@ void *ref_mesh_from_shape(const char *name) {
     if (m->hasUV) m->uvs = shape->uvs;
     m->regFaceSize = (shape->scheme == kLoop) ? 3 : 4;
     delete shape;
+    if (!m->refiner) { delete m; return nullptr; }
+    return m;
+}
+
+// `copies` replicas of a regression shape laid out along x (vertices, UVs, faces, crease / corner tags replicated
+// with index offsets): a large adaptive mesh with extraordinary vertices, creases and UV seams for config 4.
+void *ref_mesh_from_shape_tiled(const char *name, int copies) {
+    auto &reg = shapeRegistry();
+    auto it = reg.find(name);
+    if (it == reg.end() || copies < 1) return nullptr;
+    Shape *base = Shape::parseObj(it->second);
+    if (!base) return nullptr;
+    Shape big;
+    big.scheme = base->scheme;
+    big.isLeftHanded = base->isLeftHanded;
+    const int nv = base->GetNumVertices(), nuv = (int)base->uvs.size() / 2;
+    float xmin = 1e30f, xmax = -1e30f;
+    for (int v = 0; v < nv; ++v) { xmin = std::min(xmin, base->verts[3 * v]); xmax = std::max(xmax, base->verts[3 * v]); }
+    const float pitch = (xmax - xmin) * 1.25f + 1.0f;
+    for (int c = 0; c < copies; ++c) {
+        for (int v = 0; v < nv; ++v) {
+            big.verts.push_back(base->verts[3 * v] + pitch * c);
+            big.verts.push_back(base->verts[3 * v + 1]);
+            big.verts.push_back(base->verts[3 * v + 2]);
+        }
+        big.uvs.insert(big.uvs.end(), base->uvs.begin(), base->uvs.end());
+        big.nvertsPerFace.insert(big.nvertsPerFace.end(), base->nvertsPerFace.begin(), base->nvertsPerFace.end());
+        for (size_t k = 0; k < base->faceverts.size(); ++k) big.faceverts.push_back(base->faceverts[k] + c * nv);
+        for (size_t k = 0; k < base->faceuvs.size(); ++k) big.faceuvs.push_back(base->faceuvs[k] + c * nuv);
+        for (size_t k = 0; k < base->tags.size(); ++k) {
+            Shape::tag const *t = base->tags[k];
+            const bool indexed = (t->name == "crease" || t->name == "corner");
+            if (!indexed && c > 0) continue;                     // global options once
+            Shape::tag *n = new Shape::tag(*t);
+            if (indexed) for (size_t q = 0; q < n->intargs.size(); ++q) n->intargs[q] += c * nv;
+            big.tags.push_back(n);
+        }
+    }
+    typedef Far::TopologyRefinerFactory<Shape> Factory;
+    RefMesh *m = new RefMesh;
+    m->refiner = Factory::Create(big, Factory::Options(GetSdcType(big), GetSdcOptions(big)));
+    m->positions = big.verts;
+    m->hasUV = big.HasUV();
+    if (m->hasUV) m->uvs = big.uvs;
+    m->regFaceSize = (big.scheme == kLoop) ? 3 : 4;
+    delete base;
     if (!m->refiner) { delete m; return nullptr; }
     return m;
 }

@@ -216,3 +216,92 @@ def test_limit_stencils_agree_with_patch_evaluation_on_gpu(torus_patches):
     got = a[:20000].cpu().numpy()
     for k in range(6):
         assert_close(got[:, 3 * k:3 * k + 3], exp[k][:20000], scl[k][:20000], f"limit {OUT6[k]}")
+
+
+@pytest.mark.slow
+def test_config4_adaptive_gregory_tables_ten_million_coords():
+    """BASELINE config 4 at full size with REAL Far tables: 60 tiled copies of regression shape catmark_car (98 520
+    control vertices, creases, extraordinary vertices), adaptive level 3 with Gregory-basis end caps -> 1.24 M REGULAR +
+    75 k GREGORY_BASIS patches, local-point stencils appended; 10 M random PatchCoords from Far::PatchMap::FindPatch;
+    P + 1st + 2nd derivatives (interleaved like glEvalLimit) and face-varying UVs; checked against the oracle on a sample."""
+    import time
+    from oracle import oracle, ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libosdref.so not present")
+    m = ref.Mesh.from_shape_tiled("catmark_car", 60)
+    ptab = m.patch_table(3, end_cap="gregory", fvar=True, fvar_legacy_linear=False, inf_sharp=True, legacy_sharp_corner=False)
+    st = m.stencil_table(intermediate_levels=True, patch_table=ptab)
+    fst = m.stencil_table(mode="fvar", intermediate_levels=True, patch_table=ptab)
+    assert set(int(x) for x in ptab.vertex.arrays["desc"]) == {6, 9}
+    n = 10_000_000
+    rng = np.random.default_rng(2024)
+    face = rng.integers(0, m.num_ptex_faces, n).astype(np.int32)
+    s, t = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+    coords = m.find_patches(ptab, face, s, t)
+    assert (coords["arrayIndex"] >= 0).all()
+
+    ncv, nst = st.num_control_verts, st.num_stencils
+    vb = osd.B200VertexBuffer.Create(3, ncv + nst)
+    vb.UpdateData(np.ascontiguousarray(m.positions), 0, ncv)
+    stbl = osd.B200StencilTable.Create(st)
+    pt = osd.B200PatchTable.Create(ptab)
+    pc = coords_dev(coords)
+    out = torch.empty((n, 18), device="cuda")
+    args = []
+    for k in range(6):
+        args += [out, D(3 * k, 3, 18)]
+
+    def frame():
+        assert osd.B200Evaluator.EvalStencils(vb, D(0, 3, 3), vb, D(ncv * 3, 3, 3), stbl)
+        assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)
+    frame()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        frame()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"CONFIG4 refine({nst} stencils)+EvalPatches(10M coords, 6 outputs, {len(ptab.vertex.params)} patches): "
+          f"{e0.elapsed_time(e1) / 5:.3f} ms/frame")
+
+    # oracle: refine on the CPU, evaluate a sample of the same coordinates
+    cpu_vb = np.zeros((ncv + nst, 3), np.float32)
+    cpu_vb[:ncv] = m.positions
+    assert oracle.eval_stencils(cpu_vb.reshape(-1), (0, 3, 3), [cpu_vb.reshape(-1)], [(ncv * 3, 3, 3)], st.sizes, st.offsets,
+                                st.indices, [st.weights])
+    pick = np.sort(rng.choice(n, 200_000, replace=False))
+    # make sure the sample contains Gregory patches
+    greg = np.nonzero(coords["arrayIndex"] == 1)[0][:20_000]
+    pick = np.unique(np.concatenate([pick, greg]))
+    sel = np.ascontiguousarray(coords[pick])
+    exp = oracle_patches(cpu_vb, (0, 3, 3), 3, sel, ptab.vertex, 6)
+    scl = oracle_patches(cpu_vb, (0, 3, 3), 3, sel, ptab.vertex, 6, abs_scale=True)
+    got = out[torch.from_numpy(pick).cuda()].cpu().numpy()
+    for k in range(6):
+        assert_close(got[:, 3 * k:3 * k + 3], exp[k], scl[k], f"config4 {OUT6[k]}")
+
+    # face-varying UVs through EvalPatchesFaceVarying(channel 0) on the refined fvar buffer
+    nfv, nfst = fst.num_control_verts, fst.num_stencils
+    fvb = osd.B200VertexBuffer.Create(2, nfv + nfst)
+    fvb.UpdateData(np.ascontiguousarray(m.uvs[:nfv]), 0, nfv)
+    ftbl = osd.B200StencilTable.Create(fst)
+    assert osd.B200Evaluator.EvalStencils(fvb, D(0, 2, 2), fvb, D(nfv * 2, 2, 2), ftbl)
+    uv = torch.empty((n, 2), device="cuda")
+    assert osd.B200Evaluator.EvalPatchesFaceVarying(fvb, D(0, 2, 2), uv, D(0, 2, 2), n, pc, pt, 0, None)
+    cpu_f = np.zeros((nfv + nfst, 2), np.float32)
+    cpu_f[:nfv] = m.uvs[:nfv]
+    oracle.eval_stencils(cpu_f.reshape(-1), (0, 2, 2), [cpu_f.reshape(-1)], [(nfv * 2, 2, 2)], fst.sizes, fst.offsets, fst.indices,
+                         [fst.weights])
+    fexp = oracle_patches(cpu_f, (0, 2, 2), 2, sel, ptab.fvar[0], 1)
+    fscl = oracle_patches(cpu_f, (0, 2, 2), 2, sel, ptab.fvar[0], 1, abs_scale=True)
+    assert_close(uv[torch.from_numpy(pick).cuda()].cpu().numpy(), fexp[0], fscl[0], "config4 fvar uv")
+
+    # sorted-vs-shuffled coordinate order gives identical bits per coordinate
+    order = np.argsort(coords["patchIndex"], kind="stable")
+    out2 = torch.empty((n, 18), device="cuda")
+    args2 = []
+    for k in range(6):
+        args2 += [out2, D(3 * k, 3, 18)]
+    assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args2, n, coords_dev(coords[order]), pt, None)
+    assert torch.equal(out2, out[torch.from_numpy(order).cuda()])
