@@ -223,6 +223,66 @@ def run_reference_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------- EvalPatches section --
+def bench_eval_patches(mesh, torch, osd, capi, log, n=10_000_000, iters=20):
+    """BASELINE config 4 shape of work on the synthetic torus: 10 M PatchCoords on 100 000 regular bicubic patches,
+    P + 1st + 2nd derivatives of xyz interleaved in one 18-float buffer (glEvalLimit layout), random and patch-sorted
+    coordinate order; device-resident, CUDA events.  Algorithmic bytes = n * (20 + 6*12).  Plus the reference's CPU
+    evaluators on the first 1 M of the same coordinates."""
+    from opensubdiv_b200 import synth
+    D = osd.BufferDescriptor
+    ptab = synth.torus_patch_table(mesh)
+    pt = osd.B200PatchTable.Create(ptab)
+    src = torch.from_numpy(frame_primvars(mesh, 1)[:, :3].copy()).cuda()
+    out = torch.empty((n, 18), device="cuda")
+    args = []
+    for k in range(6):
+        args += [out, D(3 * k, 3, 18)]
+    peak, _ = measured_peak()
+    res = {"workload": "torus_400x250_regular_patches_10M_coords_xyz_P+D1+D2", "coords": n, "patches": len(mesh.faces),
+           "algorithmic_bytes": n * 92}
+    coords_by_order = {}
+    for order, sort in (("random", False), ("sorted_by_patch", True)):
+        coords = synth.random_patch_coords(len(mesh.faces), n, seed=2024, sort_by_patch=sort)
+        coords_by_order[order] = coords
+        pc = torch.from_numpy(coords.view(np.uint8)).cuda()
+        for _ in range(3):
+            assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res[order] = {"ms": ms, "pts_per_s": n / (ms * 1e-3), "GBps": n * 92 / (ms * 1e-3) / 1e9,
+                      "frac_of_measured_hbm_peak": n * 92 / (ms * 1e-3) / 1e9 / peak}
+        del pc
+    try:
+        from oracle import ref as oref
+        if oref.available():
+            m = 1_000_000
+            sel = np.ascontiguousarray(coords_by_order["random"][:m])
+            tri = oref.PatchTriple(ptab.vertex.arrays, ptab.vertex.indices, ptab.vertex.params)
+            srcn = np.ascontiguousarray(frame_primvars(mesh, 1)[:, :3])
+            outs = [np.zeros((m, 3), np.float32) for _ in range(6)]
+            cpu = {}
+            for impl, thr in (("cpu", 1), ("omp", os.cpu_count() or 1)):
+                if impl == "omp":
+                    if not oref.lib().ref_has_openmp():
+                        continue
+                    oref.lib().ref_omp_set_threads(thr)
+                t0 = time.perf_counter()
+                oref.eval_patches(srcn.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 6, sel, tri, impl=impl)
+                dt = time.perf_counter() - t0
+                cpu[impl] = {"pts_per_s": m / dt, "cores": thr, "sample": f"{m} of the random coordinates, 1 call"}
+            res["cpu_baseline"] = cpu
+    except Exception as exc:
+        res["cpu_baseline"] = {"error": str(exc)}
+    return res
+
+
 # --------------------------------------------------------------------------------- B200 arm --
 def run_b200_arm(args):
     import faulthandler
@@ -432,6 +492,14 @@ def run_b200_arm(args):
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
 
+    # Second half of BASELINE.json's metric (limit pts/s, EvalPatches): reported in "eval_patches" at N=1.
+    patches = None
+    if world == 1 and not args.no_patches:
+        try:
+            patches = bench_eval_patches(mesh, torch, osd, capi, log)
+        except Exception as exc:
+            patches = {"error": str(exc)}
+
     if rank == 0:
         cpu = None
         if world == 1:                                          # the CPU baseline is a rank-0, N=1 report
@@ -468,6 +536,7 @@ def run_b200_arm(args):
                          "note": "per GPU; device time per step = one sell_kernel launch (+ the overlapped broadcast when N > 1)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "eval_patches": patches,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -487,6 +556,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant (0 = auto)")
+    ap.add_argument("--no-patches", action="store_true", help="skip the EvalPatches section of the report")
     ap.add_argument("--graph", action="store_true",
                     help="N > 1: replay a CUDA graph of two frames instead of the eager pipeline (verified at N=2 only)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

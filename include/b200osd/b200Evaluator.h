@@ -76,6 +76,22 @@ public:
         return evalTable(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, stencilTable, deviceContext);
     }
 
+    /// Extension (not in the reference): `numInstances` control-point sets sharing one topology refined in one pass.
+    /// Instance b uses srcDesc.offset + b*srcInstanceStride and dstDesc.offset + b*dstInstanceStride (in floats) --
+    /// the batched form of the per-instance loop in examples/glShareTopology/meshRefiner.h:68-88, bit-identical to it.
+    template <typename SRC_BUFFER, typename DST_BUFFER>
+    static bool EvalStencilsBatched(SRC_BUFFER *srcBuffer, BufferDescriptor const &srcDesc,
+                                    DST_BUFFER *dstBuffer, BufferDescriptor const &dstDesc,
+                                    B200StencilTable const *stencilTable, int numInstances,
+                                    long long srcInstanceStride, long long dstInstanceStride, void *deviceContext = NULL) {
+        int sd[3] = { srcDesc.offset, srcDesc.length, srcDesc.stride };
+        int dd[3] = { dstDesc.offset, dstDesc.length, dstDesc.stride };
+        return b200osd_stencil_table_eval_batched(stencilTable->GetHandle(), srcBuffer->BindCudaBuffer(), sd,
+                                                  dstBuffer->BindCudaBuffer(), dd, numInstances, srcInstanceStride,
+                                                  dstInstanceStride, 0, stencilTable->GetNumStencils(),
+                                                  B200StreamOf(deviceContext)) == B200OSD_OK;
+    }
+
     // raw device-pointer forms on reference-layout arrays
     static bool EvalStencils(const float *src, BufferDescriptor const &srcDesc,
                              float *dst, BufferDescriptor const &dstDesc,

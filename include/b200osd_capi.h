@@ -119,6 +119,15 @@ B200OSD_API int b200osd_stencil_table_eval(const b200osd_stencil_table *t,
         int nOut, float *const dsts[], const int dstDescs[][3],
         int start, int end, void *stream);
 
+/* Batched instances sharing one topology (reference pattern: one EvalStencils call per instance with
+ * shifted descriptors, examples/glShareTopology/meshRefiner.h:68-88).  Instance b (0 <= b < numInstances) uses
+ * srcDesc.offset + b*srcInstanceStride and dstDesc.offset + b*dstInstanceStride (strides in floats).  The table streams
+ * are read once per chunk of up to 4 instances.  Results are bit-identical to numInstances separate calls. */
+B200OSD_API int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *t,
+        const float *src, const int srcDesc[3], float *dst, const int dstDesc[3],
+        int numInstances, long long srcInstanceStride, long long dstInstanceStride,
+        int start, int end, void *stream);
+
 /* EvalStencils on plain reference-layout DEVICE arrays (raw CudaEvaluator::EvalStencils overloads,
  * osd/cudaEvaluator.h:171-178,284-295,449-466).  weights[k] for k < nOut. */
 B200OSD_API int b200osd_eval_stencils(

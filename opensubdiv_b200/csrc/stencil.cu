@@ -332,6 +332,26 @@ int launch_sell(const StencilIO &io, const SellTable &t, const SellPlan &p, cuda
     return check_launch("sell_kernel");
 }
 
+template <int LL, int B>
+void launch_batched_mode(const StencilIO &io, const SellTable &t, int mode, long long srcInst, long long dstInst, cudaStream_t st) {
+    const int slices = t.sliceEnd - t.sliceBegin;
+    const int grid = (slices + 7) / 8;
+    if (mode == SRC_VEC4) sell_kernel_batched<LL, B, SRC_VEC4><<<grid, 256, 0, st>>>(io, t, srcInst, dstInst);
+    else if (mode == SRC_VEC2) sell_kernel_batched<LL, B, SRC_VEC2><<<grid, 256, 0, st>>>(io, t, srcInst, dstInst);
+    else sell_kernel_batched<LL, B, SRC_SCALAR><<<grid, 256, 0, st>>>(io, t, srcInst, dstInst);
+}
+
+// chunk of B instances; returns false when (L, B) has no batched kernel
+template <int B>
+bool launch_batched(const StencilIO &io, const SellTable &t, int mode, long long srcInst, long long dstInst, cudaStream_t st) {
+    switch (io.L) {
+        case 3: launch_batched_mode<3, B>(io, t, mode, srcInst, dstInst, st); return true;
+        case 4: launch_batched_mode<4, B>(io, t, mode, srcInst, dstInst, st); return true;
+        case 6: launch_batched_mode<6, B>(io, t, mode, srcInst, dstInst, st); return true;
+        default: return false;
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------ C ABI ----
@@ -446,6 +466,63 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
     if (v == 8 || v == 12) plan.persistent = true;
     if (v == 11 || v == 12) plan.minBlocks = 8;
     return nOut == 1 ? launch_sell<1>(io, s, plan, st) : (nOut == 3 ? launch_sell<3>(io, s, plan, st) : launch_sell<6>(io, s, plan, st));
+}
+
+int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *tc, const float *src, const int srcDesc[3],
+                                       float *dst, const int dstDesc[3], int numInstances, long long srcInstanceStride,
+                                       long long dstInstanceStride, int start, int end, void *stream) {
+    b200osd_stencil_table *t = const_cast<b200osd_stencil_table *>(tc);
+    if (!t) { set_error("stencil table is NULL"); return B200OSD_ERR_INVALID; }
+    if (numInstances <= 0) return B200OSD_OK;
+    float *dsts[1] = { dst };
+    int dd[1][3] = { { dstDesc[0], dstDesc[1], dstDesc[2] } };
+    StencilIO io;
+    bool noop = false;
+    int rc = prepare_io(io, src, srcDesc, 1, dsts, dd, start, end, &noop);
+    if (rc || noop) return rc;
+    if (start < 0 || end > t->n) { set_error("row range [%d,%d) outside table of %d rows", start, end, t->n); return B200OSD_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool batchable = t->hasSell && (io.L == 3 || io.L == 4 || io.L == 6);
+    // alignment of every instance must allow the gather / store widths chosen for instance 0
+    int mode = src_mode(io);
+    if (mode == SRC_VEC4 && srcInstanceStride % 4 != 0) mode = (srcInstanceStride % 2 == 0) ? SRC_VEC2 : SRC_SCALAR;
+    if (mode == SRC_VEC2 && srcInstanceStride % 2 != 0) mode = SRC_SCALAR;
+    if (io.dstVec[0] == 4 && dstInstanceStride % 4 != 0) io.dstVec[0] = (dstInstanceStride % 2 == 0) ? 2 : 1;
+    if (io.dstVec[0] == 2 && dstInstanceStride % 2 != 0) io.dstVec[0] = 1;
+
+    SellTable s;
+    if (batchable) {
+        s.ipool = t->d_ipool;
+        for (int k = 0; k < kMaxOut; ++k) s.w4[k] = t->d_w4[k];
+        s.meta = t->d_meta;
+        s.rows = t->d_rows;
+        s.sliceBegin = t->windowSliceStart[start / t->window];
+        s.sliceEnd = t->windowSliceStart[(end + t->window - 1) / t->window];
+    }
+    int b = 0;
+    while (b < numInstances) {
+        StencilIO cur = io;
+        cur.src = io.src + (size_t)b * (size_t)srcInstanceStride;
+        cur.dst[0] = io.dst[0] + (size_t)b * (size_t)dstInstanceStride;
+        const int left = numInstances - b;
+        if (batchable && left >= 4) {
+            launch_batched<4>(cur, s, mode, srcInstanceStride, dstInstanceStride, st);
+            rc = check_launch("sell_kernel_batched");
+            b += 4;
+        } else if (batchable && left >= 2) {
+            launch_batched<2>(cur, s, mode, srcInstanceStride, dstInstanceStride, st);
+            rc = check_launch("sell_kernel_batched");
+            b += 2;
+        } else {
+            // single instance (or no batched kernel for this length): the ordinary path
+            int sd[3] = { srcDesc[0] + (int)((long long)b * srcInstanceStride), srcDesc[1], srcDesc[2] };
+            int d1[1][3] = { { dstDesc[0] + (int)((long long)b * dstInstanceStride), dstDesc[1], dstDesc[2] } };
+            rc = b200osd_stencil_table_eval(tc, src, sd, 1, dsts, d1, start, end, stream);
+            b += 1;
+        }
+        if (rc) return rc;
+    }
+    return B200OSD_OK;
 }
 
 int b200osd_eval_stencils(const float *src, const int srcDesc[3], int nOut, float *const dsts[],

@@ -304,6 +304,49 @@ __global__ void __launch_bounds__(256, MINB) sell_kernel_persist(StencilIO io, S
     }
 }
 
+// Batched instances sharing one topology (the reference's pattern is one EvalStencils call per instance
+// with shifted descriptors, examples/glShareTopology/meshRefiner.h:68-88).  Instance b reads its control vertices at
+// src + b*srcInst and writes its rows at dst + b*dstInst; the index / weight streams of a slice are read ONCE for the B
+// instances of a chunk, so table traffic per instance drops B-fold.  Value stencils only (K = 1); per instance the
+// arithmetic (order, FMA) is identical to sell_kernel, so results are bit-identical to per-instance calls.
+template <int L, int B, int SRCMODE>
+__global__ void __launch_bounds__(256) sell_kernel_batched(StencilIO io, SellTable t, long long srcInst, long long dstInst) {
+    const int lane = threadIdx.x & 31;
+    const int slice = t.sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (slice >= t.sliceEnd) return;
+    const int4 m = t.meta[slice];
+    const int row = t.rows[(size_t)slice * kSliceRows + lane];
+    const size_t base = (size_t)(unsigned)m.x + lane;
+    const uint2 *slicePool = t.ipool + (size_t)(unsigned)m.w;
+    const float4 *wp = t.w4[0] + base;
+    float acc[B][L];
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+        for (int c = 0; c < L; ++c) acc[b][c] = 0.0f;
+    for (int g = 0; g < m.y; ++g) {
+        const int4 id = load_index_group(slicePool, g * kSliceRows + lane, m.z);
+        const float4 w = ld_stream_f4(wp + (size_t)g * kSliceRows);
+        const int ids[4] = { id.x, id.y, id.z, id.w };
+        const float ws[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                float v[L];
+                load_vertex<L, SRCMODE>(io.src + (size_t)b * (size_t)srcInst, io.srcStride, ids[q], v);
+#pragma unroll
+                for (int c = 0; c < L; ++c) acc[b][c] = fmaf(ws[q], v[c], acc[b][c]);
+            }
+        }
+    }
+    if (row >= io.start && row < io.end && io.dst[0]) {
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+            store_vertex<L>(io.dst[0] + (size_t)b * (size_t)dstInst + (size_t)row * (size_t)io.dstStride[0], acc[b], io.dstVec[0]);
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(256) sell_kernel_anyL(StencilIO io, SellTable t) {
     const int lane = threadIdx.x & 31;

@@ -295,6 +295,21 @@ class B200Evaluator:
         return capi.check(rc, "B200Evaluator::EvalStencils")
 
     @staticmethod
+    def EvalStencilsBatched(srcBuffer, srcDesc, dstBuffer, dstDesc, stencilTable, numInstances: int,
+                            srcInstanceStride: int, dstInstanceStride: Optional[int] = None, deviceContext=None,
+                            start: int = 0, end: Optional[int] = None) -> bool:
+        """numInstances control-point sets refined through ONE table in one pass: instance b uses srcDesc.offset +
+        b*srcInstanceStride / dstDesc.offset + b*dstInstanceStride (floats).  Equivalent to -- and bit-identical with --
+        the reference's one-call-per-instance pattern (examples/glShareTopology/meshRefiner.h:68-88)."""
+        sd, dd = _desc(srcDesc).as_c(), _desc(dstDesc).as_c()
+        end = stencilTable.GetNumStencils() if end is None else end
+        dstInstanceStride = srcInstanceStride if dstInstanceStride is None else dstInstanceStride
+        rc = capi.lib().b200osd_stencil_table_eval_batched(stencilTable._h, _dev_ptr(srcBuffer), sd, _dev_ptr(dstBuffer), dd,
+                                                           numInstances, srcInstanceStride, dstInstanceStride, start, end,
+                                                           _stream_ptr(deviceContext))
+        return capi.check(rc, "B200Evaluator::EvalStencilsBatched")
+
+    @staticmethod
     def EvalStencilsRaw(src, srcDesc, outs: Sequence, sizes, offsets, indices, weights: Sequence, start: int, end: int,
                         deviceContext=None) -> bool:
         """Raw-pointer overloads on reference-layout device arrays (osd/cudaEvaluator.h:171-178,284-295,449-466).

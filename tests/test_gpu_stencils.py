@@ -196,6 +196,38 @@ def test_wide_index_span_falls_back_to_32bit_indices():
         assert_close(out.cpu().numpy(), exp, scale, f"wide span variant {v}")
 
 
+@pytest.mark.parametrize("L,num_instances", [(3, 1), (3, 2), (3, 7), (6, 5), (4, 4), (5, 3)])
+def test_batched_instances_equal_per_instance_calls(L, num_instances):
+    """One topology, many control-point sets in ONE buffer at a constant vertex pitch (examples/glShareTopology layout:
+    each instance = [its control vertices | its refined vertices]); the batched call must reproduce the reference's
+    one-EvalStencils-per-instance loop bit for bit."""
+    d = golden("stencils_catmark_car")
+    t = table_from(d, "t_")
+    ncv, n = t.num_control_verts, t.num_stencils
+    pitch = (ncv + n) * L                                    # floats between instances
+    rng = np.random.default_rng(L * 10 + num_instances)
+    host = np.zeros((num_instances, ncv + n, L), np.float32)
+    host[:, :ncv] = rng.standard_normal((num_instances, ncv, L)).astype(np.float32)
+    tbl = osd.B200StencilTable.Create(t)
+    a = dev(host.reshape(-1))
+    b = dev(host.reshape(-1))
+    for inst in range(num_instances):                        # reference pattern: shifted descriptors, one call each
+        assert osd.B200Evaluator.EvalStencils(a, D(inst * pitch, L, L), a, D(inst * pitch + ncv * L, L, L), tbl)
+    assert osd.B200Evaluator.EvalStencilsBatched(b, D(0, L, L), b, D(ncv * L, L, L), tbl, num_instances, pitch)
+    assert torch.equal(a, b)
+    exp = oracle_stencils(host[-1, :ncv], (0, L, L), n, L, t, 1)[0]
+    scale = oracle_stencils(host[-1, :ncv], (0, L, L), n, L, t, 1, abs_scale=True)[0]
+    got = b.view(num_instances, ncv + n, L)[-1, ncv:].cpu().numpy()
+    assert_close(got, exp, scale, f"batched L={L} x{num_instances}")
+    # row sub-range + errors behave like the single-instance call
+    c = dev(host.reshape(-1))
+    assert osd.B200Evaluator.EvalStencilsBatched(c, D(0, L, L), c, D(ncv * L, L, L), tbl, num_instances, pitch, start=100, end=3000)
+    cv = c.view(num_instances, ncv + n, L)
+    assert torch.equal(cv[:, ncv + 100:ncv + 3000], b.view(num_instances, ncv + n, L)[:, ncv + 100:ncv + 3000])
+    assert (cv[:, ncv:ncv + 100] == 0).all() and (cv[:, ncv + 3000:] == 0).all()
+    assert not osd.B200Evaluator.EvalStencilsBatched(c, D(0, L, L), c, D(0, L + 1, L + 1), tbl, num_instances, pitch)
+
+
 @pytest.fixture(scope="module")
 def config2():
     """BASELINE config 2 at full size: Catmark torus 400x250 (100k control verts), uniform level 3, last level:
@@ -310,6 +342,27 @@ def test_config2_size_independent_properties(config2):
     assert osd.B200Evaluator.EvalStencilsRaw(x, D(0, 6, 6), [(raw, D(0, 6, 6))], tbl.GetSizesBuffer(), tbl.GetOffsetsBuffer(),
                                              tbl.GetIndicesBuffer(), [tbl.GetWeightsBuffer()], 0, n)
     assert (raw - ex).abs().max().item() <= 2e-6
+    # batched instances: 8 control-point sets through one pass over the table
+    B, L3 = 8, 3
+    xs = torch.randn((B, ncv, L3), device="cuda", generator=g)
+    outb = torch.empty((B, n, L3), device="cuda")
+    one = torch.empty((n, L3), device="cuda")
+    assert osd.B200Evaluator.EvalStencilsBatched(xs, D(0, L3, L3), outb, D(0, L3, L3), tbl, B, ncv * L3, n * L3)
+    assert osd.B200Evaluator.EvalStencils(xs[5], D(0, L3, L3), one, D(0, L3, L3), tbl)
+    assert torch.equal(outb[5], one)
+    for fn, label in ((lambda: osd.B200Evaluator.EvalStencilsBatched(xs, D(0, L3, L3), outb, D(0, L3, L3), tbl, B, ncv * L3, n * L3), "batched x8"),
+                      (lambda: [osd.B200Evaluator.EvalStencils(xs[i], D(0, L3, L3), outb[i], D(0, L3, L3), tbl) for i in range(B)], "8 calls")):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"BATCHED-INSTANCES cfg2 L=3 {label}: {e0.elapsed_time(e1) / 20:.4f} ms for {B} instances "
+              f"({B * n / (e0.elapsed_time(e1) / 20 * 1e-3) / 1e9:.1f} G verts/s)")
     # independent cross-check of the whole 6.4 M-row result: torch sparse CSR matmul of the same table
     crow = torch.from_numpy(np.concatenate([table.offsets.astype(np.int64), [table.num_elements]])).cuda()
     A = torch.sparse_csr_tensor(crow, torch.from_numpy(table.indices.astype(np.int64)).cuda(),
