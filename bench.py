@@ -280,7 +280,53 @@ def bench_eval_patches(mesh, torch, osd, capi, log, n=10_000_000, iters=20):
             res["cpu_baseline"] = cpu
     except Exception as exc:
         res["cpu_baseline"] = {"error": str(exc)}
+    res["find_patches"] = bench_find_patches(torch, osd, n, iters)
     return res
+
+
+def bench_find_patches(torch, osd, n, iters):
+    """SURVEY 8f-2: (ptexFace, s, t) -> Osd::PatchCoord on the device (B200PatchMap) against Far::PatchMap::FindPatch on
+    one host core (its API is one sample per call).  Table: 60 tiled copies of regression shape catmark_car, adaptive
+    level 3, Gregory end caps (1.31 M patches, depth 0-3), built by the reference compiled under oracle/_ref.
+    Algorithmic bytes = n * (12 in + 20 out); the quadtree (a few MB) stays in L2."""
+    try:
+        from oracle import ref as oref
+        if not oref.available():
+            return {"skipped": "oracle/_ref/libosdref.so not present (the adaptive table comes from the reference's factories)"}
+        m = oref.Mesh.from_shape_tiled("catmark_car", 60)
+        ptab = m.patch_table(3, end_cap="gregory", fvar=False, inf_sharp=True, legacy_sharp_corner=False)
+        pm = osd.B200PatchMap.Create(ptab)
+        rng = np.random.default_rng(2024)
+        face = rng.integers(0, m.num_ptex_faces, n).astype(np.int32)
+        s, t = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+        df, ds, dt_ = (torch.from_numpy(x).cuda() for x in (face, s, t))
+        pc = torch.empty(n * 5, dtype=torch.int32, device="cuda")
+        found = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for _ in range(3):
+            assert pm.FindPatches(n, df, ds, dt_, pc, found)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            pm.FindPatches(n, df, ds, dt_, pc, found)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        peak, _ = measured_peak()
+        k = 2_000_000
+        t0 = time.perf_counter()
+        want = m.find_patches(ptab, face[:k], s[:k], t[:k])
+        cpu_dt = time.perf_counter() - t0
+        same = bool(np.array_equal(pc[:k * 5].cpu().numpy(), np.ascontiguousarray(want).view(np.int32)))
+        return {"workload": "catmark_car_x60_adaptive_L3_gregory_10M_samples", "samples": n, "patches": len(ptab.vertex.params),
+                "max_depth": pm.GetMaxDepth(), "tree_nodes": pm.GetNumNodes(), "found": int(found.item()),
+                "ms": ms, "samples_per_s": n / (ms * 1e-3), "algorithmic_bytes": n * 32,
+                "GBps": n * 32 / (ms * 1e-3) / 1e9, "frac_of_measured_hbm_peak": n * 32 / (ms * 1e-3) / 1e9 / peak,
+                "bit_identical_to_reference_on_sample": same,
+                "cpu_baseline": {"samples_per_s": k / cpu_dt, "cores": 1, "kind": "reference",
+                                 "sample": f"Far::PatchMap::FindPatch on the first {k} samples"}}
+    except Exception as exc:
+        return {"error": str(exc)}
 
 
 # --------------------------------------------------------------------------------- B200 arm --

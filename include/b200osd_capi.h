@@ -67,6 +67,7 @@ typedef struct b200osd_patch_param { unsigned int field0, field1; float sharpnes
 
 typedef struct b200osd_stencil_table b200osd_stencil_table;
 typedef struct b200osd_patch_table   b200osd_patch_table;
+typedef struct b200osd_patch_map     b200osd_patch_map;
 typedef struct b200osd_vertex_buffer b200osd_vertex_buffer;
 
 /* ---- library -------------------------------------------------------------------------------- */
@@ -168,6 +169,25 @@ B200OSD_API int b200osd_patch_table_eval(const b200osd_patch_table *t, int which
         const float *src, const int srcDesc[3],
         int nOut, float *const dsts[], const int dstDescs[][3],
         int numPatchCoords, const b200osd_patch_coord *patchCoords, void *stream);
+
+/* ---- patch map (Far::PatchMap, far/patchMap.h:48-217) ---------------------------
+ * Locates samples given as (ptex face, s, t) in the patches of a table and writes Osd::PatchCoord records
+ * (osd/types.h:53-54) ready for EvalPatches -- the reference does this one sample at a time on the host
+ * (examples/glEvalLimit/particles.cpp:91-115,392-394).  The map is built once per topology, on the host, from the
+ * VERTEX PatchArray[] and PatchParam[] (as flattened by Osd::CpuPatchTable) and lives in device memory.
+ * patchesAreTriangular mirrors far/patchMap.cpp:93-94 (the varying descriptor has 3 control vertices: Loop tables). */
+B200OSD_API b200osd_patch_map *b200osd_patch_map_create(int numArrays, const b200osd_patch_array *vertexArrays,
+        int numPatches, const b200osd_patch_param *patchParams, int patchesAreTriangular);
+B200OSD_API void b200osd_patch_map_destroy(b200osd_patch_map *m);
+/* info = {minPatchFace, maxPatchFace, maxDepth, triangular, numNodes, numHandles} */
+B200OSD_API int  b200osd_patch_map_info(const b200osd_patch_map *m, int info[6]);
+/* DEVICE arrays in, DEVICE records out; strides in elements (1,1,1 for three packed arrays; 3,3,3 with the pointers
+ * offset by one word each for {int face; float s; float t} records).  A sample that hits no patch (a hole, or a
+ * face outside the map: FindPatch returns NULL) gets handle.arrayIndex = -1 and keeps its (s,t); EvalPatches in this
+ * library leaves the outputs of such records untouched.  numFound (device int, may be NULL) receives the hit count. */
+B200OSD_API int  b200osd_patch_map_find(const b200osd_patch_map *m, int numSamples,
+        const int *ptexFace, int faceStride, const float *s, int sStride, const float *t, int tStride,
+        b200osd_patch_coord *outCoords, int *numFound, void *stream);
 
 /* ---- tuning / introspection (used by bench.py and the tests; not needed by clients) ---------- */
 /* Selects the stencil kernel variant used by b200osd_stencil_table_eval: 0 = auto. */

@@ -15,13 +15,13 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libb200osd.so")
-SOURCES = ["core.cu", "stencil.cu", "patch.cu"]
-HEADERS = ["common.cuh", "stencil_kernels.cuh", "patch_kernels.cuh", os.path.join("..", "..", "include", "b200osd_capi.h")]
+SOURCES = ["core.cu", "stencil.cu", "patch.cu", "patchmap.cu"]
+HEADERS = ["common.cuh", "stencil_kernels.cuh", "patch_kernels.cuh", "patchmap.cuh", os.path.join("..", "..", "include", "b200osd_capi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xptxas=-v",
+    "-Xptxas=-v", "--threads", "4",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
     "-shared",
 ]

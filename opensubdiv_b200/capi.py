@@ -29,6 +29,7 @@ SYMBOLS = [
     "b200osd_patch_table_num_fvar_channels", "b200osd_patch_table_buffer", "b200osd_patch_table_count",
     "b200osd_eval_patches", "b200osd_patch_table_eval", "b200osd_set_patch_variant", "b200osd_get_patch_variant",
     "b200osd_set_stencil_variant", "b200osd_get_stencil_variant",
+    "b200osd_patch_map_create", "b200osd_patch_map_destroy", "b200osd_patch_map_info", "b200osd_patch_map_find",
 ]
 
 
@@ -87,6 +88,11 @@ def lib():
     L.b200osd_eval_patches.argtypes = [vp, vp, i, vp, vp, i, vp, vp, vp, vp, vp]
     L.b200osd_patch_table_eval.argtypes = [vp, i, vp, vp, i, vp, vp, i, vp, vp]
     L.b200osd_set_patch_variant.argtypes = [i]
+    L.b200osd_patch_map_create.restype = vp
+    L.b200osd_patch_map_create.argtypes = [i, vp, i, vp, i]
+    L.b200osd_patch_map_destroy.argtypes = [vp]
+    L.b200osd_patch_map_info.argtypes = [vp, vp]
+    L.b200osd_patch_map_find.argtypes = [vp, i, vp, i, vp, i, vp, i, vp, vp, vp]
     L.b200osd_set_stencil_variant.argtypes = [i]
     _lib = L
     return L

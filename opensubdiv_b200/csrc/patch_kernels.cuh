@@ -210,7 +210,7 @@ B200_HD void store_outputs(const PatchIO &io, int i, bool live, const float (&ou
     __shared__ float stage[kPatchBlock / 32][32 * LT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = i - lane;
-    const int nlive = min(32, io.n - i0);
+    const unsigned livemask = __ballot_sync(0xffffffffu, live);   // lanes past the end or holding a miss write nothing
     float *st = stage[warp];
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) {
@@ -226,10 +226,9 @@ B200_HD void store_outputs(const PatchIO &io, int i, bool live, const float (&ou
         for (int q = 0; q < LT; ++q) {
             const int e = q * 32 + lane;
             const int ci = e / LT, c = e - ci * LT;
-            if (ci < nlive) st_stream_f1(base + (size_t)ci * stride + c, st[e]);
+            if ((livemask >> ci) & 1u) st_stream_f1(base + (size_t)ci * stride + c, st[e]);
         }
     }
-    (void)live;
 #else
     if (!live) return;
 #pragma unroll
@@ -548,6 +547,9 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
         patchIndex = ld_coord_word(cw + 1);
         s = int_as_float(ld_coord_word(cw + 3));
         t = int_as_float(ld_coord_word(cw + 4));
+        // arrayIndex < 0 marks a sample that hit no patch (b200osd_patch_map_find writes it for holes, where
+        // Far::PatchMap::FindPatch returns NULL and the reference's callers skip the sample): its outputs stay untouched
+        live = arrayIndex >= 0;
     }
     if (live) {
 

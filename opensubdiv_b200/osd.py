@@ -256,6 +256,60 @@ class B200PatchTable:
     def GetFVarPatchParamBuffer(self, fvarChannel: int = 0): return self._buf(2 + fvarChannel, 2)
 
 
+class B200PatchMap:
+    """Device-resident Far::PatchMap (far/patchMap.h:48-217): locates (ptexFace, s, t) samples in the patches of a
+    table and emits Osd::PatchCoord records on the device, ready for EvalPatches.  The reference answers one sample
+    per FindPatch call on the host (examples/glEvalLimit/particles.cpp:91-115,392-394); here a whole batch is one
+    kernel launch and never leaves HBM."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def Create(cls, table, patchesAreTriangular: Optional[bool] = None) -> Optional["B200PatchMap"]:
+        """`table`: the same flattened patch-table object B200PatchTable.Create takes (.vertex.arrays/.params, and
+        .varying for the triangular test of far/patchMap.cpp:93-94 unless patchesAreTriangular is given)."""
+        a = np.ascontiguousarray(table.vertex.arrays, dtype=PATCH_ARRAY_DTYPE)
+        pr = np.ascontiguousarray(table.vertex.params, dtype=PATCH_PARAM_DTYPE)
+        if patchesAreTriangular is None:
+            var = getattr(table, "varying", None)
+            patchesAreTriangular = bool(var is not None and len(var.arrays) and int(var.arrays["desc"][0]) == 4)
+        h = capi.lib().b200osd_patch_map_create(len(a), a.ctypes.data if len(a) else None, len(pr),
+                                                pr.ctypes.data if len(pr) else None, int(patchesAreTriangular))
+        if not h:
+            raise capi.B200OsdError("B200PatchMap::Create failed: " + capi.last_error())
+        return cls(h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b200osd_patch_map_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _info(self):
+        info = (C.c_int * 6)()
+        capi.check(capi.lib().b200osd_patch_map_info(self._h, info), "B200PatchMap::info")
+        return list(info)
+
+    def GetMinPatchFace(self) -> int: return self._info()[0]
+    def GetMaxPatchFace(self) -> int: return self._info()[1]
+    def GetMaxDepth(self) -> int: return self._info()[2]
+    def GetNumNodes(self) -> int: return self._info()[4]
+    def GetNumPatches(self) -> int: return self._info()[5]
+
+    def FindPatches(self, numSamples: int, ptexFace, s, t, patchCoords, numFound=None, strides=(1, 1, 1),
+                    deviceContext=None) -> bool:
+        """ptexFace (int32), s, t (float32): DEVICE arrays with element strides `strides`; patchCoords: DEVICE buffer of
+        numSamples 20-byte Osd::PatchCoord records.  A sample outside every patch (FindPatch == NULL) gets
+        handle.arrayIndex = -1; B200Evaluator.EvalPatches* leaves its outputs untouched.  numFound: optional device int."""
+        rc = capi.lib().b200osd_patch_map_find(self._h, numSamples, _dev_ptr(ptexFace), strides[0], _dev_ptr(s), strides[1],
+                                               _dev_ptr(t), strides[2], _dev_ptr(patchCoords), _dev_ptr(numFound),
+                                               _stream_ptr(deviceContext))
+        return capi.check(rc, "B200PatchMap::FindPatches")
+
+
 def _is_desc(d) -> bool:
     return isinstance(d, BufferDescriptor) or (isinstance(d, (tuple, list)) and len(d) == 3
                                                and all(isinstance(v, (int, np.integer)) for v in d))

@@ -123,6 +123,11 @@ std::map<std::string, ShapeDesc> &shapeRegistry() {
         REG(catmark_car, kCatmark);
         REG(catmark_rook, kCatmark);
         REG(catmark_chaikin0, kCatmark);
+        REG(catmark_hole_test1, kCatmark);
+        REG(catmark_hole_test2, kCatmark);
+        REG(catmark_hole_test3, kCatmark);
+        REG(catmark_hole_test4, kCatmark);
+        REG(catmark_square_hedit4, kCatmark);
         REG(loop_cube, kLoop);
         REG(loop_cube_creases0, kLoop);
         REG(loop_cube_creases1, kLoop);

@@ -19,6 +19,7 @@
 
 #include <b200osd/b200Evaluator.h>
 #include <b200osd/b200PatchTable.h>
+#include <b200osd/b200PatchMap.h>
 #include <b200osd/b200StencilTable.h>
 #include <b200osd/b200VertexBuffer.h>
 
@@ -28,6 +29,7 @@
 #include <shapes/loop_icosahedron.h>
 
 #include <cmath>
+#include <cstring>
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -147,14 +149,40 @@ static int meshCase(const char *name, std::string const &str, Scheme scheme, int
         std::mt19937 rng(2024);
         std::uniform_real_distribution<float> uni(0.0f, 1.0f);
         std::vector<Osd::PatchCoord> coords;
+        std::vector<Osd::B200PatchMap::Sample> samples;
+        std::vector<Osd::PatchCoord> located;           // one record per sample, arrayIndex = -1 where FindPatch is NULL
         for (int i = 0; i < 20000; ++i) {
-            int face = (int)(rng() % ptex.GetNumFaces());
+            int face = (int)(rng() % (ptex.GetNumFaces() + 2)) - 1;          // includes faces outside the table
             float s = uni(rng), t = uni(rng);
+            if (i % 7 == 0) s = (float)(rng() % 17) / 16.0f;                 // exactly on sub-patch boundaries
+            if (i % 11 == 0) t = (float)(rng() % 17) / 16.0f;
             if (scheme == kLoop && s + t >= 1.0f) { s = 1.0f - s; t = 1.0f - t; }
             Far::PatchTable::PatchHandle const *h = patchMap.FindPatch(face, s, t);
             if (h) coords.push_back(Osd::PatchCoord(*h, s, t));
+            Osd::B200PatchMap::Sample smp = { face, s, t };
+            samples.push_back(smp);
+            Osd::PatchCoord rec;
+            if (h) rec = Osd::PatchCoord(*h, s, t); else { rec.handle.arrayIndex = -1; rec.handle.patchIndex = 0; rec.handle.vertIndex = 0; rec.s = s; rec.t = t; }
+            located.push_back(rec);
         }
         int n = (int)coords.size();
+        {
+            // Far::PatchMap::FindPatch per sample on the host  vs  B200PatchMap::FindPatches, one launch on the device
+            int ns = (int)samples.size();
+            Osd::B200PatchMap *gpuMap = Osd::B200PatchMap::Create(farPt);
+            Osd::B200VertexBuffer *gpuSamples = Osd::B200VertexBuffer::Create(3, ns);
+            Osd::B200VertexBuffer *gpuLocated = Osd::B200VertexBuffer::Create(5, ns);
+            gpuSamples->UpdateData((const float *)&samples[0], 0, ns);
+            bool ok = gpuMap && gpuMap->FindPatches(ns, gpuSamples, gpuLocated);
+            std::vector<Osd::PatchCoord> back((size_t)ns);
+            gpuLocated->ReadData((float *)&back[0], 0, ns);
+            Osd::B200Evaluator::Synchronize();
+            int bad = ok ? 0 : ns;
+            for (int i = 0; ok && i < ns; ++i) bad += std::memcmp(&back[i], &located[i], sizeof(Osd::PatchCoord)) != 0;
+            std::snprintf(label, sizeof(label), "B200PatchMap::FindPatches %s (%d samples, %d hits)", name, ns, n);
+            report(label, (double)bad, 0.0);
+            delete gpuMap; delete gpuSamples; delete gpuLocated;
+        }
         Osd::CpuVertexBuffer *cpuCoords = Osd::CpuVertexBuffer::Create(5, n);
         Osd::B200VertexBuffer *gpuCoords = Osd::B200VertexBuffer::Create(5, n);
         cpuCoords->UpdateData((const float *)&coords[0], 0, n);

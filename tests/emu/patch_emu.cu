@@ -76,3 +76,34 @@ int emu_eval_patches(const float *src, const int srcDesc[3], int nOut, float *co
     }
     return 0;
 }
+
+// ---- patch map: the library's host builder + the kernel's descent, run on the CPU (test-only) --------------------
+#include "../../opensubdiv_b200/csrc/patchmap.cuh"
+
+extern "C" __attribute__((visibility("default")))
+int emu_patch_map_find(int numArrays, const b200osd_patch_array *arrays, int numPatches, const b200osd_patch_param *params,
+                       int triangular, int n, const int *face, const float *s, const float *t,
+                       b200osd_patch_coord *out, int info[6]) {
+    PatchMapHost host;
+    const int rc = build_patch_map(numArrays, arrays, numPatches, params, triangular, &host);
+    if (rc) return rc;
+    PatchMapView m;
+    m.nodes = host.nodes.data();
+    m.handles = host.handles.data();
+    m.minFace = host.minFace; m.maxFace = host.maxFace; m.maxDepth = host.maxDepth; m.triangular = host.triangular;
+    if (info) {
+        info[0] = m.minFace; info[1] = m.maxFace; info[2] = m.maxDepth; info[3] = m.triangular;
+        info[4] = (int)host.nodes.size(); info[5] = (int)host.handles.size();
+    }
+    int hits = 0;
+    for (int i = 0; i < n; ++i) {
+        const int p = patch_map_find(m, face[i], s[i], t[i]);
+        b200osd_patch_coord c;
+        std::memset(&c, 0, sizeof(c));
+        c.s = s[i]; c.t = t[i];
+        if (p >= 0) { c.arrayIndex = host.handles[p].x; c.patchIndex = p; c.vertIndex = host.handles[p].y; ++hits; }
+        else c.arrayIndex = -1;
+        out[i] = c;
+    }
+    return hits;
+}

@@ -203,8 +203,57 @@ def make_patches():
         save("patches_" + shape, **d)
 
 
+PATCH_MAP_CASES = (
+    # shape, isolation level, end cap
+    ("catmark_cube", 4, "gregory"),
+    ("catmark_car", 2, "gregory"),
+    ("catmark_nonquads", 3, "gregory"),          # non-quad base faces: ptex sub-faces, root depth 1
+    ("catmark_hole_test2", 3, "gregory"),        # hole faces: FindPatch returns NULL
+    ("catmark_pole64", 5, "bspline"),
+    ("catmark_edgecorner", 6, "gregory"),
+    ("loop_icosahedron", 4, "gregory"),          # triangular domain with rotated sub-triangles
+    ("loop_cube_creases0", 3, "gregory"),
+    ("loop_triangle_edgecorner", 5, "gregory"),
+)
+
+
+def patch_map_samples(mesh, n, seed):
+    """(face, s, t) locations stressing the quadtree: random interior points, every dyadic boundary down to 2^-7,
+    exact 0 / 1, points on the diagonals of triangular domains, and faces outside the table."""
+    rng = np.random.default_rng(seed)
+    nf = mesh.num_ptex_faces
+    face = rng.integers(-2, nf + 2, n).astype(np.int32)
+    s = rng.random(n, dtype=np.float32)
+    t = rng.random(n, dtype=np.float32)
+    k = rng.integers(0, 129, n)
+    snap_s, snap_t = rng.random(n) < 0.3, rng.random(n) < 0.3
+    s = np.where(snap_s, (k / 128.0), s).astype(np.float32)
+    t = np.where(snap_t, (rng.integers(0, 129, n) / 128.0), t).astype(np.float32)
+    if mesh.reg_face_size == 3:
+        flip = (s + t) > 1.0
+        s, t = np.where(flip, 1.0 - s, s).astype(np.float32), np.where(flip, 1.0 - t, t).astype(np.float32)
+        diag = rng.random(n) < 0.2                       # exactly on a sub-triangle diagonal s + t = j / 2^m
+        m = 2.0 ** rng.integers(0, 6, n)
+        j = np.floor(rng.random(n) * m) + 1
+        td = (j / m - s).astype(np.float32)
+        ok = diag & (td >= 0) & (td <= 1)
+        t = np.where(ok, td, t).astype(np.float32)
+    return face, s, t
+
+
+def make_patch_maps():
+    for shape, level, endcap in PATCH_MAP_CASES:
+        m = ref.Mesh.from_shape(shape)
+        pt = m.patch_table(level, end_cap=endcap, fvar=False, inf_sharp=True, legacy_sharp_corner=False, refine_first=True)
+        face, s, t = patch_map_samples(m, 6000, 3)
+        pc = m.find_patches(pt, face, s, t)
+        save("patchmap_" + shape, arrays=pt.vertex.arrays, params=pt.vertex.params,
+             triangular=np.int32(m.reg_face_size == 3), num_ptex_faces=np.int32(m.num_ptex_faces),
+             face=face, s=s, t=t, coords=pc)
+
+
 if __name__ == "__main__":
-    make_cube()
-    make_stencil_shapes()
-    make_limit()
-    make_patches()
+    groups = {"cube": make_cube, "stencils": make_stencil_shapes, "limit": make_limit, "patches": make_patches,
+              "patchmap": make_patch_maps}
+    for g in (sys.argv[1:] or list(groups)):
+        groups[g]()

@@ -245,7 +245,24 @@ def test_config4_adaptive_gregory_tables_ten_million_coords():
     vb.UpdateData(np.ascontiguousarray(m.positions), 0, ncv)
     stbl = osd.B200StencilTable.Create(st)
     pt = osd.B200PatchTable.Create(ptab)
-    pc = coords_dev(coords)
+
+    # the same 10 M samples located on the device -- every record bit-identical to Far::PatchMap::FindPatch
+    pm = osd.B200PatchMap.Create(ptab)
+    dface, ds, dt = dev(face), dev(s), dev(t)
+    pc = torch.zeros(n * 5, dtype=torch.int32, device="cuda")
+    found = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert pm.FindPatches(n, dface, ds, dt, pc, found)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(5):
+        pm.FindPatches(n, dface, ds, dt, pc, found)
+    f1.record()
+    torch.cuda.synchronize()
+    print(f"CONFIG4 FindPatches(10M samples, depth<={pm.GetMaxDepth()}, {pm.GetNumNodes()} nodes): "
+          f"{f0.elapsed_time(f1) / 5:.3f} ms")
+    assert int(found.item()) == n
+    assert np.array_equal(pc.cpu().numpy(), np.ascontiguousarray(coords).view(np.int32))
     out = torch.empty((n, 18), device="cuda")
     args = []
     for k in range(6):
