@@ -329,6 +329,66 @@ def bench_find_patches(torch, osd, n, iters):
         return {"error": str(exc)}
 
 
+def bench_incumbent_cuda(mesh, table, torch, osd):
+    """the reference's own CUDA backend kernels (osd/cudaKernel.cu, unmodified, compiled for sm_100a into
+    oracle/_ref/libosdcudaref.so) on the same B200 and the same device buffers: config 2 stencils with L = 3 (its tuned
+    path) and L = 6 (its generic path), and EvalPatches with 1st + 2nd derivatives.  A reported baseline, like cpu_baseline."""
+    from oracle import cuda_ref
+    from opensubdiv_b200 import synth
+    if not cuda_ref.available():
+        return {"skipped": "oracle/_ref/libosdcudaref.so not present"}
+    D = osd.BufferDescriptor
+    ncv, n = table.num_control_verts, table.num_stencils
+    tbl = osd.B200StencilTable.Create(table)
+    res = {"kind": "reference CudaEvaluator kernels (osd/cudaKernel.cu), -arch=sm_100a, same box, same buffers"}
+
+    def timed(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    for L in (3, 6):
+        pv = frame_primvars(mesh, 1)[:, :L].copy()
+        ours = torch.zeros((ncv + n, L), device="cuda")
+        ours[:ncv] = torch.from_numpy(pv).cuda()
+        theirs = ours.clone()
+        args_ref = (theirs.data_ptr(), theirs.data_ptr() + ncv * L * 4, L, L, L, tbl.GetSizesBuffer(), tbl.GetOffsetsBuffer(),
+                    tbl.GetIndicesBuffer(), tbl.GetWeightsBuffer(), 0, n)
+        ms_ref = timed(lambda: cuda_ref.eval_stencils(*args_ref), 5)
+        ms_ours = timed(lambda: osd.B200Evaluator.EvalStencils(ours, D(0, L, L), ours, D(ncv * L, L, L), tbl), 20)
+        diff = float((ours[ncv:] - theirs[ncv:]).abs().max().item())
+        res[f"eval_stencils_cfg2_L{L}"] = {"reference_cuda_ms": ms_ref, "reference_cuda_verts_per_s": n / (ms_ref * 1e-3),
+                                           "b200osd_ms": ms_ours, "b200osd_verts_per_s": n / (ms_ours * 1e-3),
+                                           "max_abs_diff": diff}
+        del ours, theirs
+    # EvalPatches: 2 M random coords on the torus patches, P + D1 + D2 interleaved (18 floats)
+    m = 2_000_000
+    ptab = synth.torus_patch_table(mesh)
+    pt = osd.B200PatchTable.Create(ptab)
+    coords = synth.random_patch_coords(len(mesh.faces), m, seed=2024)
+    pc = torch.from_numpy(coords.view(np.uint8)).cuda()
+    src = torch.from_numpy(frame_primvars(mesh, 1)[:, :3].copy()).cuda()
+    ours = torch.zeros((m, 18), device="cuda")
+    theirs = torch.zeros((m, 18), device="cuda")
+    a = []
+    for k in range(6):
+        a += [ours, D(3 * k, 3, 18)]
+    ms_ref = timed(lambda: cuda_ref.eval_patches(src.data_ptr(), [theirs.data_ptr() + 12 * k for k in range(6)], 3, 3, [18] * 6,
+                                                 m, pc.data_ptr(), pt.GetPatchArrayBuffer(), pt.GetPatchIndexBuffer(),
+                                                 pt.GetPatchParamBuffer()), 3)
+    ms_ours = timed(lambda: osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *a, m, pc, pt, None), 20)
+    res["eval_patches_2M_coords_P+D1+D2"] = {"reference_cuda_ms": ms_ref, "reference_cuda_pts_per_s": m / (ms_ref * 1e-3),
+                                            "b200osd_ms": ms_ours, "b200osd_pts_per_s": m / (ms_ours * 1e-3),
+                                            "max_abs_diff": float((ours - theirs).abs().max().item())}
+    return res
+
+
 # --------------------------------------------------------------------------------- B200 arm --
 def run_b200_arm(args):
     import faulthandler
@@ -546,6 +606,13 @@ def run_b200_arm(args):
         except Exception as exc:
             patches = {"error": str(exc)}
 
+    incumbent = None
+    if world == 1 and not args.no_patches:
+        try:
+            incumbent = bench_incumbent_cuda(mesh, table, torch, osd)
+        except Exception as exc:
+            incumbent = {"error": str(exc)}
+
     if rank == 0:
         cpu = None
         if world == 1:                                          # the CPU baseline is a rank-0, N=1 report
@@ -583,6 +650,7 @@ def run_b200_arm(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
             "eval_patches": patches,
+            "incumbent_cuda": incumbent,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

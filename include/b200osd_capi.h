@@ -193,7 +193,8 @@ B200OSD_API int  b200osd_patch_map_find(const b200osd_patch_map *m, int numSampl
 /* Selects the stencil kernel variant used by b200osd_stencil_table_eval: 0 = auto. */
 B200OSD_API void b200osd_set_stencil_variant(int variant);
 B200OSD_API int  b200osd_get_stencil_variant(void);
-/* Patch evaluation through the table handle: 0 = auto, 1 = always through the index buffer, 2 = always hull cache. */
+/* Patch evaluation through the table handle: 0 = auto, 1 = always through the index buffer, 2 = hull cache read directly,
+ * 3 = hull cache staged through shared memory, 4 = hull cache with the per-warp choice between 2 and 3 (what auto uses). */
 B200OSD_API void b200osd_set_patch_variant(int variant);
 B200OSD_API int  b200osd_get_patch_variant(void);
 

@@ -83,30 +83,40 @@ int ensure_box_tables() {
     return B200OSD_OK;
 }
 
-template <int ORDER, bool HULL>
+template <int ORDER, int MODE>
 int launch_patches_h(const PatchIO &io, int LT, cudaStream_t st) {
     const int block = kPatchBlock;
     const int grid = (io.n + block - 1) / block;
-    const size_t smem = 0;
+    const size_t smem = (size_t)(block / 32) * (size_t)io.warpWords * sizeof(float);
     switch (LT) {
-        case 1: patch_kernel<1, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
-        case 2: patch_kernel<2, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
-        case 3: patch_kernel<3, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
-        default: patch_kernel<4, ORDER, HULL><<<grid, block, smem, st>>>(io); break;
+        case 1: patch_kernel<1, ORDER, MODE><<<grid, block, smem, st>>>(io); break;
+        case 2: patch_kernel<2, ORDER, MODE><<<grid, block, smem, st>>>(io); break;
+        case 3: patch_kernel<3, ORDER, MODE><<<grid, block, smem, st>>>(io); break;
+        default: patch_kernel<4, ORDER, MODE><<<grid, block, smem, st>>>(io); break;
     }
     return check_launch("patch_kernel");
 }
 
 template <int ORDER>
-int launch_patches(const PatchIO &io, int LT, cudaStream_t st) {
-    return io.hull4 ? launch_patches_h<ORDER, true>(io, LT, st) : launch_patches_h<ORDER, false>(io, LT, st);
+int launch_patches(const PatchIO &io, int LT, int mode, cudaStream_t st) {
+    switch (mode) {
+        case 3: return launch_patches_h<ORDER, 3>(io, LT, st);
+        case 2: return launch_patches_h<ORDER, 2>(io, LT, st);
+        case 1: return launch_patches_h<ORDER, 1>(io, LT, st);
+        default: return launch_patches_h<ORDER, 0>(io, LT, st);
+    }
 }
 
-int g_patch_variant = 0;   // 0 auto, 1 always through the index buffer, 2 always through the hull cache
+// 0 auto (index buffer for few coordinates per patch, else 4), 1 through the index buffer, 2 hull cache read directly,
+// 3 hull cache staged in shared memory, 4 per-warp choice between 2 and 3, 100+T the same with threshold T (sweeps)
+int g_patch_variant = 0;
+constexpr int kStageThreshold = 8;
 
 struct HullRequest {       // filled by b200osd_patch_table_eval when the hull cache should be used
     float4 *hull4 = nullptr;
     int hullStride = 0, hullTiles = 0, numArrays = 0, numPatches = 0;
+    int staged = 0;        // 0 direct reads, 1 always staged (MODE 2), 2 per-warp choice (MODE 3)
+    int threshold = 0;
 };
 
 int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float *const dsts[],
@@ -143,7 +153,29 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
         io.hullStride = hull ? hull->hullStride : 0;
         io.hullTiles = hull ? hull->hullTiles : 0;
         io.tile = c0 / 4;
-        rc = nOut == 1 ? launch_patches<0>(io, LT, st) : (nOut == 3 ? launch_patches<1>(io, LT, st) : launch_patches<2>(io, LT, st));
+        // glEvalLimit-style interleaving: output k at float k*LT of an nOut*LT-float record in one buffer
+        io.packed = (nOut > 1 && LT == L) ? 1 : 0;
+        for (int k = 0; k < nOut && io.packed; ++k)
+            if (!io.dst[k] || io.dst[k] != io.dst[0] + (size_t)k * LT || io.dstStride[k] != nOut * LT) io.packed = 0;
+        const int nsets = nOut;
+        const int recordWords = 32 * (nsets > 1 ? ((nsets * LT) | 1) : LT);
+        io.hullPitch = 0; io.hullAdd = 0; io.hullRem = 0; io.stageThreshold = 0;
+        int mode = hull ? 1 : 0;
+        io.warpWords = recordWords;
+        if (hull && hull->staged) {
+            const int pitch = (hull->hullStride * LT) | 1;
+            const int words = std::max(recordWords, 32 * pitch);
+            if ((size_t)(kPatchBlock / 32) * words * sizeof(float) <= 48 * 1024) {     // else: direct hull reads
+                mode = hull->staged == 1 ? 2 : 3;
+                io.stageThreshold = hull->threshold;
+                io.warpWords = words;
+                io.hullPitch = pitch;
+                io.hullAdd = 32 / hull->hullStride;
+                io.hullRem = 32 % hull->hullStride;
+            }
+        }
+        rc = nOut == 1 ? launch_patches<0>(io, LT, mode, st)
+                       : (nOut == 3 ? launch_patches<1>(io, LT, mode, st) : launch_patches<2>(io, LT, mode, st));
         if (rc) return rc;
     }
     return B200OSD_OK;
@@ -231,7 +263,7 @@ int b200osd_patch_table_eval(const b200osd_patch_table *tc, int which, const flo
     // Hull cache: when many coordinates share few patches, gather every patch's control points once per call into
     // 16-byte rows so that a coordinate reads one compact, aligned block instead of 16-20 scattered vertices.
     HullRequest hull;
-    bool useHull = (g_patch_variant == 2) || (g_patch_variant == 0 && (long long)numPatchCoords >= 4LL * numPatches);
+    bool useHull = (g_patch_variant >= 2) || (g_patch_variant == 0 && (long long)numPatchCoords >= 4LL * numPatches);
     if (useHull && numPatches > 0) {
         int hs = 0;
         for (int a = 0; a < tr.nArrays; ++a) hs = std::max(hs, t->hostArrays[which][a].stride);
@@ -255,6 +287,8 @@ int b200osd_patch_table_eval(const b200osd_patch_table *tc, int which, const flo
             hull.hullTiles = tiles;
             hull.numArrays = tr.nArrays;
             hull.numPatches = numPatches;
+            hull.staged = g_patch_variant == 3 ? 1 : (g_patch_variant == 2 ? 0 : 2);     // auto = per-warp choice
+            hull.threshold = g_patch_variant >= 100 ? g_patch_variant - 100 : kStageThreshold;
         }
     }
     return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, tr.arrays, tr.indices,

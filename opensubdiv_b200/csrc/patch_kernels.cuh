@@ -44,6 +44,12 @@ struct PatchIO {
     int hullStride;                   // points per patch slot (max array stride)
     int hullTiles;                    // ceil(L / 4)
     int tile;                         // component tile evaluated by this launch
+    int packed;                       // outputs form one contiguous NSETS*LT-float record per coordinate (see store_outputs)
+    // shared memory: one private region of warpWords floats per warp (output transposition; staged hulls alias it)
+    int warpWords;
+    int hullPitch;                    // staged hulls: floats per lane row = (hullStride * LT) | 1
+    int hullAdd, hullRem;             // 32 / hullStride, 32 % hullStride (cooperative fill bookkeeping)
+    int stageThreshold;               // MODE 3: stage when a warp touches more distinct patches than this
 };
 
 enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_BASIS = 9, PT_GREGORY_TRIANGLE = 10 };
@@ -199,34 +205,70 @@ struct CvHull {
     }
 };
 
+// ... or from the warp's shared-memory copy of its 32 hulls (MODE 2): LT floats per point, odd row pitch
+struct CvSmem {
+    const float *row;
+    template <int LT>
+    B200_HD void load(int j, float (&v)[LT]) const {
+#pragma unroll
+        for (int c = 0; c < LT; ++c) v[c] = row[j * LT + c];
+    }
+};
+
+#ifdef __CUDACC__
+extern __shared__ float b200_patch_smem[];
+#endif
+
 constexpr int kPatchBlock = 128;
 
 // Results leave through shared memory: a warp's 32 x LT values of one output are transposed so that consecutive lanes
 // write consecutive floats (one 128-byte request per 32 floats when the output is packed, runs of LT otherwise)
 // instead of 32 scattered LT-float records.  `live` = this lane holds a real coordinate; i0 = the warp's first one.
+// io.packed: all NSETS outputs interleave into ONE record of NSETS*LT floats per coordinate (the glEvalLimit layout,
+// examples/glEvalLimit/glEvalLimit.cpp:277-287) -- then the warp's whole 32 x NSETS*LT block is staged and leaves as
+// NSETS*LT fully coalesced 128-byte rows instead of LT-float runs at a stride (3.5x fewer L2 write sectors for 18 floats).
 template <int LT, int NSETS>
 B200_HD void store_outputs(const PatchIO &io, int i, bool live, const float (&out)[NSETS][LT]) {
 #ifdef __CUDA_ARCH__
-    __shared__ float stage[kPatchBlock / 32][32 * LT];
+    constexpr int R = NSETS * LT;                 // floats per packed record
+    constexpr int RP = R | 1;                     // odd row pitch: conflict-free transposition
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = i - lane;
     const unsigned livemask = __ballot_sync(0xffffffffu, live);   // lanes past the end or holding a miss write nothing
-    float *st = stage[warp];
+    float *st = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
+    __syncwarp();                                               // the region may still be read as staged hulls
+    if (NSETS > 1 && io.packed) {                               // uniform across the grid
+#pragma unroll
+        for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+            for (int c = 0; c < LT; ++c) st[lane * RP + k * LT + c] = out[k][c];
+        __syncwarp();
+        float *base = io.dst[0] + (size_t)i0 * (size_t)R;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int e = q * 32 + lane;
+            const int ci = e / R, c = e - ci * R;
+            if ((livemask >> ci) & 1u) st_stream_f1(base + e, st[ci * RP + c]);
+        }
+        return;
+    }
+    // separate buffers (or a strided / partial record): all outputs are staged at once, [output][coordinate][component]
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+        for (int c = 0; c < LT; ++c) st[k * 32 * LT + lane * LT + c] = out[k][c];
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) {
         float *d = io.dst[k];
-        if (!d) continue;                                   // uniform across the block
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < LT; ++c) st[lane * LT + c] = out[k][c];
-        __syncwarp();
+        if (!d) continue;                                   // uniform across the grid
         const size_t stride = (size_t)io.dstStride[k];
         float *base = d + (size_t)i0 * stride;
 #pragma unroll
         for (int q = 0; q < LT; ++q) {
             const int e = q * 32 + lane;
             const int ci = e / LT, c = e - ci * LT;
-            if ((livemask >> ci) & 1u) st_stream_f1(base + (size_t)ci * stride + c, st[e]);
+            if ((livemask >> ci) & 1u) st_stream_f1(base + (size_t)ci * stride + c, st[k * 32 * LT + e]);
         }
     }
 #else
@@ -530,7 +572,13 @@ B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int bound
     // unknown descriptor: the reference evaluates zero points, i.e. writes zeros
 }
 
-template <int LT, int ORDER, bool HULL>
+// MODE: 0 = control points through the index buffer; 1 = from the hull cache, read directly; 2 = from the hull cache,
+// staged through shared memory: the warp copies the hulls of its distinct patches cooperatively (consecutive lanes read
+// consecutive 16-byte rows: 2 fully used 128-byte lines per 16-point hull instead of one line touch per lane and
+// point), then every lane evaluates out of its patch's row -- for incoherent coordinates ~3.5x fewer L1 wavefronts;
+// 3 = per warp: staged when the warp touches more than io.stageThreshold distinct patches, direct otherwise (coherent
+// warps read the same rows: broadcast loads are cheaper than staging).  See DESIGN.md 4.3.
+template <int LT, int ORDER, int MODE>
 B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
     float out[NSETS][LT];
@@ -551,22 +599,23 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
         // Far::PatchMap::FindPatch returns NULL and the reference's callers skip the sample): its outputs stay untouched
         live = arrayIndex >= 0;
     }
+    int type = 0, boundary = 0;
+    float d1 = 1.0f, sign = 1.0f;
+    const int *aw = nullptr;
     if (live) {
-
-        const int *aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
+        aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
         const int regDesc = ldg_i(aw + 0), irrDesc = ldg_i(aw + 1);
         const unsigned field1 = ldg_u(&io.params[patchIndex].field1);
 
         const int depth = (int)(field1 & 0xfu);
         const int nonquad = (int)((field1 >> 4) & 1u);
         const bool regular = ((field1 >> 5) & 1u) != 0;
-        const int boundary = (int)((field1 >> 7) & 0x1fu);
+        boundary = (int)((field1 >> 7) & 0x1fu);
         const int pv = (int)((field1 >> 12) & 0x3ffu), pu = (int)((field1 >> 22) & 0x3ffu);
-        const int type = regular ? regDesc : irrDesc;
+        type = regular ? regDesc : irrDesc;
 
         const float fracInv = (float)(1 << (depth - nonquad));
         const bool isTri = (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES);
-        float sign = 1.0f;
         if (isTri && (pu + pv) >= (1 << depth)) {
             const int df = 1 << depth;
             s = (float)(df - pu) - s * fracInv;
@@ -576,13 +625,78 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
             s = fmaf(s, fracInv, -(float)pu);
             t = fmaf(t, fracInv, -(float)pv);
         }
-        const float d1 = sign * (float)(1 << depth);
+        d1 = sign * (float)(1 << depth);
+    }
 
-        if (HULL) {
+    if (MODE >= 2) {
+#ifdef __CUDA_ARCH__
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int mine = live ? patchIndex : -1;
+        bool staged = true;
+        if (MODE == 3) {
+            // per warp: runs of equal patch indices (>= the number of distinct patches).  Few runs: the lanes read the
+            // same rows and broadcast loads straight from the hull cache are cheaper than staging.
+            const int prev = __shfl_up_sync(0xffffffffu, mine, 1);
+            const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || mine != prev);
+            staged = __popc(heads) > io.stageThreshold;
+        }
+        if (staged) {
+            // lanes evaluating the same patch share one staged copy: the lowest such lane (the owner) fills the row
+            const unsigned same = __match_any_sync(0xffffffffu, mine);
+            const int owner = __ffs(same) - 1;
+            const int lead = (owner == lane) ? mine : -1;
+            float *hs = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
+            const int stride = io.hullStride, pitch = io.hullPitch;
+            if (stride == 16) {
+                // pass `it` copies hulls it and it+16, one per half warp (2 x 256 contiguous bytes); rows 16 apart are
+                // 16 banks apart (odd pitch), so the two halves' shared-memory stores do not collide
+                const int j = lane & 15, hsel = lane & 16;
+#pragma unroll 4
+                for (int it = 0; it < 16; ++it) {
+                    const int h = it + hsel;
+                    const int p = __shfl_sync(0xffffffffu, lead, h);
+                    if (p >= 0) {
+                        const float4 v = ld_stream_f4(io.hull4 + ((size_t)p * (size_t)io.hullTiles + (size_t)io.tile) * 16 + j);
+                        float *d = hs + h * pitch + j * LT;
+                        d[0] = v.x;
+                        if (LT > 1) d[1] = v.y;
+                        if (LT > 2) d[2] = v.z;
+                        if (LT > 3) d[3] = v.w;
+                    }
+                }
+            } else {
+                int h = lane / stride, j = lane - h * stride;
+                for (int it = 0; it < stride; ++it) {           // 32 * stride rows in all, 32 per pass
+                    const int p = __shfl_sync(0xffffffffu, lead, h);
+                    if (p >= 0) {
+                        const float4 v = ld_stream_f4(io.hull4 + ((size_t)p * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)stride + j);
+                        float *d = hs + h * pitch + j * LT;
+                        d[0] = v.x;
+                        if (LT > 1) d[1] = v.y;
+                        if (LT > 2) d[2] = v.z;
+                        if (LT > 3) d[3] = v.w;
+                    }
+                    h += io.hullAdd;
+                    j += io.hullRem;
+                    if (j >= stride) { j -= stride; ++h; }
+                }
+            }
+            __syncwarp();
+            if (live) {
+                CvSmem cv;
+                cv.row = hs + owner * pitch;
+                eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
+            }
+        } else if (MODE == 3 && live) {
+            CvHull cv;
+            cv.base = io.hull4 + ((size_t)patchIndex * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)io.hullStride;
+            eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
+        }
+#endif
+    } else if (live) {
+        if (MODE == 1) {
             // hull cache: the patch's control points as compact 16-byte rows (8 sectors per coordinate instead of 18
-            // scattered ones for incoherent coordinates; broadcast reads for coherent ones).  Measured alternatives that
-            // did not pay (profiles/r01c_patch_sweeps.md): per-warp shared-memory staging of the hulls, and dispatching
-            // coherent warps through the index buffer.
+            // scattered ones for incoherent coordinates; broadcast reads for coherent ones)
             CvHull cv;
             cv.base = io.hull4 + ((size_t)patchIndex * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)io.hullStride;
             eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
@@ -599,11 +713,11 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
 }
 
 #ifdef __CUDACC__
-template <int LT, int ORDER, bool HULL>
+template <int LT, int ORDER, int MODE>
 __global__ void __launch_bounds__(kPatchBlock) patch_kernel(PatchIO io) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i - (int)(threadIdx.x & 31) >= io.n) return;          // whole warp past the end
-    patch_eval_coord<LT, ORDER, HULL>(io, i, i < io.n);
+    patch_eval_coord<LT, ORDER, MODE>(io, i, i < io.n);
 }
 
 // Hull cache fill.  Block (32, 8): threadIdx.x = control point j of the patch, threadIdx.y = patch inside the block,

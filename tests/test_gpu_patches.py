@@ -31,7 +31,7 @@ def test_golden_patch_tables_all_arities(name):
     pc = coords_dev(coords)
     src = dev(d["vb"])
     scales = oracle_patches(d["vb"], (0, 3, 3), 3, coords, vtx, 6, abs_scale=True)
-    for variant in (0, 1, 2):          # auto, through the index buffer, through the per-patch hull cache
+    for variant in (0, 1, 2, 3, 4):    # auto, index buffer, hull cache direct, hull cache staged in smem, per-warp choice
       for nw in (1, 3, 6):
         # outputs interleaved in one buffer, glEvalLimit style (examples/glEvalLimit/glEvalLimit.cpp:277-287)
         out = torch.full((n, 3 * nw), float("nan"), device="cuda")
@@ -69,7 +69,7 @@ def test_golden_patch_tables_all_arities(name):
         args = []
         for o in outs:
             args += [o, D(0, 2, 2)]
-        for variant in (1, 2):
+        for variant in (1, 2, 3, 4):
             set_patch_variant(variant)
             try:
                 assert osd.B200Evaluator.EvalPatchesFaceVarying(fsrc, D(0, 2, 2), *args, n, pc, pt, 0, None)
@@ -117,7 +117,7 @@ def test_primvar_lengths_and_null_outputs(L, stride, offset):
     exp = oracle_patches(src, (offset, L, stride), L, coords, vtx, 6)
     scl = oracle_patches(src, (offset, L, stride), L, coords, vtx, 6, abs_scale=True)
     pt = osd.B200PatchTable.Create(_PT(vtx))
-    for variant in (1, 2):
+    for variant in (1, 2, 3, 4):
         outs = [torch.full((n, L), float("nan"), device="cuda") for _ in range(6)]
         # NULL du and dvv are skipped (osd/cudaKernel.cu:300-327)
         bufs = [outs[0], None, outs[2], outs[3], outs[4], None]
