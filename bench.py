@@ -224,41 +224,60 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------- EvalPatches section --
-def bench_eval_patches(mesh, torch, osd, capi, log, n=10_000_000, iters=20):
+def bench_eval_patches(mesh, torch, osd, capi, log, n=10_000_000, iters=20, world=1, rank=0, strong=False):
     """BASELINE config 4 shape of work on the synthetic torus: 10 M PatchCoords on 100 000 regular bicubic patches,
     P + 1st + 2nd derivatives of xyz interleaved in one 18-float buffer (glEvalLimit layout), random and patch-sorted
     coordinate order; device-resident, CUDA events.  Algorithmic bytes = n * (20 + 6*12).  Plus the reference's CPU
-    evaluators on the first 1 M of the same coordinates."""
-    from opensubdiv_b200 import synth
+    evaluators on the first 1 M of the same coordinates.
+    N > 1: EvalPatches shards by PatchCoord range with replicated tables and no data-path collective --
+    weak: every rank evaluates n coordinates on its own mesh; strong: the n coordinates are cut into N ranges
+    (shard.coord_plan).  Time = max over ranks, pts/s = all ranks' coordinates / that time."""
+    from opensubdiv_b200 import synth, shard
     D = osd.BufferDescriptor
+    n_total = n if (strong or world == 1) else n * world
+    lo, hi = (0, n)
+    if strong and world > 1:
+        lo, hi = shard.coord_plan(n, world, rank).ranges[rank]
     ptab = synth.torus_patch_table(mesh)
     pt = osd.B200PatchTable.Create(ptab)
     src = torch.from_numpy(frame_primvars(mesh, 1)[:, :3].copy()).cuda()
-    out = torch.empty((n, 18), device="cuda")
+    nl = hi - lo
+    out = torch.empty((max(nl, 1), 18), device="cuda")
     args = []
     for k in range(6):
         args += [out, D(3 * k, 3, 18)]
     peak, _ = measured_peak()
-    res = {"workload": "torus_400x250_regular_patches_10M_coords_xyz_P+D1+D2", "coords": n, "patches": len(mesh.faces),
-           "algorithmic_bytes": n * 92}
+    res = {"workload": "torus_400x250_regular_patches_10M_coords_xyz_P+D1+D2", "coords": n_total, "coords_per_gpu": nl,
+           "patches": len(mesh.faces), "algorithmic_bytes": n_total * 92,
+           "sharding": "none (1 GPU)" if world == 1 else
+           ("PatchCoord ranges of one coordinate set, tables replicated" if strong else
+            "every rank evaluates its own coordinate set on its own mesh, tables replicated")}
     coords_by_order = {}
     for order, sort in (("random", False), ("sorted_by_patch", True)):
         coords = synth.random_patch_coords(len(mesh.faces), n, seed=2024, sort_by_patch=sort)
         coords_by_order[order] = coords
-        pc = torch.from_numpy(coords.view(np.uint8)).cuda()
+        pc = torch.from_numpy(np.ascontiguousarray(coords[lo:hi]).view(np.uint8)).cuda()
         for _ in range(3):
-            assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+            assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, nl, pc, pt, None)
         torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+            osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, nl, pc, pt, None)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        res[order] = {"ms": ms, "pts_per_s": n / (ms * 1e-3), "GBps": n * 92 / (ms * 1e-3) / 1e9,
-                      "frac_of_measured_hbm_peak": n * 92 / (ms * 1e-3) / 1e9 / peak}
+        if world > 1:
+            tms = torch.tensor([ms], device="cuda")
+            torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
+            ms = float(tms.item())
+        res[order] = {"ms": ms, "pts_per_s": n_total / (ms * 1e-3), "GBps": n_total * 92 / (ms * 1e-3) / 1e9,
+                      "frac_of_measured_hbm_peak": n_total * 92 / (ms * 1e-3) / 1e9 / (peak * world)}
         del pc
+    if world > 1:
+        return res
     try:
         from oracle import ref as oref
         if oref.available():
@@ -598,13 +617,17 @@ def run_b200_arm(args):
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
 
-    # Second half of BASELINE.json's metric (limit pts/s, EvalPatches): reported in "eval_patches" at N=1.
+    # Second half of BASELINE.json's metric (limit pts/s, EvalPatches): reported in "eval_patches" (sharded by PatchCoord range at N > 1).
     patches = None
-    if world == 1 and not args.no_patches:
-        try:
-            patches = bench_eval_patches(mesh, torch, osd, capi, log)
-        except Exception as exc:
-            patches = {"error": str(exc)}
+    if not args.no_patches:
+        if world == 1:
+            try:
+                patches = bench_eval_patches(mesh, torch, osd, capi, log)
+            except Exception as exc:
+                patches = {"error": str(exc)}
+        else:
+            # collectives inside: every rank must take the same path, so no exception is swallowed here
+            patches = bench_eval_patches(mesh, torch, osd, capi, log, world=world, rank=rank, strong=strong)
 
     incumbent = None
     if world == 1 and not args.no_patches:

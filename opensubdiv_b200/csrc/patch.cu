@@ -114,6 +114,8 @@ constexpr int kStageThreshold = 8;
 
 struct HullRequest {       // filled by b200osd_patch_table_eval when the hull cache should be used
     float4 *hull4 = nullptr;
+    const int *rowsBefore = nullptr;     // device, per patch array
+    const b200osd_patch_array *hostArrays = nullptr;
     int hullStride = 0, hullTiles = 0, numArrays = 0, numPatches = 0;
     int staged = 0;        // 0 direct reads, 1 always staged (MODE 2), 2 per-warp choice (MODE 3)
     int threshold = 0;
@@ -127,13 +129,19 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
     int rc = ensure_box_tables();
     if (rc) return rc;
     if (hull) {
-        const dim3 hblock(32, 8);
-        const dim3 hgrid((unsigned)((hull->numPatches + 7) / 8), (unsigned)hull->hullTiles);
-        hull_gather_kernel<<<hgrid, hblock, 0, st>>>(src + srcDesc[0], srcDesc[2], L, patchArrays, hull->numArrays,
-                                                     patchIndices, hull->numPatches, hull->hullStride, hull->hullTiles,
-                                                     hull->hull4);
-        rc = check_launch("hull_gather_kernel");
-        if (rc) return rc;
+        long long before = 0;
+        for (int a = 0; a < hull->numArrays; ++a) {
+            const b200osd_patch_array &pa = hull->hostArrays[a];
+            const long long rows = (long long)pa.numPatches * (long long)pa.stride;
+            if (rows > 0) {
+                const dim3 hgrid((unsigned)((rows + 255) / 256), (unsigned)hull->hullTiles);
+                hull_gather_kernel<<<hgrid, 256, 0, st>>>(src + srcDesc[0], srcDesc[2], L, patchIndices + pa.indexBase, rows,
+                                                          pa.stride, before, hull->hullTiles, hull->hull4);
+                rc = check_launch("hull_gather_kernel");
+                if (rc) return rc;
+            }
+            before += rows;
+        }
     }
     // components are evaluated in tiles of at most 4 (xyz, uv, rgba fit in one launch)
     for (int c0 = 0; c0 < L; c0 += 4) {
@@ -150,6 +158,7 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
         io.indices = patchIndices;
         io.params = patchParams;
         io.hull4 = hull ? hull->hull4 : nullptr;
+        io.hullRowsBefore = hull ? hull->rowsBefore : nullptr;
         io.hullStride = hull ? hull->hullStride : 0;
         io.hullTiles = hull ? hull->hullTiles : 0;
         io.tile = c0 / 4;
@@ -159,10 +168,10 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
             if (!io.dst[k] || io.dst[k] != io.dst[0] + (size_t)k * LT || io.dstStride[k] != nOut * LT) io.packed = 0;
         const int nsets = nOut;
         const int recordWords = 32 * (nsets > 1 ? ((nsets * LT) | 1) : LT);
-        io.hullPitch = 0; io.hullAdd = 0; io.hullRem = 0; io.stageThreshold = 0;
+        io.hullPitch = 0; io.stageThreshold = 0;
         int mode = hull ? 1 : 0;
         io.warpWords = recordWords;
-        if (hull && hull->staged) {
+        if (hull && hull->staged && hull->hullStride >= 12) {      // 3-4 point (linear) hulls: direct reads
             const int pitch = (hull->hullStride * LT) | 1;
             const int words = std::max(recordWords, 32 * pitch);
             if ((size_t)(kPatchBlock / 32) * words * sizeof(float) <= 48 * 1024) {     // else: direct hull reads
@@ -170,8 +179,6 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
                 io.stageThreshold = hull->threshold;
                 io.warpWords = words;
                 io.hullPitch = pitch;
-                io.hullAdd = 32 / hull->hullStride;
-                io.hullRem = 32 % hull->hullStride;
             }
         }
         rc = nOut == 1 ? launch_patches<0>(io, LT, mode, st)
@@ -206,6 +213,8 @@ struct b200osd_patch_table {
         b200osd_patch_array *arrays = nullptr;
         int *indices = nullptr;
         b200osd_patch_param *params = nullptr;
+        int *rowsBefore = nullptr;     // hull cache layout: per array, sum over earlier arrays of numPatches * stride
+        long long hullRows = 0;        // total rows of one component tile
         int nArrays = 0, nIndices = 0, nParams = 0;
     };
     std::vector<Triple> triples;   // 0 vertex, 1 varying, 2+c fvar channel c
@@ -217,7 +226,7 @@ struct b200osd_patch_table {
 };
 
 static void free_triple(b200osd_patch_table::Triple &tr) {
-    cudaFree(tr.arrays); cudaFree(tr.indices); cudaFree(tr.params);
+    cudaFree(tr.arrays); cudaFree(tr.indices); cudaFree(tr.params); cudaFree(tr.rowsBefore);
     tr = b200osd_patch_table::Triple();
 }
 
@@ -267,9 +276,9 @@ int b200osd_patch_table_eval(const b200osd_patch_table *tc, int which, const flo
     if (useHull && numPatches > 0) {
         int hs = 0;
         for (int a = 0; a < tr.nArrays; ++a) hs = std::max(hs, t->hostArrays[which][a].stride);
-        if (hs < 1 || hs > 32) useHull = false;       // one warp lane per control point in the cache fill
+        if (hs < 1 || hs > 32 || tr.hullRows <= 0 || !tr.rowsBefore) useHull = false;   // one warp lane per control point
         const int tiles = (srcDesc[1] + 3) / 4;
-        const size_t need = (size_t)numPatches * hs * tiles;
+        const size_t need = (size_t)std::max(tr.hullRows, 0LL) * tiles;
         if (useHull && need > t->hullCap) {
             cudaFree(t->d_hull);
             t->d_hull = nullptr;
@@ -283,11 +292,16 @@ int b200osd_patch_table_eval(const b200osd_patch_table *tc, int which, const flo
         }
         if (useHull) {
             hull.hull4 = t->d_hull;
+            hull.rowsBefore = tr.rowsBefore;
+            hull.hostArrays = t->hostArrays[which].data();
             hull.hullStride = hs;
             hull.hullTiles = tiles;
             hull.numArrays = tr.nArrays;
             hull.numPatches = numPatches;
-            hull.staged = g_patch_variant == 3 ? 1 : (g_patch_variant == 2 ? 0 : 2);     // auto = per-warp choice
+            // auto: per-warp choice while the cache is L2-resident (incoherent warps are then bound by L1 wavefronts and
+            // staging pays); a cache far larger than L2 makes incoherent reads DRAM-bound and staging only adds work
+            const bool l2Resident = need * sizeof(float4) <= (size_t)64 << 20;
+            hull.staged = g_patch_variant == 3 ? 1 : (g_patch_variant == 2 ? 0 : (g_patch_variant == 0 && !l2Resident ? 0 : 2));
             hull.threshold = g_patch_variant >= 100 ? g_patch_variant - 100 : kStageThreshold;
         }
     }
@@ -325,7 +339,16 @@ int b200osd_patch_table_set(b200osd_patch_table *t, int which, int numArrays, co
     int rc = upload_array(&tr.arrays, arrays, numArrays);
     if (!rc) rc = upload_array(&tr.indices, indices, numIndices);
     if (!rc) rc = upload_array(&tr.params, params, numParams);
+    std::vector<int> before((size_t)std::max(numArrays, 0));
+    long long rows = 0;
+    for (int a = 0; arrays && a < numArrays; ++a) {
+        before[(size_t)a] = (int)rows;
+        rows += (long long)arrays[a].numPatches * (long long)std::max(arrays[a].stride, 0);
+    }
+    if (!rc && rows > 0x7fffffffLL) rows = -1;                 // too large for 32-bit row offsets: no hull cache
+    if (!rc) rc = upload_array(&tr.rowsBefore, before.data(), arrays ? numArrays : 0);
     if (rc) { free_triple(tr); return rc; }
+    tr.hullRows = rows;
     t->hostArrays[which].assign(arrays, arrays + (arrays ? numArrays : 0));
     tr.nArrays = tr.arrays ? numArrays : 0;
     tr.nIndices = tr.indices ? numIndices : 0;

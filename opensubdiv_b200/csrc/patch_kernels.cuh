@@ -38,17 +38,18 @@ struct PatchIO {
     const b200osd_patch_array *arrays;
     const int *indices;
     const b200osd_patch_param *params;
-    // optional per-frame hull cache (see hull_gather_kernel): control points of every patch gathered into
-    // 16-byte rows, [patch][tile][point]; used when many coordinates share few patches
+    // optional per-call hull cache (see hull_gather_kernel): control points of every patch gathered into 16-byte
+    // rows, array by array: row(a, p, tile, j) = (hullRowsBefore[a] + (p - primitiveIdBase_a) * stride_a) * tiles
+    //                                            + tile * stride_a + j      -- every hull of a 16-point array is 256 B aligned
     const float4 *hull4;
-    int hullStride;                   // points per patch slot (max array stride)
+    const int *hullRowsBefore;        // per patch array: sum over earlier arrays of numPatches * stride
+    int hullStride;                   // largest array stride (row capacity of a staged hull)
     int hullTiles;                    // ceil(L / 4)
     int tile;                         // component tile evaluated by this launch
     int packed;                       // outputs form one contiguous NSETS*LT-float record per coordinate (see store_outputs)
     // shared memory: one private region of warpWords floats per warp (output transposition; staged hulls alias it)
     int warpWords;
     int hullPitch;                    // staged hulls: floats per lane row = (hullStride * LT) | 1
-    int hullAdd, hullRem;             // 32 / hullStride, 32 % hullStride (cooperative fill bookkeeping)
     int stageThreshold;               // MODE 3: stage when a warp touches more distinct patches than this
 };
 
@@ -218,6 +219,14 @@ struct CvSmem {
 #ifdef __CUDACC__
 extern __shared__ float b200_patch_smem[];
 #endif
+
+// first hull-cache row of patch p of the array described by aw (the 6 ints of its PatchArray), component tile `tile`
+B200_HD size_t hull_first_row(const int *rowsBefore, int arrayIndex, const int *aw, int p, int tiles, int tile, int *points) {
+    const int stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
+    *points = stride;
+    return ((size_t)ldg_i(rowsBefore + arrayIndex) + (size_t)(p - primBase) * (size_t)stride) * (size_t)tiles
+           + (size_t)tile * (size_t)stride;
+}
 
 constexpr int kPatchBlock = 128;
 
@@ -632,6 +641,9 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
 #ifdef __CUDA_ARCH__
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int mine = live ? patchIndex : -1;
+        int points = 0;
+        size_t row0 = 0;
+        if (live) row0 = hull_first_row(io.hullRowsBefore, arrayIndex, aw, patchIndex, io.hullTiles, io.tile, &points);
         bool staged = true;
         if (MODE == 3) {
             // per warp: runs of equal patch indices (>= the number of distinct patches).  Few runs: the lanes read the
@@ -641,44 +653,44 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
             staged = __popc(heads) > io.stageThreshold;
         }
         if (staged) {
-            // lanes evaluating the same patch share one staged copy: the lowest such lane (the owner) fills the row
+            // lanes evaluating the same patch share one staged copy: the lowest such lane (the owner) publishes the row
             const unsigned same = __match_any_sync(0xffffffffu, mine);
             const int owner = __ffs(same) - 1;
-            const int lead = (owner == lane) ? mine : -1;
+            const int np = (owner == lane && live) ? points : 0;         // rows this lane's hull contributes (0: not an owner)
             float *hs = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
-            const int stride = io.hullStride, pitch = io.hullPitch;
-            if (stride == 16) {
-                // pass `it` copies hulls it and it+16, one per half warp (2 x 256 contiguous bytes); rows 16 apart are
-                // 16 banks apart (odd pitch), so the two halves' shared-memory stores do not collide
-                const int j = lane & 15, hsel = lane & 16;
+            const int pitch = io.hullPitch;
+            // rows 0..15: pass `it` copies hulls it and it+16, one per half warp (256 contiguous bytes each); rows 16
+            // apart are 16 banks apart (odd pitch), so the two halves' shared-memory stores do not collide
+            const int j = lane & 15, hsel = lane & 16;
 #pragma unroll 4
-                for (int it = 0; it < 16; ++it) {
-                    const int h = it + hsel;
-                    const int p = __shfl_sync(0xffffffffu, lead, h);
-                    if (p >= 0) {
-                        const float4 v = ld_stream_f4(io.hull4 + ((size_t)p * (size_t)io.hullTiles + (size_t)io.tile) * 16 + j);
-                        float *d = hs + h * pitch + j * LT;
-                        d[0] = v.x;
-                        if (LT > 1) d[1] = v.y;
-                        if (LT > 2) d[2] = v.z;
-                        if (LT > 3) d[3] = v.w;
-                    }
+            for (int it = 0; it < 16; ++it) {
+                const int h = it + hsel;
+                const int n = __shfl_sync(0xffffffffu, np, h);
+                const unsigned long long r = __shfl_sync(0xffffffffu, (unsigned long long)row0, h);
+                if (j < n) {
+                    const float4 v = ld_stream_f4(io.hull4 + r + j);
+                    float *d = hs + h * pitch + j * LT;
+                    d[0] = v.x;
+                    if (LT > 1) d[1] = v.y;
+                    if (LT > 2) d[2] = v.z;
+                    if (LT > 3) d[3] = v.w;
                 }
-            } else {
-                int h = lane / stride, j = lane - h * stride;
-                for (int it = 0; it < stride; ++it) {           // 32 * stride rows in all, 32 per pass
-                    const int p = __shfl_sync(0xffffffffu, lead, h);
-                    if (p >= 0) {
-                        const float4 v = ld_stream_f4(io.hull4 + ((size_t)p * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)stride + j);
-                        float *d = hs + h * pitch + j * LT;
-                        d[0] = v.x;
-                        if (LT > 1) d[1] = v.y;
-                        if (LT > 2) d[2] = v.z;
-                        if (LT > 3) d[3] = v.w;
-                    }
-                    h += io.hullAdd;
-                    j += io.hullRem;
-                    if (j >= stride) { j -= stride; ++h; }
+            }
+            // rows 16..: only the few hulls that have them (Gregory end caps), one hull per pass
+            unsigned big = __ballot_sync(0xffffffffu, np > 16);
+            while (big) {
+                const int h = __ffs(big) - 1;
+                big &= big - 1;
+                const int n = __shfl_sync(0xffffffffu, np, h);
+                const unsigned long long r = __shfl_sync(0xffffffffu, (unsigned long long)row0, h);
+                const int jj = 16 + lane;
+                if (jj < n) {
+                    const float4 v = ld_stream_f4(io.hull4 + r + jj);
+                    float *d = hs + h * pitch + jj * LT;
+                    d[0] = v.x;
+                    if (LT > 1) d[1] = v.y;
+                    if (LT > 2) d[2] = v.z;
+                    if (LT > 3) d[3] = v.w;
                 }
             }
             __syncwarp();
@@ -689,7 +701,7 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
             }
         } else if (MODE == 3 && live) {
             CvHull cv;
-            cv.base = io.hull4 + ((size_t)patchIndex * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)io.hullStride;
+            cv.base = io.hull4 + row0;
             eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
         }
 #endif
@@ -697,8 +709,9 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
         if (MODE == 1) {
             // hull cache: the patch's control points as compact 16-byte rows (8 sectors per coordinate instead of 18
             // scattered ones for incoherent coordinates; broadcast reads for coherent ones)
+            int points;
             CvHull cv;
-            cv.base = io.hull4 + ((size_t)patchIndex * (size_t)io.hullTiles + (size_t)io.tile) * (size_t)io.hullStride;
+            cv.base = io.hull4 + hull_first_row(io.hullRowsBefore, arrayIndex, aw, patchIndex, io.hullTiles, io.tile, &points);
             eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
         } else {
             const int indexBase = ldg_i(aw + 3), stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
@@ -720,34 +733,29 @@ __global__ void __launch_bounds__(kPatchBlock) patch_kernel(PatchIO io) {
     patch_eval_coord<LT, ORDER, MODE>(io, i, i < io.n);
 }
 
-// Hull cache fill.  Block (32, 8): threadIdx.x = control point j of the patch, threadIdx.y = patch inside the block,
-// blockIdx.y = component tile.  The patch's control point j (through the index buffer) is copied into the 16-byte row
-// [patch][tile][j]; rows past the patch's own point count are left untouched (never read).
-__global__ void __launch_bounds__(256) hull_gather_kernel(const float *src, int srcStride, int L,
-                                                          const b200osd_patch_array *arrays, int numArrays,
-                                                          const int *indices, int numPatches, int hullStride,
-                                                          int hullTiles, float4 *hull4) {
-    const int j = threadIdx.x;
-    const int p = blockIdx.x * blockDim.y + threadIdx.y;
+// Hull cache fill, one launch per patch array: thread r copies control point r of the array's index list (coalesced
+// index reads, every lane busy whatever the patch size) into its 16-byte row of the per-array layout described at
+// PatchIO::hull4; blockIdx.y = component tile.
+__global__ void __launch_bounds__(256) hull_gather_kernel(const float *src, int srcStride, int L, const int *arrayIndices,
+                                                          long long rows, int stride, long long rowsBefore, int hullTiles,
+                                                          float4 *hull4) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int tile = blockIdx.y;
-    if (p >= numPatches || j >= hullStride) return;
-    int a = 0;
-    for (; a < numArrays; ++a) {
-        const int base = __ldg(&arrays[a].primitiveIdBase);
-        if (p >= base && p < base + __ldg(&arrays[a].numPatches)) break;
-    }
-    if (a == numArrays) return;
-    const int stride = __ldg(&arrays[a].stride);
-    if (j >= stride) return;
-    const int cv = __ldg(indices + __ldg(&arrays[a].indexBase) + stride * (p - __ldg(&arrays[a].primitiveIdBase)) + j);
-    const float *q = src + (size_t)cv * (size_t)srcStride + 4 * tile;
+    if (r >= rows) return;
+    const int cv = ld_stream_i1(arrayIndices + r);
+    const float *g = src + (size_t)cv * (size_t)srcStride + 4 * tile;
     const int rem = L - 4 * tile;
-    float4 r;
-    r.x = q[0];
-    r.y = rem > 1 ? q[1] : 0.0f;
-    r.z = rem > 2 ? q[2] : 0.0f;
-    r.w = rem > 3 ? q[3] : 0.0f;
-    hull4[((size_t)p * hullTiles + tile) * hullStride + j] = r;
+    float4 v;
+    v.x = __ldg(g);
+    v.y = rem > 1 ? __ldg(g + 1) : 0.0f;
+    v.z = rem > 2 ? __ldg(g + 2) : 0.0f;
+    v.w = rem > 3 ? __ldg(g + 3) : 0.0f;
+    size_t dst = (size_t)(rowsBefore + r);
+    if (hullTiles > 1) {
+        const long long q = r / stride;
+        dst = (size_t)(rowsBefore + q * stride) * (size_t)hullTiles + (size_t)tile * (size_t)stride + (size_t)(r - q * stride);
+    }
+    hull4[dst] = v;
 }
 #endif
 

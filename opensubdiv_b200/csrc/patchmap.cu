@@ -5,6 +5,7 @@
 // that feeds EvalPatches; see patchmap.cuh for the tree layout and the descent.
 #include "patchmap.cuh"
 
+#include <algorithm>
 #include <new>
 
 using namespace b200osd;
@@ -19,48 +20,56 @@ struct SampleStreams {
 
 constexpr int kFindBlock = 256;
 
-// One thread per sample.  The 20-byte records of a warp are staged in shared memory (row stride 5 words: bank
-// conflict free) and written as five fully coalesced 128-byte rows.
+// One thread per sample, grid-stride over a persistent grid (a few blocks per SM) so that the optional hit count costs
+// one atomic per block instead of one per warp.  The 20-byte records of a warp are staged in shared memory (row stride
+// 5 words: bank conflict free) and written as five fully coalesced 128-byte rows.
 __global__ void __launch_bounds__(kFindBlock) patch_map_find_kernel(PatchMapView m, SampleStreams in, int n,
                                                                      b200osd_patch_coord *out, int *numFound) {
     __shared__ int stage[kFindBlock / 32][32 * 5];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int blockHits;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i0 = i - lane;
-    if (i0 >= n) return;
-    int arrayIndex = -1, patchIndex = 0, vertIndex = 0;
-    float s = 0.0f, t = 0.0f;
-    bool hit = false;
-    if (i < n) {
-        const int face = ld_stream_i1(in.face + (size_t)i * in.faceStride);
-        s = ld_stream_f1(in.s + (size_t)i * in.sStride);
-        t = ld_stream_f1(in.t + (size_t)i * in.tStride);
-        const int p = patch_map_find(m, face, s, t);
-        if (p >= 0) {
-            const int2 h = __ldg(m.handles + p);
-            arrayIndex = h.x;
-            patchIndex = p;
-            vertIndex = h.y;
-            hit = true;
+    if (threadIdx.x == 0) blockHits = 0;
+    __syncthreads();
+    int hits = 0;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i - lane < n; i += step) {
+        const long long i0 = i - lane;
+        int arrayIndex = -1, patchIndex = 0, vertIndex = 0;
+        float s = 0.0f, t = 0.0f;
+        if (i < n) {
+            const int face = ld_stream_i1(in.face + (size_t)i * in.faceStride);
+            s = ld_stream_f1(in.s + (size_t)i * in.sStride);
+            t = ld_stream_f1(in.t + (size_t)i * in.tStride);
+            const int p = patch_map_find(m, face, s, t);
+            if (p >= 0) {
+                const int2 h = __ldg(m.handles + p);
+                arrayIndex = h.x;
+                patchIndex = p;
+                vertIndex = h.y;
+                ++hits;
+            }
+        }
+        int *st = stage[warp];
+        __syncwarp();
+        st[lane * 5 + 0] = arrayIndex;
+        st[lane * 5 + 1] = patchIndex;
+        st[lane * 5 + 2] = vertIndex;
+        st[lane * 5 + 3] = __float_as_int(s);
+        st[lane * 5 + 4] = __float_as_int(t);
+        __syncwarp();
+        const int words = (int)min(32LL, (long long)n - i0) * 5;
+        int *dst = reinterpret_cast<int *>(out + i0);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int e = q * 32 + lane;
+            if (e < words) dst[e] = st[e];
         }
     }
-    int *st = stage[warp];
-    st[lane * 5 + 0] = arrayIndex;
-    st[lane * 5 + 1] = patchIndex;
-    st[lane * 5 + 2] = vertIndex;
-    st[lane * 5 + 3] = __float_as_int(s);
-    st[lane * 5 + 4] = __float_as_int(t);
-    __syncwarp();
-    const int words = min(32, n - i0) * 5;
-    int *dst = reinterpret_cast<int *>(out + i0);
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int e = q * 32 + lane;
-        if (e < words) dst[e] = st[e];
-    }
     if (numFound) {
-        const unsigned hits = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0 && hits) atomicAdd(numFound, __popc(hits));
+        hits = __reduce_add_sync(0xffffffffu, hits);
+        if (lane == 0 && hits) atomicAdd(&blockHits, hits);
+        __syncthreads();
+        if (threadIdx.x == 0 && blockHits) atomicAdd(numFound, blockHits);
     }
 }
 
@@ -144,7 +153,7 @@ int b200osd_patch_map_find(const b200osd_patch_map *m, int numSamples, const int
     cudaStream_t st = (cudaStream_t)stream;
     if (numFound) B200_CUDA_TRY(cudaMemsetAsync(numFound, 0, sizeof(int), st));
     SampleStreams in{ptexFace, s, t, faceStride, sStride, tStride};
-    const int grid = (numSamples + kFindBlock - 1) / kFindBlock;
+    const int grid = std::min((numSamples + kFindBlock - 1) / kFindBlock, sm_count() * 8);
     patch_map_find_kernel<<<grid, kFindBlock, 0, st>>>(m->view, in, numSamples, outCoords, numFound);
     return check_launch("patch_map_find_kernel");
 }

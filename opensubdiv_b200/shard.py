@@ -11,7 +11,9 @@ control-point buffer.  So
     because no row spans ranks;
   * once per frame the deformed control points are replicated with ONE broadcast from the rank that produced them
     (`FrameBroadcaster`, double-buffered on a side stream so frame f+1 travels while frame f is evaluated);
-  * a consumer that wants the whole refined buffer on every rank calls `all_gather_rows` (optional, usually skipped).
+  * a consumer that wants the whole refined buffer on every rank calls `all_gather_rows` (optional, usually skipped);
+  * EvalPatches shards by PatchCoord range (`coord_ranges` / `coord_plan`): tables replicated, every rank refines the
+    broadcast control points itself and evaluates its own slice of the coordinates.
 
 Everything here is plumbing over torch.distributed: NCCL over NVLink on the GPU box, gloo in the CPU tests.
 """
@@ -73,6 +75,27 @@ class ShardPlan:
         """max shard cost / mean shard cost (1.0 = perfect)."""
         costs = [float(sizes[a:b].astype(np.int64).sum() + (b - a)) for a, b in self.ranges]
         return max(costs) / (sum(costs) / len(costs)) if sum(costs) else 1.0
+
+
+def coord_ranges(num_coords: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
+    """EvalPatches shards by PatchCoord range: `world` contiguous, near-equal ranges of [0, num_coords),
+    interior cuts on a multiple of `align` (a warp's worth of coordinates).  Every coordinate costs the same, so no
+    weighting is needed; the patch tables are replicated (small) and each rank refines the control points it needs
+    itself, so the only exchange is the same per-frame control-point broadcast the stencil path uses."""
+    n = int(num_coords)
+    world = max(world, 1)
+    cuts = [0]
+    for r in range(1, world):
+        c = n * r // world
+        if align > 1:
+            c = (c + align // 2) // align * align
+        cuts.append(min(max(c, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def coord_plan(num_coords: int, world: int, rank: int, align: int = 32) -> ShardPlan:
+    return ShardPlan(world, rank, coord_ranges(num_coords, world, align))
 
 
 def local_table(table, plan: ShardPlan):

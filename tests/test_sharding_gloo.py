@@ -101,3 +101,73 @@ def test_sharded_frames_equal_single_table(world, scheme):
     for rank, results, ranges in got:
         assert results == [True, True, True], (rank, results)
         assert ranges[0][0] == 0
+
+
+def test_coord_ranges_cover_and_align():
+    for n in (0, 1, 31, 32, 1000, 10_000_019):
+        for world in (1, 2, 3, 8):
+            r = shard.coord_ranges(n, world)
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            assert all(a % 32 == 0 for a, _ in r[1:] if a < n)
+            if n >= 32 * world * 8:
+                sizes = [b - a for a, b in r]
+                assert max(sizes) - min(sizes) <= 64
+
+
+def _patch_worker(rank, world, port, out_q):
+    """EvalPatches sharded by PatchCoord range: replicated tables, per-frame broadcast of the control points, every rank
+    refines locally and evaluates its own coordinates; gathered == single evaluation, bit for bit."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+    from tests.util import golden, table_from, triple_from
+    d = golden("patches_catmark_car")
+    st, vtx, coords = table_from(d, "st_"), triple_from(d, "vtx_"), d["coords"]
+    ncv, nst = st.num_control_verts, st.num_stencils
+    plan = shard.coord_plan(len(coords), world, rank)
+    mine = np.ascontiguousarray(coords[plan.start:plan.end])
+    bufs = [torch.zeros((ncv, 3)), torch.zeros((ncv, 3))]
+    bc = shard.FrameBroadcaster(bufs, root=0)
+    ok = []
+
+    def evaluate(cv, cs):
+        vb = np.zeros((ncv + nst, 3), np.float32)
+        vb[:ncv] = cv
+        assert oracle.eval_stencils(vb.reshape(-1), (0, 3, 3), [vb.reshape(-1)], [(ncv * 3, 3, 3)], st.sizes, st.offsets,
+                                    st.indices, [st.weights])
+        outs = [np.zeros((len(cs), 3), np.float32) for _ in range(3)]
+        if len(cs):
+            assert oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 3, cs,
+                                       vtx.arrays, vtx.indices, vtx.params)
+        return np.concatenate(outs, axis=1)
+
+    for frame in range(2):
+        if rank == 0:
+            bufs[frame % 2].copy_(torch.from_numpy(synth.deform(d["src0"], frame)))
+        bc.post(frame)
+        cv = bc.wait(frame).numpy()
+        local = evaluate(cv, mine)
+        bc.release(frame)
+        full = shard.all_gather_rows(torch.from_numpy(local), plan).numpy()
+        ok.append(bool(np.array_equal(full, evaluate(synth.deform(d["src0"], frame), coords))))
+    out_q.put((rank, ok, plan.ranges))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_patch_coords_equal_single_evaluation():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_patch_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, ranges in got:
+        assert ok == [True, True], (rank, ok)
+        assert ranges[0][0] == 0 and ranges[-1][1] > ranges[-1][0]
