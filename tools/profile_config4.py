@@ -29,6 +29,7 @@ face = torch.from_numpy(rng.integers(0, m.num_ptex_faces, n).astype(np.int32)).c
 s = torch.from_numpy(rng.random(n, dtype=np.float32)).cuda()
 t = torch.from_numpy(rng.random(n, dtype=np.float32)).cuda()
 pc = torch.zeros(n * 5, dtype=torch.int32, device="cuda")
+found = torch.zeros(1, dtype=torch.int32, device="cuda")
 assert pm.FindPatches(n, face, s, t, pc)
 out = torch.empty((n, 18), device="cuda")
 args = []
@@ -51,7 +52,8 @@ def timed(fn, iters=10):
 
 print(json.dumps({"patches": len(ptab.vertex.params), "stencils": nst, "coords": n,
                   "refine_ms": round(timed(lambda: osd.B200Evaluator.EvalStencils(vb, D(0, 3, 3), vb, D(ncv * 3, 3, 3), stbl)), 4),
-                  "find_ms": round(timed(lambda: pm.FindPatches(n, face, s, t, pc)), 4)}), flush=True)
+                  "find_ms": round(timed(lambda: pm.FindPatches(n, face, s, t, pc)), 4),
+                  "find_with_count_ms": round(timed(lambda: pm.FindPatches(n, face, s, t, pc, found)), 4)}), flush=True)
 for order in ("random", "sorted"):
     if order == "sorted":
         rec = pc.view(n, 5)
