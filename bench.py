@@ -206,6 +206,19 @@ def run_reference_arm(args):
     total = sum(step(args.warmup + k) for k in range(args.steps))
     value = rows * args.steps / total
     cores = probe[best]["cores"]
+    # the reference's OpenMP kernel does not scale linearly (false sharing on the result rows): thread sweep
+    sweep = {}
+    if oref.available() and oref.lib().ref_has_openmp():
+        s0 = frame_primvars(mesh, 1)
+        thr = 1
+        while thr <= threads:
+            oref.lib().ref_omp_set_threads(thr)
+            oref.eval_stencils(s0.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, 0, rows, impl="omp")
+            t0 = time.perf_counter()
+            oref.eval_stencils(s0.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, 0, rows, impl="omp")
+            sweep[str(thr)] = round(rows / (time.perf_counter() - t0) / 1e6, 2)
+            thr *= 2
+        oref.lib().ref_omp_set_threads(threads)
     line = {
         "impl": "reference", "metric": "refined_verts_per_sec_EvalStencils", "value": value, "unit": "verts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -215,7 +228,8 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "verts/s", "cores": cores, "kind": probe[best]["kind"],
                          "sample": f"{args.steps} steps of rows [0,{rows}) of {n} with Osd::{'OmpEvaluator' if best == 'omp' else 'CpuEvaluator'}"
                                    f" ({best}); probe of all evaluators: "
-                                   + ", ".join(f"{k}={v['verts_per_s'] / 1e6:.1f} Mverts/s@{v['cores']}thr" for k, v in probe.items())},
+                                   + ", ".join(f"{k}={v['verts_per_s'] / 1e6:.1f} Mverts/s@{v['cores']}thr" for k, v in probe.items()),
+                         "omp_thread_sweep_Mverts_per_s": sweep},
         "e2e": {"value": value, "unit": "verts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
