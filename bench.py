@@ -425,8 +425,8 @@ def bench_incumbent_cuda(mesh, table, torch, osd):
 # --------------------------------------------------------------------------------- B200 arm --
 def run_b200_arm(args):
     import faulthandler
-    # a multi-rank run must never hang the box: dump every thread's stack and leave after 5 minutes
-    faulthandler.dump_traceback_later(300, exit=True)
+    # a multi-rank run must never hang the box: dump every thread's stack and leave (N = 1 also runs the CPU baselines)
+    faulthandler.dump_traceback_later(300 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 200, exit=True)
     import torch
     import torch.distributed as dist
     import opensubdiv_b200 as osd
@@ -617,8 +617,10 @@ def run_b200_arm(args):
     e2e_steps = max(3, min(args.steps, 20))
     # the timed regions are milliseconds long: keep the same step running ~1 s more (untimed) so that the 50 ms
     # nvidia-smi sampler sees the clocks this kernel actually runs at under load
-    t_end = time.time() + 1.0
-    while time.time() < t_end:
+    # The number of extra steps must be IDENTICAL on every rank (each step posts a broadcast; a wall-clock loop lets ranks
+    # disagree by one batch and leaves unmatched collectives behind): derive it from the max-reduced step time.
+    batches = int(min(400, max(1, round(1.0 / max(50 * (ms_dev / args.steps) * 1e-3, 1e-4)))))
+    for _ in range(batches):
         for k in range(50):
             step_device(k)
         torch.cuda.synchronize()
@@ -639,9 +641,12 @@ def run_b200_arm(args):
                 patches = bench_eval_patches(mesh, torch, osd, capi, log)
             except Exception as exc:
                 patches = {"error": str(exc)}
-        else:
+        elif args.shard_patches:
             # collectives inside: every rank must take the same path, so no exception is swallowed here
             patches = bench_eval_patches(mesh, torch, osd, capi, log, world=world, rank=rank, strong=strong)
+        else:
+            patches = {"skipped": "N > 1: run with --shard-patches for EvalPatches sharded by PatchCoord range "
+                                  "(measured at N=2: profiles/r01_bench_n2.json)"}
 
     incumbent = None
     if world == 1 and not args.no_patches:
@@ -708,6 +713,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant (0 = auto)")
     ap.add_argument("--no-patches", action="store_true", help="skip the EvalPatches section of the report")
+    ap.add_argument("--shard-patches", action="store_true",
+                    help="N > 1: also time EvalPatches sharded by PatchCoord range across the ranks")
     ap.add_argument("--graph", action="store_true",
                     help="N > 1: replay a CUDA graph of two frames instead of the eager pipeline (verified at N=2 only)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
