@@ -75,3 +75,35 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower().replace("no reference code involved", ""), f
+
+
+def test_header_is_plain_c_and_cxx():
+    """The boundary is a C ABI: the header must compile as C99 and as C++ without anything else on the include path."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "b200osd_capi.h")
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not found")
+    for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):      # long long: C99 / C++11
+        subprocess.check_call(["gcc", "-x", lang, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", hdr])
+
+
+def test_patch_map_validation_without_a_gpu():
+    lib = capi.lib()
+    from tests.util import golden
+    d = golden("patchmap_catmark_cube")
+    arrays = np.ascontiguousarray(d["arrays"]).copy()
+    params = np.ascontiguousarray(d["params"])
+    # inconsistent table: rejected on the host before any device work, with a message
+    bad = arrays.copy()
+    bad["primitiveIdBase"][0] = 5
+    assert not lib.b200osd_patch_map_create(len(bad), bad.ctypes.data, len(params), params.ctypes.data, 0)
+    assert b"tile" in lib.b200osd_last_error()
+    assert lib.b200osd_patch_map_find(None, 4, None, 1, None, 1, None, 1, None, None, None) == capi.ERR_INVALID
+    import torch
+    if not torch.cuda.is_available():
+        # a valid table still cannot be created without a device: no host-side stand-in
+        assert not lib.b200osd_patch_map_create(len(arrays), arrays.ctypes.data, len(params), params.ctypes.data, 0)
+        with pytest.raises(osd.B200OsdError):
+            osd.B200PatchMap.Create(type("PT", (), dict(vertex=type("T", (), dict(arrays=arrays, params=params))(),
+                                                        varying=None, fvar=[]))(), patchesAreTriangular=False)
