@@ -88,6 +88,10 @@ def lib():
         L.oracle_patch_basis.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_float] + [vp] * 6
         L.oracle_version.restype = C.c_char_p
         L.oracle_set_abs_mode.argtypes = [C.c_int]
+        L.oracle_patch_map_create.restype = vp
+        L.oracle_patch_map_create.argtypes = [C.c_int, vp, C.c_int, vp, C.c_int]
+        L.oracle_patch_map_find.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.oracle_patch_map_free.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -145,3 +149,24 @@ class abs_mode:
 
     def __exit__(self, *exc):
         lib().oracle_set_abs_mode(0)
+
+
+COORD_DTYPE = np.dtype([("arrayIndex", "<i4"), ("patchIndex", "<i4"), ("vertIndex", "<i4"), ("s", "<f4"), ("t", "<f4")])
+
+
+def find_patches(arrays: np.ndarray, params: np.ndarray, triangular: bool, ptex_face, s, t) -> np.ndarray:
+    """Restates Far::PatchMap (far/patchMap.cpp:96-188) + FindPatch (far/patchMap.h:180-217) + Osd::PatchCoord
+    (osd/types.h:53-54): one 20-byte record per sample, arrayIndex = -1 where the reference returns a NULL handle."""
+    arrays, params = np.ascontiguousarray(arrays), np.ascontiguousarray(params)
+    f = np.ascontiguousarray(ptex_face, dtype=np.int32)
+    ss, tt = np.ascontiguousarray(s, dtype=np.float32), np.ascontiguousarray(t, dtype=np.float32)
+    out = np.zeros(len(f), COORD_DTYPE)
+    L = lib()
+    h = L.oracle_patch_map_create(len(arrays), _p(arrays) if len(arrays) else None, len(params),
+                                  _p(params) if len(params) else None, int(bool(triangular)))
+    assert h, "oracle_patch_map_create failed"
+    try:
+        L.oracle_patch_map_find(h, len(f), _p(f), _p(ss), _p(tt), _p(out))
+    finally:
+        L.oracle_patch_map_free(h)
+    return out

@@ -22,6 +22,7 @@
  *   osd/cpuEvaluator.cpp:157-381  EvalPatches (value, +D1, +D1+D2) and BufferAdapter :127-154
  *   osd/patchBasisTypes.h:241-426 patch descriptor ids, PatchParam bit fields, (s,t) normalisation
  *   osd/patchBasis.h:53-1610      the six bases, boundary folding, derivative scaling
+ *   far/patchMap.h:127-217, far/patchMap.cpp:96-188   PatchMap construction and FindPatch (sample location)
  */
 #include <math.h>
 #include <stddef.h>
@@ -123,6 +124,7 @@ int oracle_eval_stencils(int nw,
  *   field0 = faceId:28 | transition:4
  *   field1 = depth:4 | nonquad:1 | regular:1 | unused:1 | boundary:5 | v:10 | u:10   (LSB first)
  * -----------------------------------------------------------------------------------------------*/
+static unsigned pp_face(unsigned f0) { return f0 & 0x0fffffffu; }
 static int pp_depth(unsigned f1)    { return (int)(f1 & 0xfu); }
 static int pp_nonquad(unsigned f1)  { return (int)((f1 >> 4) & 1u); }
 static int pp_regular(unsigned f1)  { return (int)((f1 >> 5) & 1u); }
@@ -650,6 +652,180 @@ int oracle_eval_patches(int nw,
         }
     }
     return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch map: (ptexFace, s, t) -> PatchCoord.  far/patchMap.cpp:96-188 (construction), far/patchMap.h:127-217
+ * (quadrant selection and the descent), osd/types.h:53-54 (PatchCoord from a handle).
+ *
+ * A quadtree per ptex face.  Every patch is filed under the sequence of quadrants that leads from the face to the
+ * sub-domain its PatchParam (depth, u, v) describes; a query halves the domain level by level, in DOUBLE exactly as
+ * the reference does (u >= median ? u -= median ...), until it reaches a leaf.  This restatement keeps the
+ * reference's formulation on purpose: the product descends on integer bits instead, so agreement between the two is
+ * a real check.  Quad domains use the PatchParam's (u,v) bits for the path; triangular domains locate an interior
+ * point of the sub-triangle and track the 180-degree rotation of centre triangles.
+ * Child word: 0 = unset, (index << 2) | 1 = inner node, (index << 2) | 3 = leaf (patch index).
+ * Build with stdlib only; single-threaded; not reentrant on one map.
+ * -----------------------------------------------------------------------------------------------*/
+#include <stdlib.h>
+
+typedef struct { unsigned child[4]; } oracle_qnode;
+typedef struct {
+    oracle_qnode *nodes;
+    int numNodes, capNodes;
+    int *arrayOf, *vertOf;            /* per patch: handle.arrayIndex, handle.vertIndex (patchIndex = position) */
+    int numPatches, minFace, maxFace, maxDepth, triangular;
+} oracle_patch_map;
+
+static int pm_type_points(int type)   /* far/patchDescriptor.h: control points per patch type */
+{
+    switch (type) {
+        case 1: return 1;  case 2: return 2;  case 3: return 4;  case 4: return 3;  case 5: return 12;
+        case 6: return 16; case 7: return 4;  case 8: return 4;  case 9: return 20; case 10: return 18;
+        default: return 0;
+    }
+}
+
+/* far/patchMap.h:146-175: quadrant of (u,v) in a triangle whose half-size is `median`; moves (u,v) into it */
+static int pm_tri_quadrant(double median, double *u, double *v, int *rotated)
+{
+    if (!*rotated) {
+        if (*u >= median) { *u -= median; return 1; }
+        if (*v >= median) { *v -= median; return 2; }
+        if ((*u + *v) >= median) { *rotated = 1; return 3; }
+        return 0;
+    }
+    if (*u < median) { *v -= median; return 1; }
+    if (*v < median) { *u -= median; return 2; }
+    *u -= median;
+    *v -= median;
+    if ((*u + *v) < median) { *rotated = 0; return 3; }
+    return 0;
+}
+
+static int pm_new_node(oracle_patch_map *m)
+{
+    if (m->numNodes == m->capNodes) {
+        int cap = m->capNodes ? 2 * m->capNodes : 64;
+        oracle_qnode *n = (oracle_qnode *)realloc(m->nodes, (size_t)cap * sizeof(oracle_qnode));
+        if (!n) return -1;
+        m->nodes = n;
+        m->capNodes = cap;
+    }
+    memset(&m->nodes[m->numNodes], 0, sizeof(oracle_qnode));
+    return m->numNodes++;
+}
+
+void oracle_patch_map_free(void *h)
+{
+    oracle_patch_map *m = (oracle_patch_map *)h;
+    if (!m) return;
+    free(m->nodes); free(m->arrayOf); free(m->vertOf); free(m);
+}
+
+void *oracle_patch_map_create(int numArrays, const oracle_array *arrays, int numPatches, const oracle_param *params,
+                              int patchesAreTriangular)
+{
+    oracle_patch_map *m = (oracle_patch_map *)calloc(1, sizeof(oracle_patch_map));
+    int a, j, h = 0, p, faces;
+    if (!m) return NULL;
+    m->triangular = patchesAreTriangular ? 1 : 0;
+    m->minFace = 0; m->maxFace = -1;
+    m->numPatches = numPatches;
+    if (numPatches <= 0) return m;
+    m->arrayOf = (int *)malloc((size_t)numPatches * sizeof(int));
+    m->vertOf = (int *)malloc((size_t)numPatches * sizeof(int));
+    if (!m->arrayOf || !m->vertOf) { oracle_patch_map_free(m); return NULL; }
+    /* handles, array by array (far/patchMap.cpp:113-135) */
+    for (a = 0; a < numArrays; ++a) {
+        int pts = pm_type_points(arrays[a].desc);
+        for (j = 0; j < arrays[a].numPatches && h < numPatches; ++j, ++h) { m->arrayOf[h] = a; m->vertOf[h] = j * pts; }
+    }
+    m->minFace = m->maxFace = (int)pp_face(params[0].field0);
+    for (p = 1; p < numPatches; ++p) {
+        int f = (int)pp_face(params[p].field0);
+        if (f < m->minFace) m->minFace = f;
+        if (f > m->maxFace) m->maxFace = f;
+    }
+    faces = m->maxFace - m->minFace + 1;
+    for (p = 0; p < faces; ++p) if (pm_new_node(m) < 0) { oracle_patch_map_free(m); return NULL; }
+
+    for (p = 0; p < numPatches; ++p) {
+        unsigned f1 = params[p].field1;
+        int depth = pp_depth(f1), root = pp_nonquad(f1) ? 1 : 0, level;
+        int node = (int)pp_face(params[p].field0) - m->minFace;
+        if (depth > m->maxDepth) m->maxDepth = depth;
+        if (depth == root) {                               /* the whole face: all four quadrants are this leaf */
+            for (j = 0; j < 4; ++j) m->nodes[node].child[j] = ((unsigned)p << 2) | 3u;
+            continue;
+        }
+        {
+            int pu = pp_u(f1), pv = pp_v(f1), rotated = 0;
+            double u = 0.25, v = 0.25, median = 0.5;
+            if (m->triangular) {                           /* interior point of the sub-triangle, far/patchParam.h:310-323 */
+                double frac = (double)(1.0f / (float)(1 << (depth - root)));
+                if ((pu + pv) >= (1 << depth)) { u = ((double)((1 << depth) - pu) - u) * frac; v = ((double)((1 << depth) - pv) - v) * frac; }
+                else { u = (u + (double)pu) * frac; v = (v + (double)pv) * frac; }
+            }
+            for (level = root + 1; level <= depth; ++level, median *= 0.5) {
+                int quadrant = m->triangular ? pm_tri_quadrant(median, &u, &v, &rotated)
+                                             : ((((pv >> (depth - level)) & 1) << 1) | ((pu >> (depth - level)) & 1));
+                if (level == depth) {
+                    m->nodes[node].child[quadrant] = ((unsigned)p << 2) | 3u;
+                } else if (m->nodes[node].child[quadrant] & 1u) {
+                    node = (int)(m->nodes[node].child[quadrant] >> 2);
+                } else {
+                    int fresh = pm_new_node(m);
+                    if (fresh < 0) { oracle_patch_map_free(m); return NULL; }
+                    m->nodes[node].child[quadrant] = ((unsigned)fresh << 2) | 1u;
+                    node = fresh;
+                }
+            }
+        }
+    }
+    return m;
+}
+
+/* n queries; out[i] = PatchCoord{handle, s, t}; a face outside the map or a hole gives arrayIndex = -1 (the reference
+ * returns a NULL handle).  Returns the number of hits. */
+int oracle_patch_map_find(const void *h, int n, const int *ptexFace, const float *s, const float *t, oracle_coord *out)
+{
+    const oracle_patch_map *m = (const oracle_patch_map *)h;
+    int i, hits = 0;
+    for (i = 0; i < n; ++i) {
+        oracle_coord c;
+        memset(&c, 0, sizeof(c));
+        c.arrayIndex = -1; c.s = s[i]; c.t = t[i];
+        if (m && ptexFace[i] >= m->minFace && ptexFace[i] <= m->maxFace) {
+            const oracle_qnode *node = &m->nodes[ptexFace[i] - m->minFace];
+            if (node->child[0] & 1u) {                     /* a root has all quadrants set or none (hole) */
+                double u = (double)s[i], v = (double)t[i], median = 0.5;
+                int rotated = 0, depth;
+                for (depth = 0; depth <= m->maxDepth; ++depth, median *= 0.5) {
+                    int quadrant;
+                    unsigned w;
+                    if (m->triangular) quadrant = pm_tri_quadrant(median, &u, &v, &rotated);
+                    else {
+                        int uh = (u >= median), vh = (v >= median);
+                        if (uh) u -= median;
+                        if (vh) v -= median;
+                        quadrant = (vh << 1) | uh;
+                    }
+                    w = node->child[quadrant];
+                    if ((w & 3u) == 3u) {
+                        int p = (int)(w >> 2);
+                        c.arrayIndex = m->arrayOf[p]; c.patchIndex = p; c.vertIndex = m->vertOf[p];
+                        ++hits;
+                        break;
+                    }
+                    if (!(w & 1u)) break;
+                    node = &m->nodes[w >> 2];
+                }
+            }
+        }
+        out[i] = c;
+    }
+    return hits;
 }
 
 const char *oracle_version(void) { return "osd_oracle 1 (restates OpenSubdiv 3.6.0 osd/cpuKernel.cpp, cpuEvaluator.cpp, patchBasis.h)"; }

@@ -48,6 +48,9 @@ def test_find_patches_vs_reference_golden(name):
         got, found, _ = find_on_device(pm, d["face"], d["s"], d["t"], aos)
         assert_same_coords(got, want, d["s"], d["t"], f"{name} aos={aos}")
         assert found == int((want["arrayIndex"] >= 0).sum())
+        from oracle import oracle
+        assert_same_coords(got, oracle.find_patches(d["arrays"], d["params"], bool(d["triangular"]), d["face"], d["s"], d["t"]),
+                           d["s"], d["t"], f"{name} vs oracle")
         miss = want["arrayIndex"] < 0          # misses keep their (s, t)
         assert np.array_equal(got["s"][miss], d["s"][miss]) and np.array_equal(got["t"][miss], d["t"][miss])
     assert pm.GetNumPatches() == len(d["params"]) and pm.GetMaxDepth() == int((d["params"]["field1"] & 0xf).max())

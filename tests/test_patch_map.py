@@ -36,6 +36,15 @@ def assert_same_coords(got, want, s, t, what):
 
 
 @pytest.mark.parametrize("name", golden_names("patchmap_"))
+def test_oracle_find_patches_vs_golden(name):
+    """The C oracle's reference-style restatement (double-precision halving) against Far::PatchMap's recorded answers."""
+    from oracle import oracle
+    d = golden(name)
+    got = oracle.find_patches(d["arrays"], d["params"], bool(d["triangular"]), d["face"], d["s"], d["t"])
+    assert_same_coords(got, d["coords"], d["s"], d["t"], f"oracle {name}")
+
+
+@pytest.mark.parametrize("name", golden_names("patchmap_"))
 def test_patch_map_descent_vs_golden(name):
     L = _lib()
     d = golden(name)
@@ -86,4 +95,7 @@ def test_patch_map_descent_vs_reference(shape, level, endcap):
         hits, got, _ = emu_find(L, pt.vertex.arrays, pt.vertex.params, m.reg_face_size == 3, face, s, t)
         assert_same_coords(got, want, s, t, f"{shape} L{level} sc={single_crease}")
         assert hits == int((want["arrayIndex"] >= 0).sum())
+        from oracle import oracle                         # pins the oracle's restatement against the live reference too
+        assert_same_coords(oracle.find_patches(pt.vertex.arrays, pt.vertex.params, m.reg_face_size == 3, face, s, t), want, s, t,
+                           f"oracle {shape} L{level} sc={single_crease}")
         m = ref.Mesh.from_shape(shape)                    # a refiner can be refined only once
