@@ -141,3 +141,53 @@ def test_limit_stencils_agree_with_patch_evaluation():
                                pt.vertex.arrays, pt.vertex.indices, pt.vertex.params)
     for a, b, tol in zip(lim, ev, (2e-6, 2e-5, 2e-5, 5e-4, 5e-4, 5e-4)):
         assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+ALL_SHAPES = ref.shape_names() if ref.available() else []
+
+
+@pytest.mark.parametrize("shape", ALL_SHAPES)
+def test_every_regression_shape_stencils_and_patches(shape):
+    """The reference's osd_regression walks its whole shape list (regression/osd_regression/main.cpp:250-330); so does
+    the oracle: uniform level-2 stencils bit-identical, adaptive level-3 EvalPatches (Gregory end caps, 6 outputs) within
+    the Gregory-triangle 3e-7, FindPatch bit-identical."""
+    m = ref.Mesh.from_shape(shape).refine_uniform(2)
+    st = m.stencil_table(intermediate_levels=True)
+    pos = m.positions
+    a, b = np.zeros((st.num_stencils, 3), np.float32), np.zeros((st.num_stencils, 3), np.float32)
+    assert ref.eval_stencils(pos.reshape(-1), (0, 3, 3), [a.reshape(-1)], [(0, 3, 3)], st)
+    assert oracle.eval_stencils(pos.reshape(-1), (0, 3, 3), [b.reshape(-1)], [(0, 3, 3)], st.sizes, st.offsets, st.indices,
+                                [st.weights])
+    assert np.array_equal(a.view(np.int32), b.view(np.int32)), shape
+    if shape.startswith("bilinear"):
+        return
+    m = ref.Mesh.from_shape(shape)
+    pt = m.patch_table(3, end_cap="gregory", inf_sharp=True, legacy_sharp_corner=False)
+    st = m.stencil_table(intermediate_levels=True, patch_table=pt)
+    ncv, n = st.num_control_verts, st.num_stencils
+    vb = np.zeros((ncv + n, 3), np.float32)
+    vb[:ncv] = m.positions
+    assert ref.eval_stencils(vb.reshape(-1), (0, 3, 3), [vb.reshape(-1)], [(ncv * 3, 3, 3)], st)
+    rng = np.random.default_rng(3)
+    k = 1500
+    face = rng.integers(0, m.num_ptex_faces, k).astype(np.int32)
+    s, t = rng.random(k, dtype=np.float32), rng.random(k, dtype=np.float32)
+    if m.reg_face_size == 3:
+        flip = s + t >= 1
+        s, t = np.where(flip, 1 - s, s).astype(np.float32), np.where(flip, 1 - t, t).astype(np.float32)
+    want = m.find_patches(pt, face, s, t)
+    got = oracle.find_patches(pt.vertex.arrays, pt.vertex.params, m.reg_face_size == 3, face, s, t)
+    hit = want["arrayIndex"] >= 0
+    assert np.array_equal(got["arrayIndex"] >= 0, hit)
+    assert np.array_equal(got[hit].view(np.int32), np.ascontiguousarray(want[hit]).view(np.int32)), shape
+    pc = np.ascontiguousarray(want[hit])
+    x = [np.zeros((len(pc), 3), np.float32) for _ in range(6)]
+    y = [np.zeros((len(pc), 3), np.float32) for _ in range(6)]
+    z = [np.zeros((len(pc), 3), np.float32) for _ in range(6)]
+    assert ref.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in x], [(0, 3, 3)] * 6, pc, pt.vertex)
+    args = (pc, pt.vertex.arrays, pt.vertex.indices, pt.vertex.params)
+    assert oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in y], [(0, 3, 3)] * 6, *args)
+    with oracle.abs_mode(2):
+        oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in z], [(0, 3, 3)] * 6, *args)
+    for xx, yy, zz in zip(x, y, z):
+        assert_close(yy, xx, zz, shape, tol=3e-7)
