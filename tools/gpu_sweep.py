@@ -89,11 +89,11 @@ def patch_case(name, mesh, n, iters):
             for k in range(nout):
                 args += [out, D(3 * k, 3, 3 * nout)]
             alg = n * (20 + nout * 12)
-            for pv in (0, 1, 2):
+            for pv in (0, 1, 2, 3, 4):
                 capi.lib().b200osd_set_patch_variant(pv)
                 ms = time_calls(lambda: osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None), iters)
                 capi.lib().b200osd_set_patch_variant(0)
-                emit(case=name, kind="patch", path={0: "auto", 1: "index_buffer", 2: "hull_cache"}[pv], coords=n, order=order_name,
+                emit(case=name, kind="patch", path={0: "auto", 1: "index_buffer", 2: "hull_cache_direct", 3: "hull_cache_staged", 4: "hull_cache_per_warp"}[pv], coords=n, order=order_name,
                      nout=nout, ms=ms, gpts_per_s=n / ms / 1e6, alg_MB=alg / 1e6, alg_GBps=alg / ms / 1e6,
                      frac_of_measured_peak=alg / ms / 1e6 / PEAK)
         # face-varying-like: 2 floats through the linear (QUADS) varying patches, value only
