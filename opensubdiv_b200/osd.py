@@ -416,6 +416,8 @@ class B200Evaluator:
                        numPatchCoords, patchCoords, patchTable [, instance [, deviceContext]])   (osd/cudaEvaluator.h:502-677)"""
         outs, rest = B200Evaluator._parse_patch_args(args)
         n, coords, pt = rest[0], rest[1], rest[2]
+        if deviceContext is None and len(rest) > 4:        # (..., patchTable, instance, deviceContext) given positionally
+            deviceContext = rest[4]
         if isinstance(pt, B200PatchTable):
             return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 0, deviceContext)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetPatchArrayBuffer(),
@@ -426,6 +428,8 @@ class B200Evaluator:
         """Same kernel on the varying triple + vertex PatchParams (osd/cudaEvaluator.h:857-1036)."""
         outs, rest = B200Evaluator._parse_patch_args(args)
         n, coords, pt = rest[0], rest[1], rest[2]
+        if deviceContext is None and len(rest) > 4:
+            deviceContext = rest[4]
         if isinstance(pt, B200PatchTable):
             return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 1, deviceContext)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetVaryingPatchArrayBuffer(),
@@ -436,7 +440,11 @@ class B200Evaluator:
         """Same kernel on the face-varying triple of `fvarChannel` (osd/cudaEvaluator.h:1068-1254)."""
         outs, rest = B200Evaluator._parse_patch_args(args)
         n, coords, pt = rest[0], rest[1], rest[2]
-        ch = rest[3] if len(rest) > 3 and isinstance(rest[3], (int, np.integer)) else 0
+        has_ch = len(rest) > 3 and isinstance(rest[3], (int, np.integer)) and not isinstance(rest[3], bool)
+        ch = int(rest[3]) if has_ch else 0
+        ctx_pos = 5 if has_ch else 4                       # (..., patchTable [, fvarChannel], instance, deviceContext)
+        if deviceContext is None and len(rest) > ctx_pos:
+            deviceContext = rest[ctx_pos]
         if isinstance(pt, B200PatchTable):
             return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 2 + ch, deviceContext)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetFVarPatchArrayBuffer(ch),

@@ -107,3 +107,28 @@ def test_patch_map_validation_without_a_gpu():
         with pytest.raises(osd.B200OsdError):
             osd.B200PatchMap.Create(type("PT", (), dict(vertex=type("T", (), dict(arrays=arrays, params=params))(),
                                                         varying=None, fvar=[]))(), patchesAreTriangular=False)
+
+
+def test_positional_device_context_reaches_the_c_abi(monkeypatch):
+    """EvalPatches*(..., patchTable [, fvarChannel], instance, deviceContext): the trailing positional deviceContext of
+    the reference signatures (osd/cudaEvaluator.h:502-523, 1068-1090) must select the stream, like the keyword form."""
+    seen = {}
+
+    def fake(src, desc, outs, n, coords, pt, which, ctx):
+        seen["which"], seen["ctx"] = which, ctx
+        return True
+    monkeypatch.setattr(osd.B200Evaluator, "_eval_patch_table", staticmethod(fake))
+    pt = osd.B200PatchTable(None)
+    D = osd.BufferDescriptor
+    assert osd.B200Evaluator.EvalPatches(1, D(0, 3, 3), 2, D(0, 3, 3), 10, 3, pt, None, 77)
+    assert seen == {"which": 0, "ctx": 77}
+    assert osd.B200Evaluator.EvalPatches(1, D(0, 3, 3), 2, D(0, 3, 3), 10, 3, pt, None)
+    assert seen == {"which": 0, "ctx": None}
+    assert osd.B200Evaluator.EvalPatchesVarying(1, D(0, 3, 3), 2, D(0, 3, 3), 10, 3, pt, None, deviceContext=5)
+    assert seen == {"which": 1, "ctx": 5}
+    assert osd.B200Evaluator.EvalPatchesFaceVarying(1, D(0, 2, 2), 2, D(0, 2, 2), 10, 3, pt, 1, None, 9)
+    assert seen == {"which": 3, "ctx": 9}
+    assert osd.B200Evaluator.EvalPatchesFaceVarying(1, D(0, 2, 2), 2, D(0, 2, 2), 10, 3, pt, 0, None)
+    assert seen == {"which": 2, "ctx": None}
+    assert osd.B200Evaluator.EvalPatchesFaceVarying(1, D(0, 2, 2), 2, D(0, 2, 2), 10, 3, pt)
+    assert seen == {"which": 2, "ctx": None}
