@@ -69,6 +69,7 @@ typedef struct b200osd_stencil_table b200osd_stencil_table;
 typedef struct b200osd_patch_table   b200osd_patch_table;
 typedef struct b200osd_patch_map     b200osd_patch_map;
 typedef struct b200osd_vertex_buffer b200osd_vertex_buffer;
+typedef struct b200osd_frame         b200osd_frame;
 
 /* ---- library -------------------------------------------------------------------------------- */
 B200OSD_API const char *b200osd_version(void);
@@ -188,6 +189,19 @@ B200OSD_API int  b200osd_patch_map_info(const b200osd_patch_map *m, int info[6])
 B200OSD_API int  b200osd_patch_map_find(const b200osd_patch_map *m, int numSamples,
         const int *ptexFace, int faceStride, const float *s, int sStride, const float *t, int tStride,
         b200osd_patch_coord *outCoords, int *numFound, void *stream);
+
+/* ---- frame capture ------------------------------------------------------------------------
+ * A frame object owns a CUDA stream.  Calls issued with that stream between _begin and _end -- EvalStencils,
+ * FindPatches, EvalPatches*, vertex-buffer updates from pinned memory -- are recorded instead of executed; _launch
+ * replays them as one graph launch on the same stream.  Run the frame once eagerly first: first calls allocate
+ * (hull cache, basis tables), which cannot be recorded.  No reference counterpart. */
+B200OSD_API b200osd_frame *b200osd_frame_create(void);
+B200OSD_API void  b200osd_frame_destroy(b200osd_frame *f);
+B200OSD_API void *b200osd_frame_stream(const b200osd_frame *f);     /* the cudaStream_t to pass as `stream` */
+B200OSD_API int   b200osd_frame_begin(b200osd_frame *f);
+B200OSD_API int   b200osd_frame_end(b200osd_frame *f);
+B200OSD_API int   b200osd_frame_launch(b200osd_frame *f);           /* asynchronous */
+B200OSD_API int   b200osd_frame_synchronize(b200osd_frame *f);
 
 /* ---- tuning / introspection (used by bench.py and the tests; not needed by clients) ---------- */
 /* Selects the stencil kernel variant used by b200osd_stencil_table_eval: 0 = auto. */

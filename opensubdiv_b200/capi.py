@@ -30,6 +30,8 @@ SYMBOLS = [
     "b200osd_eval_patches", "b200osd_patch_table_eval", "b200osd_set_patch_variant", "b200osd_get_patch_variant",
     "b200osd_set_stencil_variant", "b200osd_get_stencil_variant",
     "b200osd_patch_map_create", "b200osd_patch_map_destroy", "b200osd_patch_map_info", "b200osd_patch_map_find",
+    "b200osd_frame_create", "b200osd_frame_destroy", "b200osd_frame_stream", "b200osd_frame_begin", "b200osd_frame_end",
+    "b200osd_frame_launch", "b200osd_frame_synchronize",
 ]
 
 
@@ -94,6 +96,12 @@ def lib():
     L.b200osd_patch_map_info.argtypes = [vp, vp]
     L.b200osd_patch_map_find.argtypes = [vp, i, vp, i, vp, i, vp, i, vp, vp, vp]
     L.b200osd_set_stencil_variant.argtypes = [i]
+    L.b200osd_frame_create.restype = vp
+    L.b200osd_frame_destroy.argtypes = [vp]
+    L.b200osd_frame_stream.restype = vp
+    L.b200osd_frame_stream.argtypes = [vp]
+    for fn in (L.b200osd_frame_begin, L.b200osd_frame_end, L.b200osd_frame_launch, L.b200osd_frame_synchronize):
+        fn.argtypes = [vp]
     _lib = L
     return L
 

@@ -310,6 +310,43 @@ class B200PatchMap:
         return capi.check(rc, "B200PatchMap::FindPatches")
 
 
+class B200FrameGraph:
+    """A whole evaluation frame recorded once and replayed as ONE launch (no reference counterpart).
+
+        frame = B200FrameGraph.Create()
+        run_frame(deviceContext=frame)          # once eagerly on the frame's stream: first calls allocate
+        frame.Synchronize()
+        frame.Begin(); run_frame(deviceContext=frame); frame.End()
+        ... update the control points in place ...; frame.Launch(); frame.Synchronize()
+
+    Pass the object itself as `deviceContext` to the B200 classes (it exposes `.cuda_stream`)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def Create(cls) -> Optional["B200FrameGraph"]:
+        h = capi.lib().b200osd_frame_create()
+        return cls(h) if h else None
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b200osd_frame_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def cuda_stream(self) -> int:
+        return capi.lib().b200osd_frame_stream(self._h) or 0
+
+    def Begin(self) -> bool: return capi.check(capi.lib().b200osd_frame_begin(self._h), "B200FrameGraph::Begin")
+    def End(self) -> bool: return capi.check(capi.lib().b200osd_frame_end(self._h), "B200FrameGraph::End")
+    def Launch(self) -> bool: return capi.check(capi.lib().b200osd_frame_launch(self._h), "B200FrameGraph::Launch")
+    def Synchronize(self) -> bool: return capi.check(capi.lib().b200osd_frame_synchronize(self._h), "B200FrameGraph::Synchronize")
+
+
 def _is_desc(d) -> bool:
     return isinstance(d, BufferDescriptor) or (isinstance(d, (tuple, list)) and len(d) == 3
                                                and all(isinstance(v, (int, np.integer)) for v in d))
