@@ -191,3 +191,32 @@ def test_every_regression_shape_stencils_and_patches(shape):
         oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in z], [(0, 3, 3)] * 6, *args)
     for xx, yy, zz in zip(x, y, z):
         assert_close(yy, xx, zz, shape, tol=3e-7)
+
+
+@pytest.mark.parametrize("shape,level", [("catmark_car", 2), ("loop_icosahedron", 3), ("catmark_gregory_test2", 3),
+                                         ("catmark_edgecorner", 3), ("loop_cube_creases0", 2)])
+def test_far_basis_twin_equals_the_osd_mirror(shape, level):
+    """Far::PatchTable::EvaluateBasis (far/patchTable.cpp:581-625, what LimitStencilTableFactory uses) and the Osd mirror
+    the evaluators use (osd/patchBasis.h, restated by the oracle) are the same functions: bit-identical weights, except
+    the oracle's Bernstein-form Gregory triangle (3e-7)."""
+    m = ref.Mesh.from_shape(shape)
+    pt = m.patch_table(level, end_cap="gregory", inf_sharp=True, legacy_sharp_corner=False)
+    rng = np.random.default_rng(0)
+    k = 1500
+    face = rng.integers(0, m.num_ptex_faces, k).astype(np.int32)
+    s, t = rng.random(k, dtype=np.float32), rng.random(k, dtype=np.float32)
+    if m.reg_face_size == 3:
+        flip = s + t >= 1
+        s, t = np.where(flip, 1 - s, s).astype(np.float32), np.where(flip, 1 - t, t).astype(np.float32)
+    pc = m.find_patches(pt, face, s, t)
+    pc = np.ascontiguousarray(pc[pc["arrayIndex"] >= 0])
+    W = ref.far_basis(pt, pc)
+    for i, c in enumerate(pc):
+        a, p = pt.vertex.arrays[c["arrayIndex"]], pt.vertex.params[c["patchIndex"]]
+        typ = int(a["regDesc"] if (int(p["field1"]) >> 5) & 1 else a["desc"])
+        n, w = oracle.patch_basis(typ, int(p["field0"]), int(p["field1"]), float(c["s"]), float(c["t"]))
+        for q in range(6):
+            if typ == 10:
+                assert np.abs(W[q][i][:n] - w[q][:n]).max() <= 3e-7 * max(np.abs(W[q][i][:n]).max(), 1e-30)
+            else:
+                assert np.array_equal(W[q][i][:n].view(np.int32), w[q][:n].view(np.int32)), (shape, i, q)
