@@ -132,3 +132,27 @@ def test_positional_device_context_reaches_the_c_abi(monkeypatch):
     assert seen == {"which": 2, "ctx": None}
     assert osd.B200Evaluator.EvalPatchesFaceVarying(1, D(0, 2, 2), 2, D(0, 2, 2), 10, 3, pt)
     assert seen == {"which": 2, "ctx": None}
+
+
+def test_ctypes_prototypes_match_the_header_arity():
+    """Every declared entry point that takes arguments must have ctypes argtypes of the same arity (a missing prototype
+    would pass 64-bit pointers as C ints)."""
+    header = open(os.path.join(ROOT, "include", "b200osd_capi.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    lib = capi.lib()
+    checked = 0
+    for m in re.finditer(r"\b(b200osd_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        name, params = m.group(1), " ".join(m.group(2).split())
+        arity = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(lib, name)
+        if arity == 0:
+            continue
+        assert fn.argtypes is not None, f"{name}: no ctypes prototype"
+        assert len(fn.argtypes) == arity, f"{name}: header declares {arity} parameters, ctypes has {len(fn.argtypes)}"
+        checked += 1
+    assert checked >= 30
+    # ... and every entry point returning a pointer or a long long must declare it (default restype is a C int)
+    for m in re.finditer(r"B200OSD_API\s+([^;(]*?)\b(b200osd_[a-z_0-9]+)\s*\(", header):
+        rtype, name = " ".join(m.group(1).split()), m.group(2)
+        if "*" in rtype or "long long" in rtype:
+            assert getattr(lib, name).restype is not C.c_int, f"{name} returns '{rtype}' but ctypes restype is int"
