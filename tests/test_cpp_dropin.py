@@ -29,3 +29,14 @@ def test_dropin_program_matches_cpu_backend_on_gpu():
     print(r.stdout)
     assert r.returncode == 0, r.stdout
     assert "DROP-IN TEST PASSED" in r.stdout
+
+
+def test_every_cpp_header_is_self_sufficient():
+    """Each include/b200osd/*.h must compile on its own against the unmodified reference headers."""
+    import glob
+    import shutil
+    if not os.path.isdir("/root/reference/opensubdiv") or not shutil.which("g++"):
+        pytest.skip("reference sources or g++ not present")
+    for h in sorted(glob.glob(os.path.join(ROOT, "include", "b200osd", "*.h"))):
+        subprocess.check_call(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-Werror", "-x", "c++", "-I/root/reference",
+                               "-I" + os.path.join(ROOT, "include"), h])
