@@ -92,6 +92,15 @@ def lib():
         L.oracle_patch_map_create.argtypes = [C.c_int, vp, C.c_int, vp, C.c_int]
         L.oracle_patch_map_find.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.oracle_patch_map_free.argtypes = [vp]
+        L.oracle_limit_table_create.restype = vp
+        L.oracle_limit_table_create.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp]
+        L.oracle_limit_table_free.argtypes = [vp]
+        L.oracle_limit_table_num_stencils.argtypes = [vp]
+        L.oracle_limit_table_num_elements.argtypes = [vp]
+        L.oracle_limit_table_ints.restype = C.POINTER(C.c_int)
+        L.oracle_limit_table_ints.argtypes = [vp, C.c_int]
+        L.oracle_limit_table_weights.restype = C.POINTER(C.c_float)
+        L.oracle_limit_table_weights.argtypes = [vp, C.c_int]
         _lib = L
     return _lib
 
@@ -170,3 +179,35 @@ def find_patches(arrays: np.ndarray, params: np.ndarray, triangular: bool, ptex_
     finally:
         L.oracle_patch_map_free(h)
     return out
+
+
+def limit_stencil_table(arrays, patch_indices, params, triangular, num_control_verts, cv_sizes, cv_offsets, cv_indices,
+                        cv_weights, ptex_face, s, t, nw: int = 6):
+    """Restates the per-location loop of Far::LimitStencilTableFactory::Create (far/stencilTableFactory.cpp:559-662)
+    and StencilBuilder's merge (far/stencilBuilder.cpp): returns (sizes, offsets, indices, [weights x nw]) for the
+    locations FindPatch resolves, in order.  cv_* = the refined + local-point stencil table WITHOUT control-vertex rows
+    (row r belongs to vertex num_control_verts + r), feature-adaptive refinement."""
+    arrays, params = np.ascontiguousarray(arrays), np.ascontiguousarray(params)
+    pix = np.ascontiguousarray(patch_indices, dtype=np.int32)
+    cs, co, ci = (np.ascontiguousarray(x, dtype=np.int32) for x in (cv_sizes, cv_offsets, cv_indices))
+    cw = np.ascontiguousarray(cv_weights, dtype=np.float32)
+    f = np.ascontiguousarray(ptex_face, dtype=np.int32)
+    ss, tt = np.ascontiguousarray(s, dtype=np.float32), np.ascontiguousarray(t, dtype=np.float32)
+    L = lib()
+    pm = L.oracle_patch_map_create(len(arrays), _p(arrays), len(params), _p(params), int(bool(triangular)))
+    assert pm
+    h = None
+    try:
+        h = L.oracle_limit_table_create(nw, pm, _p(arrays), _p(pix), _p(params), int(num_control_verts), _p(cs), _p(co), _p(ci),
+                                        _p(cw), len(f), _p(f), _p(ss), _p(tt))
+        assert h, "oracle_limit_table_create failed"
+        n, ne = L.oracle_limit_table_num_stencils(h), L.oracle_limit_table_num_elements(h)
+        ints = [np.ctypeslib.as_array(L.oracle_limit_table_ints(h, k), shape=(m,)).copy() if m else np.zeros(0, np.int32)
+                for k, m in ((0, n), (1, n), (2, ne))]
+        ws = [np.ctypeslib.as_array(L.oracle_limit_table_weights(h, k), shape=(ne,)).copy() if ne else np.zeros(0, np.float32)
+              for k in range(nw)]
+        return ints[0], ints[1], ints[2], ws
+    finally:
+        if h:
+            L.oracle_limit_table_free(h)
+        L.oracle_patch_map_free(pm)

@@ -828,4 +828,120 @@ int oracle_patch_map_find(const void *h, int n, const int *ptexFace, const float
     return hits;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Limit stencil table construction.  far/stencilTableFactory.cpp:559-662 (the per-location loop of
+ * LimitStencilTableFactory::Create) + far/stencilBuilder.cpp:154-186,318-384,520-596 (AddWithWeight / merge).
+ *
+ * For every location that FindPatch resolves: the patch's basis weights (value, 1st, 2nd derivatives) are combined
+ * with the stencils of the patch's control points -- a control point below numControlVerts is the control vertex
+ * itself (a unit stencil), any other is row (cv - numControlVerts) of the refined + local-point stencil table, which
+ * is already expressed in control vertices.  Each source element (index i, weight w != 0) contributes
+ * (wP*w, wDs*w, ...) to the entry of control vertex i, entries are created in order of first appearance and later
+ * contributions are ADDED to them, in source order -- which fixes both the element order of the result and the
+ * floating-point summation order.  A control point whose nw basis weights are all zero is skipped.  Locations outside
+ * every patch produce no stencil.  Adaptive (feature-adaptive) tables only.
+ * This is the checker for SURVEY.md 8f-4 (table construction on the device); no product code uses it.
+ * -----------------------------------------------------------------------------------------------*/
+typedef struct {
+    int n;                 /* stencils (= resolved locations) */
+    int ne, cap;           /* elements */
+    int nw;
+    int *sizes, *offsets, *indices;
+    float *w[6];
+} oracle_limit_table;
+
+void oracle_limit_table_free(void *h)
+{
+    oracle_limit_table *t = (oracle_limit_table *)h;
+    int k;
+    if (!t) return;
+    free(t->sizes); free(t->offsets); free(t->indices);
+    for (k = 0; k < 6; ++k) free(t->w[k]);
+    free(t);
+}
+
+#ifndef ORACLE_F64
+static int lt_grow(oracle_limit_table *t)
+{
+    int k, cap = t->cap ? 2 * t->cap : 4096;
+    int *ix = (int *)realloc(t->indices, (size_t)cap * sizeof(int));
+    if (!ix) return 0;
+    t->indices = ix;
+    for (k = 0; k < t->nw; ++k) {
+        float *w = (float *)realloc(t->w[k], (size_t)cap * sizeof(float));
+        if (!w) return 0;
+        t->w[k] = w;
+    }
+    t->cap = cap;
+    return 1;
+}
+
+void *oracle_limit_table_create(int nw, const void *patchMap,
+                                const oracle_array *arrays, const int *patchIndices, const oracle_param *params,
+                                int numControlVerts, const int *cvSizes, const int *cvOffsets, const int *cvIndices,
+                                const float *cvWeights,
+                                int numLocations, const int *ptexFace, const float *s, const float *t)
+{
+    oracle_limit_table *T = (oracle_limit_table *)calloc(1, sizeof(oracle_limit_table));
+    oracle_coord c;
+    float wb[6][20];
+    int loc, j, k, q, e;
+    if (!T || (nw != 1 && nw != 3 && nw != 6)) { free(T); return NULL; }
+    T->nw = nw;
+    T->sizes = (int *)malloc((size_t)(numLocations > 0 ? numLocations : 1) * sizeof(int));
+    T->offsets = (int *)malloc((size_t)(numLocations > 0 ? numLocations : 1) * sizeof(int));
+    if (!T->sizes || !T->offsets) { oracle_limit_table_free(T); return NULL; }
+    for (loc = 0; loc < numLocations; ++loc) {
+        const oracle_array *a;
+        const oracle_param *p;
+        const int *cvs;
+        int type, np, start;
+        if (oracle_patch_map_find(patchMap, 1, &ptexFace[loc], &s[loc], &t[loc], &c) != 1) continue;
+        a = &arrays[c.arrayIndex];
+        p = &params[c.patchIndex];
+        type = pp_regular(p->field1) ? a->regDesc : a->desc;
+        cvs = patchIndices + a->indexBase + a->stride * (c.patchIndex - a->primitiveIdBase);
+        np = oracle_patch_basis(type, p->field0, p->field1, s[loc], t[loc], wb[0], nw >= 3 ? wb[1] : NULL,
+                                nw >= 3 ? wb[2] : NULL, nw >= 6 ? wb[3] : NULL, nw >= 6 ? wb[4] : NULL, nw >= 6 ? wb[5] : NULL);
+        start = T->ne;
+        for (k = 0; k < np; ++k) {
+            const int cv = cvs[k];
+            const int unit = cv < numControlVerts;
+            const int sz = unit ? 1 : cvSizes[cv - numControlVerts];
+            const int off = unit ? 0 : cvOffsets[cv - numControlVerts];
+            int allZero = 1;
+            for (q = 0; q < nw; ++q) if (wb[q][k] != 0.0f) allZero = 0;
+            if (allZero) continue;
+            for (j = 0; j < sz; ++j) {
+                const float w = unit ? 1.0f : cvWeights[off + j];
+                const int src = unit ? cv : cvIndices[off + j];
+                if (w == 0.0f) continue;
+                for (e = start; e < T->ne; ++e) if (T->indices[e] == src) break;
+                if (e == T->ne) {
+                    if (T->ne == T->cap && !lt_grow(T)) { oracle_limit_table_free(T); return NULL; }
+                    T->indices[e] = src;
+                    for (q = 0; q < nw; ++q) T->w[q][e] = wb[q][k] * w;
+                    T->ne++;
+                } else {
+                    for (q = 0; q < nw; ++q) T->w[q][e] += wb[q][k] * w;
+                }
+            }
+        }
+        T->sizes[T->n] = T->ne - start;
+        T->offsets[T->n] = start;
+        T->n++;
+    }
+    return T;
+}
+#endif
+
+int oracle_limit_table_num_stencils(const void *h) { return ((const oracle_limit_table *)h)->n; }
+int oracle_limit_table_num_elements(const void *h) { return ((const oracle_limit_table *)h)->ne; }
+const int *oracle_limit_table_ints(const void *h, int which)   /* 0 sizes, 1 offsets, 2 indices */
+{
+    const oracle_limit_table *t = (const oracle_limit_table *)h;
+    return which == 0 ? t->sizes : (which == 1 ? t->offsets : t->indices);
+}
+const float *oracle_limit_table_weights(const void *h, int k) { return ((const oracle_limit_table *)h)->w[k]; }
+
 const char *oracle_version(void) { return "osd_oracle 1 (restates OpenSubdiv 3.6.0 osd/cpuKernel.cpp, cpuEvaluator.cpp, patchBasis.h)"; }
