@@ -166,9 +166,10 @@ B200OSD_API int b200osd_eval_patches(
 /* EvalPatches through the table handle (fast path): which = 0 vertex, 1 varying, 2+c face-varying channel c.
  * Same contract as b200osd_eval_patches; additionally, when numPatchCoords >= 4 x the number of patches, every
  * patch's control points are first gathered once into a compact per-patch hull cache owned by the table.
- * Because that cache is per-call state of the TABLE, calls on one table handle must be ordered: issue them on one
- * stream (what the reference does implicitly -- everything runs on the legacy default stream), or order the streams
- * yourself; for evaluation on several streams at once create one table object per stream.  Handles are not
+ * That cache is per-call state of the TABLE: calls on one stream are ordered by the stream (what the reference gets
+ * implicitly -- everything runs on the legacy default stream); when consecutive calls on one table use different
+ * streams the library waits for the device in between (inside a stream capture it cannot: order the streams
+ * yourself).  For concurrent evaluation on several streams create one table object per stream.  Handles are not
  * thread-safe. */
 B200OSD_API int b200osd_patch_table_eval(const b200osd_patch_table *t, int which,
         const float *src, const int srcDesc[3],

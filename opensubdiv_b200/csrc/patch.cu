@@ -222,6 +222,8 @@ struct b200osd_patch_table {
     // hull cache scratch (per-call contents; grown on demand)
     float4 *d_hull = nullptr;
     size_t hullCap = 0;
+    bool hullUsed = false;               // the cache is per-call state: remember which stream last wrote / read it
+    cudaStream_t hullStream = nullptr;
     std::vector<std::vector<b200osd_patch_array>> hostArrays;   // host copies of the PatchArray descriptors
 };
 
@@ -291,6 +293,18 @@ int b200osd_patch_table_eval(const b200osd_patch_table *tc, int which, const flo
             }
         }
         if (useHull) {
+            // The cache is shared by every call on this table.  Calls on ONE stream are ordered by the stream; when the
+            // stream changes, the previous call may still be reading the cache, so wait for the device once (the
+            // reference never meets this: all its launches go to the legacy default stream).  While the new stream is
+            // being captured no synchronisation is possible -- ordering is then the caller's job (b200osd_capi.h).
+            cudaStream_t cur = (cudaStream_t)stream;
+            if (t->hullUsed && t->hullStream != cur) {
+                cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+                if (cudaStreamIsCapturing(cur, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+                if (cs == cudaStreamCaptureStatusNone) B200_CUDA_TRY(cudaDeviceSynchronize());
+            }
+            t->hullUsed = true;
+            t->hullStream = cur;
             hull.hull4 = t->d_hull;
             hull.rowsBefore = tr.rowsBefore;
             hull.hostArrays = t->hostArrays[which].data();
