@@ -15,6 +15,11 @@ One step = one frame = one EvalStencils pass over the whole table.
   cpu_baseline  the reference's own Osd::CpuEvaluator / OmpEvaluator (oracle/_ref, compiled in place from
              /root/reference) on this box's host cores, same table, bounded number of frames; falls back to the
              C oracle port when the reference build is absent
+  eval_patches  (N = 1; N > 1 with --shard-patches) the second half of the metric: limit pts/s of EvalPatches with 1st +
+             2nd derivatives on 10 M PatchCoords (random and patch-sorted), FindPatches on a real adaptive table, and the
+             reference's CPU evaluators on a sample of the same coordinates
+  incumbent_cuda  (N = 1) the reference's own CUDA kernels (osd/cudaKernel.cu compiled for sm_100a under oracle/_ref) on
+             the same device buffers: a reported baseline like cpu_baseline
 
 Multi-GPU (N > 1): weak scaling.  The scene is N such meshes; rank r owns the stencil rows of mesh r (row-range
 sharding, tables pre-sharded, no collective on the table side); every frame rank 0's deformed control points of the
