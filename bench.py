@@ -430,8 +430,9 @@ def bench_incumbent_cuda(mesh, table, torch, osd):
 # --------------------------------------------------------------------------------- B200 arm --
 def run_b200_arm(args):
     import faulthandler
-    # a multi-rank run must never hang the box: dump every thread's stack and leave (N = 1 also runs the CPU baselines)
-    faulthandler.dump_traceback_later(300 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 200, exit=True)
+    # a run must never hang the box: dump every thread's stack and leave after 5 minutes (a first `import torch` on a
+    # fresh box alone can take a minute)
+    faulthandler.dump_traceback_later(300, exit=True)
     import torch
     import torch.distributed as dist
     import opensubdiv_b200 as osd
