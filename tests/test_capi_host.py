@@ -156,3 +156,23 @@ def test_ctypes_prototypes_match_the_header_arity():
         rtype, name = " ".join(m.group(1).split()), m.group(2)
         if "*" in rtype or "long long" in rtype:
             assert getattr(lib, name).restype is not C.c_int, f"{name} returns '{rtype}' but ctypes restype is int"
+
+
+def test_plain_c_example_builds_against_the_abi(tmp_path):
+    """examples/c_abi_example.c: a C99 client of the library (compiles with -pedantic, links, and without a device fails
+    loudly instead of computing on the host)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not found")
+    exe = str(tmp_path / "c_abi_example")
+    libdir = os.path.join(ROOT, "opensubdiv_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_example.c"), "-L", libdir, "-lb200osd",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    import torch
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "refined[4] = 0.5 0.5 0.125" in r.stdout, r.stdout
+    else:
+        assert r.returncode == 2 and "no CUDA device" in r.stdout
