@@ -25,7 +25,7 @@ int main(void)
     b200osd_vertex_buffer *vb = b200osd_vertex_buffer_create(3, 4 + 5);
     b200osd_stencil_table *st;
     if (!vb) { printf("no CUDA device: %s\n", b200osd_last_error()); return 2; }   /* no CPU fallback */
-    st = b200osd_stencil_table_create(5, sizes, offsets, indices, weights, NULL, NULL, NULL, NULL, NULL, 0);
+    st = b200osd_stencil_table_create(5, 4, sizes, offsets, indices, weights, NULL, NULL, NULL, NULL, NULL, 0);
     if (!st) { printf("table: %s\n", b200osd_last_error()); return 1; }
 
     b200osd_vertex_buffer_update(vb, &cage[0][0], 0, 4, NULL);

@@ -16,6 +16,11 @@
 // kernels.  Differences from CudaEvaluator, all deliberate: a length mismatch returns false like Osd::CpuEvaluator
 // (cpuEvaluator.cpp:47; the CUDA backend does not check), and `deviceContext` may point at a B200DeviceContext to
 // choose a stream.
+//
+// The evaluator is also INSTANTIATABLE (osd/mesh.h:305-409, modelled on osd/glComputeEvaluator.h:98-128): Create()
+// returns an instance that Osd::EvaluatorCacheT can cache per descriptor set and that every static Eval* accepts as
+// `instance`.  What an instance caches is the grouping of one PatchCoord set by patch (BindPatchCoords): EvalPatches*
+// calls on that same coordinate buffer then skip the per-call device sort.
 #ifndef B200OSD_EVALUATOR_H
 #define B200OSD_EVALUATOR_H
 
@@ -34,6 +39,45 @@ namespace Osd {
 
 class B200Evaluator {
 public:
+    // ------------------------------------------------------------------------------------- instantiation ----
+    typedef bool Instantiatable;
+
+    static B200Evaluator *Create(BufferDescriptor const &srcDesc, BufferDescriptor const &dstDesc,
+                                 BufferDescriptor const &duDesc, BufferDescriptor const &dvDesc,
+                                 void *deviceContext = NULL) {
+        return Create(srcDesc, dstDesc, duDesc, dvDesc, BufferDescriptor(), BufferDescriptor(), BufferDescriptor(), deviceContext);
+    }
+    static B200Evaluator *Create(BufferDescriptor const &srcDesc, BufferDescriptor const &dstDesc,
+                                 BufferDescriptor const &duDesc, BufferDescriptor const &dvDesc,
+                                 BufferDescriptor const &duuDesc, BufferDescriptor const &duvDesc,
+                                 BufferDescriptor const &dvvDesc, void *deviceContext = NULL) {
+        (void)srcDesc; (void)dstDesc; (void)duDesc; (void)dvDesc; (void)duuDesc; (void)duvDesc; (void)dvvDesc; (void)deviceContext;
+        // nothing to compile per descriptor set (the kernels are specialised at build time); the instance exists for
+        // its cached PatchCoord grouping
+        return new B200Evaluator();
+    }
+    ~B200Evaluator() { b200osd_patch_plan_destroy(_plan); }
+
+    /// Groups the `numPatchCoords` coordinates of `patchCoords` by patch on the device and keeps the grouping: every
+    /// later EvalPatches / EvalPatchesVarying / EvalPatchesFaceVarying call given this instance, this table and this
+    /// same coordinate buffer reuses it.  Call again after the coordinates change.  (Scratch is allocated here, when the
+    /// table changes or the set outgrows the previous one -- never inside an Eval call.)
+    template <typename PATCHCOORD_BUFFER>
+    bool BindPatchCoords(int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, B200PatchTable const *patchTable,
+                         void *deviceContext = NULL) {
+        if (!patchTable) return false;
+        if (!_plan || _planTable != patchTable->GetHandle() || b200osd_patch_plan_capacity(_plan) < numPatchCoords) {
+            b200osd_patch_plan_destroy(_plan);
+            _plan = b200osd_patch_plan_create(patchTable->GetHandle(), numPatchCoords);
+            _planTable = patchTable->GetHandle();
+            if (!_plan) return false;
+        }
+        _planCoords = (const void *)patchCoords->BindCudaBuffer();
+        _planCount = numPatchCoords;
+        return b200osd_patch_plan_bin(_plan, numPatchCoords, (const b200osd_patch_coord *)_planCoords,
+                                      B200StreamOf(deviceContext)) == B200OSD_OK;
+    }
+
     // ------------------------------------------------------------------------------------------ stencils ----
     template <typename SRC_BUFFER, typename DST_BUFFER, typename STENCIL_TABLE>
     static bool EvalStencils(SRC_BUFFER *srcBuffer, BufferDescriptor const &srcDesc,
@@ -144,11 +188,10 @@ public:
                             DST_BUFFER *dstBuffer, BufferDescriptor const &dstDesc,
                             int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                             B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[1] = { dstBuffer->BindCudaBuffer() };
         BufferDescriptor descs[1] = { dstDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), instance, deviceContext);
     }
 
     template <typename SRC_BUFFER, typename DST_BUFFER, typename PATCHCOORD_BUFFER, typename PATCH_TABLE>
@@ -158,11 +201,10 @@ public:
                             DST_BUFFER *dvBuffer, BufferDescriptor const &dvDesc,
                             int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                             B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[3] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[3] = { dstDesc, duDesc, dvDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), instance, deviceContext);
     }
 
     template <typename SRC_BUFFER, typename DST_BUFFER, typename PATCHCOORD_BUFFER, typename PATCH_TABLE>
@@ -175,12 +217,11 @@ public:
                             DST_BUFFER *dvvBuffer, BufferDescriptor const &dvvDesc,
                             int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                             B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[6] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer(),
                            duuBuffer->BindCudaBuffer(), duvBuffer->BindCudaBuffer(), dvvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[6] = { dstDesc, duDesc, dvDesc, duuDesc, duvDesc, dvvDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VERTEX(patchTable), instance, deviceContext);
     }
 
     // raw forms
@@ -227,11 +268,10 @@ public:
                                    DST_BUFFER *dstBuffer, BufferDescriptor const &dstDesc,
                                    int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                                    B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[1] = { dstBuffer->BindCudaBuffer() };
         BufferDescriptor descs[1] = { dstDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), instance, deviceContext);
     }
 
     template <typename SRC_BUFFER, typename DST_BUFFER, typename PATCHCOORD_BUFFER, typename PATCH_TABLE>
@@ -241,11 +281,10 @@ public:
                                    DST_BUFFER *dvBuffer, BufferDescriptor const &dvDesc,
                                    int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                                    B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[3] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[3] = { dstDesc, duDesc, dvDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), instance, deviceContext);
     }
 
     template <typename SRC_BUFFER, typename DST_BUFFER, typename PATCHCOORD_BUFFER, typename PATCH_TABLE>
@@ -258,12 +297,11 @@ public:
                                    DST_BUFFER *dvvBuffer, BufferDescriptor const &dvvDesc,
                                    int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                                    B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[6] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer(),
                            duuBuffer->BindCudaBuffer(), duvBuffer->BindCudaBuffer(), dvvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[6] = { dstDesc, duDesc, dvDesc, duuDesc, duvDesc, dvvDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_VARYING(patchTable), instance, deviceContext);
     }
 
     // face-varying: the channel's own (arrays, indices, params) triple (cudaEvaluator.h:1068-1090)
@@ -272,11 +310,10 @@ public:
                                        DST_BUFFER *dstBuffer, BufferDescriptor const &dstDesc,
                                        int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                                        int fvarChannel, B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[1] = { dstBuffer->BindCudaBuffer() };
         BufferDescriptor descs[1] = { dstDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 1, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), instance, deviceContext);
     }
 
     template <typename SRC_BUFFER, typename DST_BUFFER, typename PATCHCOORD_BUFFER, typename PATCH_TABLE>
@@ -286,11 +323,10 @@ public:
                                        DST_BUFFER *dvBuffer, BufferDescriptor const &dvDesc,
                                        int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                                        int fvarChannel, B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[3] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[3] = { dstDesc, duDesc, dvDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 3, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), instance, deviceContext);
     }
 
     template <typename SRC_BUFFER, typename DST_BUFFER, typename PATCHCOORD_BUFFER, typename PATCH_TABLE>
@@ -303,12 +339,11 @@ public:
                                        DST_BUFFER *dvvBuffer, BufferDescriptor const &dvvDesc,
                                        int numPatchCoords, PATCHCOORD_BUFFER *patchCoords, PATCH_TABLE *patchTable,
                                        int fvarChannel, B200Evaluator const *instance, void *deviceContext = NULL) {
-        (void)instance;
         float *dsts[6] = { dstBuffer->BindCudaBuffer(), duBuffer->BindCudaBuffer(), dvBuffer->BindCudaBuffer(),
                            duuBuffer->BindCudaBuffer(), duvBuffer->BindCudaBuffer(), dvvBuffer->BindCudaBuffer() };
         BufferDescriptor descs[6] = { dstDesc, duDesc, dvDesc, duuDesc, duvDesc, dvvDesc };
         return evalPatchTable(srcBuffer->BindCudaBuffer(), srcDesc, 6, dsts, descs, numPatchCoords,
-                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), deviceContext);
+                           patchCoords->BindCudaBuffer(), B200OSD_PATCH_TRIPLE_FVAR(patchTable, fvarChannel), instance, deviceContext);
     }
 
 #undef B200OSD_PATCH_TRIPLE_VERTEX
@@ -358,28 +393,33 @@ private:
                                      B200StreamOf(deviceContext)) == B200OSD_OK;
     }
 
-    // fast path: B200PatchTable owns the handle (and the hull cache)
+    // fast path: B200PatchTable owns the handle; an instance whose bound coordinate set matches supplies the cached grouping
     static bool evalPatchTable(const float *src, BufferDescriptor const &srcDesc, int n, float *const *dsts,
                                BufferDescriptor const *descs, int numPatchCoords, const void *patchCoords,
-                               B200PatchTable const *table, int which, void *deviceContext) {
+                               B200PatchTable const *table, int which, B200Evaluator const *instance, void *deviceContext) {
         int sd[3] = { srcDesc.offset, srcDesc.length, srcDesc.stride };
         int dd[6][3];
         flatten(n, descs, dd);
+        if (instance && instance->_plan && instance->_planTable == table->GetHandle() &&
+            instance->_planCoords == patchCoords && instance->_planCount == numPatchCoords)
+            return b200osd_patch_plan_eval(instance->_plan, which, src, sd, n, dsts, dd, numPatchCoords,
+                                           (const b200osd_patch_coord *)patchCoords, B200StreamOf(deviceContext)) == B200OSD_OK;
         return b200osd_patch_table_eval(table->GetHandle(), which, src, sd, n, dsts, dd, numPatchCoords,
                                         (const b200osd_patch_coord *)patchCoords, B200StreamOf(deviceContext)) == B200OSD_OK;
     }
     static bool evalPatchTable(const float *src, BufferDescriptor const &srcDesc, int n, float *const *dsts,
                                BufferDescriptor const *descs, int numPatchCoords, const void *patchCoords,
-                               B200PatchTable *table, int which, void *deviceContext) {
+                               B200PatchTable *table, int which, B200Evaluator const *instance, void *deviceContext) {
         return evalPatchTable(src, srcDesc, n, dsts, descs, numPatchCoords, patchCoords,
-                              static_cast<B200PatchTable const *>(table), which, deviceContext);
+                              static_cast<B200PatchTable const *>(table), which, instance, deviceContext);
     }
 
     // any other patch-table type with the reference's device-pointer accessors (e.g. Osd::CudaPatchTable)
     template <typename PATCH_TABLE>
     static bool evalPatchTable(const float *src, BufferDescriptor const &srcDesc, int n, float *const *dsts,
                                BufferDescriptor const *descs, int numPatchCoords, const void *patchCoords,
-                               PATCH_TABLE *table, int which, void *deviceContext) {
+                               PATCH_TABLE *table, int which, B200Evaluator const *instance, void *deviceContext) {
+        (void)instance;
         if (which == 0)
             return evalPatches(src, srcDesc, n, dsts, descs, numPatchCoords, patchCoords, table->GetPatchArrayBuffer(),
                                table->GetPatchIndexBuffer(), table->GetPatchParamBuffer(), deviceContext);
@@ -400,6 +440,14 @@ private:
                                     (const b200osd_patch_array *)patchArrays, (const int *)patchIndices,
                                     (const b200osd_patch_param *)patchParams, B200StreamOf(deviceContext)) == B200OSD_OK;
     }
+
+    B200Evaluator() : _plan(NULL), _planTable(NULL), _planCoords(NULL), _planCount(0) {}
+    B200Evaluator(B200Evaluator const &);
+    B200Evaluator &operator=(B200Evaluator const &);
+    b200osd_patch_plan *_plan;
+    b200osd_patch_table const *_planTable;
+    const void *_planCoords;
+    int _planCount;
 };
 
 }  // namespace Osd

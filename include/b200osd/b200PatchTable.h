@@ -52,7 +52,7 @@ public:
     void *GetFVarPatchIndexBuffer(int fvarChannel = 0) const { return buf(2 + fvarChannel, 1); }
     void *GetFVarPatchParamBuffer(int fvarChannel = 0) const { return buf(2 + fvarChannel, 2); }
 
-    /// The C-ABI handle for B200Evaluator's fast path (the table may stage per-patch control hulls).
+    /// The C-ABI handle for B200Evaluator's fast path (immutable after Create: shareable across threads and streams).
     b200osd_patch_table const *GetHandle() const { return _h; }
 
 private:

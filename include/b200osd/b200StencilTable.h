@@ -19,13 +19,13 @@ public:
     static B200StencilTable *Create(Far::StencilTable const *stencilTable, void *deviceContext = NULL) {
         (void)deviceContext;
         if (!stencilTable) return NULL;
-        return wrap(make(stencilTable->GetNumStencils(), stencilTable->GetSizes(), stencilTable->GetOffsets(),
+        return wrap(make(stencilTable->GetNumStencils(), stencilTable->GetNumControlVertices(), stencilTable->GetSizes(), stencilTable->GetOffsets(),
                          stencilTable->GetControlIndices(), stencilTable->GetWeights(), NULL, NULL, NULL, NULL, NULL));
     }
     static B200StencilTable *Create(Far::LimitStencilTable const *t, void *deviceContext = NULL) {
         (void)deviceContext;
         if (!t) return NULL;
-        return wrap(make(t->GetNumStencils(), t->GetSizes(), t->GetOffsets(), t->GetControlIndices(), t->GetWeights(),
+        return wrap(make(t->GetNumStencils(), t->GetNumControlVertices(), t->GetSizes(), t->GetOffsets(), t->GetControlIndices(), t->GetWeights(),
                          &t->GetDuWeights(), &t->GetDvWeights(), &t->GetDuuWeights(), &t->GetDuvWeights(), &t->GetDvvWeights()));
     }
     ~B200StencilTable() { b200osd_stencil_table_destroy(_h); }
@@ -46,12 +46,13 @@ public:
     b200osd_stencil_table const *GetHandle() const { return _h; }
 
 private:
-    static b200osd_stencil_table *make(int n, std::vector<int> const &sizes, std::vector<Far::Index> const &offsets,
+    static b200osd_stencil_table *make(int n, int numControlVertices, std::vector<int> const &sizes, std::vector<Far::Index> const &offsets,
                                        std::vector<Far::Index> const &indices, std::vector<float> const &weights,
                                        std::vector<float> const *du, std::vector<float> const *dv,
                                        std::vector<float> const *duu, std::vector<float> const *duv,
                                        std::vector<float> const *dvv) {
-        return b200osd_stencil_table_create(n, data(sizes), data(offsets), data(indices), data(weights),
+        // the real control-vertex count lets the library recognise unfactorized tables (rows referencing earlier rows)
+        return b200osd_stencil_table_create(n, numControlVertices, data(sizes), data(offsets), data(indices), data(weights),
                                             du ? data(*du) : NULL, dv ? data(*dv) : NULL, duu ? data(*duu) : NULL,
                                             duv ? data(*duv) : NULL, dvv ? data(*dvv) : NULL, 0);
     }

@@ -15,13 +15,20 @@ namespace Osd {
 
 /// Optional device context for every B200 class: the opaque `void *deviceContext` argument of the Osd
 /// templates may point at one of these to select a CUDA stream (NULL = legacy default stream, as the reference).
+/// The struct is TAGGED: Osd::CudaEvaluator ignores deviceContext altogether, so an existing client may hand over
+/// a pointer to something else (e.g. through Osd::Mesh's DEVICE_CONTEXT); anything whose first word is not the tag is
+/// treated like NULL instead of being read as a stream.
 struct B200DeviceContext {
+    static const unsigned kTag = 0xB2000D5Cu;
+    unsigned tag;
     void *stream;   // cudaStream_t
-    B200DeviceContext(void *s = NULL) : stream(s) {}
+    B200DeviceContext(void *s = NULL) : tag(kTag), stream(s) {}
 };
 
 inline void *B200StreamOf(void *deviceContext) {
-    return deviceContext ? static_cast<B200DeviceContext *>(deviceContext)->stream : NULL;
+    if (!deviceContext) return NULL;
+    B200DeviceContext const *c = static_cast<B200DeviceContext const *>(deviceContext);
+    return c->tag == B200DeviceContext::kTag ? c->stream : NULL;
 }
 
 class B200VertexBuffer {

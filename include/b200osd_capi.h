@@ -99,16 +99,24 @@ B200OSD_API int    b200osd_vertex_buffer_read(b200osd_vertex_buffer *vb, float *
  * The table keeps (a) verbatim device copies (the Get*Buffer() pointers of the reference class) and
  * (b) a B200-specific bucketed copy (rows sorted by size inside windows, 32-row slices stored
  * element-major for coalesced 128-bit loads) used by b200osd_stencil_table_eval.
+ * numControlVertices: Far::StencilTable::GetNumControlVertices() (far/stencilTable.h:161), or <= 0 for "1 + largest
+ * index".  Given the real count, a table built with factorizeIntermediateLevels = false (far/stencilTableFactory.h:66-75:
+ * rows of later levels reference EARLIER ROWS through indices >= numControlVertices, far tutorial 4_3) is recognised and
+ * evaluated one dependency level after the other on the stream -- with src and dst aliased as in Osd::Mesh::Refine
+ * (osd/mesh.h:505-519: row r is vertex numControlVertices + r of the same buffer) that reproduces the sequential CPU
+ * evaluator; a table whose rows are not in dependency order is rejected (NULL, B200OSD_ERR_UNSUPPORTED in the message).
  * flags: bit 0 = skip the bucketed copy (verbatim only); bit 1 = also order rows by locality inside a window;
  * bit 2 = keep 32-bit indices even when a slice fits 16-bit offsets; bit 3 = sort each row's elements by control index
  * (same terms, different summation order than the reference: opt-in).                                       */
 B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
-        int numStencils, const int *sizes, const int *offsets, const int *indices, const float *weights,
+        int numStencils, int numControlVertices,
+        const int *sizes, const int *offsets, const int *indices, const float *weights,
         const float *duWeights, const float *dvWeights,
         const float *duuWeights, const float *duvWeights, const float *dvvWeights, int flags);
 B200OSD_API void b200osd_stencil_table_destroy(b200osd_stencil_table *t);
 B200OSD_API int  b200osd_stencil_table_num_stencils(const b200osd_stencil_table *t);
-B200OSD_API int  b200osd_stencil_table_num_control_vertices(const b200osd_stencil_table *t); /* 1 + max index */
+B200OSD_API int  b200osd_stencil_table_num_control_vertices(const b200osd_stencil_table *t);
+B200OSD_API int  b200osd_stencil_table_num_levels(const b200osd_stencil_table *t);   /* 1 unless the table is unfactorized */
 B200OSD_API long long b200osd_stencil_table_num_elements(const b200osd_stencil_table *t);
 /* which: 0 sizes, 1 offsets, 2 indices, 3 weights, 4 du, 5 dv, 6 duu, 7 duv, 8 dvv -> device pointer or NULL */
 B200OSD_API const void *b200osd_stencil_table_buffer(const b200osd_stencil_table *t, int which);
@@ -164,14 +172,38 @@ B200OSD_API int b200osd_eval_patches(
         const b200osd_patch_param *patchParams, void *stream);
 
 /* EvalPatches through the table handle (fast path): which = 0 vertex, 1 varying, 2+c face-varying channel c.
- * Same contract as b200osd_eval_patches; additionally, when numPatchCoords >= 4 x the number of patches, every
- * patch's control points are first gathered once into a compact per-patch hull cache owned by the table.
- * That cache is per-call state of the TABLE: calls on one stream are ordered by the stream (what the reference gets
- * implicitly -- everything runs on the legacy default stream); when consecutive calls on one table use different
- * streams the library waits for the device in between (inside a stream capture it cannot: order the streams
- * yourself).  For concurrent evaluation on several streams create one table object per stream.  Handles are not
- * thread-safe. */
+ * Same contract as b200osd_eval_patches.  The table is immutable: any number of threads and streams may evaluate one
+ * table concurrently.  Coordinates are evaluated in the caller's order, one warp per 32 of them; a warp copies every
+ * DISTINCT control hull among its coordinates once into shared memory, so a set that arrives grouped by patch (sorted,
+ * tessellation grids) costs one hull fetch per run of equal patches.  For large INCOHERENT sets (numPatchCoords >= 65536
+ * and >= 2 x the number of patches, 12-20 point hulls) a sampling probe on the device switches the call to a per-call
+ * hull cache: the index buffer is dereferenced once into scratch and every coordinate reads its hull as one contiguous
+ * 192-240 byte block.  The scratch comes from a stream-ordered memory pool on `stream` (no cudaMalloc, no
+ * synchronisation, legal during stream capture); results are bit-identical whichever way a call is served. */
 B200OSD_API int b200osd_patch_table_eval(const b200osd_patch_table *t, int which,
+        const float *src, const int srcDesc[3],
+        int nOut, float *const dsts[], const int dstDescs[][3],
+        int numPatchCoords, const b200osd_patch_coord *patchCoords, void *stream);
+/* how b200osd_patch_table_eval serves calls on this table (bench / tests): 0 = automatic (above), 1 = always the caller's
+ * order, 2 = group the coordinates by patch on the device per call (counting sort; results still land at the caller's
+ * index), 3 = always the per-call hull cache */
+B200OSD_API void b200osd_patch_table_set_variant(b200osd_patch_table *t, int variant);
+B200OSD_API int  b200osd_patch_table_get_variant(const b200osd_patch_table *t);
+
+/* ---- patch plan: a cached grouping of ONE coordinate set (the per-use state an "instantiatable" evaluator owns in the
+ * reference design: osd/mesh.h:305-409, osd/glComputeEvaluator.h:98-128) ------------------------------------------------
+ * _create allocates scratch for up to maxPatchCoords coordinates (the only allocation); _bin groups the coordinates at
+ * `patchCoords` by patch on the device (asynchronous on `stream`); _eval evaluates that same set (same pointer, same
+ * count: anything else returns B200OSD_ERR_INVALID) through the cached grouping -- vertex, varying and every face-varying
+ * slot share one grouping because PatchCoord.handle.patchIndex means the same patch in all of them.  Re-bin after the
+ * coordinates change.  One plan serves one stream at a time. */
+typedef struct b200osd_patch_plan b200osd_patch_plan;
+B200OSD_API b200osd_patch_plan *b200osd_patch_plan_create(const b200osd_patch_table *t, int maxPatchCoords);
+B200OSD_API void b200osd_patch_plan_destroy(b200osd_patch_plan *p);
+B200OSD_API int  b200osd_patch_plan_capacity(const b200osd_patch_plan *p);
+B200OSD_API int  b200osd_patch_plan_bin(b200osd_patch_plan *p, int numPatchCoords,
+        const b200osd_patch_coord *patchCoords, void *stream);
+B200OSD_API int  b200osd_patch_plan_eval(const b200osd_patch_plan *p, int which,
         const float *src, const int srcDesc[3],
         int nOut, float *const dsts[], const int dstDescs[][3],
         int numPatchCoords, const b200osd_patch_coord *patchCoords, void *stream);
@@ -198,8 +230,8 @@ B200OSD_API int  b200osd_patch_map_find(const b200osd_patch_map *m, int numSampl
 /* ---- frame capture ------------------------------------------------------------------------
  * A frame object owns a CUDA stream.  Calls issued with that stream between _begin and _end -- EvalStencils,
  * FindPatches, EvalPatches*, vertex-buffer updates from pinned memory -- are recorded instead of executed; _launch
- * replays them as one graph launch on the same stream.  Run the frame once eagerly first: first calls allocate
- * (hull cache, basis tables), which cannot be recorded.  No reference counterpart. */
+ * replays them as one graph launch on the same stream.  Run the frame once eagerly first (the stream-ordered scratch
+ * pool of b200osd_patch_table_eval fills on first use).  No reference counterpart. */
 B200OSD_API b200osd_frame *b200osd_frame_create(void);
 B200OSD_API void  b200osd_frame_destroy(b200osd_frame *f);
 B200OSD_API void *b200osd_frame_stream(const b200osd_frame *f);     /* the cudaStream_t to pass as `stream` */
@@ -208,14 +240,11 @@ B200OSD_API int   b200osd_frame_end(b200osd_frame *f);
 B200OSD_API int   b200osd_frame_launch(b200osd_frame *f);           /* asynchronous */
 B200OSD_API int   b200osd_frame_synchronize(b200osd_frame *f);
 
-/* ---- tuning / introspection (used by bench.py and the tests; not needed by clients) ---------- */
-/* Selects the stencil kernel variant used by b200osd_stencil_table_eval: 0 = auto. */
-B200OSD_API void b200osd_set_stencil_variant(int variant);
-B200OSD_API int  b200osd_get_stencil_variant(void);
-/* Patch evaluation through the table handle: 0 = auto, 1 = always through the index buffer, 2 = hull cache read directly,
- * 3 = hull cache staged through shared memory, 4 = hull cache with the per-warp choice between 2 and 3 (what auto uses). */
-B200OSD_API void b200osd_set_patch_variant(int variant);
-B200OSD_API int  b200osd_get_patch_variant(void);
+/* ---- tuning / introspection (used by bench.py and the tests; not needed by clients) ----------
+ * Kernel variant of b200osd_stencil_table_eval for THIS table (there is no process-wide state): 0 = auto,
+ * 1 = reference-layout (CSR) kernel, 2 = scalar gathers, 8 = persistent grid, 11 = 8 resident blocks/SM, 12 = 8 + 11. */
+B200OSD_API void b200osd_stencil_table_set_variant(b200osd_stencil_table *t, int variant);
+B200OSD_API int  b200osd_stencil_table_get_variant(const b200osd_stencil_table *t);
 
 #ifdef __cplusplus
 }

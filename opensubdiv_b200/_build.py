@@ -21,6 +21,10 @@ HEADERS = ["common.cuh", "stencil_kernels.cuh", "patch_kernels.cuh", "patchmap.c
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
+    # no implicit mul+add contraction: every FMA in the kernels is written as fmaf(), so the arithmetic is exactly what the
+    # source says, identical across kernels that share device functions (caller-order / hull-cache / grouped patch paths
+    # must agree bit for bit) and identical to the host emulation in tests/emu (-ffp-contract=off)
+    "-fmad=false",
     "-Xptxas=-v", "--threads", "4",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
     "-shared",

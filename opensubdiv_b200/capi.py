@@ -22,13 +22,15 @@ SYMBOLS = [
     "b200osd_vertex_buffer_read",
     "b200osd_stencil_table_create", "b200osd_stencil_table_destroy", "b200osd_stencil_table_num_stencils",
     "b200osd_stencil_table_num_control_vertices", "b200osd_stencil_table_num_elements",
+    "b200osd_stencil_table_num_levels",
     "b200osd_stencil_table_buffer", "b200osd_stencil_table_stream_bytes", "b200osd_stencil_table_eval",
-    "b200osd_stencil_table_eval_batched",
+    "b200osd_stencil_table_eval_batched", "b200osd_stencil_table_set_variant", "b200osd_stencil_table_get_variant",
     "b200osd_eval_stencils",
     "b200osd_patch_table_create", "b200osd_patch_table_destroy", "b200osd_patch_table_set",
     "b200osd_patch_table_num_fvar_channels", "b200osd_patch_table_buffer", "b200osd_patch_table_count",
-    "b200osd_eval_patches", "b200osd_patch_table_eval", "b200osd_set_patch_variant", "b200osd_get_patch_variant",
-    "b200osd_set_stencil_variant", "b200osd_get_stencil_variant",
+    "b200osd_eval_patches", "b200osd_patch_table_eval", "b200osd_patch_table_set_variant", "b200osd_patch_table_get_variant",
+    "b200osd_patch_plan_create", "b200osd_patch_plan_destroy", "b200osd_patch_plan_capacity", "b200osd_patch_plan_bin",
+    "b200osd_patch_plan_eval",
     "b200osd_patch_map_create", "b200osd_patch_map_destroy", "b200osd_patch_map_info", "b200osd_patch_map_find",
     "b200osd_frame_create", "b200osd_frame_destroy", "b200osd_frame_stream", "b200osd_frame_begin", "b200osd_frame_end",
     "b200osd_frame_launch", "b200osd_frame_synchronize",
@@ -66,7 +68,7 @@ def lib():
     L.b200osd_vertex_buffer_update.argtypes = [vp, vp, i, i, vp]
     L.b200osd_vertex_buffer_read.argtypes = [vp, vp, i, i, vp]
     L.b200osd_stencil_table_create.restype = vp
-    L.b200osd_stencil_table_create.argtypes = [i] + [vp] * 9 + [i]
+    L.b200osd_stencil_table_create.argtypes = [i, i] + [vp] * 9 + [i]
     L.b200osd_stencil_table_destroy.argtypes = [vp]
     L.b200osd_stencil_table_num_stencils.argtypes = [vp]
     L.b200osd_stencil_table_num_control_vertices.argtypes = [vp]
@@ -89,13 +91,22 @@ def lib():
     L.b200osd_patch_table_count.argtypes = [vp, i, i]
     L.b200osd_eval_patches.argtypes = [vp, vp, i, vp, vp, i, vp, vp, vp, vp, vp]
     L.b200osd_patch_table_eval.argtypes = [vp, i, vp, vp, i, vp, vp, i, vp, vp]
-    L.b200osd_set_patch_variant.argtypes = [i]
+    L.b200osd_patch_table_set_variant.argtypes = [vp, i]
+    L.b200osd_patch_table_get_variant.argtypes = [vp]
+    L.b200osd_patch_plan_create.restype = vp
+    L.b200osd_patch_plan_create.argtypes = [vp, i]
+    L.b200osd_patch_plan_destroy.argtypes = [vp]
+    L.b200osd_patch_plan_capacity.argtypes = [vp]
+    L.b200osd_patch_plan_bin.argtypes = [vp, i, vp, vp]
+    L.b200osd_patch_plan_eval.argtypes = [vp, i, vp, vp, i, vp, vp, i, vp, vp]
     L.b200osd_patch_map_create.restype = vp
     L.b200osd_patch_map_create.argtypes = [i, vp, i, vp, i]
     L.b200osd_patch_map_destroy.argtypes = [vp]
     L.b200osd_patch_map_info.argtypes = [vp, vp]
     L.b200osd_patch_map_find.argtypes = [vp, i, vp, i, vp, i, vp, i, vp, vp, vp]
-    L.b200osd_set_stencil_variant.argtypes = [i]
+    L.b200osd_stencil_table_set_variant.argtypes = [vp, i]
+    L.b200osd_stencil_table_get_variant.argtypes = [vp]
+    L.b200osd_stencil_table_num_levels.argtypes = [vp]
     L.b200osd_frame_create.restype = vp
     L.b200osd_frame_destroy.argtypes = [vp]
     L.b200osd_frame_stream.restype = vp

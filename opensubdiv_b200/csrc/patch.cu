@@ -1,14 +1,23 @@
 // patch.cu -- host side of the limit-evaluation path: argument validation mirroring the reference
-// evaluator, component tiling, kernel dispatch, and the device patch-table container.
+// evaluator, component tiling, device-side binning of the coordinates, kernel dispatch, and the device
+// patch-table container.
 //
 // Reference behaviour mirrored (paths relative to /root/reference/opensubdiv):
 //   osd/cpuEvaluator.cpp:165-176,224-241,300-331  src NULL -> false; value-only form with dst NULL -> false;
 //                                                 a non-NULL output whose length != srcDesc.length -> false
 //   osd/cudaKernel.cu:300-327                     NULL derivative outputs are skipped
 //   osd/cudaPatchTable.cpp:69-162                 device copies of PatchArray[], indices, PatchParam[] (+varying, fvar)
+//   osd/mesh.h:305-409, osd/glComputeEvaluator.h:98-128   "instantiatable" evaluators own per-use cached state: here
+//                                                 the patch plan (a cached binning of one coordinate set)
+//
+// No entry point below allocates with cudaMalloc, frees, or synchronises the device: tables are immutable after
+// _set, plans own their scratch from _create on, and the automatic binning of b200osd_patch_table_eval takes its
+// scratch from a stream-ordered memory pool (cudaMallocFromPoolAsync / cudaFreeAsync: asynchronous, legal inside a
+// stream capture, reused from the pool after the first call).
 #include "patch_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -41,7 +50,7 @@ const signed char kBox12[12][15] = {
 const signed char kMonoA[15] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 4, 3, 2, 1, 0 };
 const signed char kMonoB[15] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4 };
 
-int g_box_device = -1;
+constexpr int kMaxDevices = 64;
 
 // The derivative tables are obtained by differentiating kBox12 monomial by monomial.
 int upload_box_tables() {
@@ -69,80 +78,171 @@ int upload_box_tables() {
     return B200OSD_OK;
 }
 
+// __constant__ symbols are per device: uploaded once per device, lock-free afterwards.  Called when a table with
+// triangle patches is created (never from an evaluation entry: cudaMemcpyToSymbol synchronises).
 int ensure_box_tables() {
-    // __constant__ symbols are per device: (re)upload when the current device changes.
+    static std::atomic<bool> done[kMaxDevices];
+    static std::mutex mu;
     int dev = 0;
     B200_CUDA_TRY(cudaGetDevice(&dev));
-    static std::mutex mu;
+    if (dev < 0 || dev >= kMaxDevices) { set_error("device ordinal %d out of range", dev); return B200OSD_ERR_UNSUPPORTED; }
+    if (done[dev].load(std::memory_order_acquire)) return B200OSD_OK;
     std::lock_guard<std::mutex> lock(mu);
-    if (dev != g_box_device) {
+    if (!done[dev].load(std::memory_order_relaxed)) {
         int rc = upload_box_tables();
         if (rc) return rc;
-        g_box_device = dev;
+        done[dev].store(true, std::memory_order_release);
     }
     return B200OSD_OK;
 }
 
-template <int ORDER, int MODE>
-int launch_patches_h(const PatchIO &io, int LT, cudaStream_t st) {
-    const int block = kPatchBlock;
-    const int grid = (io.n + block - 1) / block;
-    const size_t smem = (size_t)(block / 32) * (size_t)io.warpWords * sizeof(float);
-    switch (LT) {
-        case 1: patch_kernel<1, ORDER, MODE><<<grid, block, smem, st>>>(io); break;
-        case 2: patch_kernel<2, ORDER, MODE><<<grid, block, smem, st>>>(io); break;
-        case 3: patch_kernel<3, ORDER, MODE><<<grid, block, smem, st>>>(io); break;
-        default: patch_kernel<4, ORDER, MODE><<<grid, block, smem, st>>>(io); break;
+// Stream-ordered scratch: one pool per device that never trims, so that after the first call an allocation is a
+// pointer bump on the stream -- no cudaMalloc, no synchronisation, legal during stream capture.
+int scratch_pool(cudaMemPool_t *out) {
+    static cudaMemPool_t pools[kMaxDevices];
+    static std::atomic<bool> ready[kMaxDevices];
+    static std::mutex mu;
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) { set_error("device ordinal %d out of range", dev); return B200OSD_ERR_UNSUPPORTED; }
+    if (!ready[dev].load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!ready[dev].load(std::memory_order_relaxed)) {
+            cudaMemPoolProps props;
+            std::memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            B200_CUDA_TRY(cudaMemPoolCreate(&pools[dev], &props));
+            unsigned long long keep = ~0ULL;
+            B200_CUDA_TRY(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+            ready[dev].store(true, std::memory_order_release);
+        }
     }
-    return check_launch("patch_kernel");
+    *out = pools[dev];
+    return B200OSD_OK;
 }
 
-template <int ORDER>
-int launch_patches(const PatchIO &io, int LT, int mode, cudaStream_t st) {
-    switch (mode) {
-        case 3: return launch_patches_h<ORDER, 3>(io, LT, st);
-        case 2: return launch_patches_h<ORDER, 2>(io, LT, st);
-        case 1: return launch_patches_h<ORDER, 1>(io, LT, st);
-        default: return launch_patches_h<ORDER, 0>(io, LT, st);
-    }
-}
-
-// 0 auto (index buffer for few coordinates per patch, else 4), 1 through the index buffer, 2 hull cache read directly,
-// 3 hull cache staged in shared memory, 4 per-warp choice between 2 and 3, 100+T the same with threshold T (sweeps)
-int g_patch_variant = 0;
-constexpr int kStageThreshold = 8;
-
-struct HullRequest {       // filled by b200osd_patch_table_eval when the hull cache should be used
-    float4 *hull4 = nullptr;
-    const int *rowsBefore = nullptr;     // device, per patch array
-    const b200osd_patch_array *hostArrays = nullptr;
-    int hullStride = 0, hullTiles = 0, numArrays = 0, numPatches = 0;
-    int staged = 0;        // 0 direct reads, 1 always staged (MODE 2), 2 per-warp choice (MODE 3)
-    int threshold = 0;
+// ------------------------------------------------------------------------------------ binning --
+struct BinScratch {              // carved out of one allocation, every region 256-byte aligned
+    BinState *state = nullptr;   // [1]            } zeroed together
+    int *count = nullptr;        // [numBins]      }
+    int *start = nullptr;        // [numBins]
+    int *blockSum = nullptr;     // [scanBlocks]
+    int2 *keyRank = nullptr;     // [n]
+    int *perm = nullptr;         // [n]
+    size_t zeroBytes = 0;
 };
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t bin_scratch_bytes(int maxCoords, int numPatches) {
+    const size_t bins = (size_t)numPatches + 1, blocks = (bins + kScanTile - 1) / kScanTile;
+    return align256(sizeof(BinState)) + align256(bins * 4) + align256(bins * 4) + align256(blocks * 4)
+         + align256((size_t)maxCoords * 8) + align256((size_t)maxCoords * 4);
+}
+
+BinScratch carve_bin_scratch(void *base, int maxCoords, int numPatches) {
+    const size_t bins = (size_t)numPatches + 1, blocks = (bins + kScanTile - 1) / kScanTile;
+    char *p = static_cast<char *>(base);
+    BinScratch s;
+    s.state = reinterpret_cast<BinState *>(p);       p += align256(sizeof(BinState));
+    s.count = reinterpret_cast<int *>(p);            p += align256(bins * 4);
+    s.zeroBytes = (size_t)(p - static_cast<char *>(base));
+    s.start = reinterpret_cast<int *>(p);            p += align256(bins * 4);
+    s.blockSum = reinterpret_cast<int *>(p);         p += align256(blocks * 4);
+    s.keyRank = reinterpret_cast<int2 *>(p);         p += align256((size_t)maxCoords * 8);
+    s.perm = reinterpret_cast<int *>(p);
+    return s;
+}
+
+// probe (unless forced) -> count -> scan -> scatter, all on `st`; every kernel after the probe returns at once when the
+// probe found the coordinates already coherent
+int run_binning(const BinScratch &s, const b200osd_patch_coord *coords, int n, int numPatches, bool force, cudaStream_t st) {
+    const int bins = numPatches + 1, blocks = (bins + kScanTile - 1) / kScanTile;
+    B200_CUDA_TRY(cudaMemsetAsync(s.state, 0, s.zeroBytes, st));
+    bin_probe_kernel<<<kBinProbeWarps / 4, 128, 0, st>>>(coords, n, s.state, kPatchModeGrouped, force ? 1 : 0);
+    int rc = check_launch("bin_probe_kernel");
+    if (rc) return rc;
+    bin_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(coords, n, numPatches, s.state, s.count, s.keyRank);
+    if ((rc = check_launch("bin_count_kernel"))) return rc;
+    bin_scan_local_kernel<<<blocks, kScanThreads, 0, st>>>(s.state, s.count, s.start, s.blockSum, bins);
+    if ((rc = check_launch("bin_scan_local_kernel"))) return rc;
+    bin_scan_top_kernel<<<1, kScanThreads, 0, st>>>(s.state, s.blockSum, blocks);
+    if ((rc = check_launch("bin_scan_top_kernel"))) return rc;
+    bin_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.state, s.keyRank, s.start, s.blockSum, n, s.perm);
+    return check_launch("bin_scatter_kernel");
+}
+
+// ----------------------------------------------------------------------------------- dispatch --
+int patch_grid(long long n) {
+    const long long need = (n + kPatchBlock - 1) / kPatchBlock;
+    return (int)std::min<long long>(need, (long long)sm_count() * 16);       // persistent: at most 64 warps per SM
+}
+
+template <int ORDER, bool TRI>
+int launch_run(const PatchIO &io, int LT, cudaStream_t st) {
+    const int grid = patch_grid(io.n);
+    const size_t smem = (size_t)(kPatchBlock / 32) * (size_t)io.warpWords * sizeof(float);
+    switch (LT) {
+        case 1: patch_run_kernel<1, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io); break;
+        case 2: patch_run_kernel<2, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io); break;
+        case 3: patch_run_kernel<3, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io); break;
+        default: patch_run_kernel<4, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io); break;
+    }
+    return check_launch("patch_run_kernel");
+}
+
+template <int ORDER, bool TRI>
+int launch_hull(const PatchIO &io, int LT, const float *hull, cudaStream_t st) {
+    const int grid = patch_grid(io.n);
+    const size_t smem = (size_t)(kPatchBlock / 32) * (size_t)io.warpWords * sizeof(float);
+    switch (LT) {
+        case 1: patch_hull_kernel<1, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io, hull); break;
+        case 2: patch_hull_kernel<2, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io, hull); break;
+        case 3: patch_hull_kernel<3, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io, hull); break;
+        default: patch_hull_kernel<4, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io, hull); break;
+    }
+    return check_launch("patch_hull_kernel");
+}
+
+int launch_hull_build(const PatchIO &io, int LT, long long rows, float *hull, cudaStream_t st) {
+    const int grid = (int)std::min<long long>((rows + 255) / 256, (long long)sm_count() * 32);
+    switch (LT) {
+        case 1: hull_build_kernel<1><<<grid, 256, 0, st>>>(io.src, io.srcStride, io.indices, rows, hull, io.binState); break;
+        case 2: hull_build_kernel<2><<<grid, 256, 0, st>>>(io.src, io.srcStride, io.indices, rows, hull, io.binState); break;
+        case 3: hull_build_kernel<3><<<grid, 256, 0, st>>>(io.src, io.srcStride, io.indices, rows, hull, io.binState); break;
+        default: hull_build_kernel<4><<<grid, 256, 0, st>>>(io.src, io.srcStride, io.indices, rows, hull, io.binState); break;
+    }
+    return check_launch("hull_build_kernel");
+}
+
+struct PatchShape {            // what the host knows about the table behind a call
+    int maxPoints = 20;        // largest control hull (raw device arrays: unknown, assume the largest type)
+    bool hasTri = true;        // triangle types may occur
+};
+
+// How a call is served.  perm / state: grouped order (state NULL: unconditionally).  hull: scratch for the per-call
+// hull cache of hullRows rows (state NULL: unconditionally; otherwise the probe's verdict in *state picks between the
+// hull kernels and the caller-order kernel -- both are launched, the one not chosen returns at once).
+struct PatchRoute {
+    const int *perm = nullptr;
+    const BinState *state = nullptr;
+    float *hull = nullptr;
+    long long hullRows = 0;
+};
+
+#define B200_PATCH_DISPATCH(fn, ...)                                                                                   \
+    (shape.hasTri ? (nOut == 1 ? fn<0, true>(__VA_ARGS__) : (nOut == 3 ? fn<1, true>(__VA_ARGS__) : fn<2, true>(__VA_ARGS__))) \
+                  : (nOut == 1 ? fn<0, false>(__VA_ARGS__) : (nOut == 3 ? fn<1, false>(__VA_ARGS__) : fn<2, false>(__VA_ARGS__))))
 
 int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float *const dsts[],
                         const int dstDescs[][3], int numPatchCoords, const b200osd_patch_coord *patchCoords,
                         const b200osd_patch_array *patchArrays, const int *patchIndices,
-                        const b200osd_patch_param *patchParams, const HullRequest *hull, cudaStream_t st) {
+                        const b200osd_patch_param *patchParams, const PatchShape &shape,
+                        const PatchRoute &route, cudaStream_t st) {
     const int L = srcDesc[1];
-    int rc = ensure_box_tables();
-    if (rc) return rc;
-    if (hull) {
-        long long before = 0;
-        for (int a = 0; a < hull->numArrays; ++a) {
-            const b200osd_patch_array &pa = hull->hostArrays[a];
-            const long long rows = (long long)pa.numPatches * (long long)pa.stride;
-            if (rows > 0) {
-                const dim3 hgrid((unsigned)((rows + 255) / 256), (unsigned)hull->hullTiles);
-                hull_gather_kernel<<<hgrid, 256, 0, st>>>(src + srcDesc[0], srcDesc[2], L, patchIndices + pa.indexBase, rows,
-                                                          pa.stride, before, hull->hullTiles, hull->hull4);
-                rc = check_launch("hull_gather_kernel");
-                if (rc) return rc;
-            }
-            before += rows;
-        }
-    }
     // components are evaluated in tiles of at most 4 (xyz, uv, rgba fit in one launch)
     for (int c0 = 0; c0 < L; c0 += 4) {
         const int LT = (L - c0) < 4 ? (L - c0) : 4;
@@ -157,36 +257,37 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
         io.arrays = patchArrays;
         io.indices = patchIndices;
         io.params = patchParams;
-        io.hull4 = hull ? hull->hull4 : nullptr;
-        io.hullRowsBefore = hull ? hull->rowsBefore : nullptr;
-        io.hullStride = hull ? hull->hullStride : 0;
-        io.hullTiles = hull ? hull->hullTiles : 0;
-        io.tile = c0 / 4;
-        // glEvalLimit-style interleaving: output k at float k*LT of an nOut*LT-float record in one buffer
-        io.packed = (nOut > 1 && LT == L) ? 1 : 0;
+        io.perm = route.perm;
+        io.binState = route.state;
+        // one record per coordinate: output k at float k*LT of an nOut*LT-float record in one buffer (glEvalLimit-style
+        // interleaving, or a single tightly packed output)
+        const int R = nOut * LT;
+        io.packed = (LT == L) ? 1 : 0;
         for (int k = 0; k < nOut && io.packed; ++k)
-            if (!io.dst[k] || io.dst[k] != io.dst[0] + (size_t)k * LT || io.dstStride[k] != nOut * LT) io.packed = 0;
-        const int nsets = nOut;
-        const int recordWords = 32 * (nsets > 1 ? ((nsets * LT) | 1) : LT);
-        io.hullPitch = 0; io.stageThreshold = 0;
-        int mode = hull ? 1 : 0;
-        io.warpWords = recordWords;
-        if (hull && hull->staged && hull->hullStride >= 12) {      // 3-4 point (linear) hulls: direct reads
-            const int pitch = (hull->hullStride * LT) | 1;
-            const int words = std::max(recordWords, 32 * pitch);
-            if ((size_t)(kPatchBlock / 32) * words * sizeof(float) <= 48 * 1024) {     // else: direct hull reads
-                mode = hull->staged == 1 ? 2 : 3;
-                io.stageThreshold = hull->threshold;
-                io.warpWords = words;
-                io.hullPitch = pitch;
-            }
+            if (!io.dst[k] || io.dst[k] != io.dst[0] + (size_t)k * LT || io.dstStride[k] != R) io.packed = 0;
+        io.vecStore = 0;
+        if (io.packed) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(io.dst[0]);
+            if (a % 16 == 0) io.vecStore |= 1;
+            if (a % 8 == 0 && R % 2 == 0) io.vecStore |= 2;
         }
-        rc = nOut == 1 ? launch_patches<0>(io, LT, mode, st)
-                       : (nOut == 3 ? launch_patches<1>(io, LT, mode, st) : launch_patches<2>(io, LT, mode, st));
+        if (LT == 4 && reinterpret_cast<uintptr_t>(io.src) % 16 == 0 && io.srcStride % 4 == 0) io.vecStore |= 4;
+        // shared memory per warp: coordinates in (160 words), staged hulls, results out (32 records + 32 indices)
+        io.hullPitch = hull_pitch(LT, shape.maxPoints);
+        io.warpWords = (std::max(std::max(160, 32 * R + 32), kHullSlots * io.hullPitch) + 3) & ~3;
+        int rc = B200OSD_OK;
+        if (route.hull) {
+            rc = launch_hull_build(io, LT, route.hullRows, route.hull, st);
+            if (!rc) rc = B200_PATCH_DISPATCH(launch_hull, io, LT, route.hull, st);
+            if (rc) return rc;
+            if (!route.state) continue;                          // forced: the hull kernels did the tile
+        }
+        rc = B200_PATCH_DISPATCH(launch_run, io, LT, st);
         if (rc) return rc;
     }
     return B200OSD_OK;
 }
+#undef B200_PATCH_DISPATCH
 
 // reference-mirroring argument checks (osd/cpuEvaluator.cpp:165-176,224-241,300-331); *empty = nothing to do
 int validate_patch_args(const float *src, const int srcDesc[3], int nOut, float *const dsts[], const int dstDescs[][3],
@@ -206,6 +307,8 @@ int validate_patch_args(const float *src, const int srcDesc[3], int nOut, float 
     return B200OSD_OK;
 }
 
+bool is_tri_type(int t) { return t == PT_TRIANGLES || t == PT_LOOP || t == PT_GREGORY_TRIANGLE; }
+
 }  // namespace
 
 struct b200osd_patch_table {
@@ -213,27 +316,33 @@ struct b200osd_patch_table {
         b200osd_patch_array *arrays = nullptr;
         int *indices = nullptr;
         b200osd_patch_param *params = nullptr;
-        int *rowsBefore = nullptr;     // hull cache layout: per array, sum over earlier arrays of numPatches * stride
-        long long hullRows = 0;        // total rows of one component tile
         int nArrays = 0, nIndices = 0, nParams = 0;
+        int maxPoints = 0;             // largest control hull over the slot's arrays
+        bool hasTri = false;           // a triangle patch type occurs
     };
-    std::vector<Triple> triples;   // 0 vertex, 1 varying, 2+c fvar channel c
+    std::vector<Triple> triples;       // 0 vertex, 1 varying, 2+c fvar channel c
     int numFVar = 0;
-    // hull cache scratch (per-call contents; grown on demand)
-    float4 *d_hull = nullptr;
-    size_t hullCap = 0;
-    bool hullUsed = false;               // the cache is per-call state: remember which stream last wrote / read it
-    cudaStream_t hullStream = nullptr;
-    std::vector<std::vector<b200osd_patch_array>> hostArrays;   // host copies of the PatchArray descriptors
+    int variant = 0;                   // b200osd_patch_table_set_variant
 };
 
-static void free_triple(b200osd_patch_table::Triple &tr) {
-    cudaFree(tr.arrays); cudaFree(tr.indices); cudaFree(tr.params); cudaFree(tr.rowsBefore);
+struct b200osd_patch_plan {
+    const b200osd_patch_table *table = nullptr;
+    int maxCoords = 0, numPatches = 0;
+    void *block = nullptr;             // one cudaMalloc'ed allocation, carved into `s`
+    BinScratch s;
+    int n = 0;                         // the coordinate set the permutation was built for
+    const b200osd_patch_coord *coords = nullptr;
+};
+
+namespace {
+
+void free_triple(b200osd_patch_table::Triple &tr) {
+    cudaFree(tr.arrays); cudaFree(tr.indices); cudaFree(tr.params);
     tr = b200osd_patch_table::Triple();
 }
 
 template <typename T>
-static int upload_array(T **d, const T *h, int n) {
+int upload_array(T **d, const T *h, int n) {
     *d = nullptr;
     if (n <= 0 || !h) return B200OSD_OK;
     cudaError_t e = cudaMalloc((void **)d, (size_t)n * sizeof(T));
@@ -242,6 +351,20 @@ static int upload_array(T **d, const T *h, int n) {
     if (e != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(e)); cudaFree(*d); *d = nullptr; return B200OSD_ERR_CUDA; }
     return B200OSD_OK;
 }
+
+// the (arrays, indices, params) triple a call on slot `which` evaluates, with the varying slot borrowing the vertex params
+int resolve_triple(const b200osd_patch_table *t, int which, const b200osd_patch_table::Triple **tr,
+                   const b200osd_patch_param **params, int *numPatches) {
+    if (!t || which < 0 || which >= (int)t->triples.size()) { set_error("patch table: bad table / slot"); return B200OSD_ERR_INVALID; }
+    *tr = &t->triples[which];
+    *params = (*tr)->params;
+    *numPatches = (*tr)->nParams;
+    if (which == 1 && !*params) { *params = t->triples[0].params; *numPatches = t->triples[0].nParams; }   // osd/cudaEvaluator.h:857-878
+    if (!(*tr)->arrays || !(*tr)->indices || !*params) { set_error("patch table slot %d is empty", which); return B200OSD_ERR_INVALID; }
+    return B200OSD_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -253,78 +376,155 @@ int b200osd_eval_patches(const float *src, const int srcDesc[3], int nOut, float
     int rc = validate_patch_args(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, &empty);
     if (rc || empty) return rc;
     if (!patchCoords || !patchArrays || !patchIndices || !patchParams) { set_error("patch table / coords are NULL"); return B200OSD_ERR_INVALID; }
+    // device arrays of unknown shape: any type may occur (the box-spline tables must be on the device) and nothing is
+    // known about the number of patches, so the coordinates are evaluated in the caller's order
+    if ((rc = ensure_box_tables())) return rc;
+    PatchShape shape;
     return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, patchArrays, patchIndices,
-                               patchParams, nullptr, (cudaStream_t)stream);
+                               patchParams, shape, PatchRoute(), (cudaStream_t)stream);
 }
 
-int b200osd_patch_table_eval(const b200osd_patch_table *tc, int which, const float *src, const int srcDesc[3], int nOut,
+int b200osd_patch_table_eval(const b200osd_patch_table *t, int which, const float *src, const int srcDesc[3], int nOut,
                              float *const dsts[], const int dstDescs[][3], int numPatchCoords,
                              const b200osd_patch_coord *patchCoords, void *stream) {
-    b200osd_patch_table *t = const_cast<b200osd_patch_table *>(tc);
-    if (!t || which < 0 || which >= (int)t->triples.size()) { set_error("patch_table_eval: bad table / slot"); return B200OSD_ERR_INVALID; }
+    const b200osd_patch_table::Triple *tr = nullptr;
+    const b200osd_patch_param *params = nullptr;
+    int numPatches = 0;
+    int rc = resolve_triple(t, which, &tr, &params, &numPatches);
+    if (rc) return rc;
     bool empty = false;
-    int rc = validate_patch_args(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, &empty);
+    rc = validate_patch_args(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, &empty);
     if (rc || empty) return rc;
-    const b200osd_patch_table::Triple &tr = t->triples[which];
-    const b200osd_patch_param *params = tr.params;
-    int numPatches = tr.nParams;
-    if (which == 1 && !params) { params = t->triples[0].params; numPatches = t->triples[0].nParams; }   // varying shares vertex params
-    if (!patchCoords || !tr.arrays || !tr.indices || !params) { set_error("patch table slot %d is empty", which); return B200OSD_ERR_INVALID; }
+    if (!patchCoords) { set_error("patchCoords is NULL"); return B200OSD_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PatchShape shape;
+    shape.maxPoints = std::max(tr->maxPoints, 3);
+    shape.hasTri = tr->hasTri;
 
-    // Hull cache: when many coordinates share few patches, gather every patch's control points once per call into
-    // 16-byte rows so that a coordinate reads one compact, aligned block instead of 16-20 scattered vertices.
-    HullRequest hull;
-    bool useHull = (g_patch_variant >= 2) || (g_patch_variant == 0 && (long long)numPatchCoords >= 4LL * numPatches);
-    if (useHull && numPatches > 0) {
-        int hs = 0;
-        for (int a = 0; a < tr.nArrays; ++a) hs = std::max(hs, t->hostArrays[which][a].stride);
-        if (hs < 1 || hs > 32 || tr.hullRows <= 0 || !tr.rowsBefore) useHull = false;   // one warp lane per control point
-        const int tiles = (srcDesc[1] + 3) / 4;
-        const size_t need = (size_t)std::max(tr.hullRows, 0LL) * tiles;
-        if (useHull && need > t->hullCap) {
-            cudaFree(t->d_hull);
-            t->d_hull = nullptr;
-            t->hullCap = 0;
-            if (cudaMalloc((void **)&t->d_hull, need * sizeof(float4)) != cudaSuccess) {
-                cudaGetLastError();
-                useHull = false;                      // not enough memory for the cache: evaluate through the indices
-            } else {
-                t->hullCap = need;
-            }
+    // How the coordinates are served (variant: 0 automatic, 1 caller's order, 2 grouped by patch per call, 3 hull cache):
+    //  * caller's order, hulls staged per warp -- right for coherent sets (sorted by patch, tessellation grids) and for
+    //    small calls;
+    //  * per-call hull cache -- right for INCOHERENT sets when several coordinates share a patch and the hull is worth
+    //    gathering (16-20 points of 3-4 floats, not the 4-point linear patches of varying data): one 192-byte read per
+    //    coordinate instead of 18 scattered ones.  Whether the set is coherent is found out on the device by a sampling
+    //    probe; both kernels are enqueued and the one not chosen returns at once;
+    //  * grouped by patch (counting sort per call): measured slower than the hull cache on B200 -- the random 20-byte
+    //    coordinate reads and 72-byte result writes cost more DRAM row activations than the hull reads they save
+    //    (profiles/r02b_*) -- so it is never chosen automatically; an evaluator instance can still cache a grouping.
+    const int LT0 = std::min(srcDesc[1], 4);
+    const bool worth = numPatchCoords >= 65536 && (long long)numPatchCoords >= 2LL * numPatches && shape.maxPoints * LT0 >= 32;
+    const int variant = t->variant;
+    if (variant == 1 || (variant == 0 && !worth))
+        return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, tr->arrays, tr->indices,
+                                   params, shape, PatchRoute(), st);
+    cudaMemPool_t pool;
+    if ((rc = scratch_pool(&pool))) return rc;
+    void *block = nullptr;
+    PatchRoute route;
+    if (variant == 2) {
+        const size_t bytes = bin_scratch_bytes(numPatchCoords, numPatches);
+        if (cudaMallocFromPoolAsync(&block, bytes, pool, st) != cudaSuccess) { cudaGetLastError(); block = nullptr; }
+        if (block) {
+            const BinScratch s = carve_bin_scratch(block, numPatchCoords, numPatches);
+            rc = run_binning(s, patchCoords, numPatchCoords, numPatches, true, st);
+            route.perm = s.perm;
+            route.state = s.state;
         }
-        if (useHull) {
-            // The cache is shared by every call on this table.  Calls on ONE stream are ordered by the stream; when the
-            // stream changes, the previous call may still be reading the cache, so wait for the device once (the
-            // reference never meets this: all its launches go to the legacy default stream).  While the new stream is
-            // being captured no synchronisation is possible -- ordering is then the caller's job (b200osd_capi.h).
-            cudaStream_t cur = (cudaStream_t)stream;
-            if (t->hullUsed && t->hullStream != cur) {
-                cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-                if (cudaStreamIsCapturing(cur, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
-                if (cs == cudaStreamCaptureStatusNone) B200_CUDA_TRY(cudaDeviceSynchronize());
+    } else {
+        const size_t hullBytes = align256((size_t)tr->nIndices * LT0 * sizeof(float));
+        if (cudaMallocFromPoolAsync(&block, align256(sizeof(BinState)) + hullBytes, pool, st) != cudaSuccess) { cudaGetLastError(); block = nullptr; }
+        if (block) {
+            BinState *state = static_cast<BinState *>(block);
+            route.hull = reinterpret_cast<float *>(static_cast<char *>(block) + align256(sizeof(BinState)));
+            route.hullRows = tr->nIndices;
+            if (variant == 0) {                                  // the probe decides on the device
+                rc = cudaMemsetAsync(state, 0, sizeof(BinState), st) == cudaSuccess ? B200OSD_OK : B200OSD_ERR_CUDA;
+                if (!rc) {
+                    bin_probe_kernel<<<kBinProbeWarps / 4, 128, 0, st>>>(patchCoords, numPatchCoords, state, kPatchModeHull, 0);
+                    rc = check_launch("bin_probe_kernel");
+                }
+                route.state = state;
             }
-            t->hullUsed = true;
-            t->hullStream = cur;
-            hull.hull4 = t->d_hull;
-            hull.rowsBefore = tr.rowsBefore;
-            hull.hostArrays = t->hostArrays[which].data();
-            hull.hullStride = hs;
-            hull.hullTiles = tiles;
-            hull.numArrays = tr.nArrays;
-            hull.numPatches = numPatches;
-            // auto: per-warp choice while the cache is L2-resident (incoherent warps are then bound by L1 wavefronts and
-            // staging pays); a cache far larger than L2 makes incoherent reads DRAM-bound and staging only adds work
-            const bool l2Resident = need * sizeof(float4) <= (size_t)64 << 20;
-            hull.staged = g_patch_variant == 3 ? 1 : (g_patch_variant == 2 ? 0 : (g_patch_variant == 0 && !l2Resident ? 0 : 2));
-            hull.threshold = g_patch_variant >= 100 ? g_patch_variant - 100 : kStageThreshold;
         }
     }
-    return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, tr.arrays, tr.indices,
-                               params, useHull ? &hull : nullptr, (cudaStream_t)stream);
+    // no scratch: the caller's order is still correct
+    if (!rc)
+        rc = eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, tr->arrays, tr->indices,
+                                 params, shape, block ? route : PatchRoute(), st);
+    if (block) cudaFreeAsync(block, st);
+    return rc;
 }
 
-void b200osd_set_patch_variant(int v) { g_patch_variant = v; }
-int b200osd_get_patch_variant(void) { return g_patch_variant; }
+// ---------------------------------------------------------------------------------- patch plan --
+b200osd_patch_plan *b200osd_patch_plan_create(const b200osd_patch_table *t, int maxPatchCoords) {
+    if (!t || t->triples.empty() || maxPatchCoords <= 0) { set_error("patch_plan_create: bad table / size"); return nullptr; }
+    b200osd_patch_plan *p = new (std::nothrow) b200osd_patch_plan;
+    if (!p) return nullptr;
+    p->table = t;
+    p->maxCoords = maxPatchCoords;
+    p->numPatches = t->triples[0].nParams;
+    for (const auto &tr : t->triples) p->numPatches = std::max(p->numPatches, tr.nParams);
+    const size_t bytes = bin_scratch_bytes(maxPatchCoords, p->numPatches);
+    cudaError_t e = cudaMalloc(&p->block, bytes);
+    if (e != cudaSuccess) {
+        set_error("patch_plan_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        delete p;
+        return nullptr;
+    }
+    p->s = carve_bin_scratch(p->block, maxPatchCoords, p->numPatches);
+    return p;
+}
+
+void b200osd_patch_plan_destroy(b200osd_patch_plan *p) {
+    if (!p) return;
+    cudaFree(p->block);
+    delete p;
+}
+
+int b200osd_patch_plan_capacity(const b200osd_patch_plan *p) { return p ? p->maxCoords : 0; }
+
+int b200osd_patch_plan_bin(b200osd_patch_plan *p, int numPatchCoords, const b200osd_patch_coord *patchCoords, void *stream) {
+    if (!p) { set_error("patch plan is NULL"); return B200OSD_ERR_INVALID; }
+    if (numPatchCoords < 0 || numPatchCoords > p->maxCoords) {
+        set_error("patch_plan_bin: %d coordinates exceed the plan's capacity %d", numPatchCoords, p->maxCoords);
+        return B200OSD_ERR_INVALID;
+    }
+    p->n = 0;
+    p->coords = nullptr;
+    if (numPatchCoords == 0) return B200OSD_OK;
+    if (!patchCoords) { set_error("patchCoords is NULL"); return B200OSD_ERR_INVALID; }
+    int rc = run_binning(p->s, patchCoords, numPatchCoords, p->numPatches, true, (cudaStream_t)stream);
+    if (rc) return rc;
+    p->n = numPatchCoords;
+    p->coords = patchCoords;
+    return B200OSD_OK;
+}
+
+int b200osd_patch_plan_eval(const b200osd_patch_plan *p, int which, const float *src, const int srcDesc[3], int nOut,
+                            float *const dsts[], const int dstDescs[][3], int numPatchCoords,
+                            const b200osd_patch_coord *patchCoords, void *stream) {
+    if (!p) { set_error("patch plan is NULL"); return B200OSD_ERR_INVALID; }
+    const b200osd_patch_table::Triple *tr = nullptr;
+    const b200osd_patch_param *params = nullptr;
+    int numPatches = 0;
+    int rc = resolve_triple(p->table, which, &tr, &params, &numPatches);
+    if (rc) return rc;
+    bool empty = false;
+    rc = validate_patch_args(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, &empty);
+    if (rc || empty) return rc;
+    if (numPatchCoords != p->n || patchCoords != p->coords) {
+        set_error("patch_plan_eval: the plan was binned for another coordinate set (%d coordinates at %p)", p->n, (const void *)p->coords);
+        return B200OSD_ERR_INVALID;
+    }
+    PatchShape shape;
+    shape.maxPoints = std::max(tr->maxPoints, 3);
+    shape.hasTri = tr->hasTri;
+    PatchRoute route;
+    route.perm = p->s.perm;
+    route.state = p->s.state;
+    return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, tr->arrays, tr->indices,
+                               params, shape, route, (cudaStream_t)stream);
+}
 
 // -------------------------------------------------------------------------------- patch table --
 b200osd_patch_table *b200osd_patch_table_create(int numFVarChannels) {
@@ -333,15 +533,12 @@ b200osd_patch_table *b200osd_patch_table_create(int numFVarChannels) {
     if (!t) return nullptr;
     t->numFVar = numFVarChannels;
     t->triples.resize(2 + numFVarChannels);
-    t->hostArrays.resize(2 + numFVarChannels);
     return t;
 }
-
 
 void b200osd_patch_table_destroy(b200osd_patch_table *t) {
     if (!t) return;
     for (auto &tr : t->triples) free_triple(tr);
-    cudaFree(t->d_hull);
     delete t;
 }
 
@@ -350,23 +547,24 @@ int b200osd_patch_table_set(b200osd_patch_table *t, int which, int numArrays, co
     if (!t || which < 0 || which >= (int)t->triples.size()) { set_error("patch_table_set: bad table / slot"); return B200OSD_ERR_INVALID; }
     b200osd_patch_table::Triple &tr = t->triples[which];
     free_triple(tr);
-    int rc = upload_array(&tr.arrays, arrays, numArrays);
+    int maxPoints = 0;
+    bool hasTri = false;
+    for (int a = 0; arrays && a < numArrays; ++a) {
+        for (int d : { arrays[a].regDesc, arrays[a].desc }) {
+            maxPoints = std::max(maxPoints, patch_type_points(d));
+            hasTri = hasTri || is_tri_type(d);
+        }
+    }
+    int rc = hasTri ? ensure_box_tables() : B200OSD_OK;
+    if (!rc) rc = upload_array(&tr.arrays, arrays, numArrays);
     if (!rc) rc = upload_array(&tr.indices, indices, numIndices);
     if (!rc) rc = upload_array(&tr.params, params, numParams);
-    std::vector<int> before((size_t)std::max(numArrays, 0));
-    long long rows = 0;
-    for (int a = 0; arrays && a < numArrays; ++a) {
-        before[(size_t)a] = (int)rows;
-        rows += (long long)arrays[a].numPatches * (long long)std::max(arrays[a].stride, 0);
-    }
-    if (!rc && rows > 0x7fffffffLL) rows = -1;                 // too large for 32-bit row offsets: no hull cache
-    if (!rc) rc = upload_array(&tr.rowsBefore, before.data(), arrays ? numArrays : 0);
     if (rc) { free_triple(tr); return rc; }
-    tr.hullRows = rows;
-    t->hostArrays[which].assign(arrays, arrays + (arrays ? numArrays : 0));
     tr.nArrays = tr.arrays ? numArrays : 0;
     tr.nIndices = tr.indices ? numIndices : 0;
     tr.nParams = tr.params ? numParams : 0;
+    tr.maxPoints = maxPoints;
+    tr.hasTri = hasTri;
     return B200OSD_OK;
 }
 
@@ -386,5 +584,8 @@ int b200osd_patch_table_count(const b200osd_patch_table *t, int which, int kind)
     if (kind == 2 && which == 1 && !tr.params) return t->triples[0].nParams;
     return kind == 0 ? tr.nArrays : (kind == 1 ? tr.nIndices : tr.nParams);
 }
+
+void b200osd_patch_table_set_variant(b200osd_patch_table *t, int variant) { if (t) t->variant = variant; }
+int b200osd_patch_table_get_variant(const b200osd_patch_table *t) { return t ? t->variant : 0; }
 
 }  // extern "C"

@@ -6,27 +6,44 @@
 //   osd/patchBasis.h:53-1610       linear / B-spline / Gregory / box-spline / Gregory-triangle bases, boundary
 //                                  folding, derivative scaling (d1 = +-2^depth, d2 = sign*d1*d1)
 //
-// Design (one thread per PatchCoord, everything in registers):
-//   REGULAR (bicubic B-spline, the overwhelmingly common type) is evaluated in SEPARABLE form: the 1-D weight
-//   vectors in s and t (value / 1st / 2nd derivative, boundary-folded and pre-scaled) are kept, each of the 4 rows
-//   of control points is first contracted with the three s-vectors, and the row results are then combined with
-//   the t-vectors.  That is 16*3 + 4*6 = 72 multiply-adds per component instead of the 16*6 = 96 (plus 96
-//   products to form the tensor weights) of the reference formulation; boundary folding is linear in the 1-D
-//   weights so it commutes with the tensor product.  Summation order differs from the reference, see DESIGN.md.
-//   GREGORY_BASIS and QUADS are unrolled per control point with compile-time point tables.
-//   LOOP / GREGORY_TRIANGLE / TRIANGLES use a weight-array formulation (local memory), correct but not tuned.
+// Design (one thread per PatchCoord, one warp per 32 consecutive coordinates, everything in registers):
+//   * A warp first finds the DISTINCT patches among its 32 coordinates (match.any) and copies each distinct control
+//     hull ONCE from the index buffer + the caller's primvar buffer into shared memory, two hulls per pass (one per
+//     half warp: a coalesced read of the patch's 16-20 indices, then one vertex per lane).  Every lane then evaluates
+//     out of its patch's staged row (128-bit shared-memory loads, broadcast when lanes share a patch).  Coordinates
+//     that arrive grouped by patch -- sorted by the caller, or binned on the device, see below -- therefore cost one
+//     hull fetch per RUN of equal patches instead of one per coordinate.  No per-call cache in global memory.
+//   * Device-side binning (SURVEY.md section 7 "bin/sort once per coord set, or a per-call device counting sort"):
+//     bin_* kernels build a permutation that groups the coordinates by patch (counting sort on patchIndex with one
+//     atomic per coordinate); patch_run_kernel then walks the permutation, gathers its coordinates and writes every
+//     result at the CALLER's index i, so outputs are bit-identical per index to the unbinned evaluation.  A sampling
+//     probe leaves already coherent coordinate sets alone.
+//   * REGULAR (bicubic B-spline, the overwhelmingly common type) is evaluated in SEPARABLE form: the 1-D weight
+//     vectors in s and t (value / 1st / 2nd derivative, boundary-folded and pre-scaled) are kept, each of the 4 rows
+//     of control points is first contracted with the three s-vectors, and the row results are then combined with
+//     the t-vectors.  That is 16*3 + 4*6 = 72 multiply-adds per component instead of the 16*6 = 96 (plus 96
+//     products to form the tensor weights) of the reference formulation; boundary folding is linear in the 1-D
+//     weights so it commutes with the tensor product.  Summation order differs from the reference, see DESIGN.md.
+//   * GREGORY_BASIS and QUADS are unrolled per control point with compile-time point tables.  The triangle types
+//     (LOOP / GREGORY_TRIANGLE / TRIANGLES) live in a separate kernel instantiation (TRI) so that quad tables do not
+//     carry their code or stack frame.
 #pragma once
 
 #include "common.cuh"
 
 // Every function below is __host__ __device__ so that tests/emu can run the *identical* arithmetic on the CPU
-// (a test-only numerical harness, never a product path: libb200osd.so only ever launches the __global__ kernel).
+// (a test-only numerical harness, never a product path: libb200osd.so only ever launches the __global__ kernels).
 #define B200_HD __host__ __device__ __forceinline__
 #define B200_HD_NOINLINE __host__ __device__
 
 namespace b200osd {
 
 constexpr int kPatchMaxOut = 6;
+
+struct BinState {                     // device-side state of one call (probe and bin_* kernels)
+    int mode;                         // kPatchMode*: caller's order / per-call hull cache / grouped order (perm is valid)
+    int heads, lanes, ticket;         // coherence probe: runs of equal patches / coordinates sampled / warps done
+};
 
 struct PatchIO {
     const float *src;                 // already offset by srcDesc.offset (+ component tile offset)
@@ -38,19 +55,14 @@ struct PatchIO {
     const b200osd_patch_array *arrays;
     const int *indices;
     const b200osd_patch_param *params;
-    // optional per-call hull cache (see hull_gather_kernel): control points of every patch gathered into 16-byte
-    // rows, array by array: row(a, p, tile, j) = (hullRowsBefore[a] + (p - primitiveIdBase_a) * stride_a) * tiles
-    //                                            + tile * stride_a + j      -- every hull of a 16-point array is 256 B aligned
-    const float4 *hull4;
-    const int *hullRowsBefore;        // per patch array: sum over earlier arrays of numPatches * stride
-    int hullStride;                   // largest array stride (row capacity of a staged hull)
-    int hullTiles;                    // ceil(L / 4)
-    int tile;                         // component tile evaluated by this launch
     int packed;                       // outputs form one contiguous NSETS*LT-float record per coordinate (see store_outputs)
-    // shared memory: one private region of warpWords floats per warp (output transposition; staged hulls alias it)
+    int vecStore;                     // packed records may leave as 16-byte (contiguous warp block) / 8-byte (binned) stores
+    // binned order (patch_run_kernel): position j evaluates coordinate perm[j] when *binState says so
+    const int *perm;
+    const BinState *binState;
+    // shared memory: one private region of warpWords floats per warp (coordinates in, staged hulls, results out)
     int warpWords;
-    int hullPitch;                    // staged hulls: floats per lane row = (hullStride * LT) | 1
-    int stageThreshold;               // MODE 3: stage when a warp touches more distinct patches than this
+    int hullPitch;                    // floats between staged hulls (see hull_pitch)
 };
 
 enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_BASIS = 9, PT_GREGORY_TRIANGLE = 10 };
@@ -101,13 +113,6 @@ B200_HD unsigned ldg_u(const unsigned *p) {
 B200_HD float ldg_f(const float *p) {
 #ifdef __CUDA_ARCH__
     return __ldg(p);
-#else
-    return *p;
-#endif
-}
-B200_HD int ld_coord_word(const int *p) {
-#ifdef __CUDA_ARCH__
-    return ld_stream_i1(p);
 #else
     return *p;
 #endif
@@ -177,7 +182,9 @@ B200_HD void bezier_1d(float t, float (&b)[4], float (&d)[4], float (&dd)[4]) {
 B200_HD void fold_lo(float (&w)[4]) { w[2] -= w[0]; w[1] = fmaf(2.0f, w[0], w[1]); w[0] = 0.0f; }
 B200_HD void fold_hi(float (&w)[4]) { w[1] -= w[3]; w[2] = fmaf(2.0f, w[3], w[2]); w[3] = 0.0f; }
 
-// Control-point access of one patch: either through the patch's index list into the caller's primvar buffer ...
+// Control-point access of one patch.  load(j): point j; load_row(i): points 4i..4i+3 (one row of a 4 x 4 hull).
+// Either through the patch's index list into the caller's primvar buffer (host emulation in tests/emu, and the
+// reference formulation) ...
 struct CvIndirect {
     const float *src;
     int stride;
@@ -188,110 +195,79 @@ struct CvIndirect {
 #pragma unroll
         for (int c = 0; c < LT; ++c) v[c] = ldg_f(p + c);
     }
-};
-// ... or from the hull cache: point j of this patch's component tile is one aligned 16-byte row
-struct CvHull {
-    const float4 *base;
     template <int LT>
-    B200_HD void load(int j, float (&v)[LT]) const {
-#ifdef __CUDA_ARCH__
-        const float4 t = __ldg(base + j);
-#else
-        const float4 t = base[j];
-#endif
-        if (LT > 0) v[0] = t.x;
-        if (LT > 1) v[1] = t.y;
-        if (LT > 2) v[2] = t.z;
-        if (LT > 3) v[3] = t.w;
+    B200_HD void load_row(int i, float (&v)[4][LT]) const {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load<LT>(4 * i + j, v[j]);
     }
 };
 
-// ... or from the warp's shared-memory copy of its 32 hulls (MODE 2): LT floats per point, odd row pitch
-struct CvSmem {
+// ... or from the warp's shared-memory copy of the hull (patch_run_kernel): point j is one aligned unit of
+// hull_unit(LT) floats -- 16 bytes for 3 or 4 components (one 128-bit load), 8 for 2, 4 for 1 ...
+__host__ __device__ constexpr int hull_unit(int LT) { return LT >= 3 ? 4 : LT; }
+// floats between staged hulls: an odd number of units, so that the rows of different hulls start in different banks
+B200_HD int hull_pitch(int LT, int maxPoints) { return hull_unit(LT) * (maxPoints | 1); }
+
+struct CvStaged {
     const float *row;
     template <int LT>
     B200_HD void load(int j, float (&v)[LT]) const {
+        if constexpr (LT >= 3) {
+            const float4 t = *reinterpret_cast<const float4 *>(row + 4 * j);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z;
+            if constexpr (LT > 3) v[3] = t.w;
+        } else if constexpr (LT == 2) {
+            const float2 t = *reinterpret_cast<const float2 *>(row + 2 * j);
+            v[0] = t.x; v[1] = t.y;
+        } else {
+            v[0] = row[j];
+        }
+    }
+    template <int LT>
+    B200_HD void load_row(int i, float (&v)[4][LT]) const {
 #pragma unroll
-        for (int c = 0; c < LT; ++c) v[c] = row[j * LT + c];
+        for (int j = 0; j < 4; ++j) load<LT>(4 * i + j, v[j]);
+    }
+};
+
+// ... or from the per-call hull cache (patch_hull_kernel): the index buffer dereferenced once per call, LT floats per
+// point, a patch's points contiguous and its first point 16-byte aligned whenever its hull is (16- and 20-point hulls of
+// 1-4 floats are).  A row of a 4 x 4 hull is 4*LT contiguous floats: LT 128-bit loads.
+struct CvPacked {
+    const float *base;             // first point of the patch
+    bool aligned;                  // base is 16-byte aligned
+    template <int LT>
+    B200_HD void load(int j, float (&v)[LT]) const {
+#pragma unroll
+        for (int c = 0; c < LT; ++c) v[c] = ldg_f(base + j * LT + c);
+    }
+    template <int LT>
+    B200_HD void load_row(int i, float (&v)[4][LT]) const {
+#ifdef __CUDA_ARCH__
+        if (aligned) {
+            float f[4 * LT];
+#pragma unroll
+            for (int q = 0; q < LT; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(base + 4 * LT * i) + q);
+                f[4 * q + 0] = t.x; f[4 * q + 1] = t.y; f[4 * q + 2] = t.z; f[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < LT; ++c) v[j][c] = f[j * LT + c];
+            return;
+        }
+#endif
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load<LT>(4 * i + j, v[j]);
     }
 };
 
 #ifdef __CUDACC__
-extern __shared__ float b200_patch_smem[];
+extern __shared__ __align__(16) float b200_patch_smem[];
 #endif
-
-// first hull-cache row of patch p of the array described by aw (the 6 ints of its PatchArray), component tile `tile`
-B200_HD size_t hull_first_row(const int *rowsBefore, int arrayIndex, const int *aw, int p, int tiles, int tile, int *points) {
-    const int stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
-    *points = stride;
-    return ((size_t)ldg_i(rowsBefore + arrayIndex) + (size_t)(p - primBase) * (size_t)stride) * (size_t)tiles
-           + (size_t)tile * (size_t)stride;
-}
 
 constexpr int kPatchBlock = 128;
-
-// Results leave through shared memory: a warp's 32 x LT values of one output are transposed so that consecutive lanes
-// write consecutive floats (one 128-byte request per 32 floats when the output is packed, runs of LT otherwise)
-// instead of 32 scattered LT-float records.  `live` = this lane holds a real coordinate; i0 = the warp's first one.
-// io.packed: all NSETS outputs interleave into ONE record of NSETS*LT floats per coordinate (the glEvalLimit layout,
-// examples/glEvalLimit/glEvalLimit.cpp:277-287) -- then the warp's whole 32 x NSETS*LT block is staged and leaves as
-// NSETS*LT fully coalesced 128-byte rows instead of LT-float runs at a stride (3.5x fewer L2 write sectors for 18 floats).
-template <int LT, int NSETS>
-B200_HD void store_outputs(const PatchIO &io, int i, bool live, const float (&out)[NSETS][LT]) {
-#ifdef __CUDA_ARCH__
-    constexpr int R = NSETS * LT;                 // floats per packed record
-    constexpr int RP = R | 1;                     // odd row pitch: conflict-free transposition
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i0 = i - lane;
-    const unsigned livemask = __ballot_sync(0xffffffffu, live);   // lanes past the end or holding a miss write nothing
-    float *st = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
-    __syncwarp();                                               // the region may still be read as staged hulls
-    if (NSETS > 1 && io.packed) {                               // uniform across the grid
-#pragma unroll
-        for (int k = 0; k < NSETS; ++k)
-#pragma unroll
-            for (int c = 0; c < LT; ++c) st[lane * RP + k * LT + c] = out[k][c];
-        __syncwarp();
-        float *base = io.dst[0] + (size_t)i0 * (size_t)R;
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int e = q * 32 + lane;
-            const int ci = e / R, c = e - ci * R;
-            if ((livemask >> ci) & 1u) st_stream_f1(base + e, st[ci * RP + c]);
-        }
-        return;
-    }
-    // separate buffers (or a strided / partial record): all outputs are staged at once, [output][coordinate][component]
-#pragma unroll
-    for (int k = 0; k < NSETS; ++k)
-#pragma unroll
-        for (int c = 0; c < LT; ++c) st[k * 32 * LT + lane * LT + c] = out[k][c];
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < NSETS; ++k) {
-        float *d = io.dst[k];
-        if (!d) continue;                                   // uniform across the grid
-        const size_t stride = (size_t)io.dstStride[k];
-        float *base = d + (size_t)i0 * stride;
-#pragma unroll
-        for (int q = 0; q < LT; ++q) {
-            const int e = q * 32 + lane;
-            const int ci = e / LT, c = e - ci * LT;
-            if ((livemask >> ci) & 1u) st_stream_f1(base + (size_t)ci * stride + c, st[k * 32 * LT + e]);
-        }
-    }
-#else
-    if (!live) return;
-#pragma unroll
-    for (int k = 0; k < NSETS; ++k) {
-        float *d = io.dst[k];
-        if (!d) continue;
-        d += (size_t)i * (size_t)io.dstStride[k];
-#pragma unroll
-        for (int c = 0; c < LT; ++c) st_out(d + c, out[k][c]);
-    }
-#endif
-}
 
 // -------------------------------------------------------------------------------- REGULAR path --
 template <int LT, int ORDER, typename CV>
@@ -325,15 +301,15 @@ B200_HD void eval_regular(const CV &cv, float s, float t, int boundary,
         float r0[LT], r1[LT], r2[LT];
 #pragma unroll
         for (int c = 0; c < LT; ++c) { r0[c] = 0.0f; r1[c] = 0.0f; r2[c] = 0.0f; }
+        float vv[4][LT];
+        cv.template load_row<LT>(i, vv);                          // points 4i .. 4i+3
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float v[LT];
-            cv.template load<LT>(4 * i + j, v);
 #pragma unroll
             for (int c = 0; c < LT; ++c) {
-                r0[c] = fmaf(bs[j], v[c], r0[c]);
-                if (ORDER >= 1) r1[c] = fmaf(ds[j], v[c], r1[c]);
-                if (ORDER >= 2) r2[c] = fmaf(dss[j], v[c], r2[c]);
+                r0[c] = fmaf(bs[j], vv[j][c], r0[c]);
+                if (ORDER >= 1) r1[c] = fmaf(ds[j], vv[j][c], r1[c]);
+                if (ORDER >= 2) r2[c] = fmaf(dss[j], vv[j][c], r2[c]);
             }
         }
 #pragma unroll
@@ -553,7 +529,8 @@ B200_HD_NOINLINE int tri_weights(int type, float s, float t, int boundary, float
 }
 
 // --------------------------------------------------------------------------------------- kernel --
-template <int LT, int ORDER, typename CV>
+// TRI = false drops the triangle types (their code and local-memory frame) from the instantiation.
+template <int LT, int ORDER, bool TRI, typename CV>
 B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int boundary, float d1, float sign,
                              float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
@@ -563,7 +540,7 @@ B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int bound
         eval_gregory<LT, ORDER>(cv, s, t, d1, out);
     } else if (type == PT_QUADS) {
         eval_quads<LT, ORDER>(cv, s, t, d1, out);
-    } else if (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES) {
+    } else if (TRI && (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES)) {
         float w[NSETS][20];
         const int np = tri_weights<ORDER>(type, s, t, boundary, w);
         const float d2 = sign * d1 * d1;     // osd/patchBasis.h:1598: d2Scale = derivSign * d1Scale * d1Scale
@@ -581,181 +558,486 @@ B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int bound
     // unknown descriptor: the reference evaluates zero points, i.e. writes zeros
 }
 
-// MODE: 0 = control points through the index buffer; 1 = from the hull cache, read directly; 2 = from the hull cache,
-// staged through shared memory: the warp copies the hulls of its distinct patches cooperatively (consecutive lanes read
-// consecutive 16-byte rows: 2 fully used 128-byte lines per 16-point hull instead of one line touch per lane and
-// point), then every lane evaluates out of its patch's row -- for incoherent coordinates ~3.5x fewer L1 wavefronts;
-// 3 = per warp: staged when the warp touches more than io.stageThreshold distinct patches, direct otherwise (coherent
-// warps read the same rows: broadcast loads are cheaper than staging).  See DESIGN.md 4.3.
-template <int LT, int ORDER, int MODE>
-B200_HD void patch_eval_coord(const PatchIO &io, int i, bool live) {
+// number of control points of a patch type (osd/patchBasisTypes.h:241-246; unknown descriptors: none)
+B200_HD int patch_type_points(int type) {
+    return type == PT_REGULAR ? 16 : (type == PT_GREGORY_BASIS ? 20 : (type == PT_QUADS ? 4 : (type == PT_LOOP ? 12
+           : (type == PT_GREGORY_TRIANGLE ? 18 : (type == PT_TRIANGLES ? 3 : 0)))));
+}
+
+// What a coordinate needs besides (s,t): decoded from its PatchArray and PatchParam (osd/patchBasisTypes.h:366-426).
+struct PatchSite {
+    int type, boundary, cvOffset;     // cvOffset: first control-vertex index of the patch in the index buffer
+    float s, t, d1, sign;
+};
+
+B200_HD void decode_patch_site(const PatchIO &io, int arrayIndex, int patchIndex, float s, float t, PatchSite &ps) {
+    const int *aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
+    const int regDesc = ldg_i(aw + 0), irrDesc = ldg_i(aw + 1);
+    const int indexBase = ldg_i(aw + 3), stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
+    const unsigned field1 = ldg_u(&io.params[patchIndex].field1);
+    const int depth = (int)(field1 & 0xfu);
+    const int nonquad = (int)((field1 >> 4) & 1u);
+    const bool regular = ((field1 >> 5) & 1u) != 0;
+    ps.boundary = (int)((field1 >> 7) & 0x1fu);
+    const int pv = (int)((field1 >> 12) & 0x3ffu), pu = (int)((field1 >> 22) & 0x3ffu);
+    ps.type = regular ? regDesc : irrDesc;
+    ps.cvOffset = indexBase + stride * (patchIndex - primBase);
+    ps.sign = 1.0f;
+    const float fracInv = (float)(1 << (depth - nonquad));
+    const bool isTri = (ps.type == PT_LOOP || ps.type == PT_GREGORY_TRIANGLE || ps.type == PT_TRIANGLES);
+    if (isTri && (pu + pv) >= (1 << depth)) {
+        const int df = 1 << depth;
+        ps.s = (float)(df - pu) - s * fracInv;
+        ps.t = (float)(df - pv) - t * fracInv;
+        ps.sign = -1.0f;
+    } else {
+        ps.s = fmaf(s, fracInv, -(float)pu);
+        ps.t = fmaf(t, fracInv, -(float)pv);
+    }
+    ps.d1 = ps.sign * (float)(1 << depth);
+}
+
+// One coordinate evaluated straight through the index buffer: the reference formulation, used by the host emulation
+// of the kernel arithmetic (tests/emu); patch_run_kernel evaluates the same functions out of staged hulls.
+template <int LT, int ORDER>
+B200_HD void patch_eval_coord(const PatchIO &io, int i) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
     float out[NSETS][LT];
 #pragma unroll
     for (int k = 0; k < NSETS; ++k)
 #pragma unroll
         for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
-
-    int arrayIndex = 0, patchIndex = 0;
-    float s = 0.0f, t = 0.0f;
-    if (live) {
-        const int *cw = reinterpret_cast<const int *>(io.coords + i);
-        arrayIndex = ld_coord_word(cw + 0);
-        patchIndex = ld_coord_word(cw + 1);
-        s = int_as_float(ld_coord_word(cw + 3));
-        t = int_as_float(ld_coord_word(cw + 4));
-        // arrayIndex < 0 marks a sample that hit no patch (b200osd_patch_map_find writes it for holes, where
-        // Far::PatchMap::FindPatch returns NULL and the reference's callers skip the sample): its outputs stay untouched
-        live = arrayIndex >= 0;
+    const b200osd_patch_coord pc = io.coords[i];
+    // arrayIndex < 0 marks a sample that hit no patch (b200osd_patch_map_find writes it for holes, where
+    // Far::PatchMap::FindPatch returns NULL and the reference's callers skip the sample): its outputs stay untouched
+    if (pc.arrayIndex < 0) return;
+    PatchSite ps;
+    decode_patch_site(io, pc.arrayIndex, pc.patchIndex, pc.s, pc.t, ps);
+    CvIndirect cv;
+    cv.src = io.src;
+    cv.stride = io.srcStride;
+    cv.cvs = io.indices + ps.cvOffset;
+    eval_patch_type<LT, ORDER, true>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, out);
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k) {
+        float *d = io.dst[k];
+        if (!d) continue;
+        d += (size_t)i * (size_t)io.dstStride[k];
+#pragma unroll
+        for (int c = 0; c < LT; ++c) st_out(d + c, out[k][c]);
     }
-    int type = 0, boundary = 0;
-    float d1 = 1.0f, sign = 1.0f;
-    const int *aw = nullptr;
-    if (live) {
-        aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
-        const int regDesc = ldg_i(aw + 0), irrDesc = ldg_i(aw + 1);
-        const unsigned field1 = ldg_u(&io.params[patchIndex].field1);
-
-        const int depth = (int)(field1 & 0xfu);
-        const int nonquad = (int)((field1 >> 4) & 1u);
-        const bool regular = ((field1 >> 5) & 1u) != 0;
-        boundary = (int)((field1 >> 7) & 0x1fu);
-        const int pv = (int)((field1 >> 12) & 0x3ffu), pu = (int)((field1 >> 22) & 0x3ffu);
-        type = regular ? regDesc : irrDesc;
-
-        const float fracInv = (float)(1 << (depth - nonquad));
-        const bool isTri = (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES);
-        if (isTri && (pu + pv) >= (1 << depth)) {
-            const int df = 1 << depth;
-            s = (float)(df - pu) - s * fracInv;
-            t = (float)(df - pv) - t * fracInv;
-            sign = -1.0f;
-        } else {
-            s = fmaf(s, fracInv, -(float)pu);
-            t = fmaf(t, fracInv, -(float)pv);
-        }
-        d1 = sign * (float)(1 << depth);
-    }
-
-    if (MODE >= 2) {
-#ifdef __CUDA_ARCH__
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int mine = live ? patchIndex : -1;
-        int points = 0;
-        size_t row0 = 0;
-        if (live) row0 = hull_first_row(io.hullRowsBefore, arrayIndex, aw, patchIndex, io.hullTiles, io.tile, &points);
-        bool staged = true;
-        if (MODE == 3) {
-            // per warp: runs of equal patch indices (>= the number of distinct patches).  Few runs: the lanes read the
-            // same rows and broadcast loads straight from the hull cache are cheaper than staging.
-            const int prev = __shfl_up_sync(0xffffffffu, mine, 1);
-            const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || mine != prev);
-            staged = __popc(heads) > io.stageThreshold;
-        }
-        if (staged) {
-            // lanes evaluating the same patch share one staged copy: the lowest such lane (the owner) publishes the row
-            const unsigned same = __match_any_sync(0xffffffffu, mine);
-            const int owner = __ffs(same) - 1;
-            const int np = (owner == lane && live) ? points : 0;         // rows this lane's hull contributes (0: not an owner)
-            float *hs = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
-            const int pitch = io.hullPitch;
-            // rows 0..15: pass `it` copies hulls it and it+16, one per half warp (256 contiguous bytes each); rows 16
-            // apart are 16 banks apart (odd pitch), so the two halves' shared-memory stores do not collide
-            const int j = lane & 15, hsel = lane & 16;
-#pragma unroll 4
-            for (int it = 0; it < 16; ++it) {
-                const int h = it + hsel;
-                const int n = __shfl_sync(0xffffffffu, np, h);
-                const unsigned long long r = __shfl_sync(0xffffffffu, (unsigned long long)row0, h);
-                if (j < n) {
-                    const float4 v = ld_stream_f4(io.hull4 + r + j);
-                    float *d = hs + h * pitch + j * LT;
-                    d[0] = v.x;
-                    if (LT > 1) d[1] = v.y;
-                    if (LT > 2) d[2] = v.z;
-                    if (LT > 3) d[3] = v.w;
-                }
-            }
-            // rows 16..: only the few hulls that have them (Gregory end caps), one hull per pass
-            unsigned big = __ballot_sync(0xffffffffu, np > 16);
-            while (big) {
-                const int h = __ffs(big) - 1;
-                big &= big - 1;
-                const int n = __shfl_sync(0xffffffffu, np, h);
-                const unsigned long long r = __shfl_sync(0xffffffffu, (unsigned long long)row0, h);
-                const int jj = 16 + lane;
-                if (jj < n) {
-                    const float4 v = ld_stream_f4(io.hull4 + r + jj);
-                    float *d = hs + h * pitch + jj * LT;
-                    d[0] = v.x;
-                    if (LT > 1) d[1] = v.y;
-                    if (LT > 2) d[2] = v.z;
-                    if (LT > 3) d[3] = v.w;
-                }
-            }
-            __syncwarp();
-            if (live) {
-                CvSmem cv;
-                cv.row = hs + owner * pitch;
-                eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
-            }
-        } else if (MODE == 3 && live) {
-            CvHull cv;
-            cv.base = io.hull4 + row0;
-            eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
-        }
-#endif
-    } else if (live) {
-        if (MODE == 1) {
-            // hull cache: the patch's control points as compact 16-byte rows (8 sectors per coordinate instead of 18
-            // scattered ones for incoherent coordinates; broadcast reads for coherent ones)
-            int points;
-            CvHull cv;
-            cv.base = io.hull4 + hull_first_row(io.hullRowsBefore, arrayIndex, aw, patchIndex, io.hullTiles, io.tile, &points);
-            eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
-        } else {
-            const int indexBase = ldg_i(aw + 3), stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
-            CvIndirect cv;
-            cv.src = io.src;
-            cv.stride = io.srcStride;
-            cv.cvs = io.indices + indexBase + stride * (patchIndex - primBase);
-            eval_patch_type<LT, ORDER>(cv, type, s, t, boundary, d1, sign, out);
-        }
-    }
-    store_outputs<LT, NSETS>(io, i, live, out);
 }
 
 #ifdef __CUDACC__
-template <int LT, int ORDER, int MODE>
-__global__ void __launch_bounds__(kPatchBlock) patch_kernel(PatchIO io) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i - (int)(threadIdx.x & 31) >= io.n) return;          // whole warp past the end
-    patch_eval_coord<LT, ORDER, MODE>(io, i, i < io.n);
+// Results leave through shared memory.  `ix` holds the caller's index of each lane's coordinate (-1: nothing to write).
+//  * packed (all NSETS outputs interleave into ONE record of R = NSETS*LT floats per coordinate, the glEvalLimit layout,
+//    examples/glEvalLimit/glEvalLimit.cpp:277-287; also a single tightly packed output): the warp's 32 records are
+//    staged at pitch R.  In caller order (contiguous) the whole 32 x R block leaves as 128-bit stores of consecutive
+//    addresses; in binned order every record is written by consecutive lanes (64-bit when R is even), so a 72-byte
+//    record costs its 3-4 sectors once instead of 18 scattered 4-byte writes;
+//  * separate / strided outputs: per output, consecutive lanes write the consecutive floats of a record.
+template <int LT, int NSETS>
+__device__ __forceinline__ void store_outputs(const PatchIO &io, float *st, int i, bool live, bool contiguous,
+                                              const float (&out)[NSETS][LT]) {
+    constexpr int R = NSETS * LT;
+    const int lane = threadIdx.x & 31;
+    int *ix = reinterpret_cast<int *>(st + 32 * R);
+    __syncwarp();                                               // the region may still be read as staged hulls
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k) {
+        if constexpr (LT == 4) {
+            *reinterpret_cast<float4 *>(st + lane * R + k * LT) = make_float4(out[k][0], out[k][1], out[k][2], out[k][3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < LT; ++c) st[lane * R + k * LT + c] = out[k][c];
+        }
+    }
+    ix[lane] = live ? i : -1;
+    const unsigned livemask = __ballot_sync(0xffffffffu, live);
+    __syncwarp();
+    if (io.packed) {                                            // uniform across the grid
+        float *d0 = io.dst[0];
+        if (contiguous && livemask == 0xffffffffu && (io.vecStore & 1)) {
+            float *base = d0 + (size_t)(i - lane) * (size_t)R;
+            const float4 *s4 = reinterpret_cast<const float4 *>(st);
+#pragma unroll
+            for (int q = 0; q < (8 * R + 31) / 32; ++q) {
+                const int e = q * 32 + lane;
+                if (e < 8 * R) {
+                    const float4 v = s4[e];
+                    st_stream_f4(base + 4 * e, v.x, v.y, v.z, v.w);
+                }
+            }
+        } else if (R % 2 == 0 && (io.vecStore & 2)) {
+            constexpr int R2 = R % 2 == 0 ? R / 2 : 1;
+            const float2 *s2 = reinterpret_cast<const float2 *>(st);
+#pragma unroll
+            for (int q = 0; q < R2; ++q) {
+                const int e = q * 32 + lane;                    // float2 index in the staged block
+                const int ci = e / R2, c = e - ci * R2;
+                const int ii = ix[ci];
+                if (ii >= 0) {
+                    const float2 v = s2[e];
+                    st_stream_f2(d0 + (size_t)ii * (size_t)R + 2 * c, v.x, v.y);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int e = q * 32 + lane;
+                const int ci = e / R, c = e - ci * R;
+                const int ii = ix[ci];
+                if (ii >= 0) st_stream_f1(d0 + (size_t)ii * (size_t)R + c, st[e]);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k) {
+        float *d = io.dst[k];
+        if (!d) continue;                                       // uniform across the grid
+        const size_t stride = (size_t)io.dstStride[k];
+#pragma unroll
+        for (int q = 0; q < LT; ++q) {
+            const int e = q * 32 + lane;
+            const int ci = e / LT, c = e - ci * LT;
+            const int ii = ix[ci];
+            if (ii >= 0) st_stream_f1(d + (size_t)ii * stride + c, st[ci * R + k * LT + c]);
+        }
+    }
 }
 
-// Hull cache fill, one launch per patch array: thread r copies control point r of the array's index list (coalesced
-// index reads, every lane busy whatever the patch size) into its 16-byte row of the per-array layout described at
-// PatchIO::hull4; blockIdx.y = component tile.
-__global__ void __launch_bounds__(256) hull_gather_kernel(const float *src, int srcStride, int L, const int *arrayIndices,
-                                                          long long rows, int stride, long long rowsBefore, int hullTiles,
-                                                          float4 *hull4) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int tile = blockIdx.y;
-    if (r >= rows) return;
-    const int cv = ld_stream_i1(arrayIndices + r);
-    const float *g = src + (size_t)cv * (size_t)srcStride + 4 * tile;
-    const int rem = L - 4 * tile;
-    float4 v;
-    v.x = __ldg(g);
-    v.y = rem > 1 ? __ldg(g + 1) : 0.0f;
-    v.z = rem > 2 ? __ldg(g + 2) : 0.0f;
-    v.w = rem > 3 ? __ldg(g + 3) : 0.0f;
-    size_t dst = (size_t)(rowsBefore + r);
-    if (hullTiles > 1) {
-        const long long q = r / stride;
-        dst = (size_t)(rowsBefore + q * stride) * (size_t)hullTiles + (size_t)tile * (size_t)stride + (size_t)(r - q * stride);
+// One lane's coordinate: position j of the caller's order, or of the grouped order (perm).  The warp's 32 records are
+// 640 contiguous bytes in caller order: five coalesced loads, then a conflict-free transposition through `st`.
+struct LaneCoord {
+    int i, arrayIndex, patchIndex;
+    float s, t;
+    bool live;
+};
+
+__device__ __forceinline__ LaneCoord load_lane_coord(const PatchIO &io, float *st, long long j0, int lane, bool grouped) {
+    LaneCoord c;
+    const long long j = j0 + lane;
+    c.live = j < io.n;
+    c.i = (int)j; c.arrayIndex = -1; c.patchIndex = 0; c.s = 0.0f; c.t = 0.0f;
+    if (grouped) {
+        if (c.live) {
+            c.i = ld_stream_i1(io.perm + j);
+            const int *cw = reinterpret_cast<const int *>(io.coords + c.i);    // a 20-byte record: 1-2 sectors, kept in L1
+            c.arrayIndex = __ldg(cw + 0);
+            c.patchIndex = __ldg(cw + 1);
+            c.s = __int_as_float(__ldg(cw + 3));
+            c.t = __int_as_float(__ldg(cw + 4));
+        }
+    } else {
+        int *cw = reinterpret_cast<int *>(st);
+        const int *g = reinterpret_cast<const int *>(io.coords) + (size_t)j0 * 5;
+        const int words = (int)min((long long)32, (long long)io.n - j0) * 5;
+        __syncwarp();                                           // the region may still be read as staged results
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int e = q * 32 + lane;
+            if (e < words) cw[e] = ld_stream_i1(g + e);
+        }
+        __syncwarp();
+        if (c.live) {
+            c.arrayIndex = cw[lane * 5 + 0];
+            c.patchIndex = cw[lane * 5 + 1];
+            c.s = __int_as_float(cw[lane * 5 + 3]);
+            c.t = __int_as_float(cw[lane * 5 + 4]);
+        }
+        __syncwarp();
     }
-    hull4[dst] = v;
+    // arrayIndex < 0 marks a sample that hit no patch (b200osd_patch_map_find writes it for holes, where
+    // Far::PatchMap::FindPatch returns NULL and the reference's callers skip the sample): its outputs stay untouched
+    c.live = c.live && c.arrayIndex >= 0;
+    return c;
+}
+
+constexpr int kHullSlots = 8;                                   // distinct hulls staged per round (4 passes of two)
+constexpr int kPatchModeDirect = 0, kPatchModeHull = 1, kPatchModeGrouped = 2;
+
+// Hulls staged per warp: one warp per 32 coordinates, persistent grid (a block walks tiles with a grid stride).
+// Runs in the caller's order, or -- when `perm` is given and the call's state says so -- in the grouped order.
+template <int LT, int ORDER, bool TRI>
+__global__ void __launch_bounds__(kPatchBlock, 7) patch_run_kernel(PatchIO io) {
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+    constexpr int LTU = hull_unit(LT);
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int PASSES = kHullSlots / 2;
+    const int mode = io.binState ? io.binState->mode : (io.perm ? kPatchModeGrouped : kPatchModeDirect);   // grid-uniform
+    if (mode == kPatchModeHull) return;                         // this call is served by patch_hull_kernel
+    const bool grouped = io.perm != nullptr && mode == kPatchModeGrouped;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *st = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
+    const int pitch = io.hullPitch;
+    const int half = lane >> 4, jj = lane & 15;
+
+    const int tiles = (int)(((long long)io.n + 31) >> 5);
+    for (int tile = blockIdx.x * (kPatchBlock / 32) + warp; tile < tiles; tile += gridDim.x * (kPatchBlock / 32)) {
+        const LaneCoord lc = load_lane_coord(io, st, (long long)tile << 5, lane, grouped);
+        const bool live = lc.live;
+        PatchSite ps;
+        ps.type = 0; ps.boundary = 0; ps.cvOffset = 0; ps.s = 0.0f; ps.t = 0.0f; ps.d1 = 1.0f; ps.sign = 1.0f;
+        if (live) decode_patch_site(io, lc.arrayIndex, lc.patchIndex, lc.s, lc.t, ps);
+        const int np = live ? patch_type_points(ps.type) : 0;
+
+        // distinct patches of the warp: the lowest lane of each group of equal patches owns the staged copy
+        const int key = live ? lc.patchIndex : (-1 - lane);
+        const unsigned same = __match_any_sync(FULL, key);
+        const int owner = __ffs(same) - 1;
+        const unsigned owners = __ballot_sync(FULL, live && owner == lane);
+        const int slot = __popc(owners & ((1u << owner) - 1u));  // dense number of my hull among the warp's hulls
+
+        float out[NSETS][LT];
+#pragma unroll
+        for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+            for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+
+        unsigned rem = owners;
+        for (int base = 0; rem != 0u; base += kHullSlots) {
+            // this round's hulls, two per pass (one per half warp).  All passes' index loads are issued before the first
+            // vertex load: the index -> vertex dependency is paid once per round, not once per pass.
+            const unsigned round = rem;
+            int cvi[PASSES];
+            bool more = false;                                  // some hull of the round has points 16..
+#pragma unroll
+            for (int q = 0; q < PASSES; ++q) {
+                int h0 = -1, h1 = -1;
+                if (rem) { h0 = __ffs(rem) - 1; rem &= rem - 1u; }
+                if (rem) { h1 = __ffs(rem) - 1; rem &= rem - 1u; }
+                const int h = half ? h1 : h0;
+                const int hs = h < 0 ? 0 : h;
+                const int n_s = __shfl_sync(FULL, np, hs);         // every lane takes part in the shuffles
+                const int off_h = __shfl_sync(FULL, ps.cvOffset, hs);
+                const int n_h = h < 0 ? 0 : n_s;
+                more = more || n_h > 16;
+                cvi[q] = (jj < n_h) ? ldg_i(io.indices + off_h + jj) : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < PASSES; ++q) {
+                if (cvi[q] >= 0) {
+                    const float *g = io.src + (size_t)cvi[q] * (size_t)io.srcStride;
+                    float *d = st + (2 * q + half) * pitch + jj * LTU;
+                    if (LT == 4 && (io.vecStore & 4)) {
+                        *reinterpret_cast<float4 *>(d) = __ldg(reinterpret_cast<const float4 *>(g));
+                    } else if constexpr (LT >= 3) {
+                        *reinterpret_cast<float4 *>(d) = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + LT - 1));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < LT; ++c) d[c] = __ldg(g + c);
+                    }
+                }
+            }
+            if (__any_sync(FULL, more)) {                       // points 16.. of 18 / 20-point hulls (end caps): rare
+                unsigned r2 = round;
+#pragma unroll
+                for (int q = 0; q < PASSES; ++q) {
+                    int h0 = -1, h1 = -1;
+                    if (r2) { h0 = __ffs(r2) - 1; r2 &= r2 - 1u; }
+                    if (r2) { h1 = __ffs(r2) - 1; r2 &= r2 - 1u; }
+                    const int h = half ? h1 : h0;
+                    const int hs = h < 0 ? 0 : h;
+                    const int n_s = __shfl_sync(FULL, np, hs);         // every lane takes part in the shuffles
+                    const int off_h = __shfl_sync(FULL, ps.cvOffset, hs);
+                    const int n_h = h < 0 ? 0 : n_s;
+                    const int pnt = jj + 16;
+                    if (pnt < n_h) {
+                        const int ci = ldg_i(io.indices + off_h + pnt);
+                        const float *g = io.src + (size_t)ci * (size_t)io.srcStride;
+                        float *d = st + (2 * q + half) * pitch + pnt * LTU;
+#pragma unroll
+                        for (int c = 0; c < LT; ++c) d[c] = __ldg(g + c);
+                    }
+                }
+            }
+            __syncwarp();
+            if (live && slot >= base && slot < base + kHullSlots) {
+                CvStaged cv;
+                cv.row = st + (slot - base) * pitch;
+                eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, out);
+            }
+            __syncwarp();                                       // the next round (or the result staging) overwrites the rows
+        }
+        store_outputs<LT, NSETS>(io, st, lc.i, live, !grouped, out);
+    }
+}
+
+// ---- per-call hull cache: for INCOHERENT coordinates (every lane another patch) ------------------------------------
+// hull_build_kernel dereferences the index buffer once per call: cache row r = the LT floats of control vertex
+// indices[r], so a patch's hull is one contiguous block (192 bytes for 16 xyz points) at its index offset.
+// patch_hull_kernel then reads every coordinate's hull with 128-bit loads straight from the cache: ONE random access
+// of 192-240 bytes per coordinate instead of 18 scattered ones.  Both return at once unless the call's state (set by
+// the coherence probe) asks for them.
+template <int LT>
+__global__ void __launch_bounds__(256) hull_build_kernel(const float *src, int srcStride, const int *indices, long long rows,
+                                                         float *hull, const BinState *state) {
+    if (state && state->mode != kPatchModeHull) return;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        const int cv = ld_stream_i1(indices + r);
+        const float *g = src + (size_t)cv * (size_t)srcStride;
+        float *d = hull + (size_t)r * LT;
+#pragma unroll
+        for (int c = 0; c < LT; ++c) d[c] = __ldg(g + c);
+    }
+}
+
+template <int LT, int ORDER, bool TRI>
+__global__ void __launch_bounds__(kPatchBlock, 6) patch_hull_kernel(PatchIO io, const float *hull) {
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+    if (io.binState && io.binState->mode != kPatchModeHull) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *st = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
+    const int tiles = (int)(((long long)io.n + 31) >> 5);
+    for (int tile = blockIdx.x * (kPatchBlock / 32) + warp; tile < tiles; tile += gridDim.x * (kPatchBlock / 32)) {
+        const LaneCoord lc = load_lane_coord(io, st, (long long)tile << 5, lane, false);
+        float out[NSETS][LT];
+#pragma unroll
+        for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+            for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+        if (lc.live) {
+            PatchSite ps;
+            decode_patch_site(io, lc.arrayIndex, lc.patchIndex, lc.s, lc.t, ps);
+            CvPacked cv;
+            cv.base = hull + (size_t)ps.cvOffset * LT;
+            cv.aligned = ((size_t)ps.cvOffset * LT) % 4 == 0;   // the cache itself is 256-byte aligned
+            eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, out);
+        }
+        store_outputs<LT, NSETS>(io, st, lc.i, lc.live, true, out);
+    }
+}
+
+// ------------------------------------------------------------------------------------ binning --
+// Counting sort of the coordinates by patch (one bin per patch, plus bin numPatches for records that hit no patch).
+//   probe   : samples 256 warps' worth of consecutive coordinates; already coherent sets (few distinct patches per
+//             warp) are left in the caller's order -- every later bin kernel then returns at once
+//   count   : rank of every coordinate inside its bin (one atomic each)
+//   scan    : exclusive prefix sums of the bin sizes (per 4096-bin block, then over the block totals)
+//   scatter : perm[start[bin] + rank] = i
+constexpr int kBinProbeWarps = 256;
+constexpr int kScanThreads = 1024, kScanItems = 4, kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(128) bin_probe_kernel(const b200osd_patch_coord *coords, int n, BinState *state,
+                                                        int modeIfIncoherent, int force) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int total = (gridDim.x * blockDim.x) >> 5;
+    const long long start = ((long long)n * w / total) & ~31LL;
+    const long long i = start + lane;
+    const bool valid = i < n;
+    const int key = valid ? __ldg(reinterpret_cast<const int *>(coords + i) + 1) : -1;
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, valid && (lane == 0 || key != prev));
+    const unsigned lanes = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) {
+        atomicAdd(&state->heads, __popc(heads));
+        atomicAdd(&state->lanes, __popc(lanes));
+        __threadfence();
+        if (atomicAdd(&state->ticket, 1) == total - 1) {
+            __threadfence();
+            const int h = atomicAdd(&state->heads, 0), l = atomicAdd(&state->lanes, 0);
+            // incoherent: on average, a run of equal patches is shorter than 2 coordinates
+            state->mode = (force || 2 * h > l) ? modeIfIncoherent : kPatchModeDirect;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_count_kernel(const b200osd_patch_coord *coords, int n, int numPatches,
+                                                        const BinState *state, int *count, int2 *keyRank) {
+    if (state->mode != kPatchModeGrouped) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int *cw = reinterpret_cast<const int *>(coords + i);
+    const int a = __ldg(cw + 0), p = __ldg(cw + 1);
+    const int bin = (a < 0 || p < 0 || p >= numPatches) ? numPatches : p;
+    const int r = atomicAdd(count + bin, 1);
+    keyRank[i] = make_int2(bin, r);
+}
+
+__global__ void __launch_bounds__(kScanThreads) bin_scan_local_kernel(const BinState *state, const int *count, int *start,
+                                                                      int *blockSum, int numBins) {
+    if (state->mode != kPatchModeGrouped) return;
+    __shared__ int warpSum[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.x * kScanTile + tid * kScanItems;
+    int v[kScanItems], sum = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+        v[q] = (i0 + q < numBins) ? count[i0 + q] : 0;
+        sum += v[q];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warpSum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int ws = warpSum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, ws, d);
+            if (lane >= d) ws += o;
+        }
+        warpSum[lane] = ws;                                     // inclusive over warps
+    }
+    __syncthreads();
+    int run = incl - sum + (warp > 0 ? warpSum[warp - 1] : 0);  // exclusive prefix of this thread inside the block
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+        if (i0 + q < numBins) start[i0 + q] = run;
+        run += v[q];
+    }
+    if (tid == kScanThreads - 1) blockSum[blockIdx.x] = warpSum[kScanThreads / 32 - 1];
+}
+
+// exclusive scan of the block totals in place (single block; loops with a carry when there are more than 1024)
+__global__ void __launch_bounds__(kScanThreads) bin_scan_top_kernel(const BinState *state, int *blockSum, int numBlocks) {
+    if (state->mode != kPatchModeGrouped) return;
+    __shared__ int warpSum[kScanThreads / 32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < numBlocks; b0 += kScanThreads) {
+        const int v = (b0 + tid < numBlocks) ? blockSum[b0 + tid] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warpSum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int ws = warpSum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, ws, d);
+                if (lane >= d) ws += o;
+            }
+            warpSum[lane] = ws;
+        }
+        __syncthreads();
+        const int excl = carry + incl - v + (warp > 0 ? warpSum[warp - 1] : 0);
+        if (b0 + tid < numBlocks) blockSum[b0 + tid] = excl;
+        __syncthreads();
+        if (tid == 0) carry += warpSum[kScanThreads / 32 - 1];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const BinState *state, const int2 *keyRank, const int *start,
+                                                          const int *blockOff, int n, int *perm) {
+    if (state->mode != kPatchModeGrouped) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 kr = keyRank[i];
+    perm[__ldg(start + kr.x) + __ldg(blockOff + kr.x / kScanTile) + kr.y] = i;
 }
 #endif
 

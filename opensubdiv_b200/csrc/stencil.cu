@@ -8,21 +8,23 @@
 #include "stencil_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <numeric>
 #include <vector>
 
 using namespace b200osd;
 
-namespace b200osd {
-int g_stencil_variant = 0;
-}
-
 struct b200osd_stencil_table {
     int n = 0;
     long long ne = 0;
     int nCV = 0;
     int numW = 1;
+    int variant = 0;                     // kernel variant for this table (b200osd_stencil_table_set_variant); 0 = auto
+    // Unfactorized tables (far/stencilTableFactory.h:66-75 factorizeIntermediateLevels = false): rows of level l > 0
+    // reference rows of earlier levels through indices >= nCV.  levelStart holds the first row of every dependency
+    // level (+ sentinel); such a table is evaluated level by level on the stream (empty: one launch).
+    std::vector<int> levelStart;
     // verbatim copies (reference layout)
     int *d_sizes = nullptr, *d_offsets = nullptr, *d_indices = nullptr;
     float *d_w[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
@@ -43,6 +45,7 @@ struct b200osd_stencil_table {
 namespace {
 
 constexpr int kWindowRows = 2048;   // rows sorted together; keeps a window's outputs close in time and space
+constexpr int kMaxTmaStages = 6, kMaxDevicesTma = 64;
 
 template <typename T>
 int upload(T **dptr, const T *host, size_t count) {
@@ -163,14 +166,17 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
         std::memset(pool.data(), 0, poolUnits * sizeof(uint2));
         for (int s = 0; s < t->numSlices; ++s) {
             const int lo = meta[s].z;
+            const int padTo = meta[s].y * kVec;
             uint2 *sp = pool.data() + (size_t)(unsigned)meta[s].w;
             for (int lane = 0; lane < kSliceRows; ++lane) {
                 const int row = rows[(size_t)s * kSliceRows + lane];
                 if (row < 0) continue;
                 const int sz = sizes[row], off = offsets[row];
-                for (int j = 0; j < sz; ++j) {
+                // padded slots (weight 0) repeat the row's own first index: 0 * x is only ever formed with a vertex the row
+                // references anyway, so a NaN / Inf control vertex reaches exactly the rows the reference lets it reach
+                for (int j = 0; j < (sz > 0 ? padTo : 0); ++j) {
                     const size_t slot = (size_t)(j / kVec) * kSliceRows + lane;
-                    const int ix = indices[elem(off, j)];
+                    const int ix = indices[j < sz ? elem(off, j) : elem(off, 0)];
                     if (lo >= 0) reinterpret_cast<unsigned short *>(sp + slot)[j % kVec] = (unsigned short)(ix - lo);
                     else reinterpret_cast<int *>(reinterpret_cast<int4 *>(sp) + slot)[j % kVec] = ix;
                 }
@@ -332,6 +338,71 @@ int launch_sell(const StencilIO &io, const SellTable &t, const SellPlan &p, cuda
     return check_launch("sell_kernel");
 }
 
+// ---- TMA-staged kernel: persistent grid, per-warp shared-memory rings (stencil_kernels.cuh: sell_tma_kernel) ----
+// shape = 10 * (groups per chunk: 1, 2 or 4) + ring stages (2..6); e.g. 13 = one group per chunk, three stages
+template <int LL, int K, int SRCMODE, int C, int MINB>
+int launch_tma_final(const StencilIO &io, const SellTable &t, int stages, int slices, cudaStream_t st) {
+    const int block = 256, warps = block / 32;
+    const size_t smem = (size_t)warps * ((size_t)stages * tma_stage_bytes<K, C>() + kTmaBarrierBytes);
+    // per (instantiation, stage count, device): opt in to the large dynamic shared memory and size the persistent grid
+    static std::atomic<int> perSM[kMaxTmaStages + 1][kMaxDevicesTma];
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevicesTma || stages < 2 || stages > kMaxTmaStages) { set_error("TMA kernel: bad device / stage count"); return B200OSD_ERR_UNSUPPORTED; }
+    int b = perSM[stages][dev].load(std::memory_order_acquire);
+    if (b == 0) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(sell_tma_kernel<LL, K, SRCMODE, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sell_tma_kernel<LL, K, SRCMODE, C, MINB>, block, smem) != cudaSuccess || b < 1) {
+            cudaGetLastError();
+            set_error("TMA kernel does not fit (%zu bytes of shared memory per block)", smem);
+            return B200OSD_ERR_UNSUPPORTED;
+        }
+        perSM[stages][dev].store(b, std::memory_order_release);
+    }
+    const int need = (slices + warps - 1) / warps;
+    const int grid = std::min(need, b * sm_count());
+    sell_tma_kernel<LL, K, SRCMODE, C, MINB><<<grid, block, smem, st>>>(io, t, stages);
+    return check_launch("sell_tma_kernel");
+}
+
+template <int LL, int K, int SRCMODE>
+int launch_tma_shape(const StencilIO &io, const SellTable &t, int shape, int slices, cudaStream_t st) {
+    const int M = shape / 1000, C = (shape % 100) / 10, stages = shape % 10;
+    // exploration (bench sweeps): explicit resident-block hints for the headline shape
+    if (K == 1 && LL == 6 && M > 0) {
+#define B200_TMA_CASE(CC, MM) if (C == CC && M == MM) return launch_tma_final<LL, K, SRCMODE, CC, (K == 1 && LL == 6 ? MM : 1)>(io, t, stages, slices, st);
+        B200_TMA_CASE(2, 3) B200_TMA_CASE(2, 5) B200_TMA_CASE(2, 6) B200_TMA_CASE(2, 8)
+        B200_TMA_CASE(4, 3) B200_TMA_CASE(4, 4) B200_TMA_CASE(1, 8)
+#undef B200_TMA_CASE
+        return B200OSD_ERR_UNSUPPORTED;
+    }
+    // small chunks go with many resident warps (registers capped for 6 blocks of 8 warps), large chunks with few
+    if (C == 1) return launch_tma_final<LL, K, SRCMODE, 1, (K == 1 ? 6 : 3)>(io, t, stages, slices, st);
+    if (C == 2) return launch_tma_final<LL, K, SRCMODE, 2, (K == 1 ? 4 : 2)>(io, t, stages, slices, st);
+    if (C == 4 && K == 1) return launch_tma_final<LL, K, SRCMODE, 4, 2>(io, t, stages, slices, st);
+    return B200OSD_ERR_UNSUPPORTED;
+}
+
+template <int LL, int K>
+int launch_tma_mode(const StencilIO &io, const SellTable &t, int mode, int shape, int slices, cudaStream_t st) {
+    if (mode == SRC_VEC4) return launch_tma_shape<LL, K, SRC_VEC4>(io, t, shape, slices, st);
+    if (mode == SRC_VEC2) return launch_tma_shape<LL, K, SRC_VEC2>(io, t, shape, slices, st);
+    return launch_tma_shape<LL, K, SRC_SCALAR>(io, t, shape, slices, st);
+}
+
+// returns B200OSD_ERR_UNSUPPORTED (without a launch) for primvar lengths / shapes the kernel is not instantiated for
+template <int K>
+int launch_tma(const StencilIO &io, const SellTable &t, int mode, int shape, cudaStream_t st) {
+    const int slices = t.sliceEnd - t.sliceBegin;
+    switch (io.L) {
+        case 3: return launch_tma_mode<3, K>(io, t, mode, shape, slices, st);
+        case 4: return launch_tma_mode<4, K>(io, t, mode, shape, slices, st);
+        case 6: return launch_tma_mode<6, K>(io, t, mode, shape, slices, st);
+        case 8: return launch_tma_mode<8, K>(io, t, mode, shape, slices, st);
+        default: return B200OSD_ERR_UNSUPPORTED;
+    }
+}
+
 template <int LL, int B>
 void launch_batched_mode(const StencilIO &io, const SellTable &t, int mode, long long srcInst, long long dstInst, cudaStream_t st) {
     const int slices = t.sliceEnd - t.sliceBegin;
@@ -355,9 +426,104 @@ bool launch_batched(const StencilIO &io, const SellTable &t, int mode, long long
 }  // namespace
 
 // ------------------------------------------------------------------------------------ C ABI ----
+namespace {
+
+// Dependency levels of an unfactorized table: level(row) = 0 when every index < nCV, else 1 + max level of the rows it
+// references (index - nCV).  Far emits rows level by level, so levels are non-decreasing with the row number; anything
+// else (a forward reference) cannot be evaluated by launches over row ranges and is rejected.
+int find_levels(b200osd_stencil_table *t, const int *sizes, const int *offsets, const int *indices) {
+    std::vector<int> level((size_t)t->n, 0);
+    int maxLevel = 0;
+    for (int i = 0; i < t->n; ++i) {
+        int lv = 0;
+        for (int j = 0; j < sizes[i]; ++j) {
+            const int ix = indices[offsets[i] + j];
+            if (ix < t->nCV) continue;
+            const int r = ix - t->nCV;
+            if (r >= i) {
+                set_error("stencil %d references stencil %d (index %d >= %d control vertices): not in dependency order", i, r, ix, t->nCV);
+                return B200OSD_ERR_UNSUPPORTED;
+            }
+            lv = std::max(lv, level[(size_t)r] + 1);
+        }
+        if (i > 0 && lv < level[(size_t)i - 1]) {
+            set_error("stencil %d has dependency level %d after level %d: rows are not ordered by level", i, lv, level[(size_t)i - 1]);
+            return B200OSD_ERR_UNSUPPORTED;
+        }
+        level[(size_t)i] = lv;
+        maxLevel = std::max(maxLevel, lv);
+    }
+    if (maxLevel == 0) return B200OSD_OK;
+    t->levelStart.assign((size_t)maxLevel + 2, t->n);
+    for (int i = t->n - 1; i >= 0; --i) t->levelStart[(size_t)level[(size_t)i]] = i;
+    for (int l = maxLevel; l >= 0; --l)                               // empty levels cannot occur, but stay monotone
+        t->levelStart[(size_t)l] = std::min(t->levelStart[(size_t)l], t->levelStart[(size_t)l + 1]);
+    return B200OSD_OK;
+}
+
+// one launch over rows [io.start, io.end) of the table
+int eval_rows(b200osd_stencil_table *t, const StencilIO &io, int nOut, cudaStream_t st) {
+    if (!t->hasSell || t->variant == 1) {
+        CsrTable c;
+        c.sizes = t->d_sizes; c.offsets = t->d_offsets; c.indices = t->d_indices;
+        for (int k = 0; k < kMaxOut; ++k) c.w[k] = t->d_w[k];
+        return nOut == 1 ? launch_csr<1>(io, c, st) : (nOut == 3 ? launch_csr<3>(io, c, st) : launch_csr<6>(io, c, st));
+    }
+    SellTable s;
+    s.ipool = t->d_ipool;
+    for (int k = 0; k < kMaxOut; ++k) s.w4[k] = t->d_w4[k];
+    s.meta = t->d_meta;
+    s.rows = t->d_rows;
+    s.sliceBegin = t->windowSliceStart[io.start / t->window];
+    s.sliceEnd = t->windowSliceStart[(io.end + t->window - 1) / t->window];
+
+    // Source access: gather straight from the caller's buffer with the widest load its layout allows.  Measured and
+    // rejected (DESIGN.md section 6): a 16-byte repacked copy of the control vertices, 128+64-bit loads for 24-byte vertices.
+    // Variants (bench / tests): 1 CSR kernel, 2 scalar gathers, 8 persistent grid, 11 one-shot grid with 8 resident
+    // blocks/SM asked of the register allocator, 12 both; 100 + 10*C + S = streams staged by TMA bulk copies, C groups per
+    // chunk (1, 2, 4) and S ring stages per warp (2..6), e.g. 113.
+    SellPlan plan;
+    plan.mode = src_mode(io);
+    const int L = io.L;
+    const int v = t->variant;
+    if (v >= 100 && v < 9000) {
+        const int rc = nOut == 1 ? launch_tma<1>(io, s, plan.mode, v - 100, st)
+                                 : (nOut == 3 ? launch_tma<3>(io, s, plan.mode, v - 100, st) : launch_tma<6>(io, s, plan.mode, v - 100, st));
+        if (rc != B200OSD_ERR_UNSUPPORTED) return rc;            // lengths / shapes without a TMA instantiation: the default kernels
+    }
+    // measured defaults (profiles/r01*): with derivative streams the kernel is register-heavy and latency bound and the
+    // persistent grid's descriptor prefetch wins (+27 % at K=6); up to 6 floats 64 resident warps win (+10 % at L=6)
+    if (v == 0) {
+        if (nOut > 1) plan.persistent = true;
+        else if (L <= 6) plan.minBlocks = 8;
+    }
+    if (v == 2) plan.mode = SRC_SCALAR;
+    if (v == 8 || v == 12) plan.persistent = true;
+    if (v == 11 || v == 12) plan.minBlocks = 8;
+    return nOut == 1 ? launch_sell<1>(io, s, plan, st) : (nOut == 3 ? launch_sell<3>(io, s, plan, st) : launch_sell<6>(io, s, plan, st));
+}
+
+// rows [start,end) of the table: one launch, or one per dependency level of an unfactorized table (stream order makes
+// level l's rows visible to level l+1, which is what the sequential CPU evaluator gives a caller whose src and dst
+// alias as in Osd::Mesh::Refine, osd/mesh.h:505-519)
+int eval_levels(b200osd_stencil_table *t, StencilIO io, int nOut, cudaStream_t st) {
+    if (t->levelStart.empty()) return eval_rows(t, io, nOut, st);
+    const int start = io.start, end = io.end;
+    for (size_t l = 0; l + 1 < t->levelStart.size(); ++l) {
+        io.start = std::max(start, t->levelStart[l]);
+        io.end = std::min(end, t->levelStart[l + 1]);
+        if (io.end <= io.start) continue;
+        int rc = eval_rows(t, io, nOut, st);
+        if (rc) return rc;
+    }
+    return B200OSD_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
-b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, const int *sizes, const int *offsets,
+b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, int numControlVertices, const int *sizes, const int *offsets,
                                                     const int *indices, const float *weights,
                                                     const float *du, const float *dv, const float *duu,
                                                     const float *duv, const float *dvv, int flags) {
@@ -378,11 +544,13 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, const int *
     for (int i = 0; i < numStencils; ++i) ne = std::max<long long>(ne, (long long)offsets[i] + sizes[i]);
     for (long long e = 0; e < ne; ++e) maxIdx = std::max(maxIdx, indices[e]);
     t->ne = ne;
-    t->nCV = maxIdx + 1;
+    t->nCV = numControlVertices > 0 ? numControlVertices : maxIdx + 1;
     const float *w[kMaxOut] = { weights, du, dv, duu, duv, dvv };
     t->numW = (du && dv) ? ((duu && duv && dvv) ? 6 : 3) : 1;
 
-    int rc = upload(&t->d_sizes, sizes, (size_t)numStencils);
+    int rc = B200OSD_OK;
+    if (maxIdx >= t->nCV) rc = find_levels(t, sizes, offsets, indices);      // unfactorized: rows reference earlier rows
+    if (!rc) rc = upload(&t->d_sizes, sizes, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
     for (int k = 0; k < t->numW && !rc; ++k) rc = upload(&t->d_w[k], w[k], (size_t)ne);
@@ -405,6 +573,9 @@ void b200osd_stencil_table_destroy(b200osd_stencil_table *t) {
 int b200osd_stencil_table_num_stencils(const b200osd_stencil_table *t) { return t ? t->n : 0; }
 int b200osd_stencil_table_num_control_vertices(const b200osd_stencil_table *t) { return t ? t->nCV : 0; }
 long long b200osd_stencil_table_num_elements(const b200osd_stencil_table *t) { return t ? t->ne : 0; }
+int b200osd_stencil_table_num_levels(const b200osd_stencil_table *t) {
+    return !t ? 0 : (t->levelStart.empty() ? 1 : (int)t->levelStart.size() - 1);
+}
 
 const void *b200osd_stencil_table_buffer(const b200osd_stencil_table *t, int which) {
     if (!t) return nullptr;
@@ -421,9 +592,12 @@ long long b200osd_stencil_table_stream_bytes(const b200osd_stencil_table *t, int
     return (long long)t->ipoolUnits * 8 + (long long)t->totalVec * 16 * nOut + (long long)t->numSlices * (16 + 4 * kSliceRows);
 }
 
+void b200osd_stencil_table_set_variant(b200osd_stencil_table *t, int variant) { if (t) t->variant = variant; }
+int b200osd_stencil_table_get_variant(const b200osd_stencil_table *t) { return t ? t->variant : 0; }
+
 int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src, const int srcDesc[3], int nOut,
                                float *const dsts[], const int dstDescs[][3], int start, int end, void *stream) {
-    b200osd_stencil_table *t = const_cast<b200osd_stencil_table *>(tc);
+    b200osd_stencil_table *t = const_cast<b200osd_stencil_table *>(tc);      // read-only use; launch helpers take non-const
     if (!t) { set_error("stencil table is NULL"); return B200OSD_ERR_INVALID; }
     StencilIO io;
     bool noop = false;
@@ -431,41 +605,7 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
     if (rc || noop) return rc;
     if (start < 0 || end > t->n) { set_error("row range [%d,%d) outside table of %d rows", start, end, t->n); return B200OSD_ERR_INVALID; }
     if (nOut > t->numW) { set_error("table has %d weight streams, %d outputs requested", t->numW, nOut); return B200OSD_ERR_INVALID; }
-    cudaStream_t st = (cudaStream_t)stream;
-
-    if (!t->hasSell || g_stencil_variant == 1) {
-        CsrTable c;
-        c.sizes = t->d_sizes; c.offsets = t->d_offsets; c.indices = t->d_indices;
-        for (int k = 0; k < kMaxOut; ++k) c.w[k] = t->d_w[k];
-        return nOut == 1 ? launch_csr<1>(io, c, st) : (nOut == 3 ? launch_csr<3>(io, c, st) : launch_csr<6>(io, c, st));
-    }
-
-    SellTable s;
-    s.ipool = t->d_ipool;
-    for (int k = 0; k < kMaxOut; ++k) s.w4[k] = t->d_w4[k];
-    s.meta = t->d_meta;
-    s.rows = t->d_rows;
-    s.sliceBegin = t->windowSliceStart[start / t->window];
-    s.sliceEnd = t->windowSliceStart[(end + t->window - 1) / t->window];
-
-    // Source access: gather straight from the caller's buffer with the widest load its layout allows.  Measured and
-    // rejected (DESIGN.md section 6): a 16-byte repacked copy of the control vertices, 128+64-bit loads for 24-byte vertices.
-    // Variants (bench / tests): 1 CSR kernel, 2 scalar gathers, 8 persistent grid, 11 one-shot grid with 8 resident
-    // blocks/SM asked of the register allocator, 12 both.
-    SellPlan plan;
-    plan.mode = src_mode(io);
-    const int L = io.L;
-    const int v = g_stencil_variant;
-    // measured defaults (profiles/r01*): with derivative streams the kernel is register-heavy and latency bound and the
-    // persistent grid's descriptor prefetch wins (+27 % at K=6); up to 6 floats 64 resident warps win (+10 % at L=6)
-    if (v == 0) {
-        if (nOut > 1) plan.persistent = true;
-        else if (L <= 6) plan.minBlocks = 8;
-    }
-    if (v == 2) plan.mode = SRC_SCALAR;
-    if (v == 8 || v == 12) plan.persistent = true;
-    if (v == 11 || v == 12) plan.minBlocks = 8;
-    return nOut == 1 ? launch_sell<1>(io, s, plan, st) : (nOut == 3 ? launch_sell<3>(io, s, plan, st) : launch_sell<6>(io, s, plan, st));
+    return eval_levels(t, io, nOut, (cudaStream_t)stream);
 }
 
 int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *tc, const float *src, const int srcDesc[3],
@@ -482,7 +622,8 @@ int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *tc, const fl
     if (rc || noop) return rc;
     if (start < 0 || end > t->n) { set_error("row range [%d,%d) outside table of %d rows", start, end, t->n); return B200OSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    const bool batchable = t->hasSell && (io.L == 3 || io.L == 4 || io.L == 6);
+    // unfactorized tables go level by level per instance (every instance's rows feed that instance's next level)
+    const bool batchable = t->hasSell && t->levelStart.empty() && (io.L == 3 || io.L == 4 || io.L == 6);
     // alignment of every instance must allow the gather / store widths chosen for instance 0
     int mode = src_mode(io);
     if (mode == SRC_VEC4 && srcInstanceStride % 4 != 0) mode = (srcInstanceStride % 2 == 0) ? SRC_VEC2 : SRC_SCALAR;
@@ -502,6 +643,7 @@ int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *tc, const fl
     int b = 0;
     while (b < numInstances) {
         StencilIO cur = io;
+        // 64-bit instance offsets: b * stride passes 2^31 floats for a crowd of large meshes
         cur.src = io.src + (size_t)b * (size_t)srcInstanceStride;
         cur.dst[0] = io.dst[0] + (size_t)b * (size_t)dstInstanceStride;
         const int left = numInstances - b;
@@ -514,10 +656,9 @@ int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *tc, const fl
             rc = check_launch("sell_kernel_batched");
             b += 2;
         } else {
-            // single instance (or no batched kernel for this length): the ordinary path
-            int sd[3] = { srcDesc[0] + (int)((long long)b * srcInstanceStride), srcDesc[1], srcDesc[2] };
-            int d1[1][3] = { { dstDesc[0] + (int)((long long)b * dstInstanceStride), dstDesc[1], dstDesc[2] } };
-            rc = b200osd_stencil_table_eval(tc, src, sd, 1, dsts, d1, start, end, stream);
+            // single instance (or no batched kernel for this length): the ordinary path on the shifted base pointers
+            // (the gather width is re-derived from the shifted source pointer, the store width was reduced above)
+            rc = eval_levels(t, cur, 1, st);
             b += 1;
         }
         if (rc) return rc;
@@ -532,6 +673,7 @@ int b200osd_eval_stencils(const float *src, const int srcDesc[3], int nOut, floa
     bool noop = false;
     int rc = prepare_io(io, src, srcDesc, nOut, dsts, dstDescs, start, end, &noop);
     if (rc || noop) return rc;
+    if (start < 0) { set_error("start %d is negative", start); return B200OSD_ERR_INVALID; }
     if (!sizes || !offsets || !indices) { set_error("stencil arrays are NULL"); return B200OSD_ERR_INVALID; }
     CsrTable c;
     c.sizes = sizes; c.offsets = offsets; c.indices = indices;
@@ -543,8 +685,5 @@ int b200osd_eval_stencils(const float *src, const int srcDesc[3], int nOut, floa
     cudaStream_t st = (cudaStream_t)stream;
     return nOut == 1 ? launch_csr<1>(io, c, st) : (nOut == 3 ? launch_csr<3>(io, c, st) : launch_csr<6>(io, c, st));
 }
-
-void b200osd_set_stencil_variant(int v) { g_stencil_variant = v; }
-int b200osd_get_stencil_variant(void) { return g_stencil_variant; }
 
 }  // extern "C"

@@ -304,6 +304,177 @@ __global__ void __launch_bounds__(256, MINB) sell_kernel_persist(StencilIO io, S
     }
 }
 
+// ------------------------------------------------------------------------- TMA-staged SELL path --
+// Same layout, same arithmetic (element order, FMA) as sell_kernel -- results are bit-identical -- but the index and
+// weight streams never pass through the load/store unit's register path: every warp owns a ring of shared-memory
+// stages and one elected lane streams the next chunks of its slices into it with cp.async.bulk (the 1-D TMA copy;
+// SASS: UBLKCP) completing on an mbarrier, C groups (= 4C elements of 32 rows and all K weight streams) per copy set.  The lanes then read their 8/16-byte index groups and 16-byte weight groups from shared memory (conflict-free:
+// consecutive lanes, consecutive words).  What this buys over sell_kernel:
+//   * the DRAM round trip of the streams is taken by the copy engine `stages-1` chunks ahead, so a warp never waits on
+//     HBM -- only the control-vertex gathers (L1/L2 hits) are on its critical path;
+//   * no registers hold in-flight stream data, which is what capped the K = 3 / 6 kernels at 3 blocks per SM;
+//   * the grid is persistent (one wave), slices are walked with a grid stride and their descriptors / row ids are
+//     fetched one slice ahead.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// bytes of one ring stage: C groups x 32 lanes x (16 B of 32-bit indices at most + K x 16 B of weights)
+template <int K, int C> __host__ __device__ constexpr unsigned tma_stage_bytes() { return C * 32u * 16u * (1u + K); }
+constexpr unsigned kTmaBarrierBytes = 128;          // the stage barriers of one warp (8 B each), kept on their own line
+
+struct SliceCursor {           // position in a warp's sequence of chunks: slices slice, slice+nwarps, ... x groups g0, g0+kChunk, ...
+    int slice, g0;
+    int4 m, mNext;             // descriptor of `slice` and of the next slice of this warp (fetched one slice ahead)
+};
+
+// C = groups (of 4 elements) per chunk, MINB = resident blocks per SM asked of the register allocator
+template <int L, int K, int SRCMODE, int C, int MINB>
+__global__ void __launch_bounds__(256, MINB) sell_tma_kernel(StencilIO io, SellTable t, int stages) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    constexpr unsigned stageBytes = tma_stage_bytes<K, C>();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int nwarps = gridDim.x * W;
+    const int first = t.sliceBegin + blockIdx.x * W + warp;
+    if (first >= t.sliceEnd) return;                                     // whole warp: nothing to do
+    unsigned char *ring = tma_smem + (size_t)warp * ((size_t)stages * stageBytes + kTmaBarrierBytes);
+    const unsigned ringAddr = smem_u32(ring);
+    const unsigned barAddr = ringAddr + (unsigned)stages * stageBytes;
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(barAddr + 8u * s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const unsigned long long policy = l2_evict_first_policy();
+
+    auto start_cursor = [&](SliceCursor &c) {
+        c.slice = first;
+        c.g0 = 0;
+        c.m = t.meta[first];
+        c.mNext = (first + nwarps < t.sliceEnd) ? t.meta[first + nwarps] : make_int4(0, 0, 0, 0);
+    };
+    auto advance = [&](SliceCursor &c) -> bool {                          // true: moved on to the next slice
+        c.g0 += C;
+        if (c.g0 < c.m.y) return false;
+        c.slice += nwarps;
+        c.g0 = 0;
+        c.m = c.mNext;
+        if (c.slice + nwarps < t.sliceEnd) c.mNext = t.meta[c.slice + nwarps];
+        return true;
+    };
+    // the elected lane streams chunk (c.slice, c.g0 ..) into ring stage s
+    auto issue = [&](const SliceCursor &c, int s) {
+        if (lane != 0) return;
+        const int ng = min(C, c.m.y - c.g0);
+        const bool is16 = c.m.z >= 0;
+        const unsigned idxBytes = (unsigned)ng * 32u * (is16 ? 8u : 16u), wBytes = (unsigned)ng * 512u;
+        const unsigned bar = barAddr + 8u * s, dst = ringAddr + (unsigned)s * stageBytes;
+        // generic-proxy reads of this stage (made visible to this lane by the warp barrier) precede the async-proxy writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, idxBytes + (unsigned)K * wBytes);
+        if (ng > 0) {
+            const uint2 *ip = t.ipool + (size_t)(unsigned)c.m.w + (size_t)c.g0 * 32u * (is16 ? 1u : 2u);
+            bulk_g2s(dst, ip, idxBytes, bar, policy);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                bulk_g2s(dst + C * 512u * (1u + k), t.w4[k] + (size_t)(unsigned)c.m.x + (size_t)c.g0 * 32u, wBytes, bar, policy);
+        }
+    };
+
+    SliceCursor p, c;
+    start_cursor(p);
+    c = p;
+    int pStage = 0, cStage = 0;
+    unsigned phase = 0;                                                  // bit s: parity the consumer waits for on stage s
+    for (int a = 0; a < stages - 1 && p.slice < t.sliceEnd; ++a) {
+        issue(p, pStage);
+        advance(p);
+        pStage = (pStage + 1 == stages) ? 0 : pStage + 1;
+    }
+    int row = t.rows[(size_t)c.slice * kSliceRows + lane];
+    int rowNext = (c.slice + nwarps < t.sliceEnd) ? t.rows[(size_t)(c.slice + nwarps) * kSliceRows + lane] : -1;
+    float acc[K][L];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int q = 0; q < L; ++q) acc[k][q] = 0.0f;
+
+    while (c.slice < t.sliceEnd) {
+        // refill the stage consumed in the previous iteration (the warp barrier at its end ordered the reads)
+        if (p.slice < t.sliceEnd) {
+            issue(p, pStage);
+            advance(p);
+            pStage = (pStage + 1 == stages) ? 0 : pStage + 1;
+        }
+        const unsigned bar = barAddr + 8u * cStage;
+        while (!mbar_try_wait(bar, (phase >> cStage) & 1u)) { }
+        phase ^= 1u << cStage;
+
+        const unsigned char *stage = ring + (size_t)cStage * stageBytes;
+        const int ng = min(C, c.m.y - c.g0);
+        const int indexBase = c.m.z;
+#pragma unroll
+        for (int gl = 0; gl < C; ++gl) {
+            if (gl < ng) {
+                int4 id;
+                if (indexBase >= 0) {
+                    const uint2 q = *reinterpret_cast<const uint2 *>(stage + ((size_t)gl * 32 + lane) * 8);
+                    id = make_int4(indexBase + (int)(q.x & 0xffffu), indexBase + (int)(q.x >> 16),
+                                   indexBase + (int)(q.y & 0xffffu), indexBase + (int)(q.y >> 16));
+                } else {
+                    id = *reinterpret_cast<const int4 *>(stage + ((size_t)gl * 32 + lane) * 16);
+                }
+                float4 w[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    w[k] = *reinterpret_cast<const float4 *>(stage + C * 512u * (1u + k) + ((size_t)gl * 32 + lane) * 16);
+                float v0[L], v1[L], v2[L], v3[L];
+                load_vertex<L, SRCMODE>(io.src, io.srcStride, id.x, v0);
+                load_vertex<L, SRCMODE>(io.src, io.srcStride, id.y, v1);
+                load_vertex<L, SRCMODE>(io.src, io.srcStride, id.z, v2);
+                load_vertex<L, SRCMODE>(io.src, io.srcStride, id.w, v3);
+                float wx[K], wy[K], wz[K], ww[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) { wx[k] = w[k].x; wy[k] = w[k].y; wz[k] = w[k].z; ww[k] = w[k].w; }
+                accumulate<L, K>(acc, v0, wx);
+                accumulate<L, K>(acc, v1, wy);
+                accumulate<L, K>(acc, v2, wz);
+                accumulate<L, K>(acc, v3, ww);
+            }
+        }
+        if (advance(c)) {                                                // that was the slice's last chunk
+            if (row >= io.start && row < io.end) store_row<L, K>(io, row, acc);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int q = 0; q < L; ++q) acc[k][q] = 0.0f;
+            row = rowNext;
+            rowNext = (c.slice + nwarps < t.sliceEnd) ? t.rows[(size_t)(c.slice + nwarps) * kSliceRows + lane] : -1;
+        }
+        cStage = (cStage + 1 == stages) ? 0 : cStage + 1;
+        __syncwarp();
+    }
+}
+
 // Batched instances sharing one topology (the reference's pattern is one EvalStencils call per instance
 // with shifted descriptors, examples/glShareTopology/meshRefiner.h:68-88).  Instance b reads its control vertices at
 // src + b*srcInst and writes its rows at dst + b*dstInst; the index / weight streams of a slice are read ONCE for the B

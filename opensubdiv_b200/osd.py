@@ -162,7 +162,8 @@ class B200StencilTable:
         sizes, offsets, indices = arr("sizes", np.int32), arr("offsets", np.int32), arr("indices", np.int32)
         w = [arr(n, np.float32) for n in ("weights", "du", "dv", "duu", "duv", "dvv")]
         p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
-        h = capi.lib().b200osd_stencil_table_create(len(sizes), p(sizes), p(offsets), p(indices), *[p(x) for x in w],
+        ncv = int(getattr(table, "num_control_verts", 0) or 0)       # Far::StencilTable::GetNumControlVertices(); 0 = derive
+        h = capi.lib().b200osd_stencil_table_create(len(sizes), ncv, p(sizes), p(offsets), p(indices), *[p(x) for x in w],
                                                     (0 if bucketed else 1) | (2 if locality else 0) | (0 if idx16 else 4) | (8 if sort_elements else 0))
         return cls(h) if h else None
 
@@ -198,6 +199,17 @@ class B200StencilTable:
 
     def GetStreamBytes(self, nOut: int = 1) -> int:
         return capi.lib().b200osd_stencil_table_stream_bytes(self._h, nOut)
+
+    def GetNumLevels(self) -> int:
+        """1, or the number of dependency levels of an unfactorized table (evaluated one after the other)."""
+        return capi.lib().b200osd_stencil_table_num_levels(self._h)
+
+    def SetVariant(self, variant: int) -> None:
+        """Kernel variant for this table (bench / tests): 0 auto, see include/b200osd_capi.h."""
+        capi.lib().b200osd_stencil_table_set_variant(self._h, int(variant))
+
+    def GetVariant(self) -> int:
+        return capi.lib().b200osd_stencil_table_get_variant(self._h)
 
 
 class B200PatchTable:
@@ -254,6 +266,14 @@ class B200PatchTable:
     def GetFVarPatchArrayBuffer(self, fvarChannel: int = 0): return self._buf(2 + fvarChannel, 0)
     def GetFVarPatchIndexBuffer(self, fvarChannel: int = 0): return self._buf(2 + fvarChannel, 1)
     def GetFVarPatchParamBuffer(self, fvarChannel: int = 0): return self._buf(2 + fvarChannel, 2)
+
+    def SetVariant(self, variant: int) -> None:
+        """How EvalPatches* calls through this table are served: 0 automatic, 1 caller's order, 2 grouped by patch per call,
+        3 per-call hull cache (include/b200osd_capi.h)."""
+        capi.lib().b200osd_patch_table_set_variant(self._h, int(variant))
+
+    def GetVariant(self) -> int:
+        return capi.lib().b200osd_patch_table_get_variant(self._h)
 
 
 class B200PatchMap:
@@ -361,8 +381,57 @@ def _split_outputs(args):
     return outs, args[i:]
 
 
+class B200EvaluatorInstance:
+    """What B200Evaluator.Create returns: the "instantiatable" flavour of an Osd evaluator (osd/mesh.h:305-409,
+    osd/glComputeEvaluator.h:98-128).  Nothing needs compiling per descriptor set; the state worth caching is the
+    grouping of one PatchCoord set by patch.  Pass the object as `instance` to the static EvalPatches* methods."""
+
+    def __init__(self, descs):
+        self.descs = descs
+        self._plan = None
+        self._table = None
+        self._coords_ptr = None
+        self._count = 0
+
+    def __del__(self):
+        try:
+            if self._plan:
+                capi.lib().b200osd_patch_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    def BindPatchCoords(self, numPatchCoords: int, patchCoords, patchTable, deviceContext=None) -> bool:
+        """Groups the coordinates by patch on the device and keeps the grouping for later EvalPatches* calls on the same
+        buffer and table (any slot: vertex, varying, face-varying).  Call again after the coordinates change."""
+        L = capi.lib()
+        if self._plan is None or self._table is not patchTable or L.b200osd_patch_plan_capacity(self._plan) < numPatchCoords:
+            if self._plan:
+                L.b200osd_patch_plan_destroy(self._plan)
+            self._plan = L.b200osd_patch_plan_create(patchTable._h, numPatchCoords)
+            self._table = patchTable
+            if not self._plan:
+                raise capi.B200OsdError("B200Evaluator::BindPatchCoords: " + capi.last_error())
+        self._coords_ptr = _dev_ptr(patchCoords)
+        self._count = numPatchCoords
+        return capi.check(L.b200osd_patch_plan_bin(self._plan, numPatchCoords, self._coords_ptr, _stream_ptr(deviceContext)),
+                          "B200Evaluator::BindPatchCoords")
+
+    def _matches(self, patchTable, numPatchCoords, patchCoords) -> bool:
+        return (self._plan is not None and self._table is patchTable and self._count == numPatchCoords
+                and self._coords_ptr == _dev_ptr(patchCoords))
+
+
 class B200Evaluator:
     """Static evaluator; mirrors CudaEvaluator.  Every method returns the reference's bool."""
+
+    Instantiatable = True
+
+    @staticmethod
+    def Create(srcDesc, dstDesc, duDesc=None, dvDesc=None, duuDesc=None, duvDesc=None, dvvDesc=None,
+               deviceContext=None) -> B200EvaluatorInstance:
+        """EVALUATOR::Create(srcDesc, dstDesc, duDesc, dvDesc[, duuDesc, duvDesc, dvvDesc], deviceContext) (osd/mesh.h:268-283)."""
+        return B200EvaluatorInstance((srcDesc, dstDesc, duDesc, dvDesc, duuDesc, duvDesc, dvvDesc))
 
     # ---------------------------------------------------------------------------- stencils --
     @staticmethod
@@ -435,16 +504,22 @@ class B200Evaluator:
         return outs, rest
 
     @staticmethod
-    def _eval_patch_table(srcBuffer, srcDesc, outs, numPatchCoords, patchCoords, patchTable, which, deviceContext) -> bool:
-        """Through the table handle (fast path: the table may stage per-patch control hulls)."""
+    def _eval_patch_table(srcBuffer, srcDesc, outs, numPatchCoords, patchCoords, patchTable, which, deviceContext,
+                          instance=None) -> bool:
+        """Through the table handle (fast path); an instance whose bound coordinate set matches supplies
+        its cached grouping, otherwise the library groups per call when that pays."""
         n = len(outs)
         if n not in (1, 3, 6):
             raise TypeError("EvalPatches expects 1, 3 or 6 (buffer, descriptor) outputs")
         sd = _desc(srcDesc).as_c()
         dsts = (C.c_void_p * n)(*[_dev_ptr(b) for b, _ in outs])
         dds = (C.c_int * (3 * n))(*[v for _, d in outs for v in (d.offset, d.length, d.stride)])
-        rc = capi.lib().b200osd_patch_table_eval(patchTable._h, which, _dev_ptr(srcBuffer), sd, n, dsts, dds, numPatchCoords,
-                                                 _dev_ptr(patchCoords), _stream_ptr(deviceContext))
+        if isinstance(instance, B200EvaluatorInstance) and instance._matches(patchTable, numPatchCoords, patchCoords):
+            rc = capi.lib().b200osd_patch_plan_eval(instance._plan, which, _dev_ptr(srcBuffer), sd, n, dsts, dds, numPatchCoords,
+                                                    _dev_ptr(patchCoords), _stream_ptr(deviceContext))
+        else:
+            rc = capi.lib().b200osd_patch_table_eval(patchTable._h, which, _dev_ptr(srcBuffer), sd, n, dsts, dds, numPatchCoords,
+                                                     _dev_ptr(patchCoords), _stream_ptr(deviceContext))
         return capi.check(rc, "B200Evaluator::EvalPatches")
 
     @staticmethod
@@ -455,8 +530,9 @@ class B200Evaluator:
         n, coords, pt = rest[0], rest[1], rest[2]
         if deviceContext is None and len(rest) > 4:        # (..., patchTable, instance, deviceContext) given positionally
             deviceContext = rest[4]
+        instance = rest[3] if len(rest) > 3 else None
         if isinstance(pt, B200PatchTable):
-            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 0, deviceContext)
+            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 0, deviceContext, instance)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetPatchArrayBuffer(),
                                            pt.GetPatchIndexBuffer(), pt.GetPatchParamBuffer(), deviceContext)
 
@@ -467,8 +543,9 @@ class B200Evaluator:
         n, coords, pt = rest[0], rest[1], rest[2]
         if deviceContext is None and len(rest) > 4:
             deviceContext = rest[4]
+        instance = rest[3] if len(rest) > 3 else None
         if isinstance(pt, B200PatchTable):
-            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 1, deviceContext)
+            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 1, deviceContext, instance)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetVaryingPatchArrayBuffer(),
                                            pt.GetVaryingPatchIndexBuffer(), pt.GetPatchParamBuffer(), deviceContext)
 
@@ -482,8 +559,9 @@ class B200Evaluator:
         ctx_pos = 5 if has_ch else 4                       # (..., patchTable [, fvarChannel], instance, deviceContext)
         if deviceContext is None and len(rest) > ctx_pos:
             deviceContext = rest[ctx_pos]
+        instance = rest[ctx_pos - 1] if len(rest) > ctx_pos - 1 else None
         if isinstance(pt, B200PatchTable):
-            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 2 + ch, deviceContext)
+            return B200Evaluator._eval_patch_table(srcBuffer, srcDesc, outs, n, coords, pt, 2 + ch, deviceContext, instance)
         return B200Evaluator._eval_patches(srcBuffer, srcDesc, outs, n, coords, pt.GetFVarPatchArrayBuffer(ch),
                                            pt.GetFVarPatchIndexBuffer(ch), pt.GetFVarPatchParamBuffer(ch), deviceContext)
 

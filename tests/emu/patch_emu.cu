@@ -48,10 +48,10 @@ template <int ORDER>
 static void run(const PatchIO &io, int LT) {
     for (int i = 0; i < io.n; ++i) {
         switch (LT) {
-            case 1: patch_eval_coord<1, ORDER, 0>(io, i, true); break;
-            case 2: patch_eval_coord<2, ORDER, 0>(io, i, true); break;
-            case 3: patch_eval_coord<3, ORDER, 0>(io, i, true); break;
-            default: patch_eval_coord<4, ORDER, 0>(io, i, true); break;
+            case 1: patch_eval_coord<1, ORDER>(io, i); break;
+            case 2: patch_eval_coord<2, ORDER>(io, i); break;
+            case 3: patch_eval_coord<3, ORDER>(io, i); break;
+            default: patch_eval_coord<4, ORDER>(io, i); break;
         }
     }
 }
@@ -70,7 +70,7 @@ int emu_eval_patches(const float *src, const int srcDesc[3], int nOut, float *co
         for (int k = 0; k < kPatchMaxOut; ++k) { io.dst[k] = nullptr; io.dstStride[k] = 0; }
         for (int k = 0; k < nOut; ++k)
             if (dsts[k]) { io.dst[k] = dsts[k] + dstDescs[k][0] + c0; io.dstStride[k] = dstDescs[k][2]; }
-        io.hull4 = nullptr; io.hullStride = 0; io.hullTiles = 0; io.tile = 0; io.packed = 0; io.warpWords = 0; io.hullPitch = 0; io.stageThreshold = 0; io.hullRowsBefore = nullptr;
+        io.packed = 0; io.vecStore = 0; io.perm = nullptr; io.binState = nullptr; io.warpWords = 0; io.hullPitch = 0;
         io.n = n; io.coords = coords; io.arrays = arrays; io.indices = indices; io.params = params;
         if (nOut == 1) run<0>(io, LT); else if (nOut == 3) run<1>(io, LT); else run<2>(io, LT);
     }

@@ -17,14 +17,6 @@ def coords_dev(coords):
     return torch.from_numpy(np.ascontiguousarray(coords).view(np.uint8)).cuda()
 
 
-def set_variant(v):
-    capi.lib().b200osd_set_stencil_variant(v)
-
-
-def set_patch_variant(v):
-    capi.lib().b200osd_set_patch_variant(v)
-
-
 def oracle_stencils(src, src_desc, n_rows, L, t, nw, start=0, end=None, abs_scale=False):
     outs = [np.zeros((n_rows, L), np.float32) for _ in range(nw)]
     ws = [t.weights, t.du, t.dv, t.duu, t.duv, t.dvv][:nw]

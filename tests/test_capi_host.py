@@ -114,9 +114,11 @@ def test_positional_device_context_reaches_the_c_abi(monkeypatch):
     the reference signatures (osd/cudaEvaluator.h:502-523, 1068-1090) must select the stream, like the keyword form."""
     seen = {}
 
-    def fake(src, desc, outs, n, coords, pt, which, ctx):
+    def fake(src, desc, outs, n, coords, pt, which, ctx, instance=None):
         seen["which"], seen["ctx"] = which, ctx
+        seen_instance.append(instance)
         return True
+    seen_instance = []
     monkeypatch.setattr(osd.B200Evaluator, "_eval_patch_table", staticmethod(fake))
     pt = osd.B200PatchTable(None)
     D = osd.BufferDescriptor
@@ -132,6 +134,13 @@ def test_positional_device_context_reaches_the_c_abi(monkeypatch):
     assert seen == {"which": 2, "ctx": None}
     assert osd.B200Evaluator.EvalPatchesFaceVarying(1, D(0, 2, 2), 2, D(0, 2, 2), 10, 3, pt)
     assert seen == {"which": 2, "ctx": None}
+    assert all(i is None for i in seen_instance)
+    # the instance of the "instantiatable" flavour (osd/mesh.h:305-409) travels in the reference's positional slot
+    inst = osd.B200Evaluator.Create(D(0, 3, 3), D(0, 3, 3))
+    assert osd.B200Evaluator.EvalPatches(1, D(0, 3, 3), 2, D(0, 3, 3), 10, 3, pt, inst, 4)
+    assert seen == {"which": 0, "ctx": 4} and seen_instance[-1] is inst
+    assert osd.B200Evaluator.EvalPatchesFaceVarying(1, D(0, 2, 2), 2, D(0, 2, 2), 10, 3, pt, 1, inst)
+    assert seen == {"which": 3, "ctx": None} and seen_instance[-1] is inst
 
 
 def test_ctypes_prototypes_match_the_header_arity():

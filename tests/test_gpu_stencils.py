@@ -5,13 +5,14 @@ import torch
 
 import opensubdiv_b200 as osd
 from opensubdiv_b200 import synth
-from tests.gpu_util import D, dev, set_variant, oracle_stencils
+from tests.gpu_util import D, dev, oracle_stencils
 from tests.util import golden, golden_names, table_from, assert_close, REL_TOL
 
 pytestmark = pytest.mark.gpu
 OUT6 = ("p", "du", "dv", "duu", "duv", "dvv")
-# 0 auto, 1 CSR kernel on the table, 2 scalar gathers, 8 persistent grid, 11 64 warps/SM, 12 both
-VARIANTS = (0, 1, 2, 8, 11, 12)
+# 0 auto, 1 CSR kernel on the table, 2 scalar gathers, 8 persistent grid, 11 64 warps/SM, 12 both,
+# 1CS: streams staged by TMA bulk copies into per-warp shared-memory rings, C groups per chunk, S stages
+VARIANTS = (0, 1, 2, 8, 11, 12, 113, 122, 143)
 
 
 def refine_same_buffer(t, src, L, variant=0, idx16=True, sort_elements=False):
@@ -21,11 +22,11 @@ def refine_same_buffer(t, src, L, variant=0, idx16=True, sort_elements=False):
     vb.UpdateData(np.ascontiguousarray(src, np.float32), 0, ncv)
     tbl = osd.B200StencilTable.Create(t, idx16=idx16, sort_elements=sort_elements)
     assert tbl is not None and tbl.GetNumStencils() == n
-    set_variant(variant)
+    tbl.SetVariant(variant)
     try:
         assert osd.B200Evaluator.EvalStencils(vb, D(0, L, L), vb, D(ncv * L, L, L), tbl)
     finally:
-        set_variant(0)
+        tbl.SetVariant(0)
     osd.B200Evaluator.Synchronize()
     return vb.as_tensor()[ncv:].cpu().numpy()
 
@@ -77,9 +78,9 @@ def test_limit_stencils_with_derivatives(name, nw):
         args = []
         for k in range(nw):
             args += [out, D(3 * k, 3, 3 * nw)]
-        set_variant(v)
+        tbl.SetVariant(v)
         assert osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), *args, tbl)
-        set_variant(0)
+        tbl.SetVariant(0)
         res = out.cpu().numpy()
         for k in range(nw):
             assert_close(res[:, 3 * k:3 * k + 3], d["out_" + OUT6[k]], scales[k], f"{name} {OUT6[k]} variant {v}")
@@ -111,9 +112,9 @@ def test_descriptors_lengths_strides_offsets(L, stride, offset):
     tbl = osd.B200StencilTable.Create(t)
     for v in VARIANTS:
         out = torch.full((len(expect),), float("nan"), device="cuda")
-        set_variant(v)
+        tbl.SetVariant(v)
         assert osd.B200Evaluator.EvalStencils(dev(src), D(offset, L, stride), out, D(offset, L, stride), tbl)
-        set_variant(0)
+        tbl.SetVariant(0)
         got = out.cpu().numpy()
         assert np.array_equal(np.isnan(got), np.isnan(expect)), "wrote outside the described elements"
         m = ~np.isnan(expect)
@@ -131,9 +132,9 @@ def test_row_ranges_noop_and_errors():
     for (a, b) in [(0, n), (0, 1), (n - 1, n), (17, 4099), (2048, 4096), (2047, 2049), (5000, 5001)]:
         for v in VARIANTS:
             out = torch.full((n, 3), float("nan"), device="cuda")
-            set_variant(v)
+            tbl.SetVariant(v)
             assert osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), out, D(0, 3, 3), tbl, start=a, end=b)
-            set_variant(0)
+            tbl.SetVariant(0)
             got = out.cpu().numpy()
             assert np.isnan(got[:a]).all() and np.isnan(got[b:]).all(), "rows outside [start,end) were written"
             assert_close(got[a:b], full[a:b], scale[a:b], f"range {a}:{b} variant {v}")     # absolute row addressing
@@ -166,9 +167,9 @@ def test_empty_and_degenerate_tables():
     tbl = osd.B200StencilTable.Create(t)
     for v in VARIANTS:
         out = torch.full((6, 3), float("nan"), device="cuda")
-        set_variant(v)
+        tbl.SetVariant(v)
         assert osd.B200Evaluator.EvalStencils(dev(src), D(0, 3, 3), out, D(0, 3, 3), tbl)
-        set_variant(0)
+        tbl.SetVariant(0)
         assert_close(out.cpu().numpy(), exp, np.maximum(scale, 1e-6), f"degenerate variant {v}")
 
 
@@ -190,9 +191,9 @@ def test_wide_index_span_falls_back_to_32bit_indices():
     assert tbl.GetStreamBytes(1) > int(sizes.sum()) * 8          # 4-byte indices + 4-byte weights (+ padding)
     for v in VARIANTS:
         out = torch.full((n, 3), float("nan"), device="cuda")
-        set_variant(v)
+        tbl.SetVariant(v)
         assert osd.B200Evaluator.EvalStencils(dev(src), D(0, 3, 3), out, D(0, 3, 3), tbl)
-        set_variant(0)
+        tbl.SetVariant(0)
         assert_close(out.cpu().numpy(), exp, scale, f"wide span variant {v}")
 
 
@@ -322,9 +323,9 @@ def test_config2_size_independent_properties(config2):
 
     def ev(src, variant=0):
         out = torch.empty((n, 6), device="cuda")
-        set_variant(variant)
+        tbl.SetVariant(variant)
         assert osd.B200Evaluator.EvalStencils(src, D(0, 6, 6), out, D(0, 6, 6), tbl)
-        set_variant(0)
+        tbl.SetVariant(0)
         return out
     ex, ey = ev(x), ev(y)
     # partition of unity: refinement weights are convex, a constant field is reproduced

@@ -66,9 +66,9 @@ def stencil_case(name, table, Ls, nouts, iters, variants=(0, 1, 2, 8, 11, 12), l
                 args += [out, D(L * k, L, L * nout)]
             alg = table.algorithmic_bytes(nout, L, L)
             for v in variants:
-                lib.b200osd_set_stencil_variant(v)
+                tbl.SetVariant(v)
                 ms = time_calls(lambda: osd.B200Evaluator.EvalStencils(src, D(0, L, L), *args, tbl), iters)
-                lib.b200osd_set_stencil_variant(0)
+                tbl.SetVariant(0)
                 emit(case=name, kind="stencil", locality=locality, idx16=idx16, sorted_elems=sort_elements, L=L, nout=nout, variant=v, ms=ms, rows=n, elements=table.num_elements,
                      gverts_per_s=n / ms / 1e6, alg_MB=alg / 1e6, alg_GBps=alg / ms / 1e6, frac_of_measured_peak=alg / ms / 1e6 / PEAK,
                      stream_MB=tbl.GetStreamBytes(nout) / 1e6, table_build_s=build_s)
@@ -89,11 +89,11 @@ def patch_case(name, mesh, n, iters):
             for k in range(nout):
                 args += [out, D(3 * k, 3, 3 * nout)]
             alg = n * (20 + nout * 12)
-            for pv in (0, 1, 2, 3, 4):
-                capi.lib().b200osd_set_patch_variant(pv)
+            for pv in (0, 1, 2, 3):
+                pt.SetVariant(pv)
                 ms = time_calls(lambda: osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None), iters)
-                capi.lib().b200osd_set_patch_variant(0)
-                emit(case=name, kind="patch", path={0: "auto", 1: "index_buffer", 2: "hull_cache_direct", 3: "hull_cache_staged", 4: "hull_cache_per_warp"}[pv], coords=n, order=order_name,
+                pt.SetVariant(0)
+                emit(case=name, kind="patch", path={0: "auto", 1: "caller_order", 2: "grouped_per_call", 3: "hull_cache"}[pv], coords=n, order=order_name,
                      nout=nout, ms=ms, gpts_per_s=n / ms / 1e6, alg_MB=alg / 1e6, alg_GBps=alg / ms / 1e6,
                      frac_of_measured_peak=alg / ms / 1e6 / PEAK)
         # face-varying-like: 2 floats through the linear (QUADS) varying patches, value only
@@ -110,28 +110,43 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--far", action="store_true", help="config 2 / 5 tables from the reference's Far::StencilTableFactory (its row order)")
+    ap.add_argument("--variants", default="0,122")
+    ap.add_argument("--sort", action="store_true", help="sort each row's elements by control index at table creation")
     a = ap.parse_args()
+    variants = tuple(int(v) for v in a.variants.split(","))
+
+    def uniform_table(mesh, level, scheme):
+        if a.far:
+            from oracle import ref as oref
+            m = oref.Mesh.from_topology(scheme, mesh.num_verts, np.full(len(mesh.faces), mesh.faces.shape[1], np.int32),
+                                        mesh.faces.reshape(-1))
+            far = m.refine_uniform(level).stencil_table()
+            return synth.SynthStencilTable(num_control_verts=far.num_control_verts, sizes=far.sizes, offsets=far.offsets,
+                                           indices=far.indices, weights=far.weights)
+        return synth.uniform_stencil_table(mesh, level)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     OUT = open(os.path.join(ROOT, "gpurun_out", "sweep.jsonl"), "a")
     emit(kind="env", gpu=torch.cuda.get_device_name(0), peak_GBps=PEAK, version=capi.lib().b200osd_version().decode())
     if a.only in ("", "stencil"):
         mesh = synth.torus_quads(400, 250)
-        table = synth.uniform_stencil_table(mesh, 3)
+        table = uniform_table(mesh, 3, "catmark")
+        tag = "_far_order" if a.far else "_index_sorted"
         if a.quick:
-            stencil_case("cfg2_catmark_400x250_L3", table, (6, 3), (1,), 5, variants=(0,))
+            stencil_case("cfg2_catmark_400x250_L3" + tag, table, (6, 8), (1,), 20, variants=variants, sort_elements=a.sort)
         else:
-            stencil_case("cfg2_catmark_400x250_L3", table, (6, 3, 4, 8), (1,), a.iters, variants=(0, 11))
+            stencil_case("cfg2_catmark_400x250_L3" + tag, table, (6, 3, 4, 8), (1,), a.iters, variants=variants)
 
             del table
             rng = np.random.default_rng(12345)
             face = np.sort(rng.integers(0, len(mesh.faces), 1_000_000)).astype(np.int32)
             ls = synth.torus_limit_stencil_table(mesh, face, rng.random(1_000_000, dtype=np.float32),
                                                  rng.random(1_000_000, dtype=np.float32))
-            stencil_case("cfg3_limit_1M_x16", ls, (3,), (1, 3, 6), a.iters, variants=(0,))
+            stencil_case("cfg3_limit_1M_x16", ls, (3,), (1, 3, 6), a.iters, variants=variants)
             del ls
             mesh5 = synth.torus_tris(1000, 500)
-            t5 = synth.uniform_stencil_table(mesh5, 2)
-            stencil_case("cfg5_loop_1000x500_L2", t5, (3,), (1,), a.iters, variants=(0,))
+            t5 = uniform_table(mesh5, 2, "loop")
+            stencil_case("cfg5_loop_1000x500_L2" + tag, t5, (3,), (1,), a.iters, variants=variants)
 
             del t5
     if a.only in ("", "patch") and not a.quick:
