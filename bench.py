@@ -1,30 +1,36 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 Osd evaluator (BASELINE.json metric: refined verts/s, EvalStencils).
+"""bench.py -- headline benchmark of the B200 Osd evaluator (BASELINE.json metric: refined verts/s of EvalStencils and
+limit pts/s of EvalPatches, with the achieved fraction of the HBM roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): synthetic deforming Catmark quad torus 400x250 (100 000 control vertices),
-uniform level 3, last level only = 6.4 M stencil rows / 84.1 M elements, 6-float interleaved xyz+normal.
+Headline workload (BASELINE.json configs[1]): synthetic deforming Catmark quad torus 400x250 (100 000 control vertices),
+uniform level 3, last level only = 6.4 M stencil rows / 84.1 M elements, 6-float interleaved xyz+normal; the table is
+built by the reference's own Far::StencilTableFactory (rows in Far's insertion order) whenever oracle/_ref is on the
+box, by opensubdiv_b200.synth (same table, elements index-sorted) otherwise -- `config.table_order` says which.
 One step = one frame = one EvalStencils pass over the whole table.
 
-  value      refined verts/s, control points already resident in HBM, CUDA-event timed (max over ranks)
-  e2e        the same metric through the C ABI with HOST buffers: per step UpdateData (pinned H2D of the control
-             points) + EvalStencils + ReadData (D2H of the refined vertices) + Synchronize
-  roofline   algorithmic bytes (reference table formats) / device time per step vs measured HBM peak
+  value         refined verts/s, control points already resident in HBM, CUDA-event timed (max over ranks)
+  e2e           the same metric through the C ABI with HOST buffers: per step UpdateData (pinned H2D of the control
+                points) + EvalStencils + ReadData (D2H of the refined vertices) + Synchronize
+  roofline      algorithmic bytes (reference table formats) / device time per step vs measured HBM peak
   cpu_baseline  the reference's own Osd::CpuEvaluator / OmpEvaluator (oracle/_ref, compiled in place from
-             /root/reference) on this box's host cores, same table, bounded number of frames; falls back to the
-             C oracle port when the reference build is absent
-  eval_patches  (N = 1; N > 1 with --shard-patches) the second half of the metric: limit pts/s of EvalPatches with 1st +
-             2nd derivatives on 10 M PatchCoords (random and patch-sorted), FindPatches on a real adaptive table, and the
-             reference's CPU evaluators on a sample of the same coordinates
-  incumbent_cuda  (N = 1) the reference's own CUDA kernels (osd/cudaKernel.cu compiled for sm_100a under oracle/_ref) on
-             the same device buffers: a reported baseline like cpu_baseline
+                /root/reference) on this box's host cores, same table, bounded number of frames
+  config3       (N = 1) LimitStencilTable rows with du, dv, duu, duv, dvv: 1 M limit locations x 16 elements, K = 1, 3, 6
+  config5       one Loop mesh (1000x500 tri torus, uniform level 2 = 8.0 M rows), STRONG scaling: rows cut into N ranges
+                balanced on elements (b200osd_shard_plan), one 6 MB broadcast of the control points per frame
+                (b200osd_comm_broadcast, NCCL over NVLink, overlapped with the previous frame's kernel) -- at every N
+  eval_patches  (N = 1) BASELINE configs[3] on real Far tables: 60 tiled copies of catmark_car, adaptive level 3,
+                Gregory-basis end caps, face-varying UVs; 10 M samples located on the device (FindPatches) and evaluated
+                with 1st + 2nd derivatives (random and patch-sorted order), EvalPatchesFaceVarying, the whole frame as
+                one graph launch, its own roofline block, and the reference's CPU evaluators on a sample
+  incumbent_cuda  (N = 1) the reference's own CUDA kernels (osd/cudaKernel.cu compiled for sm_100a under oracle/_ref)
 
-Multi-GPU (N > 1): weak scaling.  The scene is N such meshes; rank r owns the stencil rows of mesh r (row-range
-sharding, tables pre-sharded, no collective on the table side); every frame rank 0's deformed control points of the
-WHOLE scene (N x 2.4 MB) are replicated with one NCCL broadcast -- the only exchange step -- and then each rank
-evaluates its rows.  value = all rows of all ranks / max-over-ranks time.
+Multi-GPU (N > 1), headline: weak scaling.  The scene is N such meshes; rank r owns the stencil rows of mesh r; every
+frame the root's deformed control points are handed out with b200osd_comm_scatter -- each GPU receives only the 2.4 MB
+it reads -- on a high-priority side stream while the previous frame is evaluated.  value = all rows of all ranks /
+max-over-ranks time.
 """
 from __future__ import annotations
 
@@ -100,13 +106,41 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------- workload --
+def far_uniform_table(mesh, level, scheme):
+    """The uniform last-level stencil table of `mesh` in Far's own row / element order (Far::StencilTableFactory of the
+    reference compiled under oracle/_ref: the producer of the hot path's input), or None."""
+    try:
+        from oracle import ref as oref
+        if not oref.available():
+            return None
+        from opensubdiv_b200 import synth
+        m = oref.Mesh.from_topology(scheme, mesh.num_verts, np.full(len(mesh.faces), mesh.faces.shape[1], np.int32),
+                                    mesh.faces.reshape(-1))
+        far = m.refine_uniform(level).stencil_table()
+        return synth.SynthStencilTable(num_control_verts=far.num_control_verts, sizes=far.sizes, offsets=far.offsets,
+                                       indices=far.indices, weights=far.weights)
+    except Exception as exc:
+        log(f"[bench] Far table not available ({exc}); synthetic table")
+        return None
+
+
 def build_workload():
     from opensubdiv_b200 import synth
     t0 = time.time()
     mesh = synth.torus_quads(NU, NV)
-    table = synth.uniform_stencil_table(mesh, LEVEL)
-    log(f"[bench] table built in {time.time() - t0:.1f}s: {table.num_stencils} rows, {table.num_elements} elements")
-    return mesh, table
+    table = far_uniform_table(mesh, LEVEL, "catmark")
+    order = "far_insertion_order (Far::StencilTableFactory)"
+    if table is None:
+        table = synth.uniform_stencil_table(mesh, LEVEL)
+        order = "index_sorted (opensubdiv_b200.synth)"
+    log(f"[bench] config-2 table ({order}) built in {time.time() - t0:.1f}s: {table.num_stencils} rows, {table.num_elements} elements")
+    return mesh, table, order
+
+
+def shared_config(table, order):
+    """`config` is the same object in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "rows": int(table.num_stencils), "elements": int(table.num_elements),
+            "control_verts": int(table.num_control_verts), "primvar_floats": L, "table_order": order}
 
 
 def frame_primvars(mesh, frame):
@@ -125,19 +159,33 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram read+write bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+def ncu_traffic(key="sell_kernel_dram_bytes_per_launch"):
+    """dram read+write bytes per launch of a kernel from the committed ncu summary, if any."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get("sell_kernel_dram_bytes_per_launch")
+            return json.load(open(path)).get(key)
         except Exception:
             return None
     return None
 
 
+def time_calls(torch, fn, iters, warm=3, stream=None):
+    """ms per call: CUDA events on the launching stream around `iters` back-to-back calls after `warm` warm-ups."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 # ---------------------------------------------------------------------------- reference arm --
-def cpu_reference_frames(mesh, table, frames: int, threads: int, prefer: str = "auto"):
+def cpu_reference_frames(mesh, table, frames: int, threads: int):
     """Times the reference's own CPU evaluators on full frames of the workload.  Returns a dict with verts/s."""
     from oracle import ref as oref
     src = frame_primvars(mesh, 0)
@@ -145,9 +193,6 @@ def cpu_reference_frames(mesh, table, frames: int, threads: int, prefer: str = "
     dst = np.zeros((n, L), np.float32)
     res = {}
     if oref.available():
-        from types import SimpleNamespace
-        t = SimpleNamespace(sizes=table.sizes, offsets=table.offsets, indices=table.indices, weights=table.weights,
-                            num_stencils=n, weight_streams=lambda nw: [table.weights])
         lib = oref.lib()
         impls = [("cpu", 1)]
         if lib.ref_has_openmp():
@@ -155,12 +200,12 @@ def cpu_reference_frames(mesh, table, frames: int, threads: int, prefer: str = "
         for impl, thr in impls:
             if impl == "omp":
                 lib.ref_omp_set_threads(thr)
-            oref.eval_stencils(src.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, impl=impl)   # warm
+            oref.eval_stencils(src.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], table, impl=impl)   # warm
             ts = []
             for f in range(frames):
                 s = frame_primvars(mesh, f + 1)
                 t0 = time.perf_counter()
-                oref.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, impl=impl)
+                oref.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], table, impl=impl)
                 ts.append(time.perf_counter() - t0)
             res[impl] = {"ms_per_frame": 1e3 * float(np.mean(ts)), "verts_per_s": n / float(np.mean(ts)), "cores": thr,
                          "kind": "reference"}
@@ -181,16 +226,13 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    mesh, table = build_workload()
+    mesh, table, order = build_workload()
     threads = os.cpu_count() or 1
     probe = cpu_reference_frames(mesh, table, 1, threads)
     best = max(probe, key=lambda k: probe[k]["verts_per_s"])
     from oracle import ref as oref
     n = table.num_stencils
     dst = np.zeros((n, L), np.float32)
-    from types import SimpleNamespace
-    t = SimpleNamespace(sizes=table.sizes, offsets=table.offsets, indices=table.indices, weights=table.weights,
-                        num_stencils=n, weight_streams=lambda nw: [table.weights])
 
     # bounded sample: full frames unless K of them would take more than ~2 minutes, then a leading row range
     est = probe[best]["ms_per_frame"] * 1e-3
@@ -204,7 +246,7 @@ def run_reference_arm(args):
             oracle.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], table.sizes, table.offsets,
                                  table.indices, [table.weights], 0, rows)
         else:
-            oref.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, 0, rows, impl=best)
+            oref.eval_stencils(s.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], table, 0, rows, impl=best)
         return time.perf_counter() - t0
     for w in range(args.warmup):
         step(w)
@@ -218,9 +260,9 @@ def run_reference_arm(args):
         thr = 1
         while thr <= threads:
             oref.lib().ref_omp_set_threads(thr)
-            oref.eval_stencils(s0.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, 0, rows, impl="omp")
+            oref.eval_stencils(s0.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], table, 0, rows, impl="omp")
             t0 = time.perf_counter()
-            oref.eval_stencils(s0.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], t, 0, rows, impl="omp")
+            oref.eval_stencils(s0.reshape(-1), (0, L, L), [dst.reshape(-1)], [(0, L, L)], table, 0, rows, impl="omp")
             sweep[str(thr)] = round(rows / (time.perf_counter() - t0) / 1e6, 2)
             thr *= 2
         oref.lib().ref_omp_set_threads(threads)
@@ -228,8 +270,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "refined_verts_per_sec_EvalStencils", "value": value, "unit": "verts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows": n, "elements": table.num_elements, "control_verts": table.num_control_verts,
-                   "primvar_floats": L},
+        "config": shared_config(table, order),
         "cpu_baseline": {"value": value, "unit": "verts/s", "cores": cores, "kind": probe[best]["kind"],
                          "sample": f"{args.steps} steps of rows [0,{rows}) of {n} with Osd::{'OmpEvaluator' if best == 'omp' else 'CpuEvaluator'}"
                                    f" ({best}); probe of all evaluators: "
@@ -242,129 +283,170 @@ def run_reference_arm(args):
     return 0
 
 
-# ------------------------------------------------------------------------- EvalPatches section --
-def bench_eval_patches(mesh, torch, osd, capi, log, n=10_000_000, iters=20, world=1, rank=0, strong=False):
-    """BASELINE config 4 shape of work on the synthetic torus: 10 M PatchCoords on 100 000 regular bicubic patches,
-    P + 1st + 2nd derivatives of xyz interleaved in one 18-float buffer (glEvalLimit layout), random and patch-sorted
-    coordinate order; device-resident, CUDA events.  Algorithmic bytes = n * (20 + 6*12).  Plus the reference's CPU
-    evaluators on the first 1 M of the same coordinates.
-    N > 1: EvalPatches shards by PatchCoord range with replicated tables and no data-path collective --
-    weak: every rank evaluates n coordinates on its own mesh; strong: the n coordinates are cut into N ranges
-    (shard.coord_plan).  Time = max over ranks, pts/s = all ranks' coordinates / that time."""
-    from opensubdiv_b200 import synth, shard
+# ------------------------------------------------------------------------------ config 3 --
+def bench_config3(mesh, torch, osd, iters):
+    """BASELINE configs[2]: LimitStencilTable rows with 1st and 2nd derivative weights at 1 M random limit locations of the
+    config-2 mesh (16 elements per row, 7 streams), xyz, outputs interleaved in one 18-float record.  Algorithmic bytes
+     = rows * (8 + 16*4*(1+K)) + nCV*12 + rows*K*12."""
+    from opensubdiv_b200 import synth
     D = osd.BufferDescriptor
-    n_total = n if (strong or world == 1) else n * world
-    lo, hi = (0, n)
-    if strong and world > 1:
-        lo, hi = shard.coord_plan(n, world, rank).ranges[rank]
-    ptab = synth.torus_patch_table(mesh)
-    pt = osd.B200PatchTable.Create(ptab)
+    n = 1_000_000
+    rng = np.random.default_rng(12345)
+    face = np.sort(rng.integers(0, len(mesh.faces), n)).astype(np.int32)
+    ls = synth.torus_limit_stencil_table(mesh, face, rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32))
+    tbl = osd.B200StencilTable.Create(ls)
+    ncv = ls.num_control_verts
     src = torch.from_numpy(frame_primvars(mesh, 1)[:, :3].copy()).cuda()
-    nl = hi - lo
-    out = torch.empty((max(nl, 1), 18), device="cuda")
-    args = []
-    for k in range(6):
-        args += [out, D(3 * k, 3, 18)]
     peak, _ = measured_peak()
-    res = {"workload": "torus_400x250_regular_patches_10M_coords_xyz_P+D1+D2", "coords": n_total, "coords_per_gpu": nl,
-           "patches": len(mesh.faces), "algorithmic_bytes": n_total * 92,
-           "sharding": "none (1 GPU)" if world == 1 else
-           ("PatchCoord ranges of one coordinate set, tables replicated" if strong else
-            "every rank evaluates its own coordinate set on its own mesh, tables replicated")}
-    coords_by_order = {}
-    for order, sort in (("random", False), ("sorted_by_patch", True)):
-        coords = synth.random_patch_coords(len(mesh.faces), n, seed=2024, sort_by_patch=sort)
-        coords_by_order[order] = coords
-        pc = torch.from_numpy(np.ascontiguousarray(coords[lo:hi]).view(np.uint8)).cuda()
-        for _ in range(3):
-            assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, nl, pc, pt, None)
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, nl, pc, pt, None)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        if world > 1:
-            tms = torch.tensor([ms], device="cuda")
-            torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
-            ms = float(tms.item())
-        res[order] = {"ms": ms, "pts_per_s": n_total / (ms * 1e-3), "GBps": n_total * 92 / (ms * 1e-3) / 1e9,
-                      "frac_of_measured_hbm_peak": n_total * 92 / (ms * 1e-3) / 1e9 / (peak * world)}
-        del pc
-    if world > 1:
-        return res
-    try:
-        from oracle import ref as oref
-        if oref.available():
-            m = 1_000_000
-            sel = np.ascontiguousarray(coords_by_order["random"][:m])
-            tri = oref.PatchTriple(ptab.vertex.arrays, ptab.vertex.indices, ptab.vertex.params)
-            srcn = np.ascontiguousarray(frame_primvars(mesh, 1)[:, :3])
-            outs = [np.zeros((m, 3), np.float32) for _ in range(6)]
-            cpu = {}
-            for impl, thr in (("cpu", 1), ("omp", os.cpu_count() or 1)):
-                if impl == "omp":
-                    if not oref.lib().ref_has_openmp():
-                        continue
-                    oref.lib().ref_omp_set_threads(thr)
-                t0 = time.perf_counter()
-                oref.eval_patches(srcn.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 6, sel, tri, impl=impl)
-                dt = time.perf_counter() - t0
-                cpu[impl] = {"pts_per_s": m / dt, "cores": thr, "sample": f"{m} of the random coordinates, 1 call"}
-            res["cpu_baseline"] = cpu
-    except Exception as exc:
-        res["cpu_baseline"] = {"error": str(exc)}
-    res["find_patches"] = bench_find_patches(torch, osd, n, iters)
+    res = {"workload": "limit_stencils_1M_locations_x16_elements_xyz", "rows": n}
+    for K in (1, 3, 6):
+        out = torch.empty((n, 3 * K), device="cuda")
+        a = []
+        for k in range(K):
+            a += [out, D(3 * k, 3, 3 * K)]
+        ms = time_calls(torch, lambda: osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), *a, tbl), iters)
+        alg = ls.algorithmic_bytes(K, 3, 3)
+        res[f"K{K}"] = {"ms": ms, "pts_per_s": n / (ms * 1e-3), "algorithmic_bytes": alg,
+                        "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": alg / (ms * 1e-3) / 1e9 / peak}}
+    del tbl
     return res
 
 
-def bench_find_patches(torch, osd, n, iters):
-    """SURVEY 8f-2: (ptexFace, s, t) -> Osd::PatchCoord on the device (B200PatchMap) against Far::PatchMap::FindPatch on
-    one host core (its API is one sample per call).  Table: 60 tiled copies of regression shape catmark_car, adaptive
-    level 3, Gregory end caps (1.31 M patches, depth 0-3), built by the reference compiled under oracle/_ref.
-    Algorithmic bytes = n * (12 in + 20 out); the quadtree (a few MB) stays in L2."""
+# ------------------------------------------------------------------------- EvalPatches section --
+def bench_eval_patches(torch, osd, capi, n=10_000_000, iters=10):
+    """BASELINE configs[3] on REAL Far tables: 60 tiled copies of regression shape catmark_car (98 520 control vertices,
+    creases, extraordinary vertices), adaptive level 3, Gregory-basis end caps (1.24 M REGULAR + 75 k GREGORY_BASIS
+    patches), face-varying UVs (FVAR_LINEAR_CORNERS_ONLY: mixed REGULAR / GREGORY_BASIS fvar patches), local-point
+    stencils appended.  10 M samples (ptex face, s, t), mt-style seeded, located on the device (B200PatchMap::FindPatches),
+    evaluated with P + 1st + 2nd derivatives interleaved like glEvalLimit (18 floats) and with EvalPatchesFaceVarying.
+    Algorithmic bytes: n*(20 + 6*12) for xyz, n*(20 + 8) for UVs; tables (tens of MB) counted as resident."""
+    from oracle import ref as oref
+    if not oref.available():
+        return {"skipped": "oracle/_ref/libosdref.so not present (the adaptive tables come from the reference's Far factories)"}
+    D = osd.BufferDescriptor
+    t0 = time.time()
+    m = oref.Mesh.from_shape_tiled("catmark_car", 60)
+    ptab = m.patch_table(3, end_cap="gregory", fvar=True, fvar_legacy_linear=False, inf_sharp=True, legacy_sharp_corner=False)
+    st = m.stencil_table(intermediate_levels=True, patch_table=ptab)
+    fst = m.stencil_table(mode="fvar", intermediate_levels=True, patch_table=ptab)
+    log(f"[bench] config-4 tables built in {time.time() - t0:.1f}s: {len(ptab.vertex.params)} patches, {st.num_stencils} stencils")
+    ncv, nst = st.num_control_verts, st.num_stencils
+    vb = osd.B200VertexBuffer.Create(3, ncv + nst)
+    vb.UpdateData(np.ascontiguousarray(m.positions), 0, ncv)
+    stbl = osd.B200StencilTable.Create(st)
+    pt = osd.B200PatchTable.Create(ptab)
+    pm = osd.B200PatchMap.Create(ptab)
+    rng = np.random.default_rng(2024)
+    face_h = rng.integers(0, m.num_ptex_faces, n).astype(np.int32)
+    s_h, t_h = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+    face, s, t = (torch.from_numpy(x).cuda() for x in (face_h, s_h, t_h))
+    pc = torch.zeros(n * 5, dtype=torch.int32, device="cuda")
+    found = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = torch.empty((n, 18), device="cuda")
+    args = []
+    for k in range(6):
+        args += [out, D(3 * k, 3, 18)]
+    peak, peak_src = measured_peak()
+
+    def refine():
+        assert osd.B200Evaluator.EvalStencils(vb, D(0, 3, 3), vb, D(ncv * 3, 3, 3), stbl)
+
+    def find():
+        assert pm.FindPatches(n, face, s, t, pc, found)
+    refine()
+    find()
+    res = {"workload": "catmark_car_x60_adaptive_L3_gregory_fvar_10M_samples_xyz_P+D1+D2", "coords": n,
+           "patches": int(len(ptab.vertex.params)), "gregory_patches": int(ptab.vertex.arrays["numPatches"][1]) if len(ptab.vertex.arrays) > 1 else 0,
+           "stencils": int(nst), "control_verts": int(ncv), "algorithmic_bytes": n * 92, "peak": peak, "peak_source": peak_src,
+           "refine_ms": time_calls(torch, refine, iters), "find_patches_ms": time_calls(torch, find, iters),
+           "found": int(found.item())}
+
+    def entry(ms, alg):
+        return {"ms": ms, "pts_per_s": n / (ms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
+    # random order (what FindPatches of random samples produces), as the static API serves it (probe -> per-call hull cache)
+    ms = time_calls(torch, lambda: osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None), iters)
+    res["random"] = entry(ms, n * 92)
+    res["random"]["roofline"]["traffic"] = ncu_traffic("patch_random_dram_bytes_per_call")
+    res["random"]["served_by"] = "coherence probe -> per-call hull cache (hull_build_kernel + patch_hull_kernel)"
+    # the same set grouped by patch on the device per call (counting sort), and through a cached grouping
+    pt.SetVariant(2)
+    res["random_grouped_per_call"] = entry(time_calls(torch, lambda: osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None), iters), n * 92)
+    pt.SetVariant(0)
+    inst = osd.B200Evaluator.Create(D(0, 3, 3), D(0, 3, 18))
+    res["group_once_ms"] = time_calls(torch, lambda: inst.BindPatchCoords(n, pc, pt), 3)
+    res["random_cached_grouping"] = entry(time_calls(torch, lambda: osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, inst), iters), n * 92)
+    del inst
+    # face-varying UVs (value only) on the refined fvar buffer
+    nfv, nfst = fst.num_control_verts, fst.num_stencils
+    fvb = osd.B200VertexBuffer.Create(2, nfv + nfst)
+    fvb.UpdateData(np.ascontiguousarray(m.uvs[:nfv]), 0, nfv)
+    ftbl = osd.B200StencilTable.Create(fst)
+    assert osd.B200Evaluator.EvalStencils(fvb, D(0, 2, 2), fvb, D(nfv * 2, 2, 2), ftbl)
+    uv = torch.empty((n, 2), device="cuda")
+    ms = time_calls(torch, lambda: osd.B200Evaluator.EvalPatchesFaceVarying(fvb, D(0, 2, 2), uv, D(0, 2, 2), n, pc, pt, 0, None), iters)
+    res["face_varying_uv"] = entry(ms, n * 28)
+    # the whole frame -- refine + FindPatches + EvalPatches + EvalPatchesFaceVarying -- eagerly and as ONE graph launch with
+    # the refined vertices pinned in L2 between the kernels (SURVEY.md 8f-3)
+    fg = osd.B200FrameGraph.Create()
+    fstream = torch.cuda.ExternalStream(fg.cuda_stream)
+
+    def frame(ctx):
+        assert osd.B200Evaluator.EvalStencils(vb, D(0, 3, 3), vb, D(ncv * 3, 3, 3), stbl, None, ctx)
+        assert pm.FindPatches(n, face, s, t, pc, None, deviceContext=ctx)
+        assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None, ctx)
+        assert osd.B200Evaluator.EvalPatchesFaceVarying(fvb, D(0, 2, 2), uv, D(0, 2, 2), n, pc, pt, 0, None, ctx)
+    res["frame_eager_ms"] = time_calls(torch, lambda: frame(fg), iters, stream=fstream)
     try:
-        from oracle import ref as oref
-        if not oref.available():
-            return {"skipped": "oracle/_ref/libosdref.so not present (the adaptive table comes from the reference's factories)"}
-        m = oref.Mesh.from_shape_tiled("catmark_car", 60)
-        ptab = m.patch_table(3, end_cap="gregory", fvar=False, inf_sharp=True, legacy_sharp_corner=False)
-        pm = osd.B200PatchMap.Create(ptab)
-        rng = np.random.default_rng(2024)
-        face = rng.integers(0, m.num_ptex_faces, n).astype(np.int32)
-        s, t = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
-        df, ds, dt_ = (torch.from_numpy(x).cuda() for x in (face, s, t))
-        pc = torch.empty(n * 5, dtype=torch.int32, device="cuda")
-        found = torch.zeros(1, dtype=torch.int32, device="cuda")
-        for _ in range(3):
-            assert pm.FindPatches(n, df, ds, dt_, pc, found)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            pm.FindPatches(n, df, ds, dt_, pc, found)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        peak, _ = measured_peak()
-        k = 2_000_000
-        t0 = time.perf_counter()
-        want = m.find_patches(ptab, face[:k], s[:k], t[:k])
-        cpu_dt = time.perf_counter() - t0
-        same = bool(np.array_equal(pc[:k * 5].cpu().numpy(), np.ascontiguousarray(want).view(np.int32)))
-        return {"workload": "catmark_car_x60_adaptive_L3_gregory_10M_samples", "samples": n, "patches": len(ptab.vertex.params),
-                "max_depth": pm.GetMaxDepth(), "tree_nodes": pm.GetNumNodes(), "found": int(found.item()),
-                "ms": ms, "samples_per_s": n / (ms * 1e-3), "algorithmic_bytes": n * 32,
-                "GBps": n * 32 / (ms * 1e-3) / 1e9, "frac_of_measured_hbm_peak": n * 32 / (ms * 1e-3) / 1e9 / peak,
-                "bit_identical_to_reference_on_sample": same,
-                "cpu_baseline": {"samples_per_s": k / cpu_dt, "cores": 1, "kind": "reference",
-                                 "sample": f"Far::PatchMap::FindPatch on the first {k} samples"}}
+        fg.SetL2Window(vb.BindCudaBuffer(), (ncv + nst) * 12)
+        assert fg.Begin()
+        frame(fg)
+        assert fg.End()
+        res["frame_graph_ms"] = time_calls(torch, lambda: fg.Launch(), iters, stream=fstream)
+        res["frame_graph"] = "EvalStencils -> FindPatches -> EvalPatches -> EvalPatchesFaceVarying recorded once, one cudaGraphLaunch per frame, refined vertices under a persisting L2 window"
     except Exception as exc:
-        return {"error": str(exc)}
+        res["frame_graph_ms"] = None
+        res["frame_graph"] = f"capture failed: {exc}"
+    fg.Synchronize()
+    fg.SetL2Window(None, 0)
+    # patch-sorted order (coherent: tessellation-style sets; the probe keeps the caller's order)
+    rec = pc.view(n, 5)
+    order = torch.argsort(rec[:, 1].to(torch.int64))
+    pcs = rec[order].contiguous().view(-1)
+    ms = time_calls(torch, lambda: osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pcs, pt, None), iters)
+    res["sorted_by_patch"] = entry(ms, n * 92)
+    res["sorted_by_patch"]["roofline"]["traffic"] = ncu_traffic("patch_sorted_dram_bytes_per_call")
+    res["sorted_by_patch"]["served_by"] = "coherence probe -> caller's order, hulls staged per warp (patch_run_kernel)"
+    # the reference's CPU evaluators on the first 1 M of the random coordinates
+    try:
+        k = 1_000_000
+        sel = np.ascontiguousarray(m.find_patches(ptab, face_h[:k], s_h[:k], t_h[:k]))
+        same = bool(np.array_equal(pc[:k * 5].cpu().numpy(), sel.view(np.int32)))
+        res["find_patches_bit_identical_on_sample"] = same
+        cpu_vb = np.zeros((ncv + nst, 3), np.float32)
+        cpu_vb[:ncv] = m.positions
+        oref.eval_stencils(cpu_vb.reshape(-1), (0, 3, 3), [cpu_vb.reshape(-1)], [(ncv * 3, 3, 3)], st, impl="cpu")
+        outs = [np.zeros((k, 3), np.float32) for _ in range(6)]
+        cpu = {}
+        for impl, thr in (("cpu", 1), ("omp", os.cpu_count() or 1)):
+            if impl == "omp":
+                if not oref.lib().ref_has_openmp():
+                    continue
+                oref.lib().ref_omp_set_threads(thr)
+            t1 = time.perf_counter()
+            oref.eval_patches(cpu_vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 6, sel, ptab.vertex, impl=impl)
+            dt = time.perf_counter() - t1
+            cpu[impl] = {"pts_per_s": k / dt, "cores": thr, "kind": "reference", "sample": f"{k} of the random coordinates, 1 call"}
+        res["cpu_baseline"] = cpu
+        got = out_check = None
+        assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)
+        got = out[:k].cpu().numpy()
+        res["max_abs_diff_vs_cpu_evaluator_P_on_sample"] = float(np.abs(got[:, 0:3] - outs[0]).max())
+    except Exception as exc:
+        res["cpu_baseline"] = {"error": str(exc)}
+    return res
 
 
 def bench_incumbent_cuda(mesh, table, torch, osd):
@@ -379,31 +461,19 @@ def bench_incumbent_cuda(mesh, table, torch, osd):
     ncv, n = table.num_control_verts, table.num_stencils
     tbl = osd.B200StencilTable.Create(table)
     res = {"kind": "reference CudaEvaluator kernels (osd/cudaKernel.cu), -arch=sm_100a, same box, same buffers"}
-
-    def timed(fn, iters):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
-
-    for L in (3, 6):
-        pv = frame_primvars(mesh, 1)[:, :L].copy()
-        ours = torch.zeros((ncv + n, L), device="cuda")
+    for LL in (3, 6):
+        pv = frame_primvars(mesh, 1)[:, :LL].copy()
+        ours = torch.zeros((ncv + n, LL), device="cuda")
         ours[:ncv] = torch.from_numpy(pv).cuda()
         theirs = ours.clone()
-        args_ref = (theirs.data_ptr(), theirs.data_ptr() + ncv * L * 4, L, L, L, tbl.GetSizesBuffer(), tbl.GetOffsetsBuffer(),
+        args_ref = (theirs.data_ptr(), theirs.data_ptr() + ncv * LL * 4, LL, LL, LL, tbl.GetSizesBuffer(), tbl.GetOffsetsBuffer(),
                     tbl.GetIndicesBuffer(), tbl.GetWeightsBuffer(), 0, n)
-        ms_ref = timed(lambda: cuda_ref.eval_stencils(*args_ref), 5)
-        ms_ours = timed(lambda: osd.B200Evaluator.EvalStencils(ours, D(0, L, L), ours, D(ncv * L, L, L), tbl), 20)
+        ms_ref = time_calls(torch, lambda: cuda_ref.eval_stencils(*args_ref), 5, warm=1)
+        ms_ours = time_calls(torch, lambda: osd.B200Evaluator.EvalStencils(ours, D(0, LL, LL), ours, D(ncv * LL, LL, LL), tbl), 20)
         diff = float((ours[ncv:] - theirs[ncv:]).abs().max().item())
-        res[f"eval_stencils_cfg2_L{L}"] = {"reference_cuda_ms": ms_ref, "reference_cuda_verts_per_s": n / (ms_ref * 1e-3),
-                                           "b200osd_ms": ms_ours, "b200osd_verts_per_s": n / (ms_ours * 1e-3),
-                                           "max_abs_diff": diff}
+        res[f"eval_stencils_cfg2_L{LL}"] = {"reference_cuda_ms": ms_ref, "reference_cuda_verts_per_s": n / (ms_ref * 1e-3),
+                                            "b200osd_ms": ms_ours, "b200osd_verts_per_s": n / (ms_ours * 1e-3),
+                                            "max_abs_diff": diff}
         del ours, theirs
     # EvalPatches: 2 M random coords on the torus patches, P + D1 + D2 interleaved (18 floats)
     m = 2_000_000
@@ -417,26 +487,145 @@ def bench_incumbent_cuda(mesh, table, torch, osd):
     a = []
     for k in range(6):
         a += [ours, D(3 * k, 3, 18)]
-    ms_ref = timed(lambda: cuda_ref.eval_patches(src.data_ptr(), [theirs.data_ptr() + 12 * k for k in range(6)], 3, 3, [18] * 6,
-                                                 m, pc.data_ptr(), pt.GetPatchArrayBuffer(), pt.GetPatchIndexBuffer(),
-                                                 pt.GetPatchParamBuffer()), 3)
-    ms_ours = timed(lambda: osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *a, m, pc, pt, None), 20)
+    ms_ref = time_calls(torch, lambda: cuda_ref.eval_patches(src.data_ptr(), [theirs.data_ptr() + 12 * k for k in range(6)], 3, 3, [18] * 6,
+                                                             m, pc.data_ptr(), pt.GetPatchArrayBuffer(), pt.GetPatchIndexBuffer(),
+                                                             pt.GetPatchParamBuffer()), 3, warm=1)
+    ms_ours = time_calls(torch, lambda: osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *a, m, pc, pt, None), 20)
     res["eval_patches_2M_coords_P+D1+D2"] = {"reference_cuda_ms": ms_ref, "reference_cuda_pts_per_s": m / (ms_ref * 1e-3),
                                             "b200osd_ms": ms_ours, "b200osd_pts_per_s": m / (ms_ours * 1e-3),
                                             "max_abs_diff": float((ours - theirs).abs().max().item())}
     return res
 
 
+# ------------------------------------------------------------------ pipelined frames (N >= 1) --
+class FramePipe:
+    """Frames of one stencil table over double-buffered control blocks: the exchange of frame f+1 (b200osd_comm_* on a
+    high-priority side stream) is posted before frame f's kernel is enqueued, so it travels over NVLink while frame f is
+    evaluated.  exchange(b) fills control block b; evaluate(b, r) refines block b into result region r."""
+
+    def __init__(self, torch, exchange, evaluate, active):
+        self.torch, self.exchange, self.evaluate, self.active = torch, exchange, evaluate, active
+        self.main = torch.cuda.current_stream()
+        self.side = torch.cuda.Stream(priority=-1)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self.free + self.ready:
+            e.record(self.main)
+        self.f, self.posted = 0, -1
+
+    def post(self, g, before=None):
+        b = g % 2
+        if before is not None:
+            before(g)                                            # e.g. the H2D upload of frame g's control points (root)
+        if self.active:
+            self.side.wait_event(self.free[b])                   # the last reader of this block has finished
+            self.side.wait_stream(self.main)                     # the producer of this frame's data (root)
+            self.exchange(b, self.side)
+            self.ready[b].record(self.side)
+        else:
+            self.ready[b].record(self.main)
+        self.posted = g
+
+    def step(self, region=0, before=None, after=None):
+        f = self.f
+        for g in (f, f + 1):                                     # prologue posts f, steady state posts only f+1
+            if g > self.posted:
+                self.post(g, before)
+        self.main.wait_event(self.ready[f % 2])
+        self.evaluate(f % 2, region)
+        self.free[f % 2].record(self.main)
+        if after is not None:
+            after(f, region)
+        self.f = f + 1
+
+
+def timed_steps(torch, dist, world, step_fn, steps, warmup, stream, tail_events=()):
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for w in range(warmup):
+        step_fn(w)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(steps):
+        step_fn(warmup + k)
+    for e in tail_events:                                        # read-backs still in flight belong to the timed region
+        stream.wait_event(e)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return ms
+
+
+def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps, warmup):
+    """BASELINE configs[4]: ONE Loop mesh (1000x500 tri torus = 500 000 control vertices, 1 M faces), uniform level 2 =
+    8.0 M rows, xyz; rows cut into `world` contiguous ranges balanced on elements (b200osd_shard_plan, cuts on the
+    2048-row bucketing window); every frame all 6 MB of control points are broadcast from rank 0 (b200osd_comm_broadcast
+    on a high-priority side stream, double-buffered against the previous frame's kernel); outputs stay sharded."""
+    from opensubdiv_b200 import synth
+    D = osd.BufferDescriptor
+    t0 = time.time()
+    mesh = synth.torus_tris(1000, 500)
+    table = far_uniform_table(mesh, 2, "loop")
+    order = "far_insertion_order"
+    if table is None:
+        table = synth.uniform_stencil_table(mesh, 2)
+        order = "index_sorted (synth)"
+    n_total, ncv = table.num_stencils, table.num_control_verts
+    alg_total = table.algorithmic_bytes(1, 3, 3)
+    plan = shard.ShardPlan.for_table(table.sizes, world, rank, align=2048)
+    local = shard.local_table(table, plan) if world > 1 else table
+    alg_local = local.algorithmic_bytes(1, 3, 3)
+    n = local.num_stencils
+    tbl = osd.B200StencilTable.Create(local)
+    assert tbl is not None, capi.last_error()
+    log(f"[bench] rank {rank}: config-5 table ({order}), rows [{plan.start},{plan.end}) of {n_total}, built in {time.time() - t0:.1f}s")
+    vb = osd.B200VertexBuffer.Create(3, 2 * ncv + n)
+    vt = vb.as_tensor()
+    for b in (0, 1):
+        vb.UpdateData(np.ascontiguousarray(synth.deform(mesh.positions, b), np.float32), b * ncv, ncv)
+    blocks = [vt[:ncv], vt[ncv:2 * ncv]]
+    torch.cuda.synchronize()
+
+    def exchange(b, stream):
+        assert comm.Broadcast(blocks[b], ncv * 3, 0, deviceContext=stream)
+
+    def evaluate(b, region):
+        assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, D(2 * ncv * 3, 3, 3), tbl)
+    pipe = FramePipe(torch, exchange, evaluate, active=world > 1)
+    ms = timed_steps(torch, dist, world, lambda k: pipe.step(), steps, warmup, torch.cuda.current_stream())
+    ms_step = ms / steps
+    peak, _ = measured_peak()
+    sizes = {}
+    for sz in np.unique(table.sizes):
+        sizes[str(int(sz))] = int((table.sizes == sz).sum())
+    return {"workload": "loop_tri_torus_1000x500_uniform_L2_laststencils_xyz", "scaling": "strong", "table_order": order,
+            "rows": int(n_total), "elements": int(table.num_elements), "control_verts": int(ncv), "row_sizes": sizes,
+            "rows_this_rank": int(n), "imbalance": plan.imbalance(table.sizes),
+            "exchange": "none (1 GPU)" if world == 1 else f"b200osd_comm_broadcast of {ncv * 12} B per frame from rank 0, side stream, double-buffered",
+            "n_gpus": world, "steps": steps, "ms_per_step": ms_step, "value": n_total / (ms_step * 1e-3), "unit": "verts/s",
+            "roofline_per_gpu": {"bound": "hbm", "achieved": alg_local / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": alg_local / (ms_step * 1e-3) / 1e9 / peak, "algorithmic_bytes_this_rank": int(alg_local),
+                                 "algorithmic_bytes_total": int(alg_total)}}
+
+
 # --------------------------------------------------------------------------------- B200 arm --
 def run_b200_arm(args):
     import faulthandler
-    # a run must never hang the box: dump every thread's stack and leave after 5 minutes (a first `import torch` on a
+    # a run must never hang the box: dump every thread's stack and leave after 10 minutes (a first `import torch` on a
     # fresh box alone can take a minute)
-    faulthandler.dump_traceback_later(300, exit=True)
+    faulthandler.dump_traceback_later(600, exit=True)
     import torch
     import torch.distributed as dist
     import opensubdiv_b200 as osd
-    from opensubdiv_b200 import capi
+    from opensubdiv_b200 import capi, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -444,58 +633,46 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    comm = comm_wide = None
     if world > 1:
-        # NCCL kernels on a high-priority stream: their few CTAs are dispatched as soon as an SM slot frees up instead
-        # of queueing behind the 25 000-block evaluation grid (which would serialise broadcast and kernel)
-        opts = None
-        try:
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.is_high_priority_stream = True
-        except Exception:
-            opts = None
-        if opts is not None:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
-        else:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # torch.distributed is the bootstrap and the timing reduction; the per-frame exchange is the C data plane
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                 # the version banner goes to stdout: keep stdout to the one JSON line
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # two communicators: the headline's 2.4 MB per-rank hand-out hides behind a 0.16 ms kernel and should take as few SMs
+        # from it as possible (2 CTAs); config 5's 6 MB broadcast is on the critical path of 15-60 us kernels (NCCL's default)
+        comm = shard.B200Comm.Create(max_ctas=2)
+        comm_wide = shard.B200Comm.Create()
     D = osd.BufferDescriptor
     lib = capi.lib()
 
-    from opensubdiv_b200 import shard
-    mesh, table = build_workload()
-    ncv = table.num_control_verts
-    strong = (args.scaling == "strong") and world > 1
-    if strong:
-        # one mesh, rows cut into `world` contiguous ranges balanced on stencil elements; every rank needs all control points
-        plan = shard.ShardPlan.for_table(table.sizes, world, rank, align=2048)
-        alg_bytes_total = table.algorithmic_bytes(1, L, L)
-        table = shard.local_table(table, plan)
-        meshes_in_scene, my_mesh = 1, 0
-        total_rows = sum(b - a for a, b in plan.ranges)
-    else:
-        # `world` meshes; rank r owns all rows of mesh r; the scene's control points are replicated every frame
-        alg_bytes_total = table.algorithmic_bytes(1, L, L) * world
-        meshes_in_scene, my_mesh = world, rank
-        total_rows = table.num_stencils * world
-    n = table.num_stencils
+    mesh, table, order = build_workload()
+    config = shared_config(table, order)
+    ncv, n = table.num_control_verts, table.num_stencils
+    # weak scaling: `world` meshes; rank r owns all rows of mesh r
+    alg_bytes = table.algorithmic_bytes(1, L, L)
+    total_rows = n * world
     t0 = time.time()
     tbl = osd.B200StencilTable.Create(table)
     assert tbl is not None, capi.last_error()
+    if args.variant:
+        tbl.SetVariant(args.variant)
     log(f"[bench] rank {rank}: B200StencilTable of {n} rows built in {time.time() - t0:.1f}s")
 
-    # vertex buffer = [ control block A | control block B | this rank's refined rows ]; A/B are the two halves of the
-    # double-buffered per-frame broadcast (frame f lives in block f % 2)
-    scene_cv = ncv * meshes_in_scene
-    # ... and two refined regions so that (host-buffer path) the D2H read-back of frame f overlaps frame f+1's kernel
-    vb = osd.B200VertexBuffer.Create(L, 2 * scene_cv + 2 * n)
+    # vertex buffer = [ control block A | control block B | refined region 0 | refined region 1 ]: A/B are the two halves of
+    # the double-buffered per-frame exchange (frame f lives in block f % 2); two refined regions so that (host-buffer path)
+    # the D2H read-back of frame f overlaps frame f+1's kernel
+    vb = osd.B200VertexBuffer.Create(L, 2 * ncv + 2 * n)
     assert vb is not None, capi.last_error()
     vt = vb.as_tensor()
-    blocks = [vt[:scene_cv], vt[scene_cv:2 * scene_cv]]
-    src_descs = [D((b * scene_cv + my_mesh * ncv) * L, L, L) for b in (0, 1)]
-    dst_vertex = [2 * scene_cv, 2 * scene_cv + n]
+    blocks = [vt[:ncv], vt[ncv:2 * ncv]]
+    src_descs = [D(b * ncv * L, L, L) for b in (0, 1)]
+    dst_vertex = [2 * ncv, 2 * ncv + n]
     dst_descs = [D(v * L, L, L) for v in dst_vertex]
-    bc = shard.FrameBroadcaster(blocks, root=0)
-
-    frames = [torch.from_numpy(np.tile(frame_primvars(mesh, f), (meshes_in_scene, 1))).pin_memory() for f in range(4)]
+    # the root holds the whole scene's control points of a frame (world meshes) and hands every rank its own mesh
+    scene = [torch.empty((world * ncv, L), device="cuda") for _ in (0, 1)] if (world > 1 and rank == 0) else [None, None]
+    frames = [torch.from_numpy(frame_primvars(mesh, f)).pin_memory() for f in range(4)]
+    scene_frames = [torch.from_numpy(np.tile(frames[f].numpy(), (world, 1))).pin_memory() for f in range(4)] if (world > 1 and rank == 0) else None
     host_out = [torch.empty((n, L), dtype=torch.float32).pin_memory() for _ in range(2)]
     stream = torch.cuda.current_stream()
     copy_stream = torch.cuda.Stream()
@@ -504,127 +681,108 @@ def run_b200_arm(args):
     for e in d2h_done:
         e.record(stream)
     for b in (0, 1):                                       # device-resident control points for the `value` measurement
-        vb.UpdateData(frames[b], b * scene_cv, scene_cv)
+        vb.UpdateData(frames[b], b * ncv, ncv)
+        if scene[b] is not None:
+            scene[b].copy_(scene_frames[b], non_blocking=True)
     torch.cuda.synchronize()
 
-    # Frames are pipelined: the broadcast of frame f+1 is posted BEFORE frame f's kernel is enqueued, so on the side
-    # stream it only waits for the kernel that last read its buffer (frame f-1) and travels while frame f is evaluated.
-    state = {"f": 0, "posted": -1}
+    def exchange(b, side):
+        assert comm.Scatter(scene[b], blocks[b], ncv * L, 0, deviceContext=side)
 
-    def advance(e2e):
-        f = state["f"]
-        for g in (f, f + 1):                                   # prologue posts f, steady state posts only f+1
-            if g > state["posted"]:
-                if e2e and rank == 0:                          # host-buffer path: this frame's control points H2D (root)
-                    vb.UpdateData(frames[g % len(frames)], (g % 2) * scene_cv, scene_cv)
-                bc.post(g)
-                state["posted"] = g
-        bc.wait(f)
-        r = f % 2 if e2e else 0
-        if e2e:
-            stream.wait_event(d2h_done[r])                     # refined region r: read-back of frame f-2 has finished
-        ok = osd.B200Evaluator.EvalStencils(vb, src_descs[f % 2], vb, dst_descs[r], tbl)
-        assert ok
-        bc.release(f)
-        if e2e:                                                # D2H of this rank's refined vertices on the copy stream
-            kernel_done[r].record(stream)
-            copy_stream.wait_event(kernel_done[r])
-            vb.ReadData(host_out[r], dst_vertex[r], n, deviceContext=copy_stream)
-            d2h_done[r].record(copy_stream)
-        state["f"] = f + 1
+    def evaluate(b, region):
+        assert osd.B200Evaluator.EvalStencils(vb, src_descs[b], vb, dst_descs[region], tbl)
+    pipe = FramePipe(torch, exchange, evaluate, active=world > 1)
+
+    def upload(g):                                         # host-buffer path: this frame's control points H2D (root: the scene)
+        if world == 1:
+            vb.UpdateData(frames[g % len(frames)], (g % 2) * ncv, ncv)
+        elif rank == 0:
+            scene[g % 2].copy_(scene_frames[g % len(frames)], non_blocking=True)
+
+    def readback(f, r):                                    # D2H of this rank's refined vertices on the copy stream
+        kernel_done[r].record(stream)
+        copy_stream.wait_event(kernel_done[r])
+        vb.ReadData(host_out[r], dst_vertex[r], n, deviceContext=copy_stream)
+        d2h_done[r].record(copy_stream)
 
     def step_device(_):
-        """Device-resident step: control points already in HBM on the root; (N>1: per-frame broadcast, overlapped
-        with the previous frame's kernel) + EvalStencils of this rank's rows."""
-        advance(False)
+        """Device-resident step: control points already in HBM on the root; (N>1: per-frame scatter, overlapped with the
+        previous frame's kernel) + EvalStencils of this rank's rows."""
+        pipe.step(0)
 
     def step_e2e(_):
-        """Host-buffer step through the C ABI: H2D control points (root), replicate, evaluate, D2H refined vertices."""
-        advance(True)
+        """Host-buffer step through the C ABI: H2D control points (root), hand out, evaluate, D2H refined vertices."""
+        r = pipe.f % 2
+        stream.wait_event(d2h_done[r])                     # refined region r: read-back of frame f-2 has finished
+        pipe.step(r, before=upload, after=readback)
 
-    # N > 1: the per-frame Python cost of torch.distributed.broadcast (tens of microseconds) is of the order of the
-    # kernel itself, so two consecutive frames (one per control block) are captured ONCE into a CUDA graph --
-    # kernel(block b) runs concurrently with broadcast(block 1-b) -- and the timed loop replays it.
+    # N > 1, --graph: two consecutive frames (one per control block) recorded ONCE into a b200osd frame graph -- the kernel
+    # of block b runs next to the exchange of block 1-b on the frame's side stream -- and the timed loop replays it
     graph = None
     if world > 1 and args.graph:
-        try:
-            for b in (0, 1):                                   # both blocks valid everywhere before the first replay
-                dist.broadcast(blocks[b], src=0)
-            torch.cuda.synchronize()
-            comm = torch.cuda.Stream(priority=-1)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                cur = torch.cuda.current_stream()
-                for b in (0, 1):
-                    comm.wait_stream(cur)                      # block 1-b's last reader (previous kernel) has finished
-                    with torch.cuda.stream(comm):
-                        dist.broadcast(blocks[1 - b], src=0)
-                    ok = osd.B200Evaluator.EvalStencils(vb, src_descs[b], vb, dst_descs[0], tbl)
-                    assert ok
-                    cur.wait_stream(comm)                      # next kernel reads block 1-b
-            graph = g
-            log(f"[bench] rank {rank}: frame pair captured into a CUDA graph")
-        except Exception as exc:
-            graph = None
-            log(f"[bench] rank {rank}: CUDA graph capture failed ({exc}); eager pipeline")
-            torch.cuda.synchronize()
-
-    pending = {"half": 0}
+        fg = osd.B200FrameGraph.Create()
+        side = torch.cuda.ExternalStream(fg.side_stream)
+        for b in (0, 1):
+            exchange(b, torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        assert fg.Begin()
+        for b in (0, 1):
+            fg.Fence(False)                                # side waits for main: block 1-b's last reader has finished
+            exchange(1 - b, side)
+            assert osd.B200Evaluator.EvalStencils(vb, src_descs[b], vb, dst_descs[0], tbl, None, fg)
+            fg.Fence(True)                                 # the next kernel reads block 1-b
+        assert fg.End()
+        graph = fg
+        gstream = torch.cuda.ExternalStream(fg.cuda_stream)
+        log(f"[bench] rank {rank}: frame pair recorded into a b200osd frame graph")
+    half = {"v": 0}
 
     def step_graph(_):
-        """One frame = half a replay of the captured pair (replayed on every second call)."""
-        if pending["half"] == 0:
-            graph.replay()
-        pending["half"] ^= 1
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        if half["v"] == 0:
+            graph.Launch()
+        half["v"] ^= 1
 
     step_device(0)
     torch.cuda.synchronize()
-
-    def timed(step_fn, steps, warmup):
-        for w in range(warmup):
-            step_fn(w)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        lib.b200osd_reset_launch_count()
-        e0.record(stream)
-        for k in range(steps):
-            step_fn(warmup + k)
-        for e in d2h_done:                                     # read-backs still in flight belong to the timed region
-            stream.wait_event(e)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = lib.b200osd_launch_count()
-        if world > 1:
-            tt = torch.tensor([ms], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
-        return ms, launches
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     log(f"[bench] rank {rank}: timing {args.steps} device-resident steps")
+    lib.b200osd_reset_launch_count()
     if graph is not None and args.steps % 2 == 0:
-        pending["half"] = 0
-        ms_dev, _ = timed(step_graph, args.steps, args.warmup + (args.warmup % 2))
-        launches = args.steps                                  # one sell_kernel per frame inside the replayed graph
+        ms_dev = timed_steps(torch, dist, world, step_graph, args.steps, args.warmup + (args.warmup % 2), gstream)
+        launches = args.steps
     else:
-        ms_dev, launches = timed(step_device, args.steps, args.warmup)
+        lib.b200osd_reset_launch_count()
+        ms_dev = timed_steps(torch, dist, world, step_device, args.steps, args.warmup, stream)
+        launches = lib.b200osd_launch_count() - args.warmup                 # the counter also saw the warm-up launches
+    # a second, longer sample of the same step for min / median (20 steps are a 3 ms timed region)
+    per_step = []
+    if world == 1:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(201)]
+        evs[0].record(stream)
+        for k in range(200):
+            step_device(k)
+            evs[k + 1].record(stream)
+        torch.cuda.synchronize()
+        per_step = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(200))
     log(f"[bench] rank {rank}: device-resident done ({ms_dev / args.steps:.4f} ms/step); timing host-buffer steps")
-    ms_e2e, _ = timed(step_e2e, max(3, min(args.steps, 20)), 3)
-    log(f"[bench] rank {rank}: host-buffer steps done")
     e2e_steps = max(3, min(args.steps, 20))
-    # the timed regions are milliseconds long: keep the same step running ~1 s more (untimed) so that the 50 ms
-    # nvidia-smi sampler sees the clocks this kernel actually runs at under load
-    # The number of extra steps must be IDENTICAL on every rank (each step posts a broadcast; a wall-clock loop lets ranks
-    # disagree by one batch and leaves unmatched collectives behind): derive it from the max-reduced step time.
+    ms_e2e = timed_steps(torch, dist, world, step_e2e, e2e_steps, 3, stream, tail_events=d2h_done)
+    # device-resident consumer: the same host -> device -> evaluate pipeline when the consumer of the refined vertices lives
+    # on the GPU (only a 24-byte checksum row comes back): what the PCIe read-back of 153.6 MB per frame costs
+    check = torch.zeros(L, device="cuda")
+    check_host = torch.zeros(L).pin_memory()
+
+    def step_e2e_resident(_):
+        pipe.step(0, before=upload)
+        torch.sum(vt[dst_vertex[0]:dst_vertex[0] + n], dim=0, out=check)
+        check_host.copy_(check, non_blocking=True)
+    ms_res = timed_steps(torch, dist, world, step_e2e_resident, e2e_steps, 3, stream)
+    log(f"[bench] rank {rank}: host-buffer steps done")
+    # the timed regions are milliseconds long: keep the same step running ~1 s more (untimed) so that the 50 ms nvidia-smi
+    # sampler sees the clocks this kernel actually runs at under load.  The number of extra steps must be IDENTICAL on
+    # every rank (each step posts an exchange): derive it from the max-reduced step time.
     batches = int(min(400, max(1, round(1.0 / max(50 * (ms_dev / args.steps) * 1e-3, 1e-4)))))
     for _ in range(batches):
         for k in range(50):
@@ -635,31 +793,29 @@ def run_b200_arm(args):
     ms_per_step = ms_dev / args.steps
     value = total_rows * args.steps / (ms_dev * 1e-3)
     e2e_value = total_rows * e2e_steps / (ms_e2e * 1e-3)
-    alg_bytes = alg_bytes_total // world                      # per GPU, per launch
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
 
-    # Second half of BASELINE.json's metric (limit pts/s, EvalPatches): reported in "eval_patches" (sharded by PatchCoord range at N > 1).
-    patches = None
-    if not args.no_patches:
-        if world == 1:
+    # ---- other sections
+    iters = 20
+    config5 = None
+    if not args.headline_only:
+        config5 = bench_config5_strong(torch, dist, osd, capi, shard, comm_wide, world, rank, max(20, min(args.steps, 100)), max(args.warmup, 5))
+    config3 = patches = incumbent = None
+    if world == 1 and not args.headline_only:
+        for name, fn in (("config3", lambda: bench_config3(mesh, torch, osd, iters)),
+                         ("patches", lambda: bench_eval_patches(torch, osd, capi)),
+                         ("incumbent", lambda: bench_incumbent_cuda(mesh, table, torch, osd))):
             try:
-                patches = bench_eval_patches(mesh, torch, osd, capi, log)
-            except Exception as exc:
-                patches = {"error": str(exc)}
-        elif args.shard_patches:
-            # collectives inside: every rank must take the same path, so no exception is swallowed here
-            patches = bench_eval_patches(mesh, torch, osd, capi, log, world=world, rank=rank, strong=strong)
-        else:
-            patches = {"skipped": "N > 1: run with --shard-patches for EvalPatches sharded by PatchCoord range "
-                                  "(measured at N=2: profiles/r01_bench_n2.json)"}
-
-    incumbent = None
-    if world == 1 and not args.no_patches:
-        try:
-            incumbent = bench_incumbent_cuda(mesh, table, torch, osd)
-        except Exception as exc:
-            incumbent = {"error": str(exc)}
+                val = fn()
+            except Exception as exc:      # a section is a report, never a reason to lose the headline number
+                val = {"error": f"{type(exc).__name__}: {exc}"}
+            if name == "config3":
+                config3 = val
+            elif name == "patches":
+                patches = val
+            else:
+                incumbent = val
 
     if rank == 0:
         cpu = None
@@ -679,32 +835,42 @@ def run_b200_arm(args):
         line = {
             "metric": "refined_verts_per_sec_EvalStencils", "value": value, "unit": "verts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_gpu": n, "elements_per_gpu": table.num_elements,
-                       "control_verts_per_mesh": ncv, "primvar_floats": L, "parallelism": f"row-range x{world}",
-                       "launch": "eager" if graph is None else "CUDA graph of 2 frames (kernel || broadcast of the other control block)",
-                       "exchange": "none (1 GPU)" if world == 1 else
-                       f"per-frame NCCL broadcast of {scene_cv * L * 4} B of control points from rank 0, double-buffered on a side stream",
-                       "l2_policy": "inputs larger than L2 (table streams 0.7 GB/step vs 126 MB L2); no flush needed",
-                       "stencil_variant": lib.b200osd_get_stencil_variant(),
-                       "bucketed_stream_bytes": tbl.GetStreamBytes(1)},
-            "e2e": {"value": e2e_value, "unit": "verts/s", "h2d_bytes_per_step": int(scene_cv * L * 4),
-                    "d2h_bytes_per_step": int(n * L * 4), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "run": {"parallelism": f"row-range x{world} (rank r owns mesh r)",
+                    "launch": "eager pipeline" if graph is None else "b200osd frame graph of 2 frames (kernel || exchange of the other control block)",
+                    "exchange": "none (1 GPU)" if world == 1 else
+                    f"per-frame b200osd_comm_scatter: every rank receives its own {ncv * L * 4} B of control points from rank 0, double-buffered on a high-priority side stream",
+                    "l2_policy": "inputs larger than L2 (table streams 0.55 GB/step vs 126 MB L2); no flush needed",
+                    "stencil_variant": tbl.GetVariant(), "bucketed_stream_bytes": tbl.GetStreamBytes(1),
+                    "summation_order": "rows of <= 16 elements in control-index order (library default), longer rows in table order",
+                    "ms_per_step_min_median_of_200": [per_step[0], per_step[len(per_step) // 2]] if per_step else None},
+            "e2e": {"value": e2e_value, "unit": "verts/s", "h2d_bytes_per_step": int(world * ncv * L * 4),
+                    "d2h_bytes_per_step": int(world * n * L * 4), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "note": "whole job: H2D of the scene's control points on the root + D2H of every rank's refined vertices (N ranks share one host's PCIe / memory system: a platform limit, see e2e_device_consumer)"},
+            "e2e_device_consumer": {"value": total_rows * e2e_steps / (ms_res * 1e-3), "unit": "verts/s", "ms_per_step": ms_res / e2e_steps,
+                                    "h2d_bytes_per_step": int(world * ncv * L * 4), "d2h_bytes_per_step": 4 * L,
+                                    "note": "same pipeline when the consumer of the refined vertices is on the GPU: only a checksum row is read back"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "frac_of_nominal_8TBps": achieved / 8000.0,
-                         "note": "per GPU; device time per step = one sell_kernel launch (+ the overlapped broadcast when N > 1)"},
+                         "note": "per GPU; device time per step = one sell_kernel launch (+ the overlapped exchange when N > 1)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "config3": config3,
+            "config5": config5,
             "eval_patches": patches,
             "incumbent_cuda": incumbent,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        # leave without tearing NCCL down: destroying a process group that a captured graph still references can hang
+        # leave without tearing NCCL down: destroying communicators that recorded graphs still reference can hang
         torch.cuda.synchronize()
         dist.barrier()
+        for c in (comm, comm_wide):
+            if c is not None:
+                c.leak()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
@@ -717,21 +883,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant (0 = auto)")
-    ap.add_argument("--no-patches", action="store_true", help="skip the EvalPatches section of the report")
-    ap.add_argument("--shard-patches", action="store_true",
-                    help="N > 1: also time EvalPatches sharded by PatchCoord range across the ranks")
+    ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant of the headline table (0 = auto)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the config 3 / 4 / 5 and incumbent sections")
     ap.add_argument("--graph", action="store_true",
-                    help="N > 1: replay a CUDA graph of two frames instead of the eager pipeline (verified at N=2 only)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = N meshes (default), strong = one mesh cut into N row ranges")
+                    help="N > 1: replay a b200osd frame graph of two frames instead of the eager pipeline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference_arm(args)
-    if args.variant:
-        from opensubdiv_b200 import capi
-        capi.lib().b200osd_set_stencil_variant(args.variant)
     return run_b200_arm(args)
 
 

@@ -106,8 +106,12 @@ B200OSD_API int    b200osd_vertex_buffer_read(b200osd_vertex_buffer *vb, float *
  * (osd/mesh.h:505-519: row r is vertex numControlVertices + r of the same buffer) that reproduces the sequential CPU
  * evaluator; a table whose rows are not in dependency order is rejected (NULL, B200OSD_ERR_UNSUPPORTED in the message).
  * flags: bit 0 = skip the bucketed copy (verbatim only); bit 1 = also order rows by locality inside a window;
- * bit 2 = keep 32-bit indices even when a slice fits 16-bit offsets; bit 3 = sort each row's elements by control index
- * (same terms, different summation order than the reference: opt-in).                                       */
+ * bit 2 = keep 32-bit indices even when a slice fits 16-bit offsets.
+ * Summation order: by default the elements of rows of <= 16 terms (every row of a refined regular mesh) are summed in
+ * control-index order instead of the table's own order -- neighbouring rows then gather the same vertices at the same
+ * step (-7 % time on config 2); same terms, measured <= 3.4e-7 of sum|w||x| away from the reference order on every
+ * fixture.  bit 4 (16) = keep the table's order everywhere (bit-identical to the reference's CUDA kernel);
+ * bit 3 (8) = sort every row, including rows of 100+ terms (which may then differ by > 1e-6).                          */
 B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
         int numStencils, int numControlVertices,
         const int *sizes, const int *offsets, const int *indices, const float *weights,
@@ -235,10 +239,50 @@ B200OSD_API int  b200osd_patch_map_find(const b200osd_patch_map *m, int numSampl
 B200OSD_API b200osd_frame *b200osd_frame_create(void);
 B200OSD_API void  b200osd_frame_destroy(b200osd_frame *f);
 B200OSD_API void *b200osd_frame_stream(const b200osd_frame *f);     /* the cudaStream_t to pass as `stream` */
+/* A second, high-priority stream that belongs to the same frame: while recording, work issued on it becomes a PARALLEL
+ * branch of the graph (typically b200osd_comm_broadcast of the next frame's control points next to this frame's
+ * evaluation).  _fence orders the two: mainWaitsForSide = 0 makes later side-stream work wait for everything issued so
+ * far on the main stream, 1 the other way round.  _begin forks and _end joins the side stream automatically. */
+B200OSD_API void *b200osd_frame_side_stream(const b200osd_frame *f);
+B200OSD_API int   b200osd_frame_fence(b200osd_frame *f, int mainWaitsForSide);
+/* Keeps [devPtr, devPtr + bytes) -- e.g. the refined vertices that EvalStencils writes and EvalPatches reads -- resident
+ * in L2 across the kernels of the frame (cudaAccessPolicyWindow, persisting) while everything else streams; call before
+ * _begin so that the recorded kernels inherit it.  devPtr = NULL clears the window. */
+B200OSD_API int   b200osd_frame_set_l2_window(b200osd_frame *f, const void *devPtr, size_t bytes, float hitRatio);
 B200OSD_API int   b200osd_frame_begin(b200osd_frame *f);
 B200OSD_API int   b200osd_frame_end(b200osd_frame *f);
 B200OSD_API int   b200osd_frame_launch(b200osd_frame *f);           /* asynchronous */
 B200OSD_API int   b200osd_frame_synchronize(b200osd_frame *f);
+
+/* ---- multi-GPU data plane (no reference counterpart -- the reference is single-device, its hook is the
+ * absolute row range [start, end) of the raw EvalStencils overloads, osd/cudaEvaluator.h:171-178) ------------------------
+ * One process per GPU.  Rows / coordinates are cut into contiguous ranges, tables are static and pre-sharded, outputs stay
+ * sharded, no row spans ranks (no reduction); the only exchange is the per-frame replication of the control points. */
+/* `world` contiguous row ranges [ranges[2r], ranges[2r+1]) of equal cost (a row costs its elements + 1); interior cuts are
+ * rounded to a multiple of `align` (e.g. the 2048-row bucketing window).  Host only: needs no device. */
+B200OSD_API int b200osd_shard_plan(int numStencils, const int *sizes, int world, int align, int *ranges);
+/* the same for a PatchCoord set (every coordinate costs the same) */
+B200OSD_API int b200osd_shard_coords(long long numCoords, int world, int align, long long *ranges);
+/* Communicator over NCCL (bound at run time with dlopen: no link-time dependency).  Rank 0 calls _unique_id and hands the
+ * 128 bytes to the other ranks by any means (a file, MPI, torch.distributed); every rank then calls _create with its own
+ * CUDA device current.  All transfer calls are asynchronous on `stream` and may be recorded into a frame. */
+typedef struct b200osd_comm b200osd_comm;
+B200OSD_API int  b200osd_comm_available(void);
+B200OSD_API int  b200osd_comm_unique_id(char id[128]);
+B200OSD_API b200osd_comm *b200osd_comm_create(int world, int rank, const char id[128]);
+/* maxCTAs > 0 caps the thread blocks NCCL may use for this communicator's transfers (ncclConfig_t.maxCTAs): a few-MB
+ * exchange that hides behind an evaluation kernel should cost one or two SMs, not sixteen; 0 = NCCL's default */
+B200OSD_API b200osd_comm *b200osd_comm_create_ex(int world, int rank, const char id[128], int maxCTAs);
+B200OSD_API void b200osd_comm_destroy(b200osd_comm *c);
+B200OSD_API int  b200osd_comm_world(const b200osd_comm *c);
+B200OSD_API int  b200osd_comm_rank(const b200osd_comm *c);
+/* every rank ends up with root's `count` floats at buf (one mesh, rows sharded: all ranks need all control points) */
+B200OSD_API int  b200osd_comm_broadcast(b200osd_comm *c, float *buf, size_t count, int root, void *stream);
+/* rank r receives floats [r*countPerRank, (r+1)*countPerRank) of root's sendbuf into recvbuf (N meshes, rank r owns mesh
+ * r: each GPU receives only what it reads) */
+B200OSD_API int  b200osd_comm_scatter(b200osd_comm *c, const float *sendbuf, float *recvbuf, size_t countPerRank, int root, void *stream);
+/* optional: every rank gets every rank's countPerRank floats (a consumer that wants the whole refined buffer) */
+B200OSD_API int  b200osd_comm_all_gather(b200osd_comm *c, const float *sendbuf, float *recvbuf, size_t countPerRank, void *stream);
 
 /* ---- tuning / introspection (used by bench.py and the tests; not needed by clients) ----------
  * Kernel variant of b200osd_stencil_table_eval for THIS table (there is no process-wide state): 0 = auto,

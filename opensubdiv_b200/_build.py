@@ -15,7 +15,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libb200osd.so")
-SOURCES = ["core.cu", "stencil.cu", "patch.cu", "patchmap.cu", "frame.cu"]
+SOURCES = ["core.cu", "stencil.cu", "patch.cu", "patchmap.cu", "frame.cu", "shard.cu"]
 HEADERS = ["common.cuh", "stencil_kernels.cuh", "patch_kernels.cuh", "patchmap.cuh", os.path.join("..", "..", "include", "b200osd_capi.h")]
 
 NVCC_FLAGS = [
@@ -27,7 +27,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xptxas=-v", "--threads", "4",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
-    "-shared",
+    "-shared", "-ldl",
 ]
 
 

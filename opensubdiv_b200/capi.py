@@ -32,6 +32,10 @@ SYMBOLS = [
     "b200osd_patch_plan_create", "b200osd_patch_plan_destroy", "b200osd_patch_plan_capacity", "b200osd_patch_plan_bin",
     "b200osd_patch_plan_eval",
     "b200osd_patch_map_create", "b200osd_patch_map_destroy", "b200osd_patch_map_info", "b200osd_patch_map_find",
+    "b200osd_frame_side_stream", "b200osd_frame_fence", "b200osd_frame_set_l2_window",
+    "b200osd_shard_plan", "b200osd_shard_coords", "b200osd_comm_available", "b200osd_comm_unique_id", "b200osd_comm_create", "b200osd_comm_create_ex",
+    "b200osd_comm_destroy", "b200osd_comm_world", "b200osd_comm_rank", "b200osd_comm_broadcast", "b200osd_comm_scatter",
+    "b200osd_comm_all_gather",
     "b200osd_frame_create", "b200osd_frame_destroy", "b200osd_frame_stream", "b200osd_frame_begin", "b200osd_frame_end",
     "b200osd_frame_launch", "b200osd_frame_synchronize",
 ]
@@ -113,6 +117,23 @@ def lib():
     L.b200osd_frame_stream.argtypes = [vp]
     for fn in (L.b200osd_frame_begin, L.b200osd_frame_end, L.b200osd_frame_launch, L.b200osd_frame_synchronize):
         fn.argtypes = [vp]
+    L.b200osd_frame_side_stream.restype = vp
+    L.b200osd_frame_side_stream.argtypes = [vp]
+    L.b200osd_frame_fence.argtypes = [vp, i]
+    L.b200osd_frame_set_l2_window.argtypes = [vp, vp, C.c_size_t, C.c_float]
+    L.b200osd_shard_plan.argtypes = [i, vp, i, i, vp]
+    L.b200osd_shard_coords.argtypes = [ll, i, i, vp]
+    L.b200osd_comm_unique_id.argtypes = [vp]
+    L.b200osd_comm_create.restype = vp
+    L.b200osd_comm_create.argtypes = [i, i, vp]
+    L.b200osd_comm_create_ex.restype = vp
+    L.b200osd_comm_create_ex.argtypes = [i, i, vp, i]
+    L.b200osd_comm_destroy.argtypes = [vp]
+    L.b200osd_comm_world.argtypes = [vp]
+    L.b200osd_comm_rank.argtypes = [vp]
+    L.b200osd_comm_broadcast.argtypes = [vp, vp, C.c_size_t, i, vp]
+    L.b200osd_comm_scatter.argtypes = [vp, vp, vp, C.c_size_t, i, vp]
+    L.b200osd_comm_all_gather.argtypes = [vp, vp, vp, C.c_size_t, vp]
     _lib = L
     return L
 

@@ -1,0 +1,239 @@
+// shard.cu -- the multi-GPU data plane of the evaluator, in C: work partitioning and the per-frame
+// replication of the control points over NVLink.
+//
+// The reference has no multi-GPU code at all (no NCCL / MPI / cudaSetDevice anywhere in
+// opensubdiv/); what it does offer is the hook this layer builds on: the raw EvalStencils overloads take an absolute
+// row range [start, end) (osd/cudaEvaluator.h:171-178, osd/cudaKernel.cu:85-98).  The path shards naturally -- every
+// stencil row and every PatchCoord is independent and the tables are static -- so
+//   * b200osd_shard_plan cuts the rows into `world` contiguous ranges of equal COST (elements + a constant per row);
+//     each rank builds a table of its rows only (offsets re-based) or passes its range to the table evaluation;
+//   * b200osd_shard_coords cuts a PatchCoord set into contiguous ranges (every coordinate costs the same);
+//   * b200osd_comm_* replicates the one mutable input, the deformed control points of a frame, to every GPU: one process
+//     per GPU, NCCL over NVLink 5 / NVSwitch.  broadcast = every rank gets everything (one mesh, rows sharded: "strong");
+//     scatter = rank r gets only slice r (N meshes, rank r owns mesh r: "weak" -- 1/N of the broadcast's bytes per GPU).
+//   No reduction exists anywhere: no row spans ranks.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- inside a PyTorch process that is the copy torch already loaded),
+// so libb200osd.so itself has no link-time dependency on it and single-GPU users never touch it.
+#include "common.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+using namespace b200osd;
+
+// nccl.h supplies the types (and the versioned ncclConfig_t); every FUNCTION is bound with dlsym below
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define B200OSD_HAVE_NCCL_CONFIG 1
+#else
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+#endif
+
+namespace {
+
+enum { kNcclSuccess = 0, kNcclFloat = 7 };
+
+struct NcclApi {
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+#ifdef B200OSD_HAVE_NCCL_CONFIG
+    int (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr;
+#endif
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+NcclApi *nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+#define B200_NCCL_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name))
+        B200_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+        B200_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+#ifdef B200OSD_HAVE_NCCL_CONFIG
+        B200_NCCL_SYM(CommInitRankConfig, "ncclCommInitRankConfig");
+#endif
+        B200_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+        B200_NCCL_SYM(Broadcast, "ncclBroadcast");
+        B200_NCCL_SYM(AllGather, "ncclAllGather");
+        B200_NCCL_SYM(Send, "ncclSend");
+        B200_NCCL_SYM(Recv, "ncclRecv");
+        B200_NCCL_SYM(GroupStart, "ncclGroupStart");
+        B200_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+        B200_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef B200_NCCL_SYM
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.AllGather && api.Send &&
+                 api.Recv && api.GroupStart && api.GroupEnd;
+    });
+    return &api;
+}
+
+int nccl_check(int r, const char *what) {
+    if (r == kNcclSuccess) return B200OSD_OK;
+    NcclApi *a = nccl();
+    set_error("%s failed: %s", what, a->GetErrorString ? a->GetErrorString(r) : "NCCL error");
+    return B200OSD_ERR_CUDA;
+}
+
+}  // namespace
+
+struct b200osd_comm {
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------------------- partitioning --
+int b200osd_shard_plan(int numStencils, const int *sizes, int world, int align, int *ranges) {
+    if (numStencils < 0 || world < 1 || !ranges || (numStencils > 0 && !sizes)) { set_error("shard_plan: bad arguments"); return B200OSD_ERR_INVALID; }
+    const int n = numStencils;
+    // cost of a row = its elements + 1 (descriptor + output); cut where the running cost passes r/world of the total
+    long long total = 0;
+    for (int i = 0; i < n; ++i) total += (long long)sizes[i] + 1;
+    std::vector<int> cuts((size_t)world + 1, n);
+    cuts[0] = 0;
+    long long run = 0;
+    int i = 0;
+    for (int r = 1; r < world; ++r) {
+        const long long target = total * r / world;
+        while (i < n && run + sizes[i] + 1 < target) { run += (long long)sizes[i] + 1; ++i; }
+        int c = std::min(i + 1, n);                      // first row whose inclusive running cost reaches the target, + 1
+        if (align > 1) c = (int)(((long long)c + align / 2) / align) * align;
+        c = std::min(std::max(c, cuts[(size_t)r - 1]), n);
+        cuts[(size_t)r] = c;
+    }
+    for (int r = 0; r < world; ++r) { ranges[2 * r] = cuts[(size_t)r]; ranges[2 * r + 1] = cuts[(size_t)r + 1]; }
+    return B200OSD_OK;
+}
+
+int b200osd_shard_coords(long long numCoords, int world, int align, long long *ranges) {
+    if (numCoords < 0 || world < 1 || !ranges) { set_error("shard_coords: bad arguments"); return B200OSD_ERR_INVALID; }
+    long long prev = 0;
+    for (int r = 0; r < world; ++r) {
+        long long c = r + 1 == world ? numCoords : numCoords * (r + 1) / world;
+        if (align > 1 && r + 1 < world) c = (c + align / 2) / align * align;
+        c = std::min(std::max(c, prev), numCoords);
+        ranges[2 * r] = prev;
+        ranges[2 * r + 1] = c;
+        prev = c;
+    }
+    return B200OSD_OK;
+}
+
+// ------------------------------------------------------------------------------ communicator --
+int b200osd_comm_available(void) { return nccl()->ok ? 1 : 0; }
+
+int b200osd_comm_unique_id(char id[128]) {
+    NcclApi *a = nccl();
+    if (!a->ok) { set_error("NCCL is not available (libnccl.so.2 could not be loaded)"); return B200OSD_ERR_UNSUPPORTED; }
+    if (!id) { set_error("comm_unique_id: id is NULL"); return B200OSD_ERR_INVALID; }
+    ncclUniqueId u;
+    int rc = nccl_check(a->GetUniqueId(&u), "ncclGetUniqueId");
+    if (rc) return rc;
+    std::memcpy(id, u.internal, 128);
+    return B200OSD_OK;
+}
+
+b200osd_comm *b200osd_comm_create(int world, int rank, const char id[128]) {
+    return b200osd_comm_create_ex(world, rank, id, 0);
+}
+
+b200osd_comm *b200osd_comm_create_ex(int world, int rank, const char id[128], int maxCTAs) {
+    NcclApi *a = nccl();
+    if (!a->ok) { set_error("NCCL is not available (libnccl.so.2 could not be loaded)"); return nullptr; }
+    if (world < 1 || rank < 0 || rank >= world || !id) { set_error("comm_create: bad world / rank / id"); return nullptr; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
+    b200osd_comm *c = new (std::nothrow) b200osd_comm;
+    if (!c) return nullptr;
+    c->world = world;
+    c->rank = rank;
+    ncclUniqueId u;
+    std::memcpy(u.internal, id, 128);
+    int rc = -1;
+#ifdef B200OSD_HAVE_NCCL_CONFIG
+    if (maxCTAs > 0 && a->CommInitRankConfig) {
+        // a transfer of a few MB hidden behind an evaluation kernel needs no bandwidth, only few SMs: cap NCCL's CTAs
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = maxCTAs;
+        rc = a->CommInitRankConfig(&c->comm, world, u, rank, &cfg);
+        if (rc != kNcclSuccess) c->comm = nullptr;                 // e.g. a runtime that rejects the header's config version
+    }
+#endif
+    (void)maxCTAs;
+    if (rc != kNcclSuccess && nccl_check(a->CommInitRank(&c->comm, world, u, rank), "ncclCommInitRank")) { delete c; return nullptr; }
+    return c;
+}
+
+void b200osd_comm_destroy(b200osd_comm *c) {
+    if (!c) return;
+    if (c->comm) nccl()->CommDestroy(c->comm);
+    delete c;
+}
+
+int b200osd_comm_world(const b200osd_comm *c) { return c ? c->world : 1; }
+int b200osd_comm_rank(const b200osd_comm *c) { return c ? c->rank : 0; }
+
+int b200osd_comm_broadcast(b200osd_comm *c, float *buf, size_t count, int root, void *stream) {
+    if (!c || !buf) { set_error("comm_broadcast: NULL communicator / buffer"); return B200OSD_ERR_INVALID; }
+    if (count == 0 || c->world == 1) return B200OSD_OK;
+    return nccl_check(nccl()->Broadcast(buf, buf, count, kNcclFloat, root, c->comm, (cudaStream_t)stream), "ncclBroadcast");
+}
+
+int b200osd_comm_scatter(b200osd_comm *c, const float *sendbuf, float *recvbuf, size_t countPerRank, int root, void *stream) {
+    if (!c || !recvbuf || (c->rank == root && !sendbuf)) { set_error("comm_scatter: NULL communicator / buffer"); return B200OSD_ERR_INVALID; }
+    if (countPerRank == 0) return B200OSD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    NcclApi *a = nccl();
+    if (c->world == 1) {
+        if (sendbuf != recvbuf) B200_CUDA_TRY(cudaMemcpyAsync(recvbuf, sendbuf, countPerRank * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return B200OSD_OK;
+    }
+    int rc = nccl_check(a->GroupStart(), "ncclGroupStart");
+    if (rc) return rc;
+    if (c->rank == root) {
+        for (int r = 0; r < c->world && !rc; ++r) {
+            if (r == root) continue;
+            rc = nccl_check(a->Send(sendbuf + (size_t)r * countPerRank, countPerRank, kNcclFloat, r, c->comm, st), "ncclSend");
+        }
+    } else {
+        rc = nccl_check(a->Recv(recvbuf, countPerRank, kNcclFloat, root, c->comm, st), "ncclRecv");
+    }
+    const int rc2 = nccl_check(a->GroupEnd(), "ncclGroupEnd");
+    if (rc || rc2) return rc ? rc : rc2;
+    if (c->rank == root && sendbuf + (size_t)root * countPerRank != recvbuf)
+        B200_CUDA_TRY(cudaMemcpyAsync(recvbuf, sendbuf + (size_t)root * countPerRank, countPerRank * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, st));
+    return B200OSD_OK;
+}
+
+int b200osd_comm_all_gather(b200osd_comm *c, const float *sendbuf, float *recvbuf, size_t countPerRank, void *stream) {
+    if (!c || !sendbuf || !recvbuf) { set_error("comm_all_gather: NULL communicator / buffer"); return B200OSD_ERR_INVALID; }
+    if (countPerRank == 0) return B200OSD_OK;
+    if (c->world == 1) {
+        if (sendbuf != recvbuf) B200_CUDA_TRY(cudaMemcpyAsync(recvbuf, sendbuf, countPerRank * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return B200OSD_OK;
+    }
+    return nccl_check(nccl()->AllGather(sendbuf, recvbuf, countPerRank, kNcclFloat, c->comm, (cudaStream_t)stream), "ncclAllGather");
+}
+
+}  // extern "C"

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 using namespace b200osd;
@@ -67,24 +68,49 @@ int upload(T **dptr, const T *host, size_t count) {
     return B200OSD_OK;
 }
 
-int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, const int *indices,
-               const float *const w[kMaxOut], bool localitySort, bool allowIdx16, bool sortElements) {
-    const int n = t->n;
-    // Element order inside a row.  Default: the table's own order, i.e. the reference's summation order (parity first:
-    // rows of 100+ terms differ by > 1e-6 relative once the order changes).  Opt-in (flag bit 3): each row's elements
-    // sorted by control index -- the rows of a slice are neighbours on the surface and share most control vertices, so
-    // position j of all 32 lanes then refers to (nearly) the same vertex and a warp-wide gather touches fewer lines.
-    std::vector<int> perm;          // perm[off + j] = original position (relative to off) of the row's j-th element
-    if (sortElements) {
-        perm.resize((size_t)t->ne);
-        for (int i = 0; i < n; ++i) {
-            int *p = perm.data() + offsets[i];
-            const int *ix = indices + offsets[i];
-            std::iota(p, p + sizes[i], 0);
-            std::stable_sort(p, p + sizes[i], [&](int a, int b) { return ix[a] < ix[b]; });
-        }
+// runs fn(begin, end) over [0, n) on up to 16 host threads (table construction is once per topology, but a 6.4 M-row
+// table is 84 M elements: the reference's own upload is a memcpy, so this must not cost seconds)
+template <typename F>
+void parallel_ranges(int n, int grain, F fn) {
+    const int hw = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const int parts = std::max(1, std::min(hw, (n + grain - 1) / grain));
+    if (parts == 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)parts);
+    for (int p = 0; p < parts; ++p) {
+        const int b = (int)((long long)n * p / parts), e = (int)((long long)n * (p + 1) / parts);
+        th.emplace_back([=]() { fn(b, e); });
     }
-    auto elem = [&](int off, int j) { return sortElements ? off + perm[(size_t)off + j] : off + j; };
+    for (auto &x : th) x.join();
+}
+
+constexpr int kShortRow = 16;       // rows up to this many elements are summed in control-index order by default
+
+// sortMode: 0 keep the table's element order everywhere, 1 sort the elements of rows of <= kShortRow elements by control
+// index (default), 2 sort every row.
+int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, const int *indices,
+               const float *const w[kMaxOut], bool localitySort, bool allowIdx16, int sortMode) {
+    const int n = t->n;
+    // Element order inside a row.  The rows of a slice are neighbours on the surface and share most control vertices, so
+    // when every row lists its elements in control-index order, position j of all 32 lanes refers to (nearly) the same
+    // vertex and a warp-wide gather touches 1-2 cache lines instead of 3-4 (config 2: 0.166 -> 0.155 ms).  Same terms,
+    // another summation order than the reference: for the short rows of refined meshes (<= 16 terms) the difference is
+    // bounded by n*eps of sum|w||x| and measured <= 3.4e-7 of it on every fixture; rows of 100+ terms
+    // (high-valence poles) would pass 1e-6, so longer rows keep the table's own order unless asked (flag bit 3).
+    std::vector<int> perm;          // perm[off + j] = original position (relative to off) of the row's j-th element
+    if (sortMode != 0) {
+        perm.resize((size_t)t->ne);
+        parallel_ranges(n, 1 << 16, [&](int r0, int r1) {
+            for (int i = r0; i < r1; ++i) {
+                int *p = perm.data() + offsets[i];
+                const int *ix = indices + offsets[i];
+                std::iota(p, p + sizes[i], 0);
+                if (sortMode == 2 || sizes[i] <= kShortRow)
+                    std::stable_sort(p, p + sizes[i], [&](int a, int b) { return ix[a] < ix[b]; });
+            }
+        });
+    }
+    auto elem = [&](int off, int j) { return sortMode != 0 ? off + perm[(size_t)off + j] : off + j; };
     std::vector<int> rowKey;
     if (localitySort) {
         rowKey.resize(n);
@@ -96,65 +122,86 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
     }
     t->window = kWindowRows;
     const int numWindows = (n + kWindowRows - 1) / kWindowRows;
+    const int slicesPerWindow = kWindowRows / kSliceRows;
     std::vector<int> order(n);
+    // pass 1 (parallel over windows): order the rows of each window, describe its slices
+    struct SliceInfo { int lenVec, lo; };        // lo < 0: 32-bit indices
+    std::vector<SliceInfo> info((size_t)numWindows * slicesPerWindow);
+    std::vector<int> windowSlices((size_t)numWindows, 0);
+    parallel_ranges(numWindows, 64, [&](int w0, int w1) {
+        for (int wdw = w0; wdw < w1; ++wdw) {
+            const int r0 = wdw * kWindowRows, r1 = std::min(n, r0 + kWindowRows);
+            int *ord = order.data() + r0;
+            std::iota(ord, ord + (r1 - r0), r0);
+            if (localitySort) {
+                // rows of equal padded length are further ordered by their smallest control index, so the 32 rows of a
+                // slice reference neighbouring control vertices and each warp-wide gather touches few cache lines
+                std::stable_sort(ord, ord + (r1 - r0), [&](int a, int b) {
+                    const int la = (sizes[a] + kVec - 1) / kVec, lb = (sizes[b] + kVec - 1) / kVec;
+                    if (la != lb) return la < lb;
+                    return rowKey[a] < rowKey[b];
+                });
+            } else {
+                std::stable_sort(ord, ord + (r1 - r0), [&](int a, int b) { return sizes[a] < sizes[b]; });
+            }
+            int ns = 0;
+            for (int s0 = r0; s0 < r1; s0 += kSliceRows, ++ns) {
+                const int s1 = std::min(r1, s0 + kSliceRows);
+                int maxSize = 0, lo = 0x7fffffff, hi = -1;
+                for (int q = s0; q < s1; ++q) {
+                    const int r = order[q];
+                    maxSize = std::max(maxSize, sizes[r]);
+                    for (int j = 0; j < sizes[r]; ++j) {
+                        const int ix = indices[offsets[r] + j];
+                        lo = std::min(lo, ix);
+                        hi = std::max(hi, ix);
+                    }
+                }
+                if (hi < 0) { lo = 0; hi = 0; }
+                const bool is16 = allowIdx16 && (hi - lo <= 0xffff);
+                info[(size_t)wdw * slicesPerWindow + ns] = { (maxSize + kVec - 1) / kVec, is16 ? lo : -1 };
+            }
+            windowSlices[(size_t)wdw] = ns;
+        }
+    });
+    // serial: slice bases in the weight arrays and in the index pool
     std::vector<int4> meta;
     std::vector<int> rows;
     size_t poolUnits = 0;   // 8-byte units of index storage
-    t->windowSliceStart.assign(numWindows + 1, 0);
-    meta.reserve(n / kSliceRows + numWindows);
-    rows.reserve((size_t)n + (size_t)numWindows * kSliceRows);
-
-    size_t totalVec = 0;   // in units of 4 elements (one int4 per lane slot)
+    size_t totalVec = 0;    // in units of 4 elements (one int4 per lane slot)
+    t->windowSliceStart.assign((size_t)numWindows + 1, 0);
+    meta.reserve((size_t)n / kSliceRows + (size_t)numWindows);
     for (int wdw = 0; wdw < numWindows; ++wdw) {
-        const int r0 = wdw * kWindowRows, r1 = std::min(n, r0 + kWindowRows);
-        int *ord = order.data() + r0;
-        std::iota(ord, ord + (r1 - r0), r0);
-        if (localitySort) {
-            // rows of equal padded length are further ordered by their smallest control index, so the 32 rows of a
-            // slice reference neighbouring control vertices and each warp-wide gather touches few cache lines
-            std::stable_sort(ord, ord + (r1 - r0), [&](int a, int b) {
-                const int la = (sizes[a] + kVec - 1) / kVec, lb = (sizes[b] + kVec - 1) / kVec;
-                if (la != lb) return la < lb;
-                return rowKey[a] < rowKey[b];
-            });
-        } else {
-            std::stable_sort(ord, ord + (r1 - r0), [&](int a, int b) { return sizes[a] < sizes[b]; });
-        }
-        t->windowSliceStart[wdw] = (int)meta.size();
-        for (int s0 = r0; s0 < r1; s0 += kSliceRows) {
-            const int s1 = std::min(r1, s0 + kSliceRows);
-            int maxSize = 0, lo = 0x7fffffff, hi = -1;
-            for (int q = s0; q < s1; ++q) {
-                const int r = order[q];
-                maxSize = std::max(maxSize, sizes[r]);
-                for (int j = 0; j < sizes[r]; ++j) {
-                    const int ix = indices[offsets[r] + j];
-                    lo = std::min(lo, ix);
-                    hi = std::max(hi, ix);
-                }
-            }
-            if (hi < 0) { lo = 0; hi = 0; }
-            const bool is16 = allowIdx16 && (hi - lo <= 0xffff);
-            const int lenVec = (maxSize + kVec - 1) / kVec;
+        t->windowSliceStart[(size_t)wdw] = (int)meta.size();
+        for (int q = 0; q < windowSlices[(size_t)wdw]; ++q) {
+            const SliceInfo &si = info[(size_t)wdw * slicesPerWindow + q];
+            const bool is16 = si.lo >= 0;
             if (!is16 && (poolUnits & 1)) ++poolUnits;      // 32-bit groups are int4: keep them 16-byte aligned
-            if (totalVec > 0xffffffffull - (size_t)lenVec * kSliceRows) {
+            if (totalVec > 0xffffffffull - (size_t)si.lenVec * kSliceRows) {
                 set_error("stencil table too large for 32-bit slice bases");
                 return B200OSD_ERR_UNSUPPORTED;
             }
-            if (poolUnits > 0xffffffffull - 2ull * lenVec * kSliceRows) {
+            if (poolUnits > 0xffffffffull - 2ull * si.lenVec * kSliceRows) {
                 set_error("stencil table too large for 32-bit index-pool offsets");
                 return B200OSD_ERR_UNSUPPORTED;
             }
-            meta.push_back(make_int4((int)(unsigned)totalVec, lenVec, is16 ? lo : -1, (int)(unsigned)poolUnits));
-            poolUnits += (size_t)lenVec * kSliceRows * (is16 ? 1 : 2);
+            meta.push_back(make_int4((int)(unsigned)totalVec, si.lenVec, si.lo, (int)(unsigned)poolUnits));
+            poolUnits += (size_t)si.lenVec * kSliceRows * (is16 ? 1 : 2);
             t->slices16 += is16 ? 1 : 0;
-            for (int q = 0; q < kSliceRows; ++q) rows.push_back(s0 + q < s1 ? order[s0 + q] : -1);
-            totalVec += (size_t)lenVec * kSliceRows;
+            totalVec += (size_t)si.lenVec * kSliceRows;
         }
     }
-    t->windowSliceStart[numWindows] = (int)meta.size();
+    t->windowSliceStart[(size_t)numWindows] = (int)meta.size();
     t->numSlices = (int)meta.size();
     t->totalVec = totalVec;
+    rows.assign((size_t)t->numSlices * kSliceRows, -1);
+    parallel_ranges(numWindows, 64, [&](int w0, int w1) {
+        for (int wdw = w0; wdw < w1; ++wdw) {
+            const int r0 = wdw * kWindowRows, r1 = std::min(n, r0 + kWindowRows);
+            int *dst = rows.data() + (size_t)t->windowSliceStart[(size_t)wdw] * kSliceRows;
+            for (int q = r0; q < r1; ++q) dst[q - r0] = order[q];   // slices of a window are consecutive 32-row groups
+        }
+    });
 
     // element-major fill: slot (slice, g, lane) holds elements 4g..4g+3 of the lane's row (zero weight padding).
     // Per slice the indices are 16-bit offsets from the slice's smallest index when the slice spans < 65536 control
@@ -163,44 +210,49 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
     int rc = B200OSD_OK;
     {
         std::vector<uint2> pool(poolUnits);
-        std::memset(pool.data(), 0, poolUnits * sizeof(uint2));
-        for (int s = 0; s < t->numSlices; ++s) {
-            const int lo = meta[s].z;
-            const int padTo = meta[s].y * kVec;
-            uint2 *sp = pool.data() + (size_t)(unsigned)meta[s].w;
-            for (int lane = 0; lane < kSliceRows; ++lane) {
-                const int row = rows[(size_t)s * kSliceRows + lane];
-                if (row < 0) continue;
-                const int sz = sizes[row], off = offsets[row];
-                // padded slots (weight 0) repeat the row's own first index: 0 * x is only ever formed with a vertex the row
-                // references anyway, so a NaN / Inf control vertex reaches exactly the rows the reference lets it reach
-                for (int j = 0; j < (sz > 0 ? padTo : 0); ++j) {
-                    const size_t slot = (size_t)(j / kVec) * kSliceRows + lane;
-                    const int ix = indices[j < sz ? elem(off, j) : elem(off, 0)];
-                    if (lo >= 0) reinterpret_cast<unsigned short *>(sp + slot)[j % kVec] = (unsigned short)(ix - lo);
-                    else reinterpret_cast<int *>(reinterpret_cast<int4 *>(sp) + slot)[j % kVec] = ix;
+        parallel_ranges(t->numSlices, 2048, [&](int s0, int s1) {
+            for (int s = s0; s < s1; ++s) {
+                const int lo = meta[s].z;
+                const int padTo = meta[s].y * kVec;
+                uint2 *sp = pool.data() + (size_t)(unsigned)meta[s].w;
+                std::memset(sp, 0, (size_t)meta[s].y * kSliceRows * (lo >= 0 ? 1 : 2) * sizeof(uint2));
+                for (int lane = 0; lane < kSliceRows; ++lane) {
+                    const int row = rows[(size_t)s * kSliceRows + lane];
+                    if (row < 0) continue;
+                    const int sz = sizes[row], off = offsets[row];
+                    // padded slots (weight 0) repeat the row's own first index: 0 * x is only ever formed with a vertex the
+                    // row references anyway, so a NaN / Inf control vertex reaches exactly the rows the reference lets it reach
+                    for (int j = 0; j < (sz > 0 ? padTo : 0); ++j) {
+                        const size_t slot = (size_t)(j / kVec) * kSliceRows + lane;
+                        const int ix = indices[j < sz ? elem(off, j) : elem(off, 0)];
+                        if (lo >= 0) reinterpret_cast<unsigned short *>(sp + slot)[j % kVec] = (unsigned short)(ix - lo);
+                        else reinterpret_cast<int *>(reinterpret_cast<int4 *>(sp) + slot)[j % kVec] = ix;
+                    }
                 }
             }
-        }
+        });
+        // alignment gaps between slices (one unit at most) are never read
         t->ipoolUnits = poolUnits;
         rc = upload(&t->d_ipool, pool.data(), poolUnits);
     }
     if (rc) return rc;
     std::vector<float4> w4(totalVec);
     for (int k = 0; k < t->numW; ++k) {
-        std::memset(w4.data(), 0, totalVec * sizeof(float4));
-        for (int s = 0; s < t->numSlices; ++s) {
-            const size_t base = (unsigned)meta[s].x;
-            for (int lane = 0; lane < kSliceRows; ++lane) {
-                const int row = rows[(size_t)s * kSliceRows + lane];
-                if (row < 0) continue;
-                const int sz = sizes[row], off = offsets[row];
-                for (int j = 0; j < sz; ++j) {
-                    float *slot = reinterpret_cast<float *>(&w4[base + (size_t)(j / kVec) * kSliceRows + lane]);
-                    slot[j % kVec] = w[k][elem(off, j)];
+        parallel_ranges(t->numSlices, 2048, [&](int s0, int s1) {
+            for (int s = s0; s < s1; ++s) {
+                const size_t base = (unsigned)meta[s].x;
+                std::memset(w4.data() + base, 0, (size_t)meta[s].y * kSliceRows * sizeof(float4));
+                for (int lane = 0; lane < kSliceRows; ++lane) {
+                    const int row = rows[(size_t)s * kSliceRows + lane];
+                    if (row < 0) continue;
+                    const int sz = sizes[row], off = offsets[row];
+                    for (int j = 0; j < sz; ++j) {
+                        float *slot = reinterpret_cast<float *>(&w4[base + (size_t)(j / kVec) * kSliceRows + lane]);
+                        slot[j % kVec] = w[k][elem(off, j)];
+                    }
                 }
             }
-        }
+        });
         rc = upload(&t->d_w4[k], w4.data(), totalVec);
         if (rc) return rc;
     }
@@ -491,11 +543,18 @@ int eval_rows(b200osd_stencil_table *t, const StencilIO &io, int nOut, cudaStrea
                                  : (nOut == 3 ? launch_tma<3>(io, s, plan.mode, v - 100, st) : launch_tma<6>(io, s, plan.mode, v - 100, st));
         if (rc != B200OSD_ERR_UNSUPPORTED) return rc;            // lengths / shapes without a TMA instantiation: the default kernels
     }
-    // measured defaults (profiles/r01*): with derivative streams the kernel is register-heavy and latency bound and the
-    // persistent grid's descriptor prefetch wins (+27 % at K=6); up to 6 floats 64 resident warps win (+10 % at L=6)
+    // measured defaults (profiles/r02e_sweep_tma.jsonl): with derivative streams (K = 3, 6) the TMA-staged kernel wins by
+    // 25-33 % (config 3, K = 6: 0.120 -> 0.090 ms = 90 % of the roofline): no registers hold in-flight weight groups and the
+    // stream latency is off the warps' critical path; for K = 1 the one-shot kernel with 64 resident warps is as fast or
+    // faster (its gathers need the occupancy), up to 6 floats with 8 blocks/SM asked of the register allocator.
     if (v == 0) {
-        if (nOut > 1) plan.persistent = true;
-        else if (L <= 6) plan.minBlocks = 8;
+        if (nOut > 1) {
+            const int rc = nOut == 3 ? launch_tma<3>(io, s, plan.mode, 22, st) : launch_tma<6>(io, s, plan.mode, 22, st);
+            if (rc != B200OSD_ERR_UNSUPPORTED) return rc;
+            plan.persistent = true;                              // lengths without a TMA instantiation
+        } else if (L <= 6) {
+            plan.minBlocks = 8;
+        }
     }
     if (v == 2) plan.mode = SRC_SCALAR;
     if (v == 8 || v == 12) plan.persistent = true;
@@ -554,7 +613,7 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, int numCont
     if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
     for (int k = 0; k < t->numW && !rc; ++k) rc = upload(&t->d_w[k], w[k], (size_t)ne);
-    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w, (flags & 2) != 0, !(flags & 4), (flags & 8) != 0);
+    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w, (flags & 2) != 0, !(flags & 4), (flags & 8) ? 2 : ((flags & 16) ? 0 : 1));
     if (rc) {
         b200osd_stencil_table_destroy(t);
         return nullptr;

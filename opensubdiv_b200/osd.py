@@ -153,9 +153,11 @@ class B200StencilTable:
 
     @classmethod
     def Create(cls, table, deviceContext=None, bucketed: bool = True, locality: bool = False,
-               idx16: bool = True, sort_elements: bool = False) -> Optional["B200StencilTable"]:
+               idx16: bool = True, sort_elements: bool = False, keep_order: bool = False) -> Optional["B200StencilTable"]:
         """`table` is anything with the Far::StencilTable / LimitStencilTable accessors as numpy arrays:
-        sizes, offsets, indices, weights and optionally du, dv, duu, duv, dvv (far/stencilTable.h:156-186,434-456)."""
+        sizes, offsets, indices, weights and optionally du, dv, duu, duv, dvv (far/stencilTable.h:156-186,434-456).
+        Summation order (include/b200osd_capi.h): default = rows of <= 16 terms in control-index order; keep_order = the
+        table's own order everywhere; sort_elements = every row in control-index order."""
         def arr(name, dt):
             a = getattr(table, name, None)
             return None if a is None else np.ascontiguousarray(a, dtype=dt)
@@ -164,7 +166,8 @@ class B200StencilTable:
         p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
         ncv = int(getattr(table, "num_control_verts", 0) or 0)       # Far::StencilTable::GetNumControlVertices(); 0 = derive
         h = capi.lib().b200osd_stencil_table_create(len(sizes), ncv, p(sizes), p(offsets), p(indices), *[p(x) for x in w],
-                                                    (0 if bucketed else 1) | (2 if locality else 0) | (0 if idx16 else 4) | (8 if sort_elements else 0))
+                                                    (0 if bucketed else 1) | (2 if locality else 0) | (0 if idx16 else 4)
+                                                    | (8 if sort_elements else 0) | (16 if keep_order else 0))
         return cls(h) if h else None
 
     def __del__(self):
@@ -360,6 +363,20 @@ class B200FrameGraph:
     @property
     def cuda_stream(self) -> int:
         return capi.lib().b200osd_frame_stream(self._h) or 0
+
+    @property
+    def side_stream(self) -> int:
+        """The frame's second (high-priority) stream: work issued on it while recording is a parallel branch."""
+        return capi.lib().b200osd_frame_side_stream(self._h) or 0
+
+    def Fence(self, mainWaitsForSide: bool) -> bool:
+        return capi.check(capi.lib().b200osd_frame_fence(self._h, int(bool(mainWaitsForSide))), "B200FrameGraph::Fence")
+
+    def SetL2Window(self, buf, num_bytes: int, hitRatio: float = 1.0) -> bool:
+        """Keep [buf, buf + num_bytes) L2-resident across the frame's kernels (call before Begin); buf=None clears."""
+        ptr = None if buf is None else (buf if isinstance(buf, int) else _dev_ptr(buf))
+        return capi.check(capi.lib().b200osd_frame_set_l2_window(self._h, ptr, int(num_bytes), float(hitRatio)),
+                          "B200FrameGraph::SetL2Window")
 
     def Begin(self) -> bool: return capi.check(capi.lib().b200osd_frame_begin(self._h), "B200FrameGraph::Begin")
     def End(self) -> bool: return capi.check(capi.lib().b200osd_frame_end(self._h), "B200FrameGraph::End")

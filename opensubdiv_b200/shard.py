@@ -1,4 +1,8 @@
-"""Row-range sharding of the stencil path across the GPUs of one box (one process per GPU, torch.distributed).
+"""Row-range sharding of the stencil path across the GPUs of one box (one process per GPU).
+
+The data plane is in C (include/b200osd_capi.h: b200osd_shard_plan / _shard_coords / b200osd_comm_*, NCCL bound at run
+time); this module is the Python mirror used by bench.py and the tests.  torch.distributed is only the bootstrap (it
+carries the 128-byte NCCL id to the other ranks) and, in the CPU tests, the gloo stand-in for the exchange.
 
 The reference has no multi-GPU code (no NCCL/MPI anywhere); this layer is new.  The path shards
 naturally: every stencil row is independent, the tables are static, and the only per-frame shared input is the small
@@ -28,21 +32,15 @@ import numpy as np
 def balanced_row_ranges(sizes: np.ndarray, world: int, align: int = 1) -> List[Tuple[int, int]]:
     """`world` contiguous row ranges [a,b) covering [0,n) with near-equal sum(sizes) (+1 per row for the fixed per-row
     cost: descriptor + output).  `align` rounds interior cut points to a multiple (e.g. the bucketing window)."""
+    from . import capi
     n = int(len(sizes))
-    if world <= 1 or n == 0:
-        return [(0, n)] + [(n, n)] * (max(world, 1) - 1)
-    cost = np.cumsum(sizes.astype(np.int64) + 1)
-    total = int(cost[-1])
-    cuts = [0]
-    for r in range(1, world):
-        target = total * r // world
-        c = int(np.searchsorted(cost, target, side="left")) + 1
-        if align > 1:
-            c = int(round(c / align)) * align
-        c = min(max(c, cuts[-1]), n)
-        cuts.append(c)
-    cuts.append(n)
-    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+    world = max(int(world), 1)
+    sz = np.ascontiguousarray(sizes, dtype=np.int32)
+    out = np.zeros(2 * world, dtype=np.int32)
+    rc = capi.lib().b200osd_shard_plan(n, sz.ctypes.data if n else None, world, int(align), out.ctypes.data)
+    if rc != capi.OK:
+        raise capi.B200OsdError("b200osd_shard_plan: " + capi.last_error())
+    return [(int(out[2 * r]), int(out[2 * r + 1])) for r in range(world)]
 
 
 @dataclass
@@ -82,16 +80,13 @@ def coord_ranges(num_coords: int, world: int, align: int = 32) -> List[Tuple[int
     interior cuts on a multiple of `align` (a warp's worth of coordinates).  Every coordinate costs the same, so no
     weighting is needed; the patch tables are replicated (small) and each rank refines the control points it needs
     itself, so the only exchange is the same per-frame control-point broadcast the stencil path uses."""
-    n = int(num_coords)
-    world = max(world, 1)
-    cuts = [0]
-    for r in range(1, world):
-        c = n * r // world
-        if align > 1:
-            c = (c + align // 2) // align * align
-        cuts.append(min(max(c, cuts[-1]), n))
-    cuts.append(n)
-    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+    from . import capi
+    world = max(int(world), 1)
+    out = np.zeros(2 * world, dtype=np.int64)
+    rc = capi.lib().b200osd_shard_coords(int(num_coords), world, int(align), out.ctypes.data)
+    if rc != capi.OK:
+        raise capi.B200OsdError("b200osd_shard_coords: " + capi.last_error())
+    return [(int(out[2 * r]), int(out[2 * r + 1])) for r in range(world)]
 
 
 def coord_plan(num_coords: int, world: int, rank: int, align: int = 32) -> ShardPlan:
@@ -165,3 +160,68 @@ def all_gather_rows(local_rows, plan: ShardPlan, group=None):
     parts = [torch.empty_like(pad) for _ in range(plan.world)]
     dist.all_gather(parts, pad, group=group)
     return torch.cat([p[: b - a] for p, (a, b) in zip(parts, plan.ranges)], dim=0)
+
+
+class B200Comm:
+    """The C communicator (b200osd_comm_*: NCCL over NVLink, one process per GPU).  `Create` bootstraps through an
+    already initialised torch.distributed group of any backend (it only carries the 128-byte id), or takes the id."""
+
+    def __init__(self, handle, world, rank):
+        self._h, self.world, self.rank = handle, world, rank
+
+    @staticmethod
+    def available() -> bool:
+        from . import capi
+        return bool(capi.lib().b200osd_comm_available())
+
+    @classmethod
+    def Create(cls, world: Optional[int] = None, rank: Optional[int] = None, unique_id: Optional[bytes] = None, group=None,
+               max_ctas: int = 0):
+        import ctypes as C
+        from . import capi
+        L = capi.lib()
+        if unique_id is None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            buf = (C.c_char * 128)()
+            if rank == 0 and L.b200osd_comm_unique_id(buf) != capi.OK:
+                raise capi.B200OsdError("b200osd_comm_unique_id: " + capi.last_error())
+            box = [bytes(buf)]
+            dist.broadcast_object_list(box, src=0, group=group)
+            unique_id = box[0]
+        idbuf = (C.c_char * 128).from_buffer_copy(unique_id)
+        h = L.b200osd_comm_create_ex(int(world), int(rank), idbuf, int(max_ctas))
+        if not h:
+            raise capi.B200OsdError("b200osd_comm_create: " + capi.last_error())
+        return cls(h, int(world), int(rank))
+
+    def __del__(self):
+        try:
+            if self._h:
+                from . import capi
+                capi.lib().b200osd_comm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def leak(self) -> None:
+        """Skip ncclCommDestroy at interpreter exit (a communicator that recorded graphs still reference)."""
+        self._h = None
+
+    def Broadcast(self, buf, count: int, root: int = 0, deviceContext=None) -> bool:
+        from . import capi
+        from .osd import _dev_ptr, _stream_ptr
+        return capi.check(capi.lib().b200osd_comm_broadcast(self._h, _dev_ptr(buf), int(count), int(root), _stream_ptr(deviceContext)),
+                          "B200Comm::Broadcast")
+
+    def Scatter(self, sendbuf, recvbuf, count_per_rank: int, root: int = 0, deviceContext=None) -> bool:
+        from . import capi
+        from .osd import _dev_ptr, _stream_ptr
+        return capi.check(capi.lib().b200osd_comm_scatter(self._h, _dev_ptr(sendbuf) if sendbuf is not None else None, _dev_ptr(recvbuf),
+                                                          int(count_per_rank), int(root), _stream_ptr(deviceContext)), "B200Comm::Scatter")
+
+    def AllGather(self, sendbuf, recvbuf, count_per_rank: int, deviceContext=None) -> bool:
+        from . import capi
+        from .osd import _dev_ptr, _stream_ptr
+        return capi.check(capi.lib().b200osd_comm_all_gather(self._h, _dev_ptr(sendbuf), _dev_ptr(recvbuf), int(count_per_rank),
+                                                             _stream_ptr(deviceContext)), "B200Comm::AllGather")

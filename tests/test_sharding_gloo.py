@@ -171,3 +171,42 @@ def test_sharded_patch_coords_equal_single_evaluation():
     for rank, ok, ranges in got:
         assert ok == [True, True], (rank, ok)
         assert ranges[0][0] == 0 and ranges[-1][1] > ranges[-1][0]
+
+
+def test_c_shard_plan_matches_a_straight_restatement():
+    """b200osd_shard_plan / b200osd_shard_coords (the C data plane: include/b200osd_capi.h) against a direct numpy
+    restatement of their contract; called through ctypes exactly as a C++ host would call them."""
+    from opensubdiv_b200 import capi
+    rng = np.random.default_rng(7)
+    sizes = rng.integers(1, 31, 50_000).astype(np.int32)
+    cost = np.cumsum(sizes.astype(np.int64) + 1)
+    for world in (1, 2, 5, 8):
+        for align in (1, 32, 2048):
+            out = np.zeros(2 * world, np.int32)
+            assert capi.lib().b200osd_shard_plan(len(sizes), sizes.ctypes.data, world, align, out.ctypes.data) == capi.OK
+            cuts = [0]
+            for r in range(1, world):
+                c = int(np.searchsorted(cost, int(cost[-1]) * r // world, side="left")) + 1
+                if align > 1:
+                    c = (c + align // 2) // align * align
+                cuts.append(min(max(c, cuts[-1]), len(sizes)))
+            cuts.append(len(sizes))
+            assert out.reshape(world, 2).tolist() == [[cuts[i], cuts[i + 1]] for i in range(world)]
+            co = np.zeros(2 * world, np.int64)
+            assert capi.lib().b200osd_shard_coords(10_000_001, world, align, co.ctypes.data) == capi.OK
+            co = co.reshape(world, 2)
+            assert co[0, 0] == 0 and co[-1, 1] == 10_000_001 and (co[1:, 0] == co[:-1, 1]).all()
+            assert (np.diff(co, axis=1) >= 0).all() and all(int(a) % align == 0 for a in co[1:, 0])
+    bad = np.zeros(2, np.int32)
+    assert capi.lib().b200osd_shard_plan(10, None, 1, 1, bad.ctypes.data) == capi.ERR_INVALID
+
+
+def test_communicator_needs_a_device():
+    """No CPU fallback in the exchange either: without a CUDA device b200osd_comm_create returns NULL with a message."""
+    import ctypes as C
+    from opensubdiv_b200 import capi
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    ident = (C.c_char * 128)()
+    assert not capi.lib().b200osd_comm_create(1, 0, ident)
+    assert capi.last_error()

@@ -15,12 +15,12 @@ from opensubdiv_b200 import capi, synth  # noqa: E402
 D = osd.BufferDescriptor
 n = int(os.environ.get("N", 10_000_000))
 ncu = os.environ.get("NCU") == "1"
-if ncu:
-    capi.lib().b200osd_set_patch_variant(int(os.environ.get("VARIANTS", "0").split(",")[0]))
 variants = [int(v) for v in os.environ.get("VARIANTS", "0").split(",")]
 mesh = synth.torus_quads(400, 250)
 ptab = synth.torus_patch_table(mesh)
 pt = osd.B200PatchTable.Create(ptab)
+if ncu:
+    pt.SetVariant(int(os.environ.get("VARIANTS", "0").split(",")[0]))
 src = torch.from_numpy(np.ascontiguousarray(synth.deform(mesh.positions, 1))).cuda()
 
 
@@ -47,7 +47,7 @@ for sort in (False, True):
         torch.cuda.synchronize()
         continue
     for variant in variants:
-        capi.lib().b200osd_set_patch_variant(variant)
+        pt.SetVariant(variant)
         for nw in (1, 3, 6):
             for inter in (True, False):
                 if nw == 1 and not inter:
@@ -67,5 +67,5 @@ for sort in (False, True):
                                   "layout": "interleaved" if inter else "separate", "ms": round(ms, 4),
                                   "Gpts_per_s": round(n / ms / 1e6, 2)}), flush=True)
                 del a, keep
-    capi.lib().b200osd_set_patch_variant(0)
+    pt.SetVariant(0)
 print("done")
