@@ -28,8 +28,9 @@ One step = one frame = one EvalStencils pass over the whole table.
   incumbent_cuda  (N = 1) the reference's own CUDA kernels (osd/cudaKernel.cu compiled for sm_100a under oracle/_ref)
 
 Multi-GPU (N > 1), headline: weak scaling.  The scene is N such meshes; rank r owns the stencil rows of mesh r; every
-frame the root's deformed control points are handed out with b200osd_comm_scatter -- each GPU receives only the 2.4 MB
-it reads -- on a high-priority side stream while the previous frame is evaluated.  value = all rows of all ranks /
+frame every GPU pulls its own mesh's 2.4 MB of deformed control points out of the root's peer-memory window by DMA over
+NVLink (b200osd_window_get: copy engines, no collective kernel next to the evaluation) on a side stream while the
+previous frame is evaluated.  value = all rows of all ranks /
 max-over-ranks time.
 """
 from __future__ import annotations
@@ -516,11 +517,11 @@ class FramePipe:
     def post(self, g, before=None):
         b = g % 2
         if before is not None:
-            before(g)                                            # e.g. the H2D upload of frame g's control points (root)
+            before(g)                                            # e.g. the H2D upload of frame g's control points (1 GPU)
         if self.active:
             self.side.wait_event(self.free[b])                   # the last reader of this block has finished
             self.side.wait_stream(self.main)                     # the producer of this frame's data (root)
-            self.exchange(b, self.side)
+            self.exchange(b, self.side, g)
             self.ready[b].record(self.side)
         else:
             self.ready[b].record(self.main)
@@ -594,13 +595,45 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
     blocks = [vt[:ncv], vt[ncv:2 * ncv]]
     torch.cuda.synchronize()
 
-    def exchange(b, stream):
+    def exchange(b, stream, g=0):
         assert comm.Broadcast(blocks[b], ncv * 3, 0, deviceContext=stream)
 
     def evaluate(b, region):
         assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, D(2 * ncv * 3, 3, 3), tbl)
-    pipe = FramePipe(torch, exchange, evaluate, active=world > 1)
-    ms = timed_steps(torch, dist, world, lambda k: pipe.step(), steps, warmup, torch.cuda.current_stream())
+    launch = "eager pipeline"
+    ms = None
+    if world > 1:
+        # per-rank kernels are 15-60 us here: the Python issue loop would be the bottleneck, so two frames (one per control
+        # block; the kernel of block b next to the broadcast of block 1-b) are recorded once into a b200osd frame graph
+        try:
+            fg = osd.B200FrameGraph.Create()
+            side = torch.cuda.ExternalStream(fg.side_stream)
+            gstream = torch.cuda.ExternalStream(fg.cuda_stream)
+            for b in (0, 1):
+                exchange(b, torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            assert fg.Begin()
+            for b in (0, 1):
+                fg.Fence(False)                            # side waits for main: block 1-b's last reader has finished
+                exchange(1 - b, side)
+                assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, D(2 * ncv * 3, 3, 3), tbl, None, fg)
+                fg.Fence(True)                             # the next kernel reads block 1-b
+            assert fg.End()
+            half = {"v": 0}
+
+            def step_graph(_):
+                if half["v"] == 0:
+                    fg.Launch()
+                half["v"] ^= 1
+            steps += steps % 2
+            ms = timed_steps(torch, dist, world, step_graph, steps, warmup + warmup % 2, gstream)
+            launch = "b200osd frame graph of 2 frames (kernel || broadcast of the other control block), one cudaGraphLaunch per 2 frames"
+        except Exception as exc:
+            log(f"[bench] rank {rank}: config-5 frame graph failed ({exc}); eager pipeline")
+            ms = None
+    if ms is None:
+        pipe = FramePipe(torch, exchange, evaluate, active=world > 1)
+        ms = timed_steps(torch, dist, world, lambda k: pipe.step(), steps, warmup, torch.cuda.current_stream())
     ms_step = ms / steps
     peak, _ = measured_peak()
     sizes = {}
@@ -610,6 +643,7 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
             "rows": int(n_total), "elements": int(table.num_elements), "control_verts": int(ncv), "row_sizes": sizes,
             "rows_this_rank": int(n), "imbalance": plan.imbalance(table.sizes),
             "exchange": "none (1 GPU)" if world == 1 else f"b200osd_comm_broadcast of {ncv * 12} B per frame from rank 0, side stream, double-buffered",
+            "launch": launch,
             "n_gpus": world, "steps": steps, "ms_per_step": ms_step, "value": n_total / (ms_step * 1e-3), "unit": "verts/s",
             "roofline_per_gpu": {"bound": "hbm", "achieved": alg_local / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": alg_local / (ms_step * 1e-3) / 1e9 / peak, "algorithmic_bytes_this_rank": int(alg_local),
@@ -639,10 +673,7 @@ def run_b200_arm(args):
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"                 # the version banner goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        # two communicators: the headline's 2.4 MB per-rank hand-out hides behind a 0.16 ms kernel and should take as few SMs
-        # from it as possible (2 CTAs); config 5's 6 MB broadcast is on the critical path of 15-60 us kernels (NCCL's default)
-        comm = shard.B200Comm.Create(max_ctas=2)
-        comm_wide = shard.B200Comm.Create()
+        comm = comm_wide = shard.B200Comm.Create()
     D = osd.BufferDescriptor
     lib = capi.lib()
 
@@ -669,8 +700,16 @@ def run_b200_arm(args):
     src_descs = [D(b * ncv * L, L, L) for b in (0, 1)]
     dst_vertex = [2 * ncv, 2 * ncv + n]
     dst_descs = [D(v * L, L, L) for v in dst_vertex]
-    # the root holds the whole scene's control points of a frame (world meshes) and hands every rank its own mesh
-    scene = [torch.empty((world * ncv, L), device="cuda") for _ in (0, 1)] if (world > 1 and rank == 0) else [None, None]
+    # The root holds the whole scene's control points of a frame (world meshes) in a peer-memory window; every rank PULLS
+    # its own mesh's 2.4 MB from it by DMA over NVLink (b200osd_window_get) -- no collective kernel runs next to the
+    # evaluation.  Ordering across ranks: ready(b) root -> all, pulled(b) all -> root (b200osd_window_signal / _wait).
+    win = None
+    scene = [None, None]
+    slice_bytes = ncv * L * 4
+    if world > 1:
+        win = shard.B200Window.Create(comm, 2 * world * slice_bytes)
+        wt = win.local_tensor().view(2, world * ncv, L)
+        scene = [wt[0], wt[1]]
     frames = [torch.from_numpy(frame_primvars(mesh, f)).pin_memory() for f in range(4)]
     scene_frames = [torch.from_numpy(np.tile(frames[f].numpy(), (world, 1))).pin_memory() for f in range(4)] if (world > 1 and rank == 0) else None
     host_out = [torch.empty((n, L), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -682,22 +721,32 @@ def run_b200_arm(args):
         e.record(stream)
     for b in (0, 1):                                       # device-resident control points for the `value` measurement
         vb.UpdateData(frames[b], b * ncv, ncv)
-        if scene[b] is not None:
+        if world > 1 and rank == 0:
             scene[b].copy_(scene_frames[b], non_blocking=True)
     torch.cuda.synchronize()
+    mode = {"e2e": False}
 
-    def exchange(b, side):
-        assert comm.Scatter(scene[b], blocks[b], ncv * L, 0, deviceContext=side)
+    def exchange(b, side, g=0):
+        if rank == 0:
+            if g >= 2:
+                assert win.Wait(-1, 2 + b, side)           # every rank has pulled the previous contents of scene block b
+            if mode["e2e"]:                                # host-buffer path: this frame's scene, H2D on the side stream
+                with torch.cuda.stream(side):
+                    scene[b].copy_(scene_frames[g % len(frames)], non_blocking=True)
+            assert win.Signal(-1, b, side)                 # scene block b is complete
+            assert win.Get(0, b * world * slice_bytes, blocks[b], slice_bytes, side)
+        else:
+            assert win.Wait(0, b, side)
+            assert win.Get(0, (b * world + rank) * slice_bytes, blocks[b], slice_bytes, side)
+            assert win.Signal(0, 2 + b, side)              # pulled
 
     def evaluate(b, region):
         assert osd.B200Evaluator.EvalStencils(vb, src_descs[b], vb, dst_descs[region], tbl)
     pipe = FramePipe(torch, exchange, evaluate, active=world > 1)
 
-    def upload(g):                                         # host-buffer path: this frame's control points H2D (root: the scene)
+    def upload(g):                                         # host-buffer path, 1 GPU: this frame's control points H2D
         if world == 1:
             vb.UpdateData(frames[g % len(frames)], (g % 2) * ncv, ncv)
-        elif rank == 0:
-            scene[g % 2].copy_(scene_frames[g % len(frames)], non_blocking=True)
 
     def readback(f, r):                                    # D2H of this rank's refined vertices on the copy stream
         kernel_done[r].record(stream)
@@ -706,12 +755,14 @@ def run_b200_arm(args):
         d2h_done[r].record(copy_stream)
 
     def step_device(_):
-        """Device-resident step: control points already in HBM on the root; (N>1: per-frame scatter, overlapped with the
+        """Device-resident step: control points already in HBM on the root; (N>1: per-frame hand-out, overlapped with the
         previous frame's kernel) + EvalStencils of this rank's rows."""
+        mode["e2e"] = False
         pipe.step(0)
 
     def step_e2e(_):
         """Host-buffer step through the C ABI: H2D control points (root), hand out, evaluate, D2H refined vertices."""
+        mode["e2e"] = True
         r = pipe.f % 2
         stream.wait_event(d2h_done[r])                     # refined region r: read-back of frame f-2 has finished
         pipe.step(r, before=upload, after=readback)
@@ -722,13 +773,10 @@ def run_b200_arm(args):
     if world > 1 and args.graph:
         fg = osd.B200FrameGraph.Create()
         side = torch.cuda.ExternalStream(fg.side_stream)
-        for b in (0, 1):
-            exchange(b, torch.cuda.current_stream())
-        torch.cuda.synchronize()
         assert fg.Begin()
         for b in (0, 1):
             fg.Fence(False)                                # side waits for main: block 1-b's last reader has finished
-            exchange(1 - b, side)
+            exchange(1 - b, side, 0)                       # g = 0: scene blocks are not rewritten in the recorded frames
             assert osd.B200Evaluator.EvalStencils(vb, src_descs[b], vb, dst_descs[0], tbl, None, fg)
             fg.Fence(True)                                 # the next kernel reads block 1-b
         assert fg.End()
@@ -775,6 +823,7 @@ def run_b200_arm(args):
     check_host = torch.zeros(L).pin_memory()
 
     def step_e2e_resident(_):
+        mode["e2e"] = True
         pipe.step(0, before=upload)
         torch.sum(vt[dst_vertex[0]:dst_vertex[0] + n], dim=0, out=check)
         check_host.copy_(check, non_blocking=True)
@@ -840,7 +889,7 @@ def run_b200_arm(args):
             "run": {"parallelism": f"row-range x{world} (rank r owns mesh r)",
                     "launch": "eager pipeline" if graph is None else "b200osd frame graph of 2 frames (kernel || exchange of the other control block)",
                     "exchange": "none (1 GPU)" if world == 1 else
-                    f"per-frame b200osd_comm_scatter: every rank receives its own {ncv * L * 4} B of control points from rank 0, double-buffered on a high-priority side stream",
+                    f"per-frame pull over NVLink peer memory: every rank copies its own {ncv * L * 4} B of control points out of rank 0's window by DMA (b200osd_window_get; ready / pulled ordering by b200osd_window_signal / _wait), double-buffered on a high-priority side stream",
                     "l2_policy": "inputs larger than L2 (table streams 0.55 GB/step vs 126 MB L2); no flush needed",
                     "stencil_variant": tbl.GetVariant(), "bucketed_stream_bytes": tbl.GetStreamBytes(1),
                     "summation_order": "rows of <= 16 elements in control-index order (library default), longer rows in table order",
@@ -868,9 +917,12 @@ def run_b200_arm(args):
         # leave without tearing NCCL down: destroying communicators that recorded graphs still reference can hang
         torch.cuda.synchronize()
         dist.barrier()
-        for c in (comm, comm_wide):
-            if c is not None:
-                c.leak()
+        if win is not None:
+            if win.Error():
+                log(f"[bench] rank {rank}: a window wait timed out")
+            win.leak()
+        if comm is not None:
+            comm.leak()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)

@@ -284,6 +284,23 @@ B200OSD_API int  b200osd_comm_scatter(b200osd_comm *c, const float *sendbuf, flo
 /* optional: every rank gets every rank's countPerRank floats (a consumer that wants the whole refined buffer) */
 B200OSD_API int  b200osd_comm_all_gather(b200osd_comm *c, const float *sendbuf, float *recvbuf, size_t countPerRank, void *stream);
 
+/* Peer-memory window: one-sided exchange over NVLink WITHOUT collective kernels.  _create (collective over `c`) allocates
+ * `bytes` of device memory on every rank and maps every rank's block into every other rank (CUDA IPC); _local is this
+ * rank's block.  _get copies from any rank's block into local memory by DMA (copy engines: no SM is taken from a kernel
+ * running next to it); _signal / _wait order streams ACROSS ranks through per-(slot, sender) counters in peer memory,
+ * written and polled by one-thread kernels: work issued on `stream` after _wait(src, slot) runs only once the matching
+ * _signal(dst, slot) of rank src -- issued on ITS stream after the data was produced -- has executed.  rank = -1 means
+ * every peer.  16 slots.  A wait gives up after 10 s and sets the error flag (b200osd_window_error != 0). */
+typedef struct b200osd_window b200osd_window;
+B200OSD_API b200osd_window *b200osd_window_create(b200osd_comm *c, size_t bytes);
+B200OSD_API void   b200osd_window_destroy(b200osd_window *w);
+B200OSD_API void  *b200osd_window_local(const b200osd_window *w);
+B200OSD_API size_t b200osd_window_bytes(const b200osd_window *w);
+B200OSD_API int    b200osd_window_get(b200osd_window *w, int srcRank, size_t srcOffsetBytes, void *dst, size_t bytes, void *stream);
+B200OSD_API int    b200osd_window_signal(b200osd_window *w, int dstRank, int slot, void *stream);
+B200OSD_API int    b200osd_window_wait(b200osd_window *w, int srcRank, int slot, void *stream);
+B200OSD_API int    b200osd_window_error(b200osd_window *w);
+
 /* ---- tuning / introspection (used by bench.py and the tests; not needed by clients) ----------
  * Kernel variant of b200osd_stencil_table_eval for THIS table (there is no process-wide state): 0 = auto,
  * 1 = reference-layout (CSR) kernel, 2 = scalar gathers, 8 = persistent grid, 11 = 8 resident blocks/SM, 12 = 8 + 11. */

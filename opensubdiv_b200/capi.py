@@ -36,6 +36,8 @@ SYMBOLS = [
     "b200osd_shard_plan", "b200osd_shard_coords", "b200osd_comm_available", "b200osd_comm_unique_id", "b200osd_comm_create", "b200osd_comm_create_ex",
     "b200osd_comm_destroy", "b200osd_comm_world", "b200osd_comm_rank", "b200osd_comm_broadcast", "b200osd_comm_scatter",
     "b200osd_comm_all_gather",
+    "b200osd_window_create", "b200osd_window_destroy", "b200osd_window_local", "b200osd_window_bytes", "b200osd_window_get",
+    "b200osd_window_signal", "b200osd_window_wait", "b200osd_window_error",
     "b200osd_frame_create", "b200osd_frame_destroy", "b200osd_frame_stream", "b200osd_frame_begin", "b200osd_frame_end",
     "b200osd_frame_launch", "b200osd_frame_synchronize",
 ]
@@ -134,6 +136,17 @@ def lib():
     L.b200osd_comm_broadcast.argtypes = [vp, vp, C.c_size_t, i, vp]
     L.b200osd_comm_scatter.argtypes = [vp, vp, vp, C.c_size_t, i, vp]
     L.b200osd_comm_all_gather.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.b200osd_window_create.restype = vp
+    L.b200osd_window_create.argtypes = [vp, C.c_size_t]
+    L.b200osd_window_destroy.argtypes = [vp]
+    L.b200osd_window_local.restype = vp
+    L.b200osd_window_local.argtypes = [vp]
+    L.b200osd_window_bytes.restype = C.c_size_t
+    L.b200osd_window_bytes.argtypes = [vp]
+    L.b200osd_window_get.argtypes = [vp, i, C.c_size_t, vp, C.c_size_t, vp]
+    L.b200osd_window_signal.argtypes = [vp, i, i, vp]
+    L.b200osd_window_wait.argtypes = [vp, i, i, vp]
+    L.b200osd_window_error.argtypes = [vp]
     _lib = L
     return L
 

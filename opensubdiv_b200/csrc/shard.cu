@@ -237,3 +237,160 @@ int b200osd_comm_all_gather(b200osd_comm *c, const float *sendbuf, float *recvbu
 }
 
 }  // extern "C"
+
+// --------------------------------------------------------------------------- peer-memory window --
+// One-sided exchange over NVLink peer memory, without NCCL kernels: every rank owns a device buffer that all other ranks
+// of the box can address (CUDA IPC), data moves by DMA (copy engines: cudaMemcpyAsync between peer-mapped pointers) and
+// ordering is carried by per-(slot, sender) counters in peer memory written / polled by ONE-thread kernels.  An
+// evaluation kernel that runs next to such an exchange keeps all of its SMs -- the NCCL path costs it the 8-16 thread
+// blocks of the collective's kernel for the duration of the transfer.
+namespace {
+
+constexpr int kWindowSlots = 16;
+
+// after everything issued so far on the stream: bump my counter for (slot -> peer p) and store it into p's flag array
+__global__ void window_signal_kernel(int *const *peerFlags, int *sendSeq, int world, int rank, int slot, int dst) {
+    const int p = threadIdx.x;
+    if (p >= world || p == rank || (dst >= 0 && p != dst)) return;
+    const int v = sendSeq[slot * world + p] + 1;
+    sendSeq[slot * world + p] = v;
+    __threadfence_system();
+    *reinterpret_cast<volatile int *>(peerFlags[p] + slot * world + rank) = v;
+}
+
+// later work on the stream waits until the next signal of (slot, sender p) has arrived; gives up after 10 s (sets *error)
+__global__ void window_wait_kernel(const int *flags, int *expect, int world, int rank, int slot, int src, int *error) {
+    const int p = threadIdx.x;
+    if (p >= world || p == rank || (src >= 0 && p != src)) return;
+    const int want = expect[slot * world + p] + 1;
+    expect[slot * world + p] = want;
+    const volatile int *f = flags + slot * world + p;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*f < want) {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { *error = 1; return; }
+    }
+    __threadfence_system();
+}
+
+}  // namespace
+
+struct b200osd_window {
+    b200osd_comm *comm = nullptr;
+    int world = 1, rank = 0;
+    size_t bytes = 0;
+    void *block = nullptr;                 // one cudaMalloc: [ data (bytes, 256-aligned) | flags | sendSeq | expect | error | peerFlags table ]
+    char *data = nullptr;
+    int *flags = nullptr, *sendSeq = nullptr, *expect = nullptr, *error = nullptr;
+    int **d_peerFlags = nullptr;
+    std::vector<char *> peerData;          // every rank's data region as mapped here (own: local pointer)
+    std::vector<void *> opened;            // IPC mappings to close
+};
+
+extern "C" {
+
+b200osd_window *b200osd_window_create(b200osd_comm *c, size_t bytes) {
+    if (!c || bytes == 0) { set_error("window_create: NULL communicator / empty window"); return nullptr; }
+    NcclApi *a = nccl();
+    b200osd_window *w = new (std::nothrow) b200osd_window;
+    if (!w) return nullptr;
+    w->comm = c;
+    w->world = c->world;
+    w->rank = c->rank;
+    w->bytes = bytes;
+    const size_t dataBytes = (bytes + 255) & ~(size_t)255;
+    const size_t ctr = (size_t)kWindowSlots * w->world * sizeof(int);
+    const size_t total = dataBytes + 3 * ((ctr + 255) & ~(size_t)255) + 256 + (((size_t)w->world * sizeof(int *) + 255) & ~(size_t)255);
+    cudaError_t e = cudaMalloc(&w->block, total);
+    if (e != cudaSuccess) { set_error("window_create: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e)); delete w; return nullptr; }
+    cudaMemset(w->block, 0, total);
+    char *p = static_cast<char *>(w->block);
+    w->data = p;                                         p += dataBytes;
+    w->flags = reinterpret_cast<int *>(p);               p += (ctr + 255) & ~(size_t)255;
+    w->sendSeq = reinterpret_cast<int *>(p);             p += (ctr + 255) & ~(size_t)255;
+    w->expect = reinterpret_cast<int *>(p);              p += (ctr + 255) & ~(size_t)255;
+    w->error = reinterpret_cast<int *>(p);               p += 256;
+    w->d_peerFlags = reinterpret_cast<int **>(p);
+    w->peerData.assign((size_t)w->world, nullptr);
+    std::vector<int *> peerFlags((size_t)w->world, nullptr);
+    w->peerData[(size_t)w->rank] = w->data;
+    peerFlags[(size_t)w->rank] = w->flags;
+    bool ok = true;
+    if (w->world > 1) {
+        // every rank's IPC handle of its block travels through one all-gather; offsets inside the block are identical
+        cudaIpcMemHandle_t mine;
+        ok = cudaIpcGetMemHandle(&mine, w->block) == cudaSuccess;
+        const size_t hb = sizeof(cudaIpcMemHandle_t);
+        const size_t slotFloats = (hb + 3) / 4;
+        float *dsend = nullptr, *drecv = nullptr;
+        ok = ok && cudaMalloc((void **)&dsend, slotFloats * 4) == cudaSuccess && cudaMalloc((void **)&drecv, slotFloats * 4 * w->world) == cudaSuccess;
+        std::vector<cudaIpcMemHandle_t> all((size_t)w->world);
+        if (ok) {
+            cudaMemcpy(dsend, &mine, hb, cudaMemcpyHostToDevice);
+            ok = a->AllGather(dsend, drecv, slotFloats, kNcclFloat, c->comm, (cudaStream_t)0) == kNcclSuccess &&
+                 cudaStreamSynchronize(0) == cudaSuccess;
+            for (int r = 0; ok && r < w->world; ++r)
+                ok = cudaMemcpy(&all[(size_t)r], reinterpret_cast<char *>(drecv) + (size_t)r * slotFloats * 4, hb, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        cudaFree(dsend);
+        cudaFree(drecv);
+        for (int r = 0; ok && r < w->world; ++r) {
+            if (r == w->rank) continue;
+            void *base = nullptr;
+            if (cudaIpcOpenMemHandle(&base, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+            w->opened.push_back(base);
+            w->peerData[(size_t)r] = static_cast<char *>(base);
+            peerFlags[(size_t)r] = reinterpret_cast<int *>(static_cast<char *>(base) + dataBytes);
+        }
+    }
+    if (ok) ok = cudaMemcpy(w->d_peerFlags, peerFlags.data(), (size_t)w->world * sizeof(int *), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        set_error("window_create: exchanging / opening the peer mappings failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b200osd_window_destroy(w);
+        return nullptr;
+    }
+    return w;
+}
+
+void b200osd_window_destroy(b200osd_window *w) {
+    if (!w) return;
+    for (void *p : w->opened) cudaIpcCloseMemHandle(p);
+    cudaFree(w->block);
+    delete w;
+}
+
+void *b200osd_window_local(const b200osd_window *w) { return w ? (void *)w->data : nullptr; }
+size_t b200osd_window_bytes(const b200osd_window *w) { return w ? w->bytes : 0; }
+
+int b200osd_window_get(b200osd_window *w, int srcRank, size_t srcOffsetBytes, void *dst, size_t bytes, void *stream) {
+    if (!w || !dst || srcRank < 0 || srcRank >= w->world) { set_error("window_get: bad window / rank / destination"); return B200OSD_ERR_INVALID; }
+    if (srcOffsetBytes + bytes > w->bytes) { set_error("window_get: [%zu,+%zu) outside the %zu-byte window", srcOffsetBytes, bytes, w->bytes); return B200OSD_ERR_INVALID; }
+    if (bytes == 0) return B200OSD_OK;
+    B200_CUDA_TRY(cudaMemcpyAsync(dst, w->peerData[(size_t)srcRank] + srcOffsetBytes, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B200OSD_OK;
+}
+
+int b200osd_window_signal(b200osd_window *w, int dstRank, int slot, void *stream) {
+    if (!w || slot < 0 || slot >= kWindowSlots || dstRank >= w->world) { set_error("window_signal: bad window / slot / rank"); return B200OSD_ERR_INVALID; }
+    if (w->world == 1) return B200OSD_OK;
+    window_signal_kernel<<<1, 32 * ((w->world + 31) / 32), 0, (cudaStream_t)stream>>>(w->d_peerFlags, w->sendSeq, w->world, w->rank, slot, dstRank);
+    return check_launch("window_signal_kernel");
+}
+
+int b200osd_window_wait(b200osd_window *w, int srcRank, int slot, void *stream) {
+    if (!w || slot < 0 || slot >= kWindowSlots || srcRank >= w->world) { set_error("window_wait: bad window / slot / rank"); return B200OSD_ERR_INVALID; }
+    if (w->world == 1) return B200OSD_OK;
+    window_wait_kernel<<<1, 32 * ((w->world + 31) / 32), 0, (cudaStream_t)stream>>>(w->flags, w->expect, w->world, w->rank, slot, srcRank, w->error);
+    return check_launch("window_wait_kernel");
+}
+
+int b200osd_window_error(b200osd_window *w) {
+    if (!w) return 0;
+    int e = 0;
+    if (cudaMemcpy(&e, w->error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return e;
+}
+
+}  // extern "C"

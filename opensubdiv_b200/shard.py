@@ -225,3 +225,62 @@ class B200Comm:
         from .osd import _dev_ptr, _stream_ptr
         return capi.check(capi.lib().b200osd_comm_all_gather(self._h, _dev_ptr(sendbuf), _dev_ptr(recvbuf), int(count_per_rank),
                                                              _stream_ptr(deviceContext)), "B200Comm::AllGather")
+
+
+class B200Window:
+    """Peer-memory window (b200osd_window_*): every rank's block is addressable by every other rank; data moves by DMA,
+    ordering by one-thread signal / wait kernels -- no collective kernel takes SMs from the evaluation."""
+
+    def __init__(self, handle, comm, nbytes):
+        self._h, self.comm, self.nbytes = handle, comm, nbytes
+        self._tensor = None
+
+    @classmethod
+    def Create(cls, comm: B200Comm, nbytes: int) -> "B200Window":
+        from . import capi
+        h = capi.lib().b200osd_window_create(comm._h, int(nbytes))
+        if not h:
+            raise capi.B200OsdError("b200osd_window_create: " + capi.last_error())
+        return cls(h, comm, int(nbytes))
+
+    def leak(self) -> None:
+        self._h = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                from . import capi
+                capi.lib().b200osd_window_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def local_tensor(self):
+        """Zero-copy float32 torch view of this rank's block."""
+        if self._tensor is None:
+            import torch
+            from . import capi
+            from .osd import _CudaArrayView
+            ptr = capi.lib().b200osd_window_local(self._h)
+            self._tensor = torch.as_tensor(_CudaArrayView(ptr, self.nbytes // 4, self), device="cuda")
+        return self._tensor
+
+    def Get(self, src_rank: int, src_offset_bytes: int, dst, nbytes: int, deviceContext=None) -> bool:
+        from . import capi
+        from .osd import _dev_ptr, _stream_ptr
+        return capi.check(capi.lib().b200osd_window_get(self._h, int(src_rank), int(src_offset_bytes), _dev_ptr(dst), int(nbytes),
+                                                        _stream_ptr(deviceContext)), "B200Window::Get")
+
+    def Signal(self, dst_rank: int, slot: int, deviceContext=None) -> bool:
+        from . import capi
+        from .osd import _stream_ptr
+        return capi.check(capi.lib().b200osd_window_signal(self._h, int(dst_rank), int(slot), _stream_ptr(deviceContext)), "B200Window::Signal")
+
+    def Wait(self, src_rank: int, slot: int, deviceContext=None) -> bool:
+        from . import capi
+        from .osd import _stream_ptr
+        return capi.check(capi.lib().b200osd_window_wait(self._h, int(src_rank), int(slot), _stream_ptr(deviceContext)), "B200Window::Wait")
+
+    def Error(self) -> int:
+        from . import capi
+        return capi.lib().b200osd_window_error(self._h)
