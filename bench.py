@@ -294,7 +294,8 @@ def bench_config3(mesh, torch, osd, iters):
     n = 1_000_000
     rng = np.random.default_rng(12345)
     face = np.sort(rng.integers(0, len(mesh.faces), n)).astype(np.int32)
-    ls = synth.torus_limit_stencil_table(mesh, face, rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32))
+    s_h, t_h = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+    ls = synth.torus_limit_stencil_table(mesh, face, s_h, t_h)
     tbl = osd.B200StencilTable.Create(ls)
     ncv = ls.num_control_verts
     src = torch.from_numpy(frame_primvars(mesh, 1)[:, :3].copy()).cuda()
@@ -311,6 +312,50 @@ def bench_config3(mesh, torch, osd, iters):
                         "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": alg / (ms * 1e-3) / 1e9 / peak}}
     del tbl
+    # the same table CONSTRUCTED on the device (b200osd_limit_stencil_table_create) from the located samples,
+    # next to Far::LimitStencilTableFactory::Create on one host core (far/stencilTableFactory.cpp:413-662)
+    try:
+        from types import SimpleNamespace
+        ptab = synth.torus_patch_table(mesh)
+        pt = osd.B200PatchTable.Create(ptab)
+        pm = osd.B200PatchMap.Create(ptab)
+        z = np.zeros(0, np.int32)
+        # every control point of the level-0 patches of a regular mesh is a control vertex: no refined rows
+        cv = osd.B200StencilTable.Create(SimpleNamespace(num_control_verts=ncv, sizes=z, offsets=z, indices=z, weights=np.zeros(0, np.float32)))
+        fd = torch.from_numpy(face).cuda()
+        sd, td = torch.from_numpy(s_h).cuda(), torch.from_numpy(t_h).cuda()
+        pc = torch.zeros(n * 5, dtype=torch.int32, device="cuda")
+        assert pm.FindPatches(n, fd, sd, td, pc)
+        torch.cuda.synchronize()
+        build = {}
+        for label, bucketed in (("reference_layout_only", False), ("with_bucketed_layout", True)):
+            osd.B200StencilTable.CreateLimitStencils(pt, cv, n, pc, 6, bucketed=bucketed)      # warm (allocator, first launch)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lim = osd.B200StencilTable.CreateLimitStencils(pt, cv, n, pc, 6, bucketed=bucketed)
+            torch.cuda.synchronize()
+            build[label + "_ms"] = 1e3 * (time.perf_counter() - t0)
+        out = torch.empty((n, 18), device="cuda")
+        a = []
+        for k in range(6):
+            a += [out, D(3 * k, 3, 18)]
+        build["eval_K6_ms"] = time_calls(torch, lambda: osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), *a, lim), iters)
+        build["rows"], build["elements"] = lim.GetNumStencils(), lim.GetNumElements()
+        build["same_elements_as_host_table"] = bool(lim.GetNumElements() == ls.num_elements)
+        from oracle import ref as oref
+        if oref.available():
+            m = oref.Mesh.from_topology("catmark", mesh.num_verts, np.full(len(mesh.faces), 4, np.int32), mesh.faces.reshape(-1))
+            rpt = m.patch_table(3, end_cap="gregory")
+            t0 = time.perf_counter()
+            want = m.limit_stencil_table(face, s_h, t_h, True, True, patch_table=rpt)
+            build["reference_host_build_ms"] = 1e3 * (time.perf_counter() - t0)
+            build["reference_host_build"] = "Far::LimitStencilTableFactory::Create, 1 core, same 1 M locations"
+            sizes, offsets, indices, ws = lim.ToHost(6)
+            build["bit_identical_to_far"] = bool(np.array_equal(indices, want.indices) and all(
+                np.array_equal(ws[k].view(np.int32), w.view(np.int32)) for k, w in enumerate(want.weight_streams(6))))
+        res["device_table_construction"] = build
+    except Exception as exc:
+        res["device_table_construction"] = {"error": f"{type(exc).__name__}: {exc}"}
     return res
 
 

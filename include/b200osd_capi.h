@@ -212,6 +212,20 @@ B200OSD_API int  b200osd_patch_plan_eval(const b200osd_patch_plan *p, int which,
         int nOut, float *const dsts[], const int dstDescs[][3],
         int numPatchCoords, const b200osd_patch_coord *patchCoords, void *stream);
 
+/* ---- limit-stencil construction on the device -------------------------------------------------------
+ * The per-location loop of Far::LimitStencilTableFactory::Create (far/stencilTableFactory.cpp:559-662) with the merge of
+ * Far's StencilBuilder (far/stencilBuilder.cpp): for each located sample (a DEVICE PatchCoord, e.g. from
+ * b200osd_patch_map_find; arrayIndex < 0 produces no row, like FindPatch == NULL) the basis weights of its patch (value;
+ * + 1st; + 2nd derivatives: numWeightSets = 1, 3, 6) are combined with the stencils of the patch's control points.
+ * cvStencils = the refined + local-point stencil table of the same topology WITHOUT control-vertex rows (row r belongs to
+ * vertex numControlVertices + r; the table Osd::Mesh builds, osd/mesh.h:588-659).  The result is the table Far builds --
+ * same rows, same element order; for Catmark patches bit-identical weights -- as a stencil table handle that owns its
+ * device arrays.  flags as for b200osd_stencil_table_create (bit 0: keep only the reference-layout arrays, no read-back).
+ * Synchronous (it allocates the result).  A stencil may reference at most 512 control vertices. */
+B200OSD_API b200osd_stencil_table *b200osd_limit_stencil_table_create(
+        const b200osd_patch_table *patchTable, const b200osd_stencil_table *cvStencils,
+        int numLocations, const b200osd_patch_coord *patchCoords, int numWeightSets, int flags, void *stream);
+
 /* ---- patch map (Far::PatchMap, far/patchMap.h:48-217) ---------------------------
  * Locates samples given as (ptex face, s, t) in the patches of a table and writes Osd::PatchCoord records
  * (osd/types.h:53-54) ready for EvalPatches -- the reference does this one sample at a time on the host

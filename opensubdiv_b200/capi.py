@@ -25,7 +25,7 @@ SYMBOLS = [
     "b200osd_stencil_table_num_levels",
     "b200osd_stencil_table_buffer", "b200osd_stencil_table_stream_bytes", "b200osd_stencil_table_eval",
     "b200osd_stencil_table_eval_batched", "b200osd_stencil_table_set_variant", "b200osd_stencil_table_get_variant",
-    "b200osd_eval_stencils",
+    "b200osd_eval_stencils", "b200osd_limit_stencil_table_create",
     "b200osd_patch_table_create", "b200osd_patch_table_destroy", "b200osd_patch_table_set",
     "b200osd_patch_table_num_fvar_channels", "b200osd_patch_table_buffer", "b200osd_patch_table_count",
     "b200osd_eval_patches", "b200osd_patch_table_eval", "b200osd_patch_table_set_variant", "b200osd_patch_table_get_variant",
@@ -87,6 +87,8 @@ def lib():
     L.b200osd_stencil_table_eval.argtypes = [vp, vp, vp, i, vp, vp, i, i, vp]
     L.b200osd_stencil_table_eval_batched.argtypes = [vp, vp, vp, vp, vp, i, ll, ll, i, i, vp]
     L.b200osd_eval_stencils.argtypes = [vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, vp]
+    L.b200osd_limit_stencil_table_create.restype = vp
+    L.b200osd_limit_stencil_table_create.argtypes = [vp, vp, i, vp, i, i, vp]
     L.b200osd_patch_table_create.restype = vp
     L.b200osd_patch_table_create.argtypes = [i]
     L.b200osd_patch_table_destroy.argtypes = [vp]

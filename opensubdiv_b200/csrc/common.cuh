@@ -38,6 +38,17 @@ inline int check_launch(const char *what) {
 // Number of SMs of the current device (148 on B200); cached.
 int sm_count();
 
+// Wraps reference-layout DEVICE arrays (built on the device, e.g. by the limit-stencil builder) into a stencil table that
+// owns them; unless flags bit 0 is set the arrays are also read back once to build the bucketed layout (stencil.cu).
+// On failure the arrays are freed and NULL is returned.
+struct AdoptedArrays {
+    int numStencils, numControlVertices, numW;
+    long long numElements;
+    int *sizes, *offsets, *indices;
+    float *w[6];
+};
+::b200osd_stencil_table *adopt_device_table(const AdoptedArrays &a, int flags);
+
 // ---- streaming loads/stores -------------------------------------------------------------------
 // Table streams (indices / weights / coords) are read exactly once per launch: bypass L1 allocation
 // so the L1 stays available for the primvar gathers.  Outputs are written once: st.global.cs (evict-first).

@@ -15,6 +15,7 @@
 // scratch from a stream-ordered memory pool (cudaMallocFromPoolAsync / cudaFreeAsync: asynchronous, legal inside a
 // stream capture, reused from the pool after the first call).
 #include "patch_kernels.cuh"
+#include "limit_kernels.cuh"      // same translation unit: the triangle bases read this unit's __constant__ tables
 
 #include <algorithm>
 #include <atomic>
@@ -583,6 +584,102 @@ int b200osd_patch_table_count(const b200osd_patch_table *t, int which, int kind)
     const b200osd_patch_table::Triple &tr = t->triples[which];
     if (kind == 2 && which == 1 && !tr.params) return t->triples[0].nParams;
     return kind == 0 ? tr.nArrays : (kind == 1 ? tr.nIndices : tr.nParams);
+}
+
+// ------------------------------------------------------------------ limit-stencil construction --
+b200osd_stencil_table *b200osd_limit_stencil_table_create(const b200osd_patch_table *pt, const b200osd_stencil_table *cvStencils,
+                                                          int numLocations, const b200osd_patch_coord *patchCoords,
+                                                          int numWeightSets, int flags, void *stream) {
+    if (!pt || pt->triples.empty() || !cvStencils || numLocations < 0 || (numLocations > 0 && !patchCoords) ||
+        (numWeightSets != 1 && numWeightSets != 3 && numWeightSets != 6)) {
+        set_error("limit_stencil_table_create: bad arguments");
+        return nullptr;
+    }
+    const b200osd_patch_table::Triple &tr = pt->triples[0];
+    if (!tr.arrays || !tr.indices || !tr.params) { set_error("limit_stencil_table_create: the patch table has no vertex patches"); return nullptr; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = numLocations;
+    const int tiles = (n + kScanTile - 1) / kScanTile;
+    // scratch: per location {size, resolved, offset, row}, tile sums of both scans, {elements, rows, overflow}
+    int *scratch = nullptr;
+    const size_t words = 4 * (size_t)std::max(n, 1) + 2 * (size_t)std::max(tiles, 1) + 4;
+    if (cudaMalloc((void **)&scratch, words * sizeof(int)) != cudaSuccess) {
+        set_error("limit_stencil_table_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    int *sizeLoc = scratch, *resolved = scratch + n, *offLoc = scratch + 2 * (size_t)n, *rowLoc = scratch + 3 * (size_t)n;
+    int *tileA = scratch + 4 * (size_t)n, *tileB = tileA + std::max(tiles, 1), *totals = tileB + std::max(tiles, 1);
+    cudaMemsetAsync(totals, 0, 4 * sizeof(int), st);
+    LimitIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.n = n;
+    io.coords = patchCoords;
+    io.arrays = tr.arrays;
+    io.patchIndices = tr.indices;
+    io.params = tr.params;
+    io.numControlVertices = b200osd_stencil_table_num_control_vertices(cvStencils);
+    io.cvSizes = static_cast<const int *>(b200osd_stencil_table_buffer(cvStencils, 0));
+    io.cvOffsets = static_cast<const int *>(b200osd_stencil_table_buffer(cvStencils, 1));
+    io.cvIndices = static_cast<const int *>(b200osd_stencil_table_buffer(cvStencils, 2));
+    io.cvWeights = static_cast<const float *>(b200osd_stencil_table_buffer(cvStencils, 3));
+    io.sizeOfLocation = sizeLoc;
+    io.resolved = resolved;
+    io.offsetOfLocation = offLoc;
+    io.rowOfLocation = rowLoc;
+    io.overflow = totals + 2;
+    const int NW = numWeightSets;
+    const int grid = std::max(1, std::min((n + kLimitWarps - 1) / kLimitWarps, sm_count() * 16));
+    auto smem = [&](bool fill) { return (size_t)kLimitWarps * ((size_t)kLimitCap * 4 * (1 + (fill ? NW : 0)) + 20 * 6 * 4); };
+    int hostTotals[4] = { 0, 0, 0, 0 };
+    AdoptedArrays out;
+    std::memset(&out, 0, sizeof(out));
+    bool ok = true;
+    if (n > 0) {
+        if (NW == 1) limit_merge_kernel<1, false><<<grid, 32 * kLimitWarps, smem(false), st>>>(io);
+        else if (NW == 3) limit_merge_kernel<3, false><<<grid, 32 * kLimitWarps, smem(false), st>>>(io);
+        else limit_merge_kernel<6, false><<<grid, 32 * kLimitWarps, smem(false), st>>>(io);
+        ok = check_launch("limit_merge_kernel(count)") == B200OSD_OK;
+        if (ok) {
+            scan_local_kernel<<<tiles, kScanThreads, 0, st>>>(sizeLoc, offLoc, tileA, n);
+            scan_top_kernel<<<1, kScanThreads, 0, st>>>(tileA, tiles, totals + 0);
+            scan_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(offLoc, tileA, n);
+            scan_local_kernel<<<tiles, kScanThreads, 0, st>>>(resolved, rowLoc, tileB, n);
+            scan_top_kernel<<<1, kScanThreads, 0, st>>>(tileB, tiles, totals + 1);
+            scan_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowLoc, tileB, n);
+            ok = check_launch("scan kernels") == B200OSD_OK &&
+                 cudaMemcpyAsync(hostTotals, totals, sizeof(hostTotals), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                 cudaStreamSynchronize(st) == cudaSuccess;
+        }
+    }
+    const long long ne = hostTotals[0];
+    const int rows = hostTotals[1];
+    if (ok && hostTotals[2]) { set_error("limit_stencil_table_create: a limit stencil references more than %d control vertices", kLimitCap); ok = false; }
+    if (ok) {
+        out.numStencils = rows;
+        out.numControlVertices = io.numControlVertices;
+        out.numW = NW;
+        out.numElements = ne;
+        auto alloc = [&](void **p, size_t bytes) { return bytes == 0 || cudaMalloc(p, bytes) == cudaSuccess; };
+        ok = alloc((void **)&out.sizes, (size_t)rows * 4) && alloc((void **)&out.offsets, (size_t)rows * 4) && alloc((void **)&out.indices, (size_t)ne * 4);
+        for (int k = 0; ok && k < NW; ++k) ok = alloc((void **)&out.w[k], (size_t)ne * 4);
+        if (!ok) set_error("limit_stencil_table_create: cudaMalloc of the table failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (ok && n > 0 && rows > 0) {
+        io.sizes = out.sizes; io.offsets = out.offsets; io.indices = out.indices;
+        for (int k = 0; k < NW; ++k) io.w[k] = out.w[k];
+        if (NW == 1) limit_merge_kernel<1, true><<<grid, 32 * kLimitWarps, smem(true), st>>>(io);
+        else if (NW == 3) limit_merge_kernel<3, true><<<grid, 32 * kLimitWarps, smem(true), st>>>(io);
+        else limit_merge_kernel<6, true><<<grid, 32 * kLimitWarps, smem(true), st>>>(io);
+        ok = check_launch("limit_merge_kernel(fill)") == B200OSD_OK && cudaStreamSynchronize(st) == cudaSuccess;
+        if (!ok) set_error("limit_stencil_table_create: fill failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(scratch);
+    if (!ok) {
+        cudaFree(out.sizes); cudaFree(out.offsets); cudaFree(out.indices);
+        for (int k = 0; k < 6; ++k) cudaFree(out.w[k]);
+        return nullptr;
+    }
+    return adopt_device_table(out, flags);
 }
 
 void b200osd_patch_table_set_variant(b200osd_patch_table *t, int variant) { if (t) t->variant = variant; }

@@ -580,6 +580,47 @@ int eval_levels(b200osd_stencil_table *t, StencilIO io, int nOut, cudaStream_t s
 
 }  // namespace
 
+namespace b200osd {
+
+b200osd_stencil_table *adopt_device_table(const AdoptedArrays &a, int flags) {
+    b200osd_stencil_table *t = new (std::nothrow) b200osd_stencil_table;
+    auto fail = [&]() -> b200osd_stencil_table * {
+        if (t) {
+            b200osd_stencil_table_destroy(t);                     // frees what it adopted
+        } else {
+            cudaFree(a.sizes); cudaFree(a.offsets); cudaFree(a.indices);
+            for (int k = 0; k < kMaxOut; ++k) cudaFree(a.w[k]);
+        }
+        return nullptr;
+    };
+    if (!t) return fail();
+    t->n = a.numStencils;
+    t->ne = a.numElements;
+    t->nCV = a.numControlVertices;
+    t->numW = a.numW;
+    t->d_sizes = a.sizes; t->d_offsets = a.offsets; t->d_indices = a.indices;
+    for (int k = 0; k < kMaxOut; ++k) t->d_w[k] = a.w[k];
+    if ((flags & 1) || a.numStencils == 0) return t;
+    // the bucketed layout is built on the host: one read-back of the finished table
+    std::vector<int> sizes((size_t)a.numStencils), offsets((size_t)a.numStencils), indices((size_t)a.numElements);
+    std::vector<std::vector<float>> w((size_t)a.numW, std::vector<float>((size_t)a.numElements));
+    bool ok = cudaMemcpy(sizes.data(), a.sizes, sizes.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(offsets.data(), a.offsets, offsets.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(indices.data(), a.indices, indices.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    const float *wp[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    for (int k = 0; ok && k < a.numW; ++k) {
+        ok = cudaMemcpy(w[(size_t)k].data(), a.w[k], (size_t)a.numElements * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        wp[k] = w[(size_t)k].data();
+    }
+    if (!ok) { set_error("adopt_device_table: read-back failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(); }
+    if (build_sell(t, sizes.data(), offsets.data(), indices.data(), wp, (flags & 2) != 0, !(flags & 4),
+                   (flags & 8) ? 2 : ((flags & 16) ? 0 : 1)) != B200OSD_OK)
+        return fail();
+    return t;
+}
+
+}  // namespace b200osd
+
 extern "C" {
 
 b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, int numControlVertices, const int *sizes, const int *offsets,

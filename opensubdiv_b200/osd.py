@@ -82,8 +82,8 @@ def _dev_ptr(buf) -> Optional[int]:
 
 
 class _CudaArrayView:
-    def __init__(self, ptr: int, n: int, owner):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr: int, n: int, owner, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
         self._owner = owner
 
 
@@ -170,6 +170,18 @@ class B200StencilTable:
                                                     | (8 if sort_elements else 0) | (16 if keep_order else 0))
         return cls(h) if h else None
 
+    @classmethod
+    def CreateLimitStencils(cls, patchTable, cvStencilTable, numLocations: int, patchCoords, numWeightSets: int = 6,
+                            bucketed: bool = True, deviceContext=None) -> Optional["B200StencilTable"]:
+        """Far::LimitStencilTableFactory::Create on the DEVICE (far/stencilTableFactory.cpp:559-662): patchCoords are located
+        samples (device PatchCoord records, e.g. from B200PatchMap.FindPatches), cvStencilTable the refined + local-point
+        stencil table of the topology; numWeightSets 1 / 3 / 6 = value / + 1st / + 2nd derivative weights."""
+        h = capi.lib().b200osd_limit_stencil_table_create(patchTable._h, cvStencilTable._h, int(numLocations), _dev_ptr(patchCoords),
+                                                          int(numWeightSets), 0 if bucketed else 1, _stream_ptr(deviceContext))
+        if not h:
+            raise capi.B200OsdError("B200StencilTable::CreateLimitStencils: " + capi.last_error())
+        return cls(h)
+
     def __del__(self):
         try:
             if self._h:
@@ -202,6 +214,18 @@ class B200StencilTable:
 
     def GetStreamBytes(self, nOut: int = 1) -> int:
         return capi.lib().b200osd_stencil_table_stream_bytes(self._h, nOut)
+
+    def ToHost(self, numWeightSets: int = 1):
+        """(sizes, offsets, indices, [weights, du, ...]) of the reference-layout device arrays as numpy arrays."""
+        import torch
+        n, ne = self.GetNumStencils(), self.GetNumElements()
+
+        def get(ptr, count, typestr):
+            if not ptr or count == 0:
+                return np.zeros(0, np.int32 if typestr == "<i4" else np.float32)
+            return torch.as_tensor(_CudaArrayView(ptr, count, self, typestr), device="cuda").cpu().numpy().copy()
+        return (get(self._buf(0), n, "<i4"), get(self._buf(1), n, "<i4"), get(self._buf(2), ne, "<i4"),
+                [get(self._buf(3 + k), ne, "<f4") for k in range(numWeightSets)])
 
     def GetNumLevels(self) -> int:
         """1, or the number of dependency levels of an unfactorized table (evaluated one after the other)."""
