@@ -100,11 +100,12 @@ B200OSD_API int    b200osd_vertex_buffer_read(b200osd_vertex_buffer *vb, float *
  * (b) a B200-specific bucketed copy (rows sorted by size inside windows, 32-row slices stored
  * element-major for coalesced 128-bit loads) used by b200osd_stencil_table_eval.
  * numControlVertices: Far::StencilTable::GetNumControlVertices() (far/stencilTable.h:161), or <= 0 for "1 + largest
- * index".  Given the real count, a table built with factorizeIntermediateLevels = false (far/stencilTableFactory.h:66-75:
- * rows of later levels reference EARLIER ROWS through indices >= numControlVertices, far tutorial 4_3) is recognised and
- * evaluated one dependency level after the other on the stream -- with src and dst aliased as in Osd::Mesh::Refine
- * (osd/mesh.h:505-519: row r is vertex numControlVertices + r of the same buffer) that reproduces the sequential CPU
- * evaluator; a table whose rows are not in dependency order is rejected (NULL, B200OSD_ERR_UNSUPPORTED in the message).
+ * index".  Given the real count, a table built with factorizeIntermediateLevels = false (far/stencilTableFactory.h:66-75,
+ * far tutorial 4_3) is recognised by indices that reach past the control vertices: its level-l rows index the vertices of
+ * level l-1, so a caller applies it one level at a time -- src = the previous level's block, [start,end) = the level's
+ * rows -- which the absolute row range supports as is.  An evaluation of such a table whose source extent overlaps the
+ * rows it writes (e.g. all levels in one call on the Osd::Mesh::Refine layout) is order dependent even in the sequential
+ * CPU evaluator; it is refused with B200OSD_ERR_UNSUPPORTED instead of racing.
  * flags: bit 0 = skip the bucketed copy (verbatim only); bit 1 = also order rows by locality inside a window;
  * bit 2 = keep 32-bit indices even when a slice fits 16-bit offsets.
  * Summation order: by default the elements of rows of <= 16 terms (every row of a refined regular mesh) are summed in
@@ -120,7 +121,7 @@ B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
 B200OSD_API void b200osd_stencil_table_destroy(b200osd_stencil_table *t);
 B200OSD_API int  b200osd_stencil_table_num_stencils(const b200osd_stencil_table *t);
 B200OSD_API int  b200osd_stencil_table_num_control_vertices(const b200osd_stencil_table *t);
-B200OSD_API int  b200osd_stencil_table_num_levels(const b200osd_stencil_table *t);   /* 1 unless the table is unfactorized */
+B200OSD_API int  b200osd_stencil_table_is_factorized(const b200osd_stencil_table *t);  /* 0: indices reach past the control vertices */
 B200OSD_API long long b200osd_stencil_table_num_elements(const b200osd_stencil_table *t);
 /* which: 0 sizes, 1 offsets, 2 indices, 3 weights, 4 du, 5 dv, 6 duu, 7 duv, 8 dvv -> device pointer or NULL */
 B200OSD_API const void *b200osd_stencil_table_buffer(const b200osd_stencil_table *t, int which);

@@ -22,7 +22,7 @@ SYMBOLS = [
     "b200osd_vertex_buffer_read",
     "b200osd_stencil_table_create", "b200osd_stencil_table_destroy", "b200osd_stencil_table_num_stencils",
     "b200osd_stencil_table_num_control_vertices", "b200osd_stencil_table_num_elements",
-    "b200osd_stencil_table_num_levels",
+    "b200osd_stencil_table_is_factorized",
     "b200osd_stencil_table_buffer", "b200osd_stencil_table_stream_bytes", "b200osd_stencil_table_eval",
     "b200osd_stencil_table_eval_batched", "b200osd_stencil_table_set_variant", "b200osd_stencil_table_get_variant",
     "b200osd_eval_stencils", "b200osd_limit_stencil_table_create",
@@ -114,7 +114,7 @@ def lib():
     L.b200osd_patch_map_find.argtypes = [vp, i, vp, i, vp, i, vp, i, vp, vp, vp]
     L.b200osd_stencil_table_set_variant.argtypes = [vp, i]
     L.b200osd_stencil_table_get_variant.argtypes = [vp]
-    L.b200osd_stencil_table_num_levels.argtypes = [vp]
+    L.b200osd_stencil_table_is_factorized.argtypes = [vp]
     L.b200osd_frame_create.restype = vp
     L.b200osd_frame_destroy.argtypes = [vp]
     L.b200osd_frame_stream.restype = vp

@@ -196,6 +196,19 @@ int launch_run(const PatchIO &io, int LT, cudaStream_t st) {
 }
 
 template <int ORDER, bool TRI>
+int launch_direct(const PatchIO &io, int LT, cudaStream_t st) {
+    const int grid = patch_grid(io.n);
+    const size_t smem = (size_t)(kPatchBlock / 32) * (size_t)io.warpWords * sizeof(float);
+    switch (LT) {
+        case 1: patch_direct_kernel<1, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io); break;
+        case 2: patch_direct_kernel<2, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io); break;
+        case 3: patch_direct_kernel<3, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io); break;
+        default: patch_direct_kernel<4, ORDER, TRI><<<grid, kPatchBlock, smem, st>>>(io); break;
+    }
+    return check_launch("patch_direct_kernel");
+}
+
+template <int ORDER, bool TRI>
 int launch_hull(const PatchIO &io, int LT, const float *hull, cudaStream_t st) {
     const int grid = patch_grid(io.n);
     const size_t smem = (size_t)(kPatchBlock / 32) * (size_t)io.warpWords * sizeof(float);
@@ -273,16 +286,29 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
             if (a % 8 == 0 && R % 2 == 0) io.vecStore |= 2;
         }
         if (LT == 4 && reinterpret_cast<uintptr_t>(io.src) % 16 == 0 && io.srcStride % 4 == 0) io.vecStore |= 4;
-        // shared memory per warp: coordinates in (160 words), staged hulls, results out (32 records + 32 indices)
-        io.hullPitch = hull_pitch(LT, shape.maxPoints);
-        io.warpWords = (std::max(std::max(160, 32 * R + 32), kHullSlots * io.hullPitch) + 3) & ~3;
+        // shared memory per warp: [ staged hulls, later the results (32 records + 32 indices) | 160 words of prefetched coordinates ]
+        const int outWords = 32 * R + 32;
         int rc = B200OSD_OK;
         if (route.hull) {
+            io.hullPitch = 0;
+            io.coordWords = (outWords + 3) & ~3;
+            io.warpWords = io.coordWords + 160;
             rc = launch_hull_build(io, LT, route.hullRows, route.hull, st);
             if (!rc) rc = B200_PATCH_DISPATCH(launch_hull, io, LT, route.hull, st);
             if (rc) return rc;
             if (!route.state) continue;                          // forced: the hull kernels did the tile
         }
+        if (shape.maxPoints <= 4) {                              // linear patches: per-lane reads, nothing to stage
+            io.hullPitch = 0;
+            io.coordWords = (outWords + 3) & ~3;
+            io.warpWords = io.coordWords + 160;
+            rc = B200_PATCH_DISPATCH(launch_direct, io, LT, st);
+            if (rc) return rc;
+            continue;
+        }
+        io.hullPitch = hull_pitch(LT, shape.maxPoints);
+        io.coordWords = (std::max(outWords, kHullSlots * io.hullPitch) + 3) & ~3;
+        io.warpWords = io.coordWords + 160;
         rc = B200_PATCH_DISPATCH(launch_run, io, LT, st);
         if (rc) return rc;
     }
@@ -432,7 +458,7 @@ int b200osd_patch_table_eval(const b200osd_patch_table *t, int which, const floa
             route.state = s.state;
         }
     } else {
-        const size_t hullBytes = align256((size_t)tr->nIndices * LT0 * sizeof(float));
+        const size_t hullBytes = align256((size_t)tr->nIndices * LT0 * sizeof(float) + 64);   // + the last hull's partial 16-byte piece
         if (cudaMallocFromPoolAsync(&block, align256(sizeof(BinState)) + hullBytes, pool, st) != cudaSuccess) { cudaGetLastError(); block = nullptr; }
         if (block) {
             BinState *state = static_cast<BinState *>(block);

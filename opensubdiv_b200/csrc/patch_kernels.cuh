@@ -62,7 +62,8 @@ struct PatchIO {
     const BinState *binState;
     // shared memory: one private region of warpWords floats per warp (coordinates in, staged hulls, results out)
     int warpWords;
-    int hullPitch;                    // floats between staged hulls (see hull_pitch)
+    int coordWords;                   // offset (floats) of the warp's 160-word coordinate prefetch buffer inside its region
+    int hullPitch;                    // floats between staged hulls (see hull_pitch / packed_pitch)
 };
 
 enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_BASIS = 9, PT_GREGORY_TRIANGLE = 10 };
@@ -233,8 +234,9 @@ struct CvStaged {
 // ... or from the per-call hull cache (patch_hull_kernel): the index buffer dereferenced once per call, LT floats per
 // point, a patch's points contiguous and its first point 16-byte aligned whenever its hull is (16- and 20-point hulls of
 // 1-4 floats are).  A row of a 4 x 4 hull is 4*LT contiguous floats: LT 128-bit loads.
+
 struct CvPacked {
-    const float *base;             // first point of the patch
+    const float *base;             // first point of the patch in the hull cache
     bool aligned;                  // base is 16-byte aligned
     template <int LT>
     B200_HD void load(int j, float (&v)[LT]) const {
@@ -715,41 +717,59 @@ struct LaneCoord {
     bool live;
 };
 
-__device__ __forceinline__ LaneCoord load_lane_coord(const PatchIO &io, float *st, long long j0, int lane, bool grouped) {
+// In caller order the 32 records of a tile are 640 contiguous bytes: they are fetched with asynchronous 4-byte copies
+// (cp.async: global -> shared without registers) ONE TILE AHEAD, so that the DRAM latency of the coordinate stream is
+// off the warp's critical path; prefetch_tile_coords is called for the next tile once the current one has been read.
+__device__ __forceinline__ void prefetch_tile_coords(const PatchIO &io, float *coordBuf, int tile, int tiles, int lane) {
+    if (tile < tiles) {
+        const long long j0 = (long long)tile << 5;
+        const int *g = reinterpret_cast<const int *>(io.coords) + (size_t)j0 * 5;
+        const int words = (int)min((long long)32, (long long)io.n - j0) * 5;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(coordBuf);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int e = q * 32 + lane;
+            if (e < words) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * e), "l"(g + e) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ LaneCoord read_tile_coords(const PatchIO &io, const float *coordBuf, long long j0, int lane) {
     LaneCoord c;
     const long long j = j0 + lane;
     c.live = j < io.n;
     c.i = (int)j; c.arrayIndex = -1; c.patchIndex = 0; c.s = 0.0f; c.t = 0.0f;
-    if (grouped) {
-        if (c.live) {
-            c.i = ld_stream_i1(io.perm + j);
-            const int *cw = reinterpret_cast<const int *>(io.coords + c.i);    // a 20-byte record: 1-2 sectors, kept in L1
-            c.arrayIndex = __ldg(cw + 0);
-            c.patchIndex = __ldg(cw + 1);
-            c.s = __int_as_float(__ldg(cw + 3));
-            c.t = __int_as_float(__ldg(cw + 4));
-        }
-    } else {
-        int *cw = reinterpret_cast<int *>(st);
-        const int *g = reinterpret_cast<const int *>(io.coords) + (size_t)j0 * 5;
-        const int words = (int)min((long long)32, (long long)io.n - j0) * 5;
-        __syncwarp();                                           // the region may still be read as staged results
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            const int e = q * 32 + lane;
-            if (e < words) cw[e] = ld_stream_i1(g + e);
-        }
-        __syncwarp();
-        if (c.live) {
-            c.arrayIndex = cw[lane * 5 + 0];
-            c.patchIndex = cw[lane * 5 + 1];
-            c.s = __int_as_float(cw[lane * 5 + 3]);
-            c.t = __int_as_float(cw[lane * 5 + 4]);
-        }
-        __syncwarp();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (c.live) {
+        const int *cw = reinterpret_cast<const int *>(coordBuf);
+        c.arrayIndex = cw[lane * 5 + 0];
+        c.patchIndex = cw[lane * 5 + 1];
+        c.s = __int_as_float(cw[lane * 5 + 3]);
+        c.t = __int_as_float(cw[lane * 5 + 4]);
     }
+    __syncwarp();                                               // every lane has its record: the buffer may be refilled
     // arrayIndex < 0 marks a sample that hit no patch (b200osd_patch_map_find writes it for holes, where
     // Far::PatchMap::FindPatch returns NULL and the reference's callers skip the sample): its outputs stay untouched
+    c.live = c.live && c.arrayIndex >= 0;
+    return c;
+}
+
+// grouped order: position j evaluates coordinate perm[j]; a 20-byte record is 1-2 sectors, kept in L1 between the loads
+__device__ __forceinline__ LaneCoord gather_lane_coord(const PatchIO &io, long long j0, int lane) {
+    LaneCoord c;
+    const long long j = j0 + lane;
+    c.live = j < io.n;
+    c.i = (int)j; c.arrayIndex = -1; c.patchIndex = 0; c.s = 0.0f; c.t = 0.0f;
+    if (c.live) {
+        c.i = ld_stream_i1(io.perm + j);
+        const int *cw = reinterpret_cast<const int *>(io.coords + c.i);
+        c.arrayIndex = __ldg(cw + 0);
+        c.patchIndex = __ldg(cw + 1);
+        c.s = __int_as_float(__ldg(cw + 3));
+        c.t = __int_as_float(__ldg(cw + 4));
+    }
     c.live = c.live && c.arrayIndex >= 0;
     return c;
 }
@@ -773,9 +793,19 @@ __global__ void __launch_bounds__(kPatchBlock, 7) patch_run_kernel(PatchIO io) {
     const int pitch = io.hullPitch;
     const int half = lane >> 4, jj = lane & 15;
 
+    float *coordBuf = st + io.coordWords;
     const int tiles = (int)(((long long)io.n + 31) >> 5);
-    for (int tile = blockIdx.x * (kPatchBlock / 32) + warp; tile < tiles; tile += gridDim.x * (kPatchBlock / 32)) {
-        const LaneCoord lc = load_lane_coord(io, st, (long long)tile << 5, lane, grouped);
+    const int tileStep = gridDim.x * (kPatchBlock / 32);
+    int tile = blockIdx.x * (kPatchBlock / 32) + warp;
+    if (!grouped) prefetch_tile_coords(io, coordBuf, tile, tiles, lane);
+    for (; tile < tiles; tile += tileStep) {
+        LaneCoord lc;
+        if (grouped) {
+            lc = gather_lane_coord(io, (long long)tile << 5, lane);
+        } else {
+            lc = read_tile_coords(io, coordBuf, (long long)tile << 5, lane);
+            prefetch_tile_coords(io, coordBuf, tile + tileStep, tiles, lane);
+        }
         const bool live = lc.live;
         PatchSite ps;
         ps.type = 0; ps.boundary = 0; ps.cvOffset = 0; ps.s = 0.0f; ps.t = 0.0f; ps.d1 = 1.0f; ps.sign = 1.0f;
@@ -864,6 +894,47 @@ __global__ void __launch_bounds__(kPatchBlock, 7) patch_run_kernel(PatchIO io) {
     }
 }
 
+// Small hulls (the 3- and 4-point linear patches of varying and linear face-varying data): nothing worth sharing between
+// lanes, every lane reads its 3-4 control points straight through the index buffer.
+template <int LT, int ORDER, bool TRI>
+__global__ void __launch_bounds__(kPatchBlock, 8) patch_direct_kernel(PatchIO io) {
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+    const int mode = io.binState ? io.binState->mode : (io.perm ? kPatchModeGrouped : kPatchModeDirect);
+    if (mode == kPatchModeHull) return;
+    const bool grouped = io.perm != nullptr && mode == kPatchModeGrouped;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *st = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
+    float *coordBuf = st + io.coordWords;
+    const int tiles = (int)(((long long)io.n + 31) >> 5);
+    const int tileStep = gridDim.x * (kPatchBlock / 32);
+    int tile = blockIdx.x * (kPatchBlock / 32) + warp;
+    if (!grouped) prefetch_tile_coords(io, coordBuf, tile, tiles, lane);
+    for (; tile < tiles; tile += tileStep) {
+        LaneCoord lc;
+        if (grouped) {
+            lc = gather_lane_coord(io, (long long)tile << 5, lane);
+        } else {
+            lc = read_tile_coords(io, coordBuf, (long long)tile << 5, lane);
+            prefetch_tile_coords(io, coordBuf, tile + tileStep, tiles, lane);
+        }
+        float out[NSETS][LT];
+#pragma unroll
+        for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+            for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+        if (lc.live) {
+            PatchSite ps;
+            decode_patch_site(io, lc.arrayIndex, lc.patchIndex, lc.s, lc.t, ps);
+            CvIndirect cv;
+            cv.src = io.src;
+            cv.stride = io.srcStride;
+            cv.cvs = io.indices + ps.cvOffset;
+            eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, out);
+        }
+        store_outputs<LT, NSETS>(io, st, lc.i, lc.live, !grouped, out);
+    }
+}
+
 // ---- per-call hull cache: for INCOHERENT coordinates (every lane another patch) ------------------------------------
 // hull_build_kernel dereferences the index buffer once per call: cache row r = the LT floats of control vertex
 // indices[r], so a patch's hull is one contiguous block (192 bytes for 16 xyz points) at its index offset.
@@ -874,24 +945,48 @@ template <int LT>
 __global__ void __launch_bounds__(256) hull_build_kernel(const float *src, int srcStride, const int *indices, long long rows,
                                                          float *hull, const BinState *state) {
     if (state && state->mode != kPatchModeHull) return;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
-        const int cv = ld_stream_i1(indices + r);
-        const float *g = src + (size_t)cv * (size_t)srcStride;
-        float *d = hull + (size_t)r * LT;
+    // four consecutive rows per thread: one 128-bit index load, LT 128-bit stores
+    const long long quads = rows >> 2;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+        const int4 cv = ld_stream_i4(reinterpret_cast<const int4 *>(indices) + q);
+        const int c4[4] = { cv.x, cv.y, cv.z, cv.w };
+        float f[4 * LT];
 #pragma unroll
-        for (int c = 0; c < LT; ++c) d[c] = __ldg(g + c);
+        for (int r = 0; r < 4; ++r) {
+            const float *g = src + (size_t)c4[r] * (size_t)srcStride;
+#pragma unroll
+            for (int c = 0; c < LT; ++c) f[r * LT + c] = __ldg(g + c);
+        }
+        float4 *d = reinterpret_cast<float4 *>(hull + (size_t)q * 4 * LT);
+#pragma unroll
+        for (int k = 0; k < LT; ++k) d[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(rows & 3)) {      // the last 1-3 rows
+        const long long r = (quads << 2) + threadIdx.x;
+        const float *g = src + (size_t)ld_stream_i1(indices + r) * (size_t)srcStride;
+#pragma unroll
+        for (int c = 0; c < LT; ++c) hull[(size_t)r * LT + c] = __ldg(g + c);
     }
 }
 
+// One lane per coordinate, every lane another patch: each lane reads its hull straight from the cache (LT 128-bit loads
+// per row of four points).  Measured alternatives (profiles/r02q_*): copying the warp's 32 hulls cooperatively into
+// shared memory first (two full lines per hull instead of one line touch per lane and piece) relieves the L1 wavefront
+// pipe (84 % -> lower) but serialises a load -> store -> barrier -> evaluate chain per warp and is 25 % SLOWER.
 template <int LT, int ORDER, bool TRI>
 __global__ void __launch_bounds__(kPatchBlock, 6) patch_hull_kernel(PatchIO io, const float *hull) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
     if (io.binState && io.binState->mode != kPatchModeHull) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *st = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
+    float *coordBuf = st + io.coordWords;
     const int tiles = (int)(((long long)io.n + 31) >> 5);
-    for (int tile = blockIdx.x * (kPatchBlock / 32) + warp; tile < tiles; tile += gridDim.x * (kPatchBlock / 32)) {
-        const LaneCoord lc = load_lane_coord(io, st, (long long)tile << 5, lane, false);
+    const int tileStep = gridDim.x * (kPatchBlock / 32);
+    int tile = blockIdx.x * (kPatchBlock / 32) + warp;
+    prefetch_tile_coords(io, coordBuf, tile, tiles, lane);
+    for (; tile < tiles; tile += tileStep) {
+        const LaneCoord lc = read_tile_coords(io, coordBuf, (long long)tile << 5, lane);
+        prefetch_tile_coords(io, coordBuf, tile + tileStep, tiles, lane);
         float out[NSETS][LT];
 #pragma unroll
         for (int k = 0; k < NSETS; ++k)

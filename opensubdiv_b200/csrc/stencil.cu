@@ -22,10 +22,12 @@ struct b200osd_stencil_table {
     int nCV = 0;
     int numW = 1;
     int variant = 0;                     // kernel variant for this table (b200osd_stencil_table_set_variant); 0 = auto
-    // Unfactorized tables (far/stencilTableFactory.h:66-75 factorizeIntermediateLevels = false): rows of level l > 0
-    // reference rows of earlier levels through indices >= nCV.  levelStart holds the first row of every dependency
-    // level (+ sentinel); such a table is evaluated level by level on the stream (empty: one launch).
-    std::vector<int> levelStart;
+    // Unfactorized tables (far/stencilTableFactory.h:66-75 factorizeIntermediateLevels = false; far tutorial 4_3): the rows
+    // of level l index the vertices of level l-1 (level-local numbering: far/stencilTableFactory.cpp:108-133 never advances
+    // the source index), so their indices reach past the control vertices and a caller applies them one level at a time,
+    // src = the previous level's block.  rowMaxIndex (only kept for such tables) = largest index of every row: an
+    // evaluation whose source extent overlaps the rows it writes is order dependent and refused.
+    std::vector<int> rowMaxIndex;
     // verbatim copies (reference layout)
     int *d_sizes = nullptr, *d_offsets = nullptr, *d_indices = nullptr;
     float *d_w[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
@@ -480,39 +482,6 @@ bool launch_batched(const StencilIO &io, const SellTable &t, int mode, long long
 // ------------------------------------------------------------------------------------ C ABI ----
 namespace {
 
-// Dependency levels of an unfactorized table: level(row) = 0 when every index < nCV, else 1 + max level of the rows it
-// references (index - nCV).  Far emits rows level by level, so levels are non-decreasing with the row number; anything
-// else (a forward reference) cannot be evaluated by launches over row ranges and is rejected.
-int find_levels(b200osd_stencil_table *t, const int *sizes, const int *offsets, const int *indices) {
-    std::vector<int> level((size_t)t->n, 0);
-    int maxLevel = 0;
-    for (int i = 0; i < t->n; ++i) {
-        int lv = 0;
-        for (int j = 0; j < sizes[i]; ++j) {
-            const int ix = indices[offsets[i] + j];
-            if (ix < t->nCV) continue;
-            const int r = ix - t->nCV;
-            if (r >= i) {
-                set_error("stencil %d references stencil %d (index %d >= %d control vertices): not in dependency order", i, r, ix, t->nCV);
-                return B200OSD_ERR_UNSUPPORTED;
-            }
-            lv = std::max(lv, level[(size_t)r] + 1);
-        }
-        if (i > 0 && lv < level[(size_t)i - 1]) {
-            set_error("stencil %d has dependency level %d after level %d: rows are not ordered by level", i, lv, level[(size_t)i - 1]);
-            return B200OSD_ERR_UNSUPPORTED;
-        }
-        level[(size_t)i] = lv;
-        maxLevel = std::max(maxLevel, lv);
-    }
-    if (maxLevel == 0) return B200OSD_OK;
-    t->levelStart.assign((size_t)maxLevel + 2, t->n);
-    for (int i = t->n - 1; i >= 0; --i) t->levelStart[(size_t)level[(size_t)i]] = i;
-    for (int l = maxLevel; l >= 0; --l)                               // empty levels cannot occur, but stay monotone
-        t->levelStart[(size_t)l] = std::min(t->levelStart[(size_t)l], t->levelStart[(size_t)l + 1]);
-    return B200OSD_OK;
-}
-
 // one launch over rows [io.start, io.end) of the table
 int eval_rows(b200osd_stencil_table *t, const StencilIO &io, int nOut, cudaStream_t st) {
     if (!t->hasSell || t->variant == 1) {
@@ -562,18 +531,24 @@ int eval_rows(b200osd_stencil_table *t, const StencilIO &io, int nOut, cudaStrea
     return nOut == 1 ? launch_sell<1>(io, s, plan, st) : (nOut == 3 ? launch_sell<3>(io, s, plan, st) : launch_sell<6>(io, s, plan, st));
 }
 
-// rows [start,end) of the table: one launch, or one per dependency level of an unfactorized table (stream order makes
-// level l's rows visible to level l+1, which is what the sequential CPU evaluator gives a caller whose src and dst
-// alias as in Osd::Mesh::Refine, osd/mesh.h:505-519)
-int eval_levels(b200osd_stencil_table *t, StencilIO io, int nOut, cudaStream_t st) {
-    if (t->levelStart.empty()) return eval_rows(t, io, nOut, st);
-    const int start = io.start, end = io.end;
-    for (size_t l = 0; l + 1 < t->levelStart.size(); ++l) {
-        io.start = std::max(start, t->levelStart[l]);
-        io.end = std::min(end, t->levelStart[l + 1]);
-        if (io.end <= io.start) continue;
-        int rc = eval_rows(t, io, nOut, st);
-        if (rc) return rc;
+// An unfactorized table applied to a buffer in which the source vertices it reads overlap the rows it writes has no
+// defined parallel result (the sequential CPU evaluator's would depend on the row order): refuse it.  Applied level by
+// level -- src = the previous level's block, [start,end) = the level's rows, far tutorial 4_3 -- nothing overlaps.
+int check_unfactorized(const b200osd_stencil_table *t, const StencilIO &io, int nOut) {
+    if (t->rowMaxIndex.empty()) return B200OSD_OK;
+    int m = -1;
+    for (int i = io.start; i < io.end; ++i) m = std::max(m, t->rowMaxIndex[(size_t)i]);
+    if (m < 0) return B200OSD_OK;
+    const float *sLo = io.src, *sHi = io.src + (size_t)m * (size_t)io.srcStride + io.L;
+    for (int k = 0; k < nOut; ++k) {
+        if (!io.dst[k]) continue;
+        const float *dLo = io.dst[k] + (size_t)io.start * (size_t)io.dstStride[k];
+        const float *dHi = io.dst[k] + (size_t)(io.end - 1) * (size_t)io.dstStride[k] + io.L;
+        if (sLo < dHi && dLo < sHi) {
+            set_error("unfactorized stencil table: rows [%d,%d) read source vertices up to %d, which overlap the rows they write; "
+                      "apply such a table one level at a time (src = the previous level's vertices)", io.start, io.end, m);
+            return B200OSD_ERR_UNSUPPORTED;
+        }
     }
     return B200OSD_OK;
 }
@@ -649,7 +624,11 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, int numCont
     t->numW = (du && dv) ? ((duu && duv && dvv) ? 6 : 3) : 1;
 
     int rc = B200OSD_OK;
-    if (maxIdx >= t->nCV) rc = find_levels(t, sizes, offsets, indices);      // unfactorized: rows reference earlier rows
+    if (numControlVertices > 0 && maxIdx >= t->nCV) {                        // unfactorized (see rowMaxIndex)
+        t->rowMaxIndex.assign((size_t)numStencils, -1);
+        for (int i = 0; i < numStencils; ++i)
+            for (int j = 0; j < sizes[i]; ++j) t->rowMaxIndex[(size_t)i] = std::max(t->rowMaxIndex[(size_t)i], indices[offsets[i] + j]);
+    }
     if (!rc) rc = upload(&t->d_sizes, sizes, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
@@ -673,9 +652,7 @@ void b200osd_stencil_table_destroy(b200osd_stencil_table *t) {
 int b200osd_stencil_table_num_stencils(const b200osd_stencil_table *t) { return t ? t->n : 0; }
 int b200osd_stencil_table_num_control_vertices(const b200osd_stencil_table *t) { return t ? t->nCV : 0; }
 long long b200osd_stencil_table_num_elements(const b200osd_stencil_table *t) { return t ? t->ne : 0; }
-int b200osd_stencil_table_num_levels(const b200osd_stencil_table *t) {
-    return !t ? 0 : (t->levelStart.empty() ? 1 : (int)t->levelStart.size() - 1);
-}
+int b200osd_stencil_table_is_factorized(const b200osd_stencil_table *t) { return t && t->rowMaxIndex.empty() ? 1 : 0; }
 
 const void *b200osd_stencil_table_buffer(const b200osd_stencil_table *t, int which) {
     if (!t) return nullptr;
@@ -705,7 +682,8 @@ int b200osd_stencil_table_eval(const b200osd_stencil_table *tc, const float *src
     if (rc || noop) return rc;
     if (start < 0 || end > t->n) { set_error("row range [%d,%d) outside table of %d rows", start, end, t->n); return B200OSD_ERR_INVALID; }
     if (nOut > t->numW) { set_error("table has %d weight streams, %d outputs requested", t->numW, nOut); return B200OSD_ERR_INVALID; }
-    return eval_levels(t, io, nOut, (cudaStream_t)stream);
+    if ((rc = check_unfactorized(t, io, nOut))) return rc;
+    return eval_rows(t, io, nOut, (cudaStream_t)stream);
 }
 
 int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *tc, const float *src, const int srcDesc[3],
@@ -722,8 +700,7 @@ int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *tc, const fl
     if (rc || noop) return rc;
     if (start < 0 || end > t->n) { set_error("row range [%d,%d) outside table of %d rows", start, end, t->n); return B200OSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    // unfactorized tables go level by level per instance (every instance's rows feed that instance's next level)
-    const bool batchable = t->hasSell && t->levelStart.empty() && (io.L == 3 || io.L == 4 || io.L == 6);
+    const bool batchable = t->hasSell && (io.L == 3 || io.L == 4 || io.L == 6);
     // alignment of every instance must allow the gather / store widths chosen for instance 0
     int mode = src_mode(io);
     if (mode == SRC_VEC4 && srcInstanceStride % 4 != 0) mode = (srcInstanceStride % 2 == 0) ? SRC_VEC2 : SRC_SCALAR;
@@ -758,7 +735,8 @@ int b200osd_stencil_table_eval_batched(const b200osd_stencil_table *tc, const fl
         } else {
             // single instance (or no batched kernel for this length): the ordinary path on the shifted base pointers
             // (the gather width is re-derived from the shifted source pointer, the store width was reduced above)
-            rc = eval_levels(t, cur, 1, st);
+            rc = check_unfactorized(t, cur, 1);
+            if (!rc) rc = eval_rows(t, cur, 1, st);
             b += 1;
         }
         if (rc) return rc;

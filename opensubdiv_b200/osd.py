@@ -227,9 +227,9 @@ class B200StencilTable:
         return (get(self._buf(0), n, "<i4"), get(self._buf(1), n, "<i4"), get(self._buf(2), ne, "<i4"),
                 [get(self._buf(3 + k), ne, "<f4") for k in range(numWeightSets)])
 
-    def GetNumLevels(self) -> int:
-        """1, or the number of dependency levels of an unfactorized table (evaluated one after the other)."""
-        return capi.lib().b200osd_stencil_table_num_levels(self._h)
+    def IsFactorized(self) -> bool:
+        """False for a table built with factorizeIntermediateLevels = false (apply it one level at a time)."""
+        return bool(capi.lib().b200osd_stencil_table_is_factorized(self._h))
 
     def SetVariant(self, variant: int) -> None:
         """Kernel variant for this table (bench / tests): 0 auto, see include/b200osd_capi.h."""

@@ -70,7 +70,7 @@ int emu_eval_patches(const float *src, const int srcDesc[3], int nOut, float *co
         for (int k = 0; k < kPatchMaxOut; ++k) { io.dst[k] = nullptr; io.dstStride[k] = 0; }
         for (int k = 0; k < nOut; ++k)
             if (dsts[k]) { io.dst[k] = dsts[k] + dstDescs[k][0] + c0; io.dstStride[k] = dstDescs[k][2]; }
-        io.packed = 0; io.vecStore = 0; io.perm = nullptr; io.binState = nullptr; io.warpWords = 0; io.hullPitch = 0;
+        io.packed = 0; io.vecStore = 0; io.perm = nullptr; io.binState = nullptr; io.warpWords = 0; io.coordWords = 0; io.hullPitch = 0;
         io.n = n; io.coords = coords; io.arrays = arrays; io.indices = indices; io.params = params;
         if (nOut == 1) run<0>(io, LT); else if (nOut == 3) run<1>(io, LT); else run<2>(io, LT);
     }

@@ -372,3 +372,70 @@ def test_config2_size_independent_properties(config2):
     A = torch.sparse_csr_tensor(crow, torch.from_numpy(table.indices.astype(np.int64)).cuda(),
                                 torch.from_numpy(table.weights).cuda(), size=(n, ncv))
     assert (A @ x - ex).abs().max().item() <= 5e-6
+
+
+def test_unfactorized_table_applied_level_by_level():
+    """factorizeIntermediateLevels = false (far/stencilTableFactory.h:66-75, far tutorial 4_3): the rows of level l index
+    the vertices of level l-1, so the table is applied one level at a time with the absolute row range -- src = the
+    previous level's block of the buffer -- and gives the factorized table's result.  All levels in ONE call on the
+    Osd::Mesh::Refine layout would read rows it is writing: refused (B200OSD_ERR_UNSUPPORTED), not raced."""
+    from oracle import ref
+    from opensubdiv_b200 import capi
+    if not ref.available():
+        pytest.skip("oracle/_ref/libosdref.so not present")
+    for shape, level in (("catmark_cube_creases0", 4), ("catmark_car", 3), ("loop_icosahedron", 3)):
+        m = ref.Mesh.from_shape(shape).refine_uniform(level)
+        fact = m.stencil_table(intermediate_levels=True, factorize=True)
+        unf = m.stencil_table(intermediate_levels=True, factorize=False)
+        ncv, n = unf.num_control_verts, unf.num_stencils
+        assert unf.indices.max() >= ncv and fact.indices.max() < ncv
+        tbl = osd.B200StencilTable.Create(unf)
+        assert not tbl.IsFactorized() and osd.B200StencilTable.Create(fact).IsFactorized()
+        want = oracle_stencils(m.positions, (0, 3, 3), n, 3, fact, 1)[0]
+        scale = oracle_stencils(m.positions, (0, 3, 3), n, 3, fact, 1, abs_scale=True)[0]
+        for v in (0, 1, 8):
+            tbl.SetVariant(v)
+            vb = osd.B200VertexBuffer.Create(3, ncv + n)
+            vb.UpdateData(np.ascontiguousarray(m.positions, np.float32), 0, ncv)
+            src_vertex, row = 0, 0                               # level l-1 starts at vertex src_vertex; level l's first row
+            for lv in range(1, level + 1):
+                nv = m.level_num_verts(lv)
+                # row i of the table is written to element i of dst (absolute addressing): dst = the refined region
+                assert osd.B200Evaluator.EvalStencils(vb, D(src_vertex * 3, 3, 3), vb, D(ncv * 3, 3, 3), tbl, start=row, end=row + nv)
+                src_vertex = ncv + row
+                row += nv
+            assert row == n
+            osd.B200Evaluator.Synchronize()
+            got = vb.as_tensor()[ncv:].cpu().numpy()
+            # level-by-level interpolation accumulates rounding over `level` steps
+            assert_close(got, want, scale, f"{shape} unfactorized, level by level, variant {v}", tol=1e-6 * level)
+        tbl.SetVariant(0)
+        vb = osd.B200VertexBuffer.Create(3, ncv + n)
+        with pytest.raises(capi.B200OsdError, match="one level at a time"):
+            osd.B200Evaluator.EvalStencils(vb, D(0, 3, 3), vb, D(ncv * 3, 3, 3), tbl)
+
+
+def test_non_finite_control_vertex_reaches_only_the_rows_that_reference_it():
+    """padded slots of the bucketed layout carry weight 0 -- they must not pull a NaN / Inf of some other vertex
+    into a row (0 * NaN = NaN).  The reference only propagates a non-finite value to rows that reference the vertex."""
+    d = golden("stencils_catmark_car")
+    t = table_from(d, "t_")
+    n = t.num_stencils
+    src = np.ascontiguousarray(d["src"], np.float32).copy()
+    bad = int(t.indices[t.offsets[n // 3]])                     # a vertex some rows reference
+    for poison in (np.nan, np.inf):
+        src[bad] = poison
+        rowid = np.repeat(np.arange(n), t.sizes)
+        touched = np.zeros(n, bool)
+        touched[rowid[t.indices == bad]] = True
+        assert touched.any() and not touched.all()
+        for idx16 in (True, False):
+            for kw in (dict(), dict(keep_order=True)):
+                tbl = osd.B200StencilTable.Create(t, idx16=idx16, **kw)
+                for v in (0, 1, 8, 122):
+                    out = torch.zeros((n, 3), device="cuda")
+                    tbl.SetVariant(v)
+                    assert osd.B200Evaluator.EvalStencils(dev(src), D(0, 3, 3), out, D(0, 3, 3), tbl)
+                    got = out.cpu().numpy()
+                    assert np.isfinite(got[~touched]).all(), f"poison {poison} leaked (idx16={idx16}, {kw}, variant {v})"
+                    assert (~np.isfinite(got[touched])).all(axis=1).all()

@@ -48,3 +48,15 @@ def assert_close(got, ref, scale, what="", tol=REL_TOL):
     worst = float(err.max()) if err.size else 0.0
     assert worst <= tol, f"{what}: max relative error {worst:.3e} > {tol:.1e} at {np.unravel_index(err.argmax(), err.shape)}"
     return worst
+
+
+def assert_close_bbox(got, ref, bbox, depth, order, what="", tol=REL_TOL):
+    """Second, scale-free gate for patch evaluation: |got - ref| <= tol * bbox * 2^(order * depth), with
+    bbox the extent of the control points and depth the patch's subdivision depth -- a derivative of order k of a
+    depth-d sub-patch is naturally 2^(k d) times larger than the geometry.  Returns the worst ratio error / (bbox 2^(k d))."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = float(bbox) * np.power(2.0, order * np.asarray(depth, np.float64))[:, None]
+    err = np.abs(got - ref) / scale
+    worst = float(err.max()) if err.size else 0.0
+    assert worst <= tol, f"{what}: error {worst:.3e} of bbox*2^(order*depth) > {tol:.1e} at {np.unravel_index(err.argmax(), err.shape)}"
+    return worst

@@ -32,11 +32,15 @@ args = []
 for k in range(6):
     args += [out, D(3 * k, 3, 18)]
 assert osd.B200Evaluator.EvalStencils(vb, D(0, 3, 3), vb, D(ncv * 3, 3, 3), stbl)
-pt.SetVariant(2)
-assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)       # random, grouped
-pt.SetVariant(1)
-assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)       # random, caller order
+mode = os.environ.get("MODE", "auto")
+if mode == "all":
+    pt.SetVariant(2)
+    assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)   # random, grouped per call
+    pt.SetVariant(1)
+    assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)   # random, caller order
+pt.SetVariant(0)
+assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)       # random, automatic (probe -> hull cache)
 rec = pc.view(n, 5)
 pcs = rec[torch.argsort(rec[:, 1].to(torch.int64))].contiguous().view(-1)
-assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pcs, pt, None)      # sorted, caller order
+assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pcs, pt, None)      # sorted, automatic (probe -> caller order)
 torch.cuda.synchronize()
