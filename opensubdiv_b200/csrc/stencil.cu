@@ -421,19 +421,14 @@ int launch_tma_final(const StencilIO &io, const SellTable &t, int stages, int sl
 
 template <int LL, int K, int SRCMODE>
 int launch_tma_shape(const StencilIO &io, const SellTable &t, int shape, int slices, cudaStream_t st) {
-    const int M = shape / 1000, C = (shape % 100) / 10, stages = shape % 10;
-    // exploration (bench sweeps): explicit resident-block hints for the headline shape
-    if (K == 1 && LL == 6 && M > 0) {
-#define B200_TMA_CASE(CC, MM) if (C == CC && M == MM) return launch_tma_final<LL, K, SRCMODE, CC, (K == 1 && LL == 6 ? MM : 1)>(io, t, stages, slices, st);
-        B200_TMA_CASE(2, 3) B200_TMA_CASE(2, 5) B200_TMA_CASE(2, 6) B200_TMA_CASE(2, 8)
-        B200_TMA_CASE(4, 3) B200_TMA_CASE(4, 4) B200_TMA_CASE(1, 8)
-#undef B200_TMA_CASE
-        return B200OSD_ERR_UNSUPPORTED;
-    }
-    // small chunks go with many resident warps (registers capped for 6 blocks of 8 warps), large chunks with few
+    const int C = (shape % 100) / 10, stages = shape % 10;
+    // small chunks go with many resident warps (registers capped for 6 blocks of 8 warps), large chunks with few; which
+    // (chunk, stages, occupancy) combinations were measured: profiles/r02e_sweep_tma.jsonl, r02f_sweep_tma_occupancy.jsonl
     if (C == 1) return launch_tma_final<LL, K, SRCMODE, 1, (K == 1 ? 6 : 3)>(io, t, stages, slices, st);
     if (C == 2) return launch_tma_final<LL, K, SRCMODE, 2, (K == 1 ? 4 : 2)>(io, t, stages, slices, st);
-    if (C == 4 && K == 1) return launch_tma_final<LL, K, SRCMODE, 4, 2>(io, t, stages, slices, st);
+    if constexpr (K == 1) {
+        if (C == 4) return launch_tma_final<LL, K, SRCMODE, 4, 2>(io, t, stages, slices, st);
+    }
     return B200OSD_ERR_UNSUPPORTED;
 }
 
@@ -507,7 +502,7 @@ int eval_rows(b200osd_stencil_table *t, const StencilIO &io, int nOut, cudaStrea
     plan.mode = src_mode(io);
     const int L = io.L;
     const int v = t->variant;
-    if (v >= 100 && v < 9000) {
+    if (v >= 100 && v < 150) {
         const int rc = nOut == 1 ? launch_tma<1>(io, s, plan.mode, v - 100, st)
                                  : (nOut == 3 ? launch_tma<3>(io, s, plan.mode, v - 100, st) : launch_tma<6>(io, s, plan.mode, v - 100, st));
         if (rc != B200OSD_ERR_UNSUPPORTED) return rc;            // lengths / shapes without a TMA instantiation: the default kernels

@@ -210,6 +210,24 @@ static int meshCase(const char *name, std::string const &str, Scheme scheme, int
             std::snprintf(label, sizeof(label), "EvalPatches %s %s (%d coords)", name, names[k], n);
             report(label, maxCondDiff(&x[0], &y[0], n, k, coords, cpu.GetPatchTable(), cpu.GetVertexBuffer()->BindCpuBuffer()), 1e-6);
         }
+        // the instantiatable flavour (osd/mesh.h:305-409): an instance from EvaluatorCacheT, the coordinate set bound once
+        // (grouped by patch on the device), the same static call with the instance -- bit-identical to the call without
+        {
+            Osd::EvaluatorCacheT<Osd::B200Evaluator> cache;
+            Osd::B200Evaluator *ev = Osd::GetEvaluator<Osd::B200Evaluator>(&cache, src, p, du, dv, duu, duv, dvv, (void *)NULL);
+            Osd::B200VertexBuffer *gpuOut2 = Osd::B200VertexBuffer::Create(18, n);
+            bool bound = ev && ev->BindPatchCoords(n, gpuCoords, gpu->GetPatchTable());
+            bool c = bound && Osd::B200Evaluator::EvalPatches(gpu->GetVertexBuffer(), src, gpuOut2, p, gpuOut2, du, gpuOut2, dv,
+                                                              gpuOut2, duu, gpuOut2, duv, gpuOut2, dvv, n, gpuCoords,
+                                                              gpu->GetPatchTable(), ev);
+            std::vector<float> out2((size_t)n * 18);
+            gpuOut2->ReadData(&out2[0], 0, n);
+            Osd::B200Evaluator::Synchronize();
+            bool same = c && std::memcmp(&out[0], &out2[0], out.size() * sizeof(float)) == 0;
+            std::printf("%-58s %s\n", "EvalPatches through an EvaluatorCacheT instance", same ? "bit-identical  ok" : "MISMATCH");
+            if (!same) g_fail = 1;
+            delete gpuOut2;
+        }
         // varying through the same coords (linear patches)
         bool c1 = Osd::CpuEvaluator::EvalPatchesVarying(cpu.GetVertexBuffer(), src, cpuOut, p, n, cpuCoords, cpu.GetPatchTable(),
                                                         (Osd::CpuEvaluator const *)NULL);
