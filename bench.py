@@ -25,6 +25,7 @@ One step = one frame = one EvalStencils pass over the whole table.
                 Gregory-basis end caps, face-varying UVs; 10 M samples located on the device (FindPatches) and evaluated
                 with 1st + 2nd derivatives (random and patch-sorted order), EvalPatchesFaceVarying, the whole frame as
                 one graph launch, its own roofline block, and the reference's CPU evaluators on a sample
+  eval_patches_loop  (N = 1) the Loop counterpart: 3000 tiled loop_icosahedron, box-spline + Gregory-triangle patches
   incumbent_cuda  (N = 1) the reference's own CUDA kernels (osd/cudaKernel.cu compiled for sm_100a under oracle/_ref)
 
 Multi-GPU (N > 1), headline: weak scaling.  The scene is N such meshes; rank r owns the stencil rows of mesh r; every
@@ -497,6 +498,71 @@ def bench_eval_patches(torch, osd, capi, n=10_000_000, iters=10):
     return res
 
 
+def bench_eval_patches_loop(torch, osd, n=10_000_000, iters=10):
+    """The Loop counterpart of config 4 (no throughput number existed for the triangle bases): 3000 tiled copies
+    of regression shape loop_icosahedron, adaptive level 3, Gregory-triangle end caps = 1.14 M LOOP (12-point box spline) +
+    180 k GREGORY_TRIANGLE (18-point) patches; 10 M samples located on the device (triangular ptex domains), P + 1st + 2nd
+    derivatives of xyz interleaved (92 algorithmic bytes per coordinate)."""
+    from oracle import ref as oref
+    if not oref.available():
+        return {"skipped": "oracle/_ref/libosdref.so not present"}
+    D = osd.BufferDescriptor
+    m = oref.Mesh.from_shape_tiled("loop_icosahedron", 3000)
+    ptab = m.patch_table(3, end_cap="gregory")
+    st = m.stencil_table(intermediate_levels=True, patch_table=ptab)
+    ncv, nst = st.num_control_verts, st.num_stencils
+    vb = osd.B200VertexBuffer.Create(3, ncv + nst)
+    vb.UpdateData(np.ascontiguousarray(m.positions), 0, ncv)
+    stbl = osd.B200StencilTable.Create(st)
+    pt = osd.B200PatchTable.Create(ptab)
+    pm = osd.B200PatchMap.Create(ptab)
+    rng = np.random.default_rng(77)
+    face_h = rng.integers(0, m.num_ptex_faces, n).astype(np.int32)
+    s_h, t_h = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+    flip = s_h + t_h > 1.0                                   # triangular domain (glStencilViewer.cpp:364-371)
+    s_h, t_h = np.where(flip, 1.0 - s_h, s_h).astype(np.float32), np.where(flip, 1.0 - t_h, t_h).astype(np.float32)
+    face, s, t = (torch.from_numpy(x).cuda() for x in (face_h, s_h, t_h))
+    pc = torch.zeros(n * 5, dtype=torch.int32, device="cuda")
+    found = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = torch.empty((n, 18), device="cuda")
+    args = []
+    for k in range(6):
+        args += [out, D(3 * k, 3, 18)]
+    assert osd.B200Evaluator.EvalStencils(vb, D(0, 3, 3), vb, D(ncv * 3, 3, 3), stbl)
+    assert pm.FindPatches(n, face, s, t, pc, found)
+    peak, _ = measured_peak()
+    res = {"workload": "loop_icosahedron_x3000_adaptive_L3_gregory_triangle_10M_samples_xyz_P+D1+D2", "coords": n,
+           "patches": int(len(ptab.vertex.params)), "loop_patches": int(ptab.vertex.arrays["numPatches"][0]),
+           "gregory_triangle_patches": int(ptab.vertex.arrays["numPatches"][1]) if len(ptab.vertex.arrays) > 1 else 0,
+           "found": int(found.item()),
+           "find_patches_ms": time_calls(torch, lambda: pm.FindPatches(n, face, s, t, pc, found), iters)}
+
+    def entry(ms):
+        return {"ms": ms, "pts_per_s": n / (ms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": n * 92 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": n * 92 / (ms * 1e-3) / 1e9 / peak}}
+    res["random"] = entry(time_calls(torch, lambda: osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None), iters))
+    rec = pc.view(n, 5)
+    pcs = rec[torch.argsort(rec[:, 1].to(torch.int64))].contiguous().view(-1)
+    res["sorted_by_patch"] = entry(time_calls(torch, lambda: osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pcs, pt, None), iters))
+    try:
+        k = 200_000
+        sel = np.ascontiguousarray(m.find_patches(ptab, face_h[:k], s_h[:k], t_h[:k]))
+        res["find_patches_bit_identical_on_sample"] = bool(np.array_equal(pc[:k * 5].cpu().numpy(), sel.view(np.int32)))
+        cpu_vb = np.zeros((ncv + nst, 3), np.float32)
+        cpu_vb[:ncv] = m.positions
+        oref.eval_stencils(cpu_vb.reshape(-1), (0, 3, 3), [cpu_vb.reshape(-1)], [(ncv * 3, 3, 3)], st, impl="cpu")
+        outs = [np.zeros((k, 3), np.float32) for _ in range(6)]
+        t1 = time.perf_counter()
+        oref.eval_patches(cpu_vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 6, sel, ptab.vertex, impl="cpu")
+        res["cpu_baseline"] = {"pts_per_s": k / (time.perf_counter() - t1), "cores": 1, "kind": "reference", "sample": f"{k} of the random coordinates"}
+        assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)
+        res["max_abs_diff_vs_cpu_evaluator_P_on_sample"] = float(np.abs(out[:k, 0:3].cpu().numpy() - outs[0]).max())
+    except Exception as exc:
+        res["cpu_baseline"] = {"error": str(exc)}
+    return res
+
+
 def bench_incumbent_cuda(mesh, table, torch, osd):
     """the reference's own CUDA backend kernels (osd/cudaKernel.cu, unmodified, compiled for sm_100a into
     oracle/_ref/libosdcudaref.so) on the same B200 and the same device buffers: config 2 stencils with L = 3 (its tuned
@@ -897,10 +963,11 @@ def run_b200_arm(args):
     config5 = None
     if not args.headline_only:
         config5 = bench_config5_strong(torch, dist, osd, capi, shard, comm_wide, world, rank, max(20, min(args.steps, 100)), max(args.warmup, 5))
-    config3 = patches = incumbent = None
+    config3 = patches = patches_loop = incumbent = None
     if world == 1 and not args.headline_only:
         for name, fn in (("config3", lambda: bench_config3(mesh, torch, osd, iters)),
                          ("patches", lambda: bench_eval_patches(torch, osd, capi)),
+                         ("patches_loop", lambda: bench_eval_patches_loop(torch, osd)),
                          ("incumbent", lambda: bench_incumbent_cuda(mesh, table, torch, osd))):
             try:
                 val = fn()
@@ -910,6 +977,8 @@ def run_b200_arm(args):
                 config3 = val
             elif name == "patches":
                 patches = val
+            elif name == "patches_loop":
+                patches_loop = val
             else:
                 incumbent = val
 
@@ -957,6 +1026,7 @@ def run_b200_arm(args):
             "config3": config3,
             "config5": config5,
             "eval_patches": patches,
+            "eval_patches_loop": patches_loop,
             "incumbent_cuda": incumbent,
         }
         print(json.dumps(line), flush=True)
