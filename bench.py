@@ -493,6 +493,7 @@ def bench_eval_patches(torch, osd, capi, n=10_000_000, iters=10):
         assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)
         got = out[:k].cpu().numpy()
         res["max_abs_diff_vs_cpu_evaluator_P_on_sample"] = float(np.abs(got[:, 0:3] - outs[0]).max())
+        res["max_rel_diff_vs_cpu_evaluator_P_on_sample"] = float(np.abs(got[:, 0:3] - outs[0]).max() / max(np.abs(outs[0]).max(), 1e-30))
     except Exception as exc:
         res["cpu_baseline"] = {"error": str(exc)}
     return res
@@ -557,7 +558,9 @@ def bench_eval_patches_loop(torch, osd, n=10_000_000, iters=10):
         oref.eval_patches(cpu_vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in outs], [(0, 3, 3)] * 6, sel, ptab.vertex, impl="cpu")
         res["cpu_baseline"] = {"pts_per_s": k / (time.perf_counter() - t1), "cores": 1, "kind": "reference", "sample": f"{k} of the random coordinates"}
         assert osd.B200Evaluator.EvalPatches(vb, D(0, 3, 3), *args, n, pc, pt, None)
-        res["max_abs_diff_vs_cpu_evaluator_P_on_sample"] = float(np.abs(out[:k, 0:3].cpu().numpy() - outs[0]).max())
+        diff = np.abs(out[:k, 0:3].cpu().numpy() - outs[0]).max()
+        res["max_abs_diff_vs_cpu_evaluator_P_on_sample"] = float(diff)
+        res["max_rel_diff_vs_cpu_evaluator_P_on_sample"] = float(diff / max(np.abs(outs[0]).max(), 1e-30))   # against the mesh extent
     except Exception as exc:
         res["cpu_baseline"] = {"error": str(exc)}
     return res

@@ -25,77 +25,9 @@
 
 using namespace b200osd;
 
-namespace b200osd {
-signed char g_box_tab_host[6][12][15];
-float g_box_scale_host[6];
-}
-
 namespace {
 
-// Quartic box-spline basis of the regular Loop patch: 12 bivariate quartics, coefficients x12 on the monomials
-//   1 s t s^2 st t^2 s^3 s^2t st^2 t^3 s^4 s^3t s^2t^2 st^3 t^4     (osd/patchBasis.h:557-572 in expanded form)
-const signed char kBox12[12][15] = {
-    { 1, -2, -4, 0, 6, 6, 2, 0, -6, -4, -1, -2, 0, 2, 1 },
-    { 1, 2, -2, 0, -6, 0, -4, 0, 6, 2, 2, 4, 0, -2, -1 },
-    { 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, -1, -2, 0, 0, 0 },
-    { 1, -4, -2, 6, 6, 0, -4, -6, 0, 2, 1, 2, 0, -2, -1 },
-    { 6, 0, 0, -12, -12, -12, 8, 12, 12, 8, -1, -2, 0, -2, -1 },
-    { 1, 4, 2, 6, 6, 0, -4, -6, -12, -4, -1, -2, 0, 4, 2 },
-    { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 0, 0, 0 },
-    { 1, -2, 2, 0, -6, 0, 2, 6, 0, -4, -1, -2, 0, 4, 2 },
-    { 1, 2, 4, 0, 6, 6, -4, -12, -6, -4, 2, 4, 0, -2, -1 },
-    { 0, 0, 0, 0, 0, 0, 2, 6, 6, 2, -1, -2, 0, -2, -1 },
-    { 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, -2, -1 },
-    { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 1 },
-};
-const signed char kMonoA[15] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 4, 3, 2, 1, 0 };
-const signed char kMonoB[15] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4 };
-
 constexpr int kMaxDevices = 64;
-
-// The derivative tables are obtained by differentiating kBox12 monomial by monomial.
-int upload_box_tables() {
-    static const int das[6] = { 0, 1, 0, 2, 1, 0 }, dbs[6] = { 0, 0, 1, 0, 1, 2 };
-    static const int divisor[6] = { 1, 2, 2, 12, 6, 12 };
-    signed char tab[6][12][15];
-    std::memset(tab, 0, sizeof(tab));
-    for (int k = 0; k < 6; ++k)
-        for (int i = 0; i < 12; ++i)
-            for (int m = 0; m < 15; ++m) {
-                int a = kMonoA[m], b = kMonoB[m], c = kBox12[i][m];
-                if (c == 0 || a < das[k] || b < dbs[k]) continue;
-                for (int q = 0; q < das[k]; ++q) c *= (a - q);
-                for (int q = 0; q < dbs[k]; ++q) c *= (b - q);
-                int n = -1;
-                for (int mm = 0; mm < 15; ++mm)
-                    if (kMonoA[mm] == a - das[k] && kMonoB[mm] == b - dbs[k]) n = mm;
-                tab[k][i][n] += (signed char)(c / divisor[k]);
-            }
-    const float scale[6] = { 1.0f / 12.0f, 1.0f / 6.0f, 1.0f / 6.0f, 1.0f, 0.5f, 1.0f };
-    std::memcpy(g_box_tab_host, tab, sizeof(tab));
-    std::memcpy(g_box_scale_host, scale, sizeof(scale));
-    B200_CUDA_TRY(cudaMemcpyToSymbol(g_box_tab, tab, sizeof(tab)));
-    B200_CUDA_TRY(cudaMemcpyToSymbol(g_box_scale, scale, sizeof(scale)));
-    return B200OSD_OK;
-}
-
-// __constant__ symbols are per device: uploaded once per device, lock-free afterwards.  Called when a table with
-// triangle patches is created (never from an evaluation entry: cudaMemcpyToSymbol synchronises).
-int ensure_box_tables() {
-    static std::atomic<bool> done[kMaxDevices];
-    static std::mutex mu;
-    int dev = 0;
-    B200_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= kMaxDevices) { set_error("device ordinal %d out of range", dev); return B200OSD_ERR_UNSUPPORTED; }
-    if (done[dev].load(std::memory_order_acquire)) return B200OSD_OK;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!done[dev].load(std::memory_order_relaxed)) {
-        int rc = upload_box_tables();
-        if (rc) return rc;
-        done[dev].store(true, std::memory_order_release);
-    }
-    return B200OSD_OK;
-}
 
 // Stream-ordered scratch: one pool per device that never trims, so that after the first call an allocation is a
 // pointer bump on the stream -- no cudaMalloc, no synchronisation, legal during stream capture.
@@ -403,9 +335,8 @@ int b200osd_eval_patches(const float *src, const int srcDesc[3], int nOut, float
     int rc = validate_patch_args(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, &empty);
     if (rc || empty) return rc;
     if (!patchCoords || !patchArrays || !patchIndices || !patchParams) { set_error("patch table / coords are NULL"); return B200OSD_ERR_INVALID; }
-    // device arrays of unknown shape: any type may occur (the box-spline tables must be on the device) and nothing is
-    // known about the number of patches, so the coordinates are evaluated in the caller's order
-    if ((rc = ensure_box_tables())) return rc;
+    // device arrays of unknown shape: any type may occur and nothing is known about the number of patches, so the
+    // coordinates are evaluated in the caller's order
     PatchShape shape;
     return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, patchArrays, patchIndices,
                                patchParams, shape, PatchRoute(), (cudaStream_t)stream);
@@ -582,8 +513,7 @@ int b200osd_patch_table_set(b200osd_patch_table *t, int which, int numArrays, co
             hasTri = hasTri || is_tri_type(d);
         }
     }
-    int rc = hasTri ? ensure_box_tables() : B200OSD_OK;
-    if (!rc) rc = upload_array(&tr.arrays, arrays, numArrays);
+    int rc = upload_array(&tr.arrays, arrays, numArrays);
     if (!rc) rc = upload_array(&tr.indices, indices, numIndices);
     if (!rc) rc = upload_array(&tr.params, params, numParams);
     if (rc) { free_triple(tr); return rc; }

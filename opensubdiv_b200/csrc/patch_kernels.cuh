@@ -31,6 +31,8 @@
 
 #include "common.cuh"
 
+#include <utility>
+
 // Every function below is __host__ __device__ so that tests/emu can run the *identical* arithmetic on the CPU
 // (a test-only numerical harness, never a product path: libb200osd.so only ever launches the __global__ kernels).
 #define B200_HD __host__ __device__ __forceinline__
@@ -68,27 +70,48 @@ struct PatchIO {
 
 enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_BASIS = 9, PT_GREGORY_TRIANGLE = 10 };
 
-// Derived box-spline tables (filled once on the host, see patch.cu): g_box_tab[k][i][m], k = value,ds,dt,dss,dst,dtt
-__constant__ signed char g_box_tab[6][12][15];
-__constant__ float g_box_scale[6];
-#ifndef __CUDA_ARCH__
-extern signed char g_box_tab_host[6][12][15];     // host mirror (filled by the same derivation) for tests/emu
-extern float g_box_scale_host[6];
-#endif
-
-B200_HD float box_coeff(int k, int i, int m) {
-#ifdef __CUDA_ARCH__
-    return (float)g_box_tab[k][i][m];
-#else
-    return (float)g_box_tab_host[k][i][m];
-#endif
+// Quartic box-spline basis of the regular Loop patch: 12 bivariate quartics, coefficients x12 on the monomials
+//   1 s t s^2 st t^2 s^3 s^2t st^2 t^3 s^4 s^3t s^2t^2 st^3 t^4     (osd/patchBasis.h:557-572 in expanded form).
+// The five derivative tables follow by differentiating monomial by monomial, all at compile time: the kernels see
+// every coefficient as an immediate operand and zero coefficients cost nothing.
+struct BoxTables { int c[6][12][15]; };
+constexpr BoxTables make_box_tables() {
+    constexpr int base[12][15] = {
+        { 1, -2, -4, 0, 6, 6, 2, 0, -6, -4, -1, -2, 0, 2, 1 },
+        { 1, 2, -2, 0, -6, 0, -4, 0, 6, 2, 2, 4, 0, -2, -1 },
+        { 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, -1, -2, 0, 0, 0 },
+        { 1, -4, -2, 6, 6, 0, -4, -6, 0, 2, 1, 2, 0, -2, -1 },
+        { 6, 0, 0, -12, -12, -12, 8, 12, 12, 8, -1, -2, 0, -2, -1 },
+        { 1, 4, 2, 6, 6, 0, -4, -6, -12, -4, -1, -2, 0, 4, 2 },
+        { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 0, 0, 0 },
+        { 1, -2, 2, 0, -6, 0, 2, 6, 0, -4, -1, -2, 0, 4, 2 },
+        { 1, 2, 4, 0, 6, 6, -4, -12, -6, -4, 2, 4, 0, -2, -1 },
+        { 0, 0, 0, 0, 0, 0, 2, 6, 6, 2, -1, -2, 0, -2, -1 },
+        { 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, -2, -1 },
+        { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 1 },
+    };
+    constexpr int A[15] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 4, 3, 2, 1, 0 };      // power of s of monomial m
+    constexpr int B[15] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4 };      // power of t
+    constexpr int das[6] = { 0, 1, 0, 2, 1, 0 }, dbs[6] = { 0, 0, 1, 0, 1, 2 }; // value, ds, dt, dss, dst, dtt
+    constexpr int divisor[6] = { 1, 2, 2, 12, 6, 12 };                          // folded into box_scale()
+    BoxTables t{};
+    for (int k = 0; k < 6; ++k)
+        for (int i = 0; i < 12; ++i)
+            for (int m = 0; m < 15; ++m) {
+                int a = A[m], b = B[m], c = base[i][m];
+                if (c == 0 || a < das[k] || b < dbs[k]) continue;
+                for (int q = 0; q < das[k]; ++q) c *= (a - q);
+                for (int q = 0; q < dbs[k]; ++q) c *= (b - q);
+                for (int mm = 0; mm < 15; ++mm)
+                    if (A[mm] == a - das[k] && B[mm] == b - dbs[k]) t.c[k][i][mm] += c / divisor[k];
+            }
+    return t;
 }
-B200_HD float box_scale(int k) {
-#ifdef __CUDA_ARCH__
-    return g_box_scale[k];
-#else
-    return g_box_scale_host[k];
-#endif
+template <int K, int I, int M>
+struct BoxC { static constexpr int v = make_box_tables().c[K][I][M]; };
+template <int K>
+B200_HD constexpr float box_scale() {
+    return K == 0 ? 1.0f / 12.0f : (K == 1 || K == 2 ? 1.0f / 6.0f : (K == 4 ? 0.5f : 1.0f));
 }
 B200_HD float rcp_rn(float x) {
 #ifdef __CUDA_ARCH__
@@ -414,7 +437,8 @@ B200_HD void eval_quads(const CV &cv, float s, float t, float d1,
     }
 }
 
-// ------------------------------------------------------------- triangle bases (weight-array form) --
+// ------------------------------------------------------------------------------- triangle bases --
+// Weights live in registers: one derivative set at a time (12 or 18 floats), every index a compile-time constant.
 B200_HD void refl(float *w, int phantom, int plus0, int plus1, int minus) {
     const float v = w[phantom];
     w[plus0] += v;
@@ -423,18 +447,19 @@ B200_HD void refl(float *w, int phantom, int plus0, int plus1, int minus) {
 }
 
 // Box-spline boundary folding (osd/patchBasis.h:663-886): every phantom point is a reflection B + (B' - I).
-B200_HD_NOINLINE void box_fold_boundary(int mask, float *w) {
-    const signed char PH[3][3] = { { 0, 1, 2 }, { 6, 9, 11 }, { 10, 7, 3 } };
-    const signed char B1[3] = { 4, 5, 8 }, B2[3] = { 5, 8, 4 }, I1[3] = { 8, 4, 5 };
-    const signed char B0[3] = { 3, 2, 11 }, I0[3] = { 7, 1, 9 };
-    const signed char B3[3] = { 6, 10, 0 }, I2[3] = { 9, 7, 1 };
-    const signed char VP[3][2] = { { 3, 0 }, { 2, 6 }, { 11, 10 } };
-    const signed char VB0[3] = { 7, 1, 9 }, VI0[3] = { 8, 4, 5 };
-    const signed char VB2[3] = { 1, 9, 7 }, VI1[3] = { 5, 8, 4 };
+B200_HD void box_fold_boundary(int mask, float (&w)[12]) {
+    constexpr int PH[3][3] = { { 0, 1, 2 }, { 6, 9, 11 }, { 10, 7, 3 } };
+    constexpr int B1[3] = { 4, 5, 8 }, B2[3] = { 5, 8, 4 }, I1[3] = { 8, 4, 5 };
+    constexpr int B0[3] = { 3, 2, 11 }, I0[3] = { 7, 1, 9 };
+    constexpr int B3[3] = { 6, 10, 0 }, I2[3] = { 9, 7, 1 };
+    constexpr int VP[3][2] = { { 3, 0 }, { 2, 6 }, { 11, 10 } };
+    constexpr int VB0[3] = { 7, 1, 9 }, VI0[3] = { 8, 4, 5 };
+    constexpr int VB2[3] = { 1, 9, 7 }, VI1[3] = { 5, 8, 4 };
     const int upper = (mask >> 3) & 3;
     int ebits = mask & 7, vbits = 0;
     if (upper == 1) { vbits = ebits; ebits = 0; }
     else if (upper == 2) { vbits = ((ebits & 1) << 2) | (ebits >> 1); }
+#pragma unroll
     for (int e = 0; e < 3; ++e) {
         if (!(ebits & (1 << e))) continue;
         const int prev = (e + 2) % 3, next = (e + 1) % 3;
@@ -445,6 +470,7 @@ B200_HD_NOINLINE void box_fold_boundary(int mask, float *w) {
         else                     refl(w, PH[e][2], B2[e], B3[e], I2[e]);
         w[PH[e][0]] = 0.0f; w[PH[e][1]] = 0.0f; w[PH[e][2]] = 0.0f;
     }
+#pragma unroll
     for (int v = 0; v < 3; ++v) {
         if (!(vbits & (1 << v))) continue;
         refl(w, VP[v][0], B1[v], VB0[v], VI0[v]);
@@ -453,81 +479,188 @@ B200_HD_NOINLINE void box_fold_boundary(int mask, float *w) {
     }
 }
 
-B200_HD float bern(int n, int i, int j, int k, float u, float v, float w) {
-    if (i < 0 || j < 0 || k < 0) return 0.0f;
-    const float fact[5] = { 1.0f, 1.0f, 2.0f, 6.0f, 24.0f };
-    float r = fact[n] / (fact[i] * fact[j] * fact[k]);
-    for (int q = 0; q < i; ++q) r *= u;
-    for (int q = 0; q < j; ++q) r *= v;
-    for (int q = 0; q < k; ++q) r *= w;
-    return r;
+// the 15 monomials of kBox12's columns
+B200_HD void box_monomials(float s, float t, float (&M)[15]) {
+    M[0] = 1.0f; M[1] = s; M[2] = t;
+    M[3] = s * s; M[4] = s * t; M[5] = t * t;
+    M[6] = M[3] * s; M[7] = M[4] * s; M[8] = M[4] * t; M[9] = M[5] * t;
+    M[10] = M[6] * s; M[11] = M[7] * s; M[12] = M[3] * M[5]; M[13] = M[8] * t; M[14] = M[9] * t;
 }
 
-// Weight arrays for LOOP (12), GREGORY_TRIANGLE (18) and TRIANGLES (3); returns the number of points.
+template <int K, int I, int... Ms>
+B200_HD float box_row(const float (&M)[15], std::integer_sequence<int, Ms...>) {
+    float acc = 0.0f;
+    ((acc = (BoxC<K, I, Ms>::v != 0) ? fmaf((float)BoxC<K, I, Ms>::v, M[Ms], acc) : acc), ...);
+    return acc;
+}
+
+// Weights of derivative set K (0 value, 1 ds, 2 dt, 3 dss, 4 dst, 5 dtt) of the 12-point box spline, boundary folded.
+template <int K, int... Is>
+B200_HD void box_set_seq(const float (&M)[15], float (&w)[12], std::integer_sequence<int, Is...>) {
+    ((w[Is] = box_scale<K>() * box_row<K, Is>(M, std::make_integer_sequence<int, 15>{})), ...);
+}
+template <int K>
+B200_HD void loop_weight_set(const float (&M)[15], int boundary, float (&w)[12]) {
+    box_set_seq<K>(M, w, std::make_integer_sequence<int, 12>{});
+    if (boundary) box_fold_boundary(boundary, w);
+}
+
+// n! / (i! j! k!) u^i v^j w^k, zero outside the triangle (osd/patchBasis.h:1006-1125 in closed form)
+template <int N, int I, int J, int K>
+B200_HD float bern(float u, float v, float w) {
+    if constexpr (I < 0 || J < 0 || K < 0) {
+        return 0.0f;
+    } else {
+        constexpr float fact[5] = { 1.0f, 1.0f, 2.0f, 6.0f, 24.0f };
+        float r = fact[N] / (fact[I] * fact[J] * fact[K]);
+#pragma unroll
+        for (int q = 0; q < I; ++q) r *= u;
+#pragma unroll
+        for (int q = 0; q < J; ++q) r *= v;
+#pragma unroll
+        for (int q = 0; q < K; ++q) r *= w;
+        return r;
+    }
+}
+
+// quartic triangular Bernstein function n (row-major over (i,j), k = 4-i-j) differentiated per set K
+constexpr int kGtI[15] = { 0, 1, 2, 3, 4, 0, 1, 2, 3, 0, 1, 2, 0, 1, 0 };
+constexpr int kGtJ[15] = { 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4 };
+// the 18 Gregory-triangle points: which Bernstein function feeds each, and which rational blend scales it (-1: none)
+constexpr int kGtSrc[18] = { 0, 1, 5, 6, 6, 4, 8, 3, 7, 7, 14, 12, 13, 10, 10, 2, 11, 9 };
+constexpr int kGtBlend[18] = { -1, -1, -1, 0, 1, -1, -1, -1, 2, 3, -1, -1, -1, 4, 5, -1, -1, -1 };
+
+template <int K, int N>
+B200_HD float gt_basis(float u, float v, float w) {
+    constexpr int i = kGtI[N], j = kGtJ[N], k = 4 - i - j;
+    if constexpr (K == 0) {
+        return bern<4, i, j, k>(u, v, w);
+    } else if constexpr (K == 1) {
+        return 4.0f * (bern<3, i - 1, j, k>(u, v, w) - bern<3, i, j, k - 1>(u, v, w));
+    } else if constexpr (K == 2) {
+        return 4.0f * (bern<3, i, j - 1, k>(u, v, w) - bern<3, i, j, k - 1>(u, v, w));
+    } else if constexpr (K == 3) {
+        return 12.0f * (bern<2, i - 2, j, k>(u, v, w) - 2.0f * bern<2, i - 1, j, k - 1>(u, v, w) + bern<2, i, j, k - 2>(u, v, w));
+    } else if constexpr (K == 4) {
+        return 12.0f * (bern<2, i - 1, j - 1, k>(u, v, w) - bern<2, i - 1, j, k - 1>(u, v, w)
+                        - bern<2, i, j - 1, k - 1>(u, v, w) + bern<2, i, j, k - 2>(u, v, w));
+    } else {
+        return 12.0f * (bern<2, i, j - 2, k>(u, v, w) - 2.0f * bern<2, i, j - 1, k - 1>(u, v, w) + bern<2, i, j, k - 2>(u, v, w));
+    }
+}
+
+// rational blends of the three interior point pairs (osd/patchBasis.h:1160-1200)
+B200_HD void gt_blends(float u, float v, float ww, float (&G)[6]) {
+    G[0] = 1.0f; G[1] = 0.0f; G[2] = 1.0f; G[3] = 0.0f; G[4] = 1.0f; G[5] = 0.0f;
+    if ((u + v) > 0.0f)  { G[0] = u / (u + v);   G[1] = v / (u + v); }
+    if ((v + ww) > 0.0f) { G[2] = v / (v + ww);  G[3] = ww / (v + ww); }
+    if ((ww + u) > 0.0f) { G[4] = ww / (ww + u); G[5] = u / (ww + u); }
+}
+
+template <int K, int I>
+B200_HD float gt_point(float u, float v, float ww, const float (&G)[6]) {
+    constexpr int src = kGtSrc[I], blend = kGtBlend[I];
+    if constexpr (blend < 0) return gt_basis<K, src>(u, v, ww);
+    else return gt_basis<K, src>(u, v, ww) * G[blend];
+}
+template <int K, int... Is>
+B200_HD void gt_set_seq(float u, float v, float ww, const float (&G)[6], float (&w)[18], std::integer_sequence<int, Is...>) {
+    ((w[Is] = gt_point<K, Is>(u, v, ww, G)), ...);
+}
+template <int K>
+B200_HD void gregory_tri_weight_set(float u, float v, float ww, const float (&G)[6], float (&w)[18]) {
+    gt_set_seq<K>(u, v, ww, G, w, std::make_integer_sequence<int, 18>{});
+}
+
+// linear triangle: derivative set K of the 3 weights
+template <int K>
+B200_HD void triangle_weight_set(float s, float t, float (&w)[3]) {
+    if constexpr (K == 0) { w[0] = 1.0f - s - t; w[1] = s; w[2] = t; }
+    else if constexpr (K == 1) { w[0] = -1.0f; w[1] = 1.0f; w[2] = 0.0f; }
+    else if constexpr (K == 2) { w[0] = -1.0f; w[1] = 0.0f; w[2] = 1.0f; }
+    else { w[0] = 0.0f; w[1] = 0.0f; w[2] = 0.0f; }
+}
+
+// One derivative set of one triangle type, into registers.  NP = 12 (LOOP), 18 (GREGORY_TRIANGLE), 3 (TRIANGLES).
+struct TriParams {
+    float s, t, ww;
+    int boundary;
+    float M[15];     // LOOP
+    float G[6];      // GREGORY_TRIANGLE
+};
+template <int TYPE, int K, int NP>
+B200_HD void tri_weight_set(const TriParams &tp, float (&w)[NP]) {
+    if constexpr (TYPE == PT_LOOP) loop_weight_set<K>(tp.M, tp.boundary, w);
+    else if constexpr (TYPE == PT_GREGORY_TRIANGLE) gregory_tri_weight_set<K>(tp.s, tp.t, tp.ww, tp.G, w);
+    else triangle_weight_set<K>(tp.s, tp.t, w);
+}
+template <int TYPE>
+B200_HD void tri_prepare(float s, float t, int boundary, TriParams &tp) {
+    tp.s = s; tp.t = t; tp.ww = 1.0f - s - t; tp.boundary = boundary;
+    if constexpr (TYPE == PT_LOOP) box_monomials(s, t, tp.M);
+    if constexpr (TYPE == PT_GREGORY_TRIANGLE) gt_blends(s, t, tp.ww, tp.G);
+}
+template <int TYPE>
+B200_HD constexpr int tri_points() { return TYPE == PT_LOOP ? 12 : (TYPE == PT_GREGORY_TRIANGLE ? 18 : 3); }
+
+// out[K] += sum_j (w_j * scale) cv_j for set K; recurses over the NSETS sets so K stays a compile-time constant.
+template <int LT, int NSETS, int TYPE, int K, typename CV>
+B200_HD void tri_accumulate(const CV &cv, const TriParams &tp, float d1, float d2, float (&out)[NSETS][LT]) {
+    if constexpr (K < NSETS) {
+        constexpr int NP = tri_points<TYPE>();
+        float w[NP];
+        tri_weight_set<TYPE, K, NP>(tp, w);
+        const float scale = K == 0 ? 1.0f : (K < 3 ? d1 : d2);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            float v[LT];
+            cv.template load<LT>(j, v);
+            const float wk = w[j] * scale;
+#pragma unroll
+            for (int c = 0; c < LT; ++c) out[K][c] = fmaf(wk, v[c], out[K][c]);
+        }
+        tri_accumulate<LT, NSETS, TYPE, K + 1>(cv, tp, d1, d2, out);
+    }
+}
+template <int LT, int ORDER, int TYPE, typename CV>
+B200_HD void eval_triangle_type(const CV &cv, float s, float t, int boundary, float d1, float sign,
+                                float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
+    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+    TriParams tp;
+    tri_prepare<TYPE>(s, t, boundary, tp);
+    const float d2 = sign * d1 * d1;     // osd/patchBasis.h:1598: d2Scale = derivSign * d1Scale * d1Scale
+    tri_accumulate<LT, NSETS, TYPE, 0>(cv, tp, d1, d2, out);
+}
+
+// Weight arrays w[k][i] of all NSETS sets (the limit-stencil builder wants them side by side); returns the point count.
+template <int NSETS, int TYPE, int K>
+B200_HD void tri_weights_type(const TriParams &tp, float (*w)[20]) {
+    if constexpr (K < NSETS) {
+        constexpr int NP = tri_points<TYPE>();
+        float wk[NP];
+        tri_weight_set<TYPE, K, NP>(tp, wk);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) w[K][i] = wk[i];
+        tri_weights_type<NSETS, TYPE, K + 1>(tp, w);
+    }
+}
 template <int ORDER>
 B200_HD_NOINLINE int tri_weights(int type, float s, float t, int boundary, float (*w)[20]) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
+    TriParams tp;
     if (type == PT_TRIANGLES) {
-        w[0][0] = 1.0f - s - t; w[0][1] = s; w[0][2] = t;
-        if (ORDER >= 1) {
-            w[1][0] = -1.0f; w[1][1] = 1.0f; w[1][2] = 0.0f;
-            w[2][0] = -1.0f; w[2][1] = 0.0f; w[2][2] = 1.0f;
-        }
-        if (ORDER >= 2)
-            for (int k = 3; k < 6; ++k) { w[k][0] = 0.0f; w[k][1] = 0.0f; w[k][2] = 0.0f; }
+        tri_prepare<PT_TRIANGLES>(s, t, boundary, tp);
+        tri_weights_type<NSETS, PT_TRIANGLES, 0>(tp, w);
         return 3;
     }
     if (type == PT_LOOP) {
-        float M[15];
-        M[0] = 1.0f; M[1] = s; M[2] = t;
-        M[3] = s * s; M[4] = s * t; M[5] = t * t;
-        M[6] = M[3] * s; M[7] = M[4] * s; M[8] = M[4] * t; M[9] = M[5] * t;
-        M[10] = M[6] * s; M[11] = M[7] * s; M[12] = M[3] * M[5]; M[13] = M[8] * t; M[14] = M[9] * t;
-        for (int k = 0; k < NSETS; ++k) {
-            for (int i = 0; i < 12; ++i) {
-                float acc = 0.0f;
-#pragma unroll
-                for (int m = 0; m < 15; ++m) acc = fmaf(box_coeff(k, i, m), M[m], acc);
-                w[k][i] = box_scale(k) * acc;
-            }
-            if (boundary) box_fold_boundary(boundary, w[k]);
-        }
+        tri_prepare<PT_LOOP>(s, t, boundary, tp);
+        tri_weights_type<NSETS, PT_LOOP, 0>(tp, w);
         return 12;
     }
-    // GREGORY_TRIANGLE: quartic Bernstein over the triangle + rational blends on the 3 interior points
-    {
-        const signed char PI[15] = { 0, 1, 2, 3, 4, 0, 1, 2, 3, 0, 1, 2, 0, 1, 0 };
-        const signed char PJ[15] = { 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4 };
-        const signed char SRC[18] = { 0, 1, 5, 6, 6, 4, 8, 3, 7, 7, 14, 12, 13, 10, 10, 2, 11, 9 };
-        const signed char GI[18] = { -1, -1, -1, 0, 1, -1, -1, -1, 2, 3, -1, -1, -1, 4, 5, -1, -1, -1 };
-        const int DS[6] = { 0, 1, 0, 2, 1, 0 }, DT[6] = { 0, 0, 1, 0, 1, 2 };
-        const float u = s, v = t, ww = 1.0f - u - v;
-        float G[6] = { 1.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.0f };
-        if ((u + v) > 0.0f)  { G[0] = u / (u + v);   G[1] = v / (u + v); }
-        if ((v + ww) > 0.0f) { G[2] = v / (v + ww);  G[3] = ww / (v + ww); }
-        if ((ww + u) > 0.0f) { G[4] = ww / (ww + u); G[5] = u / (ww + u); }
-        for (int k = 0; k < NSETS; ++k) {
-            float B[15];
-            const int ds = DS[k], dt = DT[k];
-            for (int n = 0; n < 15; ++n) {
-                const int i = PI[n], j = PJ[n], kk = 4 - i - j;
-                float r;
-                if (ds + dt == 0) r = bern(4, i, j, kk, u, v, ww);
-                else if (ds + dt == 1)
-                    r = 4.0f * ((ds ? bern(3, i - 1, j, kk, u, v, ww) : bern(3, i, j - 1, kk, u, v, ww)) - bern(3, i, j, kk - 1, u, v, ww));
-                else if (ds == 2)
-                    r = 12.0f * (bern(2, i - 2, j, kk, u, v, ww) - 2.0f * bern(2, i - 1, j, kk - 1, u, v, ww) + bern(2, i, j, kk - 2, u, v, ww));
-                else if (dt == 2)
-                    r = 12.0f * (bern(2, i, j - 2, kk, u, v, ww) - 2.0f * bern(2, i, j - 1, kk - 1, u, v, ww) + bern(2, i, j, kk - 2, u, v, ww));
-                else
-                    r = 12.0f * (bern(2, i - 1, j - 1, kk, u, v, ww) - bern(2, i - 1, j, kk - 1, u, v, ww)
-                                 - bern(2, i, j - 1, kk - 1, u, v, ww) + bern(2, i, j, kk - 2, u, v, ww));
-                B[n] = r;
-            }
-            for (int i = 0; i < 18; ++i) w[k][i] = (GI[i] < 0) ? B[SRC[i]] : B[SRC[i]] * G[GI[i]];
-        }
-        return 18;
-    }
+    tri_prepare<PT_GREGORY_TRIANGLE>(s, t, boundary, tp);
+    tri_weights_type<NSETS, PT_GREGORY_TRIANGLE, 0>(tp, w);
+    return 18;
 }
 
 // --------------------------------------------------------------------------------------- kernel --
@@ -535,27 +668,18 @@ B200_HD_NOINLINE int tri_weights(int type, float s, float t, int boundary, float
 template <int LT, int ORDER, bool TRI, typename CV>
 B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int boundary, float d1, float sign,
                              float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
-    constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
     if (type == PT_REGULAR) {
         eval_regular<LT, ORDER>(cv, s, t, boundary, d1, out);
     } else if (type == PT_GREGORY_BASIS) {
         eval_gregory<LT, ORDER>(cv, s, t, d1, out);
     } else if (type == PT_QUADS) {
         eval_quads<LT, ORDER>(cv, s, t, d1, out);
-    } else if (TRI && (type == PT_LOOP || type == PT_GREGORY_TRIANGLE || type == PT_TRIANGLES)) {
-        float w[NSETS][20];
-        const int np = tri_weights<ORDER>(type, s, t, boundary, w);
-        const float d2 = sign * d1 * d1;     // osd/patchBasis.h:1598: d2Scale = derivSign * d1Scale * d1Scale
-        for (int j = 0; j < np; ++j) {
-            float v[LT];
-            cv.template load<LT>(j, v);
-#pragma unroll
-            for (int k = 0; k < NSETS; ++k) {
-                const float wk = w[k][j] * (k == 0 ? 1.0f : (k < 3 ? d1 : d2));
-#pragma unroll
-                for (int c = 0; c < LT; ++c) out[k][c] = fmaf(wk, v[c], out[k][c]);
-            }
-        }
+    } else if (TRI && type == PT_LOOP) {
+        eval_triangle_type<LT, ORDER, PT_LOOP>(cv, s, t, boundary, d1, sign, out);
+    } else if (TRI && type == PT_GREGORY_TRIANGLE) {
+        eval_triangle_type<LT, ORDER, PT_GREGORY_TRIANGLE>(cv, s, t, boundary, d1, sign, out);
+    } else if (TRI && type == PT_TRIANGLES) {
+        eval_triangle_type<LT, ORDER, PT_TRIANGLES>(cv, s, t, boundary, d1, sign, out);
     }
     // unknown descriptor: the reference evaluates zero points, i.e. writes zeros
 }
@@ -780,7 +904,7 @@ constexpr int kPatchModeDirect = 0, kPatchModeHull = 1, kPatchModeGrouped = 2;
 // Hulls staged per warp: one warp per 32 coordinates, persistent grid (a block walks tiles with a grid stride).
 // Runs in the caller's order, or -- when `perm` is given and the call's state says so -- in the grouped order.
 template <int LT, int ORDER, bool TRI>
-__global__ void __launch_bounds__(kPatchBlock, 7) patch_run_kernel(PatchIO io) {
+__global__ void __launch_bounds__(kPatchBlock, TRI ? 4 : 7) patch_run_kernel(PatchIO io) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
     constexpr int LTU = hull_unit(LT);
     constexpr unsigned FULL = 0xffffffffu;
@@ -974,7 +1098,7 @@ __global__ void __launch_bounds__(256) hull_build_kernel(const float *src, int s
 // shared memory first (two full lines per hull instead of one line touch per lane and piece) relieves the L1 wavefront
 // pipe (84 % -> lower) but serialises a load -> store -> barrier -> evaluate chain per warp and is 25 % SLOWER.
 template <int LT, int ORDER, bool TRI>
-__global__ void __launch_bounds__(kPatchBlock, 6) patch_hull_kernel(PatchIO io, const float *hull) {
+__global__ void __launch_bounds__(kPatchBlock, TRI ? 4 : 6) patch_hull_kernel(PatchIO io, const float *hull) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
     if (io.binState && io.binState->mode != kPatchModeHull) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
