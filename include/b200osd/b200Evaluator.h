@@ -436,9 +436,16 @@ private:
         int sd[3] = { srcDesc.offset, srcDesc.length, srcDesc.stride };
         int dd[6][3];
         flatten(n, descs, dd);
-        return b200osd_eval_patches(src, sd, n, dsts, dd, numPatchCoords, (const b200osd_patch_coord *)patchCoords,
-                                    (const b200osd_patch_array *)patchArrays, (const int *)patchIndices,
-                                    (const b200osd_patch_param *)patchParams, B200StreamOf(deviceContext)) == B200OSD_OK;
+        // a client built with OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES keeps that behaviour (osd/patchBasis.h:421-487)
+#ifdef OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES
+        const int options = B200OSD_PATCH_GREGORY_TRUE_DERIVATIVES;
+#else
+        const int options = 0;
+#endif
+        return b200osd_eval_patches_ex(src, sd, n, dsts, dd, numPatchCoords, (const b200osd_patch_coord *)patchCoords,
+                                       (const b200osd_patch_array *)patchArrays, (const int *)patchIndices,
+                                       (const b200osd_patch_param *)patchParams, options,
+                                       B200StreamOf(deviceContext)) == B200OSD_OK;
     }
 
     B200Evaluator() : _plan(NULL), _planTable(NULL), _planCoords(NULL), _planCount(0) {}

@@ -37,6 +37,10 @@ public:
             ok = b200osd_patch_table_set(h, 2 + c, (int)cpu.GetNumPatchArrays(), arrays(cpu.GetFVarPatchArrayBuffer(c)),
                                          (int)cpu.GetFVarPatchIndexSize(c), cpu.GetFVarPatchIndexBuffer(c),
                                          (int)cpu.GetFVarPatchParamSize(c), params(cpu.GetFVarPatchParamBuffer(c))) == B200OSD_OK;
+#ifdef OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES
+        // the reference's build-time switch (CMakeLists.txt:340,640; osd/patchBasis.h:421-487) carried over per table
+        if (ok) ok = b200osd_patch_table_set_options(h, B200OSD_PATCH_GREGORY_TRUE_DERIVATIVES) == B200OSD_OK;
+#endif
         if (!ok) { b200osd_patch_table_destroy(h); return NULL; }      // cudaPatchTable.cpp:59-66
         return new B200PatchTable(h);
     }

@@ -176,6 +176,20 @@ B200OSD_API int b200osd_eval_patches(
         const b200osd_patch_array *patchArrays, const int *patchIndices,
         const b200osd_patch_param *patchParams, void *stream);
 
+/* Evaluation options.  The reference chooses at BUILD time (cmake -DOPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES=ON,
+ * CMakeLists.txt:340,640) whether the derivative weights of the 8 interior points of a GREGORY_BASIS patch are the
+ * default approximation (osd/patchBasis.h:421-440) or the true derivatives of the rational blend (:441-487; Far does
+ * the same, far/patchBasis.cpp:462).  Here it is a run-time option of the call or the table; the C++ headers in
+ * include/b200osd/ set it when the client is compiled with that macro, so a drop-in build keeps its behaviour. */
+#define B200OSD_PATCH_GREGORY_TRUE_DERIVATIVES 1
+/* b200osd_eval_patches with an `options` mask (0 = b200osd_eval_patches) */
+B200OSD_API int b200osd_eval_patches_ex(
+        const float *src, const int srcDesc[3],
+        int nOut, float *const dsts[], const int dstDescs[][3],
+        int numPatchCoords, const b200osd_patch_coord *patchCoords,
+        const b200osd_patch_array *patchArrays, const int *patchIndices,
+        const b200osd_patch_param *patchParams, int options, void *stream);
+
 /* EvalPatches through the table handle (fast path): which = 0 vertex, 1 varying, 2+c face-varying channel c.
  * Same contract as b200osd_eval_patches.  The table is immutable: any number of threads and streams may evaluate one
  * table concurrently.  Coordinates are evaluated in the caller's order, one warp per 32 of them; a warp copies every
@@ -194,6 +208,10 @@ B200OSD_API int b200osd_patch_table_eval(const b200osd_patch_table *t, int which
  * index), 3 = always the per-call hull cache */
 B200OSD_API void b200osd_patch_table_set_variant(b200osd_patch_table *t, int variant);
 B200OSD_API int  b200osd_patch_table_get_variant(const b200osd_patch_table *t);
+/* evaluation options (B200OSD_PATCH_*) of every call through this table: b200osd_patch_table_eval, patch plans, and the
+ * limit-stencil tables b200osd_limit_stencil_table_create builds from it.  Set before the table is shared. */
+B200OSD_API int  b200osd_patch_table_set_options(b200osd_patch_table *t, int options);
+B200OSD_API int  b200osd_patch_table_get_options(const b200osd_patch_table *t);
 
 /* ---- patch plan: a cached grouping of ONE coordinate set (the per-use state an "instantiatable" evaluator owns in the
  * reference design: osd/mesh.h:305-409, osd/glComputeEvaluator.h:98-128) ------------------------------------------------

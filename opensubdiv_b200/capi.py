@@ -28,7 +28,8 @@ SYMBOLS = [
     "b200osd_eval_stencils", "b200osd_limit_stencil_table_create",
     "b200osd_patch_table_create", "b200osd_patch_table_destroy", "b200osd_patch_table_set",
     "b200osd_patch_table_num_fvar_channels", "b200osd_patch_table_buffer", "b200osd_patch_table_count",
-    "b200osd_eval_patches", "b200osd_patch_table_eval", "b200osd_patch_table_set_variant", "b200osd_patch_table_get_variant",
+    "b200osd_eval_patches", "b200osd_eval_patches_ex", "b200osd_patch_table_eval", "b200osd_patch_table_set_variant",
+    "b200osd_patch_table_get_variant", "b200osd_patch_table_set_options", "b200osd_patch_table_get_options",
     "b200osd_patch_plan_create", "b200osd_patch_plan_destroy", "b200osd_patch_plan_capacity", "b200osd_patch_plan_bin",
     "b200osd_patch_plan_eval",
     "b200osd_patch_map_create", "b200osd_patch_map_destroy", "b200osd_patch_map_info", "b200osd_patch_map_find",
@@ -98,7 +99,10 @@ def lib():
     L.b200osd_patch_table_buffer.argtypes = [vp, i, i]
     L.b200osd_patch_table_count.argtypes = [vp, i, i]
     L.b200osd_eval_patches.argtypes = [vp, vp, i, vp, vp, i, vp, vp, vp, vp, vp]
+    L.b200osd_eval_patches_ex.argtypes = [vp, vp, i, vp, vp, i, vp, vp, vp, vp, i, vp]
     L.b200osd_patch_table_eval.argtypes = [vp, i, vp, vp, i, vp, vp, i, vp, vp]
+    L.b200osd_patch_table_set_options.argtypes = [vp, i]
+    L.b200osd_patch_table_get_options.argtypes = [vp]
     L.b200osd_patch_table_set_variant.argtypes = [vp, i]
     L.b200osd_patch_table_get_variant.argtypes = [vp]
     L.b200osd_patch_plan_create.restype = vp

@@ -46,6 +46,7 @@ struct LimitIO {
     int *sizes, *offsets, *indices;             // the table
     float *w[6];
     int *overflow;                              // set when a stencil exceeds kLimitCap entries
+    int options;                                // kPatchOpt*: the patch table's evaluation options
 };
 
 // ---- the reference's polynomial forms (restated; see the header comment) ----
@@ -105,7 +106,7 @@ __device__ __forceinline__ void ref_fold_line(float *w, int i0, int i1, int i2, 
 
 // weights of all NW sets into w[set * 20 + point]; returns the number of points.  s, t are already normalised.
 template <int NW>
-__device__ int ref_patch_weights(int type, float s, float t, int boundary, float *w) {
+__device__ int ref_patch_weights(int type, float s, float t, int boundary, int options, float *w) {
     constexpr int order = NW == 1 ? 0 : (NW == 3 ? 1 : 2);
     if (type == PT_REGULAR) {
         float bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4];
@@ -128,7 +129,7 @@ __device__ int ref_patch_weights(int type, float s, float t, int boundary, float
     if (type == PT_GREGORY_BASIS) {
         const signed char COL[20] = { 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2, 0, 0, 1, 1, 1 };
         const signed char ROW[20] = { 0, 0, 1, 1, 1, 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2 };
-        float bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4], G[8];
+        float bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4], G[8], R[4];
         const float sc = 1.0f - s, tc = 1.0f - t;
         ref_bezier3(s, bs, order >= 1 ? ds : nullptr, order >= 2 ? dss : nullptr);
         ref_bezier3(t, bt, order >= 1 ? dt : nullptr, order >= 2 ? dtt : nullptr);
@@ -138,10 +139,34 @@ __device__ int ref_patch_weights(int type, float s, float t, int boundary, float
             const float r = (den[c] <= 0.0f) ? 1.0f : (1.0f / den[c]);
             G[2 * c] = a[c] * r;
             G[2 * c + 1] = 1.0f - a[c] * r;
+            R[c] = r;
         }
+        const bool trueDerivatives = (options & kPatchOptGregoryTrueDerivatives) != 0;
         for (int i = 0; i < 20; ++i) {
             const int col = COL[i], row = ROW[i], p = i % 5;
-            if (p >= 3) {
+            if (p >= 3 && order >= 1 && trueDerivatives) {
+                // far/patchBasis.cpp:483-530 (OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES), operation for operation
+                const float NDS[8] = { 1.0f, 0.0f, 0.0f, -1.0f, -1.0f, 0.0f, 0.0f, 1.0f };
+                const float NDT[8] = { 0.0f, 1.0f, 1.0f, 0.0f, 0.0f, -1.0f, -1.0f, 0.0f };
+                const float DDS[8] = { 1.0f, 1.0f, -1.0f, -1.0f, -1.0f, -1.0f, 1.0f, 1.0f };
+                const float DDT[8] = { 1.0f, 1.0f, 1.0f, 1.0f, -1.0f, -1.0f, -1.0f, -1.0f };
+                const int k = 2 * (i / 5) + (p - 3);
+                const float g = G[k], D = R[i / 5];
+                w[i] = bs[col] * bt[row] * g;
+                const float Gds = (NDS[k] - DDS[k] * g) * D;
+                const float Gdt = (NDT[k] - DDT[k] * g) * D;
+                w[20 + i] = (ds[col] * g + bs[col] * Gds) * bt[row];
+                w[40 + i] = (dt[row] * g + bt[row] * Gdt) * bs[col];
+                if (order >= 2) {
+                    const float Dsq = D * D;
+                    const float Gdss = 2.0f * DDS[k] * Dsq * (g * DDS[k] - NDS[k]);
+                    const float Gdst = Dsq * (2.0f * g * DDS[k] * DDT[k] - NDS[k] * DDT[k] - NDT[k] * DDS[k]);
+                    const float Gdtt = 2.0f * DDT[k] * Dsq * (g * DDT[k] - NDT[k]);
+                    w[60 + i] = (dss[col] * g + 2.0f * ds[col] * Gds + bs[col] * Gdss) * bt[row];
+                    w[80 + i] = bt[row] * (bs[col] * Gdst + ds[col] * Gdt) + dt[row] * (ds[col] * g + bs[col] * Gds);
+                    w[100 + i] = (dtt[row] * g + 2.0f * dt[row] * Gdt + bt[row] * Gdtt) * bs[col];
+                }
+            } else if (p >= 3) {
                 const float g = G[2 * (i / 5) + (p - 3)];
                 w[i] = bs[col] * bt[row] * g;
                 if (order >= 1) { w[20 + i] = ds[col] * bt[row] * g; w[40 + i] = dt[row] * bs[col] * g; }
@@ -204,7 +229,7 @@ __global__ void __launch_bounds__(32 * kLimitWarps) limit_merge_kernel(LimitIO i
         int np = 0;
         __syncwarp();
         if (lane == 0) {
-            np = ref_patch_weights<NW>(ps.type, ps.s, ps.t, ps.boundary, wb);
+            np = ref_patch_weights<NW>(ps.type, ps.s, ps.t, ps.boundary, io.options, wb);
             // derivative scaling (osd/patchBasis.h:1568-1607): d1 = +-2^depth, d2 = sign * d1 * d1
             if (NW >= 3) {
                 const float d1 = ps.d1;

@@ -167,6 +167,7 @@ int launch_hull_build(const PatchIO &io, int LT, long long rows, float *hull, cu
 struct PatchShape {            // what the host knows about the table behind a call
     int maxPoints = 20;        // largest control hull (raw device arrays: unknown, assume the largest type)
     bool hasTri = true;        // triangle types may occur
+    int options = 0;           // kPatchOpt* (PatchIO::options): any set bit selects the general kernel instantiation
 };
 
 // How a call is served.  perm / state: grouped order (state NULL: unconditionally).  hull: scratch for the per-call
@@ -180,7 +181,7 @@ struct PatchRoute {
 };
 
 #define B200_PATCH_DISPATCH(fn, ...)                                                                                   \
-    (shape.hasTri ? (nOut == 1 ? fn<0, true>(__VA_ARGS__) : (nOut == 3 ? fn<1, true>(__VA_ARGS__) : fn<2, true>(__VA_ARGS__))) \
+    ((shape.hasTri || shape.options) ? (nOut == 1 ? fn<0, true>(__VA_ARGS__) : (nOut == 3 ? fn<1, true>(__VA_ARGS__) : fn<2, true>(__VA_ARGS__))) \
                   : (nOut == 1 ? fn<0, false>(__VA_ARGS__) : (nOut == 3 ? fn<1, false>(__VA_ARGS__) : fn<2, false>(__VA_ARGS__))))
 
 int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float *const dsts[],
@@ -205,6 +206,7 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
         io.params = patchParams;
         io.perm = route.perm;
         io.binState = route.state;
+        io.options = shape.options;
         // one record per coordinate: output k at float k*LT of an nOut*LT-float record in one buffer (glEvalLimit-style
         // interleaving, or a single tightly packed output)
         const int R = nOut * LT;
@@ -282,6 +284,7 @@ struct b200osd_patch_table {
     std::vector<Triple> triples;       // 0 vertex, 1 varying, 2+c fvar channel c
     int numFVar = 0;
     int variant = 0;                   // b200osd_patch_table_set_variant
+    int options = 0;                   // b200osd_patch_table_set_options
 };
 
 struct b200osd_patch_plan {
@@ -331,6 +334,15 @@ int b200osd_eval_patches(const float *src, const int srcDesc[3], int nOut, float
                          const int dstDescs[][3], int numPatchCoords, const b200osd_patch_coord *patchCoords,
                          const b200osd_patch_array *patchArrays, const int *patchIndices,
                          const b200osd_patch_param *patchParams, void *stream) {
+    return b200osd_eval_patches_ex(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, patchArrays,
+                                   patchIndices, patchParams, 0, stream);
+}
+
+int b200osd_eval_patches_ex(const float *src, const int srcDesc[3], int nOut, float *const dsts[],
+                            const int dstDescs[][3], int numPatchCoords, const b200osd_patch_coord *patchCoords,
+                            const b200osd_patch_array *patchArrays, const int *patchIndices,
+                            const b200osd_patch_param *patchParams, int options, void *stream) {
+    if (options & ~B200OSD_PATCH_GREGORY_TRUE_DERIVATIVES) { set_error("eval_patches: unknown option bits 0x%x", options); return B200OSD_ERR_INVALID; }
     bool empty = false;
     int rc = validate_patch_args(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, &empty);
     if (rc || empty) return rc;
@@ -338,6 +350,7 @@ int b200osd_eval_patches(const float *src, const int srcDesc[3], int nOut, float
     // device arrays of unknown shape: any type may occur and nothing is known about the number of patches, so the
     // coordinates are evaluated in the caller's order
     PatchShape shape;
+    shape.options = options;
     return eval_patches_common(src, srcDesc, nOut, dsts, dstDescs, numPatchCoords, patchCoords, patchArrays, patchIndices,
                                patchParams, shape, PatchRoute(), (cudaStream_t)stream);
 }
@@ -358,6 +371,7 @@ int b200osd_patch_table_eval(const b200osd_patch_table *t, int which, const floa
     PatchShape shape;
     shape.maxPoints = std::max(tr->maxPoints, 3);
     shape.hasTri = tr->hasTri;
+    shape.options = t->options;
 
     // How the coordinates are served (variant: 0 automatic, 1 caller's order, 2 grouped by patch per call, 3 hull cache):
     //  * caller's order, hulls staged per warp -- right for coherent sets (sorted by patch, tessellation grids) and for
@@ -477,6 +491,7 @@ int b200osd_patch_plan_eval(const b200osd_patch_plan *p, int which, const float 
     PatchShape shape;
     shape.maxPoints = std::max(tr->maxPoints, 3);
     shape.hasTri = tr->hasTri;
+    shape.options = p->table->options;
     PatchRoute route;
     route.perm = p->s.perm;
     route.state = p->s.state;
@@ -573,6 +588,7 @@ b200osd_stencil_table *b200osd_limit_stencil_table_create(const b200osd_patch_ta
     io.arrays = tr.arrays;
     io.patchIndices = tr.indices;
     io.params = tr.params;
+    io.options = pt->options;
     io.numControlVertices = b200osd_stencil_table_num_control_vertices(cvStencils);
     io.cvSizes = static_cast<const int *>(b200osd_stencil_table_buffer(cvStencils, 0));
     io.cvOffsets = static_cast<const int *>(b200osd_stencil_table_buffer(cvStencils, 1));
@@ -640,5 +656,13 @@ b200osd_stencil_table *b200osd_limit_stencil_table_create(const b200osd_patch_ta
 
 void b200osd_patch_table_set_variant(b200osd_patch_table *t, int variant) { if (t) t->variant = variant; }
 int b200osd_patch_table_get_variant(const b200osd_patch_table *t) { return t ? t->variant : 0; }
+
+int b200osd_patch_table_set_options(b200osd_patch_table *t, int options) {
+    if (!t) { set_error("patch table is NULL"); return B200OSD_ERR_INVALID; }
+    if (options & ~B200OSD_PATCH_GREGORY_TRUE_DERIVATIVES) { set_error("patch_table_set_options: unknown option bits 0x%x", options); return B200OSD_ERR_INVALID; }
+    t->options = options;
+    return B200OSD_OK;
+}
+int b200osd_patch_table_get_options(const b200osd_patch_table *t) { return t ? t->options : 0; }
 
 }  // extern "C"

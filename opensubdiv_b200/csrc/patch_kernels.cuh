@@ -66,7 +66,13 @@ struct PatchIO {
     int warpWords;
     int coordWords;                   // offset (floats) of the warp's 160-word coordinate prefetch buffer inside its region
     int hullPitch;                    // floats between staged hulls (see hull_pitch / packed_pitch)
+    int options;                      // kPatchOptGregoryTrueDerivatives
 };
+
+// PatchIO::options / b200osd_patch_table_set_options.  Bit 0: the 8 interior points of GREGORY_BASIS patches get the true
+// derivative weights (quotient + product rule), what the reference computes when it is built with
+// OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES (osd/patchBasis.h:441-487); default is its approximation (:421-440).
+enum { kPatchOptGregoryTrueDerivatives = 1 };
 
 enum { PT_QUADS = 3, PT_TRIANGLES = 4, PT_LOOP = 5, PT_REGULAR = 6, PT_GREGORY_BASIS = 9, PT_GREGORY_TRIANGLE = 10 };
 
@@ -359,7 +365,7 @@ B200_HD void eval_regular(const CV &cv, float s, float t, int boundary,
 // (osd/patchBasis.h:345-378); the reciprocal is replaced by 1 when a+b <= 0.  Derivatives use the reference's
 // default approximation: Bezier derivative weights times the same G (osd/patchBasis.h:421-440).
 template <int LT, int ORDER, typename CV>
-B200_HD void eval_gregory(const CV &cv, float s, float t, float d1,
+B200_HD void eval_gregory(const CV &cv, float s, float t, float d1, bool trueDerivatives,
                           float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     constexpr int COL[20] = { 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2, 0, 0, 1, 1, 1 };
     constexpr int ROW[20] = { 0, 0, 1, 1, 1, 0, 1, 0, 1, 1, 3, 3, 2, 2, 2, 3, 2, 3, 2, 2 };
@@ -367,7 +373,7 @@ B200_HD void eval_gregory(const CV &cv, float s, float t, float d1,
     bezier_1d<ORDER>(s, bs, ds, dss);
     bezier_1d<ORDER>(t, bt, dt, dtt);
     const float sc = 1.0f - s, tc = 1.0f - t;
-    float G[8];
+    float G[8], R[4];
     {
         const float a[4] = { s, t, sc, tc };
         const float den[4] = { s + t, sc + t, sc + tc, s + tc };
@@ -376,10 +382,11 @@ B200_HD void eval_gregory(const CV &cv, float s, float t, float d1,
             const float r = (den[c] <= 0.0f) ? 1.0f : rcp_rn(den[c]);
             G[2 * c] = a[c] * r;
             G[2 * c + 1] = 1.0f - G[2 * c];
+            R[c] = r;
         }
     }
+    const float d2 = d1 * d1;
     if (ORDER >= 1) {
-        const float d2 = d1 * d1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             ds[j] *= d1; dt[j] *= d1;
@@ -400,8 +407,32 @@ B200_HD void eval_gregory(const CV &cv, float s, float t, float d1,
         const float gs = bs[col] * g, gt = bt[row];
         float w[NSETS];
         w[0] = gs * gt;
-        if (ORDER >= 1) { w[1] = ds[col] * g * gt; w[2] = gs * dt[row]; }
-        if (ORDER >= 2) { w[3] = dss[col] * g * gt; w[4] = ds[col] * g * dt[row]; w[5] = gs * dtt[row]; }
+        if (ORDER >= 1 && p >= 3 && trueDerivatives) {
+            // G = N / D with constant N', D' (osd/patchBasis.h:441-487); ds.. are already scaled by d1, so G' takes d1 too
+            constexpr float NDS[8] = { 1.0f, 0.0f, 0.0f, -1.0f, -1.0f, 0.0f, 0.0f, 1.0f };
+            constexpr float NDT[8] = { 0.0f, 1.0f, 1.0f, 0.0f, 0.0f, -1.0f, -1.0f, 0.0f };
+            constexpr float DDS[8] = { 1.0f, 1.0f, -1.0f, -1.0f, -1.0f, -1.0f, 1.0f, 1.0f };
+            constexpr float DDT[8] = { 1.0f, 1.0f, 1.0f, 1.0f, -1.0f, -1.0f, -1.0f, -1.0f };
+            const int k = 2 * (i / 5) + (p - 3);
+            const float D = R[i / 5];
+            const float Gds = (NDS[k] - DDS[k] * g) * D * d1, Gdt = (NDT[k] - DDT[k] * g) * D * d1;
+            const float ws = ds[col] * g + bs[col] * Gds;          // d/ds (Bs G)
+            const float wt = dt[row] * g + bt[row] * Gdt;          // d/dt (Bt G)
+            w[1] = ws * bt[row];
+            w[2] = wt * bs[col];
+            if (ORDER >= 2) {
+                const float Dsq = D * D * d2;
+                const float Gdss = 2.0f * DDS[k] * Dsq * (g * DDS[k] - NDS[k]);
+                const float Gdst = Dsq * (2.0f * g * DDS[k] * DDT[k] - NDS[k] * DDT[k] - NDT[k] * DDS[k]);
+                const float Gdtt = 2.0f * DDT[k] * Dsq * (g * DDT[k] - NDT[k]);
+                w[3] = (dss[col] * g + 2.0f * ds[col] * Gds + bs[col] * Gdss) * bt[row];
+                w[4] = bt[row] * (bs[col] * Gdst + ds[col] * Gdt) + dt[row] * ws;
+                w[5] = (dtt[row] * g + 2.0f * dt[row] * Gdt + bt[row] * Gdtt) * bs[col];
+            }
+        } else {
+            if (ORDER >= 1) { w[1] = ds[col] * g * gt; w[2] = gs * dt[row]; }
+            if (ORDER >= 2) { w[3] = dss[col] * g * gt; w[4] = ds[col] * g * dt[row]; w[5] = gs * dtt[row]; }
+        }
 #pragma unroll
         for (int k = 0; k < NSETS; ++k)
 #pragma unroll
@@ -664,14 +695,15 @@ B200_HD_NOINLINE int tri_weights(int type, float s, float t, int boundary, float
 }
 
 // --------------------------------------------------------------------------------------- kernel --
-// TRI = false drops the triangle types (their code and local-memory frame) from the instantiation.
+// TRI = true is the general instantiation (128 registers): the triangle types and the optional evaluation modes
+// (PatchIO::options).  TRI = false keeps REGULAR / GREGORY_BASIS / QUADS in their default form at 72 registers.
 template <int LT, int ORDER, bool TRI, typename CV>
-B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int boundary, float d1, float sign,
+B200_HD void eval_patch_type(const CV &cv, int type, float s, float t, int boundary, float d1, float sign, int options,
                              float (&out)[ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6)][LT]) {
     if (type == PT_REGULAR) {
         eval_regular<LT, ORDER>(cv, s, t, boundary, d1, out);
     } else if (type == PT_GREGORY_BASIS) {
-        eval_gregory<LT, ORDER>(cv, s, t, d1, out);
+        eval_gregory<LT, ORDER>(cv, s, t, d1, TRI && (options & kPatchOptGregoryTrueDerivatives) != 0, out);
     } else if (type == PT_QUADS) {
         eval_quads<LT, ORDER>(cv, s, t, d1, out);
     } else if (TRI && type == PT_LOOP) {
@@ -743,7 +775,7 @@ B200_HD void patch_eval_coord(const PatchIO &io, int i) {
     cv.src = io.src;
     cv.stride = io.srcStride;
     cv.cvs = io.indices + ps.cvOffset;
-    eval_patch_type<LT, ORDER, true>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, out);
+    eval_patch_type<LT, ORDER, true>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, io.options, out);
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) {
         float *d = io.dst[k];
@@ -1010,7 +1042,7 @@ __global__ void __launch_bounds__(kPatchBlock, TRI ? 4 : 7) patch_run_kernel(Pat
             if (live && slot >= base && slot < base + kHullSlots) {
                 CvStaged cv;
                 cv.row = st + (slot - base) * pitch;
-                eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, out);
+                eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, io.options, out);
             }
             __syncwarp();                                       // the next round (or the result staging) overwrites the rows
         }
@@ -1053,7 +1085,7 @@ __global__ void __launch_bounds__(kPatchBlock, 8) patch_direct_kernel(PatchIO io
             cv.src = io.src;
             cv.stride = io.srcStride;
             cv.cvs = io.indices + ps.cvOffset;
-            eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, out);
+            eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, io.options, out);
         }
         store_outputs<LT, NSETS>(io, st, lc.i, lc.live, !grouped, out);
     }
@@ -1122,7 +1154,7 @@ __global__ void __launch_bounds__(kPatchBlock, TRI ? 4 : 6) patch_hull_kernel(Pa
             CvPacked cv;
             cv.base = hull + (size_t)ps.cvOffset * LT;
             cv.aligned = ((size_t)ps.cvOffset * LT) % 4 == 0;   // the cache itself is 256-byte aligned
-            eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, out);
+            eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, io.options, out);
         }
         store_outputs<LT, NSETS>(io, st, lc.i, lc.live, true, out);
     }

@@ -29,6 +29,7 @@ PATCH_COORD_DTYPE = np.dtype([("arrayIndex", "<i4"), ("patchIndex", "<i4"), ("ve
 PATCH_ARRAY_DTYPE = np.dtype([("regDesc", "<i4"), ("desc", "<i4"), ("numPatches", "<i4"),
                               ("indexBase", "<i4"), ("stride", "<i4"), ("primitiveIdBase", "<i4")])  # :66-122
 PATCH_PARAM_DTYPE = np.dtype([("field0", "<u4"), ("field1", "<u4"), ("sharpness", "<f4")])           # :127-130
+PATCH_GREGORY_TRUE_DERIVATIVES = 1          # B200OSD_PATCH_GREGORY_TRUE_DERIVATIVES (include/b200osd_capi.h)
 
 
 @dataclass(frozen=True)
@@ -302,6 +303,17 @@ class B200PatchTable:
     def GetVariant(self) -> int:
         return capi.lib().b200osd_patch_table_get_variant(self._h)
 
+    def SetGregoryTrueDerivatives(self, on: bool = True) -> None:
+        """The reference's build option OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES (osd/patchBasis.h:421-487) as a per-table
+        run-time option: derivative weights of the interior points of GREGORY_BASIS patches by quotient + product rule
+        instead of the default approximation.  Applies to EvalPatches* through this table and to CreateLimitStencils."""
+        if not capi.check(capi.lib().b200osd_patch_table_set_options(self._h, PATCH_GREGORY_TRUE_DERIVATIVES if on else 0),
+                          "B200PatchTable::SetGregoryTrueDerivatives"):
+            raise capi.B200OsdError(capi.last_error())
+
+    def GetGregoryTrueDerivatives(self) -> bool:
+        return bool(capi.lib().b200osd_patch_table_get_options(self._h) & PATCH_GREGORY_TRUE_DERIVATIVES)
+
 
 class B200PatchMap:
     """Device-resident Far::PatchMap (far/patchMap.h:48-217): locates (ptexFace, s, t) samples in the patches of a
@@ -526,15 +538,16 @@ class B200Evaluator:
 
     # ----------------------------------------------------------------------------- patches --
     @staticmethod
-    def _eval_patches(srcBuffer, srcDesc, outs, numPatchCoords, patchCoords, arrays, indices, params, deviceContext) -> bool:
+    def _eval_patches(srcBuffer, srcDesc, outs, numPatchCoords, patchCoords, arrays, indices, params, deviceContext,
+                      options: int = 0) -> bool:
         n = len(outs)
         if n not in (1, 3, 6):
             raise TypeError("EvalPatches expects 1, 3 or 6 (buffer, descriptor) outputs")
         sd = _desc(srcDesc).as_c()
         dsts = (C.c_void_p * n)(*[_dev_ptr(b) for b, _ in outs])
         dds = (C.c_int * (3 * n))(*[v for _, d in outs for v in (d.offset, d.length, d.stride)])
-        rc = capi.lib().b200osd_eval_patches(_dev_ptr(srcBuffer), sd, n, dsts, dds, numPatchCoords, _dev_ptr(patchCoords),
-                                             arrays, indices, params, _stream_ptr(deviceContext))
+        rc = capi.lib().b200osd_eval_patches_ex(_dev_ptr(srcBuffer), sd, n, dsts, dds, numPatchCoords, _dev_ptr(patchCoords),
+                                                arrays, indices, params, options, _stream_ptr(deviceContext))
         return capi.check(rc, "B200Evaluator::EvalPatches")
 
     @staticmethod
@@ -608,11 +621,13 @@ class B200Evaluator:
 
     @staticmethod
     def EvalPatchesRaw(src, srcDesc, outs: Sequence, numPatchCoords, patchCoords, patchArrays, patchIndices, patchParams,
-                       deviceContext=None) -> bool:
-        """Raw-pointer overloads (osd/cudaEvaluator.h:706-713,752-761,815-827)."""
+                       deviceContext=None, gregory_true_derivatives: bool = False) -> bool:
+        """Raw-pointer overloads (osd/cudaEvaluator.h:706-713,752-761,815-827).  gregory_true_derivatives: what the
+        reference does when built with OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES (b200osd_eval_patches_ex)."""
         outs = [(b, _desc(d)) for b, d in outs]
         return B200Evaluator._eval_patches(src, srcDesc, outs, numPatchCoords, patchCoords, _dev_ptr(patchArrays),
-                                           _dev_ptr(patchIndices), _dev_ptr(patchParams), deviceContext)
+                                           _dev_ptr(patchIndices), _dev_ptr(patchParams), deviceContext,
+                                           PATCH_GREGORY_TRUE_DERIVATIVES if gregory_true_derivatives else 0)
 
     @staticmethod
     def Synchronize(deviceContext=None) -> None:

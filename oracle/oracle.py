@@ -50,6 +50,7 @@ def lib64():
         L.oracle_eval_stencils.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
         L.oracle_eval_patches.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
         L.oracle_set_abs_mode.argtypes = [C.c_int]
+        L.oracle_set_gregory_true_derivatives.argtypes = [C.c_int]
         _lib64 = L
     return _lib64
 
@@ -88,6 +89,7 @@ def lib():
         L.oracle_patch_basis.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_float] + [vp] * 6
         L.oracle_version.restype = C.c_char_p
         L.oracle_set_abs_mode.argtypes = [C.c_int]
+        L.oracle_set_gregory_true_derivatives.argtypes = [C.c_int]
         L.oracle_patch_map_create.restype = vp
         L.oracle_patch_map_create.argtypes = [C.c_int, vp, C.c_int, vp, C.c_int]
         L.oracle_patch_map_find.argtypes = [vp, C.c_int, vp, vp, vp, vp]
@@ -142,6 +144,19 @@ def patch_basis(patch_type: int, field0: int, field1: int, s: float, t: float, n
     ptrs = [_p(x) for x in w[:nw]] + [None] * (6 - nw)
     n = lib().oracle_patch_basis(patch_type, int(field0) & 0xFFFFFFFF, int(field1) & 0xFFFFFFFF, s, t, *ptrs)
     return n, w[:nw]
+
+
+class gregory_true_derivatives:
+    """Context manager: inside it the Gregory basis uses the reference's OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES form
+    (osd/patchBasis.h:441-487) in every entry of the fp32 oracle (patch_basis, eval_patches, limit_stencil_table)."""
+
+    def __enter__(self):
+        lib().oracle_set_gregory_true_derivatives(1)
+        lib64().oracle_set_gregory_true_derivatives(1)
+
+    def __exit__(self, *exc):
+        lib().oracle_set_gregory_true_derivatives(0)
+        lib64().oracle_set_gregory_true_derivatives(0)
 
 
 class abs_mode:

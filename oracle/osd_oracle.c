@@ -268,13 +268,21 @@ static int basis_regular(real s, real t, int boundary, real *w[6], int order)
  * carry the rational blend G: with (a,b) the distances from corner c along its E+ / E- directions,
  * G+ = a/(a+b) and G- = 1 - G+ (so each pair sums to one exactly); when a+b <= 0 the reciprocal is
  * replaced by 1 (:369-372).  Derivatives use the reference's default approximation (:421-440): the
- * Bezier derivative weights times the same G (OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES is off).  */
+ * Bezier derivative weights times the same G; with oracle_set_gregory_true_derivatives(1) they follow the
+ * reference's OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES build instead (:441-487): quotient rule for G = N/D
+ * (N' and D' are the constants below), product rule for B*G.  Pinned against oracle/_ref/libosdref_td.so.  */
+static int g_gregory_true = 0;
+void oracle_set_gregory_true_derivatives(int on) { g_gregory_true = on; }
+static const real GREG_NDS[8] = { 1.0f, 0.0f,  0.0f, -1.0f, -1.0f,  0.0f,  0.0f,  1.0f };
+static const real GREG_NDT[8] = { 0.0f, 1.0f,  1.0f,  0.0f,  0.0f, -1.0f, -1.0f,  0.0f };
+static const real GREG_DDS[8] = { 1.0f, 1.0f, -1.0f, -1.0f, -1.0f, -1.0f,  1.0f,  1.0f };
+static const real GREG_DDT[8] = { 1.0f, 1.0f,  1.0f,  1.0f, -1.0f, -1.0f, -1.0f, -1.0f };
 static const signed char GREG_COL[20] = { 0, 1, 0, 1, 1,   3, 3, 2, 2, 2,   3, 2, 3, 2, 2,   0, 0, 1, 1, 1 };
 static const signed char GREG_ROW[20] = { 0, 0, 1, 1, 1,   0, 1, 0, 1, 1,   3, 3, 2, 2, 2,   3, 2, 3, 2, 2 };
 
 static int basis_gregory(real s, real t, real *w[6], int order)
 {
-    real bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4], G[8];
+    real bs[4], bt[4], ds[4], dt[4], dss[4], dtt[4], G[8], R[4];
     real sc = 1.0f - s, tc = 1.0f - t;
     real a[4], b[4];
     int c, i;
@@ -290,13 +298,33 @@ static int basis_gregory(real s, real t, real *w[6], int order)
         real r = (d <= 0.0f) ? 1.0f : (1.0f / d);
         G[2 * c] = a[c] * r;
         G[2 * c + 1] = 1.0f - a[c] * r;
+        R[c] = r;
         (void)b;
     }
     for (i = 0; i < 20; ++i) {
         int col = GREG_COL[i], row = GREG_ROW[i], p = i % 5;
         int rational = (p >= 3);
         real g = rational ? G[2 * (i / 5) + (p - 3)] : 1.0f;
-        if (rational) {
+        if (rational && g_gregory_true) {
+            int k = 2 * (i / 5) + (p - 3);
+            real D = R[i / 5];
+            w[0][i] = bs[col] * bt[row] * g;
+            if (order >= 1) {
+                real Gds = (GREG_NDS[k] - GREG_DDS[k] * g) * D;
+                real Gdt = (GREG_NDT[k] - GREG_DDT[k] * g) * D;
+                w[1][i] = (ds[col] * g + bs[col] * Gds) * bt[row];
+                w[2][i] = (dt[row] * g + bt[row] * Gdt) * bs[col];
+                if (order >= 2) {
+                    real Dsqr_inv = D * D;
+                    real Gdss = 2.0f * GREG_DDS[k] * Dsqr_inv * (g * GREG_DDS[k] - GREG_NDS[k]);
+                    real Gdst = Dsqr_inv * (2.0f * g * GREG_DDS[k] * GREG_DDT[k] - GREG_NDS[k] * GREG_DDT[k] - GREG_NDT[k] * GREG_DDS[k]);
+                    real Gdtt = 2.0f * GREG_DDT[k] * Dsqr_inv * (g * GREG_DDT[k] - GREG_NDT[k]);
+                    w[3][i] = (dss[col] * g + 2.0f * ds[col] * Gds + bs[col] * Gdss) * bt[row];
+                    w[4][i] = bt[row] * (bs[col] * Gdst + ds[col] * Gdt) + dt[row] * (ds[col] * g + bs[col] * Gds);
+                    w[5][i] = (dtt[row] * g + 2.0f * dt[row] * Gdt + bt[row] * Gdtt) * bs[col];
+                }
+            }
+        } else if (rational) {
             w[0][i] = bs[col] * bt[row] * g;
             if (order >= 1) {
                 w[1][i] = ds[col] * bt[row] * g;

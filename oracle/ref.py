@@ -9,6 +9,7 @@ import this module; the product (opensubdiv_b200/) never does.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from dataclasses import dataclass, field
@@ -18,6 +19,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libosdref.so")
+# the same sources compiled with -DOPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES (oracle/ref/Makefile)
+LIB_PATH_TD = os.path.join(_HERE, "_ref", "libosdref_td.so")
 
 # numpy mirrors of the Osd POD types (osd/types.h:42-130, osd/patchBasisTypes.h:249-288)
 PATCH_COORD_DTYPE = np.dtype([("arrayIndex", "<i4"), ("patchIndex", "<i4"), ("vertIndex", "<i4"),
@@ -26,20 +29,37 @@ PATCH_ARRAY_DTYPE = np.dtype([("regDesc", "<i4"), ("desc", "<i4"), ("numPatches"
                               ("indexBase", "<i4"), ("stride", "<i4"), ("primitiveIdBase", "<i4")])
 PATCH_PARAM_DTYPE = np.dtype([("field0", "<u4"), ("field1", "<u4"), ("sharpness", "<f4")])
 
-_lib = None
+_libs = {}
+_active = LIB_PATH
 
 
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
+def true_derivatives_available() -> bool:
+    return os.path.exists(LIB_PATH_TD)
+
+
+@contextlib.contextmanager
+def true_derivatives():
+    """Inside this context every call goes to the reference built with OPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES.
+    Handles (Mesh, tables) stay with the library that made them: create and use them inside the same context."""
+    global _active
+    prev, _active = _active, LIB_PATH_TD
+    try:
+        yield
+    finally:
+        _active = prev
+
+
 def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not available():
-        raise RuntimeError(f"{LIB_PATH} not built (make -C oracle/ref needs /root/reference)")
-    L = C.CDLL(LIB_PATH)
+    path = _active
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not built (make -C oracle/ref needs /root/reference)")
+    L = C.CDLL(path)
     vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
     L.ref_shape_name.restype = C.c_char_p
     L.ref_mesh_from_shape.restype = vp
@@ -96,7 +116,7 @@ def lib():
     L.ref_osd_patch_basis.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float] + [vp] * 6
     L.ref_omp_set_threads.argtypes = [C.c_int]
     L.ref_version.restype = C.c_char_p
-    _lib = L
+    _libs[path] = L
     return L
 
 

@@ -26,9 +26,9 @@ static void run(const PatchIO &io, int LT) {
 }
 
 extern "C" __attribute__((visibility("default")))
-int emu_eval_patches(const float *src, const int srcDesc[3], int nOut, float *const dsts[], const int dstDescs[][3],
-                     int n, const b200osd_patch_coord *coords, const b200osd_patch_array *arrays, const int *indices,
-                     const b200osd_patch_param *params) {
+int emu_eval_patches_ex(const float *src, const int srcDesc[3], int nOut, float *const dsts[], const int dstDescs[][3],
+                        int n, const b200osd_patch_coord *coords, const b200osd_patch_array *arrays, const int *indices,
+                        const b200osd_patch_param *params, int options) {
     const int L = srcDesc[1];
     for (int c0 = 0; c0 < L; c0 += 4) {
         const int LT = (L - c0) < 4 ? (L - c0) : 4;
@@ -39,10 +39,17 @@ int emu_eval_patches(const float *src, const int srcDesc[3], int nOut, float *co
         for (int k = 0; k < nOut; ++k)
             if (dsts[k]) { io.dst[k] = dsts[k] + dstDescs[k][0] + c0; io.dstStride[k] = dstDescs[k][2]; }
         io.packed = 0; io.vecStore = 0; io.perm = nullptr; io.binState = nullptr; io.warpWords = 0; io.coordWords = 0; io.hullPitch = 0;
-        io.n = n; io.coords = coords; io.arrays = arrays; io.indices = indices; io.params = params;
+        io.n = n; io.coords = coords; io.arrays = arrays; io.indices = indices; io.params = params; io.options = options;
         if (nOut == 1) run<0>(io, LT); else if (nOut == 3) run<1>(io, LT); else run<2>(io, LT);
     }
     return 0;
+}
+
+extern "C" __attribute__((visibility("default")))
+int emu_eval_patches(const float *src, const int srcDesc[3], int nOut, float *const dsts[], const int dstDescs[][3],
+                     int n, const b200osd_patch_coord *coords, const b200osd_patch_array *arrays, const int *indices,
+                     const b200osd_patch_param *params) {
+    return emu_eval_patches_ex(src, srcDesc, nOut, dsts, dstDescs, n, coords, arrays, indices, params, 0);
 }
 
 // ---- patch map: the library's host builder + the kernel's descent, run on the CPU (test-only) --------------------

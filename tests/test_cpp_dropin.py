@@ -38,5 +38,7 @@ def test_every_cpp_header_is_self_sufficient():
     if not os.path.isdir("/root/reference/opensubdiv") or not shutil.which("g++"):
         pytest.skip("reference sources or g++ not present")
     for h in sorted(glob.glob(os.path.join(ROOT, "include", "b200osd", "*.h"))):
-        subprocess.check_call(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-Werror", "-x", "c++", "-I/root/reference",
-                               "-I" + os.path.join(ROOT, "include"), h])
+        # also the way a client of a -DOPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES=ON reference build compiles them
+        for extra in ([], ["-DOPENSUBDIV_GREGORY_EVAL_TRUE_DERIVATIVES"]):
+            subprocess.check_call(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-Werror", "-x", "c++", "-I/root/reference",
+                                   "-I" + os.path.join(ROOT, "include"), h] + extra)
