@@ -28,6 +28,18 @@ public:
         return wrap(make(t->GetNumStencils(), t->GetNumControlVertices(), t->GetSizes(), t->GetOffsets(), t->GetControlIndices(), t->GetWeights(),
                          &t->GetDuWeights(), &t->GetDvWeights(), &t->GetDuuWeights(), &t->GetDuvWeights(), &t->GetDvvWeights()));
     }
+    /// From a table that already lives on the device in the reference layout, e.g. an Osd::CudaStencilTable
+    /// (osd/cudaEvaluator.h:57-90): anything with GetSizesBuffer() ... GetWeightsBuffer() [, GetDuWeightsBuffer() ...]
+    /// returning device pointers.  One conversion; afterwards EvalStencils runs on the bucketed layout.
+    template <typename DEVICE_STENCIL_TABLE>
+    static B200StencilTable *CreateFromDevice(DEVICE_STENCIL_TABLE const *t, int numControlVertices = 0) {
+        if (!t) return NULL;
+        return wrap(b200osd_stencil_table_create_from_device(
+            t->GetNumStencils(), numControlVertices, (const int *)t->GetSizesBuffer(), (const int *)t->GetOffsetsBuffer(),
+            (const int *)t->GetIndicesBuffer(), (const float *)t->GetWeightsBuffer(), (const float *)t->GetDuWeightsBuffer(),
+            (const float *)t->GetDvWeightsBuffer(), (const float *)t->GetDuuWeightsBuffer(),
+            (const float *)t->GetDuvWeightsBuffer(), (const float *)t->GetDvvWeightsBuffer(), 0));
+    }
     ~B200StencilTable() { b200osd_stencil_table_destroy(_h); }
 
     // interfaces needed by the evaluator templates (device pointers, reference layout)

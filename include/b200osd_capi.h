@@ -118,6 +118,15 @@ B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
         const int *sizes, const int *offsets, const int *indices, const float *weights,
         const float *duWeights, const float *dvWeights,
         const float *duuWeights, const float *duvWeights, const float *dvvWeights, int flags);
+/* The same from DEVICE arrays in the reference layout -- what a client holds that already built an Osd::CudaStencilTable
+ * (osd/cudaEvaluator.h:57-90: GetSizesBuffer() ... GetDvvWeightsBuffer()).  Instead of evaluating those arrays row by row
+ * through b200osd_eval_stencils (thread per row, ~55 % of the roofline), convert once and evaluate through the table.
+ * Synchronous; the client's arrays are only read. */
+B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create_from_device(
+        int numStencils, int numControlVertices,
+        const int *sizes, const int *offsets, const int *indices, const float *weights,
+        const float *duWeights, const float *dvWeights,
+        const float *duuWeights, const float *duvWeights, const float *dvvWeights, int flags);
 B200OSD_API void b200osd_stencil_table_destroy(b200osd_stencil_table *t);
 B200OSD_API int  b200osd_stencil_table_num_stencils(const b200osd_stencil_table *t);
 B200OSD_API int  b200osd_stencil_table_num_control_vertices(const b200osd_stencil_table *t);

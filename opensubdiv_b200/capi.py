@@ -20,7 +20,7 @@ SYMBOLS = [
     "b200osd_vertex_buffer_create", "b200osd_vertex_buffer_destroy", "b200osd_vertex_buffer_num_elements",
     "b200osd_vertex_buffer_num_vertices", "b200osd_vertex_buffer_bind", "b200osd_vertex_buffer_update",
     "b200osd_vertex_buffer_read",
-    "b200osd_stencil_table_create", "b200osd_stencil_table_destroy", "b200osd_stencil_table_num_stencils",
+    "b200osd_stencil_table_create", "b200osd_stencil_table_create_from_device", "b200osd_stencil_table_destroy", "b200osd_stencil_table_num_stencils",
     "b200osd_stencil_table_num_control_vertices", "b200osd_stencil_table_num_elements",
     "b200osd_stencil_table_is_factorized",
     "b200osd_stencil_table_buffer", "b200osd_stencil_table_stream_bytes", "b200osd_stencil_table_eval",
@@ -76,6 +76,8 @@ def lib():
     L.b200osd_vertex_buffer_read.argtypes = [vp, vp, i, i, vp]
     L.b200osd_stencil_table_create.restype = vp
     L.b200osd_stencil_table_create.argtypes = [i, i] + [vp] * 9 + [i]
+    L.b200osd_stencil_table_create_from_device.restype = vp
+    L.b200osd_stencil_table_create_from_device.argtypes = [i, i] + [vp] * 9 + [i]
     L.b200osd_stencil_table_destroy.argtypes = [vp]
     L.b200osd_stencil_table_num_stencils.argtypes = [vp]
     L.b200osd_stencil_table_num_control_vertices.argtypes = [vp]

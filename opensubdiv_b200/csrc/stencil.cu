@@ -636,6 +636,39 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, int numCont
     return t;
 }
 
+b200osd_stencil_table *b200osd_stencil_table_create_from_device(int numStencils, int numControlVertices, const int *sizes,
+                                                                const int *offsets, const int *indices, const float *weights,
+                                                                const float *du, const float *dv, const float *duu,
+                                                                const float *duv, const float *dvv, int flags) {
+    if (numStencils < 0 || (numStencils > 0 && (!sizes || !offsets || !indices || !weights))) {
+        set_error("stencil_table_create_from_device: missing arrays");
+        return nullptr;
+    }
+    // one read-back of the client's arrays (an Osd::CudaStencilTable keeps no host copy), then the ordinary create
+    std::vector<int> hs((size_t)numStencils), ho((size_t)numStencils);
+    auto pull = [](void *dst, const void *src, size_t bytes) { return bytes == 0 || cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
+    bool ok = pull(hs.data(), sizes, hs.size() * 4) && pull(ho.data(), offsets, ho.size() * 4);
+    long long ne = 0;
+    for (int i = 0; ok && i < numStencils; ++i) {
+        if (hs[(size_t)i] < 0 || ho[(size_t)i] < 0) { set_error("stencil_table_create_from_device: negative size / offset in row %d", i); return nullptr; }
+        ne = std::max<long long>(ne, (long long)ho[(size_t)i] + hs[(size_t)i]);
+    }
+    std::vector<int> hi((size_t)ne);
+    const float *dw[kMaxOut] = { weights, du, dv, duu, duv, dvv };
+    std::vector<std::vector<float>> hw(kMaxOut);
+    const float *hp[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    ok = ok && pull(hi.data(), indices, hi.size() * 4);
+    for (int k = 0; ok && k < kMaxOut; ++k) {
+        if (!dw[k]) continue;
+        hw[(size_t)k].resize((size_t)ne);
+        ok = pull(hw[(size_t)k].data(), dw[k], (size_t)ne * 4);
+        hp[k] = hw[(size_t)k].data();
+    }
+    if (!ok) { set_error("stencil_table_create_from_device: read-back failed: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
+    return b200osd_stencil_table_create(numStencils, numControlVertices, hs.data(), ho.data(), hi.data(), hp[0], hp[1], hp[2],
+                                        hp[3], hp[4], hp[5], flags);
+}
+
 void b200osd_stencil_table_destroy(b200osd_stencil_table *t) {
     if (!t) return;
     cudaFree(t->d_sizes); cudaFree(t->d_offsets); cudaFree(t->d_indices);

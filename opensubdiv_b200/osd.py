@@ -172,6 +172,19 @@ class B200StencilTable:
         return cls(h) if h else None
 
     @classmethod
+    def CreateFromDevice(cls, numStencils: int, sizes, offsets, indices, weights, du=None, dv=None, duu=None, duv=None,
+                         dvv=None, numControlVertices: int = 0, keep_order: bool = False) -> Optional["B200StencilTable"]:
+        """From DEVICE arrays in the reference layout (the buffers of an Osd::CudaStencilTable, osd/cudaEvaluator.h:57-90):
+        one conversion to the bucketed layout instead of evaluating the raw arrays row by row (EvalStencilsRaw)."""
+        p = lambda a: None if a is None else _dev_ptr(a)
+        h = capi.lib().b200osd_stencil_table_create_from_device(int(numStencils), int(numControlVertices), p(sizes), p(offsets),
+                                                                p(indices), p(weights), p(du), p(dv), p(duu), p(duv), p(dvv),
+                                                                16 if keep_order else 0)
+        if not h:
+            raise capi.B200OsdError("B200StencilTable::CreateFromDevice: " + capi.last_error())
+        return cls(h)
+
+    @classmethod
     def CreateLimitStencils(cls, patchTable, cvStencilTable, numLocations: int, patchCoords, numWeightSets: int = 6,
                             bucketed: bool = True, deviceContext=None) -> Optional["B200StencilTable"]:
         """Far::LimitStencilTableFactory::Create on the DEVICE (far/stencilTableFactory.cpp:559-662): patchCoords are located

@@ -306,6 +306,20 @@ static void limitCase(const char *name, std::string const &str, Scheme scheme) {
             for (int c = 0; c < 3; ++c) { x[3 * i + c] = out[18 * i + c]; y[3 * i + c] = cout->BindCpuBuffer()[18 * i + c]; }
         report("EvalStencils raw overload (reference-layout arrays)", maxRelDiff(&x[0], &y[0], x.size()), 1e-6);
     }
+    // a table that already lives on the device in the reference layout (what an Osd::CudaStencilTable is) converted once
+    {
+        Osd::B200StencilTable *conv = Osd::B200StencilTable::CreateFromDevice(gtab, nCV);
+        Osd::B200VertexBuffer *gout2 = Osd::B200VertexBuffer::Create(18, n);
+        Osd::B200Evaluator::EvalStencils(gsrc, src, gout, p, gout, du, gout, dv, gout, duu, gout, duv, gout, dvv, gtab);
+        Osd::B200Evaluator::EvalStencils(gsrc, src, gout2, p, gout2, du, gout2, dv, gout2, duu, gout2, duv, gout2, dvv, conv);
+        std::vector<float> out2((size_t)n * 18);
+        gout->ReadData(&out[0], 0, n);
+        gout2->ReadData(&out2[0], 0, n);
+        Osd::B200Evaluator::Synchronize();
+        report("EvalStencils through CreateFromDevice(device arrays) vs Create(Far table), bitwise",
+               conv && std::memcmp(&out[0], &out2[0], out.size() * sizeof(float)) == 0 ? 0.0 : 1.0, 0.0);
+        delete conv; delete gout2;
+    }
     delete gtab; delete csrc; delete cout; delete gsrc; delete gout; delete lst; delete refiner;
 }
 

@@ -92,6 +92,23 @@ def test_limit_stencils_with_derivatives(name, nw):
                                              tbl.GetOffsetsBuffer(), tbl.GetIndicesBuffer(), ws, 0, n)
     for k in range(nw):
         assert_close(outs[k].cpu().numpy(), d["out_" + OUT6[k]], scales[k], f"{name} raw {OUT6[k]}")
+    # a client that only holds those device arrays (an Osd::CudaStencilTable) converts them once and gets the fast path:
+    # bit-identical to the table created from the host arrays
+    ws9 = [tbl.GetWeightsBuffer(), tbl.GetDuWeightsBuffer(), tbl.GetDvWeightsBuffer(), tbl.GetDuuWeightsBuffer(),
+           tbl.GetDuvWeightsBuffer(), tbl.GetDvvWeightsBuffer()]
+    ws9 = [w if k < nw else None for k, w in enumerate(ws9)]
+    tbl2 = osd.B200StencilTable.CreateFromDevice(n, tbl.GetSizesBuffer(), tbl.GetOffsetsBuffer(), tbl.GetIndicesBuffer(), *ws9,
+                                                 numControlVertices=t.num_control_verts)
+    assert tbl2.GetNumStencils() == n
+    a = torch.full((n, 3 * nw), float("nan"), device="cuda")
+    b = torch.full((n, 3 * nw), float("nan"), device="cuda")
+    aa, bb = [], []
+    for k in range(nw):
+        aa += [a, D(3 * k, 3, 3 * nw)]
+        bb += [b, D(3 * k, 3, 3 * nw)]
+    assert osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), *aa, tbl)
+    assert osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), *bb, tbl2)
+    assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("L,stride,offset", [(1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (5, 5, 0), (6, 6, 0), (8, 8, 0),
