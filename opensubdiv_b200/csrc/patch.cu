@@ -242,7 +242,7 @@ int eval_patches_common(const float *src, const int srcDesc[3], int nOut, float 
         }
         io.hullPitch = hull_pitch(LT, shape.maxPoints);
         io.coordWords = (std::max(outWords, kHullSlots * io.hullPitch) + 3) & ~3;
-        io.warpWords = io.coordWords + 160;
+        io.warpWords = io.coordWords + 160 + 64;                // + (first index, points) of the tile's distinct patches
         rc = B200_PATCH_DISPATCH(launch_run, io, LT, st);
         if (rc) return rc;
     }

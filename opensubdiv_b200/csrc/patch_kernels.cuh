@@ -728,11 +728,10 @@ struct PatchSite {
     float s, t, d1, sign;
 };
 
-B200_HD void decode_patch_site(const PatchIO &io, int arrayIndex, int patchIndex, float s, float t, PatchSite &ps) {
-    const int *aw = reinterpret_cast<const int *>(io.arrays + arrayIndex);
-    const int regDesc = ldg_i(aw + 0), irrDesc = ldg_i(aw + 1);
-    const int indexBase = ldg_i(aw + 3), stride = ldg_i(aw + 4), primBase = ldg_i(aw + 5);
-    const unsigned field1 = ldg_u(&io.params[patchIndex].field1);
+// aw: the six ints of the coordinate's PatchArray, already fetched (registers, shared memory ...)
+B200_HD void decode_patch_site_arr(const int *aw, int patchIndex, float s, float t, unsigned field1, PatchSite &ps) {
+    const int regDesc = aw[0], irrDesc = aw[1];
+    const int indexBase = aw[3], stride = aw[4], primBase = aw[5];
     const int depth = (int)(field1 & 0xfu);
     const int nonquad = (int)((field1 >> 4) & 1u);
     const bool regular = ((field1 >> 5) & 1u) != 0;
@@ -753,6 +752,12 @@ B200_HD void decode_patch_site(const PatchIO &io, int arrayIndex, int patchIndex
         ps.t = fmaf(t, fracInv, -(float)pv);
     }
     ps.d1 = ps.sign * (float)(1 << depth);
+}
+
+B200_HD void decode_patch_site(const PatchIO &io, int arrayIndex, int patchIndex, float s, float t, PatchSite &ps) {
+    const int *g = reinterpret_cast<const int *>(io.arrays + arrayIndex);
+    const int aw[6] = { ldg_i(g + 0), ldg_i(g + 1), 0, ldg_i(g + 3), ldg_i(g + 4), ldg_i(g + 5) };
+    decode_patch_site_arr(aw, patchIndex, s, t, ldg_u(&io.params[patchIndex].field1), ps);
 }
 
 // One coordinate evaluated straight through the index buffer: the reference formulation, used by the host emulation
@@ -933,21 +938,105 @@ __device__ __forceinline__ LaneCoord gather_lane_coord(const PatchIO &io, long l
 constexpr int kHullSlots = 8;                                   // distinct hulls staged per round (4 passes of two)
 constexpr int kPatchModeDirect = 0, kPatchModeHull = 1, kPatchModeGrouped = 2;
 
-// Hulls staged per warp: one warp per 32 coordinates, persistent grid (a block walks tiles with a grid stride).
-// Runs in the caller's order, or -- when `perm` is given and the call's state says so -- in the grouped order.
+// One tile of 32 coordinates, start to finish: decode, stage the warp's distinct hulls (kHullSlots per round) with
+// blocking loads, evaluate, store.  The body of patch_run_kernel.
 template <int LT, int ORDER, bool TRI>
-__global__ void __launch_bounds__(kPatchBlock, TRI ? 4 : 7) patch_run_kernel(PatchIO io) {
+__device__ __forceinline__ void patch_tile_sync(const PatchIO &io, float *st, int pitch, const LaneCoord &lc, bool contiguous) {
     constexpr int NSETS = ORDER == 0 ? 1 : (ORDER == 1 ? 3 : 6);
     constexpr int LTU = hull_unit(LT);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int PASSES = kHullSlots / 2;
+    const int lane = threadIdx.x & 31;
+    const int half = lane >> 4, jj = lane & 15;
+    const bool live = lc.live;
+    PatchSite ps;
+    ps.type = 0; ps.boundary = 0; ps.cvOffset = 0; ps.s = 0.0f; ps.t = 0.0f; ps.d1 = 1.0f; ps.sign = 1.0f;
+    if (live) decode_patch_site(io, lc.arrayIndex, lc.patchIndex, lc.s, lc.t, ps);
+    const int np = live ? patch_type_points(ps.type) : 0;
+
+    // distinct patches of the warp: the lowest lane of each group of equal patches owns the staged copy
+    const int key = live ? lc.patchIndex : (-1 - lane);
+    const unsigned same = __match_any_sync(FULL, key);
+    const int owner = __ffs(same) - 1;
+    const unsigned owners = __ballot_sync(FULL, live && owner == lane);
+    const int slot = __popc(owners & ((1u << owner) - 1u));  // dense number of my hull among the warp's hulls
+
+    float out[NSETS][LT];
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k)
+#pragma unroll
+        for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
+
+    // every distinct patch leaves (first index, points) at its slot: the staging lanes below read them from there
+    // instead of locating the owner lane and shuffling
+    int *slotInfo = reinterpret_cast<int *>(st + io.coordWords + 160);      // [32] first index, [32] points
+    if (live && owner == lane) { slotInfo[slot] = ps.cvOffset; slotInfo[32 + slot] = np; }
+    const int count = __popc(owners);
+    __syncwarp();
+#pragma unroll 1
+    for (int base = 0; base < count; base += kHullSlots) {
+        // this round's hulls, two per pass (one per half warp).  All passes' index loads are issued before the first
+        // vertex load: the index -> vertex dependency is paid once per round, not once per pass.
+        int cvi[PASSES];
+        bool more = false;                                  // some hull of the round has points 16..
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) {
+            const int hi = base + 2 * q + half;
+            const int n_h = hi < count ? slotInfo[32 + hi] : 0;
+            more = more || n_h > 16;
+            cvi[q] = (jj < n_h) ? ldg_i(io.indices + slotInfo[hi] + jj) : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) {
+            if (cvi[q] >= 0) {
+                const float *g = io.src + (size_t)cvi[q] * (size_t)io.srcStride;
+                float *d = st + (2 * q + half) * pitch + jj * LTU;
+                if (LT == 4 && (io.vecStore & 4)) {
+                    *reinterpret_cast<float4 *>(d) = __ldg(reinterpret_cast<const float4 *>(g));
+                } else if constexpr (LT >= 3) {
+                    *reinterpret_cast<float4 *>(d) = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + LT - 1));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < LT; ++c) d[c] = __ldg(g + c);
+                }
+            }
+        }
+        if (__any_sync(FULL, more)) {                       // points 16.. of 18 / 20-point hulls (end caps): rare
+#pragma unroll
+            for (int q = 0; q < PASSES; ++q) {
+                const int hi = base + 2 * q + half;
+                const int n_h = hi < count ? slotInfo[32 + hi] : 0;
+                const int pnt = jj + 16;
+                if (pnt < n_h) {
+                    const int ci = ldg_i(io.indices + slotInfo[hi] + pnt);
+                    const float *g = io.src + (size_t)ci * (size_t)io.srcStride;
+                    float *d = st + (2 * q + half) * pitch + pnt * LTU;
+#pragma unroll
+                    for (int c = 0; c < LT; ++c) d[c] = __ldg(g + c);
+                }
+            }
+        }
+        __syncwarp();
+        if (live && slot >= base && slot < base + kHullSlots) {
+            CvStaged cv;
+            cv.row = st + (slot - base) * pitch;
+            eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, io.options, out);
+        }
+        __syncwarp();                                       // the next round (or the result staging) overwrites the rows
+    }
+    store_outputs<LT, NSETS>(io, st, lc.i, live, contiguous, out);
+}
+
+// Hulls staged per warp: one warp per 32 coordinates, persistent grid (a block walks tiles with a grid stride).
+// Runs in the caller's order, or -- when `perm` is given and the call's state says so -- in the grouped order.
+template <int LT, int ORDER, bool TRI>
+__global__ void __launch_bounds__(kPatchBlock, TRI ? 4 : 7) patch_run_kernel(PatchIO io) {
     const int mode = io.binState ? io.binState->mode : (io.perm ? kPatchModeGrouped : kPatchModeDirect);   // grid-uniform
     if (mode == kPatchModeHull) return;                         // this call is served by patch_hull_kernel
     const bool grouped = io.perm != nullptr && mode == kPatchModeGrouped;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *st = b200_patch_smem + (size_t)warp * (size_t)io.warpWords;
     const int pitch = io.hullPitch;
-    const int half = lane >> 4, jj = lane & 15;
 
     float *coordBuf = st + io.coordWords;
     const int tiles = (int)(((long long)io.n + 31) >> 5);
@@ -962,91 +1051,7 @@ __global__ void __launch_bounds__(kPatchBlock, TRI ? 4 : 7) patch_run_kernel(Pat
             lc = read_tile_coords(io, coordBuf, (long long)tile << 5, lane);
             prefetch_tile_coords(io, coordBuf, tile + tileStep, tiles, lane);
         }
-        const bool live = lc.live;
-        PatchSite ps;
-        ps.type = 0; ps.boundary = 0; ps.cvOffset = 0; ps.s = 0.0f; ps.t = 0.0f; ps.d1 = 1.0f; ps.sign = 1.0f;
-        if (live) decode_patch_site(io, lc.arrayIndex, lc.patchIndex, lc.s, lc.t, ps);
-        const int np = live ? patch_type_points(ps.type) : 0;
-
-        // distinct patches of the warp: the lowest lane of each group of equal patches owns the staged copy
-        const int key = live ? lc.patchIndex : (-1 - lane);
-        const unsigned same = __match_any_sync(FULL, key);
-        const int owner = __ffs(same) - 1;
-        const unsigned owners = __ballot_sync(FULL, live && owner == lane);
-        const int slot = __popc(owners & ((1u << owner) - 1u));  // dense number of my hull among the warp's hulls
-
-        float out[NSETS][LT];
-#pragma unroll
-        for (int k = 0; k < NSETS; ++k)
-#pragma unroll
-            for (int c = 0; c < LT; ++c) out[k][c] = 0.0f;
-
-        unsigned rem = owners;
-        for (int base = 0; rem != 0u; base += kHullSlots) {
-            // this round's hulls, two per pass (one per half warp).  All passes' index loads are issued before the first
-            // vertex load: the index -> vertex dependency is paid once per round, not once per pass.
-            const unsigned round = rem;
-            int cvi[PASSES];
-            bool more = false;                                  // some hull of the round has points 16..
-#pragma unroll
-            for (int q = 0; q < PASSES; ++q) {
-                int h0 = -1, h1 = -1;
-                if (rem) { h0 = __ffs(rem) - 1; rem &= rem - 1u; }
-                if (rem) { h1 = __ffs(rem) - 1; rem &= rem - 1u; }
-                const int h = half ? h1 : h0;
-                const int hs = h < 0 ? 0 : h;
-                const int n_s = __shfl_sync(FULL, np, hs);         // every lane takes part in the shuffles
-                const int off_h = __shfl_sync(FULL, ps.cvOffset, hs);
-                const int n_h = h < 0 ? 0 : n_s;
-                more = more || n_h > 16;
-                cvi[q] = (jj < n_h) ? ldg_i(io.indices + off_h + jj) : -1;
-            }
-#pragma unroll
-            for (int q = 0; q < PASSES; ++q) {
-                if (cvi[q] >= 0) {
-                    const float *g = io.src + (size_t)cvi[q] * (size_t)io.srcStride;
-                    float *d = st + (2 * q + half) * pitch + jj * LTU;
-                    if (LT == 4 && (io.vecStore & 4)) {
-                        *reinterpret_cast<float4 *>(d) = __ldg(reinterpret_cast<const float4 *>(g));
-                    } else if constexpr (LT >= 3) {
-                        *reinterpret_cast<float4 *>(d) = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + LT - 1));
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < LT; ++c) d[c] = __ldg(g + c);
-                    }
-                }
-            }
-            if (__any_sync(FULL, more)) {                       // points 16.. of 18 / 20-point hulls (end caps): rare
-                unsigned r2 = round;
-#pragma unroll
-                for (int q = 0; q < PASSES; ++q) {
-                    int h0 = -1, h1 = -1;
-                    if (r2) { h0 = __ffs(r2) - 1; r2 &= r2 - 1u; }
-                    if (r2) { h1 = __ffs(r2) - 1; r2 &= r2 - 1u; }
-                    const int h = half ? h1 : h0;
-                    const int hs = h < 0 ? 0 : h;
-                    const int n_s = __shfl_sync(FULL, np, hs);         // every lane takes part in the shuffles
-                    const int off_h = __shfl_sync(FULL, ps.cvOffset, hs);
-                    const int n_h = h < 0 ? 0 : n_s;
-                    const int pnt = jj + 16;
-                    if (pnt < n_h) {
-                        const int ci = ldg_i(io.indices + off_h + pnt);
-                        const float *g = io.src + (size_t)ci * (size_t)io.srcStride;
-                        float *d = st + (2 * q + half) * pitch + pnt * LTU;
-#pragma unroll
-                        for (int c = 0; c < LT; ++c) d[c] = __ldg(g + c);
-                    }
-                }
-            }
-            __syncwarp();
-            if (live && slot >= base && slot < base + kHullSlots) {
-                CvStaged cv;
-                cv.row = st + (slot - base) * pitch;
-                eval_patch_type<LT, ORDER, TRI>(cv, ps.type, ps.s, ps.t, ps.boundary, ps.d1, ps.sign, io.options, out);
-            }
-            __syncwarp();                                       // the next round (or the result staging) overwrites the rows
-        }
-        store_outputs<LT, NSETS>(io, st, lc.i, live, !grouped, out);
+        patch_tile_sync<LT, ORDER, TRI>(io, st, pitch, lc, !grouped);
     }
 }
 
