@@ -342,7 +342,9 @@ def bench_config3(mesh, torch, osd, iters):
             a += [out, D(3 * k, 3, 18)]
         build["eval_K6_ms"] = time_calls(torch, lambda: osd.B200Evaluator.EvalStencils(src, D(0, 3, 3), *a, lim), iters)
         build["rows"], build["elements"] = lim.GetNumStencils(), lim.GetNumElements()
-        build["same_elements_as_host_table"] = bool(lim.GetNumElements() == ls.num_elements)
+        # the timed table above is synthesised with exactly 16 entries per row; Far and the device builder drop the
+        # entries whose weight is exactly zero (samples on a knot line), hence a handful fewer elements
+        build["elements_of_the_synthesised_table"] = int(ls.num_elements)
         from oracle import ref as oref
         if oref.available():
             m = oref.Mesh.from_topology("catmark", mesh.num_verts, np.full(len(mesh.faces), 4, np.int32), mesh.faces.reshape(-1))

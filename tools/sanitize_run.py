@@ -86,6 +86,19 @@ def patches():
             for k in range(6):
                 assert_close(res[:, 3 * k:3 * k + 3], d["out_" + OUT6[k]], scales[k], f"{name} variant {variant} {OUT6[k]}")
         pt.SetVariant(0)
+        if name == "patches_catmark_car":              # the general kernel instantiation with the true Gregory derivatives
+            g = golden("truederiv_catmark_car")
+            pt.SetGregoryTrueDerivatives(True)
+            for variant in (1, 3):
+                pt.SetVariant(variant)
+                out = torch.zeros((n, 18), device="cuda")
+                a = []
+                for k in range(6):
+                    a += [out, D(3 * k, 3, 18)]
+                assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *a, n, pc, pt, None)
+                assert np.abs(out.cpu().numpy()[:, 3:6] - g["out_du"]).max() <= 1e-3 * max(1.0, np.abs(g["out_du"]).max())
+            pt.SetVariant(0)
+            pt.SetGregoryTrueDerivatives(False)
         inst = osd.B200Evaluator.Create(D(0, 3, 3), D(0, 3, 18))
         assert inst.BindPatchCoords(n, pc, pt)
         out = torch.zeros((n, 3), device="cuda")
