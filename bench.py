@@ -713,8 +713,23 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
     blocks = [vt[:ncv], vt[ncv:2 * ncv]]
     torch.cuda.synchronize()
 
+    # How rank 0's control points reach every rank: one ncclBroadcast (default), or -- B200OSD_CFG5_EXCHANGE=scatter_allgather
+    # -- the same bytes as a scatter (rank r receives slice r) followed by an in-place all-gather, so that the root sends each
+    # byte once.  Measured at N = 2: 0.0989 ms per frame against 0.0762 for the broadcast (two collectives' launch latency
+    # and SMs next to a 58 us kernel), so the broadcast stays.
+    mode = os.environ.get("B200OSD_CFG5_EXCHANGE", "broadcast")
+    per = (ncv * 3) // max(world, 1)
+    if world <= 1 or per * world != ncv * 3:
+        mode = "broadcast"
+    flats = [blk.view(-1) for blk in blocks]
+
     def exchange(b, stream, g=0):
-        assert comm.Broadcast(blocks[b], ncv * 3, 0, deviceContext=stream)
+        if mode == "broadcast":
+            assert comm.Broadcast(blocks[b], ncv * 3, 0, deviceContext=stream)
+        else:
+            mine = flats[b][rank * per:(rank + 1) * per]
+            assert comm.Scatter(flats[b] if rank == 0 else None, mine, per, 0, deviceContext=stream)
+            assert comm.AllGather(mine, flats[b], per, deviceContext=stream)
 
     def evaluate(b, region):
         assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, D(2 * ncv * 3, 3, 3), tbl)
@@ -760,7 +775,9 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
     return {"workload": "loop_tri_torus_1000x500_uniform_L2_laststencils_xyz", "scaling": "strong", "table_order": order,
             "rows": int(n_total), "elements": int(table.num_elements), "control_verts": int(ncv), "row_sizes": sizes,
             "rows_this_rank": int(n), "imbalance": plan.imbalance(table.sizes),
-            "exchange": "none (1 GPU)" if world == 1 else f"b200osd_comm_broadcast of {ncv * 12} B per frame from rank 0, side stream, double-buffered",
+            "exchange": "none (1 GPU)" if world == 1 else (
+                f"b200osd_comm_broadcast of {ncv * 12} B per frame from rank 0, side stream, double-buffered" if mode == "broadcast" else
+                f"{ncv * 12} B per frame from rank 0 as b200osd_comm_scatter ({per * 4} B per rank) + in-place b200osd_comm_all_gather, side stream, double-buffered"),
             "launch": launch,
             "n_gpus": world, "steps": steps, "ms_per_step": ms_step, "value": n_total / (ms_step * 1e-3), "unit": "verts/s",
             "roofline_per_gpu": {"bound": "hbm", "achieved": alg_local / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -794,6 +811,14 @@ def run_b200_arm(args):
         comm = comm_wide = shard.B200Comm.Create()
     D = osd.BufferDescriptor
     lib = capi.lib()
+    if args.config5_only:
+        res = bench_config5_strong(torch, dist, osd, capi, shard, comm_wide, world, rank, max(20, min(args.steps, 100)), max(args.warmup, 5))
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     mesh, table, order = build_workload()
     config = shared_config(table, order)
@@ -1059,6 +1084,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="stencil kernel variant of the headline table (0 = auto)")
     ap.add_argument("--headline-only", action="store_true", help="skip the config 3 / 4 / 5 and incumbent sections")
+    ap.add_argument("--config5-only", action="store_true", help="run only the config-5 strong-scaling section and print it (experiments)")
     ap.add_argument("--graph", action="store_true",
                     help="N > 1: replay a b200osd frame graph of two frames instead of the eager pipeline")
     args = ap.parse_args()
