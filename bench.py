@@ -699,32 +699,76 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
         order = "index_sorted (synth)"
     n_total, ncv = table.num_stencils, table.num_control_verts
     alg_total = table.algorithmic_bytes(1, 3, 3)
-    plan = shard.ShardPlan.for_table(table.sizes, world, rank, align=2048)
-    local = shard.local_table(table, plan) if world > 1 else table
+    # How rank 0's control points reach the ranks (B200OSD_CFG5_EXCHANGE):
+    #  * window_locality (default): rows are dealt out by the smallest control vertex they reference
+    #    (b200osd_shard_plan_locality), so a rank needs ~1/world of the control points + a halo, and PULLS just those
+    #    runs from the root's peer-memory window by DMA every frame (b200osd_shard_control_runs, b200osd_window_get);
+    #  * broadcast: contiguous row ranges (b200osd_shard_plan); a contiguous range of a Far table references the whole
+    #    mesh, so all 6 MB are broadcast every frame (b200osd_comm_broadcast);
+    #  * scatter_allgather: the same bytes as scatter + in-place all-gather (measured slower than the broadcast at N = 2).
+    mode = os.environ.get("B200OSD_CFG5_EXCHANGE", "window_locality") if world > 1 else "none"
+    runs = []
+    if mode == "window_locality":
+        plan = shard.LocalityPlan.for_table(table, world, rank)
+        local = shard.local_table_rows(table, plan.rows)
+        local = synth.SynthStencilTable(num_control_verts=ncv, sizes=local.sizes, offsets=local.offsets, indices=local.indices,
+                                        weights=local.weights)
+        runs = shard.control_runs(local, 1024, 8)
+        rows_desc = f"{len(plan.rows)} rows by locality, control runs {runs}"
+    else:
+        plan = shard.ShardPlan.for_table(table.sizes, world, rank, align=2048)
+        local = shard.local_table(table, plan) if world > 1 else table
+        rows_desc = f"rows [{plan.start},{plan.end})"
     alg_local = local.algorithmic_bytes(1, 3, 3)
+    if mode == "window_locality":                            # this rank reads only its runs of the control points
+        alg_local += 12 * (sum(b - a for a, b in runs) - ncv)
     n = local.num_stencils
     tbl = osd.B200StencilTable.Create(local)
     assert tbl is not None, capi.last_error()
-    log(f"[bench] rank {rank}: config-5 table ({order}), rows [{plan.start},{plan.end}) of {n_total}, built in {time.time() - t0:.1f}s")
+    log(f"[bench] rank {rank}: config-5 table ({order}), {rows_desc} of {n_total}, built in {time.time() - t0:.1f}s")
     vb = osd.B200VertexBuffer.Create(3, 2 * ncv + n)
     vt = vb.as_tensor()
-    for b in (0, 1):
-        vb.UpdateData(np.ascontiguousarray(synth.deform(mesh.positions, b), np.float32), b * ncv, ncv)
+    frames5 = [np.ascontiguousarray(synth.deform(mesh.positions, b), np.float32) for b in (0, 1)]
     blocks = [vt[:ncv], vt[ncv:2 * ncv]]
+    win5 = None
+    if mode == "window_locality":
+        win5 = shard.B200Window.Create(comm, 2 * ncv * 12)
+        if rank == 0:                                        # the root's two control blocks live in its window
+            wt = win5.local_tensor().view(2, ncv, 3)
+            for b in (0, 1):
+                wt[b].copy_(torch.from_numpy(frames5[b]))
+    else:
+        for b in (0, 1):
+            vb.UpdateData(frames5[b], b * ncv, ncv)
     torch.cuda.synchronize()
-
-    # How rank 0's control points reach every rank: one ncclBroadcast (default), or -- B200OSD_CFG5_EXCHANGE=scatter_allgather
-    # -- the same bytes as a scatter (rank r receives slice r) followed by an in-place all-gather, so that the root sends each
-    # byte once.  Measured at N = 2: 0.0989 ms per frame against 0.0762 for the broadcast (two collectives' launch latency
-    # and SMs next to a 58 us kernel), so the broadcast stays.
-    mode = os.environ.get("B200OSD_CFG5_EXCHANGE", "broadcast")
     per = (ncv * 3) // max(world, 1)
-    if world <= 1 or per * world != ncv * 3:
+    if mode == "scatter_allgather" and per * world != ncv * 3:
         mode = "broadcast"
     flats = [blk.view(-1) for blk in blocks]
+    # one fused kernel (wait + copy with SM loads + signal) or wait + cudaMemcpyAsync per run + signal.  Measured: the kernel
+    # wins when the transfer is small (N = 8, 0.79 MB: 0.0271 vs 0.0310 ms per frame), the copy engine when it is large
+    # (N = 2, 3.0 MB: 0.0638 vs 0.0697 ms -- the copy then competes with the HBM-bound evaluation for SMs)
+    pull_choice = os.environ.get("B200OSD_CFG5_PULL", "auto")
+    pull_kernel = pull_choice == "kernel" or (pull_choice == "auto" and 12 * sum(b - a for a, b in runs) <= 1_500_000)
 
     def exchange(b, stream, g=0):
-        if mode == "broadcast":
+        if mode == "window_locality":
+            # ready(b): root -> all (slot b); pulled(b): all -> root (slot 2 + b), needed once the root rewrites a block.
+            # A non-root rank's whole exchange is ONE kernel: wait for ready(b), copy its runs over NVLink, signal pulled(b)
+            pulls = [((b * ncv + lo) * 12, blocks[b][lo:hi], (hi - lo) * 12) for lo, hi in runs]
+            if rank == 0:
+                if g >= 2:
+                    assert win5.Wait(-1, 2 + b, stream)
+                assert win5.Signal(-1, b, stream)
+                assert win5.Pull(0, -1, pulls, -1, -1, stream)
+            elif pull_kernel:
+                assert win5.Pull(0, b, pulls, 0, 2 + b, stream)
+            else:
+                assert win5.Wait(0, b, stream)
+                for off, dst, nb in pulls:
+                    assert win5.Get(0, off, dst, nb, stream)
+                assert win5.Signal(0, 2 + b, stream)
+        elif mode == "broadcast":
             assert comm.Broadcast(blocks[b], ncv * 3, 0, deviceContext=stream)
         else:
             mine = flats[b][rank * per:(rank + 1) * per]
@@ -745,22 +789,25 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
             for b in (0, 1):
                 exchange(b, torch.cuda.current_stream())
             torch.cuda.synchronize()
+            per_graph = max(2, int(os.environ.get("B200OSD_CFG5_FRAMES_PER_GRAPH", "2")) // 2 * 2)
             assert fg.Begin()
-            for b in (0, 1):
+            for f in range(per_graph):
+                b = f % 2
                 fg.Fence(False)                            # side waits for main: block 1-b's last reader has finished
                 exchange(1 - b, side)
                 assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, D(2 * ncv * 3, 3, 3), tbl, None, fg)
                 fg.Fence(True)                             # the next kernel reads block 1-b
             assert fg.End()
-            half = {"v": 0}
+            phase = {"v": 0}
 
             def step_graph(_):
-                if half["v"] == 0:
+                if phase["v"] == 0:
                     fg.Launch()
-                half["v"] ^= 1
-            steps += steps % 2
-            ms = timed_steps(torch, dist, world, step_graph, steps, warmup + warmup % 2, gstream)
-            launch = "b200osd frame graph of 2 frames (kernel || broadcast of the other control block), one cudaGraphLaunch per 2 frames"
+                phase["v"] = (phase["v"] + 1) % per_graph
+            steps = (steps + per_graph - 1) // per_graph * per_graph
+            ms = timed_steps(torch, dist, world, step_graph, steps, (max(warmup, 1) + per_graph - 1) // per_graph * per_graph, gstream)
+            launch = (f"b200osd frame graph of {per_graph} frames (kernel || exchange of the other control block), "
+                      f"one cudaGraphLaunch per {per_graph} frames")
         except Exception as exc:
             log(f"[bench] rank {rank}: config-5 frame graph failed ({exc}); eager pipeline")
             ms = None
@@ -768,6 +815,11 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
         pipe = FramePipe(torch, exchange, evaluate, active=world > 1)
         ms = timed_steps(torch, dist, world, lambda k: pipe.step(), steps, warmup, torch.cuda.current_stream())
     ms_step = ms / steps
+    win_error = 0
+    if win5 is not None:                                     # never torn down: recorded graphs and peers may still reference it
+        torch.cuda.synchronize()
+        win_error = win5.Error()
+        win5.leak()
     peak, _ = measured_peak()
     sizes = {}
     for sz in np.unique(table.sizes):
@@ -775,9 +827,14 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
     return {"workload": "loop_tri_torus_1000x500_uniform_L2_laststencils_xyz", "scaling": "strong", "table_order": order,
             "rows": int(n_total), "elements": int(table.num_elements), "control_verts": int(ncv), "row_sizes": sizes,
             "rows_this_rank": int(n), "imbalance": plan.imbalance(table.sizes),
-            "exchange": "none (1 GPU)" if world == 1 else (
-                f"b200osd_comm_broadcast of {ncv * 12} B per frame from rank 0, side stream, double-buffered" if mode == "broadcast" else
-                f"{ncv * 12} B per frame from rank 0 as b200osd_comm_scatter ({per * 4} B per rank) + in-place b200osd_comm_all_gather, side stream, double-buffered"),
+            "exchange": {"none": "none (1 GPU)",
+                         "window_locality": f"rows dealt out by locality (b200osd_shard_plan_locality); rank 0 pulls {12 * sum(b - a for a, b in runs)} B "
+                                            f"of the {ncv * 12} B of control points per frame in {len(runs)} DMA run(s) from the root's peer-memory "
+                                            "window (" + ("b200osd_window_pull: wait + copy + signal in one kernel" if pull_kernel else "b200osd_window_get") + "), side stream, double-buffered",
+                         "broadcast": f"b200osd_comm_broadcast of {ncv * 12} B per frame from rank 0, side stream, double-buffered",
+                         "scatter_allgather": f"{ncv * 12} B per frame from rank 0 as b200osd_comm_scatter ({per * 4} B per rank) + in-place "
+                                              "b200osd_comm_all_gather, side stream, double-buffered"}[mode],
+            "window_wait_timeouts": win_error,
             "launch": launch,
             "n_gpus": world, "steps": steps, "ms_per_step": ms_step, "value": n_total / (ms_step * 1e-3), "unit": "verts/s",
             "roofline_per_gpu": {"bound": "hbm", "achieved": alg_local / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

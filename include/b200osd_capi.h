@@ -303,6 +303,21 @@ B200OSD_API int   b200osd_frame_synchronize(b200osd_frame *f);
 /* `world` contiguous row ranges [ranges[2r], ranges[2r+1]) of equal cost (a row costs its elements + 1); interior cuts are
  * rounded to a multiple of `align` (e.g. the 2048-row bucketing window).  Host only: needs no device. */
 B200OSD_API int b200osd_shard_plan(int numStencils, const int *sizes, int world, int align, int *ranges);
+/* Strong scaling of ONE mesh wants more than balance: a contiguous row range of a Far table references control vertices
+ * from all over the mesh (its face-, edge- and vertex-points are separate blocks), so every rank would need every control
+ * point every frame.  This plan orders the rows by the smallest control vertex they reference (stable; rowOrder[numStencils]
+ * = the rows in that order) and cuts THAT order into `world` chunks of equal cost (ranges[2r], ranges[2r+1]) = positions
+ * in rowOrder).  A rank builds its table from its rows and, per frame, needs only the control vertices
+ * [controlRanges[2r], controlRanges[2r+1]) -- on a mesh whose vertex numbering has any locality about 1/world of them plus
+ * a halo, pulled with b200osd_window_get.  Outputs stay sharded, in rowOrder.  Host only: needs no device. */
+B200OSD_API int b200osd_shard_plan_locality(int numStencils, const int *sizes, const int *offsets, const int *indices,
+                                            int world, int *rowOrder, int *ranges, int *controlRanges);
+/* The control vertices a (local) table references, as at most maxRuns index runs [runs[2k], runs[2k+1]) at `granularity`
+ * vertices (a closed mesh has a seam: the bounding interval of a chunk can be the whole mesh while two runs are 1/world of
+ * it).  The closest runs are merged when there are more than maxRuns.  Returns the number of runs, -1 on bad arguments.
+ * These are the per-frame transfers of a rank: one b200osd_window_get per run.  Host only. */
+B200OSD_API int b200osd_shard_control_runs(int numStencils, const int *sizes, const int *offsets, const int *indices,
+                                           int granularity, int maxRuns, int *runs);
 /* the same for a PatchCoord set (every coordinate costs the same) */
 B200OSD_API int b200osd_shard_coords(long long numCoords, int world, int align, long long *ranges);
 /* Communicator over NCCL (bound at run time with dlopen: no link-time dependency).  Rank 0 calls _unique_id and hands the
@@ -339,6 +354,13 @@ B200OSD_API void   b200osd_window_destroy(b200osd_window *w);
 B200OSD_API void  *b200osd_window_local(const b200osd_window *w);
 B200OSD_API size_t b200osd_window_bytes(const b200osd_window *w);
 B200OSD_API int    b200osd_window_get(b200osd_window *w, int srcRank, size_t srcOffsetBytes, void *dst, size_t bytes, void *stream);
+/* wait + copy + signal as ONE kernel (SM loads over NVLink peer memory instead of a copy engine; for per-frame exchanges of
+ * a few hundred KB, where the DMA set-up and two extra launches dominate): waits for the next signal of (waitSlot, srcRank)
+ * when waitSlot >= 0, copies numRuns (<= 8) byte ranges [srcOffsetBytes[r], +bytes[r]) of srcRank's window to dsts[r]
+ * (multiples of 4 bytes), then signals (signalSlot -> signalRank, -1 = every other rank) when signalSlot >= 0.  One pull at
+ * a time per window (issue them on one stream). */
+B200OSD_API int    b200osd_window_pull(b200osd_window *w, int srcRank, int waitSlot, int numRuns, const size_t *srcOffsetBytes,
+                                       void *const *dsts, const size_t *bytes, int signalRank, int signalSlot, void *stream);
 B200OSD_API int    b200osd_window_signal(b200osd_window *w, int dstRank, int slot, void *stream);
 B200OSD_API int    b200osd_window_wait(b200osd_window *w, int srcRank, int slot, void *stream);
 B200OSD_API int    b200osd_window_error(b200osd_window *w);

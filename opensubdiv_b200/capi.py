@@ -34,10 +34,10 @@ SYMBOLS = [
     "b200osd_patch_plan_eval",
     "b200osd_patch_map_create", "b200osd_patch_map_destroy", "b200osd_patch_map_info", "b200osd_patch_map_find",
     "b200osd_frame_side_stream", "b200osd_frame_fence", "b200osd_frame_set_l2_window",
-    "b200osd_shard_plan", "b200osd_shard_coords", "b200osd_comm_available", "b200osd_comm_unique_id", "b200osd_comm_create", "b200osd_comm_create_ex",
+    "b200osd_shard_plan", "b200osd_shard_plan_locality", "b200osd_shard_control_runs", "b200osd_shard_coords", "b200osd_comm_available", "b200osd_comm_unique_id", "b200osd_comm_create", "b200osd_comm_create_ex",
     "b200osd_comm_destroy", "b200osd_comm_world", "b200osd_comm_rank", "b200osd_comm_broadcast", "b200osd_comm_scatter",
     "b200osd_comm_all_gather",
-    "b200osd_window_create", "b200osd_window_destroy", "b200osd_window_local", "b200osd_window_bytes", "b200osd_window_get",
+    "b200osd_window_create", "b200osd_window_destroy", "b200osd_window_local", "b200osd_window_bytes", "b200osd_window_get", "b200osd_window_pull",
     "b200osd_window_signal", "b200osd_window_wait", "b200osd_window_error",
     "b200osd_frame_create", "b200osd_frame_destroy", "b200osd_frame_stream", "b200osd_frame_begin", "b200osd_frame_end",
     "b200osd_frame_launch", "b200osd_frame_synchronize",
@@ -132,6 +132,8 @@ def lib():
     L.b200osd_frame_fence.argtypes = [vp, i]
     L.b200osd_frame_set_l2_window.argtypes = [vp, vp, C.c_size_t, C.c_float]
     L.b200osd_shard_plan.argtypes = [i, vp, i, i, vp]
+    L.b200osd_shard_plan_locality.argtypes = [i, vp, vp, vp, i, vp, vp, vp]
+    L.b200osd_shard_control_runs.argtypes = [i, vp, vp, vp, i, i, vp]
     L.b200osd_shard_coords.argtypes = [ll, i, i, vp]
     L.b200osd_comm_unique_id.argtypes = [vp]
     L.b200osd_comm_create.restype = vp
@@ -152,6 +154,7 @@ def lib():
     L.b200osd_window_bytes.restype = C.c_size_t
     L.b200osd_window_bytes.argtypes = [vp]
     L.b200osd_window_get.argtypes = [vp, i, C.c_size_t, vp, C.c_size_t, vp]
+    L.b200osd_window_pull.argtypes = [vp, i, i, i, vp, vp, vp, i, i, vp]
     L.b200osd_window_signal.argtypes = [vp, i, i, vp]
     L.b200osd_window_wait.argtypes = [vp, i, i, vp]
     L.b200osd_window_error.argtypes = [vp]

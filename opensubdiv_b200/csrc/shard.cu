@@ -23,6 +23,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 using namespace b200osd;
@@ -122,6 +123,100 @@ int b200osd_shard_plan(int numStencils, const int *sizes, int world, int align, 
     }
     for (int r = 0; r < world; ++r) { ranges[2 * r] = cuts[(size_t)r]; ranges[2 * r + 1] = cuts[(size_t)r + 1]; }
     return B200OSD_OK;
+}
+
+int b200osd_shard_plan_locality(int numStencils, const int *sizes, const int *offsets, const int *indices, int world,
+                                int *rowOrder, int *ranges, int *controlRanges) {
+    if (numStencils < 0 || world < 1 || !ranges || !controlRanges || (numStencils > 0 && (!sizes || !offsets || !indices || !rowOrder))) {
+        set_error("shard_plan_locality: bad arguments");
+        return B200OSD_ERR_INVALID;
+    }
+    const int n = numStencils;
+    // key of a row: the smallest control vertex it references (rows of an empty stencil go first)
+    std::vector<int> key((size_t)n, -1);
+    int maxKey = -1;
+    for (int i = 0; i < n; ++i) {
+        if (sizes[i] < 0 || offsets[i] < 0) { set_error("shard_plan_locality: negative size / offset in row %d", i); return B200OSD_ERR_INVALID; }
+        int k = -1;
+        for (int j = 0; j < sizes[i]; ++j) {
+            const int v = indices[(size_t)offsets[i] + j];
+            if (v < 0) { set_error("shard_plan_locality: negative index in row %d", i); return B200OSD_ERR_INVALID; }
+            k = (k < 0 || v < k) ? v : k;
+        }
+        key[(size_t)i] = k;
+        maxKey = std::max(maxKey, k);
+    }
+    // counting sort by key, stable: rows of equal key keep the table's order
+    std::vector<long long> start((size_t)maxKey + 3, 0);
+    for (int i = 0; i < n; ++i) ++start[(size_t)(key[(size_t)i] + 1) + 1];
+    for (size_t k = 1; k < start.size(); ++k) start[k] += start[k - 1];
+    for (int i = 0; i < n; ++i) rowOrder[start[(size_t)(key[(size_t)i] + 1)]++] = i;
+    // cuts balanced on cost (elements + 1 per row), like b200osd_shard_plan
+    long long total = 0;
+    for (int i = 0; i < n; ++i) total += (long long)sizes[i] + 1;
+    std::vector<int> cuts((size_t)world + 1, n);
+    cuts[0] = 0;
+    long long run = 0;
+    int i = 0;
+    for (int r = 1; r < world; ++r) {
+        const long long target = total * r / world;
+        while (i < n && run + sizes[rowOrder[i]] + 1 < target) { run += (long long)sizes[rowOrder[i]] + 1; ++i; }
+        cuts[(size_t)r] = std::min(std::max(std::min(i + 1, n), cuts[(size_t)r - 1]), n);
+    }
+    for (int r = 0; r < world; ++r) {
+        ranges[2 * r] = cuts[(size_t)r];
+        ranges[2 * r + 1] = cuts[(size_t)r + 1];
+        int lo = 0x7fffffff, hi = -1;
+        for (int q = cuts[(size_t)r]; q < cuts[(size_t)r + 1]; ++q) {
+            const int row = rowOrder[q];
+            for (int j = 0; j < sizes[row]; ++j) {
+                const int v = indices[(size_t)offsets[row] + j];
+                lo = std::min(lo, v);
+                hi = std::max(hi, v);
+            }
+        }
+        controlRanges[2 * r] = hi < 0 ? 0 : lo;
+        controlRanges[2 * r + 1] = hi + 1;
+    }
+    return B200OSD_OK;
+}
+
+int b200osd_shard_control_runs(int numStencils, const int *sizes, const int *offsets, const int *indices, int granularity,
+                               int maxRuns, int *runs) {
+    if (numStencils < 0 || granularity < 1 || maxRuns < 1 || !runs || (numStencils > 0 && (!sizes || !offsets || !indices))) {
+        set_error("shard_control_runs: bad arguments");
+        return -1;
+    }
+    int maxIdx = -1;
+    for (int i = 0; i < numStencils; ++i)
+        for (int j = 0; j < sizes[i]; ++j) maxIdx = std::max(maxIdx, indices[(size_t)offsets[i] + j]);
+    if (maxIdx < 0) return 0;
+    const int blocks = maxIdx / granularity + 1;
+    std::vector<char> used((size_t)blocks, 0);
+    for (int i = 0; i < numStencils; ++i)
+        for (int j = 0; j < sizes[i]; ++j) {
+            const int v = indices[(size_t)offsets[i] + j];
+            if (v < 0) { set_error("shard_control_runs: negative index in row %d", i); return -1; }
+            used[(size_t)(v / granularity)] = 1;
+        }
+    std::vector<std::pair<int, int>> r;                  // [first block, last block + 1)
+    for (int b = 0; b < blocks; ++b) {
+        if (!used[(size_t)b]) continue;
+        if (!r.empty() && r.back().second == b) r.back().second = b + 1;
+        else r.push_back(std::make_pair(b, b + 1));
+    }
+    while ((int)r.size() > maxRuns) {                    // too many pieces: close the smallest gap
+        size_t best = 0;
+        for (size_t k = 1; k + 1 < r.size(); ++k)
+            if (r[k + 1].first - r[k].second < r[best + 1].first - r[best].second) best = k;
+        r[best].second = r[best + 1].second;
+        r.erase(r.begin() + (long)best + 1);
+    }
+    for (size_t k = 0; k < r.size(); ++k) {
+        runs[2 * k] = r[k].first * granularity;
+        runs[2 * k + 1] = std::min(r[k].second * granularity, maxIdx + 1);
+    }
+    return (int)r.size();
 }
 
 int b200osd_shard_coords(long long numCoords, int world, int align, long long *ranges) {
@@ -275,6 +370,77 @@ __global__ void window_wait_kernel(const int *flags, int *expect, int world, int
     __threadfence_system();
 }
 
+// wait + copy + signal in ONE kernel: the copy reads the source rank's window with ordinary (uncached) loads over NVLink
+// peer memory instead of going through a copy engine, which takes the DMA set-up latency and two kernel launches off a
+// per-frame exchange of a few hundred KB.  Every block waits for the flag on its own (no block waits for another one, so
+// the grid needs no co-residency); the last block to finish advances the wait counter and signals.
+constexpr int kPullMaxRuns = 8, kPullBlocks = 32, kPullThreads = 256, kPullUnroll = 8;
+struct PullArgs {
+    const char *src[kPullMaxRuns];
+    char *dst[kPullMaxRuns];
+    unsigned long long bytes[kPullMaxRuns];
+    int n;
+};
+
+__global__ void __launch_bounds__(kPullThreads) window_pull_kernel(PullArgs a, const int *flags, int *expect, int *const *peerFlags,
+                                                                  int *sendSeq, int *error, int *done, int world, int rank,
+                                                                  int srcRank, int waitSlot, int sigRank, int sigSlot) {
+    if (waitSlot >= 0) {
+        if (threadIdx.x == 0) {
+            const int want = expect[waitSlot * world + srcRank] + 1;      // advanced by the last block, after every block read it
+            const volatile int *f = flags + waitSlot * world + srcRank;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (*f < want) {
+                __nanosleep(100);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 10000000000ull) { *error = 1; break; }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < a.n; ++r) {
+        const bool vec = ((reinterpret_cast<uintptr_t>(a.src[r]) | reinterpret_cast<uintptr_t>(a.dst[r])) & 15) == 0;
+        const size_t nv = vec ? a.bytes[r] / 16 : 0;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(a.src[r]);
+        uint4 *d4 = reinterpret_cast<uint4 *>(a.dst[r]);
+        // kPullUnroll independent 16-byte loads in flight per thread: a load over NVLink takes ~2 us, so the bytes in
+        // flight (blocks x threads x unroll x 16 = 1 MB) decide the copy rate, not the instruction count
+        for (size_t i = tid; i < nv; i += nth * kPullUnroll) {
+            uint4 v[kPullUnroll];
+#pragma unroll
+            for (int u = 0; u < kPullUnroll; ++u)
+                if (i + u * nth < nv) v[u] = __ldcv(s4 + i + u * nth);
+#pragma unroll
+            for (int u = 0; u < kPullUnroll; ++u)
+                if (i + u * nth < nv) d4[i + u * nth] = v[u];
+        }
+        const unsigned *s1 = reinterpret_cast<const unsigned *>(a.src[r] + nv * 16);
+        unsigned *d1 = reinterpret_cast<unsigned *>(a.dst[r] + nv * 16);
+        const size_t nw = (a.bytes[r] - nv * 16) / 4;
+        for (size_t i = tid; i < nw; i += nth) d1[i] = __ldcv(s1 + i);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(done, 1) == (int)gridDim.x - 1) {                  // the last block
+            *done = 0;
+            if (waitSlot >= 0) expect[waitSlot * world + srcRank] += 1;
+            if (sigSlot >= 0) {
+                for (int p = 0; p < world; ++p) {
+                    if (p == rank || (sigRank >= 0 && p != sigRank)) continue;
+                    const int v = sendSeq[sigSlot * world + p] + 1;
+                    sendSeq[sigSlot * world + p] = v;
+                    __threadfence_system();
+                    *reinterpret_cast<volatile int *>(peerFlags[p] + sigSlot * world + rank) = v;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 struct b200osd_window {
@@ -370,6 +536,33 @@ int b200osd_window_get(b200osd_window *w, int srcRank, size_t srcOffsetBytes, vo
     if (bytes == 0) return B200OSD_OK;
     B200_CUDA_TRY(cudaMemcpyAsync(dst, w->peerData[(size_t)srcRank] + srcOffsetBytes, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return B200OSD_OK;
+}
+
+int b200osd_window_pull(b200osd_window *w, int srcRank, int waitSlot, int numRuns, const size_t *srcOffsetBytes, void *const *dsts,
+                        const size_t *bytes, int signalRank, int signalSlot, void *stream) {
+    if (!w || srcRank < 0 || srcRank >= w->world || numRuns < 0 || numRuns > kPullMaxRuns || waitSlot >= kWindowSlots ||
+        signalSlot >= kWindowSlots || signalRank >= w->world || (numRuns > 0 && (!srcOffsetBytes || !dsts || !bytes))) {
+        set_error("window_pull: bad window / rank / slot / runs (at most %d runs)", kPullMaxRuns);
+        return B200OSD_ERR_INVALID;
+    }
+    PullArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = numRuns;
+    for (int r = 0; r < numRuns; ++r) {
+        if (!dsts[r] || bytes[r] % 4 != 0 || srcOffsetBytes[r] % 4 != 0 || srcOffsetBytes[r] + bytes[r] > w->bytes) {
+            set_error("window_pull: run %d: [%zu,+%zu) outside the %zu-byte window, NULL destination or not a multiple of 4 bytes",
+                      r, srcOffsetBytes[r], bytes[r], w->bytes);
+            return B200OSD_ERR_INVALID;
+        }
+        a.src[r] = w->peerData[(size_t)srcRank] + srcOffsetBytes[r];
+        a.dst[r] = static_cast<char *>(dsts[r]);
+        a.bytes[r] = bytes[r];
+    }
+    if (w->world == 1) { waitSlot = -1; signalSlot = -1; }
+    window_pull_kernel<<<kPullBlocks, kPullThreads, 0, (cudaStream_t)stream>>>(a, w->flags, w->expect, w->d_peerFlags, w->sendSeq, w->error,
+                                                                            w->error + 1, w->world, w->rank, srcRank, waitSlot,
+                                                                            signalRank, signalSlot);
+    return check_launch("window_pull_kernel");
 }
 
 int b200osd_window_signal(b200osd_window *w, int dstRank, int slot, void *stream) {

@@ -75,6 +75,87 @@ class ShardPlan:
         return max(costs) / (sum(costs) / len(costs)) if sum(costs) else 1.0
 
 
+@dataclass
+class LocalityPlan:
+    """b200osd_shard_plan_locality: rows ordered by the smallest control vertex they reference, cut into `world` chunks of
+    equal cost.  `rows` = this rank's global row numbers in evaluation order; [ctrl_lo, ctrl_hi) = the control vertices
+    they reference (what the rank has to receive every frame)."""
+    world: int
+    rank: int
+    row_order: np.ndarray
+    ranges: List[Tuple[int, int]]
+    control_ranges: List[Tuple[int, int]]
+
+    @classmethod
+    def for_table(cls, table, world: int, rank: int) -> "LocalityPlan":
+        from . import capi
+        n = int(len(table.sizes))
+        world = max(int(world), 1)
+        sz, off, idx = (np.ascontiguousarray(x, dtype=np.int32) for x in (table.sizes, table.offsets, table.indices))
+        order = np.zeros(n, dtype=np.int32)
+        ranges = np.zeros(2 * world, dtype=np.int32)
+        ctrl = np.zeros(2 * world, dtype=np.int32)
+        p = lambda a: a.ctypes.data if a.size else None
+        rc = capi.lib().b200osd_shard_plan_locality(n, p(sz), p(off), p(idx), world, p(order), ranges.ctypes.data, ctrl.ctypes.data)
+        if rc != capi.OK:
+            raise capi.B200OsdError("b200osd_shard_plan_locality: " + capi.last_error())
+        return cls(world, rank, order, [(int(ranges[2 * r]), int(ranges[2 * r + 1])) for r in range(world)],
+                   [(int(ctrl[2 * r]), int(ctrl[2 * r + 1])) for r in range(world)])
+
+    @property
+    def rows(self) -> np.ndarray:
+        a, b = self.ranges[self.rank]
+        return self.row_order[a:b]
+
+    @property
+    def ctrl_lo(self) -> int:
+        return self.control_ranges[self.rank][0]
+
+    @property
+    def ctrl_hi(self) -> int:
+        return self.control_ranges[self.rank][1]
+
+    def imbalance(self, sizes: np.ndarray) -> float:
+        costs = [float(sizes[self.row_order[a:b]].astype(np.int64).sum() + (b - a)) for a, b in self.ranges]
+        return max(costs) / (sum(costs) / len(costs)) if sum(costs) else 1.0
+
+
+def control_runs(table, granularity: int = 1024, max_runs: int = 8) -> List[Tuple[int, int]]:
+    """b200osd_shard_control_runs: the control vertices `table` (a rank's local table) references, as index runs [lo, hi)."""
+    from . import capi
+    n = int(len(table.sizes))
+    sz, off, idx = (np.ascontiguousarray(x, dtype=np.int32) for x in (table.sizes, table.offsets, table.indices))
+    runs = np.zeros(2 * max_runs, dtype=np.int32)
+    p = lambda a: a.ctypes.data if a.size else None
+    k = capi.lib().b200osd_shard_control_runs(n, p(sz), p(off), p(idx), int(granularity), int(max_runs), runs.ctypes.data)
+    if k < 0:
+        raise capi.B200OsdError("b200osd_shard_control_runs: " + capi.last_error())
+    return [(int(runs[2 * q]), int(runs[2 * q + 1])) for q in range(k)]
+
+
+def local_table_rows(table, rows: np.ndarray):
+    """The given rows (global row numbers, any order) as a self-contained reference-layout table, in that order."""
+    from types import SimpleNamespace
+    rows = np.asarray(rows, dtype=np.int64)
+    sizes = np.ascontiguousarray(np.asarray(table.sizes)[rows], dtype=np.int32)
+    offsets = np.zeros(len(rows), dtype=np.int32)
+    if len(rows) > 1:
+        np.cumsum(sizes[:-1], out=offsets[1:])
+    ne = int(sizes.astype(np.int64).sum())
+    # element e of the local table = element (src_off[row] + e - offsets[row]) of the global one
+    src_off = np.asarray(table.offsets, dtype=np.int64)[rows]
+    take = np.repeat(src_off - offsets, sizes) + np.arange(ne, dtype=np.int64)
+    out = SimpleNamespace(num_control_verts=int(getattr(table, "num_control_verts", 0) or 0), sizes=sizes, offsets=offsets,
+                          indices=np.ascontiguousarray(np.asarray(table.indices)[take], dtype=np.int32),
+                          weights=np.ascontiguousarray(np.asarray(table.weights)[take], dtype=np.float32))
+    for k in ("du", "dv", "duu", "duv", "dvv"):
+        w = getattr(table, k, None)
+        setattr(out, k, None if w is None else np.ascontiguousarray(np.asarray(w)[take], dtype=np.float32))
+    out.num_stencils = len(rows)
+    out.num_elements = ne
+    return out
+
+
 def coord_ranges(num_coords: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
     """EvalPatches shards by PatchCoord range: `world` contiguous, near-equal ranges of [0, num_coords),
     interior cuts on a multiple of `align` (a warp's worth of coordinates).  Every coordinate costs the same, so no
@@ -270,6 +351,19 @@ class B200Window:
         from .osd import _dev_ptr, _stream_ptr
         return capi.check(capi.lib().b200osd_window_get(self._h, int(src_rank), int(src_offset_bytes), _dev_ptr(dst), int(nbytes),
                                                         _stream_ptr(deviceContext)), "B200Window::Get")
+
+    def Pull(self, src_rank: int, wait_slot: int, runs, signal_rank: int = -1, signal_slot: int = -1, deviceContext=None) -> bool:
+        """b200osd_window_pull: wait (wait_slot >= 0) + copy + signal (signal_slot >= 0) as one kernel.
+        runs = [(src_offset_bytes, dst, nbytes), ...] (at most 8)."""
+        import ctypes as C
+        from . import capi
+        from .osd import _dev_ptr, _stream_ptr
+        k = len(runs)
+        offs = (C.c_size_t * max(k, 1))(*[int(r[0]) for r in runs])
+        dsts = (C.c_void_p * max(k, 1))(*[_dev_ptr(r[1]) for r in runs])
+        nb = (C.c_size_t * max(k, 1))(*[int(r[2]) for r in runs])
+        return capi.check(capi.lib().b200osd_window_pull(self._h, int(src_rank), int(wait_slot), k, offs, dsts, nb, int(signal_rank),
+                                                         int(signal_slot), _stream_ptr(deviceContext)), "B200Window::Pull")
 
     def Signal(self, dst_rank: int, slot: int, deviceContext=None) -> bool:
         from . import capi

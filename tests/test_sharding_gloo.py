@@ -201,6 +201,55 @@ def test_c_shard_plan_matches_a_straight_restatement():
     assert capi.lib().b200osd_shard_plan(10, None, 1, 1, bad.ctypes.data) == capi.ERR_INVALID
 
 
+def test_locality_plan_deals_rows_by_the_control_vertices_they_reference():
+    """b200osd_shard_plan_locality + b200osd_shard_control_runs (strong scaling of one mesh): the row order is a stable
+    sort by the smallest referenced control vertex, the chunks are balanced, every chunk's runs cover what its rows
+    reference and are a fraction of the mesh; applying the per-rank tables and scattering the results back equals the
+    single-table result (oracle as the per-rank compute)."""
+    from oracle import oracle
+    mesh = synth.torus_quads(40, 30)
+    t = synth.uniform_stencil_table(mesh, 2)
+    ncv, n = t.num_control_verts, t.num_stencils
+    key = np.minimum.reduceat(t.indices, t.offsets)
+    src = np.random.default_rng(3).standard_normal((ncv, 3)).astype(np.float32)
+    want = np.zeros((n, 3), np.float32)
+    assert oracle.eval_stencils(src.reshape(-1), (0, 3, 3), [want.reshape(-1)], [(0, 3, 3)], t.sizes, t.offsets, t.indices, [t.weights])
+    for world in (1, 2, 3, 8):
+        plans = [shard.LocalityPlan.for_table(t, world, r) for r in range(world)]
+        order = plans[0].row_order
+        assert np.array_equal(order, np.argsort(key, kind="stable"))
+        assert np.array_equal(np.sort(np.concatenate([p.rows for p in plans])), np.arange(n))
+        assert plans[0].imbalance(t.sizes) < 1.02
+        got = np.zeros_like(want)
+        for p in plans:
+            lt = shard.local_table_rows(t, p.rows)
+            runs = shard.control_runs(lt, 64, 4)
+            assert 1 <= len(runs) <= 4 and all(a < b for a, b in runs)
+            covered = np.zeros(ncv, bool)
+            for a, b in runs:
+                covered[a:b] = True
+            assert covered[lt.indices].all()
+            assert p.ctrl_lo == lt.indices.min() and p.ctrl_hi == lt.indices.max() + 1
+            if world == 8:
+                assert covered.sum() < 0.4 * ncv                  # ~1/8 of the mesh + halo (+ the seam's second run)
+            # the rank sees only its runs of the control points
+            part = np.full_like(src, np.nan)
+            part[covered] = src[covered]
+            out = np.zeros((len(p.rows), 3), np.float32)
+            assert oracle.eval_stencils(part.reshape(-1), (0, 3, 3), [out.reshape(-1)], [(0, 3, 3)], lt.sizes, lt.offsets, lt.indices,
+                                        [lt.weights])
+            got[p.rows] = out
+        assert np.array_equal(got, want)
+    from opensubdiv_b200 import capi
+    assert capi.lib().b200osd_shard_control_runs(1, None, None, None, 64, 4, np.zeros(8, np.int32).ctypes.data) == -1
+    # more pieces than runs allowed: the closest ones merge and still cover
+    tbl = synth.SynthStencilTable(100, np.array([1] * 5, np.int32), np.arange(5, dtype=np.int32), np.array([0, 10, 20, 50, 99], np.int32),
+                                  np.ones(5, np.float32))
+    assert shard.control_runs(tbl, 1, 8) == [(0, 1), (10, 11), (20, 21), (50, 51), (99, 100)]
+    assert shard.control_runs(tbl, 1, 3) == [(0, 21), (50, 51), (99, 100)]
+    assert shard.control_runs(tbl, 16, 8) == [(0, 32), (48, 64), (96, 100)]
+
+
 def test_communicator_needs_a_device():
     """No CPU fallback in the exchange either: without a CUDA device b200osd_comm_create returns NULL with a message."""
     import ctypes as C
