@@ -726,19 +726,23 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
     tbl = osd.B200StencilTable.Create(local)
     assert tbl is not None, capi.last_error()
     log(f"[bench] rank {rank}: config-5 table ({order}), {rows_desc} of {n_total}, built in {time.time() - t0:.1f}s")
-    vb = osd.B200VertexBuffer.Create(3, 2 * ncv + n)
+    # control blocks: two (frame f in block f % 2), three for the pulled exchange -- with a third block the pull for frame
+    # f+2 only has to wait for frame f-1's kernel, so kernel -> pull -> kernel spans three frames instead of two
+    NB = 3 if mode == "window_locality" else 2
+    vb = osd.B200VertexBuffer.Create(3, NB * ncv + n)
     vt = vb.as_tensor()
-    frames5 = [np.ascontiguousarray(synth.deform(mesh.positions, b), np.float32) for b in (0, 1)]
-    blocks = [vt[:ncv], vt[ncv:2 * ncv]]
+    frames5 = [np.ascontiguousarray(synth.deform(mesh.positions, b), np.float32) for b in range(NB)]
+    blocks = [vt[b * ncv:(b + 1) * ncv] for b in range(NB)]
+    dst5 = D(NB * ncv * 3, 3, 3)
     win5 = None
     if mode == "window_locality":
-        win5 = shard.B200Window.Create(comm, 2 * ncv * 12)
-        if rank == 0:                                        # the root's two control blocks live in its window
-            wt = win5.local_tensor().view(2, ncv, 3)
-            for b in (0, 1):
+        win5 = shard.B200Window.Create(comm, NB * ncv * 12)
+        if rank == 0:                                        # the root's control blocks live in its window
+            wt = win5.local_tensor().view(NB, ncv, 3)
+            for b in range(NB):
                 wt[b].copy_(torch.from_numpy(frames5[b]))
     else:
-        for b in (0, 1):
+        for b in range(NB):
             vb.UpdateData(frames5[b], b * ncv, ncv)
     torch.cuda.synchronize()
     per = (ncv * 3) // max(world, 1)
@@ -753,21 +757,21 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
 
     def exchange(b, stream, g=0):
         if mode == "window_locality":
-            # ready(b): root -> all (slot b); pulled(b): all -> root (slot 2 + b), needed once the root rewrites a block.
+            # ready(b): root -> all (slot b); pulled(b): all -> root (slot NB + b), needed once the root rewrites a block.
             # A non-root rank's whole exchange is ONE kernel: wait for ready(b), copy its runs over NVLink, signal pulled(b)
             pulls = [((b * ncv + lo) * 12, blocks[b][lo:hi], (hi - lo) * 12) for lo, hi in runs]
             if rank == 0:
-                if g >= 2:
-                    assert win5.Wait(-1, 2 + b, stream)
+                if g >= NB:
+                    assert win5.Wait(-1, NB + b, stream)
                 assert win5.Signal(-1, b, stream)
                 assert win5.Pull(0, -1, pulls, -1, -1, stream)
             elif pull_kernel:
-                assert win5.Pull(0, b, pulls, 0, 2 + b, stream)
+                assert win5.Pull(0, b, pulls, 0, NB + b, stream)
             else:
                 assert win5.Wait(0, b, stream)
                 for off, dst, nb in pulls:
                     assert win5.Get(0, off, dst, nb, stream)
-                assert win5.Signal(0, 2 + b, stream)
+                assert win5.Signal(0, NB + b, stream)
         elif mode == "broadcast":
             assert comm.Broadcast(blocks[b], ncv * 3, 0, deviceContext=stream)
         else:
@@ -776,7 +780,7 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
             assert comm.AllGather(mine, flats[b], per, deviceContext=stream)
 
     def evaluate(b, region):
-        assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, D(2 * ncv * 3, 3, 3), tbl)
+        assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, dst5, tbl)
     launch = "eager pipeline"
     ms = None
     if world > 1:
@@ -786,17 +790,27 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
             fg = osd.B200FrameGraph.Create()
             side = torch.cuda.ExternalStream(fg.side_stream)
             gstream = torch.cuda.ExternalStream(fg.cuda_stream)
-            for b in (0, 1):
+            for b in range(2):
                 exchange(b, torch.cuda.current_stream())
             torch.cuda.synchronize()
-            per_graph = max(2, int(os.environ.get("B200OSD_CFG5_FRAMES_PER_GRAPH", "2")) // 2 * 2)
+            per_graph = NB * max(1, int(os.environ.get("B200OSD_CFG5_GRAPH_ROUNDS", "4" if NB == 3 else "1")))   # whole rotations of the blocks
             assert fg.Begin()
-            for f in range(per_graph):
-                b = f % 2
-                fg.Fence(False)                            # side waits for main: block 1-b's last reader has finished
-                exchange(1 - b, side)
-                assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, D(2 * ncv * 3, 3, 3), tbl, None, fg)
-                fg.Fence(True)                             # the next kernel reads block 1-b
+            if NB == 2:
+                for f in range(per_graph):
+                    b = f % 2
+                    fg.Fence(False)                        # side waits for main: block 1-b's last reader has finished
+                    exchange(1 - b, side)
+                    assert osd.B200Evaluator.EvalStencils(vb, D(b * ncv * 3, 3, 3), vb, dst5, tbl, None, fg)
+                    fg.Fence(True)                         # the next kernel reads block 1-b
+            else:
+                # frame f's kernel reads block f % 3 and waits only for ITS pull (issued two frames earlier); the pull for
+                # frame f+2 is issued after the kernel and waits only for frame f-1's kernel, the last reader of its block
+                for f in range(per_graph):
+                    fg.Fence(False)                        # what the side stream issues from here on waits for kernel f-1
+                    assert osd.B200Evaluator.EvalStencils(vb, D((f % 3) * ncv * 3, 3, 3), vb, dst5, tbl, None, fg)
+                    fg.Fence(True)                         # kernels from f+1 on wait for the pulls issued so far (up to f+1)
+                    exchange((f + 2) % 3, side)
+                fg.Fence(True)                             # join the side stream before the capture ends
             assert fg.End()
             phase = {"v": 0}
 
@@ -807,7 +821,7 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
             steps = (steps + per_graph - 1) // per_graph * per_graph
             ms = timed_steps(torch, dist, world, step_graph, steps, (max(warmup, 1) + per_graph - 1) // per_graph * per_graph, gstream)
             launch = (f"b200osd frame graph of {per_graph} frames (kernel || exchange of the other control block), "
-                      f"one cudaGraphLaunch per {per_graph} frames")
+                      f"one cudaGraphLaunch per {per_graph} frames; {NB} control blocks")
         except Exception as exc:
             log(f"[bench] rank {rank}: config-5 frame graph failed ({exc}); eager pipeline")
             ms = None
@@ -830,7 +844,7 @@ def bench_config5_strong(torch, dist, osd, capi, shard, comm, world, rank, steps
             "exchange": {"none": "none (1 GPU)",
                          "window_locality": f"rows dealt out by locality (b200osd_shard_plan_locality); rank 0 pulls {12 * sum(b - a for a, b in runs)} B "
                                             f"of the {ncv * 12} B of control points per frame in {len(runs)} DMA run(s) from the root's peer-memory "
-                                            "window (" + ("b200osd_window_pull: wait + copy + signal in one kernel" if pull_kernel else "b200osd_window_get") + "), side stream, double-buffered",
+                                            "window (" + ("b200osd_window_pull: wait + copy + signal in one kernel" if pull_kernel else "b200osd_window_get") + "), side stream, three control blocks",
                          "broadcast": f"b200osd_comm_broadcast of {ncv * 12} B per frame from rank 0, side stream, double-buffered",
                          "scatter_allgather": f"{ncv * 12} B per frame from rank 0 as b200osd_comm_scatter ({per * 4} B per rank) + in-place "
                                               "b200osd_comm_all_gather, side stream, double-buffered"}[mode],
