@@ -1063,7 +1063,11 @@ def run_b200_arm(args):
     iters = 20
     config5 = None
     if not args.headline_only:
-        config5 = bench_config5_strong(torch, dist, osd, capi, shard, comm_wide, world, rank, max(20, min(args.steps, 100)), max(args.warmup, 5))
+        try:
+            config5 = bench_config5_strong(torch, dist, osd, capi, shard, comm_wide, world, rank, max(20, min(args.steps, 100)), max(args.warmup, 5))
+        except Exception as exc:          # a section is a report, never a reason to lose the headline number
+            log(f"[bench] rank {rank}: config-5 section failed: {type(exc).__name__}: {exc}")
+            config5 = {"error": f"{type(exc).__name__}: {exc}"}
     config3 = patches = patches_loop = incumbent = None
     if world == 1 and not args.headline_only:
         for name, fn in (("config3", lambda: bench_config3(mesh, torch, osd, iters)),
