@@ -112,7 +112,10 @@ B200OSD_API int    b200osd_vertex_buffer_read(b200osd_vertex_buffer *vb, float *
  * control-index order instead of the table's own order -- neighbouring rows then gather the same vertices at the same
  * step (-7 % time on config 2); same terms, measured <= 3.4e-7 of sum|w||x| away from the reference order on every
  * fixture.  bit 4 (16) = keep the table's order everywhere (bit-identical to the reference's CUDA kernel);
- * bit 3 (8) = sort every row, including rows of 100+ terms (which may then differ by > 1e-6).                          */
+ * bit 3 (8) = sort every row, including rows of 100+ terms (which may then differ by > 1e-6).
+ * The bucketed copy is built on the device from the uploaded arrays (the host orders the rows by size and lays out the
+ * slices; the passes over the elements are kernels); bit 5 (32) = build it on the host instead (the same bytes; bits 1 and
+ * 3 imply it).                                                                                                          */
 B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
         int numStencils, int numControlVertices,
         const int *sizes, const int *offsets, const int *indices, const float *weights,

@@ -266,6 +266,178 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
     return B200OSD_OK;
 }
 
+// ---- the same layout built ON THE DEVICE from the verbatim device copies ------------------------------------------
+// The host only orders the rows (it needs nothing but their sizes) and lays out the slices; the two passes over the
+// elements -- the index extent of every slice, and the element-major fill of the index pool and the weight streams -- run
+// as kernels over arrays that are on the device anyway (uploaded by Create, or written there by the limit-stencil
+// builder).  A warp per slice, a lane per row; every (group, lane) slot is written as one 8- or 16-byte store.
+struct SliceExtent { int maxSize, lo, hi; };
+
+__global__ void __launch_bounds__(128) sell_extent_kernel(const int *rows, const int *sizes, const int *offsets, const int *indices,
+                                                          int numSlices, SliceExtent *out) {
+    const int lane = threadIdx.x & 31;
+    const int s = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (s >= numSlices) return;
+    const int row = rows[(size_t)s * kSliceRows + lane];
+    int sz = 0, lo = 0x7fffffff, hi = -1;
+    if (row >= 0) {
+        sz = sizes[row];
+        const int *ix = indices + offsets[row];
+        for (int j = 0; j < sz; ++j) { const int v = ix[j]; lo = min(lo, v); hi = max(hi, v); }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        sz = max(sz, __shfl_xor_sync(0xffffffffu, sz, d));
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if (lane == 0) { out[s].maxSize = sz; out[s].lo = lo; out[s].hi = hi; }
+}
+
+// sortShort: rows of <= kShortRow elements list their elements in control-index order (stable), like build_sell's default
+template <int K>
+__global__ void __launch_bounds__(128) sell_fill_kernel(const int *rows, const int *sizes, const int *offsets, const int *indices,
+                                                        const float *w0, const float *w1, const float *w2, const float *w3,
+                                                        const float *w4, const float *w5, const int4 *meta, int numSlices,
+                                                        bool sortShort, uint2 *pool, float4 *o0, float4 *o1, float4 *o2,
+                                                        float4 *o3, float4 *o4, float4 *o5) {
+    const int lane = threadIdx.x & 31;
+    const int s = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (s >= numSlices) return;
+    const int row = rows[(size_t)s * kSliceRows + lane];
+    if (row < 0) return;                                          // the slot stays zero (memset)
+    const int sz = sizes[row], off = offsets[row];
+    if (sz <= 0) return;
+    const int4 m = meta[s];
+    const int lenVec = m.y, lo = m.z;
+    const float *wsrc[6] = { w0, w1, w2, w3, w4, w5 };
+    float4 *wdst[6] = { o0, o1, o2, o3, o4, o5 };
+    // element order of the row: pos[j] = original position of its j-th element
+    int pos[kShortRow];
+    const bool sorted = sortShort && sz <= kShortRow;
+    if (sorted) {
+        int key[kShortRow];
+        for (int j = 0; j < sz; ++j) {                            // stable insertion sort by control index
+            const int v = indices[off + j];
+            int q = j;
+            while (q > 0 && key[q - 1] > v) { key[q] = key[q - 1]; pos[q] = pos[q - 1]; --q; }
+            key[q] = v;
+            pos[q] = j;
+        }
+    }
+    uint2 *sp = pool + (size_t)(unsigned)m.w;
+    for (int g = 0; g < lenVec; ++g) {
+        int e[kVec];
+        bool real[kVec];
+#pragma unroll
+        for (int c = 0; c < kVec; ++c) {
+            const int j = g * kVec + c;
+            real[c] = j < sz;
+            const int jj = real[c] ? j : 0;                       // padded slots repeat the row's first element (weight 0)
+            e[c] = off + (sorted ? pos[jj] : jj);
+        }
+        const size_t slot = (size_t)g * kSliceRows + lane;
+        int ix[kVec];
+#pragma unroll
+        for (int c = 0; c < kVec; ++c) ix[c] = indices[e[c]];
+        if (lo >= 0) {
+            uint2 v;
+            v.x = (unsigned)((ix[0] - lo) & 0xffff) | ((unsigned)((ix[1] - lo) & 0xffff) << 16);
+            v.y = (unsigned)((ix[2] - lo) & 0xffff) | ((unsigned)((ix[3] - lo) & 0xffff) << 16);
+            sp[slot] = v;
+        } else {
+            reinterpret_cast<int4 *>(sp)[slot] = make_int4(ix[0], ix[1], ix[2], ix[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float4 v;
+            v.x = real[0] ? wsrc[k][e[0]] : 0.0f;
+            v.y = real[1] ? wsrc[k][e[1]] : 0.0f;
+            v.z = real[2] ? wsrc[k][e[2]] : 0.0f;
+            v.w = real[3] ? wsrc[k][e[3]] : 0.0f;
+            wdst[k][(size_t)(unsigned)m.x + slot] = v;
+        }
+    }
+}
+
+// sizes: host copy of the row sizes (all the host needs).  sortMode 0 or 1 (2 and the locality order stay on the host).
+int build_sell_device(b200osd_stencil_table *t, const int *sizes, bool allowIdx16, int sortMode) {
+    const int n = t->n;
+    t->window = kWindowRows;
+    const int numWindows = (n + kWindowRows - 1) / kWindowRows;
+    t->windowSliceStart.assign((size_t)numWindows + 1, 0);
+    for (int wdw = 0; wdw < numWindows; ++wdw) {
+        const int rowsHere = std::min(n, (wdw + 1) * kWindowRows) - wdw * kWindowRows;
+        t->windowSliceStart[(size_t)wdw + 1] = t->windowSliceStart[(size_t)wdw] + (rowsHere + kSliceRows - 1) / kSliceRows;
+    }
+    t->numSlices = t->windowSliceStart[(size_t)numWindows];
+    std::vector<int> rows((size_t)t->numSlices * kSliceRows, -1);
+    parallel_ranges(numWindows, 64, [&](int w0, int w1) {
+        std::vector<int> ord(kWindowRows);
+        for (int wdw = w0; wdw < w1; ++wdw) {
+            const int r0 = wdw * kWindowRows, r1 = std::min(n, r0 + kWindowRows);
+            std::iota(ord.begin(), ord.begin() + (r1 - r0), r0);
+            std::stable_sort(ord.begin(), ord.begin() + (r1 - r0), [&](int a, int b) { return sizes[a] < sizes[b]; });
+            std::copy(ord.begin(), ord.begin() + (r1 - r0), rows.begin() + (size_t)t->windowSliceStart[(size_t)wdw] * kSliceRows);
+        }
+    });
+    int rc = upload(&t->d_rows, rows.data(), rows.size());
+    if (rc) return rc;
+    // pass 1 on the device: size and index extent of every slice
+    SliceExtent *dExt = nullptr;
+    if (cudaMalloc((void **)&dExt, (size_t)t->numSlices * sizeof(SliceExtent)) != cudaSuccess) {
+        set_error("cudaMalloc of the slice extents failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return B200OSD_ERR_ALLOC;
+    }
+    const int blocks = (int)(((size_t)t->numSlices * 32 + 127) / 128);
+    sell_extent_kernel<<<blocks, 128>>>(t->d_rows, t->d_sizes, t->d_offsets, t->d_indices, t->numSlices, dExt);
+    std::vector<SliceExtent> ext((size_t)t->numSlices);
+    cudaError_t e = cudaMemcpy(ext.data(), dExt, ext.size() * sizeof(SliceExtent), cudaMemcpyDeviceToHost);
+    cudaFree(dExt);
+    if (e != cudaSuccess) { set_error("slice extents: %s", cudaGetErrorString(e)); return B200OSD_ERR_CUDA; }
+    // slice bases (serial, one entry per 32 rows)
+    std::vector<int4> meta((size_t)t->numSlices);
+    size_t poolUnits = 0, totalVec = 0;
+    for (int s = 0; s < t->numSlices; ++s) {
+        int lo = ext[(size_t)s].lo, hi = ext[(size_t)s].hi;
+        if (hi < 0) { lo = 0; hi = 0; }
+        const bool is16 = allowIdx16 && (hi - lo <= 0xffff);
+        const int lenVec = (ext[(size_t)s].maxSize + kVec - 1) / kVec;
+        if (!is16 && (poolUnits & 1)) ++poolUnits;      // 32-bit groups are int4: keep them 16-byte aligned
+        if (totalVec > 0xffffffffull - (size_t)lenVec * kSliceRows) { set_error("stencil table too large for 32-bit slice bases"); return B200OSD_ERR_UNSUPPORTED; }
+        if (poolUnits > 0xffffffffull - 2ull * lenVec * kSliceRows) { set_error("stencil table too large for 32-bit index-pool offsets"); return B200OSD_ERR_UNSUPPORTED; }
+        meta[(size_t)s] = make_int4((int)(unsigned)totalVec, lenVec, is16 ? lo : -1, (int)(unsigned)poolUnits);
+        poolUnits += (size_t)lenVec * kSliceRows * (is16 ? 1 : 2);
+        t->slices16 += is16 ? 1 : 0;
+        totalVec += (size_t)lenVec * kSliceRows;
+    }
+    t->totalVec = totalVec;
+    t->ipoolUnits = poolUnits;
+    rc = upload(&t->d_meta, meta.data(), meta.size());
+    if (rc) return rc;
+    // pass 2 on the device: the fill
+    auto zeroed = [&](void **p, size_t bytes) -> int {
+        *p = nullptr;
+        if (bytes == 0) return B200OSD_OK;
+        if (cudaMalloc(p, bytes) != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(cudaGetLastError())); *p = nullptr; return B200OSD_ERR_ALLOC; }
+        if (cudaMemset(*p, 0, bytes) != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(cudaGetLastError())); return B200OSD_ERR_CUDA; }
+        return B200OSD_OK;
+    };
+    rc = zeroed((void **)&t->d_ipool, poolUnits * sizeof(uint2));
+    for (int k = 0; k < t->numW && !rc; ++k) rc = zeroed((void **)&t->d_w4[k], totalVec * sizeof(float4));
+    if (rc) return rc;
+    const bool sortShort = sortMode == 1;
+#define B200_FILL(K)                                                                                                          \
+    sell_fill_kernel<K><<<blocks, 128>>>(t->d_rows, t->d_sizes, t->d_offsets, t->d_indices, t->d_w[0], t->d_w[1], t->d_w[2], \
+                                         t->d_w[3], t->d_w[4], t->d_w[5], t->d_meta, t->numSlices, sortShort, t->d_ipool,     \
+                                         t->d_w4[0], t->d_w4[1], t->d_w4[2], t->d_w4[3], t->d_w4[4], t->d_w4[5])
+    if (t->numW == 1) B200_FILL(1); else if (t->numW == 3) B200_FILL(3); else B200_FILL(6);
+#undef B200_FILL
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("bucketed layout kernels: %s", cudaGetErrorString(e)); return B200OSD_ERR_CUDA; }
+    t->hasSell = true;
+    return B200OSD_OK;
+}
+
 // Validation shared by both entry points.  Returns B200OSD_OK with *noop = true for end <= start.
 int prepare_io(StencilIO &io, const float *src, const int srcDesc[3], int nOut, float *const dsts[],
                const int dstDescs[][3], int start, int end, bool *noop) {
@@ -571,11 +743,20 @@ b200osd_stencil_table *adopt_device_table(const AdoptedArrays &a, int flags) {
     t->d_sizes = a.sizes; t->d_offsets = a.offsets; t->d_indices = a.indices;
     for (int k = 0; k < kMaxOut; ++k) t->d_w[k] = a.w[k];
     if ((flags & 1) || a.numStencils == 0) return t;
-    // the bucketed layout is built on the host: one read-back of the finished table
-    std::vector<int> sizes((size_t)a.numStencils), offsets((size_t)a.numStencils), indices((size_t)a.numElements);
+    std::vector<int> sizes((size_t)a.numStencils);
+    if (cudaMemcpy(sizes.data(), a.sizes, sizes.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("adopt_device_table: read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail();
+    }
+    if (!(flags & (2 | 8 | 32))) {
+        // the bucketed layout is built where the table is: the host sees the row sizes only
+        if (build_sell_device(t, sizes.data(), !(flags & 4), (flags & 16) ? 0 : 1) != B200OSD_OK) return fail();
+        return t;
+    }
+    // host builder (locality order, sort of long rows, bit 5): one read-back of the finished table
+    std::vector<int> offsets((size_t)a.numStencils), indices((size_t)a.numElements);
     std::vector<std::vector<float>> w((size_t)a.numW, std::vector<float>((size_t)a.numElements));
-    bool ok = cudaMemcpy(sizes.data(), a.sizes, sizes.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
-              cudaMemcpy(offsets.data(), a.offsets, offsets.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+    bool ok = cudaMemcpy(offsets.data(), a.offsets, offsets.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
               cudaMemcpy(indices.data(), a.indices, indices.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
     const float *wp[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     for (int k = 0; ok && k < a.numW; ++k) {
@@ -628,7 +809,12 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, int numCont
     if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
     for (int k = 0; k < t->numW && !rc; ++k) rc = upload(&t->d_w[k], w[k], (size_t)ne);
-    if (!rc && !(flags & 1) && numStencils > 0) rc = build_sell(t, sizes, offsets, indices, w, (flags & 2) != 0, !(flags & 4), (flags & 8) ? 2 : ((flags & 16) ? 0 : 1));
+    if (!rc && !(flags & 1) && numStencils > 0) {
+        // the two passes over the elements run on the device (the arrays were just uploaded); the locality order of rows, the
+        // sort of long rows and bit 5 keep the host builder
+        if (flags & (2 | 8 | 32)) rc = build_sell(t, sizes, offsets, indices, w, (flags & 2) != 0, !(flags & 4), (flags & 8) ? 2 : ((flags & 16) ? 0 : 1));
+        else rc = build_sell_device(t, sizes, !(flags & 4), (flags & 16) ? 0 : 1);
+    }
     if (rc) {
         b200osd_stencil_table_destroy(t);
         return nullptr;

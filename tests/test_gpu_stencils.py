@@ -111,6 +111,36 @@ def test_limit_stencils_with_derivatives(name, nw):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("name", golden_names("stencils_") + golden_names("limit_"))
+def test_bucketed_layout_built_on_the_device_equals_the_host_builder(name):
+    """The bucketed copy is laid out by kernels from the uploaded arrays (sell_extent_kernel / sell_fill_kernel); flag 32
+    keeps the host builder.  Same slices, same bytes: evaluations are bit-identical and stream the same number of bytes,
+    with 16- and 32-bit slice indices, in the default and in the table's own summation order, for 1 / 3 / 6 weight streams."""
+    from opensubdiv_b200 import capi
+    d = golden(name)
+    t = table_from(d, "t_")
+    n = t.num_stencils
+    nw = 6 if t.dvv is not None else (3 if t.du is not None else 1)
+    src = dev(d["src"])
+    L = d["src"].shape[1]
+    for kw in ({}, {"keep_order": True}, {"idx16": False}):
+        a_tbl = osd.B200StencilTable.Create(t, **kw)
+        b_tbl = osd.B200StencilTable.Create(t, host_layout=True, **kw)
+        for k in (1, 3, 6):
+            if k > nw:
+                continue
+            assert capi.lib().b200osd_stencil_table_stream_bytes(a_tbl._h, k) == capi.lib().b200osd_stencil_table_stream_bytes(b_tbl._h, k)
+            a = torch.full((n, L * k), float("nan"), device="cuda")
+            b = torch.full((n, L * k), float("nan"), device="cuda")
+            aa, bb = [], []
+            for q in range(k):
+                aa += [a, D(L * q, L, L * k)]
+                bb += [b, D(L * q, L, L * k)]
+            assert osd.B200Evaluator.EvalStencils(src, D(0, L, L), *aa, a_tbl)
+            assert osd.B200Evaluator.EvalStencils(src, D(0, L, L), *bb, b_tbl)
+            assert torch.equal(a, b), (name, kw, k)
+
+
 @pytest.mark.parametrize("L,stride,offset", [(1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (5, 5, 0), (6, 6, 0), (8, 8, 0),
                                              (12, 12, 0), (3, 4, 1), (6, 9, 2), (4, 8, 4), (3, 7, 2), (1, 5, 4), (17, 20, 1)])
 def test_descriptors_lengths_strides_offsets(L, stride, offset):
