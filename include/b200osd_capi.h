@@ -124,7 +124,7 @@ B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
 /* The same from DEVICE arrays in the reference layout -- what a client holds that already built an Osd::CudaStencilTable
  * (osd/cudaEvaluator.h:57-90: GetSizesBuffer() ... GetDvvWeightsBuffer()).  Instead of evaluating those arrays row by row
  * through b200osd_eval_stencils (thread per row, ~55 % of the roofline), convert once and evaluate through the table.
- * Synchronous; the client's arrays are only read. */
+ * Synchronous; the client's arrays are only read (copied device to device; the host sees the row sizes and offsets only). */
 B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create_from_device(
         int numStencils, int numControlVertices,
         const int *sizes, const int *offsets, const int *indices, const float *weights,

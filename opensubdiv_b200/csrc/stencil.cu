@@ -273,6 +273,13 @@ int build_sell(b200osd_stencil_table *t, const int *sizes, const int *offsets, c
 // builder).  A warp per slice, a lane per row; every (group, lane) slot is written as one 8- or 16-byte store.
 struct SliceExtent { int maxSize, lo, hi; };
 
+__global__ void __launch_bounds__(256) max_index_kernel(const int *indices, long long ne, int *out) {
+    int m = -1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) m = max(m, indices[i]);
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(out, m);
+}
+
 __global__ void __launch_bounds__(128) sell_extent_kernel(const int *rows, const int *sizes, const int *offsets, const int *indices,
                                                           int numSlices, SliceExtent *out) {
     const int lane = threadIdx.x & 31;
@@ -830,7 +837,9 @@ b200osd_stencil_table *b200osd_stencil_table_create_from_device(int numStencils,
         set_error("stencil_table_create_from_device: missing arrays");
         return nullptr;
     }
-    // one read-back of the client's arrays (an Osd::CudaStencilTable keeps no host copy), then the ordinary create
+    // The host reads back the row sizes and offsets only; indices and weights are copied device to device into the
+    // table's own arrays and the bucketed layout is built from them there.  (A table whose indices reach past the control
+    // vertices -- unfactorized -- or one of the host-built orders takes the round trip through the host create.)
     std::vector<int> hs((size_t)numStencils), ho((size_t)numStencils);
     auto pull = [](void *dst, const void *src, size_t bytes) { return bytes == 0 || cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
     bool ok = pull(hs.data(), sizes, hs.size() * 4) && pull(ho.data(), offsets, ho.size() * 4);
@@ -839,20 +848,56 @@ b200osd_stencil_table *b200osd_stencil_table_create_from_device(int numStencils,
         if (hs[(size_t)i] < 0 || ho[(size_t)i] < 0) { set_error("stencil_table_create_from_device: negative size / offset in row %d", i); return nullptr; }
         ne = std::max<long long>(ne, (long long)ho[(size_t)i] + hs[(size_t)i]);
     }
-    std::vector<int> hi((size_t)ne);
-    const float *dw[kMaxOut] = { weights, du, dv, duu, duv, dvv };
-    std::vector<std::vector<float>> hw(kMaxOut);
-    const float *hp[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    ok = ok && pull(hi.data(), indices, hi.size() * 4);
-    for (int k = 0; ok && k < kMaxOut; ++k) {
-        if (!dw[k]) continue;
-        hw[(size_t)k].resize((size_t)ne);
-        ok = pull(hw[(size_t)k].data(), dw[k], (size_t)ne * 4);
-        hp[k] = hw[(size_t)k].data();
-    }
     if (!ok) { set_error("stencil_table_create_from_device: read-back failed: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
-    return b200osd_stencil_table_create(numStencils, numControlVertices, hs.data(), ho.data(), hi.data(), hp[0], hp[1], hp[2],
-                                        hp[3], hp[4], hp[5], flags);
+    const float *dw[kMaxOut] = { weights, du, dv, duu, duv, dvv };
+    int maxIdx = -1;
+    if (ne > 0) {
+        int *dMax = nullptr;
+        ok = cudaMalloc((void **)&dMax, sizeof(int)) == cudaSuccess && cudaMemset(dMax, 0xff, sizeof(int)) == cudaSuccess;
+        if (ok) {
+            max_index_kernel<<<(int)std::min<long long>((ne + 255) / 256, 4096), 256>>>(indices, ne, dMax);
+            ok = cudaMemcpy(&maxIdx, dMax, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        cudaFree(dMax);
+        if (!ok) { set_error("stencil_table_create_from_device: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
+    }
+    const int nCV = numControlVertices > 0 ? numControlVertices : maxIdx + 1;
+    if (maxIdx >= nCV || (flags & (2 | 8 | 32))) {
+        std::vector<int> hi((size_t)ne);
+        std::vector<std::vector<float>> hw(kMaxOut);
+        const float *hp[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+        ok = pull(hi.data(), indices, hi.size() * 4);
+        for (int k = 0; ok && k < kMaxOut; ++k) {
+            if (!dw[k]) continue;
+            hw[(size_t)k].resize((size_t)ne);
+            ok = pull(hw[(size_t)k].data(), dw[k], (size_t)ne * 4);
+            hp[k] = hw[(size_t)k].data();
+        }
+        if (!ok) { set_error("stencil_table_create_from_device: read-back failed: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
+        return b200osd_stencil_table_create(numStencils, numControlVertices, hs.data(), ho.data(), hi.data(), hp[0], hp[1], hp[2],
+                                            hp[3], hp[4], hp[5], flags);
+    }
+    AdoptedArrays a;
+    std::memset(&a, 0, sizeof(a));
+    a.numStencils = numStencils;
+    a.numControlVertices = nCV;
+    a.numElements = ne;
+    a.numW = (du && dv) ? ((duu && duv && dvv) ? 6 : 3) : 1;
+    auto clone = [&](void **dst, const void *src, size_t bytes) {
+        *dst = nullptr;
+        if (bytes == 0) return true;
+        return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyDeviceToDevice) == cudaSuccess;
+    };
+    ok = clone((void **)&a.sizes, sizes, (size_t)numStencils * 4) && clone((void **)&a.offsets, offsets, (size_t)numStencils * 4) &&
+         clone((void **)&a.indices, indices, (size_t)ne * 4);
+    for (int k = 0; ok && k < a.numW; ++k) ok = clone((void **)&a.w[k], dw[k], (size_t)ne * 4);
+    if (!ok) {
+        set_error("stencil_table_create_from_device: device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(a.sizes); cudaFree(a.offsets); cudaFree(a.indices);
+        for (int k = 0; k < kMaxOut; ++k) cudaFree(a.w[k]);
+        return nullptr;
+    }
+    return adopt_device_table(a, flags);
 }
 
 void b200osd_stencil_table_destroy(b200osd_stencil_table *t) {
