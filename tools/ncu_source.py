@@ -18,9 +18,13 @@ ia, isrc, iinst, isamp = hdr.index("Address"), hdr.index("Source"), hdr.index("I
 ops, samp = Counter(), Counter()
 total = 0
 lines = []
+seen = set()
 for r in rows[2:]:
     if len(r) <= iinst:
         continue
+    if r[ia] in seen:             # the page lists every instruction twice (two views): count each address once
+        continue
+    seen.add(r[ia])
     try:
         n = int(r[iinst]); s = int(r[isamp])
     except ValueError:
