@@ -185,3 +185,21 @@ def test_plain_c_example_builds_against_the_abi(tmp_path):
         assert r.returncode == 0 and "refined[4] = 0.5 0.5 0.125" in r.stdout, r.stdout
     else:
         assert r.returncode == 2 and "no CUDA device" in r.stdout
+
+
+def test_plain_c_sharding_example_runs_on_the_host(tmp_path):
+    """examples/c_shard_example.c: the partitioning entries of the multi-GPU data plane (b200osd_shard_plan,
+    _shard_plan_locality, _shard_control_runs) called from C99 -- host-only functions, so the example runs here."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not found")
+    exe = str(tmp_path / "c_shard_example")
+    libdir = os.path.join(ROOT, "opensubdiv_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_shard_example.c"), "-L", libdir, "-lb200osd",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout
+    assert "rank 0: contiguous rows [0,16) | by locality 16 rows, control vertices [0,64) in 2 run(s): [0,16) [63,64) = 17 of 64" in r.stdout
+    assert "rank 3:" in r.stdout and "[47,64) = 17 of 64" in r.stdout
