@@ -153,18 +153,18 @@ __device__ int ref_patch_weights(int type, float s, float t, int boundary, int o
                 const int k = 2 * (i / 5) + (p - 3);
                 const float g = G[k], D = R[i / 5];
                 w[i] = bs[col] * bt[row] * g;
-                const float Gds = (NDS[k] - DDS[k] * g) * D;
-                const float Gdt = (NDT[k] - DDT[k] * g) * D;
-                w[20 + i] = (ds[col] * g + bs[col] * Gds) * bt[row];
-                w[40 + i] = (dt[row] * g + bt[row] * Gdt) * bs[col];
+                const float g_s = (NDS[k] - DDS[k] * g) * D;
+                const float g_t = (NDT[k] - DDT[k] * g) * D;
+                w[20 + i] = (ds[col] * g + bs[col] * g_s) * bt[row];
+                w[40 + i] = (dt[row] * g + bt[row] * g_t) * bs[col];
                 if (order >= 2) {
-                    const float Dsq = D * D;
-                    const float Gdss = 2.0f * DDS[k] * Dsq * (g * DDS[k] - NDS[k]);
-                    const float Gdst = Dsq * (2.0f * g * DDS[k] * DDT[k] - NDS[k] * DDT[k] - NDT[k] * DDS[k]);
-                    const float Gdtt = 2.0f * DDT[k] * Dsq * (g * DDT[k] - NDT[k]);
-                    w[60 + i] = (dss[col] * g + 2.0f * ds[col] * Gds + bs[col] * Gdss) * bt[row];
-                    w[80 + i] = bt[row] * (bs[col] * Gdst + ds[col] * Gdt) + dt[row] * (ds[col] * g + bs[col] * Gds);
-                    w[100 + i] = (dtt[row] * g + 2.0f * dt[row] * Gdt + bt[row] * Gdtt) * bs[col];
+                    const float invD2 = D * D;
+                    const float g_ss = 2.0f * DDS[k] * invD2 * (g * DDS[k] - NDS[k]);
+                    const float g_st = invD2 * (2.0f * g * DDS[k] * DDT[k] - NDS[k] * DDT[k] - NDT[k] * DDS[k]);
+                    const float g_tt = 2.0f * DDT[k] * invD2 * (g * DDT[k] - NDT[k]);
+                    w[60 + i] = (dss[col] * g + 2.0f * ds[col] * g_s + bs[col] * g_ss) * bt[row];
+                    w[80 + i] = bt[row] * (bs[col] * g_st + ds[col] * g_t) + dt[row] * (ds[col] * g + bs[col] * g_s);
+                    w[100 + i] = (dtt[row] * g + 2.0f * dt[row] * g_t + bt[row] * g_tt) * bs[col];
                 }
             } else if (p >= 3) {
                 const float g = G[2 * (i / 5) + (p - 3)];

@@ -415,19 +415,19 @@ B200_HD void eval_gregory(const CV &cv, float s, float t, float d1, bool trueDer
             constexpr float DDT[8] = { 1.0f, 1.0f, 1.0f, 1.0f, -1.0f, -1.0f, -1.0f, -1.0f };
             const int k = 2 * (i / 5) + (p - 3);
             const float D = R[i / 5];
-            const float Gds = (NDS[k] - DDS[k] * g) * D * d1, Gdt = (NDT[k] - DDT[k] * g) * D * d1;
-            const float ws = ds[col] * g + bs[col] * Gds;          // d/ds (Bs G)
-            const float wt = dt[row] * g + bt[row] * Gdt;          // d/dt (Bt G)
+            const float g_s = (NDS[k] - DDS[k] * g) * D * d1, g_t = (NDT[k] - DDT[k] * g) * D * d1;
+            const float ws = ds[col] * g + bs[col] * g_s;          // d/ds (Bs G)
+            const float wt = dt[row] * g + bt[row] * g_t;          // d/dt (Bt G)
             w[1] = ws * bt[row];
             w[2] = wt * bs[col];
             if (ORDER >= 2) {
-                const float Dsq = D * D * d2;
-                const float Gdss = 2.0f * DDS[k] * Dsq * (g * DDS[k] - NDS[k]);
-                const float Gdst = Dsq * (2.0f * g * DDS[k] * DDT[k] - NDS[k] * DDT[k] - NDT[k] * DDS[k]);
-                const float Gdtt = 2.0f * DDT[k] * Dsq * (g * DDT[k] - NDT[k]);
-                w[3] = (dss[col] * g + 2.0f * ds[col] * Gds + bs[col] * Gdss) * bt[row];
-                w[4] = bt[row] * (bs[col] * Gdst + ds[col] * Gdt) + dt[row] * ws;
-                w[5] = (dtt[row] * g + 2.0f * dt[row] * Gdt + bt[row] * Gdtt) * bs[col];
+                const float invD2 = D * D * d2;
+                const float g_ss = 2.0f * DDS[k] * invD2 * (g * DDS[k] - NDS[k]);
+                const float g_st = invD2 * (2.0f * g * DDS[k] * DDT[k] - NDS[k] * DDT[k] - NDT[k] * DDS[k]);
+                const float g_tt = 2.0f * DDT[k] * invD2 * (g * DDT[k] - NDT[k]);
+                w[3] = (dss[col] * g + 2.0f * ds[col] * g_s + bs[col] * g_ss) * bt[row];
+                w[4] = bt[row] * (bs[col] * g_st + ds[col] * g_t) + dt[row] * ws;
+                w[5] = (dtt[row] * g + 2.0f * dt[row] * g_t + bt[row] * g_tt) * bs[col];
             }
         } else {
             if (ORDER >= 1) { w[1] = ds[col] * g * gt; w[2] = gs * dt[row]; }

@@ -310,18 +310,18 @@ static int basis_gregory(real s, real t, real *w[6], int order)
             real D = R[i / 5];
             w[0][i] = bs[col] * bt[row] * g;
             if (order >= 1) {
-                real Gds = (GREG_NDS[k] - GREG_DDS[k] * g) * D;
-                real Gdt = (GREG_NDT[k] - GREG_DDT[k] * g) * D;
-                w[1][i] = (ds[col] * g + bs[col] * Gds) * bt[row];
-                w[2][i] = (dt[row] * g + bt[row] * Gdt) * bs[col];
+                real g_s = (GREG_NDS[k] - GREG_DDS[k] * g) * D;
+                real g_t = (GREG_NDT[k] - GREG_DDT[k] * g) * D;
+                w[1][i] = (ds[col] * g + bs[col] * g_s) * bt[row];
+                w[2][i] = (dt[row] * g + bt[row] * g_t) * bs[col];
                 if (order >= 2) {
-                    real Dsqr_inv = D * D;
-                    real Gdss = 2.0f * GREG_DDS[k] * Dsqr_inv * (g * GREG_DDS[k] - GREG_NDS[k]);
-                    real Gdst = Dsqr_inv * (2.0f * g * GREG_DDS[k] * GREG_DDT[k] - GREG_NDS[k] * GREG_DDT[k] - GREG_NDT[k] * GREG_DDS[k]);
-                    real Gdtt = 2.0f * GREG_DDT[k] * Dsqr_inv * (g * GREG_DDT[k] - GREG_NDT[k]);
-                    w[3][i] = (dss[col] * g + 2.0f * ds[col] * Gds + bs[col] * Gdss) * bt[row];
-                    w[4][i] = bt[row] * (bs[col] * Gdst + ds[col] * Gdt) + dt[row] * (ds[col] * g + bs[col] * Gds);
-                    w[5][i] = (dtt[row] * g + 2.0f * dt[row] * Gdt + bt[row] * Gdtt) * bs[col];
+                    real invD2 = D * D;
+                    real g_ss = 2.0f * GREG_DDS[k] * invD2 * (g * GREG_DDS[k] - GREG_NDS[k]);
+                    real g_st = invD2 * (2.0f * g * GREG_DDS[k] * GREG_DDT[k] - GREG_NDS[k] * GREG_DDT[k] - GREG_NDT[k] * GREG_DDS[k]);
+                    real g_tt = 2.0f * GREG_DDT[k] * invD2 * (g * GREG_DDT[k] - GREG_NDT[k]);
+                    w[3][i] = (dss[col] * g + 2.0f * ds[col] * g_s + bs[col] * g_ss) * bt[row];
+                    w[4][i] = bt[row] * (bs[col] * g_st + ds[col] * g_t) + dt[row] * (ds[col] * g + bs[col] * g_s);
+                    w[5][i] = (dtt[row] * g + 2.0f * dt[row] * g_t + bt[row] * g_tt) * bs[col];
                 }
             }
         } else if (rational) {
