@@ -81,3 +81,46 @@ def test_interior_regular_patches_meet_the_plain_bound():
                             tr.indices, tr.params)
     for k in range(6):
         assert_close(got[k], d["out_" + OUT6[k]][interior], scl[k], f"interior {OUT6[k]}")
+
+
+def _all_shapes():
+    from oracle import ref
+    return [s for s in ref.shape_names() if not s.startswith("bilinear")] if ref.available() else []
+
+
+@pytest.mark.parametrize("shape", _all_shapes())
+def test_patch_kernel_math_on_every_regression_shape(shape):
+    """The CUDA kernel's arithmetic (host emulation) against the unmodified reference's Osd::CpuEvaluator::EvalPatches on
+    EVERY shape of the reference's regression list (regression/osd_regression/main.cpp:250-330): adaptive level 3, Gregory
+    end caps, 1 500 random samples, P + D1 + D2, 1e-6 in the conditioned scale; and the emulated device patch map against
+    Far::PatchMap::FindPatch, bit-exact.  Skipped where the reference build is absent (the GPU box runs the golden subset)."""
+    from oracle import ref
+    L = _lib()
+    m = ref.Mesh.from_shape(shape)
+    # the valence-360 pole costs the reference 100 s of end-cap stencil building at level 3: one level is enough there
+    pt = m.patch_table(1 if shape.endswith("pole360") else 3, end_cap="gregory", inf_sharp=True, legacy_sharp_corner=False)
+    st = m.stencil_table(intermediate_levels=True, patch_table=pt)
+    ncv, n = st.num_control_verts, st.num_stencils
+    vb = np.zeros((ncv + n, 3), np.float32)
+    vb[:ncv] = m.positions
+    assert ref.eval_stencils(vb.reshape(-1), (0, 3, 3), [vb.reshape(-1)], [(ncv * 3, 3, 3)], st)
+    rng = np.random.default_rng(11)
+    k = 1500
+    face = rng.integers(0, m.num_ptex_faces, k).astype(np.int32)
+    s, t = rng.random(k, dtype=np.float32), rng.random(k, dtype=np.float32)
+    s[::37], t[::41] = 0.0, 1.0
+    if m.reg_face_size == 3:
+        flip = s + t >= 1
+        s, t = np.where(flip, 1 - s, s).astype(np.float32), np.where(flip, 1 - t, t).astype(np.float32)
+    want = m.find_patches(pt, face, s, t)
+    pc = np.ascontiguousarray(want[want["arrayIndex"] >= 0])
+    assert len(pc) > 0
+    x = [np.zeros((len(pc), 3), np.float32) for _ in range(6)]
+    z = [np.zeros((len(pc), 3), np.float32) for _ in range(6)]
+    assert ref.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in x], [(0, 3, 3)] * 6, pc, pt.vertex)
+    with oracle.abs_mode(2):
+        oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in z], [(0, 3, 3)] * 6, pc, pt.vertex.arrays,
+                            pt.vertex.indices, pt.vertex.params)
+    got = emu_patches(L, vb.reshape(-1), (0, 3, 3), 3, pc, pt.vertex, 6)
+    for kk in range(6):
+        assert_close(got[kk], x[kk], z[kk], f"{shape} {OUT6[kk]}")

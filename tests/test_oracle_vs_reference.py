@@ -162,7 +162,8 @@ def test_every_regression_shape_stencils_and_patches(shape):
     if shape.startswith("bilinear"):
         return
     m = ref.Mesh.from_shape(shape)
-    pt = m.patch_table(3, end_cap="gregory", inf_sharp=True, legacy_sharp_corner=False)
+    # the valence-360 pole costs the reference 100 s of end-cap stencil building at level 3: one level is enough there
+    pt = m.patch_table(1 if shape.endswith("pole360") else 3, end_cap="gregory", inf_sharp=True, legacy_sharp_corner=False)
     st = m.stencil_table(intermediate_levels=True, patch_table=pt)
     ncv, n = st.num_control_verts, st.num_stencils
     vb = np.zeros((ncv + n, 3), np.float32)
