@@ -115,7 +115,12 @@ B200OSD_API int    b200osd_vertex_buffer_read(b200osd_vertex_buffer *vb, float *
  * bit 3 (8) = sort every row, including rows of 100+ terms (which may then differ by > 1e-6).
  * The bucketed copy is built on the device from the uploaded arrays (the host orders the rows by size and lays out the
  * slices; the passes over the elements are kernels); bit 5 (32) = build it on the host instead (the same bytes; bits 1 and
- * 3 imply it).                                                                                                          */
+ * 3 imply it).
+ * bit 6 (64) = REFERENCE-EXACT arithmetic: only the verbatim layout is kept and rows are evaluated thread per row with a
+ * rounded product added to the running sum in the table's order -- operation for operation what osd/cpuKernel.cpp does,
+ * so every output is BIT-IDENTICAL to Osd::CpuEvaluator / Osd::OmpEvaluator whatever the row length (two correct fp32
+ * summations of n terms, e.g. the fused multiply-adds of the fast path, may differ by ~n * 2^-23 of sum|w||x|).  About half
+ * the speed of the bucketed path; meant for validation and for clients that diff against CPU results.                   */
 B200OSD_API b200osd_stencil_table *b200osd_stencil_table_create(
         int numStencils, int numControlVertices,
         const int *sizes, const int *offsets, const int *indices, const float *weights,

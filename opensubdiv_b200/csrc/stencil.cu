@@ -22,6 +22,7 @@ struct b200osd_stencil_table {
     int nCV = 0;
     int numW = 1;
     int variant = 0;                     // kernel variant for this table (b200osd_stencil_table_set_variant); 0 = auto
+    bool exact = false;                  // flag 64: the reference CPU kernels' arithmetic, verbatim layout only
     // Unfactorized tables (far/stencilTableFactory.h:66-75 factorizeIntermediateLevels = false; far tutorial 4_3): the rows
     // of level l index the vertices of level l-1 (level-local numbering: far/stencilTableFactory.cpp:108-133 never advances
     // the source index), so their indices reach past the control vertices and a caller applies them one level at a time,
@@ -490,24 +491,30 @@ int src_mode(const StencilIO &io) {
     return SRC_SCALAR;
 }
 
-template <int K>
-int launch_csr(const StencilIO &io, const CsrTable &t, cudaStream_t st) {
+template <int K, bool EXACT>
+int launch_csr_as(const StencilIO &io, const CsrTable &t, cudaStream_t st) {
     const int rows = io.end - io.start;
     const int block = 128;
     const int grid = (rows + block - 1) / block;
     const int mode = src_mode(io);
-#define CSR_CASE(LL)                                                                                          \
-    case LL:                                                                                                  \
-        if (mode == SRC_VEC4 && (LL % 4 == 0)) csr_kernel<LL, K, SRC_VEC4><<<grid, block, 0, st>>>(io, t);    \
-        else if (mode >= SRC_VEC2 && (LL % 2 == 0)) csr_kernel<LL, K, SRC_VEC2><<<grid, block, 0, st>>>(io, t); \
-        else csr_kernel<LL, K, SRC_SCALAR><<<grid, block, 0, st>>>(io, t);                                    \
+#define CSR_CASE(LL)                                                                                                    \
+    case LL:                                                                                                            \
+        if (mode == SRC_VEC4 && (LL % 4 == 0)) csr_kernel<LL, K, SRC_VEC4, EXACT><<<grid, block, 0, st>>>(io, t);       \
+        else if (mode >= SRC_VEC2 && (LL % 2 == 0)) csr_kernel<LL, K, SRC_VEC2, EXACT><<<grid, block, 0, st>>>(io, t);  \
+        else csr_kernel<LL, K, SRC_SCALAR, EXACT><<<grid, block, 0, st>>>(io, t);                                       \
         break;
     switch (io.L) {
         CSR_CASE(1) CSR_CASE(2) CSR_CASE(3) CSR_CASE(4) CSR_CASE(6) CSR_CASE(8)
-        default: csr_kernel_anyL<K><<<grid, block, 0, st>>>(io, t); break;
+        default: csr_kernel_anyL<K, EXACT><<<grid, block, 0, st>>>(io, t); break;
     }
 #undef CSR_CASE
     return check_launch("csr_kernel");
+}
+
+// exact: the reference CPU kernels' arithmetic (separate multiply and add) instead of fused multiply-adds
+template <int K>
+int launch_csr(const StencilIO &io, const CsrTable &t, cudaStream_t st, bool exact = false) {
+    return exact ? launch_csr_as<K, true>(io, t, st) : launch_csr_as<K, false>(io, t, st);
 }
 
 // Launch shape of the bucketed kernels.
@@ -662,7 +669,7 @@ int eval_rows(b200osd_stencil_table *t, const StencilIO &io, int nOut, cudaStrea
         CsrTable c;
         c.sizes = t->d_sizes; c.offsets = t->d_offsets; c.indices = t->d_indices;
         for (int k = 0; k < kMaxOut; ++k) c.w[k] = t->d_w[k];
-        return nOut == 1 ? launch_csr<1>(io, c, st) : (nOut == 3 ? launch_csr<3>(io, c, st) : launch_csr<6>(io, c, st));
+        return nOut == 1 ? launch_csr<1>(io, c, st, t->exact) : (nOut == 3 ? launch_csr<3>(io, c, st, t->exact) : launch_csr<6>(io, c, st, t->exact));
     }
     SellTable s;
     s.ipool = t->d_ipool;
@@ -749,7 +756,8 @@ b200osd_stencil_table *adopt_device_table(const AdoptedArrays &a, int flags) {
     t->numW = a.numW;
     t->d_sizes = a.sizes; t->d_offsets = a.offsets; t->d_indices = a.indices;
     for (int k = 0; k < kMaxOut; ++k) t->d_w[k] = a.w[k];
-    if ((flags & 1) || a.numStencils == 0) return t;
+    t->exact = (flags & 64) != 0;
+    if ((flags & (1 | 64)) || a.numStencils == 0) return t;
     std::vector<int> sizes((size_t)a.numStencils);
     if (cudaMemcpy(sizes.data(), a.sizes, sizes.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
         set_error("adopt_device_table: read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -816,7 +824,8 @@ b200osd_stencil_table *b200osd_stencil_table_create(int numStencils, int numCont
     if (!rc) rc = upload(&t->d_offsets, offsets, (size_t)numStencils);
     if (!rc) rc = upload(&t->d_indices, indices, (size_t)ne);
     for (int k = 0; k < t->numW && !rc; ++k) rc = upload(&t->d_w[k], w[k], (size_t)ne);
-    if (!rc && !(flags & 1) && numStencils > 0) {
+    t->exact = (flags & 64) != 0;
+    if (!rc && !(flags & (1 | 64)) && numStencils > 0) {
         // the two passes over the elements run on the device (the arrays were just uploaded); the locality order of rows, the
         // sort of long rows and bit 5 keep the host builder
         if (flags & (2 | 8 | 32)) rc = build_sell(t, sizes, offsets, indices, w, (flags & 2) != 0, !(flags & 4), (flags & 8) ? 2 : ((flags & 16) ? 0 : 1));
@@ -862,7 +871,7 @@ b200osd_stencil_table *b200osd_stencil_table_create_from_device(int numStencils,
         if (!ok) { set_error("stencil_table_create_from_device: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
     }
     const int nCV = numControlVertices > 0 ? numControlVertices : maxIdx + 1;
-    if (maxIdx >= nCV || (flags & (2 | 8 | 32))) {
+    if (maxIdx >= nCV || ((flags & (2 | 8 | 32)) && !(flags & (1 | 64)))) {
         std::vector<int> hi((size_t)ne);
         std::vector<std::vector<float>> hw(kMaxOut);
         const float *hp[kMaxOut] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };

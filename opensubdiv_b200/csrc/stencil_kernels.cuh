@@ -122,8 +122,20 @@ __device__ __forceinline__ void accumulate(float (&acc)[K][L], const float (&v)[
         for (int c = 0; c < L; ++c) acc[k][c] = fmaf(w[k], v[c], acc[k][c]);
 }
 
+// The arithmetic of the reference's CPU kernels, operation for operation: a rounded product added to the running sum
+// (osd/cpuKernel.cpp:71-240 compiled for x86-64 contracts nothing), in the table's element order.  With it a row is
+// bit-identical to Osd::CpuEvaluator / OmpEvaluator whatever its length -- the fused multiply-add of the fast kernels is the
+// more accurate operation, but two correct fp32 summations of n terms may differ by ~n * 2^-23 of sum|w||x|.
+template <int L, int K>
+__device__ __forceinline__ void accumulate_exact(float (&acc)[K][L], const float (&v)[L], const float (&w)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int c = 0; c < L; ++c) acc[k][c] = __fadd_rn(acc[k][c], __fmul_rn(w[k], v[c]));
+}
+
 // ------------------------------------------------------------------------------------ CSR path --
-template <int L, int K, int SRCMODE>
+template <int L, int K, int SRCMODE, bool EXACT>
 __global__ void __launch_bounds__(128) csr_kernel(StencilIO io, CsrTable t) {
     int row = io.start + blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= io.end) return;
@@ -142,13 +154,14 @@ __global__ void __launch_bounds__(128) csr_kernel(StencilIO io, CsrTable t) {
         for (int k = 0; k < K; ++k) w[k] = t.w[k][off + j];
         float v[L];
         load_vertex<L, SRCMODE>(io.src, io.srcStride, idx, v);
-        accumulate<L, K>(acc, v, w);
+        if (EXACT) accumulate_exact<L, K>(acc, v, w);
+        else accumulate<L, K>(acc, v, w);
     }
     store_row<L, K>(io, row, acc);
 }
 
 // Any primvar length: components are processed in tiles of 4, re-walking the row per tile.
-template <int K>
+template <int K, bool EXACT>
 __global__ void __launch_bounds__(128) csr_kernel_anyL(StencilIO io, CsrTable t) {
     int row = io.start + blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= io.end) return;
@@ -171,7 +184,7 @@ __global__ void __launch_bounds__(128) csr_kernel_anyL(StencilIO io, CsrTable t)
             for (int k = 0; k < K; ++k) {
                 float w = t.w[k][off + j];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[k][c] = fmaf(w, v[c], acc[k][c]);
+                for (int c = 0; c < 4; ++c) acc[k][c] = EXACT ? __fadd_rn(acc[k][c], __fmul_rn(w, v[c])) : fmaf(w, v[c], acc[k][c]);
             }
         }
 #pragma unroll

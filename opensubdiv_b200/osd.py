@@ -155,12 +155,13 @@ class B200StencilTable:
     @classmethod
     def Create(cls, table, deviceContext=None, bucketed: bool = True, locality: bool = False,
                idx16: bool = True, sort_elements: bool = False, keep_order: bool = False,
-               host_layout: bool = False) -> Optional["B200StencilTable"]:
+               host_layout: bool = False, reference_exact: bool = False) -> Optional["B200StencilTable"]:
         """`table` is anything with the Far::StencilTable / LimitStencilTable accessors as numpy arrays:
         sizes, offsets, indices, weights and optionally du, dv, duu, duv, dvv (far/stencilTable.h:156-186,434-456).
         Summation order (include/b200osd_capi.h): default = rows of <= 16 terms in control-index order; keep_order = the
         table's own order everywhere; sort_elements = every row in control-index order.  host_layout = build the bucketed
-        copy on the host instead of on the device (the same bytes)."""
+        copy on the host instead of on the device (the same bytes).  reference_exact = evaluate with the CPU reference's own
+        arithmetic (rounded product, then add, table order): bit-identical to Osd::CpuEvaluator, about half the speed."""
         def arr(name, dt):
             a = getattr(table, name, None)
             return None if a is None else np.ascontiguousarray(a, dtype=dt)
@@ -170,7 +171,7 @@ class B200StencilTable:
         ncv = int(getattr(table, "num_control_verts", 0) or 0)       # Far::StencilTable::GetNumControlVertices(); 0 = derive
         h = capi.lib().b200osd_stencil_table_create(len(sizes), ncv, p(sizes), p(offsets), p(indices), *[p(x) for x in w],
                                                     (0 if bucketed else 1) | (2 if locality else 0) | (0 if idx16 else 4)
-                                                    | (8 if sort_elements else 0) | (16 if keep_order else 0) | (32 if host_layout else 0))
+                                                    | (8 if sort_elements else 0) | (16 if keep_order else 0) | (32 if host_layout else 0) | (64 if reference_exact else 0))
         return cls(h) if h else None
 
     @classmethod

@@ -112,6 +112,35 @@ def test_limit_stencils_with_derivatives(name, nw):
 
 
 @pytest.mark.parametrize("name", golden_names("stencils_") + golden_names("limit_"))
+def test_reference_exact_mode_is_bit_identical_to_the_cpu_evaluator(name):
+    """flag 64 (reference_exact): a rounded product added to the running sum in the table's order, what osd/cpuKernel.cpp
+    does -- the committed outputs of Osd::CpuEvaluator come out bit for bit, for values and all derivative streams, through
+    the table and through a row range."""
+    d = golden(name)
+    t = table_from(d, "t_")
+    n = t.num_stencils
+    nw = 6 if t.dvv is not None else (3 if t.du is not None else 1)
+    src = dev(d["src"])
+    L = d["src"].shape[1]
+    keys = ["out"] if "out" in d.files else ["out_" + k for k in OUT6]
+    tbl = osd.B200StencilTable.Create(t, reference_exact=True)
+    for k in (1, 3, 6):
+        if k > nw or k > len(keys):
+            continue
+        outs = [torch.full((n, L), float("nan"), device="cuda") for _ in range(k)]
+        args = []
+        for o in outs:
+            args += [o, D(0, L, L)]
+        assert osd.B200Evaluator.EvalStencils(src, D(0, L, L), *args, tbl)
+        for q in range(k):
+            assert np.array_equal(outs[q].cpu().numpy().view(np.int32), d[keys[q]].view(np.int32)), (name, keys[q], k)
+    a, b = n // 3, n - n // 4
+    out = torch.zeros((n, L), device="cuda")
+    assert osd.B200Evaluator.EvalStencils(src, D(0, L, L), out, D(0, L, L), tbl, start=a, end=b)
+    assert np.array_equal(out.cpu().numpy()[a:b].view(np.int32), d[keys[0]][a:b].view(np.int32))
+
+
+@pytest.mark.parametrize("name", golden_names("stencils_") + golden_names("limit_"))
 def test_bucketed_layout_built_on_the_device_equals_the_host_builder(name):
     """The bucketed copy is laid out by kernels from the uploaded arrays (sell_extent_kernel / sell_fill_kernel); flag 32
     keeps the host builder.  Same slices, same bytes: evaluations are bit-identical and stream the same number of bytes,
