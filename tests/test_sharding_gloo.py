@@ -103,6 +103,74 @@ def test_sharded_frames_equal_single_table(world, scheme):
         assert ranges[0][0] == 0
 
 
+def _worker_locality(rank, world, port, out_q):
+    """Strong scaling with the locality plan: every frame the root sends rank r ONLY the control-vertex runs r's rows
+    reference (point-to-point, standing in for b200osd_window_pull), every rank applies its own table, the pieces are
+    gathered and put back into table order."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+    mesh = synth.torus_tris(20, 12)
+    table = synth.uniform_stencil_table(mesh, 2)
+    plans = [shard.LocalityPlan.for_table(table, world, r) for r in range(world)]
+    plan = plans[rank]
+    local = shard.local_table_rows(table, plan.rows)
+    all_runs = [shard.control_runs(shard.local_table_rows(table, p.rows), 16, 4) for p in plans]
+    runs = all_runs[rank]
+    ncv, L, n = table.num_control_verts, 3, table.num_stencils
+    results, received = [], 0
+    for frame in range(3):
+        cv = torch.full((ncv, L), float("nan"))              # what this rank knows of the frame's control points
+        if rank == 0:
+            scene = torch.from_numpy(synth.deform(mesh.positions, frame))
+            for r in range(1, world):
+                for lo, hi in all_runs[r]:
+                    dist.send(scene[lo:hi].contiguous(), dst=r)
+            for lo, hi in runs:
+                cv[lo:hi] = scene[lo:hi]
+        else:
+            for lo, hi in runs:
+                piece = torch.empty((hi - lo, L))
+                dist.recv(piece, src=0)
+                cv[lo:hi] = piece
+        received = sum(hi - lo for lo, hi in runs)
+        out = np.zeros((local.num_stencils, L), np.float32)
+        assert oracle.eval_stencils(cv.numpy().reshape(-1), (0, L, L), [out.reshape(-1)], [(0, L, L)], local.sizes, local.offsets,
+                                    local.indices, [local.weights])
+        pieces = [None] * world
+        dist.all_gather_object(pieces, (plan.rows, out))
+        full = np.zeros((n, L), np.float32)
+        for rows, vals in pieces:
+            full[rows] = vals
+        ref = np.zeros((n, L), np.float32)
+        oracle.eval_stencils(synth.deform(mesh.positions, frame).reshape(-1), (0, L, L), [ref.reshape(-1)], [(0, L, L)],
+                             table.sizes, table.offsets, table.indices, [table.weights])
+        results.append(bool(np.array_equal(full, ref)))
+    out_q.put((rank, results, received, ncv))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_locality_sharded_frames_equal_single_table(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_locality, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, results, received, ncv in got:
+        assert results == [True, True, True], (rank, results)
+        assert received < ncv                               # a rank never needs the whole control mesh
+        if world == 4:
+            assert received <= 0.6 * ncv
+
+
 def test_coord_ranges_cover_and_align():
     for n in (0, 1, 31, 32, 1000, 10_000_019):
         for world in (1, 2, 3, 8):
