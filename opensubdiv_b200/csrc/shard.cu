@@ -127,11 +127,14 @@ int b200osd_shard_plan(int numStencils, const int *sizes, int world, int align, 
 
 int b200osd_shard_plan_locality(int numStencils, const int *sizes, const int *offsets, const int *indices, int world,
                                 int *rowOrder, int *ranges, int *controlRanges) {
-    if (numStencils < 0 || world < 1 || !ranges || !controlRanges || (numStencils > 0 && (!sizes || !offsets || !indices || !rowOrder))) {
+    if (numStencils < 0 || world < 1 || !ranges || !controlRanges || (numStencils > 0 && (!sizes || !offsets || !rowOrder))) {
         set_error("shard_plan_locality: bad arguments");
         return B200OSD_ERR_INVALID;
     }
     const int n = numStencils;
+    if (!indices)                                        // legal only for a table without elements
+        for (int i = 0; i < n; ++i)
+            if (sizes[i] > 0) { set_error("shard_plan_locality: indices is NULL"); return B200OSD_ERR_INVALID; }
     // key of a row: the smallest control vertex it references (rows of an empty stencil go first)
     std::vector<int> key((size_t)n, -1);
     int maxKey = -1;
@@ -183,10 +186,13 @@ int b200osd_shard_plan_locality(int numStencils, const int *sizes, const int *of
 
 int b200osd_shard_control_runs(int numStencils, const int *sizes, const int *offsets, const int *indices, int granularity,
                                int maxRuns, int *runs) {
-    if (numStencils < 0 || granularity < 1 || maxRuns < 1 || !runs || (numStencils > 0 && (!sizes || !offsets || !indices))) {
+    if (numStencils < 0 || granularity < 1 || maxRuns < 1 || !runs || (numStencils > 0 && (!sizes || !offsets))) {
         set_error("shard_control_runs: bad arguments");
         return -1;
     }
+    if (!indices)                                        // legal only for a table without elements
+        for (int i = 0; i < numStencils; ++i)
+            if (sizes[i] > 0) { set_error("shard_control_runs: indices is NULL"); return -1; }
     int maxIdx = -1;
     for (int i = 0; i < numStencils; ++i)
         for (int j = 0; j < sizes[i]; ++j) maxIdx = std::max(maxIdx, indices[(size_t)offsets[i] + j]);

@@ -327,3 +327,44 @@ def test_communicator_needs_a_device():
     ident = (C.c_char * 128)()
     assert not capi.lib().b200osd_comm_create(1, 0, ident)
     assert capi.last_error()
+
+
+def test_locality_plan_properties_on_random_tables():
+    """Property test (hypothesis) of the host-side partitioning entries on arbitrary small tables: the order is a stable
+    sort by the smallest referenced vertex, chunks tile the order, bounding intervals and runs cover every reference, runs
+    are sorted, disjoint, at most maxRuns, and never wider than the bounding interval rounded to the granularity."""
+    from hypothesis import given, settings, strategies as hs
+    from opensubdiv_b200 import capi
+
+    @settings(max_examples=60, deadline=None)
+    @given(hs.integers(1, 200), hs.integers(1, 300), hs.integers(1, 6), hs.integers(0, 2 ** 31 - 1), hs.integers(1, 9),
+           hs.integers(1, 64), hs.integers(1, 8))
+    def check(nrows, ncv, maxsize, seed, world, gran, max_runs):
+        rng = np.random.default_rng(seed)
+        sizes = rng.integers(0, maxsize + 1, nrows).astype(np.int32)
+        offsets = np.zeros(nrows, np.int32)
+        offsets[1:] = np.cumsum(sizes[:-1])
+        ne = int(sizes.sum())
+        indices = rng.integers(0, ncv, max(ne, 1)).astype(np.int32)
+        t = synth.SynthStencilTable(ncv, sizes, offsets, indices[:ne], np.ones(ne, np.float32))
+        plans = [shard.LocalityPlan.for_table(t, world, r) for r in range(world)]
+        key = np.array([indices[offsets[i]:offsets[i] + sizes[i]].min() if sizes[i] else -1 for i in range(nrows)])
+        assert np.array_equal(plans[0].row_order, np.argsort(key, kind="stable"))
+        assert plans[0].ranges[0][0] == 0 and plans[0].ranges[-1][1] == nrows
+        assert all(plans[0].ranges[i][1] == plans[0].ranges[i + 1][0] for i in range(world - 1))
+        for p in plans:
+            lt = shard.local_table_rows(t, p.rows)
+            if lt.num_elements:
+                assert p.ctrl_lo == lt.indices.min() and p.ctrl_hi == lt.indices.max() + 1
+            runs = shard.control_runs(lt, gran, max_runs)
+            assert len(runs) <= max_runs
+            assert all(a < b for a, b in runs) and all(runs[i][1] <= runs[i + 1][0] for i in range(len(runs) - 1))
+            covered = np.zeros(ncv + gran, bool)
+            for a, b in runs:
+                covered[a:b] = True
+            assert covered[lt.indices].all()
+            if lt.num_elements:
+                assert runs[0][0] >= (p.ctrl_lo // gran) * gran and runs[-1][1] <= p.ctrl_hi
+            else:
+                assert runs == []
+    check()
