@@ -432,3 +432,31 @@ def test_one_table_two_threads_two_streams():
     assert not errs, errs
     for k in (0, 1):
         assert torch.equal(got[k], want[k])
+
+
+@pytest.mark.parametrize("ptype", [3, 4, 5, 6, 9, 10])
+def test_every_boundary_mask_depth_rotation_on_the_gpu(ptype):
+    """The synthetic PatchParam sweep of tests/test_kernel_math_emu.py (all 32 Loop / 16 B-spline boundary masks, depths
+    0..6, rotated triangles, corner and edge samples) through the real kernels in every serving mode, against the oracle."""
+    from tests.test_kernel_math_emu import synthetic_patch_sweep
+    tr, coords, vb = synthetic_patch_sweep(ptype)
+    n = len(coords)
+    exp = oracle_patches(vb, (0, 3, 3), 3, coords, tr, 6)
+    scl = oracle_patches(vb, (0, 3, 3), 3, coords, tr, 6, abs_scale=True)
+    pt = osd.B200PatchTable.Create(_PT(tr))
+    pc, src = coords_dev(coords), dev(vb)
+    first = None
+    for variant in (1, 2, 3):
+        pt.SetVariant(variant)
+        out = torch.full((n, 18), float("nan"), device="cuda")
+        args = []
+        for k in range(6):
+            args += [out, D(3 * k, 3, 18)]
+        assert osd.B200Evaluator.EvalPatches(src, D(0, 3, 3), *args, n, pc, pt, None)
+        res = out.cpu().numpy()
+        if first is None:
+            first = res
+            for k in range(6):
+                assert_close(res[:, 3 * k:3 * k + 3], exp[k], scl[k], f"type {ptype} {OUT6[k]}")
+        else:
+            assert np.array_equal(res, first), f"type {ptype}: variant {variant} differs bitwise"

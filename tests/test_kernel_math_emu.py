@@ -124,3 +124,62 @@ def test_patch_kernel_math_on_every_regression_shape(shape):
     got = emu_patches(L, vb.reshape(-1), (0, 3, 3), 3, pc, pt.vertex, 6)
     for kk in range(6):
         assert_close(got[kk], x[kk], z[kk], f"{shape} {OUT6[kk]}")
+
+
+def synthetic_patch_sweep(ptype):
+    """One synthetic patch per (type, boundary mask, depth, sub-patch, rotation) with a sample each, incl. corners and
+    edges: (triple, coords, vertex buffer).  Shared with tests/test_gpu_patches.py."""
+    from oracle.ref import PATCH_ARRAY_DTYPE, PATCH_PARAM_DTYPE, PATCH_COORD_DTYPE
+    from types import SimpleNamespace
+    npts = {3: 4, 4: 3, 5: 12, 6: 16, 9: 20, 10: 18}[ptype]
+    tri = ptype in (4, 5, 10)
+    rng = np.random.default_rng(100 + ptype)
+    masks = range(32) if ptype == 5 else (range(16) if ptype == 6 else [0])
+    params, coords = [], []
+    for mask in masks:
+        for trial in range(40):
+            depth = int(rng.integers(0, 7))
+            nonquad = int(rng.integers(0, 2)) if depth > 0 else 0
+            n = 1 << (depth - nonquad)
+            u, v = int(rng.integers(0, n)), int(rng.integers(0, n))
+            a, b = rng.random(2)
+            if tri and a + b > 1:
+                a, b = 1 - a, 1 - b
+            if trial % 7 == 0:
+                a = 0.0
+            if trial % 11 == 0:
+                b = 0.0
+            if trial % 13 == 0:
+                a, b = (1.0, 0.0) if tri else (1.0, 1.0)
+            if tri and (u + v) >= (1 << depth):
+                s, t = ((1 << depth) - u - a) / n, ((1 << depth) - v - b) / n
+            else:
+                s, t = (u + a) / n, (v + b) / n
+            f1 = depth | (nonquad << 4) | (1 << 5) | (mask << 7) | (v << 12) | (u << 22)
+            coords.append((0, len(params), 0, np.float32(s), np.float32(t)))
+            params.append((0, f1, 0.0))
+    P = len(params)
+    tr = SimpleNamespace(arrays=np.array([(ptype, ptype, P, 0, npts, 0)], PATCH_ARRAY_DTYPE),
+                         indices=(np.arange(P * npts, dtype=np.int32) % (npts * 7)).astype(np.int32),
+                         params=np.array(params, PATCH_PARAM_DTYPE))
+    pc = np.array(coords, PATCH_COORD_DTYPE)
+    vb = rng.standard_normal((npts * 7, 3)).astype(np.float32)
+    return tr, pc, vb
+
+
+@pytest.mark.parametrize("ptype", [3, 4, 5, 6, 9, 10])
+def test_patch_kernel_math_every_boundary_mask_depth_rotation(ptype):
+    """The kernel's arithmetic against the oracle (itself bit-pinned to OsdEvaluatePatchBasis,
+    tests/test_oracle_vs_reference.py) for PatchParam combinations that real tables rarely contain -- all 32 Loop masks, all
+    16 B-spline masks, depths 0..6, rotated triangles, non-quad roots, samples on patch corners and edges."""
+    L = _lib()
+    tr, pc, vb = synthetic_patch_sweep(ptype)
+    P = len(pc)
+    exp = [np.zeros((P, 3), np.float32) for _ in range(6)]
+    scl = [np.zeros((P, 3), np.float32) for _ in range(6)]
+    assert oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in exp], [(0, 3, 3)] * 6, pc, tr.arrays, tr.indices, tr.params)
+    with oracle.abs_mode(2):
+        oracle.eval_patches(vb.reshape(-1), (0, 3, 3), [o.reshape(-1) for o in scl], [(0, 3, 3)] * 6, pc, tr.arrays, tr.indices, tr.params)
+    got = emu_patches(L, vb.reshape(-1), (0, 3, 3), 3, pc, tr, 6)
+    for k in range(6):
+        assert_close(got[k], exp[k], scl[k], f"type {ptype} {OUT6[k]}")
