@@ -142,7 +142,10 @@ def build_workload():
 def shared_config(table, order):
     """`config` is the same object in both arms (the driver compares them)."""
     return {"workload": WORKLOAD, "rows": int(table.num_stencils), "elements": int(table.num_elements),
-            "control_verts": int(table.num_control_verts), "primvar_floats": L, "table_order": order}
+            "control_verts": int(table.num_control_verts), "primvar_floats": L, "table_order": order,
+            # timing rule: no L2 flush between steps because a step's inputs do not fit the 126 MB L2 -- the table alone is
+            # 0.67 GB in the reference layout (0.55 GB as streamed by the bucketed kernel), the refined output 154 MB
+            "l2_policy": "inputs larger than L2 (table >= 0.55 GB per step vs 126 MB L2): no flush between steps"}
 
 
 def frame_primvars(mesh, frame):

@@ -36,7 +36,8 @@ def test_reference_arm_prints_one_contract_line():
     # the same `config` as the B200 arm builds (bench.shared_config is the single source of both)
     sys.path.insert(0, ROOT)
     import bench
-    assert set(cfg) == {"workload", "rows", "elements", "control_verts", "primvar_floats", "table_order"}
+    assert set(cfg) == {"workload", "rows", "elements", "control_verts", "primvar_floats", "table_order", "l2_policy"}
+    assert "larger than L2" in cfg["l2_policy"]
     assert callable(bench.shared_config)
 
 
